@@ -1,0 +1,520 @@
+// The one tensor-core kernel of the contrastive-divergence engine.
+//
+// Every dense contraction on the CD-k hot path of ku/ebm/rbm.py is an instance
+// of   D(M,N) = sum_s  sign_s * A_s(M,K) * B_s(K,N)   followed by an elementwise
+// epilogue, with bf16 operands and fp32 accumulation:
+//
+//   v.W + c   -> sigmoid -> Bernoulli h     (rbm.py:46-47, 120, 124)   A K-major,  B MN-major
+//   h.W^T + b -> sigmoid -> Bernoulli v'    (rbm.py:52-53, 121-123)    A K-major,  B K-major
+//   v0^T h0 - vk^T hk  = delta W            (rbm.py:125-126)           A MN-major, B MN-major,
+//                                                                     two K-segments, 2nd negated
+//   sum_j softplus(v.W + c)_j               (rbm.py:73-75)             free-energy epilogue
+//
+// so W is kept once, row-major (V,H), and no state matrix is ever transposed:
+// operand major-ness is expressed in the UMMA shared-memory descriptors.  The
+// "segments" are K-concatenations that accumulate into the same TMEM tile: they
+// carry the positive/negative phases of delta W (negate-A bit of the
+// instruction descriptor) and, in f32x3 mode, the bf16 hi/mid/lo splits of
+// fp32 operands.
+//
+// Structure (one CTA per SM, persistent over output tiles):
+//   warp 0      TMA producer   global -> 128B-swizzled smem ring (STAGES deep)
+//   warp 1      MMA issuer     one thread, tcgen05.mma cta_group::1, M=128, N=BN
+//   warps 2..9  epilogue       tcgen05.ld TMEM -> registers -> fused math -> global
+// The fp32 accumulator is double-buffered in TMEM (2 x BN columns) so the
+// epilogue of tile i overlaps the MMAs of tile i+1.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cstdint>
+
+#include "ptx.cuh"
+#include "rng_math.cuh"
+
+namespace kucd {
+
+constexpr int kMaxSeg = 8;
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;  // 64 bf16 = one 128-byte swizzle row
+constexpr int kNumEpiWarps = 8;
+constexpr int kNumThreads = 64 + 32 * kNumEpiWarps;
+
+enum EpiMode : int {
+  kEpiRaw = 0,     // out_f32 = D
+  kEpiSample = 1,  // s = 1[u < sigmoid(D + bias)]  -> out_bf16 (0/1); optional p -> out_f32; optional colsum
+  kEpiProb = 2,    // p = sigmoid(D + bias)         -> out_bf16 (+ mid/lo splits), optional out_f32, colsum
+  kEpiFreeEnergy = 3,  // rowsum[m] += sum_n softplus(D + bias)
+  kEpiReluSample = 4,  // s = 1[u < relu(D + bias)]   (Gaussian-visible mode, rbm.py:58-59)
+  kEpiGaussian = 5,    // x = D + bias + N(0,1)       (Gaussian-visible mode, rbm.py:64-66) -> out_bf16 splits + out_f32
+};
+
+struct alignas(64) GemmParams {
+  CUtensorMap tm_a[kMaxSeg];
+  CUtensorMap tm_b[kMaxSeg];
+  int32_t num_seg;
+  uint32_t neg_mask;  // bit s: segment s enters with a minus sign
+  int32_t M, N;
+  int32_t kblocks;  // ceil(K / 64) per segment
+  int32_t pad0;
+  // ---- epilogue ----
+  const float* bias;       // readable up to ceil(N/BN)*BN entries
+  __nv_bfloat16* out_bf16;  // (M, ld_bf16), ld multiple of 8, >= round_up(N, 8)
+  __nv_bfloat16* out_mid;   // optional bf16 split parts of a real-valued output (f32x3 mode)
+  __nv_bfloat16* out_lo;
+  int64_t ld_bf16;
+  float* out_f32;  // (M, ld_f32), ld multiple of 4
+  int64_t ld_f32;
+  const float* u_inject;  // optional injected uniforms (M, ld_u): parity mode
+  int64_t ld_u;
+  float* colsum;  // optional (N): += column sums of the stored output
+  float* rowsum;  // free energy accumulator (M)
+  uint64_t seed;
+  uint64_t draw;  // draw id: distinct for every sampling launch
+  int64_t row0;   // global row index of local row 0 (data-parallel shards sample identically)
+  // ---- descriptor overrides used only by the bring-up probe (0 = default) ----
+  uint32_t dbg_lbo_a, dbg_sbo_a, dbg_adv_a, dbg_lbo_b, dbg_sbo_b, dbg_adv_b;
+};
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int kABytes = kBlockM * kBlockK * 2;
+  static constexpr int kBBytes = BN * kBlockK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kCtrlBytes = 1024;
+  static constexpr int kSmemLimit = 232448 - 1024;  // 227 KB minus alignment slack
+  static constexpr int kStagesRaw = (kSmemLimit - kCtrlBytes) / kStageBytes;
+  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kCtrlBytes + 1024;
+  static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
+};
+
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= 1ull << 46;  // descriptor version (Blackwell)
+  d |= 2ull << 61;  // SWIZZLE_128B
+  return d;
+}
+
+// kind::f16 instruction descriptor: bf16 x bf16 -> fp32, M=128, N=BN.
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool a_mn, bool b_mn, bool negate_a) {
+  return (1u << 4)                       // D format: f32
+         | (1u << 7)                     // A format: bf16
+         | (1u << 10)                    // B format: bf16
+         | ((negate_a ? 1u : 0u) << 13)  // -A
+         | ((a_mn ? 1u : 0u) << 15)      // A major: 0 = K, 1 = MN
+         | ((b_mn ? 1u : 0u) << 16)      // B major
+         | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// lane L ends up holding sum over the warp's 32 lanes of v[L] (31 shuffles).
+__device__ __forceinline__ float warp_transpose_reduce(float (&v)[32], uint32_t lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int i = 0; i < s; ++i) {
+      const float send = up ? v[i] : v[i + s];
+      const float keep = up ? v[i + s] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+  return v[0];
+}
+
+// Box-Muller on two lattice uniforms (u1 shifted off zero).
+__device__ __forceinline__ void box_muller(uint32_t b0, uint32_t b1, float& n0, float& n1) {
+  const float u1 = (static_cast<float>(b0 >> 9) + 0.5f) * 1.1920928955078125e-07f;
+  const float u2 = u01_from_bits(b1);
+  const float r = sqrtf(-2.0f * __logf(u1));
+  float s, c;
+  __sincosf(6.283185307179586f * u2, &s, &c);
+  n0 = r * c;
+  n1 = r * s;
+}
+
+// One 32-column chunk of one output row (this thread's TMEM lane).
+template <int EPI>
+__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32_t (&acc)[32], int row, int col0,
+                                               bool row_ok, uint32_t lane, float& row_acc) {
+  if (col0 >= p.N) return;  // warp-uniform
+
+  if constexpr (EPI == kEpiRaw) {
+    if (row_ok) {
+      float* dst = p.out_f32 + static_cast<int64_t>(row) * p.ld_f32 + col0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        if (col0 + 4 * q < p.N) {
+          float4 v = make_float4(__uint_as_float(acc[4 * q]), __uint_as_float(acc[4 * q + 1]),
+                                 __uint_as_float(acc[4 * q + 2]), __uint_as_float(acc[4 * q + 3]));
+          if (col0 + 4 * q + 1 >= p.N) v.y = 0.f;
+          if (col0 + 4 * q + 2 >= p.N) v.z = 0.f;
+          if (col0 + 4 * q + 3 >= p.N) v.w = 0.f;
+          *reinterpret_cast<float4*>(dst + 4 * q) = v;
+        }
+      }
+    }
+    return;
+  }
+
+  // pre-activation x = D + bias (bias is broadcast down the rows)
+  float x[32];
+  {
+    const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 b = __ldg(b4 + q);
+      x[4 * q + 0] = __uint_as_float(acc[4 * q + 0]) + b.x;
+      x[4 * q + 1] = __uint_as_float(acc[4 * q + 1]) + b.y;
+      x[4 * q + 2] = __uint_as_float(acc[4 * q + 2]) + b.z;
+      x[4 * q + 3] = __uint_as_float(acc[4 * q + 3]) + b.w;
+    }
+  }
+
+  if constexpr (EPI == kEpiFreeEnergy) {
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) s += (col0 + j < p.N) ? softplus_f32(x[j]) : 0.f;
+    row_acc += s;
+    return;
+  }
+
+  if constexpr (EPI == kEpiSample || EPI == kEpiReluSample) {
+    // probabilities
+#pragma unroll
+    for (int j = 0; j < 32; ++j) x[j] = (EPI == kEpiSample) ? sigmoid_f32(x[j]) : fmaxf(x[j], 0.f);
+    if (p.out_f32 != nullptr && row_ok) {
+      float* dst = p.out_f32 + static_cast<int64_t>(row) * p.ld_f32 + col0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        if (col0 + 4 * q < p.N)
+          *reinterpret_cast<float4*>(dst + 4 * q) = make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
+    }
+    // uniforms and threshold: bit j of `bits` = sampled state of column col0 + j
+    uint32_t bits = 0;
+    if (p.u_inject != nullptr) {
+      if (row_ok) {
+        const float* up = p.u_inject + static_cast<int64_t>(row) * p.ld_u + col0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float u = (col0 + j < p.N) ? __ldg(up + j) : 2.0f;
+          bits |= (u < x[j] ? 1u : 0u) << j;
+        }
+      }
+    } else {
+      const uint32_t grow = static_cast<uint32_t>(p.row0 + row);
+      const uint32_t k0 = static_cast<uint32_t>(p.seed), k1 = static_cast<uint32_t>(p.seed >> 32);
+      const uint32_t d0 = static_cast<uint32_t>(p.draw), d1 = static_cast<uint32_t>(p.draw >> 32);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const Philox4 r = philox4x32_10(static_cast<uint32_t>((col0 >> 2) + q), grow, d0, d1, k0, k1);
+        bits |= (u01_from_bits(r.x) < x[4 * q + 0] ? 1u : 0u) << (4 * q + 0);
+        bits |= (u01_from_bits(r.y) < x[4 * q + 1] ? 1u : 0u) << (4 * q + 1);
+        bits |= (u01_from_bits(r.z) < x[4 * q + 2] ? 1u : 0u) << (4 * q + 2);
+        bits |= (u01_from_bits(r.w) < x[4 * q + 3] ? 1u : 0u) << (4 * q + 3);
+      }
+      const int ncol = p.N - col0;  // > 0
+      if (ncol < 32) bits &= (1u << ncol) - 1u;
+      if (!row_ok) bits = 0;
+    }
+    if (row_ok) {
+      uint4* dst = reinterpret_cast<uint4*>(p.out_bf16 + static_cast<int64_t>(row) * p.ld_bf16 + col0);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (col0 + 8 * q < p.N) {
+          const uint32_t b = bits >> (8 * q);
+          uint4 v;  // bf16 1.0 = 0x3F80
+          v.x = ((b & 1u) ? 0x3F80u : 0u) | ((b & 2u) ? 0x3F800000u : 0u);
+          v.y = ((b & 4u) ? 0x3F80u : 0u) | ((b & 8u) ? 0x3F800000u : 0u);
+          v.z = ((b & 16u) ? 0x3F80u : 0u) | ((b & 32u) ? 0x3F800000u : 0u);
+          v.w = ((b & 64u) ? 0x3F80u : 0u) | ((b & 128u) ? 0x3F800000u : 0u);
+          dst[q] = v;
+        }
+      }
+    }
+    if (p.colsum != nullptr) {
+      // column sums of the 0/1 states over this warp's 32 rows: one ballot per column
+      uint32_t mine = 0;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const uint32_t b = __ballot_sync(0xffffffffu, (bits >> j) & 1u);
+        if (lane == static_cast<uint32_t>(j)) mine = b;
+      }
+      const int cnt = __popc(mine);
+      if (cnt != 0 && col0 + static_cast<int>(lane) < p.N)
+        atomicAdd(p.colsum + col0 + lane, static_cast<float>(cnt));
+    }
+    return;
+  }
+
+  if constexpr (EPI == kEpiProb || EPI == kEpiGaussian) {
+    if constexpr (EPI == kEpiProb) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) x[j] = sigmoid_f32(x[j]);
+    } else {
+      const uint32_t grow = static_cast<uint32_t>(p.row0 + row);
+      const uint32_t k0 = static_cast<uint32_t>(p.seed), k1 = static_cast<uint32_t>(p.seed >> 32);
+      const uint32_t d0 = static_cast<uint32_t>(p.draw), d1 = static_cast<uint32_t>(p.draw >> 32);
+      if (p.u_inject != nullptr) {  // injected standard normals
+        if (row_ok) {
+          const float* up = p.u_inject + static_cast<int64_t>(row) * p.ld_u + col0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[j] += (col0 + j < p.N) ? __ldg(up + j) : 0.f;
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const Philox4 r = philox4x32_10(static_cast<uint32_t>((col0 >> 2) + q), grow, d0, d1, k0, k1);
+          float n0, n1, n2, n3;
+          box_muller(r.x, r.y, n0, n1);
+          box_muller(r.z, r.w, n2, n3);
+          x[4 * q + 0] += n0;
+          x[4 * q + 1] += n1;
+          x[4 * q + 2] += n2;
+          x[4 * q + 3] += n3;
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (col0 + j >= p.N || !row_ok) x[j] = 0.f;
+    if (row_ok) {
+      if (p.out_f32 != nullptr) {
+        float* dst = p.out_f32 + static_cast<int64_t>(row) * p.ld_f32 + col0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          if (col0 + 4 * q < p.N)
+            *reinterpret_cast<float4*>(dst + 4 * q) = make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
+      }
+      // bf16 hi (+ optional mid, lo) parts: x = hi + mid + lo to ~2^-24
+      float r1[32];
+      {
+        uint4* dst = reinterpret_cast<uint4*>(p.out_bf16 + static_cast<int64_t>(row) * p.ld_bf16 + col0);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint32_t w[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float a = x[8 * q + 2 * e], b = x[8 * q + 2 * e + 1];
+            const __nv_bfloat16 ha = __float2bfloat16_rn(a), hb = __float2bfloat16_rn(b);
+            r1[8 * q + 2 * e] = a - __bfloat162float(ha);
+            r1[8 * q + 2 * e + 1] = b - __bfloat162float(hb);
+            w[e] = static_cast<uint32_t>(__bfloat16_as_ushort(ha)) |
+                   (static_cast<uint32_t>(__bfloat16_as_ushort(hb)) << 16);
+          }
+          if (col0 + 8 * q < p.N) dst[q] = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+      }
+      if (p.out_mid != nullptr) {
+        uint4* dm = reinterpret_cast<uint4*>(p.out_mid + static_cast<int64_t>(row) * p.ld_bf16 + col0);
+        uint4* dl = reinterpret_cast<uint4*>(p.out_lo + static_cast<int64_t>(row) * p.ld_bf16 + col0);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint32_t wm[4], wl[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float a = r1[8 * q + 2 * e], b = r1[8 * q + 2 * e + 1];
+            const __nv_bfloat16 ma = __float2bfloat16_rn(a), mb = __float2bfloat16_rn(b);
+            const __nv_bfloat16 la = __float2bfloat16_rn(a - __bfloat162float(ma));
+            const __nv_bfloat16 lb = __float2bfloat16_rn(b - __bfloat162float(mb));
+            wm[e] = static_cast<uint32_t>(__bfloat16_as_ushort(ma)) |
+                    (static_cast<uint32_t>(__bfloat16_as_ushort(mb)) << 16);
+            wl[e] = static_cast<uint32_t>(__bfloat16_as_ushort(la)) |
+                    (static_cast<uint32_t>(__bfloat16_as_ushort(lb)) << 16);
+          }
+          if (col0 + 8 * q < p.N) {
+            dm[q] = make_uint4(wm[0], wm[1], wm[2], wm[3]);
+            dl[q] = make_uint4(wl[0], wl[1], wl[2], wl[3]);
+          }
+        }
+      }
+    }
+    if (p.colsum != nullptr) {
+      const float s = warp_transpose_reduce(x, lane);
+      if (col0 + static_cast<int>(lane) < p.N) atomicAdd(p.colsum + col0 + lane, s);
+    }
+    return;
+  }
+}
+
+template <int BN, bool A_MN, bool B_MN, int EPI>
+__global__ void __launch_bounds__(kNumThreads, 1) gemm_bf16_kernel(const __grid_constant__ GemmParams p) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int kStages = Cfg::kStages;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* ctrl = smem + kStages * Cfg::kStageBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(ctrl);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full_bar = empty_bar + kStages;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const uint32_t warp = threadIdx.x >> 5;
+  const uint32_t lane = ptx::lane_id();
+
+  const int num_m = (p.M + kBlockM - 1) / kBlockM;
+  const int num_n = (p.N + BN - 1) / BN;
+  const int num_tiles = num_m * num_n;
+  const int kb_total = p.num_seg * p.kblocks;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.num_seg; ++s) {
+      ptx::prefetch_tensormap(&p.tm_a[s]);
+      ptx::prefetch_tensormap(&p.tm_b[s]);
+    }
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < kStages; ++s) {
+        ptx::mbar_init(&full_bar[s], 1);
+        ptx::mbar_init(&empty_bar[s], 1);
+      }
+      for (int s = 0; s < 2; ++s) {
+        ptx::mbar_init(&tmem_full_bar[s], 1);
+        ptx::mbar_init(&tmem_empty_bar[s], kNumEpiWarps);
+      }
+      ptx::fence_mbar_init();
+    }
+    __syncwarp();
+    ptx::tmem_alloc<1>(tmem_slot, Cfg::kTmemCols);
+    ptx::tmem_relinquish<1>();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ======================= TMA producer =======================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / num_n, n_blk = tile % num_n;
+        const int m0 = m_blk * kBlockM, n0 = n_blk * BN;
+        for (int s = 0; s < p.num_seg; ++s) {
+          for (int kb = 0; kb < p.kblocks; ++kb) {
+            ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
+            ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+            uint8_t* sa = smem + stage * Cfg::kStageBytes;
+            uint8_t* sb = sa + Cfg::kABytes;
+            const int k0 = kb * kBlockK;
+            if constexpr (!A_MN) {
+              ptx::tma_load_2d(sa, &p.tm_a[s], &full_bar[stage], k0, m0);  // box {64 k, 128 m}
+            } else {
+#pragma unroll
+              for (int j = 0; j < kBlockM / 64; ++j)  // boxes {64 m, 64 k}
+                ptx::tma_load_2d(sa + j * (kBlockK * 128), &p.tm_a[s], &full_bar[stage], m0 + 64 * j, k0);
+            }
+            if constexpr (!B_MN) {
+              ptx::tma_load_2d(sb, &p.tm_b[s], &full_bar[stage], k0, n0);  // box {64 k, BN n}
+            } else {
+#pragma unroll
+              for (int j = 0; j < BN / 64; ++j)  // boxes {64 n, 64 k}
+                ptx::tma_load_2d(sb + j * (kBlockK * 128), &p.tm_b[s], &full_bar[stage], n0 + 64 * j, k0);
+            }
+            if (++stage == kStages) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ======================= MMA issuer =======================
+    if (lane == 0) {
+      // K-major, 128B swizzle : rows of 128 B, 8-row groups 1024 B apart (SBO); a K=16 slice is 32 B along the row.
+      // MN-major, 128B swizzle: 64-element MN chunks kBlockK*128 B apart (LBO); 8-k groups 1024 B apart (SBO);
+      //                         a K=16 slice is two 8-k groups = 2048 B.
+      const uint32_t lbo_a = p.dbg_lbo_a ? p.dbg_lbo_a : (A_MN ? kBlockK * 128u : 16u);
+      const uint32_t sbo_a = p.dbg_sbo_a ? p.dbg_sbo_a : 1024u;
+      const uint32_t adv_a = p.dbg_adv_a ? p.dbg_adv_a : (A_MN ? 2048u : 32u);
+      const uint32_t lbo_b = p.dbg_lbo_b ? p.dbg_lbo_b : (B_MN ? kBlockK * 128u : 16u);
+      const uint32_t sbo_b = p.dbg_sbo_b ? p.dbg_sbo_b : 1024u;
+      const uint32_t adv_b = p.dbg_adv_b ? p.dbg_adv_b : (B_MN ? 2048u : 32u);
+      constexpr uint32_t idesc_pos = make_idesc(kBlockM, BN, A_MN, B_MN, false);
+      constexpr uint32_t idesc_neg = make_idesc(kBlockM, BN, A_MN, B_MN, true);
+
+      uint32_t stage = 0, phase = 0;
+      uint32_t local = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+        const uint32_t as = local & 1u, aphase = (local >> 1) & 1u;
+        ptx::mbar_wait(&tmem_empty_bar[as], aphase ^ 1u);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        int it = 0;
+        for (int s = 0; s < p.num_seg; ++s) {
+          const uint32_t idesc = ((p.neg_mask >> s) & 1u) ? idesc_neg : idesc_pos;
+          for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
+            ptx::mbar_wait(&full_bar[stage], phase);
+            ptx::tc_fence_after();
+            const uint32_t sa = ptx::smem_u32(smem + stage * Cfg::kStageBytes);
+            const uint32_t sb = sa + Cfg::kABytes;
+            const uint64_t da = make_smem_desc(sa, lbo_a, sbo_a);
+            const uint64_t db = make_smem_desc(sb, lbo_b, sbo_b);
+#pragma unroll
+            for (int k = 0; k < kBlockK / 16; ++k) {
+              ptx::mma_bf16<1>(d_tmem, da + ((k * adv_a) >> 4), db + ((k * adv_b) >> 4), idesc,
+                               (it > 0 || k > 0) ? 1u : 0u);
+            }
+            ptx::mma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+            if (++stage == kStages) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+        }
+        ptx::mma_commit(&tmem_full_bar[as]);  // accumulator complete
+        (void)kb_total;
+      }
+    }
+  } else {
+    // ======================= epilogue =======================
+    const uint32_t ew = warp - 2;
+    const uint32_t quarter = warp & 3u;  // TMEM lane quarter this warp may access
+    const uint32_t half = ew >> 2;       // which half of the tile's columns
+    constexpr int kColsPerWarp = BN / 2;
+    uint32_t local = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+      const uint32_t as = local & 1u, aphase = (local >> 1) & 1u;
+      const int m_blk = tile / num_n, n_blk = tile % num_n;
+      const int row = m_blk * kBlockM + quarter * 32 + lane;
+      const bool row_ok = row < p.M;
+      ptx::mbar_wait(&tmem_full_bar[as], aphase);
+      ptx::tc_fence_after();
+      float row_acc = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < kColsPerWarp; c += 32) {
+        const int coff = half * kColsPerWarp + c;
+        uint32_t acc[32];
+        ptx::tmem_ld_32x32(tmem_base + ((quarter * 32u) << 16) + as * BN + coff, acc);
+        ptx::tmem_ld_wait();
+        epilogue_chunk<EPI>(p, acc, row, n_blk * BN + coff, row_ok, lane, row_acc);
+      }
+      if constexpr (EPI == kEpiFreeEnergy) {
+        if (row_ok) atomicAdd(p.rowsum + row, row_acc);
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[as]);
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<1>(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+}  // namespace kucd

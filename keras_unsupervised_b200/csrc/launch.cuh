@@ -1,0 +1,176 @@
+// Host side of gemm.cuh: TMA tensor maps and the launch dispatcher.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "gemm.cuh"
+
+namespace kucd {
+
+// A bf16 matrix in device memory as the engine lays it out: row-major (rows, cols),
+// leading dimension `ld` elements (multiple of 64 so every row is 128-byte aligned).
+struct MatView {
+  const void* ptr = nullptr;
+  int64_t rows = 0, cols = 0, ld = 0;
+};
+
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn get_encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  return fn;
+}
+
+// Tensor map over a row-major bf16 matrix with a {64 x box_rows} box and 128B swizzle.
+// Out-of-bounds elements read as zero, which is what makes ragged M/N/K tails exact.
+inline bool make_tmap_bf16(CUtensorMap* tm, const MatView& m, uint32_t box_rows, std::string* err) {
+  EncodeTiledFn enc = get_encode_tiled();
+  if (enc == nullptr) {
+    if (err) *err = "cuTensorMapEncodeTiled unavailable";
+    return false;
+  }
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(m.cols), static_cast<cuuint64_t>(m.rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(m.ld) * 2};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(m.ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    if (err) {
+      char buf[256];
+      snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed (%d): ptr=%p rows=%lld cols=%lld ld=%lld box_rows=%u",
+               static_cast<int>(r), m.ptr, (long long)m.rows, (long long)m.cols, (long long)m.ld, box_rows);
+      *err = buf;
+    }
+    return false;
+  }
+  return true;
+}
+
+// One K-segment of a contraction.  `a_mn` / `b_mn` say how the operand sits in memory:
+//   A K-major : a = (M, K) row-major        A MN-major: a = (K, M) row-major
+//   B K-major : b = (N, K) row-major        B MN-major: b = (K, N) row-major
+struct GemmOperands {
+  MatView a[kMaxSeg], b[kMaxSeg];
+  int num_seg = 1;
+  uint32_t neg_mask = 0;
+  bool a_mn = false, b_mn = false;
+  int64_t M = 0, N = 0, K = 0;
+};
+
+inline int pick_bn(int64_t M, int64_t N, int num_sms) {
+  // Prefer the widest tile that still gives every SM a tile; small problems take narrower tiles.
+  const int64_t m_tiles = (M + kBlockM - 1) / kBlockM;
+  for (int bn : {256, 128}) {
+    if (m_tiles * ((N + bn - 1) / bn) >= num_sms) return bn;
+  }
+  return 64;
+}
+
+template <int BN, bool A_MN, bool B_MN, int EPI>
+inline cudaError_t launch_one(const GemmParams& p, int num_sms, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, EPI>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  const int num_tiles = ((p.M + kBlockM - 1) / kBlockM) * ((p.N + BN - 1) / BN);
+  const int grid = num_tiles < num_sms ? num_tiles : num_sms;
+  if (grid <= 0) return cudaSuccess;
+  kern<<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(p);
+  return cudaGetLastError();
+}
+
+// Operand-major combinations the engine instantiates per epilogue (keeps the fatbin small):
+//   forward  v.W   : A K-major, B MN-major      backward h.W^T : A K-major, B K-major
+//   delta W        : A MN-major, B MN-major     (raw epilogue also builds the 4th combo for the probe)
+template <int EPI, bool A_MN, bool B_MN>
+constexpr bool combo_built() {
+  if (EPI == kEpiRaw) return true;
+  if (A_MN) return false;
+  if (EPI == kEpiFreeEnergy || EPI == kEpiReluSample) return B_MN;
+  if (EPI == kEpiGaussian) return !B_MN;
+  return true;  // sample / prob: both directions
+}
+
+template <int BN, bool A_MN, bool B_MN, int EPI>
+inline cudaError_t launch_if_built(const GemmParams& p, int num_sms, cudaStream_t s) {
+  if constexpr (combo_built<EPI, A_MN, B_MN>())
+    return launch_one<BN, A_MN, B_MN, EPI>(p, num_sms, s);
+  else
+    return cudaErrorInvalidValue;
+}
+
+template <int BN, int EPI>
+inline cudaError_t launch_major(const GemmParams& p, bool a_mn, bool b_mn, int num_sms, cudaStream_t s) {
+  if (!a_mn && !b_mn) return launch_if_built<BN, false, false, EPI>(p, num_sms, s);
+  if (!a_mn && b_mn) return launch_if_built<BN, false, true, EPI>(p, num_sms, s);
+  if (a_mn && b_mn) return launch_if_built<BN, true, true, EPI>(p, num_sms, s);
+  return launch_if_built<BN, true, false, EPI>(p, num_sms, s);
+}
+
+template <int EPI>
+inline cudaError_t launch_bn(const GemmParams& p, int bn, bool a_mn, bool b_mn, int num_sms, cudaStream_t s) {
+  switch (bn) {
+    case 256: return launch_major<256, EPI>(p, a_mn, b_mn, num_sms, s);
+    case 128: return launch_major<128, EPI>(p, a_mn, b_mn, num_sms, s);
+    default: return launch_major<64, EPI>(p, a_mn, b_mn, num_sms, s);
+  }
+}
+
+// Fill the tensor maps / shape fields of `p` from `ops` (epilogue fields are the caller's) and launch.
+inline bool launch_gemm(GemmParams& p, const GemmOperands& ops, int epi, int num_sms, cudaStream_t stream,
+                        std::string* err, int force_bn = 0) {
+  if (ops.num_seg < 1 || ops.num_seg > kMaxSeg) {
+    if (err) *err = "bad segment count";
+    return false;
+  }
+  const int bn = force_bn ? force_bn : pick_bn(ops.M, ops.N, num_sms);
+  p.num_seg = ops.num_seg;
+  p.neg_mask = ops.neg_mask;
+  p.M = static_cast<int32_t>(ops.M);
+  p.N = static_cast<int32_t>(ops.N);
+  p.kblocks = static_cast<int32_t>((ops.K + kBlockK - 1) / kBlockK);
+  for (int s = 0; s < ops.num_seg; ++s) {
+    if (!make_tmap_bf16(&p.tm_a[s], ops.a[s], ops.a_mn ? 64u : static_cast<uint32_t>(kBlockM), err)) return false;
+    if (!make_tmap_bf16(&p.tm_b[s], ops.b[s], ops.b_mn ? 64u : static_cast<uint32_t>(bn), err)) return false;
+  }
+  cudaError_t e;
+  switch (epi) {
+    case kEpiRaw: e = launch_bn<kEpiRaw>(p, bn, ops.a_mn, ops.b_mn, num_sms, stream); break;
+    case kEpiSample: e = launch_bn<kEpiSample>(p, bn, ops.a_mn, ops.b_mn, num_sms, stream); break;
+    case kEpiProb: e = launch_bn<kEpiProb>(p, bn, ops.a_mn, ops.b_mn, num_sms, stream); break;
+    case kEpiFreeEnergy: e = launch_bn<kEpiFreeEnergy>(p, bn, ops.a_mn, ops.b_mn, num_sms, stream); break;
+    case kEpiReluSample: e = launch_bn<kEpiReluSample>(p, bn, ops.a_mn, ops.b_mn, num_sms, stream); break;
+    case kEpiGaussian: e = launch_bn<kEpiGaussian>(p, bn, ops.a_mn, ops.b_mn, num_sms, stream); break;
+    default:
+      if (err) *err = "bad epilogue mode";
+      return false;
+  }
+  if (e != cudaSuccess) {
+    if (err) *err = std::string("gemm launch failed: ") + cudaGetErrorString(e);
+    return false;
+  }
+  return true;
+}
+
+}  // namespace kucd
