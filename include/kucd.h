@@ -1,0 +1,217 @@
+/* kucd.h - C ABI of libkucd.so, the B200 (sm_100a) contrastive-divergence engine that sits behind
+ * keras_unsupervised's ku.ebm.RBM / ku.ebm.DBN.
+ *
+ * The reference has no FFI of its own: its boundary is the Python class surface of
+ * /root/reference/ku/ebm/rbm.py and dbn.py, and everything below that line executes inside
+ * TensorFlow through K.function objects.  Each entry point here replaces one of those K.function
+ * objects (file:line given per function); the Python shim in keras_unsupervised_b200/ebm binds them
+ * with ctypes and keeps the reference's method names and argument meaning.
+ *
+ * Conventions
+ *   - plain C: pointers, sizes and PODs only; no C++ / torch types cross this boundary.
+ *   - every function returns KUCD_OK (0) or a negative kucd_status; the message of the last failure on
+ *     the calling thread is returned by kucd_last_error().  Nothing throws, nothing aborts.
+ *   - tensors are described by kucd_tensor, a flattened DLTensor (a DLManagedTensor's dl_tensor maps
+ *     field by field).  Data may live in host memory (pageable or pinned) or on the context's GPU; the
+ *     engine copies as needed on its own stream.  The caller owns every buffer it passes and must keep
+ *     it alive until the call returns (all entry points that touch caller memory are synchronous with
+ *     respect to that memory; device work on engine-owned state may still be in flight - kucd_sync).
+ *   - there is no CPU fallback.  A device that is not compute capability 10.x yields KUCD_ERR_NOT_SM100.
+ *   - one context = one GPU = one host thread at a time.  Data-parallel training is one process (and
+ *     one context) per GPU, joined by kucd_ctx_comm_init.
+ */
+#ifndef KUCD_H_
+#define KUCD_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KUCD_ABI_VERSION 1
+
+typedef enum kucd_status {
+  KUCD_OK = 0,
+  KUCD_ERR_INVALID_ARG = -1,
+  KUCD_ERR_SHAPE_MISMATCH = -2,
+  KUCD_ERR_UNSUPPORTED_DTYPE = -3,
+  KUCD_ERR_CUDA = -4,
+  KUCD_ERR_NCCL = -5,
+  KUCD_ERR_NOT_SM100 = -6,
+  KUCD_ERR_NOT_BUILT = -7
+} kucd_status;
+
+/* DLPack device types / dtype codes (same numeric values as dlpack.h) */
+#define KUCD_DEV_CPU 1
+#define KUCD_DEV_CUDA 2
+#define KUCD_DEV_CUDA_HOST 3
+#define KUCD_DT_INT 0
+#define KUCD_DT_UINT 1
+#define KUCD_DT_FLOAT 2
+#define KUCD_DT_BFLOAT 4
+
+/* A 2-D (or 1-D: shape[1] = 1) strided tensor.  strides are in elements; the innermost stride must
+ * be 1.  Accepted element types: float32 (the reference's K.floatx()), bfloat16 and uint8. */
+typedef struct kucd_tensor {
+  void* data;
+  int32_t device_type;
+  int32_t device_id;
+  int32_t dtype_code;
+  int32_t bits;
+  int64_t shape[2];
+  int64_t strides[2];
+} kucd_tensor;
+
+/* visible-unit mode: constants of rbm.py:14-16 */
+#define KUCD_MODE_VISIBLE_BERNOULLI 0
+#define KUCD_MODE_VISIBLE_GAUSSIAN 1
+
+/* arithmetic of the contractions */
+#define KUCD_COMPUTE_BF16 0  /* W rounded to bf16 (RNE); fp32 accumulation in tensor memory */
+#define KUCD_COMPUTE_F32X3 1 /* fp32 operands carried as three bf16 terms: fp32-grade products   */
+
+/* which parameters a step may write (rbm.py:214-216 runs three single-parameter updates) */
+#define KUCD_UPDATE_W 1
+#define KUCD_UPDATE_C 2 /* hidden bias  */
+#define KUCD_UPDATE_B 4 /* visible bias */
+#define KUCD_UPDATE_ALL 7
+
+typedef struct kucd_hparams {
+  float lr;            /* hps['lr'] (rbm.py:128); multiplies batch SUMS unless normalize != 0       */
+  int32_t k;           /* Gibbs steps of the negative chain; the reference is k = 1 (rbm.py:119-124) */
+  int32_t persistent;  /* != 0: negative chain starts from the engine-held chains (PCD)               */
+  float momentum;      /* extension, 0 = reference                                                    */
+  float weight_decay;  /* extension, 0 = reference                                                    */
+  int32_t normalize;   /* 0 = batch sum (reference), 1 = divide by the GLOBAL batch rows              */
+  int32_t update_mask; /* KUCD_UPDATE_*                                                               */
+  int32_t want_stats;  /* != 0: fill kucd_step_stats (costs two free-energy passes)                   */
+} kucd_hparams;
+
+/* Injected random draws for parity runs: arrays of float32 uniforms on the caller's side of the
+ * boundary (host or device), one per sampling node of the chain, in chain order
+ *   u_h[0] : (rows, H) for h_pos            (rbm.py:46, the draw inside self.transform)
+ *   u_v[t] : (rows, V) for the t-th v_neg, t = 1..k (rbm.py:121 is t = 1; u_v[0] is unused)
+ *   u_h[t] : (rows, H) for the t-th intermediate h (CD-k extension; t = 1..k-1)
+ *   u_hc   : (rows, H) for the first h of a persistent chain (PCD only)
+ * Any pointer may be NULL: that node then draws from the engine's Philox stream. */
+#define KUCD_MAX_K 32
+typedef struct kucd_inject {
+  const kucd_tensor* u_h[KUCD_MAX_K];
+  const kucd_tensor* u_v[KUCD_MAX_K];
+  const kucd_tensor* u_hc;
+} kucd_inject;
+
+typedef struct kucd_step_stats {
+  float score;     /* mean |F(v) - F(v_neg)| with the post-update parameters (rbm.py:227-233)        */
+  float recon_err; /* mean (v - v_neg)^2 over the batch and the visible units                         */
+  float fe_mean;   /* mean F(v)                                                                       */
+  int32_t rows;
+} kucd_step_stats;
+
+typedef struct kucd_epoch_stats {
+  int64_t steps;
+  int64_t rows;
+  float device_ms; /* CUDA-event time of the epoch on the engine stream */
+  float last_score;
+  float last_recon_err;
+} kucd_epoch_stats;
+
+typedef struct kucd_timings {
+  int64_t gemm_launches;    /* tcgen05 contraction launches since the context was created / reset */
+  int64_t aux_launches;     /* update / split / reduction / conversion launches                   */
+  int64_t graph_launches;   /* CUDA-graph replays (each replays a whole CD step)                   */
+  int64_t allreduce_calls;
+  int64_t h2d_bytes, d2h_bytes;
+  float last_gemm_ms;       /* CUDA-event duration of the most recent timed contraction            */
+} kucd_timings;
+
+typedef struct kucd_ctx kucd_ctx;
+typedef struct kucd_rbm kucd_rbm;
+typedef struct kucd_dataset kucd_dataset;
+
+int kucd_abi_version(void);
+const char* kucd_last_error(void);
+
+/* ---- context ------------------------------------------------------------------------------------- */
+int kucd_ctx_create(kucd_ctx** out, int device_id, uint64_t seed);
+int kucd_ctx_destroy(kucd_ctx* ctx);
+int kucd_sync(kucd_ctx* ctx);
+int kucd_get_timings(kucd_ctx* ctx, kucd_timings* out, int reset);
+/* the CUstream the engine launches on (for callers that time with their own events) */
+int kucd_ctx_stream(kucd_ctx* ctx, void** stream_out);
+
+/* Data-parallel group (one process per GPU).  Rank 0 calls kucd_comm_unique_id and ships the 128
+ * bytes to every rank by any means (the Python shim uses torch.distributed); then every rank calls
+ * kucd_ctx_comm_init.  Afterwards every training step all-reduces dW/db/dc over NCCL. */
+int kucd_comm_unique_id(void* id128);
+int kucd_ctx_comm_init(kucd_ctx* ctx, const void* id128, int rank, int world);
+
+/* ---- model: RBM.__init__/build (rbm.py:22-40) ----------------------------------------------------- */
+int kucd_rbm_create(kucd_ctx* ctx, int64_t n_visible, int64_t n_hidden, int mode, int compute,
+                    kucd_rbm** out);
+int kucd_rbm_destroy(kucd_rbm* rbm);
+/* rbm_weight (V,H), rbm_visible_bias (V), rbm_hidden_bias (H): float32 (rbm.py:30-40) */
+int kucd_rbm_set_params(kucd_rbm* rbm, const kucd_tensor* W, const kucd_tensor* b, const kucd_tensor* c);
+int kucd_rbm_get_params(kucd_rbm* rbm, kucd_tensor* W, kucd_tensor* b, kucd_tensor* c);
+/* Philox stream of this model.  A draw is philox4x32-10(key = seed, counter = (column / 4, global row,
+ * draw id lo, draw id hi)), component column % 4, mapped to the 2^-23 lattice in [0,1) and compared
+ * with a strict < (K.random_uniform + K.less, rbm.py:46).  Draw ids: training step s (counted from
+ * `step_count`) uses 64 s + phase with phase 0 = h_pos, 1 = first h of a persistent chain, 2t = t-th
+ * v_neg, 2t+1 = t-th negative h; the n-th transform / inv_transform call uses 2^63 + n; the n-th score
+ * chain uses 2^62 + 2n (h) and 2^62 + 2n + 1 (v).  Defaults: the context seed, all counters 0. */
+int kucd_rbm_set_seed(kucd_rbm* rbm, uint64_t seed, uint64_t step_count);
+
+/* ---- inference ------------------------------------------------------------------------------------- */
+/* transform_func (rbm.py:45-48, 88-89) and RBM.call (rbm.py:80-83):  h = 1[u < sigmoid(v.W + c)]
+ * (Gaussian mode, rbm.py:58-59: relu instead of sigmoid).  h_out (rows,H) and p_out (rows,H, nullable,
+ * float32 probabilities) are caller buffers; u (rows,H, nullable) injects the uniforms. */
+int kucd_rbm_transform(kucd_rbm* rbm, const kucd_tensor* v, kucd_tensor* h_out, kucd_tensor* p_out,
+                       const kucd_tensor* u);
+/* inv_transform_func (rbm.py:51-54, 91-92):  v' = 1[u < sigmoid(h.W^T + b)]
+ * (Gaussian mode, rbm.py:64-66: v' = h.W^T + b + n, n ~ N(0,1); `u` then carries the normals). */
+int kucd_rbm_inv_transform(kucd_rbm* rbm, const kucd_tensor* h, kucd_tensor* v_out, kucd_tensor* p_out,
+                           const kucd_tensor* u);
+/* free_energy_func (rbm.py:73-76, 97-98):  F = -(v.b + sum_j log(1 + exp((v.W + c)_j))), (rows,) f32 */
+int kucd_rbm_free_energy(kucd_rbm* rbm, const kucd_tensor* v, kucd_tensor* fe_out);
+
+/* ---- training -------------------------------------------------------------------------------------- */
+/* One minibatch: the graph of rbm.py:119-134 (CD-1), generalised to CD-k / PCD, followed by the
+ * updates selected by hp->update_mask.  `global_row0` is the index of this rank's first row inside the
+ * global minibatch (0 on a single GPU): Philox draws are keyed by global row, so n ranks sample exactly
+ * what one rank would. */
+int kucd_rbm_cd_step(kucd_rbm* rbm, const kucd_tensor* v_batch, const kucd_hparams* hp,
+                     const kucd_inject* inj, int64_t global_row0, kucd_step_stats* stats);
+/* rbm.py:225-233: score = mean|F(v) - F(v_neg)| with a fresh chain (the reference's "run D").
+ * u_h (rows,H) / u_v (rows,V) nullable. */
+int kucd_rbm_score(kucd_rbm* rbm, const kucd_tensor* v_batch, const kucd_tensor* u_h,
+                   const kucd_tensor* u_v, float* score_out);
+/* statistics of the most recent cd_step, for parity tests: dW (V,H), db (V), dc (H) float32 - the
+ * un-scaled batch sums of rbm.py:125-126,131,134 (after the all-reduce when a group is attached);
+ * and the sampled states of that step: h_pos (rows,H), v_neg (rows,V), h_neg (rows,H).  Any NULL. */
+int kucd_rbm_last_stats(kucd_rbm* rbm, kucd_tensor* dW, kucd_tensor* db, kucd_tensor* dc,
+                        kucd_tensor* h_pos, kucd_tensor* v_neg, kucd_tensor* h_neg);
+/* persistent chains (PCD): (n_chains, V) states; get/set for checkpointing and parity */
+int kucd_rbm_set_chains(kucd_rbm* rbm, const kucd_tensor* v_chains);
+int kucd_rbm_get_chains(kucd_rbm* rbm, kucd_tensor* v_chains);
+
+/* ---- device-resident data sets: the minibatch loop of rbm.py:110-113,163,211-223 ------------------ */
+/* Uploads (or adopts, when already on the GPU in engine layout) a (N, dim) matrix once. */
+int kucd_dataset_create(kucd_ctx* ctx, const kucd_tensor* data, int compute, kucd_dataset** out);
+int kucd_dataset_destroy(kucd_dataset* ds);
+int kucd_dataset_shape(kucd_dataset* ds, int64_t* rows, int64_t* dim);
+int kucd_dataset_read(kucd_dataset* ds, kucd_tensor* out);
+/* One epoch over sequential slices of `batch` rows, remainder last, no shuffle (rbm.py:163,211,218);
+ * every step is one replay of a captured CUDA graph.  With a data-parallel group attached every rank
+ * passes its own shard of every global minibatch: `batch` is the per-rank row count and
+ * `global_row0` = rank * batch. */
+int kucd_rbm_fit_epoch(kucd_rbm* rbm, kucd_dataset* ds, int64_t batch, const kucd_hparams* hp,
+                       int64_t global_row0, kucd_epoch_stats* stats);
+/* DBN.fit's inter-layer step (dbn.py:55): V_p <- transform(V_p) on the whole data set, on device. */
+int kucd_rbm_transform_dataset(kucd_rbm* rbm, kucd_dataset* in, kucd_dataset** out);
+int kucd_rbm_inv_transform_dataset(kucd_rbm* rbm, kucd_dataset* in, kucd_dataset** out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KUCD_H_ */

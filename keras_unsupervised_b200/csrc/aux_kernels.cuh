@@ -1,0 +1,345 @@
+// The HBM-bound kernels around the contractions of gemm.cuh: operand ingest (any caller dtype ->
+// bf16 term planes), state export, the fused parameter update, column sums for the bias statistics,
+// the v.b term of the free energy, the score reduction and the step-state bookkeeping used under
+// CUDA-graph replay.  All of them are plain coalesced, vectorised streaming kernels sized in
+// multiples of the SM count; none is worth a tensor core.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "gemm.cuh"
+
+namespace kucd {
+
+// x = hi + mid + lo with each term a bf16 (RNE): 24 mantissa bits in three 8-bit pieces.
+__device__ __forceinline__ void split3(float x, __nv_bfloat16& hi, __nv_bfloat16& mid, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(x);
+  const float r1 = x - __bfloat162float(hi);
+  mid = __float2bfloat16_rn(r1);
+  lo = __float2bfloat16_rn(r1 - __bfloat162float(mid));
+}
+
+template <typename T>
+__device__ __forceinline__ float load_as_float(const T* p);
+template <>
+__device__ __forceinline__ float load_as_float<float>(const float* p) {
+  return __ldg(p);
+}
+template <>
+__device__ __forceinline__ float load_as_float<__nv_bfloat16>(const __nv_bfloat16* p) {
+  return __bfloat162float(*p);
+}
+template <>
+__device__ __forceinline__ float load_as_float<uint8_t>(const uint8_t* p) {
+  return static_cast<float>(__ldg(p));
+}
+
+// Caller matrix (rows, cols), row stride `src_ld` elements -> `nparts` bf16 planes (rows, ld), columns
+// [cols, ld) zeroed.  *inexact is raised when some value is not a bf16 number, which tells the host
+// whether the first plane alone carries the data exactly (binary data always does).
+template <typename T>
+__global__ void ingest_kernel(const T* __restrict__ src, int64_t src_ld, int64_t rows, int64_t cols,
+                              __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ mid,
+                              __nv_bfloat16* __restrict__ lo, int64_t ld, int nparts, int* inexact) {
+  const int64_t groups_per_row = ld / 8;
+  const int64_t total = rows * groups_per_row;
+  bool bad = false;
+  for (int64_t g = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; g < total;
+       g += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = g / groups_per_row, c0 = (g % groups_per_row) * 8;
+    __align__(16) __nv_bfloat16 h[8], m[8], l[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float x = (c0 + j < cols) ? load_as_float<T>(src + r * src_ld + c0 + j) : 0.f;
+      split3(x, h[j], m[j], l[j]);
+      bad |= (__bfloat162float(h[j]) != x);
+    }
+    *reinterpret_cast<uint4*>(hi + r * ld + c0) = *reinterpret_cast<const uint4*>(h);
+    if (nparts == 3) {
+      *reinterpret_cast<uint4*>(mid + r * ld + c0) = *reinterpret_cast<const uint4*>(m);
+      *reinterpret_cast<uint4*>(lo + r * ld + c0) = *reinterpret_cast<const uint4*>(l);
+    }
+  }
+  if (inexact != nullptr && bad) atomicOr(inexact, 1);
+}
+
+template <typename T>
+__device__ __forceinline__ void store_from_float(T* p, float x);
+template <>
+__device__ __forceinline__ void store_from_float<float>(float* p, float x) {
+  *p = x;
+}
+template <>
+__device__ __forceinline__ void store_from_float<__nv_bfloat16>(__nv_bfloat16* p, float x) {
+  *p = __float2bfloat16_rn(x);
+}
+template <>
+__device__ __forceinline__ void store_from_float<uint8_t>(uint8_t* p, float x) {
+  *p = static_cast<uint8_t>(x);
+}
+
+// bf16 planes (summed) -> caller matrix of type T
+template <typename T>
+__global__ void export_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ mid,
+                              const __nv_bfloat16* __restrict__ lo, int64_t ld, int64_t rows, int64_t cols,
+                              T* __restrict__ dst, int64_t dst_ld) {
+  const int64_t total = rows * cols;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / cols, c = i % cols;
+    float x = __bfloat162float(hi[r * ld + c]);
+    if (mid != nullptr) x += __bfloat162float(mid[r * ld + c]) + __bfloat162float(lo[r * ld + c]);
+    store_from_float<T>(dst + r * dst_ld + c, x);
+  }
+}
+
+// float32 (rows, ld_src) -> caller matrix of type T (rows, cols)
+template <typename T>
+__global__ void export_f32_kernel(const float* __restrict__ src, int64_t ld, int64_t rows, int64_t cols,
+                                  T* __restrict__ dst, int64_t dst_ld) {
+  const int64_t total = rows * cols;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / cols, c = i % cols;
+    store_from_float<T>(dst + r * dst_ld + c, src[r * ld + c]);
+  }
+}
+
+// The parameter update of rbm.py:127-134 for the weight matrix, generalised with momentum and weight
+// decay (both 0 in the reference):
+//     g = scale * dW - weight_decay * W ;  m = momentum * m + lr * g ;  W += m
+// and, in the same pass, the refresh of the bf16 operand planes the contractions read.  One float4
+// of W per thread per iteration: 4 B (dW) + 4 B (W) read, 4 B (W) + 2 B per plane written per weight.
+__global__ void update_w_kernel(float* __restrict__ W, const float* __restrict__ dW, float* __restrict__ mom,
+                                __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ mid,
+                                __nv_bfloat16* __restrict__ lo, int64_t n4, float lr, float scale, float momentum,
+                                float weight_decay) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float4 w = reinterpret_cast<const float4*>(W)[i];
+    const float4 d = reinterpret_cast<const float4*>(dW)[i];
+    float4 s;
+    s.x = lr * (scale * d.x - weight_decay * w.x);
+    s.y = lr * (scale * d.y - weight_decay * w.y);
+    s.z = lr * (scale * d.z - weight_decay * w.z);
+    s.w = lr * (scale * d.w - weight_decay * w.w);
+    if (mom != nullptr) {
+      float4 m = reinterpret_cast<const float4*>(mom)[i];
+      m.x = momentum * m.x + s.x;
+      m.y = momentum * m.y + s.y;
+      m.z = momentum * m.z + s.z;
+      m.w = momentum * m.w + s.w;
+      reinterpret_cast<float4*>(mom)[i] = m;
+      s = m;
+    }
+    w.x += s.x;
+    w.y += s.y;
+    w.z += s.z;
+    w.w += s.w;
+    reinterpret_cast<float4*>(W)[i] = w;
+    __nv_bfloat16 h[4], m4[4], l4[4];
+    split3(w.x, h[0], m4[0], l4[0]);
+    split3(w.y, h[1], m4[1], l4[1]);
+    split3(w.z, h[2], m4[2], l4[2]);
+    split3(w.w, h[3], m4[3], l4[3]);
+    reinterpret_cast<uint2*>(hi)[i] = *reinterpret_cast<const uint2*>(h);
+    if (mid != nullptr) {
+      reinterpret_cast<uint2*>(mid)[i] = *reinterpret_cast<const uint2*>(m4);
+      reinterpret_cast<uint2*>(lo)[i] = *reinterpret_cast<const uint2*>(l4);
+    }
+  }
+}
+
+// fp32 master -> bf16 planes only (after set_params)
+__global__ void refresh_planes_kernel(const float* __restrict__ W, __nv_bfloat16* __restrict__ hi,
+                                      __nv_bfloat16* __restrict__ mid, __nv_bfloat16* __restrict__ lo, int64_t n4) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float4 w = reinterpret_cast<const float4*>(W)[i];
+    __nv_bfloat16 h[4], m4[4], l4[4];
+    split3(w.x, h[0], m4[0], l4[0]);
+    split3(w.y, h[1], m4[1], l4[1]);
+    split3(w.z, h[2], m4[2], l4[2]);
+    split3(w.w, h[3], m4[3], l4[3]);
+    reinterpret_cast<uint2*>(hi)[i] = *reinterpret_cast<const uint2*>(h);
+    if (mid != nullptr) {
+      reinterpret_cast<uint2*>(mid)[i] = *reinterpret_cast<const uint2*>(m4);
+      reinterpret_cast<uint2*>(lo)[i] = *reinterpret_cast<const uint2*>(l4);
+    }
+  }
+}
+
+// bias update (rbm.py:129-134): x += lr * scale * d (+ momentum), n entries
+__global__ void update_bias_kernel(float* __restrict__ x, const float* __restrict__ d, float* __restrict__ mom,
+                                   int64_t n, float lr, float scale, float momentum) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  float s = lr * scale * d[i];
+  if (mom != nullptr) {
+    s = momentum * mom[i] + s;
+    mom[i] = s;
+  }
+  x[i] += s;
+}
+
+// out[c] += sign * sum_r (hi + mid + lo)[row_off + r, c], r < rows_valid.  One bf16 pair per thread,
+// 64 rows per block.y slab, one atomic per column per slab.
+__global__ void colsum_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ mid,
+                              const __nv_bfloat16* __restrict__ lo, int64_t ld, int64_t row_off, int32_t rows,
+                              int32_t cols, const StepDyn* dyn, float sign, float* __restrict__ out) {
+  if (dyn != nullptr) {
+    row_off += dyn->row_off;
+    rows = dyn->rows_valid < rows ? dyn->rows_valid : rows;
+  }
+  const int c = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
+  if (c >= cols) return;
+  const int r0 = blockIdx.y * 64;
+  const int r1 = r0 + 64 < rows ? r0 + 64 : rows;
+  float s0 = 0.f, s1 = 0.f;
+  for (int r = r0; r < r1; ++r) {
+    const int64_t off = (row_off + r) * ld + c;
+    float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(hi + off));
+    if (mid != nullptr) {
+      const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(mid + off));
+      const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(lo + off));
+      v.x += a.x + b.x;
+      v.y += a.y + b.y;
+    }
+    s0 += v.x;
+    s1 += v.y;
+  }
+  if (r1 > r0) {
+    atomicAdd(out + c, sign * s0);
+    if (c + 1 < cols) atomicAdd(out + c + 1, sign * s1);
+  }
+}
+
+// Free energy tail (rbm.py:73-75):  F[r] = -( v[r,:].b + softplus_sum[r] ).  One warp per row.
+__global__ void free_energy_finish_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ mid,
+                                          const __nv_bfloat16* __restrict__ lo, int64_t ld, int64_t row_off,
+                                          int32_t rows, int32_t cols, const StepDyn* dyn,
+                                          const float* __restrict__ b, const float* __restrict__ softplus_sum,
+                                          float* __restrict__ out) {
+  if (dyn != nullptr) {
+    row_off += dyn->row_off;
+    rows = dyn->rows_valid < rows ? dyn->rows_valid : rows;
+  }
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const int64_t base = (row_off + warp) * ld;
+  float s = 0.f;
+  for (int c = 2 * lane; c < cols; c += 64) {
+    float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(hi + base + c));
+    if (mid != nullptr) {
+      const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(mid + base + c));
+      const float2 l = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(lo + base + c));
+      v.x += a.x + l.x;
+      v.y += a.y + l.y;
+    }
+    s += v.x * b[c];
+    if (c + 1 < cols) s += v.y * b[c + 1];
+  }
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) out[warp] = -(s + softplus_sum[warp]);
+}
+
+// stats[0] = mean |fe - fe_p| (rbm.py:233) ; stats[2] = mean fe.  Single block: deterministic.
+__global__ void score_kernel(const float* __restrict__ fe, const float* __restrict__ fe_p, int32_t rows,
+                             const StepDyn* dyn, float* __restrict__ stats) {
+  if (dyn != nullptr) rows = dyn->rows_valid < rows ? dyn->rows_valid : rows;
+  __shared__ float sh_a[32], sh_b[32];
+  float a = 0.f, b = 0.f;
+  for (int i = threadIdx.x; i < rows; i += blockDim.x) {
+    a += fabsf(fe[i] - fe_p[i]);
+    b += fe[i];
+  }
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    sh_a[threadIdx.x >> 5] = a;
+    sh_b[threadIdx.x >> 5] = b;
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    a = threadIdx.x < (blockDim.x >> 5) ? sh_a[threadIdx.x] : 0.f;
+    b = threadIdx.x < (blockDim.x >> 5) ? sh_b[threadIdx.x] : 0.f;
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+      b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    if (threadIdx.x == 0) {
+      stats[0] = rows > 0 ? a / rows : 0.f;
+      stats[2] = rows > 0 ? b / rows : 0.f;
+      stats[3] = static_cast<float>(rows);
+    }
+  }
+}
+
+// acc[0] += sum (v0 - vk)^2 over the valid rows (reconstruction error numerator)
+__global__ void recon_kernel(const __nv_bfloat16* __restrict__ a_hi, const __nv_bfloat16* __restrict__ a_mid,
+                             const __nv_bfloat16* __restrict__ a_lo, int64_t a_ld, int64_t a_row_off,
+                             const __nv_bfloat16* __restrict__ b_hi, const __nv_bfloat16* __restrict__ b_mid,
+                             const __nv_bfloat16* __restrict__ b_lo, int64_t b_ld, int32_t rows, int32_t cols,
+                             const StepDyn* dyn, float* __restrict__ acc) {
+  if (dyn != nullptr) {
+    a_row_off += dyn->row_off;
+    rows = dyn->rows_valid < rows ? dyn->rows_valid : rows;
+  }
+  const int64_t total = static_cast<int64_t>(rows) * cols;
+  float s = 0.f;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / cols, c = i % cols;
+    float a = __bfloat162float(a_hi[(a_row_off + r) * a_ld + c]);
+    if (a_mid != nullptr)
+      a += __bfloat162float(a_mid[(a_row_off + r) * a_ld + c]) + __bfloat162float(a_lo[(a_row_off + r) * a_ld + c]);
+    float b = __bfloat162float(b_hi[r * b_ld + c]);
+    if (b_mid != nullptr) b += __bfloat162float(b_mid[r * b_ld + c]) + __bfloat162float(b_lo[r * b_ld + c]);
+    s += (a - b) * (a - b);
+  }
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0 && s != 0.f) atomicAdd(acc, s);
+}
+
+// stats[1] = acc / (rows * cols)
+__global__ void recon_finish_kernel(const float* acc, int32_t rows, int32_t cols, const StepDyn* dyn, float* stats) {
+  if (dyn != nullptr) rows = dyn->rows_valid < rows ? dyn->rows_valid : rows;
+  stats[1] = rows > 0 ? acc[0] / (static_cast<float>(rows) * cols) : 0.f;
+}
+
+// valid rows of src -> dst (persistent chains keep the rows a remainder minibatch did not touch)
+__global__ void copy_rows_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t ld,
+                                 int32_t rows, const StepDyn* dyn) {
+  if (dyn != nullptr) rows = dyn->rows_valid < rows ? dyn->rows_valid : rows;
+  const int64_t total = static_cast<int64_t>(rows) * (ld / 8);
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(src)[i];
+}
+
+__global__ void set_dyn_kernel(StepDyn* dyn, int64_t row_off, int32_t rows_valid, uint64_t step) {
+  dyn->row_off = row_off;
+  dyn->rows_valid = rows_valid;
+  dyn->pad = 0;
+  dyn->step = step;
+}
+
+// next minibatch: sequential slices, remainder last (rbm.py:163,211,218)
+__global__ void advance_dyn_kernel(StepDyn* dyn, int32_t batch, int64_t total_rows) {
+  const int64_t off = dyn->row_off + batch;
+  const int64_t left = total_rows - off;
+  dyn->row_off = off;
+  dyn->rows_valid = static_cast<int32_t>(left < 0 ? 0 : (left < batch ? left : batch));
+  dyn->step += 1;
+}
+
+}  // namespace kucd

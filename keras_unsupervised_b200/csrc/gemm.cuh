@@ -33,7 +33,7 @@
 
 namespace kucd {
 
-constexpr int kMaxSeg = 8;
+constexpr int kMaxSeg = 10;
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;  // 64 bf16 = one 128-byte swizzle row
 constexpr int kNumEpiWarps = 8;
@@ -46,6 +46,15 @@ enum EpiMode : int {
   kEpiFreeEnergy = 3,  // rowsum[m] += sum_n softplus(D + bias)
   kEpiReluSample = 4,  // s = 1[u < relu(D + bias)]   (Gaussian-visible mode, rbm.py:58-59)
   kEpiGaussian = 5,    // x = D + bias + N(0,1)       (Gaussian-visible mode, rbm.py:64-66) -> out_bf16 splits + out_f32
+};
+
+// Per-step quantities that live in device memory so that a captured CUDA graph of one CD step can be
+// replayed for every minibatch of an epoch: the kernels read them, a one-thread kernel advances them.
+struct StepDyn {
+  int64_t row_off;     // first data-set row of the current minibatch
+  int32_t rows_valid;  // rows of the current minibatch (< batch on the remainder step, rbm.py:211)
+  int32_t pad;
+  uint64_t step;       // minibatch counter: offsets the Philox draw id
 };
 
 struct alignas(64) GemmParams {
@@ -66,11 +75,17 @@ struct alignas(64) GemmParams {
   int64_t ld_f32;
   const float* u_inject;  // optional injected uniforms (M, ld_u): parity mode
   int64_t ld_u;
-  float* colsum;  // optional (N): += column sums of the stored output
+  float* colsum;  // optional (N): += colsum_sign * column sums of the stored output
+  float colsum_sign;
+  int32_t dyn_rows;  // != 0: the valid row count is min(m_valid, dyn->rows_valid) (minibatch-row outputs)
   float* rowsum;  // free energy accumulator (M)
   uint64_t seed;
   uint64_t draw;  // draw id: distinct for every sampling launch
   int64_t row0;   // global row index of local row 0 (data-parallel shards sample identically)
+  int32_t m_valid;  // rows < m_valid carry data; rows in [m_valid, M) are stored as zeros
+  uint32_t a_dyn_mask;  // bit s: the row coordinate of segment s's A operand is offset by dyn->row_off
+  const StepDyn* dyn;   // optional device-resident step state (graph replay)
+  uint64_t draw_stride;  // draw += dyn->step * draw_stride
   // ---- descriptor overrides used only by the bring-up probe (0 = default) ----
   uint32_t dbg_lbo_a, dbg_sbo_a, dbg_adv_a, dbg_lbo_b, dbg_sbo_b, dbg_adv_b;
 };
@@ -133,9 +148,9 @@ __device__ __forceinline__ float warp_transpose_reduce(float (&v)[32], uint32_t 
 __device__ __forceinline__ void box_muller(uint32_t b0, uint32_t b1, float& n0, float& n1) {
   const float u1 = (static_cast<float>(b0 >> 9) + 0.5f) * 1.1920928955078125e-07f;
   const float u2 = u01_from_bits(b1);
-  const float r = sqrtf(-2.0f * __logf(u1));
+  const float r = sqrtf(-2.0f * logf(u1));
   float s, c;
-  __sincosf(6.283185307179586f * u2, &s, &c);
+  sincospif(2.0f * u2, &s, &c);
   n0 = r * c;
   n1 = r * s;
 }
@@ -143,8 +158,9 @@ __device__ __forceinline__ void box_muller(uint32_t b0, uint32_t b1, float& n0, 
 // One 32-column chunk of one output row (this thread's TMEM lane).
 template <int EPI>
 __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32_t (&acc)[32], int row, int col0,
-                                               bool row_ok, uint32_t lane, float& row_acc) {
+                                               bool row_ok, uint64_t draw, uint32_t lane, float& row_acc) {
   if (col0 >= p.N) return;  // warp-uniform
+  const bool row_st = row < p.M;  // rows in [m_valid, M) are stored as zeros: they are K-rows of the dW contraction
 
   if constexpr (EPI == kEpiRaw) {
     if (row_ok) {
@@ -211,7 +227,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
     } else {
       const uint32_t grow = static_cast<uint32_t>(p.row0 + row);
       const uint32_t k0 = static_cast<uint32_t>(p.seed), k1 = static_cast<uint32_t>(p.seed >> 32);
-      const uint32_t d0 = static_cast<uint32_t>(p.draw), d1 = static_cast<uint32_t>(p.draw >> 32);
+      const uint32_t d0 = static_cast<uint32_t>(draw), d1 = static_cast<uint32_t>(draw >> 32);
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         const Philox4 r = philox4x32_10(static_cast<uint32_t>((col0 >> 2) + q), grow, d0, d1, k0, k1);
@@ -224,7 +240,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
       if (ncol < 32) bits &= (1u << ncol) - 1u;
       if (!row_ok) bits = 0;
     }
-    if (row_ok) {
+    if (row_st) {
       uint4* dst = reinterpret_cast<uint4*>(p.out_bf16 + static_cast<int64_t>(row) * p.ld_bf16 + col0);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
@@ -249,7 +265,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
       }
       const int cnt = __popc(mine);
       if (cnt != 0 && col0 + static_cast<int>(lane) < p.N)
-        atomicAdd(p.colsum + col0 + lane, static_cast<float>(cnt));
+        atomicAdd(p.colsum + col0 + lane, p.colsum_sign * static_cast<float>(cnt));
     }
     return;
   }
@@ -261,7 +277,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
     } else {
       const uint32_t grow = static_cast<uint32_t>(p.row0 + row);
       const uint32_t k0 = static_cast<uint32_t>(p.seed), k1 = static_cast<uint32_t>(p.seed >> 32);
-      const uint32_t d0 = static_cast<uint32_t>(p.draw), d1 = static_cast<uint32_t>(p.draw >> 32);
+      const uint32_t d0 = static_cast<uint32_t>(draw), d1 = static_cast<uint32_t>(draw >> 32);
       if (p.u_inject != nullptr) {  // injected standard normals
         if (row_ok) {
           const float* up = p.u_inject + static_cast<int64_t>(row) * p.ld_u + col0;
@@ -285,8 +301,8 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
 #pragma unroll
     for (int j = 0; j < 32; ++j)
       if (col0 + j >= p.N || !row_ok) x[j] = 0.f;
-    if (row_ok) {
-      if (p.out_f32 != nullptr) {
+    if (row_st) {
+      if (p.out_f32 != nullptr && row_ok) {
         float* dst = p.out_f32 + static_cast<int64_t>(row) * p.ld_f32 + col0;
 #pragma unroll
         for (int q = 0; q < 8; ++q)
@@ -338,13 +354,19 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
     }
     if (p.colsum != nullptr) {
       const float s = warp_transpose_reduce(x, lane);
-      if (col0 + static_cast<int>(lane) < p.N) atomicAdd(p.colsum + col0 + lane, s);
+      if (col0 + static_cast<int>(lane) < p.N) atomicAdd(p.colsum + col0 + lane, p.colsum_sign * s);
     }
     return;
   }
 }
 
-template <int BN, bool A_MN, bool B_MN, int EPI>
+// CH = 0: the whole contraction of a tile accumulates in tensor memory.
+// CH > 0: "precise" mode for fp32-grade (f32x3) runs.  The tensor core truncates when it aligns each
+// MMA's result to the running fp32 accumulator, an error that grows with the length and the magnitude of
+// the chain (measured ~2e-5 relative at K = 4096).  Here the chain is cut every CH k-blocks: each piece
+// accumulates from zero in one of the two TMEM buffers and the epilogue warps sum the pieces in
+// registers with IEEE fp32 adds while the next piece is being multiplied.
+template <int BN, bool A_MN, bool B_MN, int EPI, int CH = 0>
 __global__ void __launch_bounds__(kNumThreads, 1) gemm_bf16_kernel(const __grid_constant__ GemmParams p) {
   using Cfg = GemmCfg<BN>;
   constexpr int kStages = Cfg::kStages;
@@ -364,7 +386,16 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_bf16_kernel(const __grid_
   const int num_m = (p.M + kBlockM - 1) / kBlockM;
   const int num_n = (p.N + BN - 1) / BN;
   const int num_tiles = num_m * num_n;
-  const int kb_total = p.num_seg * p.kblocks;
+
+  // step state: host-supplied for a direct launch, device-resident under graph replay
+  int32_t dyn_row_off = 0;
+  int32_t m_valid = p.m_valid;
+  uint64_t draw = p.draw;
+  if (p.dyn != nullptr) {
+    dyn_row_off = static_cast<int32_t>(p.dyn->row_off);
+    if (p.dyn_rows != 0) m_valid = p.dyn->rows_valid < m_valid ? p.dyn->rows_valid : m_valid;
+    draw += p.dyn->step * p.draw_stride;
+  }
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.num_seg; ++s) {
@@ -401,6 +432,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_bf16_kernel(const __grid_
         const int m_blk = tile / num_n, n_blk = tile % num_n;
         const int m0 = m_blk * kBlockM, n0 = n_blk * BN;
         for (int s = 0; s < p.num_seg; ++s) {
+          const int a_off = ((p.a_dyn_mask >> s) & 1u) ? dyn_row_off : 0;  // A rows: M if K-major, K if MN-major
           for (int kb = 0; kb < p.kblocks; ++kb) {
             ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
             ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
@@ -408,11 +440,11 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_bf16_kernel(const __grid_
             uint8_t* sb = sa + Cfg::kABytes;
             const int k0 = kb * kBlockK;
             if constexpr (!A_MN) {
-              ptx::tma_load_2d(sa, &p.tm_a[s], &full_bar[stage], k0, m0);  // box {64 k, 128 m}
+              ptx::tma_load_2d(sa, &p.tm_a[s], &full_bar[stage], k0, m0 + a_off);  // box {64 k, 128 m}
             } else {
 #pragma unroll
               for (int j = 0; j < kBlockM / 64; ++j)  // boxes {64 m, 64 k}
-                ptx::tma_load_2d(sa + j * (kBlockK * 128), &p.tm_a[s], &full_bar[stage], m0 + 64 * j, k0);
+                ptx::tma_load_2d(sa + j * (kBlockK * 128), &p.tm_a[s], &full_bar[stage], m0 + 64 * j, k0 + a_off);
             }
             if constexpr (!B_MN) {
               ptx::tma_load_2d(sb, &p.tm_b[s], &full_bar[stage], k0, n0);  // box {64 k, BN n}
@@ -445,16 +477,21 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_bf16_kernel(const __grid_
       constexpr uint32_t idesc_neg = make_idesc(kBlockM, BN, A_MN, B_MN, true);
 
       uint32_t stage = 0, phase = 0;
-      uint32_t local = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
-        const uint32_t as = local & 1u, aphase = (local >> 1) & 1u;
-        ptx::mbar_wait(&tmem_empty_bar[as], aphase ^ 1u);
-        ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * BN;
+      uint32_t accn = 0;  // accumulator buffers handed to the epilogue so far
+      const int total = p.num_seg * p.kblocks;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        uint32_t as = 0, d_tmem = 0;
         int it = 0;
         for (int s = 0; s < p.num_seg; ++s) {
           const uint32_t idesc = ((p.neg_mask >> s) & 1u) ? idesc_neg : idesc_pos;
-          for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
+          for (int kb = 0; kb < p.kblocks; ++kb) {
+            const int in_piece = CH > 0 ? it % (CH > 0 ? CH : 1) : it;
+            if (in_piece == 0) {  // next accumulator buffer: wait until the epilogue has drained it
+              as = accn & 1u;
+              ptx::mbar_wait(&tmem_empty_bar[as], ((accn >> 1) & 1u) ^ 1u);
+              ptx::tc_fence_after();
+              d_tmem = tmem_base + as * BN;
+            }
             ptx::mbar_wait(&full_bar[stage], phase);
             ptx::tc_fence_after();
             const uint32_t sa = ptx::smem_u32(smem + stage * Cfg::kStageBytes);
@@ -464,17 +501,20 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_bf16_kernel(const __grid_
 #pragma unroll
             for (int k = 0; k < kBlockK / 16; ++k) {
               ptx::mma_bf16<1>(d_tmem, da + ((k * adv_a) >> 4), db + ((k * adv_b) >> 4), idesc,
-                               (it > 0 || k > 0) ? 1u : 0u);
+                               (in_piece > 0 || k > 0) ? 1u : 0u);
             }
             ptx::mma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
             if (++stage == kStages) {
               stage = 0;
               phase ^= 1u;
             }
+            ++it;
+            if (CH > 0 ? (it % (CH > 0 ? CH : 1) == 0 || it == total) : it == total) {
+              ptx::mma_commit(&tmem_full_bar[as]);  // this piece of the accumulation is complete
+              ++accn;
+            }
           }
         }
-        ptx::mma_commit(&tmem_full_bar[as]);  // accumulator complete
-        (void)kb_total;
       }
     }
   } else {
@@ -483,29 +523,62 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_bf16_kernel(const __grid_
     const uint32_t quarter = warp & 3u;  // TMEM lane quarter this warp may access
     const uint32_t half = ew >> 2;       // which half of the tile's columns
     constexpr int kColsPerWarp = BN / 2;
-    uint32_t local = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
-      const uint32_t as = local & 1u, aphase = (local >> 1) & 1u;
+    uint32_t accn = 0;
+    const int total = p.num_seg * p.kblocks;
+    const int pieces = CH > 0 ? (total + (CH > 0 ? CH : 1) - 1) / (CH > 0 ? CH : 1) : 1;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile / num_n, n_blk = tile % num_n;
       const int row = m_blk * kBlockM + quarter * 32 + lane;
-      const bool row_ok = row < p.M;
-      ptx::mbar_wait(&tmem_full_bar[as], aphase);
-      ptx::tc_fence_after();
+      const bool row_ok = row < m_valid;
       float row_acc = 0.f;
+      if constexpr (CH == 0) {
+        const uint32_t as = accn & 1u;
+        ptx::mbar_wait(&tmem_full_bar[as], (accn >> 1) & 1u);
+        ptx::tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < kColsPerWarp; c += 32) {
-        const int coff = half * kColsPerWarp + c;
-        uint32_t acc[32];
-        ptx::tmem_ld_32x32(tmem_base + ((quarter * 32u) << 16) + as * BN + coff, acc);
-        ptx::tmem_ld_wait();
-        epilogue_chunk<EPI>(p, acc, row, n_blk * BN + coff, row_ok, lane, row_acc);
+        for (int c = 0; c < kColsPerWarp; c += 32) {
+          const int coff = half * kColsPerWarp + c;
+          uint32_t acc[32];
+          ptx::tmem_ld_32x32(tmem_base + ((quarter * 32u) << 16) + as * BN + coff, acc);
+          ptx::tmem_ld_wait();
+          epilogue_chunk<EPI>(p, acc, row, n_blk * BN + coff, row_ok, draw, lane, row_acc);
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[as]);
+        ++accn;
+      } else {
+        float sum[kColsPerWarp];
+#pragma unroll
+        for (int j = 0; j < kColsPerWarp; ++j) sum[j] = 0.f;
+        for (int piece = 0; piece < pieces; ++piece) {
+          const uint32_t as = accn & 1u;
+          ptx::mbar_wait(&tmem_full_bar[as], (accn >> 1) & 1u);
+          ptx::tc_fence_after();
+#pragma unroll
+          for (int c = 0; c < kColsPerWarp; c += 32) {
+            uint32_t acc[32];
+            ptx::tmem_ld_32x32(tmem_base + ((quarter * 32u) << 16) + as * BN + half * kColsPerWarp + c, acc);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sum[c + j] += __uint_as_float(acc[j]);
+          }
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[as]);
+          ++accn;
+        }
+#pragma unroll
+        for (int c = 0; c < kColsPerWarp; c += 32) {
+          uint32_t acc[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[j] = __float_as_uint(sum[c + j]);
+          epilogue_chunk<EPI>(p, acc, row, n_blk * BN + half * kColsPerWarp + c, row_ok, draw, lane, row_acc);
+        }
       }
       if constexpr (EPI == kEpiFreeEnergy) {
         if (row_ok) atomicAdd(p.rowsum + row, row_acc);
       }
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[as]);
     }
   }
 

@@ -1,0 +1,1555 @@
+// libkucd.so - host side of the contrastive-divergence engine and its C ABI (include/kucd.h).
+//
+// What the reference does with eight K.function graph executions per minibatch
+// (/root/reference/ku/ebm/rbm.py:214-231) is here a fixed sequence of launches on one stream:
+//
+//   colsum(v0)                                    -> db            (rbm.py:134, positive half)
+//   h0 = 1[u < sigmoid(v0.W + c)]      tcgen05    -> dc += sum h0  (rbm.py:120 = :46-47)
+//   k x { v = 1[u < sigmoid(h.W^T + b)] ; h = sample or, last, sigmoid(v.W + c) }   (rbm.py:121-124)
+//   dW = v0^T h0 - vk^T hk             tcgen05, both phases in one TMEM accumulator (rbm.py:125-126)
+//   [ncclAllReduce(dW | db | dc)]                  data-parallel ranks
+//   W += lr dW ; b += lr db ; c += lr dc           fused update + bf16 plane refresh (rbm.py:127-134)
+//
+// Parameters, operand planes, chains and workspaces stay in HBM between calls; under fit_epoch the
+// sequence is captured once as a CUDA graph and replayed per minibatch, with the minibatch offset,
+// the remainder-row count and the Philox draw counter living in device memory (StepDyn).
+#include "../../include/kucd.h"
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "aux_kernels.cuh"
+#include "launch.cuh"
+
+using namespace kucd;
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+static int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CU_TRY(expr)                                                                                   \
+  do {                                                                                                 \
+    cudaError_t e_ = (expr);                                                                           \
+    if (e_ != cudaSuccess)                                                                             \
+      return fail(KUCD_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+#define KU_TRY(expr)         \
+  do {                       \
+    int rc_ = (expr);        \
+    if (rc_ != KUCD_OK) return rc_; \
+  } while (0)
+
+static inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+// ------------------------------------------------------------------------------------------------
+// NCCL, bound at run time (the process usually already holds torch's libnccl.so.2)
+// ------------------------------------------------------------------------------------------------
+struct NcclUid {
+  char internal[128];
+};
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(NcclUid*) = nullptr;
+  int (*CommInitRank)(void**, int, NcclUid, int) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+
+static int nccl_load() {
+  if (g_nccl.lib != nullptr) return KUCD_OK;
+  const char* env = getenv("KUCD_NCCL_LIB");
+  const char* names[] = {env, "libnccl.so.2", "libnccl.so", "/usr/local/cuda/lib64/libnccl.so.2"};
+  void* lib = nullptr;
+  for (const char* n : names) {
+    if (n == nullptr || *n == 0) continue;
+    lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (lib != nullptr) break;
+  }
+  if (lib == nullptr) return fail(KUCD_ERR_NCCL, "libnccl.so.2 not found (set KUCD_NCCL_LIB): %s", dlerror());
+  g_nccl.GetUniqueId = reinterpret_cast<decltype(g_nccl.GetUniqueId)>(dlsym(lib, "ncclGetUniqueId"));
+  g_nccl.CommInitRank = reinterpret_cast<decltype(g_nccl.CommInitRank)>(dlsym(lib, "ncclCommInitRank"));
+  g_nccl.CommDestroy = reinterpret_cast<decltype(g_nccl.CommDestroy)>(dlsym(lib, "ncclCommDestroy"));
+  g_nccl.AllReduce = reinterpret_cast<decltype(g_nccl.AllReduce)>(dlsym(lib, "ncclAllReduce"));
+  g_nccl.GetErrorString = reinterpret_cast<decltype(g_nccl.GetErrorString)>(dlsym(lib, "ncclGetErrorString"));
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommDestroy || !g_nccl.AllReduce ||
+      !g_nccl.GetErrorString)
+    return fail(KUCD_ERR_NCCL, "libnccl lacks a required symbol");
+  g_nccl.lib = lib;
+  return KUCD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// objects
+// ------------------------------------------------------------------------------------------------
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  int ensure(size_t n, bool zero = false) {
+    if (n <= bytes) return KUCD_OK;
+    if (p != nullptr) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+    CU_TRY(cudaMalloc(&p, n));
+    bytes = n;
+    if (zero) CU_TRY(cudaMemset(p, 0, n));
+    return KUCD_OK;
+  }
+  void release() {
+    if (p != nullptr) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+  }
+  template <typename T>
+  T* as() const {
+    return static_cast<T*>(p);
+  }
+};
+
+struct kucd_ctx {
+  int device = 0;
+  int num_sms = 0;
+  uint64_t seed = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  kucd_timings tm{};
+  void* comm = nullptr;
+  int rank = 0, world = 1;
+  DevBuf stage_in, stage_u, stage_out;  // raw caller-dtype staging for host tensors
+};
+
+// up to three bf16 term planes of one (rows, cols) matrix, leading dimension ld
+struct Planes {
+  __nv_bfloat16* p[3] = {nullptr, nullptr, nullptr};
+  int n = 1;  // live terms (1: the first plane is exact)
+  int64_t rows = 0, cols = 0, ld = 0;
+  __nv_bfloat16* mid() const { return n == 3 ? p[1] : nullptr; }
+  __nv_bfloat16* lo() const { return n == 3 ? p[2] : nullptr; }
+};
+
+struct PlaneBuf {
+  DevBuf buf[3];
+  int64_t rows = 0, ld = 0;
+  int ensure(int64_t r, int64_t ld_, int nplanes) {
+    for (int i = 0; i < nplanes; ++i) KU_TRY(buf[i].ensure(static_cast<size_t>(r) * ld_ * 2));
+    rows = r;
+    ld = ld_;
+    return KUCD_OK;
+  }
+  Planes view(int64_t r, int64_t cols, int n) const {
+    Planes v;
+    for (int i = 0; i < 3; ++i) v.p[i] = buf[i].as<__nv_bfloat16>();
+    v.n = n;
+    v.rows = r;
+    v.cols = cols;
+    v.ld = ld;
+    return v;
+  }
+  void release() {
+    for (auto& b : buf) b.release();
+  }
+};
+
+struct kucd_dataset {
+  kucd_ctx* ctx = nullptr;
+  PlaneBuf planes;
+  int64_t rows = 0, dim = 0;
+  int nparts = 1;  // live terms
+  Planes view() const { return planes.view(rows, dim, nparts); }
+};
+
+struct GraphKey {
+  const kucd_dataset* ds = nullptr;
+  int64_t batch = 0, global_row0 = 0, ds_rows = 0;
+  kucd_hparams hp{};
+  int ds_parts = 0;
+  bool operator==(const GraphKey& o) const {
+    return ds == o.ds && batch == o.batch && global_row0 == o.global_row0 && ds_rows == o.ds_rows &&
+           ds_parts == o.ds_parts && memcmp(&hp, &o.hp, sizeof hp) == 0;
+  }
+};
+
+struct kucd_rbm {
+  kucd_ctx* ctx = nullptr;
+  int64_t V = 0, H = 0, ldV = 0, ldH = 0;
+  int mode = KUCD_MODE_VISIBLE_BERNOULLI;
+  int compute = KUCD_COMPUTE_BF16;
+  int wparts = 1;
+  // parameters
+  DevBuf W32;        // (V, ldH) fp32 master
+  PlaneBuf Wp;       // bf16 operand planes of W
+  DevBuf b32, c32;   // biases, zero-padded so an epilogue may read a whole tile of them
+  DevBuf mW, mb, mc; // momentum (allocated on first use)
+  // gradient block: [dW (V*ldH) | db (ldV) | dc (ldH)] - one all-reduce covers it
+  DevBuf grad;
+  // workspaces, sized for `cap` rows
+  int64_t cap = 0;
+  PlaneBuf vin, h0, hk, vk;
+  PlaneBuf chains;  // persistent chains (n_chains, ldV)
+  int64_t n_chains = 0;
+  DevBuf fe0, fe1, sp0, sp1, pstage, stats, flag;
+  DevBuf dyn;
+  uint64_t seed = 0;  // Philox key; draws are (seed, draw id, global row, column)
+  uint64_t step_count = 0, infer_draws = 0, score_draws = 0;
+  int64_t last_rows = 0;
+  int last_vk_parts = 1, last_hk_parts = 1;
+  // captured CD step
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t graph_exec = nullptr;
+  GraphKey graph_key;
+
+  float* dW() const { return grad.as<float>(); }
+  float* db() const { return grad.as<float>() + V * ldH; }
+  float* dc() const { return grad.as<float>() + V * ldH + ldVb(); }
+  int64_t ldVb() const { return round_up(V, 256) + 256; }
+  int64_t ldHb() const { return round_up(H, 256) + 256; }
+  int64_t grad_elems() const { return V * ldH + ldVb() + ldHb(); }
+};
+
+static int grid_for(const kucd_ctx* ctx, int64_t work_items, int threads) {
+  const int64_t blocks = (work_items + threads - 1) / threads;
+  const int64_t cap = static_cast<int64_t>(ctx->num_sms) * 8;
+  return static_cast<int>(std::max<int64_t>(1, std::min(blocks, cap)));
+}
+
+// ------------------------------------------------------------------------------------------------
+// tensors at the boundary
+// ------------------------------------------------------------------------------------------------
+static int elem_size(const kucd_tensor* t) { return t->bits / 8; }
+
+static bool dtype_ok(const kucd_tensor* t) {
+  return (t->dtype_code == KUCD_DT_FLOAT && t->bits == 32) || (t->dtype_code == KUCD_DT_BFLOAT && t->bits == 16) ||
+         (t->dtype_code == KUCD_DT_UINT && t->bits == 8);
+}
+
+// vectors may arrive as (n,1) with unit stride: view them as one row of n
+static kucd_tensor as_matrix(const kucd_tensor* t) {
+  kucd_tensor m = *t;
+  if (m.shape[1] == 1 && m.shape[0] > 1 && m.strides[0] == 1) {
+    m.shape[1] = m.shape[0];
+    m.shape[0] = 1;
+    m.strides[0] = m.shape[1];
+    m.strides[1] = 1;
+  }
+  return m;
+}
+
+static int check_tensor(const kucd_ctx* ctx, const kucd_tensor* t, int64_t rows, int64_t cols, const char* name,
+                        bool f32_only = false) {
+  if (t == nullptr) return fail(KUCD_ERR_INVALID_ARG, "%s is NULL", name);
+  if (t->data == nullptr && t->shape[0] * t->shape[1] != 0) return fail(KUCD_ERR_INVALID_ARG, "%s has no data", name);
+  if (!dtype_ok(t))
+    return fail(KUCD_ERR_UNSUPPORTED_DTYPE, "%s: dtype code %d / %d bits is not float32, bfloat16 or uint8", name,
+                t->dtype_code, t->bits);
+  if (f32_only && !(t->dtype_code == KUCD_DT_FLOAT && t->bits == 32))
+    return fail(KUCD_ERR_UNSUPPORTED_DTYPE, "%s must be float32", name);
+  if (t->device_type != KUCD_DEV_CPU && t->device_type != KUCD_DEV_CUDA && t->device_type != KUCD_DEV_CUDA_HOST)
+    return fail(KUCD_ERR_INVALID_ARG, "%s: unsupported device type %d", name, t->device_type);
+  if (t->device_type == KUCD_DEV_CUDA && t->device_id != ctx->device)
+    return fail(KUCD_ERR_INVALID_ARG, "%s lives on GPU %d, the context on GPU %d", name, t->device_id, ctx->device);
+  if (t->shape[1] > 1 && t->strides[1] != 1) return fail(KUCD_ERR_INVALID_ARG, "%s: innermost stride must be 1", name);
+  if ((rows >= 0 && t->shape[0] != rows) || (cols >= 0 && t->shape[1] != cols))
+    return fail(KUCD_ERR_SHAPE_MISMATCH, "%s has shape (%lld, %lld), expected (%lld, %lld)", name,
+                (long long)t->shape[0], (long long)t->shape[1], (long long)rows, (long long)cols);
+  return KUCD_OK;
+}
+
+static bool on_device(const kucd_tensor* t) { return t->device_type == KUCD_DEV_CUDA; }
+
+// rows [r0, r0+n) of a caller tensor as a device pointer + row stride (elements)
+static int fetch_rows(kucd_ctx* ctx, const kucd_tensor* t, int64_t r0, int64_t n, DevBuf& staging, const void** ptr,
+                      int64_t* ld) {
+  const int es = elem_size(t);
+  const char* src = static_cast<const char*>(t->data) + r0 * t->strides[0] * es;
+  if (on_device(t)) {
+    *ptr = src;
+    *ld = t->strides[0];
+    return KUCD_OK;
+  }
+  const int64_t cols = t->shape[1];
+  KU_TRY(staging.ensure(static_cast<size_t>(n) * cols * es));
+  CU_TRY(cudaMemcpy2DAsync(staging.p, cols * es, src, t->strides[0] * es, cols * es, n, cudaMemcpyHostToDevice,
+                           ctx->stream));
+  ctx->tm.h2d_bytes += n * cols * es;
+  *ptr = staging.p;
+  *ld = cols;
+  return KUCD_OK;
+}
+
+template <typename F>
+static int by_dtype(const kucd_tensor* t, F&& f) {
+  if (t->dtype_code == KUCD_DT_FLOAT) return f(static_cast<float*>(nullptr));
+  if (t->dtype_code == KUCD_DT_BFLOAT) return f(static_cast<__nv_bfloat16*>(nullptr));
+  return f(static_cast<uint8_t*>(nullptr));
+}
+
+// caller rows -> bf16 planes in `dst` (rows [0,n) of dst).  nparts: planes to write.
+static int ingest_rows(kucd_ctx* ctx, const kucd_tensor* t, int64_t r0, int64_t n, const Planes& dst, int nparts,
+                       int* inexact_flag_dev) {
+  if (n == 0) return KUCD_OK;
+  const void* src;
+  int64_t ld;
+  KU_TRY(fetch_rows(ctx, t, r0, n, ctx->stage_in, &src, &ld));
+  const int64_t groups = n * (dst.ld / 8);
+  const int grid = grid_for(ctx, groups, 256);
+  by_dtype(t, [&](auto* tag) {
+    using T = std::remove_pointer_t<decltype(tag)>;
+    ingest_kernel<T><<<grid, 256, 0, ctx->stream>>>(static_cast<const T*>(src), ld, n, t->shape[1], dst.p[0], dst.p[1],
+                                                    dst.p[2], dst.ld, nparts, inexact_flag_dev);
+    return 0;
+  });
+  ctx->tm.aux_launches++;
+  CU_TRY(cudaGetLastError());
+  return KUCD_OK;
+}
+
+// device rows -> caller tensor rows [r0, r0+n)
+static int deliver_planes(kucd_ctx* ctx, const Planes& src, int64_t n, kucd_tensor* out, int64_t r0) {
+  if (n == 0) return KUCD_OK;
+  const int es = elem_size(out);
+  const int64_t cols = out->shape[1];
+  char* dst = static_cast<char*>(out->data) + r0 * out->strides[0] * es;
+  void* kdst = dst;
+  int64_t kld = out->strides[0];
+  if (!on_device(out)) {
+    KU_TRY(ctx->stage_out.ensure(static_cast<size_t>(n) * cols * es));
+    kdst = ctx->stage_out.p;
+    kld = cols;
+  }
+  const int grid = grid_for(ctx, n * cols, 256);
+  by_dtype(out, [&](auto* tag) {
+    using T = std::remove_pointer_t<decltype(tag)>;
+    export_kernel<T><<<grid, 256, 0, ctx->stream>>>(src.p[0], src.mid(), src.lo(), src.ld, n, cols, static_cast<T*>(kdst),
+                                                    kld);
+    return 0;
+  });
+  ctx->tm.aux_launches++;
+  CU_TRY(cudaGetLastError());
+  if (!on_device(out)) {
+    CU_TRY(cudaMemcpy2DAsync(dst, out->strides[0] * es, kdst, cols * es, cols * es, n, cudaMemcpyDeviceToHost,
+                             ctx->stream));
+    ctx->tm.d2h_bytes += n * cols * es;
+    CU_TRY(cudaStreamSynchronize(ctx->stream));  // stage_out is reused by the next delivery
+  }
+  return KUCD_OK;
+}
+
+static int deliver_f32(kucd_ctx* ctx, const float* src, int64_t ld, int64_t n, kucd_tensor* out, int64_t r0) {
+  if (n == 0) return KUCD_OK;
+  const int es = elem_size(out);
+  const int64_t cols = out->shape[1];
+  char* dst = static_cast<char*>(out->data) + r0 * out->strides[0] * es;
+  if (cols == 1 && ld == 1 && out->strides[0] == 1 && out->dtype_code == KUCD_DT_FLOAT) {  // a plain vector
+    CU_TRY(cudaMemcpyAsync(dst, src, n * 4, cudaMemcpyDefault, ctx->stream));
+    if (!on_device(out)) ctx->tm.d2h_bytes += n * 4;
+    CU_TRY(cudaStreamSynchronize(ctx->stream));
+    return KUCD_OK;
+  }
+  if (!on_device(out) && out->dtype_code == KUCD_DT_FLOAT) {  // straight strided copy
+    CU_TRY(cudaMemcpy2DAsync(dst, out->strides[0] * es, src, ld * 4, cols * 4, n, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->tm.d2h_bytes += n * cols * 4;
+    CU_TRY(cudaStreamSynchronize(ctx->stream));
+    return KUCD_OK;
+  }
+  void* kdst = dst;
+  int64_t kld = out->strides[0];
+  if (!on_device(out)) {
+    KU_TRY(ctx->stage_out.ensure(static_cast<size_t>(n) * cols * es));
+    kdst = ctx->stage_out.p;
+    kld = cols;
+  }
+  const int grid = grid_for(ctx, n * cols, 256);
+  by_dtype(out, [&](auto* tag) {
+    using T = std::remove_pointer_t<decltype(tag)>;
+    export_f32_kernel<T><<<grid, 256, 0, ctx->stream>>>(src, ld, n, cols, static_cast<T*>(kdst), kld);
+    return 0;
+  });
+  ctx->tm.aux_launches++;
+  CU_TRY(cudaGetLastError());
+  if (!on_device(out)) {
+    CU_TRY(cudaMemcpy2DAsync(dst, out->strides[0] * es, kdst, cols * es, cols * es, n, cudaMemcpyDeviceToHost,
+                             ctx->stream));
+    ctx->tm.d2h_bytes += n * cols * es;
+    CU_TRY(cudaStreamSynchronize(ctx->stream));
+  }
+  return KUCD_OK;
+}
+
+// injected uniforms: float32 rows on the device
+static int fetch_u(kucd_ctx* ctx, const kucd_tensor* u, int64_t r0, int64_t n, int64_t cols, const float** ptr,
+                   int64_t* ld) {
+  *ptr = nullptr;
+  *ld = 0;
+  if (u == nullptr) return KUCD_OK;
+  KU_TRY(check_tensor(ctx, u, -1, cols, "injected draws", true));
+  if (u->shape[0] < r0 + n) return fail(KUCD_ERR_SHAPE_MISMATCH, "injected draws have too few rows");
+  const void* p;
+  KU_TRY(fetch_rows(ctx, u, r0, n, ctx->stage_u, &p, ld));
+  *ptr = static_cast<const float*>(p);
+  return KUCD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// contractions
+// ------------------------------------------------------------------------------------------------
+// term pairs (ia, ib) with ia + ib <= 2: the products that matter at fp32 precision.  Smallest terms
+// first: the tensor core truncates when it aligns an addend to the running fp32 accumulator, so the
+// 2^-16 and 2^-8 terms are summed while the accumulator is still small and only the leading hi*hi
+// products are added at full magnitude.
+static int term_pairs(int na, int nb, int (*out)[2], int only_order = -1) {
+  int n = 0;
+  for (int s = 2; s >= 0; --s) {
+    if (only_order >= 0 && s != only_order) continue;
+    for (int ia = 0; ia <= s; ++ia) {
+      const int ib = s - ia;
+      if (ia < na && ib < nb) {
+        out[n][0] = ia;
+        out[n][1] = ib;
+        ++n;
+      }
+    }
+  }
+  return n;
+}
+
+struct EpiArgs {
+  int epi = kEpiSample;
+  Planes out;                  // state / probability planes
+  float* out_f32 = nullptr;    // optional fp32 copy (probabilities or raw)
+  int64_t ld_f32 = 0;
+  const float* u = nullptr;    // injected draws
+  int64_t ld_u = 0;
+  float* colsum = nullptr;
+  float colsum_sign = 1.f;
+  float* rowsum = nullptr;
+  uint64_t draw = 0;
+  uint64_t draw_stride = 0;
+  int64_t row0 = 0;
+  int32_t m_valid = -1;
+  const StepDyn* dyn = nullptr;
+  bool a_dyn = false;  // A rows are offset by dyn->row_off (A is a whole data set)
+};
+
+// forward: (rows,V).W + c -> (rows,H) ; backward: (rows,H).W^T + b -> (rows,V)
+static int project(kucd_rbm* r, bool forward, const Planes& a, int64_t rows, const EpiArgs& e) {
+  kucd_ctx* ctx = r->ctx;
+  GemmOperands ops;
+  ops.a_mn = false;
+  ops.b_mn = forward;  // W is (V,H) row-major: (K,N) forward, (N,K) backward
+  ops.M = rows;
+  ops.N = forward ? r->H : r->V;
+  ops.K = forward ? r->V : r->H;
+  int pairs[9][2];
+  const int np = term_pairs(a.n, r->wparts, pairs);
+  ops.num_seg = np;
+  uint32_t dyn_mask = 0;
+  for (int s = 0; s < np; ++s) {
+    ops.a[s] = MatView{a.p[pairs[s][0]], a.rows, a.cols, a.ld};
+    ops.b[s] = MatView{r->Wp.buf[pairs[s][1]].p, r->V, r->H, r->ldH};
+    if (e.a_dyn) dyn_mask |= 1u << s;
+  }
+  GemmParams p;
+  memset(&p, 0, sizeof p);
+  p.bias = forward ? r->c32.as<float>() : r->b32.as<float>();
+  p.out_bf16 = e.out.p[0];
+  p.out_mid = (e.out.n == 3) ? e.out.p[1] : nullptr;
+  p.out_lo = (e.out.n == 3) ? e.out.p[2] : nullptr;
+  p.ld_bf16 = e.out.ld;
+  p.out_f32 = e.out_f32;
+  p.ld_f32 = e.ld_f32;
+  p.u_inject = e.u;
+  p.ld_u = e.ld_u;
+  p.colsum = e.colsum;
+  p.colsum_sign = e.colsum_sign;
+  p.rowsum = e.rowsum;
+  p.seed = r->seed;
+  p.draw = e.draw;
+  p.draw_stride = e.draw_stride;
+  p.row0 = e.row0;
+  p.m_valid = e.m_valid < 0 ? static_cast<int32_t>(rows) : e.m_valid;
+  p.dyn = e.dyn;
+  p.dyn_rows = e.dyn != nullptr ? 1 : 0;
+  p.a_dyn_mask = dyn_mask;
+  std::string err;
+  if (!launch_gemm(p, ops, e.epi, ctx->num_sms, ctx->stream, &err, 0, r->compute == KUCD_COMPUTE_F32X3))
+    return fail(KUCD_ERR_CUDA, "%s", err.c_str());
+  ctx->tm.gemm_launches++;
+  return KUCD_OK;
+}
+
+// dW = v0^T h0 - vk^T hk   (rbm.py:125-126): contraction over the minibatch rows, every operand read
+// in place (MN-major descriptors), both phases accumulated into the same tensor-memory tile.
+static int delta_w(kucd_rbm* r, const Planes& v0, const Planes& h0, const Planes& vk, const Planes& hk, int64_t rows,
+                   const StepDyn* dyn, bool v0_dyn) {
+  kucd_ctx* ctx = r->ctx;
+  GemmOperands ops;
+  ops.a_mn = true;
+  ops.b_mn = true;
+  ops.M = r->V;
+  ops.N = r->H;
+  ops.K = rows;
+  int pairs[9][2];
+  int ns = 0;
+  uint32_t neg = 0, dyn_mask = 0;
+  for (int order = 2; order >= 0; --order) {  // small terms of both phases first, see term_pairs
+    int np = term_pairs(v0.n, h0.n, pairs, order);
+    if (ns + np > kMaxSeg) return fail(KUCD_ERR_INVALID_ARG, "too many operand terms");
+    for (int s = 0; s < np; ++s, ++ns) {
+      ops.a[ns] = MatView{v0.p[pairs[s][0]], v0.rows, v0.cols, v0.ld};
+      ops.b[ns] = MatView{h0.p[pairs[s][1]], h0.rows, h0.cols, h0.ld};
+      if (v0_dyn) dyn_mask |= 1u << ns;
+    }
+    np = term_pairs(vk.n, hk.n, pairs, order);
+    if (ns + np > kMaxSeg) return fail(KUCD_ERR_INVALID_ARG, "too many operand terms");
+    for (int s = 0; s < np; ++s, ++ns) {
+      ops.a[ns] = MatView{vk.p[pairs[s][0]], vk.rows, vk.cols, vk.ld};
+      ops.b[ns] = MatView{hk.p[pairs[s][1]], hk.rows, hk.cols, hk.ld};
+      neg |= 1u << ns;
+    }
+  }
+  ops.num_seg = ns;
+  ops.neg_mask = neg;
+  GemmParams p;
+  memset(&p, 0, sizeof p);
+  p.out_f32 = r->dW();
+  p.ld_f32 = r->ldH;
+  p.m_valid = static_cast<int32_t>(r->V);
+  p.dyn = dyn;
+  p.a_dyn_mask = dyn_mask;
+  std::string err;
+  if (!launch_gemm(p, ops, kEpiRaw, ctx->num_sms, ctx->stream, &err, 0, r->compute == KUCD_COMPUTE_F32X3))
+    return fail(KUCD_ERR_CUDA, "%s", err.c_str());
+  ctx->tm.gemm_launches++;
+  return KUCD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// workspaces
+// ------------------------------------------------------------------------------------------------
+static int ensure_workspace(kucd_rbm* r, int64_t rows) {
+  if (rows <= r->cap) return KUCD_OK;
+  const int64_t cap = round_up(rows, 128);
+  const int np = 3;  // keep all term planes available: Gaussian visibles and fp32 probabilities need them
+  KU_TRY(r->vin.ensure(cap, r->ldV, r->compute == KUCD_COMPUTE_F32X3 ? np : 1));
+  KU_TRY(r->h0.ensure(cap, r->ldH, 1));
+  KU_TRY(r->hk.ensure(cap, r->ldH, r->compute == KUCD_COMPUTE_F32X3 ? np : 1));
+  KU_TRY(r->vk.ensure(cap, r->ldV,
+                      (r->compute == KUCD_COMPUTE_F32X3 && r->mode == KUCD_MODE_VISIBLE_GAUSSIAN) ? np : 1));
+  KU_TRY(r->fe0.ensure(cap * 4));
+  KU_TRY(r->fe1.ensure(cap * 4));
+  KU_TRY(r->sp0.ensure(cap * 4));
+  KU_TRY(r->sp1.ensure(cap * 4));
+  KU_TRY(r->pstage.ensure(static_cast<size_t>(cap) * std::max(r->ldV, r->ldH) * 4));
+  r->cap = cap;
+  // a captured graph holds the old pointers
+  if (r->graph_exec != nullptr) {
+    cudaGraphExecDestroy(r->graph_exec);
+    cudaGraphDestroy(r->graph);
+    r->graph_exec = nullptr;
+    r->graph = nullptr;
+  }
+  return KUCD_OK;
+}
+
+static int vis_parts_out(const kucd_rbm* r) {
+  return (r->compute == KUCD_COMPUTE_F32X3 && r->mode == KUCD_MODE_VISIBLE_GAUSSIAN) ? 3 : 1;
+}
+static int prob_parts_out(const kucd_rbm* r) { return r->compute == KUCD_COMPUTE_F32X3 ? 3 : 1; }
+
+// ------------------------------------------------------------------------------------------------
+// the CD step (all launches on ctx->stream; capturable)
+// ------------------------------------------------------------------------------------------------
+struct StepInject {
+  const float* u_h[KUCD_MAX_K] = {};
+  int64_t ld_h[KUCD_MAX_K] = {};
+  const float* u_v[KUCD_MAX_K] = {};
+  int64_t ld_v[KUCD_MAX_K] = {};
+  const float* u_hc = nullptr;
+  int64_t ld_hc = 0;
+};
+
+static int apply_update(kucd_rbm* r, const kucd_hparams* hp, int64_t rows_global) {
+  kucd_ctx* ctx = r->ctx;
+  const float scale = hp->normalize ? 1.0f / static_cast<float>(std::max<int64_t>(rows_global, 1)) : 1.0f;
+  const bool use_mom = hp->momentum != 0.f;
+  if (use_mom) {
+    KU_TRY(r->mW.ensure(static_cast<size_t>(r->V) * r->ldH * 4, true));
+    KU_TRY(r->mb.ensure(r->ldVb() * 4, true));
+    KU_TRY(r->mc.ensure(r->ldHb() * 4, true));
+  }
+  if (hp->update_mask & KUCD_UPDATE_W) {
+    const int64_t n4 = r->V * r->ldH / 4;
+    update_w_kernel<<<grid_for(ctx, n4, 256), 256, 0, ctx->stream>>>(
+        r->W32.as<float>(), r->dW(), use_mom ? r->mW.as<float>() : nullptr, r->Wp.buf[0].as<__nv_bfloat16>(),
+        r->wparts == 3 ? r->Wp.buf[1].as<__nv_bfloat16>() : nullptr,
+        r->wparts == 3 ? r->Wp.buf[2].as<__nv_bfloat16>() : nullptr, n4, hp->lr, scale, hp->momentum,
+        hp->weight_decay);
+    ctx->tm.aux_launches++;
+  }
+  if (hp->update_mask & KUCD_UPDATE_C) {
+    update_bias_kernel<<<(r->H + 255) / 256, 256, 0, ctx->stream>>>(r->c32.as<float>(), r->dc(),
+                                                                     use_mom ? r->mc.as<float>() : nullptr, r->H, hp->lr,
+                                                                     scale, hp->momentum);
+    ctx->tm.aux_launches++;
+  }
+  if (hp->update_mask & KUCD_UPDATE_B) {
+    update_bias_kernel<<<(r->V + 255) / 256, 256, 0, ctx->stream>>>(r->b32.as<float>(), r->db(),
+                                                                     use_mom ? r->mb.as<float>() : nullptr, r->V, hp->lr,
+                                                                     scale, hp->momentum);
+    ctx->tm.aux_launches++;
+  }
+  CU_TRY(cudaGetLastError());
+  return KUCD_OK;
+}
+
+// v0: the minibatch operand (rows [0,batch) of it, or - with v0_dyn - the rows at dyn->row_off of a data set)
+static int enqueue_cd(kucd_rbm* r, const Planes& v0, int64_t batch, const kucd_hparams* hp, const StepInject* inj,
+                      int64_t global_row0, uint64_t step, const StepDyn* dyn, bool v0_dyn) {
+  kucd_ctx* ctx = r->ctx;
+  const int k = hp->k;
+  const bool gaussian = r->mode == KUCD_MODE_VISIBLE_GAUSSIAN;
+  const int epi_h = gaussian ? kEpiReluSample : kEpiSample;
+  const int epi_v = gaussian ? kEpiGaussian : kEpiSample;
+  const uint64_t draw0 = step * 64;
+  const uint64_t stride = dyn != nullptr ? 64 : 0;
+
+  CU_TRY(cudaMemsetAsync(r->db(), 0, (r->ldVb() + r->ldHb()) * 4, ctx->stream));
+  {  // db += sum_rows v0   (rbm.py:134)
+    dim3 grid(static_cast<unsigned>((r->V / 2 + 1 + 127) / 128), static_cast<unsigned>((batch + 63) / 64));
+    colsum_kernel<<<grid, 128, 0, ctx->stream>>>(v0.p[0], v0.mid(), v0.lo(), v0.ld, 0, static_cast<int32_t>(batch),
+                                                 static_cast<int32_t>(r->V), v0_dyn ? dyn : nullptr, 1.f, r->db());
+    ctx->tm.aux_launches++;
+    CU_TRY(cudaGetLastError());
+  }
+  // rows of the state buffers beyond the valid ones are written as zeros by the epilogues, so the
+  // remainder minibatch contributes nothing to the batch-contracted dW
+  const Planes h0 = r->h0.view(batch, r->H, 1);
+  {
+    EpiArgs e;
+    e.epi = epi_h;
+    e.out = h0;
+    e.u = inj ? inj->u_h[0] : nullptr;
+    e.ld_u = inj ? inj->ld_h[0] : 0;
+    e.colsum = r->dc();
+    e.colsum_sign = 1.f;
+    e.draw = draw0 + 0;
+    e.draw_stride = stride;
+    e.row0 = global_row0;
+    e.dyn = dyn;
+    e.a_dyn = v0_dyn;
+    KU_TRY(project(r, true, v0, batch, e));
+  }
+  const int vparts = vis_parts_out(r);
+  const int pparts = prob_parts_out(r);
+  Planes hcur = h0;
+  if (hp->persistent) {
+    // negative chain starts at the stored fantasy particles
+    const Planes ch = r->chains.view(batch, r->V, r->last_vk_parts);
+    EpiArgs e;
+    e.epi = epi_h;
+    e.out = r->hk.view(batch, r->H, 1);
+    e.u = inj ? inj->u_hc : nullptr;
+    e.ld_u = inj ? inj->ld_hc : 0;
+    e.draw = draw0 + 1;
+    e.draw_stride = stride;
+    e.row0 = global_row0;
+    e.dyn = dyn;
+    KU_TRY(project(r, true, ch, batch, e));
+    hcur = e.out;
+  }
+  Planes vk = r->vk.view(batch, r->V, vparts);
+  Planes hk = r->hk.view(batch, r->H, 1);
+  for (int t = 1; t <= k; ++t) {
+    {
+      EpiArgs e;
+      e.epi = epi_v;
+      e.out = vk;
+      e.u = inj ? inj->u_v[t] : nullptr;
+      e.ld_u = inj ? inj->ld_v[t] : 0;
+      if (t == k) {
+        e.colsum = r->db();
+        e.colsum_sign = -1.f;
+      }
+      e.draw = draw0 + 2 * t;
+      e.draw_stride = stride;
+      e.row0 = global_row0;
+      e.dyn = dyn;
+      KU_TRY(project(r, false, hcur, batch, e));
+    }
+    {
+      EpiArgs e;
+      const bool last = t == k;
+      e.epi = last ? kEpiProb : epi_h;  // rbm.py:124: the final hidden term is the probability
+      hk = r->hk.view(batch, r->H, last ? pparts : 1);
+      e.out = hk;
+      e.u = (!last && inj) ? inj->u_h[t] : nullptr;
+      e.ld_u = (!last && inj) ? inj->ld_h[t] : 0;
+      if (last) {
+        e.colsum = r->dc();
+        e.colsum_sign = -1.f;
+      }
+      e.draw = draw0 + 2 * t + 1;
+      e.draw_stride = stride;
+      e.row0 = global_row0;
+      e.dyn = dyn;
+      KU_TRY(project(r, true, vk, batch, e));
+      hcur = hk;
+    }
+  }
+  KU_TRY(delta_w(r, v0, h0, vk, hk, batch, dyn, v0_dyn));
+  r->last_rows = batch;
+  r->last_vk_parts = vparts;
+  r->last_hk_parts = pparts;
+
+  if (hp->persistent) {
+    for (int i = 0; i < vparts; ++i) {
+      copy_rows_kernel<<<grid_for(ctx, batch * (r->ldV / 8), 256), 256, 0, ctx->stream>>>(
+          vk.p[i], r->chains.buf[i].as<__nv_bfloat16>(), r->ldV, static_cast<int32_t>(batch), dyn);
+      ctx->tm.aux_launches++;
+    }
+    CU_TRY(cudaGetLastError());
+  }
+  if (ctx->comm != nullptr) {
+    const int rc = g_nccl.AllReduce(r->grad.p, r->grad.p, static_cast<size_t>(r->grad_elems()), /*ncclFloat32*/ 7,
+                                    /*ncclSum*/ 0, ctx->comm, ctx->stream);
+    if (rc != 0) return fail(KUCD_ERR_NCCL, "ncclAllReduce: %s", g_nccl.GetErrorString(rc));
+    ctx->tm.allreduce_calls++;
+  }
+  return KUCD_OK;
+}
+
+static int free_energy_into(kucd_rbm* r, const Planes& v, int64_t rows, float* sp, float* out, const StepDyn* dyn,
+                            bool v_dyn) {
+  kucd_ctx* ctx = r->ctx;
+  CU_TRY(cudaMemsetAsync(sp, 0, rows * 4, ctx->stream));
+  EpiArgs e;
+  e.epi = kEpiFreeEnergy;
+  e.rowsum = sp;
+  e.dyn = dyn;
+  e.a_dyn = v_dyn;
+  KU_TRY(project(r, true, v, rows, e));
+  const int threads = 256;
+  const int blocks = static_cast<int>((rows * 32 + threads - 1) / threads);
+  free_energy_finish_kernel<<<blocks, threads, 0, ctx->stream>>>(v.p[0], v.mid(), v.lo(), v.ld, 0,
+                                                                 static_cast<int32_t>(rows), static_cast<int32_t>(r->V),
+                                                                 v_dyn ? dyn : nullptr, r->b32.as<float>(), sp, out);
+  ctx->tm.aux_launches++;
+  CU_TRY(cudaGetLastError());
+  return KUCD_OK;
+}
+
+// rbm.py:225-233: fe = F(v); fresh chain v -> h -> v'; fe_p = F(v'); stats[0] = mean|fe - fe_p|
+static int enqueue_score(kucd_rbm* r, const Planes& v0, int64_t rows, const float* u_h, int64_t ld_h, const float* u_v,
+                         int64_t ld_v, int64_t row0) {
+  kucd_ctx* ctx = r->ctx;
+  const bool gaussian = r->mode == KUCD_MODE_VISIBLE_GAUSSIAN;
+  const uint64_t draw = (1ull << 62) | (2 * r->score_draws++);
+  KU_TRY(free_energy_into(r, v0, rows, r->sp0.as<float>(), r->fe0.as<float>(), nullptr, false));
+  const Planes h = r->h0.view(rows, r->H, 1);
+  {
+    EpiArgs e;
+    e.epi = gaussian ? kEpiReluSample : kEpiSample;
+    e.out = h;
+    e.u = u_h;
+    e.ld_u = ld_h;
+    e.draw = draw;
+    e.row0 = row0;
+    KU_TRY(project(r, true, v0, rows, e));
+  }
+  const Planes vn = r->vk.view(rows, r->V, vis_parts_out(r));
+  {
+    EpiArgs e;
+    e.epi = gaussian ? kEpiGaussian : kEpiSample;
+    e.out = vn;
+    e.u = u_v;
+    e.ld_u = ld_v;
+    e.draw = draw + 1;
+    e.row0 = row0;
+    KU_TRY(project(r, false, h, rows, e));
+  }
+  KU_TRY(free_energy_into(r, vn, rows, r->sp1.as<float>(), r->fe1.as<float>(), nullptr, false));
+  score_kernel<<<1, 1024, 0, ctx->stream>>>(r->fe0.as<float>(), r->fe1.as<float>(), static_cast<int32_t>(rows), nullptr,
+                                            r->stats.as<float>());
+  ctx->tm.aux_launches++;
+  CU_TRY(cudaGetLastError());
+  return KUCD_OK;
+}
+
+static int enqueue_recon(kucd_rbm* r, const Planes& v0, int64_t rows) {
+  kucd_ctx* ctx = r->ctx;
+  float* acc = r->stats.as<float>() + 8;
+  CU_TRY(cudaMemsetAsync(acc, 0, 4, ctx->stream));
+  const Planes vk = r->vk.view(rows, r->V, r->last_vk_parts);
+  recon_kernel<<<grid_for(ctx, rows * r->V, 256), 256, 0, ctx->stream>>>(
+      v0.p[0], v0.mid(), v0.lo(), v0.ld, 0, vk.p[0], vk.mid(), vk.lo(), vk.ld, static_cast<int32_t>(rows),
+      static_cast<int32_t>(r->V), nullptr, acc);
+  recon_finish_kernel<<<1, 1, 0, ctx->stream>>>(acc, static_cast<int32_t>(rows), static_cast<int32_t>(r->V), nullptr,
+                                                r->stats.as<float>());
+  ctx->tm.aux_launches += 2;
+  CU_TRY(cudaGetLastError());
+  return KUCD_OK;
+}
+
+// caller batch -> vin planes; returns the live term count
+static int ingest_batch(kucd_rbm* r, const kucd_tensor* v, int64_t r0, int64_t n, Planes* out) {
+  kucd_ctx* ctx = r->ctx;
+  const bool x3 = r->compute == KUCD_COMPUTE_F32X3;
+  Planes dst = r->vin.view(n, r->V, x3 ? 3 : 1);
+  int live = 1;
+  const bool may_be_inexact = x3 && v->dtype_code == KUCD_DT_FLOAT;
+  if (may_be_inexact) CU_TRY(cudaMemsetAsync(r->flag.p, 0, 4, ctx->stream));
+  KU_TRY(ingest_rows(ctx, v, r0, n, dst, x3 ? 3 : 1, may_be_inexact ? r->flag.as<int>() : nullptr));
+  if (may_be_inexact) {
+    int flag = 0;
+    CU_TRY(cudaMemcpyAsync(&flag, r->flag.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(cudaStreamSynchronize(ctx->stream));
+    live = flag ? 3 : 1;
+  }
+  dst.n = live;
+  *out = dst;
+  return KUCD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+int kucd_abi_version(void) { return KUCD_ABI_VERSION; }
+const char* kucd_last_error(void) { return g_err.c_str(); }
+
+int kucd_ctx_create(kucd_ctx** out, int device_id, uint64_t seed) {
+  if (out == nullptr) return fail(KUCD_ERR_INVALID_ARG, "out is NULL");
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(KUCD_ERR_CUDA, "no CUDA device is visible; the engine has no CPU path");
+  }
+  if (device_id < 0 || device_id >= ndev) return fail(KUCD_ERR_INVALID_ARG, "device %d of %d", device_id, ndev);
+  cudaDeviceProp prop;
+  CU_TRY(cudaGetDeviceProperties(&prop, device_id));
+  if (prop.major != 10)
+    return fail(KUCD_ERR_NOT_SM100, "device %d (%s) is sm_%d%d; the kernels are sm_100a only", device_id, prop.name,
+                prop.major, prop.minor);
+  CU_TRY(cudaSetDevice(device_id));
+  kucd_ctx* c = new (std::nothrow) kucd_ctx();
+  if (c == nullptr) return fail(KUCD_ERR_INVALID_ARG, "out of host memory");
+  c->device = device_id;
+  c->num_sms = prop.multiProcessorCount;
+  c->seed = seed;
+  CU_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CU_TRY(cudaEventCreate(&c->ev0));
+  CU_TRY(cudaEventCreate(&c->ev1));
+  *out = c;
+  return KUCD_OK;
+}
+
+int kucd_ctx_destroy(kucd_ctx* ctx) {
+  if (ctx == nullptr) return KUCD_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->comm != nullptr && g_nccl.CommDestroy != nullptr) g_nccl.CommDestroy(ctx->comm);
+  ctx->stage_in.release();
+  ctx->stage_u.release();
+  ctx->stage_out.release();
+  cudaEventDestroy(ctx->ev0);
+  cudaEventDestroy(ctx->ev1);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return KUCD_OK;
+}
+
+int kucd_sync(kucd_ctx* ctx) {
+  if (ctx == nullptr) return fail(KUCD_ERR_INVALID_ARG, "ctx is NULL");
+  CU_TRY(cudaStreamSynchronize(ctx->stream));
+  return KUCD_OK;
+}
+
+int kucd_get_timings(kucd_ctx* ctx, kucd_timings* out, int reset) {
+  if (ctx == nullptr || out == nullptr) return fail(KUCD_ERR_INVALID_ARG, "NULL argument");
+  *out = ctx->tm;
+  if (reset) ctx->tm = kucd_timings{};
+  return KUCD_OK;
+}
+
+int kucd_ctx_stream(kucd_ctx* ctx, void** stream_out) {
+  if (ctx == nullptr || stream_out == nullptr) return fail(KUCD_ERR_INVALID_ARG, "NULL argument");
+  *stream_out = ctx->stream;
+  return KUCD_OK;
+}
+
+int kucd_comm_unique_id(void* id128) {
+  if (id128 == nullptr) return fail(KUCD_ERR_INVALID_ARG, "id128 is NULL");
+  KU_TRY(nccl_load());
+  NcclUid id;
+  const int rc = g_nccl.GetUniqueId(&id);
+  if (rc != 0) return fail(KUCD_ERR_NCCL, "ncclGetUniqueId: %s", g_nccl.GetErrorString(rc));
+  memcpy(id128, &id, 128);
+  return KUCD_OK;
+}
+
+int kucd_ctx_comm_init(kucd_ctx* ctx, const void* id128, int rank, int world) {
+  if (ctx == nullptr || id128 == nullptr) return fail(KUCD_ERR_INVALID_ARG, "NULL argument");
+  if (world < 1 || rank < 0 || rank >= world) return fail(KUCD_ERR_INVALID_ARG, "rank %d of %d", rank, world);
+  if (world == 1) {
+    ctx->rank = 0;
+    ctx->world = 1;
+    return KUCD_OK;
+  }
+  KU_TRY(nccl_load());
+  CU_TRY(cudaSetDevice(ctx->device));
+  NcclUid id;
+  memcpy(&id, id128, 128);
+  void* comm = nullptr;
+  const int rc = g_nccl.CommInitRank(&comm, world, id, rank);
+  if (rc != 0) return fail(KUCD_ERR_NCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString(rc));
+  ctx->comm = comm;
+  ctx->rank = rank;
+  ctx->world = world;
+  return KUCD_OK;
+}
+
+// ---- model ---------------------------------------------------------------------------------------
+int kucd_rbm_create(kucd_ctx* ctx, int64_t V, int64_t H, int mode, int compute, kucd_rbm** out) {
+  if (ctx == nullptr || out == nullptr) return fail(KUCD_ERR_INVALID_ARG, "NULL argument");
+  *out = nullptr;
+  if (V <= 0 || H <= 0 || V > (1 << 24) || H > (1 << 24))
+    return fail(KUCD_ERR_INVALID_ARG, "bad dimensions V=%lld H=%lld", (long long)V, (long long)H);
+  if (mode != KUCD_MODE_VISIBLE_BERNOULLI && mode != KUCD_MODE_VISIBLE_GAUSSIAN)
+    return fail(KUCD_ERR_INVALID_ARG, "mode %d is not implemented (rbm.py:16 leaves MODE_COMPLEX as a TODO too)", mode);
+  if (compute != KUCD_COMPUTE_BF16 && compute != KUCD_COMPUTE_F32X3)
+    return fail(KUCD_ERR_INVALID_ARG, "compute %d", compute);
+  CU_TRY(cudaSetDevice(ctx->device));
+  kucd_rbm* r = new (std::nothrow) kucd_rbm();
+  if (r == nullptr) return fail(KUCD_ERR_INVALID_ARG, "out of host memory");
+  r->ctx = ctx;
+  r->seed = ctx->seed;
+  r->V = V;
+  r->H = H;
+  r->ldV = round_up(V, 64);
+  r->ldH = round_up(H, 64);
+  r->mode = mode;
+  r->compute = compute;
+  r->wparts = compute == KUCD_COMPUTE_F32X3 ? 3 : 1;
+  int rc = KUCD_OK;
+  auto T = [&](int x) {
+    if (rc == KUCD_OK) rc = x;
+  };
+  T(r->W32.ensure(static_cast<size_t>(V) * r->ldH * 4, true));
+  T(r->Wp.ensure(V, r->ldH, r->wparts));
+  for (int i = 0; i < r->wparts && rc == KUCD_OK; ++i)
+    if (cudaMemset(r->Wp.buf[i].p, 0, r->Wp.buf[i].bytes) != cudaSuccess) rc = fail(KUCD_ERR_CUDA, "memset");
+  T(r->b32.ensure(r->ldVb() * 4, true));
+  T(r->c32.ensure(r->ldHb() * 4, true));
+  T(r->grad.ensure(r->grad_elems() * 4, true));
+  T(r->stats.ensure(64, true));
+  T(r->flag.ensure(16, true));
+  T(r->dyn.ensure(sizeof(StepDyn), true));
+  if (rc != KUCD_OK) {
+    kucd_rbm_destroy(r);
+    return rc;
+  }
+  *out = r;
+  return KUCD_OK;
+}
+
+int kucd_rbm_destroy(kucd_rbm* r) {
+  if (r == nullptr) return KUCD_OK;
+  cudaSetDevice(r->ctx->device);
+  cudaStreamSynchronize(r->ctx->stream);
+  if (r->graph_exec != nullptr) cudaGraphExecDestroy(r->graph_exec);
+  if (r->graph != nullptr) cudaGraphDestroy(r->graph);
+  for (DevBuf* b : {&r->W32, &r->b32, &r->c32, &r->mW, &r->mb, &r->mc, &r->grad, &r->fe0, &r->fe1, &r->sp0, &r->sp1,
+                    &r->pstage, &r->stats, &r->flag, &r->dyn})
+    b->release();
+  for (PlaneBuf* p : {&r->Wp, &r->vin, &r->h0, &r->hk, &r->vk, &r->chains}) p->release();
+  delete r;
+  return KUCD_OK;
+}
+
+static int refresh_planes(kucd_rbm* r) {
+  kucd_ctx* ctx = r->ctx;
+  const int64_t n4 = r->V * r->ldH / 4;
+  refresh_planes_kernel<<<grid_for(ctx, n4, 256), 256, 0, ctx->stream>>>(
+      r->W32.as<float>(), r->Wp.buf[0].as<__nv_bfloat16>(), r->wparts == 3 ? r->Wp.buf[1].as<__nv_bfloat16>() : nullptr,
+      r->wparts == 3 ? r->Wp.buf[2].as<__nv_bfloat16>() : nullptr, n4);
+  ctx->tm.aux_launches++;
+  CU_TRY(cudaGetLastError());
+  return KUCD_OK;
+}
+
+int kucd_rbm_set_params(kucd_rbm* r, const kucd_tensor* W, const kucd_tensor* b, const kucd_tensor* c) {
+  if (r == nullptr) return fail(KUCD_ERR_INVALID_ARG, "rbm is NULL");
+  kucd_ctx* ctx = r->ctx;
+  CU_TRY(cudaSetDevice(ctx->device));
+  if (W != nullptr) {
+    KU_TRY(check_tensor(ctx, W, r->V, r->H, "rbm_weight", true));
+    CU_TRY(cudaMemcpy2DAsync(r->W32.p, r->ldH * 4, W->data, W->strides[0] * 4, r->H * 4, r->V, cudaMemcpyDefault,
+                             ctx->stream));
+    KU_TRY(refresh_planes(r));
+  }
+  if (b != nullptr) {
+    const kucd_tensor m = as_matrix(b);
+    KU_TRY(check_tensor(ctx, &m, 1, r->V, "rbm_visible_bias", true));
+    CU_TRY(cudaMemcpyAsync(r->b32.p, m.data, r->V * 4, cudaMemcpyDefault, ctx->stream));
+  }
+  if (c != nullptr) {
+    const kucd_tensor m = as_matrix(c);
+    KU_TRY(check_tensor(ctx, &m, 1, r->H, "rbm_hidden_bias", true));
+    CU_TRY(cudaMemcpyAsync(r->c32.p, m.data, r->H * 4, cudaMemcpyDefault, ctx->stream));
+  }
+  CU_TRY(cudaStreamSynchronize(ctx->stream));
+  return KUCD_OK;
+}
+
+int kucd_rbm_set_seed(kucd_rbm* r, uint64_t seed, uint64_t step_count) {
+  if (r == nullptr) return fail(KUCD_ERR_INVALID_ARG, "rbm is NULL");
+  r->seed = seed;
+  r->step_count = step_count;
+  r->infer_draws = 0;
+  r->score_draws = 0;
+  return KUCD_OK;
+}
+
+int kucd_rbm_get_params(kucd_rbm* r, kucd_tensor* W, kucd_tensor* b, kucd_tensor* c) {
+  if (r == nullptr) return fail(KUCD_ERR_INVALID_ARG, "rbm is NULL");
+  kucd_ctx* ctx = r->ctx;
+  CU_TRY(cudaSetDevice(ctx->device));
+  if (W != nullptr) {
+    KU_TRY(check_tensor(ctx, W, r->V, r->H, "rbm_weight", true));
+    CU_TRY(cudaMemcpy2DAsync(W->data, W->strides[0] * 4, r->W32.p, r->ldH * 4, r->H * 4, r->V, cudaMemcpyDefault,
+                             ctx->stream));
+  }
+  if (b != nullptr) {
+    const kucd_tensor m = as_matrix(b);
+    KU_TRY(check_tensor(ctx, &m, 1, r->V, "rbm_visible_bias", true));
+    CU_TRY(cudaMemcpyAsync(m.data, r->b32.p, r->V * 4, cudaMemcpyDefault, ctx->stream));
+  }
+  if (c != nullptr) {
+    const kucd_tensor m = as_matrix(c);
+    KU_TRY(check_tensor(ctx, &m, 1, r->H, "rbm_hidden_bias", true));
+    CU_TRY(cudaMemcpyAsync(m.data, r->c32.p, r->H * 4, cudaMemcpyDefault, ctx->stream));
+  }
+  CU_TRY(cudaStreamSynchronize(ctx->stream));
+  return KUCD_OK;
+}
+
+// ---- inference -------------------------------------------------------------------------------------
+static const int64_t kChunkRows = 32768;
+
+// forward = transform (rbm.py:45-48), !forward = inv_transform (rbm.py:51-54)
+static int sample_api(kucd_rbm* r, bool forward, const kucd_tensor* in, kucd_tensor* s_out, kucd_tensor* p_out,
+                      const kucd_tensor* u) {
+  if (r == nullptr) return fail(KUCD_ERR_INVALID_ARG, "rbm is NULL");
+  kucd_ctx* ctx = r->ctx;
+  CU_TRY(cudaSetDevice(ctx->device));
+  const int64_t K = forward ? r->V : r->H, N = forward ? r->H : r->V;
+  KU_TRY(check_tensor(ctx, in, -1, K, forward ? "v" : "h"));
+  const int64_t rows = in->shape[0];
+  if (s_out != nullptr) KU_TRY(check_tensor(ctx, s_out, rows, N, "sample output"));
+  if (p_out != nullptr) KU_TRY(check_tensor(ctx, p_out, rows, N, "probability output"));
+  if (u != nullptr) KU_TRY(check_tensor(ctx, u, rows, N, "injected draws", true));
+  const bool gaussian = r->mode == KUCD_MODE_VISIBLE_GAUSSIAN;
+  const uint64_t draw = (1ull << 63) | r->infer_draws++;
+  const bool x3 = r->compute == KUCD_COMPUTE_F32X3;
+  for (int64_t r0 = 0; r0 < rows; r0 += kChunkRows) {
+    const int64_t n = std::min(kChunkRows, rows - r0);
+    KU_TRY(ensure_workspace(r, n));
+    Planes a;
+    if (forward) {
+      KU_TRY(ingest_batch(r, in, r0, n, &a));
+    } else {
+      // hidden states are 0/1 in every mode: one plane
+      a = r->hk.view(n, r->H, 1);
+      if (x3 && in->dtype_code == KUCD_DT_FLOAT) {
+        Planes a3 = r->hk.view(n, r->H, 3);
+        CU_TRY(cudaMemsetAsync(r->flag.p, 0, 4, ctx->stream));
+        KU_TRY(ingest_rows(ctx, in, r0, n, a3, 3, r->flag.as<int>()));
+        int flag = 0;
+        CU_TRY(cudaMemcpyAsync(&flag, r->flag.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CU_TRY(cudaStreamSynchronize(ctx->stream));
+        a = a3;
+        a.n = flag ? 3 : 1;
+      } else {
+        KU_TRY(ingest_rows(ctx, in, r0, n, a, 1, nullptr));
+      }
+    }
+    EpiArgs e;
+    if (forward) {
+      e.epi = gaussian ? kEpiReluSample : kEpiSample;
+      e.out = r->h0.view(n, r->H, 1);
+    } else {
+      e.epi = gaussian ? kEpiGaussian : kEpiSample;
+      e.out = r->vk.view(n, r->V, vis_parts_out(r));
+    }
+    if (p_out != nullptr) {
+      e.out_f32 = r->pstage.as<float>();
+      e.ld_f32 = forward ? r->ldH : r->ldV;
+    }
+    KU_TRY(fetch_u(ctx, u, r0, n, N, &e.u, &e.ld_u));
+    e.draw = draw;
+    e.row0 = r0;
+    KU_TRY(project(r, forward, a, n, e));
+    if (s_out != nullptr) KU_TRY(deliver_planes(ctx, e.out, n, s_out, r0));
+    if (p_out != nullptr) KU_TRY(deliver_f32(ctx, e.out_f32, e.ld_f32, n, p_out, r0));
+  }
+  CU_TRY(cudaStreamSynchronize(ctx->stream));
+  return KUCD_OK;
+}
+
+int kucd_rbm_transform(kucd_rbm* r, const kucd_tensor* v, kucd_tensor* h_out, kucd_tensor* p_out,
+                       const kucd_tensor* u) {
+  return sample_api(r, true, v, h_out, p_out, u);
+}
+
+int kucd_rbm_inv_transform(kucd_rbm* r, const kucd_tensor* h, kucd_tensor* v_out, kucd_tensor* p_out,
+                           const kucd_tensor* u) {
+  return sample_api(r, false, h, v_out, p_out, u);
+}
+
+int kucd_rbm_free_energy(kucd_rbm* r, const kucd_tensor* v, kucd_tensor* fe_out) {
+  if (r == nullptr) return fail(KUCD_ERR_INVALID_ARG, "rbm is NULL");
+  kucd_ctx* ctx = r->ctx;
+  CU_TRY(cudaSetDevice(ctx->device));
+  KU_TRY(check_tensor(ctx, v, -1, r->V, "v"));
+  const int64_t rows = v->shape[0];
+  if (fe_out == nullptr) return fail(KUCD_ERR_INVALID_ARG, "fe_out is NULL");
+  kucd_tensor fo = *fe_out;  // (rows,) or (rows,1) float32
+  if (!(fo.dtype_code == KUCD_DT_FLOAT && fo.bits == 32)) return fail(KUCD_ERR_UNSUPPORTED_DTYPE, "fe_out must be float32");
+  if (fo.shape[0] != rows || fo.shape[1] != 1)
+    return fail(KUCD_ERR_SHAPE_MISMATCH, "fe_out has shape (%lld, %lld), expected (%lld, 1)", (long long)fo.shape[0],
+                (long long)fo.shape[1], (long long)rows);
+  for (int64_t r0 = 0; r0 < rows; r0 += kChunkRows) {
+    const int64_t n = std::min(kChunkRows, rows - r0);
+    KU_TRY(ensure_workspace(r, n));
+    Planes a;
+    KU_TRY(ingest_batch(r, v, r0, n, &a));
+    KU_TRY(free_energy_into(r, a, n, r->sp0.as<float>(), r->fe0.as<float>(), nullptr, false));
+    KU_TRY(deliver_f32(ctx, r->fe0.as<float>(), 1, n, &fo, r0));
+  }
+  CU_TRY(cudaStreamSynchronize(ctx->stream));
+  return KUCD_OK;
+}
+
+// ---- training --------------------------------------------------------------------------------------
+static int check_hparams(const kucd_hparams* hp) {
+  if (hp == nullptr) return fail(KUCD_ERR_INVALID_ARG, "hparams is NULL");
+  if (hp->k < 1 || hp->k >= KUCD_MAX_K) return fail(KUCD_ERR_INVALID_ARG, "k = %d is outside [1, %d)", hp->k, KUCD_MAX_K);
+  if ((hp->update_mask & ~KUCD_UPDATE_ALL) != 0) return fail(KUCD_ERR_INVALID_ARG, "update_mask %d", hp->update_mask);
+  return KUCD_OK;
+}
+
+static int ensure_chains(kucd_rbm* r, int64_t rows) {
+  if (r->n_chains >= rows) return KUCD_OK;
+  return fail(KUCD_ERR_INVALID_ARG,
+              "persistent CD needs %lld chains but %lld are set (kucd_rbm_set_chains first)", (long long)rows,
+              (long long)r->n_chains);
+}
+
+static int read_stats(kucd_rbm* r, kucd_step_stats* stats, int64_t rows) {
+  float host[4];
+  CU_TRY(cudaMemcpyAsync(host, r->stats.p, sizeof host, cudaMemcpyDeviceToHost, r->ctx->stream));
+  CU_TRY(cudaStreamSynchronize(r->ctx->stream));
+  r->ctx->tm.d2h_bytes += sizeof host;
+  stats->score = host[0];
+  stats->recon_err = host[1];
+  stats->fe_mean = host[2];
+  stats->rows = static_cast<int32_t>(rows);
+  return KUCD_OK;
+}
+
+int kucd_rbm_cd_step(kucd_rbm* r, const kucd_tensor* v_batch, const kucd_hparams* hp, const kucd_inject* inj,
+                     int64_t global_row0, kucd_step_stats* stats) {
+  if (r == nullptr) return fail(KUCD_ERR_INVALID_ARG, "rbm is NULL");
+  kucd_ctx* ctx = r->ctx;
+  CU_TRY(cudaSetDevice(ctx->device));
+  KU_TRY(check_hparams(hp));
+  KU_TRY(check_tensor(ctx, v_batch, -1, r->V, "v_batch"));
+  const int64_t rows = v_batch->shape[0];
+  if (rows == 0) return KUCD_OK;  // an empty minibatch updates nothing
+  if (rows > (1 << 22)) return fail(KUCD_ERR_INVALID_ARG, "minibatch of %lld rows", (long long)rows);
+  KU_TRY(ensure_workspace(r, rows));
+  if (hp->persistent) KU_TRY(ensure_chains(r, rows));
+  Planes v0;
+  KU_TRY(ingest_batch(r, v_batch, 0, rows, &v0));
+
+  // injected draws: each node's array is staged to the device up front
+  StepInject si;
+  std::vector<DevBuf> keep;
+  if (inj != nullptr) {
+    keep.resize(2 * KUCD_MAX_K + 1);
+    int slot = 0;
+    auto stage = [&](const kucd_tensor* u, int64_t cols, const float** p, int64_t* ld) -> int {
+      if (u == nullptr) return KUCD_OK;
+      KU_TRY(check_tensor(ctx, u, rows, cols, "injected draws", true));
+      const void* q;
+      KU_TRY(fetch_rows(ctx, u, 0, rows, keep[slot++], &q, ld));
+      *p = static_cast<const float*>(q);
+      return KUCD_OK;
+    };
+    for (int t = 0; t < hp->k; ++t) KU_TRY(stage(inj->u_h[t], r->H, &si.u_h[t], &si.ld_h[t]));
+    for (int t = 1; t <= hp->k; ++t) KU_TRY(stage(inj->u_v[t], r->V, &si.u_v[t], &si.ld_v[t]));
+    KU_TRY(stage(inj->u_hc, r->H, &si.u_hc, &si.ld_hc));
+  }
+  KU_TRY(enqueue_cd(r, v0, rows, hp, inj ? &si : nullptr, global_row0, r->step_count, nullptr, false));
+  r->step_count++;
+  if (stats != nullptr && hp->want_stats) KU_TRY(enqueue_recon(r, v0, rows));
+  KU_TRY(apply_update(r, hp, rows * ctx->world));
+  if (stats != nullptr && hp->want_stats) {
+    // the score chain reuses the state buffers, which is why last_stats must be read before asking for stats
+    KU_TRY(enqueue_score(r, v0, rows, nullptr, 0, nullptr, 0, global_row0));
+    KU_TRY(read_stats(r, stats, rows));
+  }
+  const bool host_in = !on_device(v_batch) || inj != nullptr;
+  if (host_in) CU_TRY(cudaStreamSynchronize(ctx->stream));
+  for (auto& b : keep) b.release();
+  return KUCD_OK;
+}
+
+int kucd_rbm_score(kucd_rbm* r, const kucd_tensor* v_batch, const kucd_tensor* u_h, const kucd_tensor* u_v,
+                   float* score_out) {
+  if (r == nullptr || score_out == nullptr) return fail(KUCD_ERR_INVALID_ARG, "NULL argument");
+  kucd_ctx* ctx = r->ctx;
+  CU_TRY(cudaSetDevice(ctx->device));
+  KU_TRY(check_tensor(ctx, v_batch, -1, r->V, "v_batch"));
+  const int64_t rows = v_batch->shape[0];
+  if (rows == 0) {
+    *score_out = 0.f;
+    return KUCD_OK;
+  }
+  KU_TRY(ensure_workspace(r, rows));
+  Planes v0;
+  KU_TRY(ingest_batch(r, v_batch, 0, rows, &v0));
+  DevBuf ku_h, ku_v;
+  const float *ph = nullptr, *pv = nullptr;
+  int64_t ldh = 0, ldv = 0;
+  if (u_h != nullptr) {
+    KU_TRY(check_tensor(ctx, u_h, rows, r->H, "u_h", true));
+    const void* q;
+    KU_TRY(fetch_rows(ctx, u_h, 0, rows, ku_h, &q, &ldh));
+    ph = static_cast<const float*>(q);
+  }
+  if (u_v != nullptr) {
+    KU_TRY(check_tensor(ctx, u_v, rows, r->V, "u_v", true));
+    const void* q;
+    KU_TRY(fetch_rows(ctx, u_v, 0, rows, ku_v, &q, &ldv));
+    pv = static_cast<const float*>(q);
+  }
+  KU_TRY(enqueue_score(r, v0, rows, ph, ldh, pv, ldv, 0));
+  kucd_step_stats st;
+  KU_TRY(read_stats(r, &st, rows));
+  *score_out = st.score;
+  ku_h.release();
+  ku_v.release();
+  return KUCD_OK;
+}
+
+int kucd_rbm_last_stats(kucd_rbm* r, kucd_tensor* dW, kucd_tensor* db, kucd_tensor* dc, kucd_tensor* h_pos,
+                        kucd_tensor* v_neg, kucd_tensor* h_neg) {
+  if (r == nullptr) return fail(KUCD_ERR_INVALID_ARG, "rbm is NULL");
+  kucd_ctx* ctx = r->ctx;
+  CU_TRY(cudaSetDevice(ctx->device));
+  const int64_t rows = r->last_rows;
+  if (dW != nullptr) {
+    KU_TRY(check_tensor(ctx, dW, r->V, r->H, "dW", true));
+    CU_TRY(cudaMemcpy2DAsync(dW->data, dW->strides[0] * 4, r->dW(), r->ldH * 4, r->H * 4, r->V, cudaMemcpyDefault,
+                             ctx->stream));
+  }
+  if (db != nullptr) {
+    const kucd_tensor m = as_matrix(db);
+    KU_TRY(check_tensor(ctx, &m, 1, r->V, "db", true));
+    CU_TRY(cudaMemcpyAsync(m.data, r->db(), r->V * 4, cudaMemcpyDefault, ctx->stream));
+  }
+  if (dc != nullptr) {
+    const kucd_tensor m = as_matrix(dc);
+    KU_TRY(check_tensor(ctx, &m, 1, r->H, "dc", true));
+    CU_TRY(cudaMemcpyAsync(m.data, r->dc(), r->H * 4, cudaMemcpyDefault, ctx->stream));
+  }
+  if (h_pos != nullptr) {
+    KU_TRY(check_tensor(ctx, h_pos, rows, r->H, "h_pos"));
+    KU_TRY(deliver_planes(ctx, r->h0.view(rows, r->H, 1), rows, h_pos, 0));
+  }
+  if (v_neg != nullptr) {
+    KU_TRY(check_tensor(ctx, v_neg, rows, r->V, "v_neg"));
+    KU_TRY(deliver_planes(ctx, r->vk.view(rows, r->V, r->last_vk_parts), rows, v_neg, 0));
+  }
+  if (h_neg != nullptr) {
+    KU_TRY(check_tensor(ctx, h_neg, rows, r->H, "h_neg"));
+    KU_TRY(deliver_planes(ctx, r->hk.view(rows, r->H, r->last_hk_parts), rows, h_neg, 0));
+  }
+  CU_TRY(cudaStreamSynchronize(ctx->stream));
+  return KUCD_OK;
+}
+
+int kucd_rbm_set_chains(kucd_rbm* r, const kucd_tensor* v_chains) {
+  if (r == nullptr) return fail(KUCD_ERR_INVALID_ARG, "rbm is NULL");
+  kucd_ctx* ctx = r->ctx;
+  CU_TRY(cudaSetDevice(ctx->device));
+  KU_TRY(check_tensor(ctx, v_chains, -1, r->V, "v_chains"));
+  const int64_t n = v_chains->shape[0];
+  const int np = vis_parts_out(r);
+  CU_TRY(cudaStreamSynchronize(ctx->stream));
+  KU_TRY(r->chains.ensure(round_up(std::max<int64_t>(n, 1), 128), r->ldV, np));
+  for (int i = 0; i < np; ++i) CU_TRY(cudaMemsetAsync(r->chains.buf[i].p, 0, r->chains.buf[i].bytes, ctx->stream));
+  KU_TRY(ingest_rows(ctx, v_chains, 0, n, r->chains.view(n, r->V, np), np, nullptr));
+  r->n_chains = n;
+  r->last_vk_parts = np;
+  if (r->graph_exec != nullptr) {  // chain buffers may have moved
+    cudaGraphExecDestroy(r->graph_exec);
+    cudaGraphDestroy(r->graph);
+    r->graph_exec = nullptr;
+    r->graph = nullptr;
+  }
+  CU_TRY(cudaStreamSynchronize(ctx->stream));
+  return KUCD_OK;
+}
+
+int kucd_rbm_get_chains(kucd_rbm* r, kucd_tensor* v_chains) {
+  if (r == nullptr) return fail(KUCD_ERR_INVALID_ARG, "rbm is NULL");
+  kucd_ctx* ctx = r->ctx;
+  CU_TRY(cudaSetDevice(ctx->device));
+  KU_TRY(check_tensor(ctx, v_chains, r->n_chains, r->V, "v_chains"));
+  KU_TRY(deliver_planes(ctx, r->chains.view(r->n_chains, r->V, vis_parts_out(r)), r->n_chains, v_chains, 0));
+  CU_TRY(cudaStreamSynchronize(ctx->stream));
+  return KUCD_OK;
+}
+
+// ---- data sets -------------------------------------------------------------------------------------
+int kucd_dataset_create(kucd_ctx* ctx, const kucd_tensor* data, int compute, kucd_dataset** out) {
+  if (ctx == nullptr || out == nullptr) return fail(KUCD_ERR_INVALID_ARG, "NULL argument");
+  *out = nullptr;
+  CU_TRY(cudaSetDevice(ctx->device));
+  KU_TRY(check_tensor(ctx, data, -1, -1, "data"));
+  const int64_t rows = data->shape[0], dim = data->shape[1];
+  if (dim <= 0) return fail(KUCD_ERR_INVALID_ARG, "data has no columns");
+  kucd_dataset* ds = new (std::nothrow) kucd_dataset();
+  if (ds == nullptr) return fail(KUCD_ERR_INVALID_ARG, "out of host memory");
+  ds->ctx = ctx;
+  ds->rows = rows;
+  ds->dim = dim;
+  const bool x3 = compute == KUCD_COMPUTE_F32X3 && data->dtype_code == KUCD_DT_FLOAT;
+  const int np = x3 ? 3 : 1;
+  int rc = ds->planes.ensure(std::max<int64_t>(rows, 1), round_up(dim, 64), np);
+  DevBuf flag;
+  if (rc == KUCD_OK) rc = flag.ensure(16, true);
+  for (int64_t r0 = 0; r0 < rows && rc == KUCD_OK; r0 += kChunkRows) {
+    const int64_t n = std::min(kChunkRows, rows - r0);
+    Planes dst = ds->planes.view(n, dim, np);
+    for (int i = 0; i < np; ++i) dst.p[i] += r0 * dst.ld;
+    rc = ingest_rows(ctx, data, r0, n, dst, np, x3 ? flag.as<int>() : nullptr);
+    // the host staging buffer is reused by the next chunk
+    if (rc == KUCD_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = fail(KUCD_ERR_CUDA, "sync failed");
+  }
+  int live = 1;
+  if (rc == KUCD_OK && x3) {
+    int f = 0;
+    if (cudaMemcpy(&f, flag.p, 4, cudaMemcpyDeviceToHost) != cudaSuccess) rc = fail(KUCD_ERR_CUDA, "flag read failed");
+    live = f ? 3 : 1;
+  }
+  flag.release();
+  if (rc != KUCD_OK) {
+    ds->planes.release();
+    delete ds;
+    return rc;
+  }
+  ds->nparts = live;
+  *out = ds;
+  return KUCD_OK;
+}
+
+int kucd_dataset_destroy(kucd_dataset* ds) {
+  if (ds == nullptr) return KUCD_OK;
+  cudaSetDevice(ds->ctx->device);
+  cudaStreamSynchronize(ds->ctx->stream);
+  ds->planes.release();
+  delete ds;
+  return KUCD_OK;
+}
+
+int kucd_dataset_shape(kucd_dataset* ds, int64_t* rows, int64_t* dim) {
+  if (ds == nullptr) return fail(KUCD_ERR_INVALID_ARG, "dataset is NULL");
+  if (rows != nullptr) *rows = ds->rows;
+  if (dim != nullptr) *dim = ds->dim;
+  return KUCD_OK;
+}
+
+int kucd_dataset_read(kucd_dataset* ds, kucd_tensor* out) {
+  if (ds == nullptr) return fail(KUCD_ERR_INVALID_ARG, "dataset is NULL");
+  kucd_ctx* ctx = ds->ctx;
+  CU_TRY(cudaSetDevice(ctx->device));
+  KU_TRY(check_tensor(ctx, out, ds->rows, ds->dim, "out"));
+  for (int64_t r0 = 0; r0 < ds->rows; r0 += kChunkRows) {
+    const int64_t n = std::min(kChunkRows, ds->rows - r0);
+    Planes src = ds->view();
+    for (int i = 0; i < 3; ++i)
+      if (src.p[i] != nullptr) src.p[i] += r0 * src.ld;
+    KU_TRY(deliver_planes(ctx, src, n, out, r0));
+  }
+  CU_TRY(cudaStreamSynchronize(ctx->stream));
+  return KUCD_OK;
+}
+
+int kucd_rbm_fit_epoch(kucd_rbm* r, kucd_dataset* ds, int64_t batch, const kucd_hparams* hp, int64_t global_row0,
+                       kucd_epoch_stats* stats) {
+  if (r == nullptr || ds == nullptr) return fail(KUCD_ERR_INVALID_ARG, "NULL argument");
+  kucd_ctx* ctx = r->ctx;
+  CU_TRY(cudaSetDevice(ctx->device));
+  KU_TRY(check_hparams(hp));
+  if (ds->ctx != ctx) return fail(KUCD_ERR_INVALID_ARG, "data set belongs to another context");
+  if (ds->dim != r->V)
+    return fail(KUCD_ERR_SHAPE_MISMATCH, "data set has %lld columns, the RBM %lld visible units", (long long)ds->dim,
+                (long long)r->V);
+  if (batch < 1 || batch > (1 << 22)) return fail(KUCD_ERR_INVALID_ARG, "batch_size %lld", (long long)batch);
+  const int64_t N = ds->rows;
+  const int64_t steps = (N + batch - 1) / batch;  // rbm.py:110-111
+  if (stats != nullptr) memset(stats, 0, sizeof *stats);
+  if (steps == 0) return KUCD_OK;
+  KU_TRY(ensure_workspace(r, batch));
+  if (hp->persistent) KU_TRY(ensure_chains(r, std::min(batch, N)));
+  if (hp->momentum != 0.f) {  // allocate outside the capture
+    KU_TRY(r->mW.ensure(static_cast<size_t>(r->V) * r->ldH * 4, true));
+    KU_TRY(r->mb.ensure(r->ldVb() * 4, true));
+    KU_TRY(r->mc.ensure(r->ldHb() * 4, true));
+  }
+  if (hp->normalize && N % batch != 0)
+    return fail(KUCD_ERR_INVALID_ARG, "normalize=mean under fit_epoch needs the row count to divide by batch_size");
+
+  GraphKey key;
+  key.ds = ds;
+  key.batch = batch;
+  key.global_row0 = global_row0;
+  key.ds_rows = N;
+  key.ds_parts = ds->nparts;
+  key.hp = *hp;
+  key.hp.want_stats = 0;
+  const Planes v0 = ds->view();
+  StepDyn* dyn = r->dyn.as<StepDyn>();
+  if (r->graph_exec == nullptr || !(r->graph_key == key)) {
+    if (r->graph_exec != nullptr) {
+      cudaGraphExecDestroy(r->graph_exec);
+      cudaGraphDestroy(r->graph);
+      r->graph_exec = nullptr;
+      r->graph = nullptr;
+    }
+    CU_TRY(cudaStreamSynchronize(ctx->stream));
+    CU_TRY(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed));
+    int rc = enqueue_cd(r, v0, batch, hp, nullptr, global_row0, 0, dyn, true);
+    if (rc == KUCD_OK) rc = apply_update(r, hp, batch * ctx->world);
+    if (rc == KUCD_OK) {
+      advance_dyn_kernel<<<1, 1, 0, ctx->stream>>>(dyn, static_cast<int32_t>(batch), N);
+      ctx->tm.aux_launches++;
+    }
+    cudaGraph_t g = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(ctx->stream, &g);
+    if (rc != KUCD_OK) {
+      if (g != nullptr) cudaGraphDestroy(g);
+      return rc;
+    }
+    if (ce != cudaSuccess) return fail(KUCD_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
+    cudaGraphExec_t ge = nullptr;
+    const cudaError_t ie = cudaGraphInstantiate(&ge, g, 0);
+    if (ie != cudaSuccess) {
+      cudaGraphDestroy(g);
+      return fail(KUCD_ERR_CUDA, "graph instantiation failed: %s", cudaGetErrorString(ie));
+    }
+    r->graph = g;
+    r->graph_exec = ge;
+    r->graph_key = key;
+  }
+  set_dyn_kernel<<<1, 1, 0, ctx->stream>>>(dyn, 0, static_cast<int32_t>(std::min(batch, N)), r->step_count);
+  ctx->tm.aux_launches++;
+  CU_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
+  for (int64_t s = 0; s < steps; ++s) CU_TRY(cudaGraphLaunch(r->graph_exec, ctx->stream));
+  CU_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
+  ctx->tm.graph_launches += steps;
+  r->step_count += steps;
+  r->last_rows = batch;
+  if (stats != nullptr) {
+    stats->steps = steps;
+    stats->rows = N;
+    if (hp->want_stats) {
+      // score of the last minibatch with a fresh chain, as the reference prints it (rbm.py:227-234)
+      const int64_t r0 = (steps - 1) * batch, n = N - r0;
+      Planes last = v0;
+      for (int i = 0; i < 3; ++i)
+        if (last.p[i] != nullptr) last.p[i] += r0 * last.ld;
+      last.rows = n;
+      KU_TRY(enqueue_recon(r, last, n));
+      KU_TRY(enqueue_score(r, last, n, nullptr, 0, nullptr, 0, global_row0));
+      kucd_step_stats st;
+      KU_TRY(read_stats(r, &st, n));
+      stats->last_score = st.score;
+      stats->last_recon_err = st.recon_err;
+    }
+    CU_TRY(cudaEventSynchronize(ctx->ev1));
+    CU_TRY(cudaEventElapsedTime(&stats->device_ms, ctx->ev0, ctx->ev1));
+  }
+  return KUCD_OK;
+}
+
+// dbn.py:55 / :73 / :94 on a device-resident data set
+static int map_dataset(kucd_rbm* r, bool forward, kucd_dataset* in, kucd_dataset** out) {
+  if (r == nullptr || in == nullptr || out == nullptr) return fail(KUCD_ERR_INVALID_ARG, "NULL argument");
+  kucd_ctx* ctx = r->ctx;
+  *out = nullptr;
+  CU_TRY(cudaSetDevice(ctx->device));
+  const int64_t K = forward ? r->V : r->H, N = forward ? r->H : r->V;
+  if (in->dim != K)
+    return fail(KUCD_ERR_SHAPE_MISMATCH, "data set has %lld columns, expected %lld", (long long)in->dim, (long long)K);
+  kucd_dataset* ds = new (std::nothrow) kucd_dataset();
+  if (ds == nullptr) return fail(KUCD_ERR_INVALID_ARG, "out of host memory");
+  ds->ctx = ctx;
+  ds->rows = in->rows;
+  ds->dim = N;
+  const bool gaussian = r->mode == KUCD_MODE_VISIBLE_GAUSSIAN;
+  const int np = forward ? 1 : vis_parts_out(r);
+  ds->nparts = np;
+  int rc = ds->planes.ensure(std::max<int64_t>(in->rows, 1), round_up(N, 64), np);
+  if (rc == KUCD_OK && in->rows > 0) {
+    EpiArgs e;
+    e.epi = forward ? (gaussian ? kEpiReluSample : kEpiSample) : (gaussian ? kEpiGaussian : kEpiSample);
+    e.out = ds->view();
+    e.draw = (1ull << 63) | r->infer_draws++;
+    rc = project(r, forward, in->view(), in->rows, e);
+  }
+  if (rc != KUCD_OK) {
+    ds->planes.release();
+    delete ds;
+    return rc;
+  }
+  *out = ds;
+  return KUCD_OK;
+}
+
+int kucd_rbm_transform_dataset(kucd_rbm* r, kucd_dataset* in, kucd_dataset** out) {
+  return map_dataset(r, true, in, out);
+}
+int kucd_rbm_inv_transform_dataset(kucd_rbm* r, kucd_dataset* in, kucd_dataset** out) {
+  return map_dataset(r, false, in, out);
+}
+
+}  // extern "C"

@@ -83,10 +83,13 @@ inline int pick_bn(int64_t M, int64_t N, int num_sms) {
   return 64;
 }
 
-template <int BN, bool A_MN, bool B_MN, int EPI>
+constexpr int kPreciseBN = 128;  // precise mode keeps BN/2 = 64 partial sums per epilogue thread in registers
+constexpr int kPreciseCH = 4;    // k-blocks (of 64) per tensor-memory accumulation piece
+
+template <int BN, bool A_MN, bool B_MN, int EPI, int CH = 0>
 inline cudaError_t launch_one(const GemmParams& p, int num_sms, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
-  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, EPI>;
+  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, EPI, CH>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
@@ -112,56 +115,59 @@ constexpr bool combo_built() {
   return true;  // sample / prob: both directions
 }
 
-template <int BN, bool A_MN, bool B_MN, int EPI>
+template <int BN, bool A_MN, bool B_MN, int EPI, int CH>
 inline cudaError_t launch_if_built(const GemmParams& p, int num_sms, cudaStream_t s) {
   if constexpr (combo_built<EPI, A_MN, B_MN>())
-    return launch_one<BN, A_MN, B_MN, EPI>(p, num_sms, s);
+    return launch_one<BN, A_MN, B_MN, EPI, CH>(p, num_sms, s);
   else
     return cudaErrorInvalidValue;
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, int CH>
 inline cudaError_t launch_major(const GemmParams& p, bool a_mn, bool b_mn, int num_sms, cudaStream_t s) {
-  if (!a_mn && !b_mn) return launch_if_built<BN, false, false, EPI>(p, num_sms, s);
-  if (!a_mn && b_mn) return launch_if_built<BN, false, true, EPI>(p, num_sms, s);
-  if (a_mn && b_mn) return launch_if_built<BN, true, true, EPI>(p, num_sms, s);
-  return launch_if_built<BN, true, false, EPI>(p, num_sms, s);
+  if (!a_mn && !b_mn) return launch_if_built<BN, false, false, EPI, CH>(p, num_sms, s);
+  if (!a_mn && b_mn) return launch_if_built<BN, false, true, EPI, CH>(p, num_sms, s);
+  if (a_mn && b_mn) return launch_if_built<BN, true, true, EPI, CH>(p, num_sms, s);
+  return launch_if_built<BN, true, false, EPI, CH>(p, num_sms, s);
 }
 
 template <int EPI>
-inline cudaError_t launch_bn(const GemmParams& p, int bn, bool a_mn, bool b_mn, int num_sms, cudaStream_t s) {
+inline cudaError_t launch_bn(const GemmParams& p, int bn, bool precise, bool a_mn, bool b_mn, int num_sms,
+                             cudaStream_t s) {
+  if (precise) return launch_major<kPreciseBN, EPI, kPreciseCH>(p, a_mn, b_mn, num_sms, s);
   switch (bn) {
-    case 256: return launch_major<256, EPI>(p, a_mn, b_mn, num_sms, s);
-    case 128: return launch_major<128, EPI>(p, a_mn, b_mn, num_sms, s);
-    default: return launch_major<64, EPI>(p, a_mn, b_mn, num_sms, s);
+    case 256: return launch_major<256, EPI, 0>(p, a_mn, b_mn, num_sms, s);
+    case 128: return launch_major<128, EPI, 0>(p, a_mn, b_mn, num_sms, s);
+    default: return launch_major<64, EPI, 0>(p, a_mn, b_mn, num_sms, s);
   }
 }
 
 // Fill the tensor maps / shape fields of `p` from `ops` (epilogue fields are the caller's) and launch.
 inline bool launch_gemm(GemmParams& p, const GemmOperands& ops, int epi, int num_sms, cudaStream_t stream,
-                        std::string* err, int force_bn = 0) {
+                        std::string* err, int force_bn = 0, bool precise = false) {
   if (ops.num_seg < 1 || ops.num_seg > kMaxSeg) {
     if (err) *err = "bad segment count";
     return false;
   }
-  const int bn = force_bn ? force_bn : pick_bn(ops.M, ops.N, num_sms);
+  const int bn = precise ? kPreciseBN : (force_bn ? force_bn : pick_bn(ops.M, ops.N, num_sms));
   p.num_seg = ops.num_seg;
   p.neg_mask = ops.neg_mask;
   p.M = static_cast<int32_t>(ops.M);
   p.N = static_cast<int32_t>(ops.N);
   p.kblocks = static_cast<int32_t>((ops.K + kBlockK - 1) / kBlockK);
+  if (p.m_valid <= 0 || p.m_valid > p.M) p.m_valid = p.M;
   for (int s = 0; s < ops.num_seg; ++s) {
     if (!make_tmap_bf16(&p.tm_a[s], ops.a[s], ops.a_mn ? 64u : static_cast<uint32_t>(kBlockM), err)) return false;
     if (!make_tmap_bf16(&p.tm_b[s], ops.b[s], ops.b_mn ? 64u : static_cast<uint32_t>(bn), err)) return false;
   }
   cudaError_t e;
   switch (epi) {
-    case kEpiRaw: e = launch_bn<kEpiRaw>(p, bn, ops.a_mn, ops.b_mn, num_sms, stream); break;
-    case kEpiSample: e = launch_bn<kEpiSample>(p, bn, ops.a_mn, ops.b_mn, num_sms, stream); break;
-    case kEpiProb: e = launch_bn<kEpiProb>(p, bn, ops.a_mn, ops.b_mn, num_sms, stream); break;
-    case kEpiFreeEnergy: e = launch_bn<kEpiFreeEnergy>(p, bn, ops.a_mn, ops.b_mn, num_sms, stream); break;
-    case kEpiReluSample: e = launch_bn<kEpiReluSample>(p, bn, ops.a_mn, ops.b_mn, num_sms, stream); break;
-    case kEpiGaussian: e = launch_bn<kEpiGaussian>(p, bn, ops.a_mn, ops.b_mn, num_sms, stream); break;
+    case kEpiRaw: e = launch_bn<kEpiRaw>(p, bn, precise, ops.a_mn, ops.b_mn, num_sms, stream); break;
+    case kEpiSample: e = launch_bn<kEpiSample>(p, bn, precise, ops.a_mn, ops.b_mn, num_sms, stream); break;
+    case kEpiProb: e = launch_bn<kEpiProb>(p, bn, precise, ops.a_mn, ops.b_mn, num_sms, stream); break;
+    case kEpiFreeEnergy: e = launch_bn<kEpiFreeEnergy>(p, bn, precise, ops.a_mn, ops.b_mn, num_sms, stream); break;
+    case kEpiReluSample: e = launch_bn<kEpiReluSample>(p, bn, precise, ops.a_mn, ops.b_mn, num_sms, stream); break;
+    case kEpiGaussian: e = launch_bn<kEpiGaussian>(p, bn, precise, ops.a_mn, ops.b_mn, num_sms, stream); break;
     default:
       if (err) *err = "bad epilogue mode";
       return false;

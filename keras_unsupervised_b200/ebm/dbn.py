@@ -1,0 +1,82 @@
+"""ku.ebm.DBN, same surface: a stack of RBMs trained greedily, layer by layer.
+
+Mirrors /root/reference/ku/ebm/dbn.py (`add_stack` :14, `fit` :34, `transform` :57, `inv_transform`
+:77) with the defects of SURVEY.md 2.3 (D7) resolved as the code intends: the loop variable is used
+instead of the undefined `self.rbm_layer`, the dimension check looks at `_rbm_layers`, and
+`inv_transform` really walks the stack in reverse.  Between layers the data never leaves the GPU: the
+sampled hidden states of layer l (dbn.py:55) are produced as an engine Dataset and consumed as one.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from ..engine import Dataset
+
+# Constants (dbn.py:6-8)
+MODE_VISIBLE_BERNOULLI = 0
+MODE_VISIBLE_GAUSSIAN = 1
+MODE_COMPLEX = 2  # TODO
+
+
+class DBN(object):
+    """Deep belief network."""
+
+    def add_stack(self, rbm_layer):
+        """Add a rbm layer to the dbn stack (dbn.py:14-32)."""
+        if hasattr(self, "_rbm_layers"):
+            prev = self._rbm_layers[-1]
+            prev_out = prev.output_dim
+            next_in = rbm_layer.input_shape[1] if getattr(rbm_layer, "input_shape", None) else None
+            if next_in is not None and int(prev_out) != int(next_in):
+                raise ValueError("A previous RBM layer's output dimension must"
+                                 + "be equal to a next one's input dimension.")  # dbn.py:29-30
+            self._rbm_layers.append(rbm_layer)
+        else:
+            self._rbm_layers = [rbm_layer]
+
+    def _check(self):
+        if hasattr(self, "_rbm_layers") != True:  # noqa: E712  (dbn.py:47-48)
+            raise ValueError("Any rbm layer doesn't exist.")
+
+    def fit(self, V, verbose=1):
+        """Train DBN with the data V (dbn.py:34-55): for each layer, fit, then feed its sampled hidden
+        states of the whole data set to the next layer."""
+        self._check()
+        cur = V[0] if isinstance(V, (list, tuple)) and len(V) == 1 else V
+        cur_owned = False
+        for i, rbm_layer in enumerate(self._rbm_layers):
+            print("Train {0:s}.".format(str(rbm_layer.name)))  # dbn.py:53
+            if not rbm_layer.built:
+                rbm_layer.build((None, int(cur.shape[1])))
+            m = rbm_layer._machine
+            if not isinstance(cur, Dataset) and m.ctx.world == 1:
+                cur, cur_owned = Dataset.from_array(m.ctx, cur, m.compute), True
+            rbm_layer.fit(cur, verbose=verbose)                      # dbn.py:54
+            nxt = None
+            if i + 1 < len(self._rbm_layers):
+                nxt = rbm_layer.transform(cur)                       # dbn.py:55: Dataset in -> Dataset out
+                nxt = nxt[0] if isinstance(nxt, list) else nxt
+            if cur_owned:
+                cur.close()
+            cur, cur_owned = nxt, isinstance(nxt, Dataset)
+        return self
+
+    def transform(self, V):
+        """Transform the visible unit (dbn.py:57-75)."""
+        self._check()
+        V_p = V[0] if isinstance(V, (list, tuple)) and len(V) == 1 else V
+        V_p = V_p.copy() if isinstance(V_p, np.ndarray) else V_p
+        for rbm_layer in self._rbm_layers:
+            out = rbm_layer.transform(V_p)
+            V_p = out[0] if isinstance(out, list) else out
+        return V_p
+
+    def inv_transform(self, H):
+        """Transform the hidden unit (dbn.py:77-96), top layer first."""
+        self._check()
+        H_p = H[0] if isinstance(H, (list, tuple)) and len(H) == 1 else H
+        H_p = H_p.copy() if isinstance(H_p, np.ndarray) else H_p
+        for rbm_layer in reversed(self._rbm_layers):
+            out = rbm_layer.inv_transform(H_p)
+            H_p = out[0] if isinstance(out, list) else out
+        return H_p

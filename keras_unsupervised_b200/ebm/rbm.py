@@ -1,0 +1,268 @@
+"""ku.ebm.RBM, same surface, B200 engine underneath.
+
+Mirrors /root/reference/ku/ebm/rbm.py: constructor `RBM(hps, output_dim, name=None,
+mode=MODE_VISIBLE_GAUSSIAN, **kwargs)` (rbm.py:22), `build` (:29), `call` (:80), `transform` (:88),
+`inv_transform` (:91), `compute_output_shape` (:94), `cal_free_energy` (:97), `fit` (:100),
+`get_config` (:236), attributes `rbm_weight`, `hidden_bias`, `visible_bias` (:30,34,38).  The defects
+that keep the reference from running are resolved the way the surrounding
+code intends: draws take the row count of their input, the hidden draw is (rows, H), the remainder
+minibatch is the remaining rows, `transform`/`inv_transform` stay methods, `get_config` carries `mode`.
+
+`hps` keeps the reference's keys `batch_size`, `epochs`, `lr` (rbm.py:46,110,113,128).  Optional keys,
+whose defaults reproduce the reference: `k` (1), `persistent` (False), `momentum` (0), `weight_decay`
+(0), `normalize` ('sum' | 'mean'), `dtype` ('float32' = fp32-grade three-term contractions | 'bf16'),
+`compat` ('fused': one chain updates W, b, c | 'reference': the three sequential single-parameter
+runs + per-step score of rbm.py:214-234), `seed` (42), `score_every` (0: once per epoch).
+
+Every array method calls libkucd.so; nothing is computed in Python and there is no fallback.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+from .. import _lib as L
+from ..engine import Context, Dataset, Machine
+from ..parallel import shard_rows
+
+# Constants (rbm.py:14-16)
+MODE_VISIBLE_BERNOULLI = 0
+MODE_VISIBLE_GAUSSIAN = 1
+MODE_COMPLEX = 2  # TODO in the reference as well
+
+
+def _unwrap(x):
+    """K.function takes and returns lists of one array (rbm.py:89,211,230); accept both."""
+    if isinstance(x, (list, tuple)) and len(x) == 1:
+        return x[0]
+    return x
+
+
+class RBM(object):
+    """Restricted Boltzmann machine with the reference's API."""
+
+    def __init__(self, hps, output_dim, name=None, mode=MODE_VISIBLE_GAUSSIAN, **kwargs):
+        self.hps = hps
+        self.output_dim = output_dim
+        self.name = name
+        self.mode = mode
+        if mode not in (MODE_VISIBLE_BERNOULLI, MODE_VISIBLE_GAUSSIAN):
+            raise ValueError("mode must be MODE_VISIBLE_BERNOULLI or MODE_VISIBLE_GAUSSIAN "
+                             "(MODE_COMPLEX is a TODO in the reference, rbm.py:16,68-70)")
+        self._context = kwargs.pop("context", None)
+        self.return_list = kwargs.pop("return_list", True)
+        input_shape = kwargs.pop("input_shape", None)
+        input_dim = kwargs.pop("input_dim", None)
+        self._kwargs = kwargs
+        self.built = False
+        self._machine = None
+        self.input_shape = None
+        self.output_shape = None
+        self.history = []
+        if input_shape is not None:
+            self.build((None,) + tuple(input_shape))
+        elif input_dim is not None:
+            self.build((None, int(input_dim)))
+
+    # ---- Keras-layer surface -------------------------------------------------------------------
+    def build(self, input_shape):
+        """rbm.py:29-40: W (V,H), c (H,), b (V,) ~ Keras 'uniform' = U(-0.05, 0.05), float32."""
+        n_visible = int(input_shape[1])
+        ctx = self._context or Context.default()
+        dtype = str(self.hps.get("dtype", "float32")).lower()
+        if dtype in ("float32", "fp32", "f32", "f32x3"):
+            compute = L.COMPUTE_F32X3
+        elif dtype in ("bf16", "bfloat16"):
+            compute = L.COMPUTE_BF16
+        else:
+            raise ValueError("hps['dtype'] must be 'float32' or 'bf16'")
+        seed = int(self.hps.get("seed", 42))
+        self._machine = Machine(ctx, n_visible, int(self.output_dim), int(self.mode), compute, seed=seed)
+        rng = np.random.default_rng(seed)
+        W = rng.uniform(-0.05, 0.05, (n_visible, int(self.output_dim))).astype(np.float32)
+        b = rng.uniform(-0.05, 0.05, n_visible).astype(np.float32)
+        c = rng.uniform(-0.05, 0.05, int(self.output_dim)).astype(np.float32)
+        self._machine.set_params(W, b, c)
+        self.input_shape = (None, n_visible)
+        self.output_shape = (None, int(self.output_dim))
+        self.built = True
+
+    def _ensure_built(self, x):
+        if not self.built:
+            shape = x.shape if not isinstance(x, Dataset) else x.shape
+            self.build((None, int(shape[1])))
+
+    def __call__(self, x):
+        return self.call(x)
+
+    def call(self, x):
+        """rbm.py:80-86: the layer's forward pass is the sampled hidden state."""
+        return _unwrap(self.transform(x))
+
+    def compute_output_shape(self, input_shape):
+        return (input_shape[0], self.output_dim)  # rbm.py:94-95
+
+    def get_config(self):
+        """rbm.py:236-242, plus `mode` (the reference drops it and reloads as Gaussian)."""
+        return {"hps": self.hps, "output_dim": self.output_dim, "name": self.name, "mode": self.mode}
+
+    # ---- parameters: same attribute names as the reference -------------------------------------
+    @property
+    def rbm_weight(self):
+        return self._machine.get_params()[0]
+
+    @rbm_weight.setter
+    def rbm_weight(self, W):
+        self._machine.set_params(W=W)
+
+    @property
+    def visible_bias(self):
+        return self._machine.get_params()[1]
+
+    @visible_bias.setter
+    def visible_bias(self, b):
+        self._machine.set_params(b=b)
+
+    @property
+    def hidden_bias(self):
+        return self._machine.get_params()[2]
+
+    @hidden_bias.setter
+    def hidden_bias(self, c):
+        self._machine.set_params(c=c)
+
+    def get_weights(self):
+        """Keras order of creation: rbm_weight, rbm_hidden_bias, rbm_visible_bias (rbm.py:30,34,38)."""
+        W, b, c = self._machine.get_params()
+        return [W, c, b]
+
+    def set_weights(self, weights):
+        W, c, b = weights
+        self._machine.set_params(W, b, c)
+
+    # ---- inference -----------------------------------------------------------------------------
+    def _wrap(self, out):
+        return [out] if self.return_list else out
+
+    def transform(self, v, u=None):
+        """rbm.py:88-89 -> transform_func (:45-48): h = 1[u < sigmoid(v.W + c)], sampled, float32."""
+        v = _unwrap(v)
+        self._ensure_built(v)
+        if isinstance(v, Dataset):
+            return self._machine.transform_dataset(v)
+        return self._wrap(self._machine.transform(v, u=u))
+
+    def inv_transform(self, h, u=None):
+        """rbm.py:91-92 -> inv_transform_func (:51-54 / :64-67)."""
+        h = _unwrap(h)
+        if not self.built:
+            raise ValueError("inv_transform needs a built RBM (the visible dimension is unknown)")
+        if isinstance(h, Dataset):
+            return self._machine.inv_transform_dataset(h)
+        return self._wrap(self._machine.inv_transform(h, u=u))
+
+    def cal_free_energy(self, v):
+        """rbm.py:97-98 -> free_energy_func (:73-76)."""
+        v = _unwrap(v)
+        self._ensure_built(v)
+        return self._wrap(self._machine.free_energy(v))
+
+    def transform_proba(self, v):
+        """sigmoid(v.W + c) itself (not part of the reference surface; used by parity tests)."""
+        v = _unwrap(v)
+        self._ensure_built(v)
+        return self._machine.transform(v, want_p=True)[1]
+
+    # ---- training ------------------------------------------------------------------------------
+    def _hparams(self, update_mask=L.UPDATE_ALL, want_stats=False):
+        hps = self.hps
+        norm = hps.get("normalize", "sum")
+        return Machine.hparams(lr=hps["lr"], k=hps.get("k", 1), persistent=hps.get("persistent", False),
+                               momentum=hps.get("momentum", 0.0), weight_decay=hps.get("weight_decay", 0.0),
+                               normalize=(norm in ("mean", True, 1)), update_mask=update_mask,
+                               want_stats=want_stats)
+
+    def _shard(self, V, batch):
+        """Data-parallel layout: rank r keeps rows [r*b, (r+1)*b) of every global minibatch."""
+        ctx = self._machine.ctx
+        return shard_rows(V, batch, ctx.rank, ctx.world)
+
+    def fit(self, V, verbose=1):
+        """Train RBM with the data V (rbm.py:100-234).
+
+        V : 2d array (rows x input_dim), or an engine Dataset already resident on the GPU.
+        Sequential minibatches of hps['batch_size'] rows, remainder last, hps['epochs'] passes, no
+        shuffling (rbm.py:110-113,163,211,218).
+        """
+        V = _unwrap(V)
+        self._ensure_built(V)
+        hps = self.hps
+        batch = int(hps["batch_size"])
+        epochs = int(hps["epochs"])
+        compat = hps.get("compat", "fused")
+        m = self._machine
+        if hps.get("persistent", False) and m.ctx is not None:
+            self._ensure_chains(batch)
+        if compat == "reference":
+            return self._fit_reference(np.asarray(V, dtype=np.float32), batch, epochs, verbose)
+        if compat != "fused":
+            raise ValueError("hps['compat'] must be 'fused' or 'reference'")
+
+        if isinstance(V, Dataset):
+            ds, local_batch, row0, owns = V, batch, 0, False
+        else:
+            local, local_batch, row0 = self._shard(V, batch)
+            ds, owns = Dataset.from_array(m.ctx, local, m.compute), True
+        n_rows = ds.shape[0]
+        num_step = int(math.ceil(n_rows / local_batch)) if n_rows else 0
+        hp = self._hparams()
+        try:
+            for k in range(epochs):
+                if verbose == 1:
+                    print(k + 1, "/", epochs, " epochs", end="\r")  # rbm.py:115
+                want = bool(verbose)
+                hp.want_stats = int(want)
+                st = m.fit_epoch(ds, local_batch, hp, global_row0=row0, want_stats=True)
+                st["epoch"] = k + 1
+                self.history.append(st)
+                if want:
+                    # the reference prints this after every step (rbm.py:234); once per epoch here
+                    print("\n{0:d}/{1:d}, score: {2:f}".format(num_step, num_step, st["last_score"]))
+        finally:
+            m.ctx.sync()
+            if owns:
+                ds.close()
+        return self
+
+    def _ensure_chains(self, batch):
+        m = self._machine
+        if getattr(self, "_chains_set", 0) >= batch:
+            return
+        rng = np.random.default_rng(int(self.hps.get("chain_seed", 99)))
+        ctx = m.ctx
+        rows = batch // ctx.world if ctx.world > 1 else batch
+        full = (rng.random((batch, m.V)) < 0.5).astype(np.float32)
+        m.set_chains(full[ctx.rank * rows:(ctx.rank + 1) * rows] if ctx.world > 1 else full)
+        self._chains_set = batch
+
+    def _fit_reference(self, V, batch, epochs, verbose):
+        """The reference schedule, run for run (rbm.py:214-234): three single-parameter updates with
+        fresh draws each, then the score from a fourth chain, printed per step."""
+        m = self._machine
+        n_rows = V.shape[0]
+        num_step = n_rows // batch if n_rows % batch == 0 else n_rows // batch + 1  # rbm.py:110-111
+        for k in range(epochs):
+            if verbose == 1:
+                print(k + 1, "/", epochs, " epochs", end="\r")
+            for i in range(num_step):
+                V_batch = V[i * batch:min((i + 1) * batch, n_rows)]       # rbm.py:211,218
+                m.cd_step(V_batch, self._hparams(L.UPDATE_W))              # rbm_weight_update_func
+                m.cd_step(V_batch, self._hparams(L.UPDATE_C))              # hidden_bias_update_func
+                m.cd_step(V_batch, self._hparams(L.UPDATE_B))              # visible_bias_update_func
+                score = m.score(V_batch)                                    # rbm.py:227-233
+                self.history.append({"epoch": k + 1, "step": i + 1, "last_score": score})
+                if verbose:
+                    print("\n{0:d}/{1:d}, score: {2:f}".format(i + 1, num_step, score))  # rbm.py:234
+        m.ctx.sync()
+        return self

@@ -1,0 +1,117 @@
+"""The reference-facing classes (keras_unsupervised_b200.ebm.RBM / DBN) on the GPU: the calls a user of
+ku.ebm makes, with the reference's names, argument meaning, return types and error behaviour."""
+import numpy as np
+import pytest
+
+from oracle import cd_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _structured(rng, n, dim, protos=16, flip=0.05):
+    P = (rng.random((protos, dim)) < 0.5)
+    x = P[rng.integers(0, protos, n)]
+    x ^= rng.random((n, dim)) < flip
+    return x.astype(np.float32)
+
+
+def test_rbm_surface_matches_reference(ctx, capsys):
+    from keras_unsupervised_b200.ebm import RBM, MODE_VISIBLE_BERNOULLI
+
+    rng = np.random.default_rng(0)
+    hps = {"batch_size": 128, "epochs": 2, "lr": 1e-3}
+    rbm = RBM(hps, 500, name="rbm", mode=MODE_VISIBLE_BERNOULLI, context=ctx)
+    V = (rng.random((1000, 784)) < 0.13).astype(np.float32)
+    rbm.fit(V, verbose=1)                      # 7 full minibatches + a 104-row remainder (rbm.py:110-111)
+    out = capsys.readouterr().out
+    assert "1 / 2  epochs" in out and "score:" in out      # rbm.py:115,234
+    assert rbm.rbm_weight.shape == (784, 500) and rbm.hidden_bias.shape == (500,) and rbm.visible_bias.shape == (784,)
+    h = rbm.transform(V[:100])                 # K.function returns a list of one array (rbm.py:89)
+    assert isinstance(h, list) and len(h) == 1 and h[0].shape == (100, 500) and h[0].dtype == np.float32
+    assert set(np.unique(h[0])) <= {0.0, 1.0}
+    v = rbm.inv_transform(h)                   # and accepts one (dbn.py:55 feeds it straight back)
+    assert v[0].shape == (100, 784) and set(np.unique(v[0])) <= {0.0, 1.0}
+    fe = rbm.cal_free_energy([V[:100]])
+    assert fe[0].shape == (100,)
+    assert rbm.compute_output_shape((None, 784)) == (None, 500)
+    cfg = rbm.get_config()
+    assert cfg["output_dim"] == 500 and cfg["name"] == "rbm" and cfg["hps"] is hps and cfg["mode"] == 0
+    assert rbm.call(V[:10]).shape == (10, 500)
+
+
+def test_rbm_learns_structured_data(ctx):
+    from keras_unsupervised_b200.ebm import RBM, MODE_VISIBLE_BERNOULLI
+
+    rng = np.random.default_rng(1235)
+    V = _structured(rng, 4096, 256)
+    for dtype in ("float32", "bf16"):
+        rbm = RBM({"batch_size": 128, "epochs": 1, "lr": 0.05, "normalize": "mean", "dtype": dtype, "k": 1}, 128,
+                  name="r", mode=MODE_VISIBLE_BERNOULLI, context=ctx)
+        rbm.fit(V, verbose=0)
+        first = rbm._machine.cd_step(V[:128], rbm._hparams(update_mask=0, want_stats=True))["recon_err"]
+        rbm.hps["epochs"] = 15
+        rbm.fit(V, verbose=0)
+        last = rbm._machine.cd_step(V[:128], rbm._hparams(update_mask=0, want_stats=True))["recon_err"]
+        assert last < 0.6 * first, (dtype, first, last)
+        assert np.isfinite(rbm.rbm_weight).all()
+
+
+def test_rbm_reference_schedule_mode(ctx, capsys):
+    """compat='reference': three single-parameter runs and a per-step score print (rbm.py:214-234)."""
+    from keras_unsupervised_b200.ebm import RBM, MODE_VISIBLE_BERNOULLI
+
+    rng = np.random.default_rng(2)
+    V = (rng.random((300, 200)) < 0.2).astype(np.float32)
+    rbm = RBM({"batch_size": 128, "epochs": 1, "lr": 1e-3, "compat": "reference"}, 64, name="r",
+              mode=MODE_VISIBLE_BERNOULLI, context=ctx)
+    before = ctx.timings(reset=True)
+    rbm.fit(V, verbose=1)
+    out = capsys.readouterr().out
+    assert out.count("score:") == 3 and "3/3, score:" in out
+    t = ctx.timings()
+    # per step: 3 runs x (3 projections + dW) + score (2 projections + 2 free energies) = 16 contractions
+    assert t["gemm_launches"] == 3 * 16
+
+
+def test_dbn_greedy_pretraining(ctx, capsys):
+    from keras_unsupervised_b200.ebm import DBN, RBM, MODE_VISIBLE_BERNOULLI
+
+    rng = np.random.default_rng(3)
+    V = _structured(rng, 2048, 784)
+    hps = {"batch_size": 256, "epochs": 1, "lr": 1e-3, "dtype": "bf16"}
+    dbn = DBN()
+    with pytest.raises(ValueError):
+        dbn.fit(V)                                   # dbn.py:47-48
+    dims = [500, 500, 2000]
+    for i, d in enumerate(dims):
+        dbn.add_stack(RBM(hps, d, name="rbm%d" % i, mode=MODE_VISIBLE_BERNOULLI, context=ctx))
+    dbn.fit(V, verbose=0)
+    assert capsys.readouterr().out.count("Train rbm") == 3   # dbn.py:53
+    H = dbn.transform(V[:64])
+    assert H.shape == (64, 2000) and set(np.unique(H)) <= {0.0, 1.0}
+    back = dbn.inv_transform(H)
+    assert back.shape == (64, 784)
+    bad = RBM(hps, 10, name="bad", mode=MODE_VISIBLE_BERNOULLI, context=ctx, input_dim=123)
+    with pytest.raises(ValueError):
+        dbn.add_stack(bad)                           # dbn.py:27-30
+
+
+def test_torch_cuda_tensors_zero_copy(ctx):
+    """DLPack-style hand-over: device tensors go in and come out without touching the host."""
+    import torch
+
+    from keras_unsupervised_b200.ebm import RBM, MODE_VISIBLE_BERNOULLI
+
+    rbm = RBM({"batch_size": 64, "epochs": 1, "lr": 1e-3, "dtype": "bf16", "seed": 9}, 256, name="r",
+              mode=MODE_VISIBLE_BERNOULLI, context=ctx, return_list=False)
+    x = (torch.rand(512, 320, device="cuda") < 0.3).float()
+    before = ctx.timings(reset=True)
+    h = rbm.transform(x)
+    t = ctx.timings()
+    assert h.is_cuda and h.shape == (512, 256)
+    assert t["h2d_bytes"] == 0 and t["d2h_bytes"] == 0
+    rbm._machine.set_seed(9, 0)
+    h_np = rbm.transform(x.cpu().numpy())
+    assert np.array_equal(h.cpu().numpy(), h_np)
+    hb = rbm._machine.transform(x.to(torch.bfloat16), out_dtype=torch.uint8)
+    assert hb.dtype == torch.uint8 and hb.shape == (512, 256)

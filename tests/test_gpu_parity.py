@@ -1,0 +1,332 @@
+"""GPU parity: libkucd.so (through the C ABI / ctypes) against the CPU oracle on the same seeded inputs.
+
+Bars: sampled states bit-exact under injected, margin-conditioned uniforms;
+probabilities / free energy / statistics within 1e-5 relative in float32 mode (2e-2 in bf16 mode, where
+the oracle rounds the same operands to bf16 first, so the observed gap is far smaller).
+"""
+import numpy as np
+import pytest
+
+from oracle import cd_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+RTOL_F32 = 1e-5   # north_star: probabilities, free energy, reconstruction error, float32
+RTOL_BF16 = 2e-2  # north_star: bf16
+
+
+def _machine(ctx, V, H, compute, mode=0, seed=0, pseed=0):
+    from keras_unsupervised_b200 import _lib as L
+    from keras_unsupervised_b200.engine import Machine
+
+    m = Machine(ctx, V, H, mode, L.COMPUTE_F32X3 if compute == "f32" else L.COMPUTE_BF16, seed=seed)
+    W, b, c = O.OracleRBM.init_params(V, H, seed=pseed)
+    m.set_params(W, b, c)
+    orc = O.OracleRBM(W, b, c, mode=mode, compute="f64" if compute == "f32" else "bf16")
+    return m, orc
+
+
+def _data(rng, rows, V, q=0.3):
+    return (rng.random((rows, V)) < q).astype(np.float32)
+
+
+@pytest.mark.parametrize("compute", ["f32", "bf16"])
+@pytest.mark.parametrize("rows,V,H", [(128, 784, 500), (96, 784, 500), (300, 200, 333), (1, 64, 64), (257, 1000, 72)])
+def test_transform_and_inverse_bit_exact(ctx, compute, rows, V, H):
+    rng = np.random.default_rng(rows + V)
+    m, orc = _machine(ctx, V, H, compute)
+    v = _data(rng, rows, V)
+    u = O.lattice_uniform(rng, (rows, H))
+    (u,), _, _ = O.condition_margin(orc, v, [u], [None], k=0)
+    h, p = m.transform(v, u=u, want_p=True)
+    h_ref, p_ref = orc.sample_h(v, u)
+    np.testing.assert_allclose(p, p_ref, rtol=RTOL_F32 if compute == "f32" else RTOL_BF16, atol=1e-7)
+    assert np.array_equal(h, h_ref)
+
+    hh = _data(rng, rows, H, 0.5)
+    u2 = O.lattice_uniform(rng, (rows, V))
+    p2_ref = orc.prob_v(hh)
+    bad = np.abs(u2 - p2_ref) <= 1e-4
+    u2[bad] = np.where(p2_ref[bad] > 0.5, 0.0, 0.999)
+    vv, p2 = m.inv_transform(hh, u=u2, want_p=True)
+    np.testing.assert_allclose(p2, p2_ref, rtol=RTOL_F32 if compute == "f32" else RTOL_BF16, atol=1e-7)
+    assert np.array_equal(vv, (u2 < p2_ref).astype(np.float32))
+
+
+def test_transform_edge_uniforms(ctx):
+    """Strict < (K.less, rbm.py:46): u = 0 fires unless p = 0; u just below 1 never fires for p < 1."""
+    rng = np.random.default_rng(5)
+    m, orc = _machine(ctx, 128, 64, "f32")
+    v = _data(rng, 64, 128)
+    h0 = m.transform(v, u=np.zeros((64, 64), np.float32))
+    h1 = m.transform(v, u=np.full((64, 64), 1.0 - 2.0 ** -23, np.float32))
+    assert h0.min() == 1.0 and h1.max() == 0.0
+
+
+@pytest.mark.parametrize("compute", ["f32", "bf16"])
+def test_real_valued_visibles(ctx, compute):
+    """The example feeds grey levels in [0,1], not bits (examples/rbm/rbm_softmax_mnist.py:103)."""
+    rng = np.random.default_rng(11)
+    rows, V, H = 200, 784, 500
+    m, orc = _machine(ctx, V, H, compute)
+    v = (rng.integers(0, 256, (rows, V)) / 255.0).astype(np.float32)
+    p = m.transform(v, want_p=True)[1]
+    np.testing.assert_allclose(p, orc.prob_h(v), rtol=RTOL_F32 if compute == "f32" else RTOL_BF16, atol=1e-7)
+    fe = m.free_energy(v)
+    np.testing.assert_allclose(fe, orc.free_energy(v), rtol=RTOL_F32 if compute == "f32" else RTOL_BF16)
+
+
+@pytest.mark.parametrize("compute", ["f32", "bf16"])
+@pytest.mark.parametrize("rows,V,H", [(128, 784, 500), (37, 300, 130), (1024, 512, 512)])
+def test_free_energy(ctx, compute, rows, V, H):
+    rng = np.random.default_rng(7)
+    m, orc = _machine(ctx, V, H, compute)
+    v = _data(rng, rows, V)
+    np.testing.assert_allclose(m.free_energy(v), orc.free_energy(v),
+                               rtol=RTOL_F32 if compute == "f32" else RTOL_BF16)
+
+
+def test_free_energy_matches_partition_sum_on_tiny_rbm(ctx):
+    """F(v) = -log sum_h exp(-E(v,h)) checked by brute force over all 2^H hidden states (H = 10)."""
+    rng = np.random.default_rng(3)
+    V, H, rows = 64, 10, 16
+    from keras_unsupervised_b200 import _lib as L
+    from keras_unsupervised_b200.engine import Machine
+
+    W = rng.normal(0, 0.5, (V, H)).astype(np.float32)
+    b = rng.normal(0, 0.5, V).astype(np.float32)
+    c = rng.normal(0, 0.5, H).astype(np.float32)
+    m = Machine(ctx, V, H, 0, L.COMPUTE_F32X3)
+    m.set_params(W, b, c)
+    v = _data(rng, rows, V)
+    hs = ((np.arange(1 << H)[:, None] >> np.arange(H)) & 1).astype(np.float64)
+    energy = -(v.astype(np.float64) @ b)[:, None] - hs @ c - (v.astype(np.float64) @ W) @ hs.T
+    brute = -np.log(np.exp(-energy).sum(1))
+    np.testing.assert_allclose(m.free_energy(v), brute, rtol=1e-5)
+
+
+def _inject(rng, rows, V, H, k, persistent=False):
+    u_h = [O.lattice_uniform(rng, (rows, H)) for _ in range(k)]
+    u_v = [None] + [O.lattice_uniform(rng, (rows, V)) for _ in range(k)]
+    u_hc = O.lattice_uniform(rng, (rows, H)) if persistent else None
+    return u_h, u_v, u_hc
+
+
+@pytest.mark.parametrize("compute", ["f32", "bf16"])
+@pytest.mark.parametrize("rows,V,H,k", [(128, 784, 500, 1), (96, 784, 500, 1), (64, 256, 192, 3), (200, 130, 70, 2)])
+def test_cd_step_matches_oracle(ctx, compute, rows, V, H, k):
+    rng = np.random.default_rng(17 + k)
+    m, orc = _machine(ctx, V, H, compute)
+    v = _data(rng, rows, V, 0.13)
+    u_h, u_v, _ = _inject(rng, rows, V, H, k)
+    u_h, u_v, _ = O.condition_margin(orc, v, u_h, u_v, k=k)
+    from keras_unsupervised_b200.engine import Machine
+
+    st = orc.fused_step(v, u_h, u_v, lr=1e-3, k=k)
+    m.cd_step(v, Machine.hparams(lr=1e-3, k=k), u_h=u_h, u_v=u_v)
+    got = m.last_stats(rows)
+    assert np.array_equal(got["h_pos"], st["h_pos"])
+    assert np.array_equal(got["v_neg"], st["v_neg"])
+    tol = RTOL_F32 if compute == "f32" else RTOL_BF16
+    h_neg_ref = st["h_neg"] if compute == "f32" else O.bf16_round(st["h_neg"])
+    np.testing.assert_allclose(got["h_neg"], h_neg_ref, rtol=tol, atol=1e-7)
+    scale = max(1.0, float(np.abs(st["dW"]).max()))
+    np.testing.assert_allclose(got["dW"], st["dW"], rtol=tol, atol=tol * scale)
+    np.testing.assert_allclose(got["dc"], st["dc"], rtol=tol, atol=tol * rows)
+    np.testing.assert_allclose(got["db"], st["db"], rtol=tol, atol=1e-6)
+    W, b, c = m.get_params()
+    np.testing.assert_allclose(W, orc.W, rtol=tol, atol=1e-6)
+    np.testing.assert_allclose(b, orc.b, rtol=tol, atol=1e-6)
+    np.testing.assert_allclose(c, orc.c, rtol=tol, atol=1e-6)
+
+
+def test_reference_three_pass_schedule(ctx):
+    """rbm.py:214-233: W, then c with fresh draws and the new W, then b, then the score chain."""
+    rng = np.random.default_rng(23)
+    rows, V, H = 128, 784, 500
+    m, orc = _machine(ctx, V, H, "f32")
+    from keras_unsupervised_b200 import _lib as L
+    from keras_unsupervised_b200.engine import Machine
+
+    v = _data(rng, rows, V, 0.13)
+    draws = []
+    for mask in (1, 2, 4):
+        u_h, u_v, _ = _inject(rng, rows, V, H, 1)
+        u_h, u_v, _ = O.condition_margin(orc, v, u_h, u_v, k=1)
+        draws.append((u_h[0], u_v[1]))
+        orc.apply(orc.cd_stats(v, u_h, u_v), 1e-3, mask)
+        m.cd_step(v, Machine.hparams(lr=1e-3, update_mask={1: L.UPDATE_W, 2: L.UPDATE_C, 4: L.UPDATE_B}[mask]),
+                  u_h=u_h, u_v=u_v)
+    u_h, u_v, _ = _inject(rng, rows, V, H, 1)
+    u_h, u_v, _ = O.condition_margin(orc, v, u_h, u_v, k=1)
+    s_ref = orc.score(v, u_h[0], u_v[1])
+    s = m.score(v, u_h=u_h[0], u_v=u_v[1])
+    W, b, c = m.get_params()
+    np.testing.assert_allclose(W, orc.W, rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(b, orc.b, rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(c, orc.c, rtol=1e-5, atol=1e-6)
+    assert abs(s - s_ref) <= 1e-5 * max(1.0, abs(s_ref))
+
+
+def test_persistent_chains(ctx):
+    rng = np.random.default_rng(31)
+    rows, V, H, k = 128, 320, 200, 2
+    m, orc = _machine(ctx, V, H, "f32")
+    from keras_unsupervised_b200.engine import Machine
+
+    chains = _data(rng, rows, V, 0.5)
+    orc.chains = chains.copy()
+    m.set_chains(chains)
+    for step in range(2):
+        v = _data(rng, rows, V, 0.2)
+        u_h, u_v, u_hc = _inject(rng, rows, V, H, k, persistent=True)
+        u_h, u_v, u_hc = O.condition_margin(orc, v, u_h, u_v, k=k, persistent=True, u_hc=u_hc)
+        st = orc.fused_step(v, u_h, u_v, lr=1e-3, k=k, persistent=True, u_hc=u_hc)
+        m.cd_step(v, Machine.hparams(lr=1e-3, k=k, persistent=True), u_h=u_h, u_v=u_v, u_hc=u_hc)
+        got = m.last_stats(rows)
+        assert np.array_equal(got["v_neg"], st["v_neg"])
+        assert np.array_equal(m.get_chains(rows), orc.chains)
+        np.testing.assert_allclose(got["dW"], st["dW"], rtol=1e-5, atol=1e-4)
+
+
+def test_momentum_weight_decay_mean(ctx):
+    rng = np.random.default_rng(41)
+    rows, V, H = 64, 192, 128
+    m, orc = _machine(ctx, V, H, "f32")
+    from keras_unsupervised_b200.engine import Machine
+
+    for _ in range(3):
+        v = _data(rng, rows, V)
+        u_h, u_v, _ = _inject(rng, rows, V, H, 1)
+        u_h, u_v, _ = O.condition_margin(orc, v, u_h, u_v, k=1)
+        orc.fused_step(v, u_h, u_v, lr=0.05, momentum=0.5, weight_decay=1e-3, scale=1.0 / rows)
+        m.cd_step(v, Machine.hparams(lr=0.05, momentum=0.5, weight_decay=1e-3, normalize=True), u_h=u_h, u_v=u_v)
+    W, b, c = m.get_params()
+    np.testing.assert_allclose(W, orc.W, rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(b, orc.b, rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(c, orc.c, rtol=1e-5, atol=1e-6)
+
+
+def test_philox_stream_matches_oracle(ctx):
+    """Without injection the engine draws Philox4x32-10 keyed by (seed, draw id, global row, column):
+    the oracle regenerates the same uniforms, so even 'random' runs are comparable."""
+    rng = np.random.default_rng(53)
+    rows, V, H, seed = 300, 200, 333, 1234
+    m, orc = _machine(ctx, V, H, "f32", seed=seed)
+    v = _data(rng, rows, V)
+    h, p = m.transform(v, want_p=True)          # first inference draw: id 2^63 + 0
+    u = O.philox_uniform(seed, O.draw_id("infer", 0), 0, rows, H)
+    near = np.abs(u - p) <= 4 * 2.0 ** -23
+    assert np.array_equal(h[~near], (u < orc.prob_h(v)).astype(np.float32)[~near])
+    assert near.mean() < 1e-3
+    h2 = m.transform(v)                          # second call, next draw id: a different sample
+    assert (h2 != h).mean() > 0.1
+    # chunk / shard independence: rows 100.. drawn with row0 = 100 equal the tail of the full draw
+    m.set_seed(seed, 0)
+    full = m.transform(v)
+    assert np.array_equal(full, h)
+
+
+def test_fit_epoch_graph_replay_matches_oracle(ctx):
+    """fit_epoch = CUDA-graph replay per minibatch with device-side offsets; includes a remainder step."""
+    from keras_unsupervised_b200 import _lib as L
+    from keras_unsupervised_b200.engine import Dataset, Machine
+
+    rng = np.random.default_rng(61)
+    N, B, V, H, seed = 1000, 128, 784, 500, 77
+    m, orc = _machine(ctx, V, H, "f32", seed=seed)
+    data = _data(rng, N, V, 0.13)
+    ds = Dataset.from_array(ctx, data, L.COMPUTE_F32X3)
+    assert ds.shape == (N, V)
+    assert np.array_equal(ds.numpy(), data)
+    hp = Machine.hparams(lr=1e-3, k=1)
+    for _ in range(2):
+        st = m.fit_epoch(ds, B, hp)
+        assert st["steps"] == 8 and st["rows"] == N
+    ctx.sync()
+    O.philox_fit(orc, data, B, 2, 1e-3, seed)
+    W, b, c = m.get_params()
+    # a sample may flip where |u - p| is within rounding of the two sigmoid implementations; each
+    # flip moves single entries by lr.  Demand near-equality in the mean and a bounded max.
+    assert np.abs(W - orc.W).mean() < 2e-6
+    assert np.abs(W - orc.W).max() < 5e-3
+    assert np.abs(b - orc.b).max() < 5e-3 and np.abs(c - orc.c).max() < 5e-3
+    ds.close()
+
+
+def test_dataset_transform_equals_array_transform(ctx):
+    from keras_unsupervised_b200 import _lib as L
+    from keras_unsupervised_b200.engine import Dataset
+
+    rng = np.random.default_rng(67)
+    rows, V, H, seed = 500, 256, 192, 5
+    m, orc = _machine(ctx, V, H, "bf16", seed=seed)
+    v = _data(rng, rows, V)
+    ds = Dataset.from_array(ctx, v, L.COMPUTE_BF16)
+    out = m.transform_dataset(ds)     # draw id 2^63 + 0
+    m.set_seed(seed, 0)
+    h = m.transform(v)                # same id again
+    assert np.array_equal(out.numpy(), h)
+    back = m.inv_transform_dataset(out)
+    assert back.shape == (rows, V)
+
+
+def test_errors_are_reported_not_fatal(ctx):
+    m, _ = _machine(ctx, 128, 64, "f32")
+    with pytest.raises(ValueError):
+        m.transform(np.zeros((4, 100), np.float32))
+    with pytest.raises(ValueError):
+        m.free_energy(np.zeros((4, 64), np.float32))
+    from keras_unsupervised_b200.engine import Machine
+
+    with pytest.raises(ValueError):
+        m.cd_step(np.zeros((4, 128), np.float32), Machine.hparams(k=0))
+    with pytest.raises(ValueError):
+        m.cd_step(np.zeros((4, 128), np.float32), Machine.hparams(persistent=True))
+    # empty input: nothing to do, nothing breaks
+    assert m.transform(np.zeros((0, 128), np.float32)).shape == (0, 64)
+    m.cd_step(np.zeros((0, 128), np.float32), Machine.hparams())
+
+
+def test_gaussian_visible_mode(ctx):
+    """rbm.py:55-67,139-155: relu-threshold hiddens, unit-variance Gaussian visibles."""
+    rng = np.random.default_rng(71)
+    rows, V, H = 128, 256, 128
+    m, orc = _machine(ctx, V, H, "f32", mode=1)
+    from keras_unsupervised_b200.engine import Machine
+
+    v = rng.normal(0, 1, (rows, V)).astype(np.float32)
+    u_h = O.lattice_uniform(rng, (rows, H))
+    pre = np.maximum(orc.pre_h(v), 0)
+    bad = np.abs(u_h - pre) <= 1e-4
+    u_h[bad] = 0.999
+    n_v = rng.normal(0, 1, (rows, V)).astype(np.float32)
+    h, p = m.transform(v, u=u_h, want_p=True)
+    h_ref, p_ref = orc.sample_h(v, u_h)
+    np.testing.assert_allclose(p, p_ref, rtol=1e-5, atol=1e-6)
+    assert np.array_equal(h, h_ref)
+    st = orc.fused_step(v, [u_h], [None, n_v], lr=1e-4)
+    m.cd_step(v, Machine.hparams(lr=1e-4), u_h=[u_h], u_v=[None, n_v])
+    got = m.last_stats(rows)
+    np.testing.assert_allclose(got["v_neg"], st["v_neg"], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(got["dW"], st["dW"], rtol=1e-4, atol=1e-3)
+    W, b, c = m.get_params()
+    np.testing.assert_allclose(W, orc.W, rtol=1e-5, atol=1e-6)
+
+
+def test_large_contraction_accuracy_f32(ctx):
+    """K = 4096 real-valued inputs: the longest accumulation chain of the BASELINE configs."""
+    rng = np.random.default_rng(83)
+    rows, V, H = 256, 4096, 320
+    m, orc = _machine(ctx, V, H, "f32")
+    v = rng.random((rows, V)).astype(np.float32)
+    p = m.transform(v, want_p=True)[1]
+    p_ref = orc.prob_h(v)
+    rel = np.abs(p - p_ref) / np.maximum(np.abs(p_ref), 1e-30)
+    print("max rel err K=4096 real-valued:", rel.max())
+    np.testing.assert_allclose(p, p_ref, rtol=RTOL_F32, atol=1e-7)
+    vb = (v < 0.5).astype(np.float32)
+    pb = m.transform(vb, want_p=True)[1]
+    relb = np.abs(pb - orc.prob_h(vb)) / np.maximum(orc.prob_h(vb), 1e-30)
+    print("max rel err K=4096 binary:", relb.max())
+    np.testing.assert_allclose(pb, orc.prob_h(vb), rtol=RTOL_F32, atol=1e-7)
