@@ -1,0 +1,340 @@
+#!/usr/bin/env python
+"""Benchmark of the RBM CD-k hot path on B200 (BASELINE.json metric: RBM CD-k training samples/sec).
+
+    python bench.py --gpus N --steps K --warmup W            # the engine
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port)
+
+Workload (BASELINE.json configs[2], the configuration the metric is quoted on): Bernoulli RBM
+4096 -> 4096, CD-10, minibatch 4096 rows per GPU (weak scaling), bf16 contractions, synthetic binarised
+data.  A "step" is one minibatch: 21 projections with fused sigmoid/Philox/threshold epilogues, the dW
+contraction, the all-reduce (N > 1) and the fused update.  `value` is measured with every minibatch
+already resident in HBM (K distinct minibatches, far larger than L2, replayed as one CUDA graph per
+step); `e2e` goes through the reference-facing call with float32 HOST (pinned) minibatches, the
+host->device copy and the device->host read of the step's statistic inside the timed region.
+
+One JSON line on stdout (rank 0).  Under torchrun each rank drives one GPU; time is the max over ranks
+of CUDA-event time on the engine's stream.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (V, H, batch per GPU, k, dtype, bernoulli prob of a 1)
+    "c3": dict(V=4096, H=4096, B=4096, k=10, dtype="bf16", q=0.5,
+               desc="Bernoulli RBM 4096->4096, CD-10, batch 4096 per GPU, bf16 (BASELINE.json configs[2])"),
+    "c1": dict(V=784, H=500, B=128, k=1, dtype="bf16", q=0.1307,
+               desc="Bernoulli RBM 784->500, CD-1, batch 128 (BASELINE.json configs[0])"),
+}
+METRIC = "RBM CD-k training samples/sec"
+UNIT = "samples/s"
+
+
+def flops_per_sample(V, H, k):
+    return (2 * k + 3) * 2 * V * H  # (2k+1) projections + 2 outer products
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(burst=p["bf16_tflops"], sustained=p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                    hbm=p["hbm_gbs"], source="measured (MEASURED_PEAKS.json)")
+    return dict(burst=1590.0, sustained=1400.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons while the benchmark runs (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.samples = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(device), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "50"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append((time.time(), line.strip()))
+
+    def stop(self, windows):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.proc.terminate()
+        rows = []
+        for t, line in self.samples:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                rows.append((t, float(f[0]), float(f[1]), float(f[2]), f[3:7]))
+            except ValueError:
+                continue
+        inside = [r for r in rows if any(a - 0.02 <= r[0] <= b + 0.02 for a, b in windows)]
+        used = inside if len(inside) >= 2 else [r for r in rows if r[3] > 300.0] or rows
+        if not used:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = sorted(r[1] for r in used)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in used for i in range(4) if r[4][i].lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": used[0][2], "reasons": reasons,
+                "power_w_max": max(r[3] for r in used), "samples": len(used),
+                "window": "timed regions" if used is inside else "under load (timed region shorter than the sampling period)"}
+
+
+def cpu_fused_step(orc, O, x, k, rng):
+    """One fused CD-k minibatch of the oracle port in float32, drawing its uniforms as TF would."""
+    import numpy as np
+
+    rows = x.shape[0]
+    u_h = [rng.random((rows, orc.H), dtype=np.float32) for _ in range(k)]
+    u_v = [None] + [rng.random((rows, orc.V), dtype=np.float32) for _ in range(k)]
+    orc.fused_step(x, u_h, u_v, lr=1e-3, k=k, scale=1.0 / rows)
+
+
+def cpu_arm(cfg, steps, warmup, rows):
+    """The reference's CPU path: the oracle port of ku/ebm/rbm.py (TensorFlow is not installable),
+    float32 numpy/BLAS on all host cores, `rows` rows per step (a bounded sample of the minibatch)."""
+    import numpy as np
+
+    from oracle import cd_oracle as O
+
+    rng = np.random.default_rng(7)
+    W, b, c = O.OracleRBM.init_params(cfg["V"], cfg["H"], seed=0)
+    orc = O.OracleRBM(W, b, c, compute="f32")
+    x = (np.random.default_rng(1234).random((rows, cfg["V"])) < cfg["q"]).astype(np.float32)
+    for _ in range(warmup):
+        cpu_fused_step(orc, O, x, cfg["k"], rng)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_fused_step(orc, O, x, cfg["k"], rng)
+    dt = time.perf_counter() - t0
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count()
+    return dict(value=rows * steps / dt, seconds=dt, cores=cores, rows=rows, steps=steps)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    cfg = WORKLOADS[args.workload]
+    V, H, B, k = cfg["V"], cfg["H"], cfg["B"], cfg["k"]
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    config = {"workload": cfg["desc"], "n_visible": V, "n_hidden": H, "batch_per_gpu": B, "global_batch": B * world,
+              "k": k, "schedule": "fused single chain (W, b, c from the same statistics)",
+              "parallelism": "dp%d" % world,
+              "l2": "every step reads a different minibatch; the resident data set is far larger than L2"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        rows = 256 if args.workload == "c3" else B
+        r = cpu_arm(cfg, steps, min(warmup, 2), rows)
+        line = {"metric": METRIC, "value": r["value"], "unit": UNIT, "impl": "reference", "n_gpus": args.gpus,
+                "steps": steps, "warmup": min(warmup, 2), "ms_per_step": 1e3 * r["seconds"] / steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": config,
+                "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+                                 "sample": "%d steps of %d rows (of the %d-row minibatch), fused CD-%d, float32 "
+                                           "numpy/BLAS oracle port of ku/ebm/rbm.py" % (steps, rows, B, k)},
+                "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    import numpy as np
+    import torch
+
+    from keras_unsupervised_b200 import _lib as L
+    from keras_unsupervised_b200.engine import Context, Dataset, Machine
+
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = Context(device=local_rank, seed=42)
+    if world > 1:
+        ctx.join_group(rank, world)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+
+    compute = L.COMPUTE_BF16 if cfg["dtype"] == "bf16" else L.COMPUTE_F32X3
+    m = Machine(ctx, V, H, L.MODE_VISIBLE_BERNOULLI, compute, seed=42)
+    prng = np.random.default_rng(0)
+    m.set_params(prng.uniform(-0.05, 0.05, (V, H)).astype(np.float32), prng.uniform(-0.05, 0.05, V).astype(np.float32),
+                 prng.uniform(-0.05, 0.05, H).astype(np.float32))
+
+    # K distinct synthetic binarised minibatches per rank, resident in HBM as the engine's operand planes
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(1234 + rank)
+    n_batches = max(steps, 1)
+    X = torch.empty((n_batches * B, V), dtype=torch.uint8, device="cuda")
+    for i in range(n_batches):
+        X[i * B:(i + 1) * B] = (torch.rand((B, V), device="cuda", generator=gen) < cfg["q"]).to(torch.uint8)
+    torch.cuda.synchronize()
+    ds = Dataset.from_array(ctx, X, compute)
+    hp = Machine.hparams(lr=1e-3, k=k, normalize=True)
+    row0 = rank * B
+
+    def barrier():
+        ctx.sync()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    # ---- warm-up (captures the step graph), then exactly K timed steps -----------------------------
+    done = 0
+    while done < warmup:
+        n = min(warmup - done, n_batches)
+        m.fit_range(ds, B, hp, 0, n, global_row0=row0)
+        done += n
+    barrier()
+    ext = torch.cuda.ExternalStream(ctx.stream_ptr(), device=torch.device("cuda", local_rank))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ctx.timings(reset=True)
+    t_wall0 = time.time()
+    e0.record(ext)
+    m.fit_range(ds, B, hp, 0, steps, global_row0=row0)
+    e1.record(ext)
+    ctx.sync()
+    torch.cuda.synchronize()
+    t_wall1 = time.time()
+    ms = e0.elapsed_time(e1)
+    tm = ctx.timings()
+    launches = tm["graph_kernel_launches"] + 1  # + the step-state initialisation kernel
+    if dist is not None:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * steps * B / (ms * 1e-3)
+    windows = [(t_wall0, t_wall1)]
+
+    # ---- end to end: float32 host minibatches through the public call, H2D + D2H inside -----------
+    e2e = None
+    if not args.no_e2e:
+        n_host = min(8, n_batches)
+        host = [torch.empty((B, V), dtype=torch.float32).pin_memory() for _ in range(n_host)]
+        for i in range(n_host):
+            host[i].copy_(X[i * B:(i + 1) * B].to(torch.float32))
+        hp_e = Machine.hparams(lr=1e-3, k=k, normalize=True, want_stats=2)
+        for i in range(2):
+            m.cd_step(host[i % n_host], hp_e, global_row0=row0)
+        barrier()
+        n_e2e = max(3, min(steps, 30))
+        ctx.timings(reset=True)
+        tw0 = time.time()
+        t0 = time.perf_counter()
+        for i in range(n_e2e):
+            st = m.cd_step(host[i % n_host], hp_e, global_row0=row0)  # returns after the D2H read of the statistic
+        ctx.sync()
+        dt = time.perf_counter() - t0
+        tw1 = time.time()
+        te = ctx.timings()
+        if dist is not None:
+            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": world * n_e2e * B / dt, "unit": UNIT, "h2d_bytes_per_step": te["h2d_bytes"] // n_e2e,
+               "d2h_bytes_per_step": te["d2h_bytes"] // n_e2e, "steps": n_e2e, "ms_per_step": 1e3 * dt / n_e2e,
+               "input": "float32 pinned host minibatch per step via kucd_rbm_cd_step; result read: recon_err",
+               "last_recon_err": st["recon_err"]}
+        windows.append((tw0, tw1))
+
+    # ---- roofline of the dominant kernel: per-launch CUDA events on the engine stream -------------
+    roof = None
+    pk = peaks()
+    if rank == 0:
+        ctx.set_profile(True)
+        ctx.timings(reset=True)
+        hp_d = Machine.hparams(lr=1e-3, k=k, normalize=True)
+        n_prof = 3
+        tw0 = time.time()
+        for i in range(n_prof):
+            m.cd_step(X[(i % n_batches) * B:((i % n_batches) + 1) * B], hp_d, global_row0=row0)
+        tp = ctx.timings()
+        tw1 = time.time()
+        ctx.set_profile(False)
+        windows.append((tw0, tw1))
+        if tp["proj_timed"]:
+            per_launch_ms = tp["proj_ms"] / tp["proj_timed"]
+            flop = 2.0 * B * V * H
+            ach = flop / (per_launch_ms * 1e-3) / 1e12
+            traffic = None
+            tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+            if os.path.exists(tpath):
+                with open(tpath) as f:
+                    traffic = json.load(f).get(args.workload)
+            roof = {"bound": "tensor", "kernel": "gemm_bf16_kernel<sample epilogue> (v.W+c / h.W^T+b projection)",
+                    "achieved": ach, "peak": pk["sustained"], "unit": "TFLOP/s", "frac": ach / pk["sustained"],
+                    "peak_source": pk["source"] + ", sustained figure (kernel timed inside a long step)",
+                    "traffic": traffic, "launch_ms": per_launch_ms, "launches_timed": tp["proj_timed"],
+                    "flop_per_launch": flop,
+                    "dw_launch_ms": (tp["dw_ms"] / tp["dw_timed"]) if tp["dw_timed"] else None,
+                    "step_tflops": flops_per_sample(V, H, k) * B / (ms * 1e-3 / steps) / 1e12,
+                    "step_frac_of_sustained": flops_per_sample(V, H, k) * B / (ms * 1e-3 / steps) / 1e12 / pk["sustained"]}
+    if dist is not None and world > 1 and rank != 0:
+        pass  # only rank 0 profiles; the others wait at the final barrier
+
+    clocks = sampler.stop(windows) if sampler is not None else None
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        rows = 512 if args.workload == "c3" else B
+        r = cpu_arm(cfg, 2 if args.workload == "c3" else 20, 1, rows)
+        cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+               "sample": "%d steps of %d rows (of the %d-row minibatch), fused CD-%d, float32 numpy/BLAS oracle port of "
+                         "ku/ebm/rbm.py, %.1f s" % (r["steps"], rows, B, k, r["seconds"])}
+
+    if dist is not None:
+        dist.barrier()
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+                "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": cfg["dtype"], "data": "synthetic binarised (Bernoulli %.4g), U(-0.05,0.05) weights" % cfg["q"],
+                "config": config, "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "roofline": roof,
+                "cpu_baseline": cpu,
+                "per_gpu": {"samples_per_s": value / world,
+                            "tflops": flops_per_sample(V, H, k) * value / world / 1e12,
+                            "frac_of_sustained_bf16_peak": flops_per_sample(V, H, k) * value / world / 1e12 / pk["sustained"]}}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -85,7 +85,7 @@ typedef struct kucd_hparams {
   float weight_decay;  /* extension, 0 = reference                                                    */
   int32_t normalize;   /* 0 = batch sum (reference), 1 = divide by the GLOBAL batch rows              */
   int32_t update_mask; /* KUCD_UPDATE_*                                                               */
-  int32_t want_stats;  /* != 0: fill kucd_step_stats (costs two free-energy passes)                   */
+  int32_t want_stats;  /* 1: fill kucd_step_stats (two free-energy passes + a chain); 2: recon_err only   */
 } kucd_hparams;
 
 /* Injected random draws for parity runs: arrays of float32 uniforms on the caller's side of the
@@ -118,12 +118,16 @@ typedef struct kucd_epoch_stats {
 } kucd_epoch_stats;
 
 typedef struct kucd_timings {
-  int64_t gemm_launches;    /* tcgen05 contraction launches since the context was created / reset */
-  int64_t aux_launches;     /* update / split / reduction / conversion launches                   */
-  int64_t graph_launches;   /* CUDA-graph replays (each replays a whole CD step)                   */
+  int64_t gemm_launches;    /* tcgen05 contraction launches enqueued (directly or while capturing)  */
+  int64_t aux_launches;     /* update / split / reduction / conversion launches enqueued            */
+  int64_t graph_launches;   /* CUDA-graph replays (each replays a whole CD step)                     */
+  int64_t graph_kernel_launches; /* kernels those replays launched                                    */
   int64_t allreduce_calls;
   int64_t h2d_bytes, d2h_bytes;
-  float last_gemm_ms;       /* CUDA-event duration of the most recent timed contraction            */
+  /* per-launch CUDA-event timing of directly launched contractions, on while kucd_ctx_set_profile(1) */
+  int64_t proj_timed, dw_timed; /* launches timed: projections (v.W, h.W^T), dW contractions          */
+  float proj_ms, dw_ms;         /* their summed device time                                           */
+  float last_gemm_ms;
 } kucd_timings;
 
 typedef struct kucd_ctx kucd_ctx;
@@ -138,6 +142,7 @@ int kucd_ctx_create(kucd_ctx** out, int device_id, uint64_t seed);
 int kucd_ctx_destroy(kucd_ctx* ctx);
 int kucd_sync(kucd_ctx* ctx);
 int kucd_get_timings(kucd_ctx* ctx, kucd_timings* out, int reset);
+int kucd_ctx_set_profile(kucd_ctx* ctx, int enable);
 /* the CUstream the engine launches on (for callers that time with their own events) */
 int kucd_ctx_stream(kucd_ctx* ctx, void** stream_out);
 
@@ -207,6 +212,9 @@ int kucd_dataset_read(kucd_dataset* ds, kucd_tensor* out);
  * `global_row0` = rank * batch. */
 int kucd_rbm_fit_epoch(kucd_rbm* rbm, kucd_dataset* ds, int64_t batch, const kucd_hparams* hp,
                        int64_t global_row0, kucd_epoch_stats* stats);
+/* Minibatches [step_begin, step_end) of that epoch (step_end < 0: to the end). */
+int kucd_rbm_fit_range(kucd_rbm* rbm, kucd_dataset* ds, int64_t batch, const kucd_hparams* hp,
+                       int64_t global_row0, int64_t step_begin, int64_t step_end, kucd_epoch_stats* stats);
 /* DBN.fit's inter-layer step (dbn.py:55): V_p <- transform(V_p) on the whole data set, on device. */
 int kucd_rbm_transform_dataset(kucd_rbm* rbm, kucd_dataset* in, kucd_dataset** out);
 int kucd_rbm_inv_transform_dataset(kucd_rbm* rbm, kucd_dataset* in, kucd_dataset** out);

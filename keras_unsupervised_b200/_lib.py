@@ -63,8 +63,9 @@ class EpochStats(C.Structure):
 
 class Timings(C.Structure):
     _fields_ = [("gemm_launches", C.c_int64), ("aux_launches", C.c_int64), ("graph_launches", C.c_int64),
-                ("allreduce_calls", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
-                ("last_gemm_ms", C.c_float)]
+                ("graph_kernel_launches", C.c_int64), ("allreduce_calls", C.c_int64), ("h2d_bytes", C.c_int64),
+                ("d2h_bytes", C.c_int64), ("proj_timed", C.c_int64), ("dw_timed", C.c_int64),
+                ("proj_ms", C.c_float), ("dw_ms", C.c_float), ("last_gemm_ms", C.c_float)]
 
 
 _P = C.c_void_p
@@ -78,6 +79,7 @@ SIGNATURES = {
     "kucd_sync": (C.c_int, [_P]),
     "kucd_get_timings": (C.c_int, [_P, C.POINTER(Timings), C.c_int]),
     "kucd_ctx_stream": (C.c_int, [_P, C.POINTER(_P)]),
+    "kucd_ctx_set_profile": (C.c_int, [_P, C.c_int]),
     "kucd_comm_unique_id": (C.c_int, [_P]),
     "kucd_ctx_comm_init": (C.c_int, [_P, _P, C.c_int, C.c_int]),
     "kucd_rbm_create": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int, C.c_int, C.POINTER(_P)]),
@@ -99,6 +101,8 @@ SIGNATURES = {
     "kucd_dataset_shape": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "kucd_dataset_read": (C.c_int, [_P, _TP]),
     "kucd_rbm_fit_epoch": (C.c_int, [_P, _P, C.c_int64, C.POINTER(HParams), C.c_int64, C.POINTER(EpochStats)]),
+    "kucd_rbm_fit_range": (C.c_int, [_P, _P, C.c_int64, C.POINTER(HParams), C.c_int64, C.c_int64, C.c_int64,
+                                      C.POINTER(EpochStats)]),
     "kucd_rbm_transform_dataset": (C.c_int, [_P, _P, C.POINTER(_P)]),
     "kucd_rbm_inv_transform_dataset": (C.c_int, [_P, _P, C.POINTER(_P)]),
 }

@@ -138,6 +138,15 @@ struct kucd_ctx {
   kucd_timings tm{};
   void* comm = nullptr;
   int rank = 0, world = 1;
+  // optional per-launch CUDA-event timing of the contractions (kucd_ctx_set_profile)
+  bool profile = false;
+  std::vector<cudaEvent_t> ev_pool;
+  struct Mark {
+    int cls;  // 0 = projection, 1 = dW
+    size_t e0, e1;
+  };
+  std::vector<Mark> marks;
+  size_t ev_used = 0;
   DevBuf stage_in, stage_u, stage_out;  // raw caller-dtype staging for host tensors
 };
 
@@ -220,6 +229,7 @@ struct kucd_rbm {
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t graph_exec = nullptr;
   GraphKey graph_key;
+  int64_t graph_kernels = 0;  // kernels one replay launches
 
   float* dW() const { return grad.as<float>(); }
   float* db() const { return grad.as<float>() + V * ldH; }
@@ -228,6 +238,36 @@ struct kucd_rbm {
   int64_t ldHb() const { return round_up(H, 256) + 256; }
   int64_t grad_elems() const { return V * ldH + ldVb() + ldHb(); }
 };
+
+static size_t prof_event(kucd_ctx* ctx) {
+  if (ctx->ev_used == ctx->ev_pool.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    ctx->ev_pool.push_back(e);
+  }
+  cudaEventRecord(ctx->ev_pool[ctx->ev_used], ctx->stream);
+  return ctx->ev_used++;
+}
+
+// fold the recorded marks into the timing totals (synchronises the stream)
+static void prof_collect(kucd_ctx* ctx) {
+  if (ctx->marks.empty()) return;
+  cudaStreamSynchronize(ctx->stream);
+  for (const auto& m : ctx->marks) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ctx->ev_pool[m.e0], ctx->ev_pool[m.e1]) != cudaSuccess) continue;
+    if (m.cls == 0) {
+      ctx->tm.proj_ms += ms;
+      ctx->tm.proj_timed++;
+    } else {
+      ctx->tm.dw_ms += ms;
+      ctx->tm.dw_timed++;
+    }
+    ctx->tm.last_gemm_ms = ms;
+  }
+  ctx->marks.clear();
+  ctx->ev_used = 0;
+}
 
 static int grid_for(const kucd_ctx* ctx, int64_t work_items, int threads) {
   const int64_t blocks = (work_items + threads - 1) / threads;
@@ -494,8 +534,11 @@ static int project(kucd_rbm* r, bool forward, const Planes& a, int64_t rows, con
   p.dyn_rows = e.dyn != nullptr ? 1 : 0;
   p.a_dyn_mask = dyn_mask;
   std::string err;
+  const bool prof = ctx->profile && e.dyn == nullptr;
+  const size_t pe0 = prof ? prof_event(ctx) : 0;
   if (!launch_gemm(p, ops, e.epi, ctx->num_sms, ctx->stream, &err, 0, r->compute == KUCD_COMPUTE_F32X3))
     return fail(KUCD_ERR_CUDA, "%s", err.c_str());
+  if (prof) ctx->marks.push_back({0, pe0, prof_event(ctx)});
   ctx->tm.gemm_launches++;
   return KUCD_OK;
 }
@@ -540,8 +583,11 @@ static int delta_w(kucd_rbm* r, const Planes& v0, const Planes& h0, const Planes
   p.dyn = dyn;
   p.a_dyn_mask = dyn_mask;
   std::string err;
+  const bool prof = ctx->profile && dyn == nullptr;
+  const size_t pe0 = prof ? prof_event(ctx) : 0;
   if (!launch_gemm(p, ops, kEpiRaw, ctx->num_sms, ctx->stream, &err, 0, r->compute == KUCD_COMPUTE_F32X3))
     return fail(KUCD_ERR_CUDA, "%s", err.c_str());
+  if (prof) ctx->marks.push_back({1, pe0, prof_event(ctx)});
   ctx->tm.gemm_launches++;
   return KUCD_OK;
 }
@@ -876,6 +922,7 @@ int kucd_ctx_destroy(kucd_ctx* ctx) {
   ctx->stage_in.release();
   ctx->stage_u.release();
   ctx->stage_out.release();
+  for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
   cudaEventDestroy(ctx->ev0);
   cudaEventDestroy(ctx->ev1);
   cudaStreamDestroy(ctx->stream);
@@ -891,8 +938,16 @@ int kucd_sync(kucd_ctx* ctx) {
 
 int kucd_get_timings(kucd_ctx* ctx, kucd_timings* out, int reset) {
   if (ctx == nullptr || out == nullptr) return fail(KUCD_ERR_INVALID_ARG, "NULL argument");
+  prof_collect(ctx);
   *out = ctx->tm;
   if (reset) ctx->tm = kucd_timings{};
+  return KUCD_OK;
+}
+
+int kucd_ctx_set_profile(kucd_ctx* ctx, int enable) {
+  if (ctx == nullptr) return fail(KUCD_ERR_INVALID_ARG, "ctx is NULL");
+  prof_collect(ctx);
+  ctx->profile = enable != 0;
   return KUCD_OK;
 }
 
@@ -1221,7 +1276,7 @@ int kucd_rbm_cd_step(kucd_rbm* r, const kucd_tensor* v_batch, const kucd_hparams
   KU_TRY(apply_update(r, hp, rows * ctx->world));
   if (stats != nullptr && hp->want_stats) {
     // the score chain reuses the state buffers, which is why last_stats must be read before asking for stats
-    KU_TRY(enqueue_score(r, v0, rows, nullptr, 0, nullptr, 0, global_row0));
+    if (hp->want_stats == 1) KU_TRY(enqueue_score(r, v0, rows, nullptr, 0, nullptr, 0, global_row0));
     KU_TRY(read_stats(r, stats, rows));
   }
   const bool host_in = !on_device(v_batch) || inj != nullptr;
@@ -1413,8 +1468,8 @@ int kucd_dataset_read(kucd_dataset* ds, kucd_tensor* out) {
   return KUCD_OK;
 }
 
-int kucd_rbm_fit_epoch(kucd_rbm* r, kucd_dataset* ds, int64_t batch, const kucd_hparams* hp, int64_t global_row0,
-                       kucd_epoch_stats* stats) {
+static int fit_range_impl(kucd_rbm* r, kucd_dataset* ds, int64_t batch, const kucd_hparams* hp, int64_t global_row0,
+                          int64_t step_begin, int64_t step_end, kucd_epoch_stats* stats) {
   if (r == nullptr || ds == nullptr) return fail(KUCD_ERR_INVALID_ARG, "NULL argument");
   kucd_ctx* ctx = r->ctx;
   CU_TRY(cudaSetDevice(ctx->device));
@@ -1425,8 +1480,13 @@ int kucd_rbm_fit_epoch(kucd_rbm* r, kucd_dataset* ds, int64_t batch, const kucd_
                 (long long)r->V);
   if (batch < 1 || batch > (1 << 22)) return fail(KUCD_ERR_INVALID_ARG, "batch_size %lld", (long long)batch);
   const int64_t N = ds->rows;
-  const int64_t steps = (N + batch - 1) / batch;  // rbm.py:110-111
+  const int64_t epoch_steps = (N + batch - 1) / batch;  // rbm.py:110-111
   if (stats != nullptr) memset(stats, 0, sizeof *stats);
+  if (step_end < 0) step_end = epoch_steps;
+  if (step_begin < 0 || step_begin > step_end || step_end > epoch_steps)
+    return fail(KUCD_ERR_INVALID_ARG, "minibatch range [%lld, %lld) of %lld", (long long)step_begin, (long long)step_end,
+                (long long)epoch_steps);
+  const int64_t steps = step_end - step_begin;
   if (steps == 0) return KUCD_OK;
   KU_TRY(ensure_workspace(r, batch));
   if (hp->persistent) KU_TRY(ensure_chains(r, std::min(batch, N)));
@@ -1456,6 +1516,7 @@ int kucd_rbm_fit_epoch(kucd_rbm* r, kucd_dataset* ds, int64_t batch, const kucd_
       r->graph = nullptr;
     }
     CU_TRY(cudaStreamSynchronize(ctx->stream));
+    const int64_t k0 = ctx->tm.gemm_launches + ctx->tm.aux_launches;
     CU_TRY(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed));
     int rc = enqueue_cd(r, v0, batch, hp, nullptr, global_row0, 0, dyn, true);
     if (rc == KUCD_OK) rc = apply_update(r, hp, batch * ctx->world);
@@ -1479,13 +1540,17 @@ int kucd_rbm_fit_epoch(kucd_rbm* r, kucd_dataset* ds, int64_t batch, const kucd_
     r->graph = g;
     r->graph_exec = ge;
     r->graph_key = key;
+    // the launches counted while capturing were recorded, not run: they are what one replay launches
+    r->graph_kernels = ctx->tm.gemm_launches + ctx->tm.aux_launches - k0;
   }
-  set_dyn_kernel<<<1, 1, 0, ctx->stream>>>(dyn, 0, static_cast<int32_t>(std::min(batch, N)), r->step_count);
+  set_dyn_kernel<<<1, 1, 0, ctx->stream>>>(dyn, step_begin * batch,
+                                           static_cast<int32_t>(std::min(batch, N - step_begin * batch)), r->step_count);
   ctx->tm.aux_launches++;
   CU_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
   for (int64_t s = 0; s < steps; ++s) CU_TRY(cudaGraphLaunch(r->graph_exec, ctx->stream));
   CU_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
   ctx->tm.graph_launches += steps;
+  ctx->tm.graph_kernel_launches += steps * r->graph_kernels;
   r->step_count += steps;
   r->last_rows = batch;
   if (stats != nullptr) {
@@ -1493,7 +1558,7 @@ int kucd_rbm_fit_epoch(kucd_rbm* r, kucd_dataset* ds, int64_t batch, const kucd_
     stats->rows = N;
     if (hp->want_stats) {
       // score of the last minibatch with a fresh chain, as the reference prints it (rbm.py:227-234)
-      const int64_t r0 = (steps - 1) * batch, n = N - r0;
+      const int64_t r0 = (step_end - 1) * batch, n = std::min(batch, N - r0);
       Planes last = v0;
       for (int i = 0; i < 3; ++i)
         if (last.p[i] != nullptr) last.p[i] += r0 * last.ld;
@@ -1509,6 +1574,16 @@ int kucd_rbm_fit_epoch(kucd_rbm* r, kucd_dataset* ds, int64_t batch, const kucd_
     CU_TRY(cudaEventElapsedTime(&stats->device_ms, ctx->ev0, ctx->ev1));
   }
   return KUCD_OK;
+}
+
+int kucd_rbm_fit_epoch(kucd_rbm* r, kucd_dataset* ds, int64_t batch, const kucd_hparams* hp, int64_t global_row0,
+                       kucd_epoch_stats* stats) {
+  return fit_range_impl(r, ds, batch, hp, global_row0, 0, -1, stats);
+}
+
+int kucd_rbm_fit_range(kucd_rbm* r, kucd_dataset* ds, int64_t batch, const kucd_hparams* hp, int64_t global_row0,
+                       int64_t step_begin, int64_t step_end, kucd_epoch_stats* stats) {
+  return fit_range_impl(r, ds, batch, hp, global_row0, step_begin, step_end, stats);
 }
 
 // dbn.py:55 / :73 / :94 on a device-resident data set

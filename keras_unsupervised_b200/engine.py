@@ -59,6 +59,9 @@ class Context:
         L.check(self.lib.kucd_get_timings(self.handle, C.byref(t), int(reset)))
         return {k: getattr(t, k) for k, _ in L.Timings._fields_}
 
+    def set_profile(self, enable: bool) -> None:
+        L.check(self.lib.kucd_ctx_set_profile(self.handle, int(enable)))
+
     def stream_ptr(self) -> int:
         p = C.c_void_p()
         L.check(self.lib.kucd_ctx_stream(self.handle, C.byref(p)))
@@ -200,7 +203,7 @@ class Machine:
     def hparams(lr=1e-3, k=1, persistent=False, momentum=0.0, weight_decay=0.0, normalize=False,
                 update_mask=L.UPDATE_ALL, want_stats=False) -> L.HParams:
         return L.HParams(float(lr), int(k), int(bool(persistent)), float(momentum), float(weight_decay),
-                         int(bool(normalize)), int(update_mask), int(bool(want_stats)))
+                         int(bool(normalize)), int(update_mask), int(want_stats))
 
     def cd_step(self, v_batch, hp: L.HParams, u_h=None, u_v=None, u_hc=None, global_row0: int = 0):
         """u_h: list indexed by t (0 = h_pos, t = intermediate h), u_v: list indexed by t (1..k; entry 0
@@ -277,6 +280,14 @@ class Machine:
         st = L.EpochStats()
         L.check(self.ctx.lib.kucd_rbm_fit_epoch(self.handle, ds.handle, C.c_int64(batch), C.byref(hp),
                                                 C.c_int64(global_row0), C.byref(st) if want_stats else None))
+        return {k: getattr(st, k) for k, _ in L.EpochStats._fields_}
+
+    def fit_range(self, ds: Dataset, batch: int, hp: L.HParams, step_begin: int, step_end: int,
+                  global_row0: int = 0, want_stats: bool = False) -> dict:
+        st = L.EpochStats()
+        L.check(self.ctx.lib.kucd_rbm_fit_range(self.handle, ds.handle, C.c_int64(batch), C.byref(hp),
+                                                C.c_int64(global_row0), C.c_int64(step_begin), C.c_int64(step_end),
+                                                C.byref(st) if want_stats else None))
         return {k: getattr(st, k) for k, _ in L.EpochStats._fields_}
 
     def transform_dataset(self, ds: Dataset) -> Dataset:
