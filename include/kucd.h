@@ -209,7 +209,8 @@ int kucd_dataset_read(kucd_dataset* ds, kucd_tensor* out);
 /* One epoch over sequential slices of `batch` rows, remainder last, no shuffle (rbm.py:163,211,218);
  * every step is one replay of a captured CUDA graph.  With a data-parallel group attached every rank
  * passes its own shard of every global minibatch: `batch` is the per-rank row count and
- * `global_row0` = rank * batch. */
+ * `global_row0` = rank * batch (on the remainder minibatch the engine keys the draws by
+ * rank * remaining rows, so n ranks still sample exactly what one rank would). */
 int kucd_rbm_fit_epoch(kucd_rbm* rbm, kucd_dataset* ds, int64_t batch, const kucd_hparams* hp,
                        int64_t global_row0, kucd_epoch_stats* stats);
 /* Minibatches [step_begin, step_end) of that epoch (step_end < 0: to the end). */

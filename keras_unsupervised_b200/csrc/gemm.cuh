@@ -78,6 +78,8 @@ struct alignas(64) GemmParams {
   float* colsum;  // optional (N): += colsum_sign * column sums of the stored output
   float colsum_sign;
   int32_t dyn_rows;  // != 0: the valid row count is min(m_valid, dyn->rows_valid) (minibatch-row outputs)
+  int32_t dyn_rank;  // data-parallel rank: under graph replay row0 = dyn_rank * dyn->rows_valid, so that the
+  int32_t pad2;      // remainder minibatch is keyed by global row exactly like the full ones
   float* rowsum;  // free energy accumulator (M)
   uint64_t seed;
   uint64_t draw;  // draw id: distinct for every sampling launch
@@ -158,7 +160,8 @@ __device__ __forceinline__ void box_muller(uint32_t b0, uint32_t b1, float& n0, 
 // One 32-column chunk of one output row (this thread's TMEM lane).
 template <int EPI>
 __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32_t (&acc)[32], int row, int col0,
-                                               bool row_ok, uint64_t draw, uint32_t lane, float& row_acc) {
+                                               bool row_ok, uint64_t draw, int64_t row0, uint32_t lane,
+                                               float& row_acc) {
   if (col0 >= p.N) return;  // warp-uniform
   const bool row_st = row < p.M;  // rows in [m_valid, M) are stored as zeros: they are K-rows of the dW contraction
 
@@ -225,7 +228,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
         }
       }
     } else {
-      const uint32_t grow = static_cast<uint32_t>(p.row0 + row);
+      const uint32_t grow = static_cast<uint32_t>(row0 + row);
       const uint32_t k0 = static_cast<uint32_t>(p.seed), k1 = static_cast<uint32_t>(p.seed >> 32);
       const uint32_t d0 = static_cast<uint32_t>(draw), d1 = static_cast<uint32_t>(draw >> 32);
 #pragma unroll
@@ -275,7 +278,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
 #pragma unroll
       for (int j = 0; j < 32; ++j) x[j] = sigmoid_f32(x[j]);
     } else {
-      const uint32_t grow = static_cast<uint32_t>(p.row0 + row);
+      const uint32_t grow = static_cast<uint32_t>(row0 + row);
       const uint32_t k0 = static_cast<uint32_t>(p.seed), k1 = static_cast<uint32_t>(p.seed >> 32);
       const uint32_t d0 = static_cast<uint32_t>(draw), d1 = static_cast<uint32_t>(draw >> 32);
       if (p.u_inject != nullptr) {  // injected standard normals
@@ -391,7 +394,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_bf16_kernel(const __grid_
   int32_t dyn_row_off = 0;
   int32_t m_valid = p.m_valid;
   uint64_t draw = p.draw;
+  int64_t row0 = p.row0;
   if (p.dyn != nullptr) {
+    if (p.dyn_rows != 0) row0 = static_cast<int64_t>(p.dyn_rank) * p.dyn->rows_valid;
     dyn_row_off = static_cast<int32_t>(p.dyn->row_off);
     if (p.dyn_rows != 0) m_valid = p.dyn->rows_valid < m_valid ? p.dyn->rows_valid : m_valid;
     draw += p.dyn->step * p.draw_stride;
@@ -541,7 +546,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_bf16_kernel(const __grid_
           uint32_t acc[32];
           ptx::tmem_ld_32x32(tmem_base + ((quarter * 32u) << 16) + as * BN + coff, acc);
           ptx::tmem_ld_wait();
-          epilogue_chunk<EPI>(p, acc, row, n_blk * BN + coff, row_ok, draw, lane, row_acc);
+          epilogue_chunk<EPI>(p, acc, row, n_blk * BN + coff, row_ok, draw, row0, lane, row_acc);
         }
         ptx::tc_fence_before();
         __syncwarp();
@@ -573,7 +578,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_bf16_kernel(const __grid_
           uint32_t acc[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) acc[j] = __float_as_uint(sum[c + j]);
-          epilogue_chunk<EPI>(p, acc, row, n_blk * BN + half * kColsPerWarp + c, row_ok, draw, lane, row_acc);
+          epilogue_chunk<EPI>(p, acc, row, n_blk * BN + half * kColsPerWarp + c, row_ok, draw, row0, lane, row_acc);
         }
       }
       if constexpr (EPI == kEpiFreeEnergy) {

@@ -532,6 +532,7 @@ static int project(kucd_rbm* r, bool forward, const Planes& a, int64_t rows, con
   p.m_valid = e.m_valid < 0 ? static_cast<int32_t>(rows) : e.m_valid;
   p.dyn = e.dyn;
   p.dyn_rows = e.dyn != nullptr ? 1 : 0;
+  p.dyn_rank = ctx->rank;
   p.a_dyn_mask = dyn_mask;
   std::string err;
   const bool prof = ctx->profile && e.dyn == nullptr;

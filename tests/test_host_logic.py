@@ -1,0 +1,58 @@
+"""Host-side logic that needs no GPU: the reference-facing classes' argument handling, the DBN stack
+rules (dbn.py:14-32,47-48) and the data-parallel row layout."""
+import numpy as np
+import pytest
+
+from keras_unsupervised_b200.ebm import DBN, RBM, MODE_VISIBLE_BERNOULLI, MODE_VISIBLE_GAUSSIAN, MODE_COMPLEX
+from keras_unsupervised_b200.parallel import local_batch, shard_rows
+
+
+def test_constants_and_constructor_signature():
+    assert (MODE_VISIBLE_BERNOULLI, MODE_VISIBLE_GAUSSIAN, MODE_COMPLEX) == (0, 1, 2)     # rbm.py:14-16
+    hps = {"batch_size": 128, "epochs": 1, "lr": 1e-3}
+    rbm = RBM(hps, 500, name="rbm")                                                      # rbm.py:22
+    assert rbm.mode == MODE_VISIBLE_GAUSSIAN and rbm.hps is hps and rbm.output_dim == 500 and rbm.name == "rbm"
+    assert rbm.compute_output_shape((None, 784)) == (None, 500)                           # rbm.py:94-95
+    cfg = rbm.get_config()
+    assert cfg == {"hps": hps, "output_dim": 500, "name": "rbm", "mode": MODE_VISIBLE_GAUSSIAN}
+    with pytest.raises(ValueError):
+        RBM(hps, 10, mode=MODE_COMPLEX)
+    assert not rbm.built
+    with pytest.raises(ValueError):
+        rbm.inv_transform(np.zeros((2, 500), np.float32))
+
+
+def test_dbn_stack_rules():
+    dbn = DBN()
+    for call in (dbn.fit, dbn.transform, dbn.inv_transform):
+        with pytest.raises(ValueError, match="Any rbm layer doesn't exist."):                # dbn.py:47-48
+            call(np.zeros((2, 4), np.float32))
+    hps = {"batch_size": 2, "epochs": 1, "lr": 1e-3}
+
+    class Built:  # a layer whose dimensions are known, without touching the engine
+        def __init__(self, i, o):
+            self.input_shape, self.output_shape, self.output_dim, self.name = (None, i), (None, o), o, "l"
+
+    dbn.add_stack(Built(8, 6))
+    with pytest.raises(ValueError, match="output dimension"):                                  # dbn.py:27-30
+        dbn.add_stack(Built(7, 3))
+    dbn.add_stack(Built(6, 3))
+    dbn.add_stack(RBM(hps, 2, name="unbuilt"))        # dimension unknown until data arrives: accepted
+    assert len(dbn._rbm_layers) == 3
+
+
+def test_shard_rows_layout():
+    V = np.arange(10 * 3).reshape(10, 3)
+    assert shard_rows(V, 4, 0, 1)[0] is V
+    # batch 4 over 2 ranks, 10 rows: minibatches [0:4], [4:8], remainder [8:10]
+    l0, b0, g0 = shard_rows(V, 4, 0, 2)
+    l1, b1, g1 = shard_rows(V, 4, 1, 2)
+    assert (b0, g0, b1, g1) == (2, 0, 2, 2)
+    assert l0[:, 0].tolist() == [0, 3, 12, 15, 24] and l1[:, 0].tolist() == [6, 9, 18, 21, 27]
+    # every row is owned exactly once
+    assert sorted(np.concatenate([l0, l1])[:, 0].tolist()) == V[:, 0].tolist()
+    with pytest.raises(ValueError):
+        shard_rows(V, 5, 0, 2)
+    with pytest.raises(ValueError):
+        shard_rows(np.zeros((9, 3)), 4, 0, 2)     # remainder of 1 row does not split over 2 ranks
+    assert local_batch(4096, 8192, 8) == 512

@@ -1,0 +1,75 @@
+"""Data-parallel parity check, one process per GPU (launch with torchrun, world size >= 2).
+
+Every rank trains the same RBM on its row shard of every global minibatch through fit_epoch (CUDA-graph
+replay with the NCCL all-reduce of dW | db | dc captured inside the step graph).  Rank 0 then compares the
+parameters with (a) a single-GPU engine run over the unsharded data and (b) the CPU oracle: draws are
+keyed by global row, so the sampled states are identical and the parameters agree up to the reduction
+order of the all-reduce.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from keras_unsupervised_b200 import _lib as L  # noqa: E402
+from keras_unsupervised_b200.engine import Context, Dataset, Machine  # noqa: E402
+from keras_unsupervised_b200.parallel import shard_rows  # noqa: E402
+from oracle import cd_oracle as O  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    V, H, B, N, seed, k = 320, 256, 128, 128 * 5 + 64, 21, 2
+    data = (np.random.default_rng(3).random((N, V)) < 0.25).astype(np.float32)
+    W, b, c = O.OracleRBM.init_params(V, H, seed=4)
+    ok = True
+    for compute, name in ((L.COMPUTE_F32X3, "f32"), (L.COMPUTE_BF16, "bf16")):
+        ctx = Context(device=local, seed=seed)
+        ctx.join_group(rank, world)
+        m = Machine(ctx, V, H, 0, compute, seed=seed)
+        m.set_params(W, b, c)
+        loc, lb, row0 = shard_rows(data, B, rank, world)
+        ds = Dataset.from_array(ctx, loc, compute)
+        hp = Machine.hparams(lr=1e-3, k=k)
+        for _ in range(2):
+            m.fit_epoch(ds, lb, hp, global_row0=row0, want_stats=False)
+        ctx.sync()
+        Wd, bd, cd = m.get_params()
+        t = ctx.timings()
+        if rank == 0:
+            solo_ctx = Context(device=local, seed=seed)
+            solo = Machine(solo_ctx, V, H, 0, compute, seed=seed)
+            solo.set_params(W, b, c)
+            sds = Dataset.from_array(solo_ctx, data, compute)
+            for _ in range(2):
+                solo.fit_epoch(sds, B, hp, want_stats=False)
+            solo_ctx.sync()
+            Ws, bs, cs = solo.get_params()
+            orc = O.OracleRBM(W, b, c, compute="f64" if name == "f32" else "bf16")
+            O.philox_fit(orc, data, B, 2, 1e-3, seed, k=k)
+            d_solo = float(np.abs(Wd - Ws).max())
+            d_orc = float(np.abs(Wd - orc.W).mean())
+            print("[dp_check] %s world=%d allreduce_calls=%d  max|W_dp - W_1gpu| = %.3e  mean|W_dp - W_oracle| = %.3e"
+                  % (name, world, t["allreduce_calls"], d_solo, d_orc), flush=True)
+            # identical samples => only the fp32 reduction order differs
+            ok &= d_solo < 2e-6 and float(np.abs(bd - bs).max()) < 2e-6 and float(np.abs(cd - cs).max()) < 2e-6
+            ok &= d_orc < 5e-6
+            ok &= t["graph_launches"] == 12
+        dist.barrier()
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.broadcast(flag, src=0)
+    dist.destroy_process_group()
+    if rank == 0:
+        print("[dp_check] PASS" if ok else "[dp_check] FAIL", flush=True)
+    sys.exit(0 if int(flag.item()) == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()
