@@ -277,7 +277,8 @@ def main():
     # ---- roofline of the dominant kernel: per-launch CUDA events on the engine stream -------------
     roof = None
     pk = peaks()
-    if rank == 0:
+    if True:  # every rank runs these steps (they all-reduce); rank 0 reports
+        barrier()
         ctx.set_profile(True)
         ctx.timings(reset=True)
         hp_d = Machine.hparams(lr=1e-3, k=k, normalize=True)
@@ -289,7 +290,7 @@ def main():
         tw1 = time.time()
         ctx.set_profile(False)
         windows.append((tw0, tw1))
-        if tp["proj_timed"]:
+        if tp["proj_timed"] and rank == 0:
             per_launch_ms = tp["proj_ms"] / tp["proj_timed"]
             flop = 2.0 * B * V * H
             ach = flop / (per_launch_ms * 1e-3) / 1e12
@@ -306,9 +307,6 @@ def main():
                     "dw_launch_ms": (tp["dw_ms"] / tp["dw_timed"]) if tp["dw_timed"] else None,
                     "step_tflops": flops_per_sample(V, H, k) * B / (ms * 1e-3 / steps) / 1e12,
                     "step_frac_of_sustained": flops_per_sample(V, H, k) * B / (ms * 1e-3 / steps) / 1e12 / pk["sustained"]}
-    if dist is not None and world > 1 and rank != 0:
-        pass  # only rank 0 profiles; the others wait at the final barrier
-
     clocks = sampler.stop(windows) if sampler is not None else None
 
     cpu = None
