@@ -292,7 +292,8 @@ def main():
         windows.append((tw0, tw1))
         if tp["proj_timed"] and rank == 0:
             per_launch_ms = tp["proj_ms"] / tp["proj_timed"]
-            flop = 2.0 * B * V * H
+            # 2k+1 projections per step; with the two-chain schedule each is launched as two row-halves
+            flop = n_prof * (2 * k + 1) * 2.0 * B * V * H / tp["proj_timed"]
             ach = flop / (per_launch_ms * 1e-3) / 1e12
             traffic = None
             tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
@@ -303,6 +304,7 @@ def main():
                     "achieved": ach, "peak": pk["sustained"], "unit": "TFLOP/s", "frac": ach / pk["sustained"],
                     "peak_source": pk["source"] + ", sustained figure (kernel timed inside a long step)",
                     "traffic": traffic, "launch_ms": per_launch_ms, "launches_timed": tp["proj_timed"],
+                    "launch_rows": int(round(flop / (2.0 * V * H))),
                     "flop_per_launch": flop,
                     "dw_launch_ms": (tp["dw_ms"] / tp["dw_timed"]) if tp["dw_timed"] else None,
                     "step_tflops": flops_per_sample(V, H, k) * B / (ms * 1e-3 / steps) / 1e12,

@@ -79,7 +79,8 @@ struct alignas(64) GemmParams {
   float colsum_sign;
   int32_t dyn_rows;  // != 0: the valid row count is min(m_valid, dyn->rows_valid) (minibatch-row outputs)
   int32_t dyn_rank;  // data-parallel rank: under graph replay row0 = dyn_rank * dyn->rows_valid, so that the
-  int32_t pad2;      // remainder minibatch is keyed by global row exactly like the full ones
+  int32_t dyn_row_base;  // remainder minibatch is keyed by global row exactly like the full ones;
+                         // dyn_row_base = first minibatch row of this launch (second chain of a split minibatch)
   float* rowsum;  // free energy accumulator (M)
   uint64_t seed;
   uint64_t draw;  // draw id: distinct for every sampling launch
@@ -90,6 +91,8 @@ struct alignas(64) GemmParams {
   uint64_t draw_stride;  // draw += dyn->step * draw_stride
   // ---- descriptor overrides used only by the bring-up probe (0 = default) ----
   uint32_t dbg_lbo_a, dbg_sbo_a, dbg_adv_a, dbg_lbo_b, dbg_sbo_b, dbg_adv_b;
+  uint32_t dbg_flags;  // probe only: 1 = producer signals "full" without loading (MMA pacing alone),
+                       //             2 = MMA thread commits without multiplying (TMA pacing alone)
 };
 
 template <int BN>
@@ -369,10 +372,24 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
 // the chain (measured ~2e-5 relative at K = 4096).  Here the chain is cut every CH k-blocks: each piece
 // accumulates from zero in one of the two TMEM buffers and the epilogue warps sum the pieces in
 // registers with IEEE fp32 adds while the next piece is being multiplied.
-template <int BN, bool A_MN, bool B_MN, int EPI, int CH = 0>
+//
+// CG = 2: the CTA pair of one TPC computes a 256 x BN tile with tcgen05.mma.cta_group::2.  Each CTA stages
+// its own 128 rows of A and HALF of B (BN/2 columns) - the tensor cores of the pair exchange the B halves -
+// and accumulates its 128 rows in its own tensor memory.  Per SM and per K = 16 step that is 8 KB read from
+// shared memory (plus 8 KB written by TMA) instead of 12 + 12 KB: the single-CTA 128 x 256 kernel was
+// shared-memory-bandwidth-bound at 75 % tensor-pipe activity (profiles/r01_c3_proj_ncu.md).  Rank 0 of the
+// pair issues every MMA; TMA completions of both CTAs are counted on rank 0's barrier; rank 0's commits are
+// multicast to both CTAs; the epilogue warps of both CTAs release the accumulator on rank 0's barrier.
+template <int BN, bool A_MN, bool B_MN, int EPI, int CH = 0, int CG = 1>
 __global__ void __launch_bounds__(kNumThreads, 1) gemm_bf16_kernel(const __grid_constant__ GemmParams p) {
-  using Cfg = GemmCfg<BN>;
+  static_assert(CG == 1 || CG == 2, "cta_group");
+  constexpr int kBNLocal = BN / CG;  // B columns staged by this CTA
+  constexpr int kTileM = kBlockM * CG;
+  constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
+  using Cfg = GemmCfg<kBNLocal>;
   constexpr int kStages = Cfg::kStages;
+  const uint32_t cta_rank = CG == 2 ? ptx::cluster_ctarank() : 0u;
+  const int unit = blockIdx.x / CG, num_units = gridDim.x / CG;  // a unit = one CTA, or one CTA pair
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -386,7 +403,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_bf16_kernel(const __grid_
   const uint32_t warp = threadIdx.x >> 5;
   const uint32_t lane = ptx::lane_id();
 
-  const int num_m = (p.M + kBlockM - 1) / kBlockM;
+  const int num_m = (p.M + kTileM - 1) / kTileM;
   const int num_n = (p.N + BN - 1) / BN;
   const int num_tiles = num_m * num_n;
 
@@ -396,9 +413,12 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_bf16_kernel(const __grid_
   uint64_t draw = p.draw;
   int64_t row0 = p.row0;
   if (p.dyn != nullptr) {
-    if (p.dyn_rows != 0) row0 = static_cast<int64_t>(p.dyn_rank) * p.dyn->rows_valid;
-    dyn_row_off = static_cast<int32_t>(p.dyn->row_off);
-    if (p.dyn_rows != 0) m_valid = p.dyn->rows_valid < m_valid ? p.dyn->rows_valid : m_valid;
+    if (p.dyn_rows != 0) row0 = static_cast<int64_t>(p.dyn_rank) * p.dyn->rows_valid + p.dyn_row_base;
+    dyn_row_off = static_cast<int32_t>(p.dyn->row_off) + p.dyn_row_base;
+    if (p.dyn_rows != 0) {
+      const int32_t left = p.dyn->rows_valid - p.dyn_row_base;
+      m_valid = left < m_valid ? (left < 0 ? 0 : left) : m_valid;
+    }
     draw += p.dyn->step * p.draw_stride;
   }
 
@@ -416,47 +436,60 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_bf16_kernel(const __grid_
       }
       for (int s = 0; s < 2; ++s) {
         ptx::mbar_init(&tmem_full_bar[s], 1);
-        ptx::mbar_init(&tmem_empty_bar[s], kNumEpiWarps);
+        ptx::mbar_init(&tmem_empty_bar[s], kNumEpiWarps * CG);
       }
       ptx::fence_mbar_init();
     }
     __syncwarp();
-    ptx::tmem_alloc<1>(tmem_slot, Cfg::kTmemCols);
-    ptx::tmem_relinquish<1>();
+    ptx::tmem_alloc<CG>(tmem_slot, kTmemCols);
+    ptx::tmem_relinquish<CG>();
   }
   ptx::tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) ptx::cluster_sync(); else __syncthreads();  // peer barriers must exist before any remote arrive
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
     // ======================= TMA producer =======================
     if (lane == 0) {
+      auto tma_ld = [](void* dst, const CUtensorMap* tm, uint64_t* bar, int32_t c0, int32_t c1) {
+        if constexpr (CG == 2) ptx::tma_load_2d_pair(dst, tm, bar, c0, c1);  // bytes counted on rank 0's barrier
+        else ptx::tma_load_2d(dst, tm, bar, c0, c1);
+      };
       uint32_t stage = 0, phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = unit; tile < num_tiles; tile += num_units) {
         const int m_blk = tile / num_n, n_blk = tile % num_n;
-        const int m0 = m_blk * kBlockM, n0 = n_blk * BN;
+        const int m0 = m_blk * kTileM + static_cast<int>(cta_rank) * kBlockM;  // this CTA's rows of A
+        const int n0 = n_blk * BN + static_cast<int>(cta_rank) * kBNLocal;     // this CTA's columns of B
         for (int s = 0; s < p.num_seg; ++s) {
           const int a_off = ((p.a_dyn_mask >> s) & 1u) ? dyn_row_off : 0;  // A rows: M if K-major, K if MN-major
           for (int kb = 0; kb < p.kblocks; ++kb) {
             ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
-            ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+            if (p.dbg_flags & 1u) {
+              if (cta_rank == 0) ptx::mbar_arrive(&full_bar[stage]);
+              if (++stage == kStages) {
+                stage = 0;
+                phase ^= 1u;
+              }
+              continue;
+            }
+            if (cta_rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes * CG);
             uint8_t* sa = smem + stage * Cfg::kStageBytes;
             uint8_t* sb = sa + Cfg::kABytes;
             const int k0 = kb * kBlockK;
             if constexpr (!A_MN) {
-              ptx::tma_load_2d(sa, &p.tm_a[s], &full_bar[stage], k0, m0 + a_off);  // box {64 k, 128 m}
+              tma_ld(sa, &p.tm_a[s], &full_bar[stage], k0, m0 + a_off);  // box {64 k, 128 m}
             } else {
 #pragma unroll
               for (int j = 0; j < kBlockM / 64; ++j)  // boxes {64 m, 64 k}
-                ptx::tma_load_2d(sa + j * (kBlockK * 128), &p.tm_a[s], &full_bar[stage], m0 + 64 * j, k0 + a_off);
+                tma_ld(sa + j * (kBlockK * 128), &p.tm_a[s], &full_bar[stage], m0 + 64 * j, k0 + a_off);
             }
             if constexpr (!B_MN) {
-              ptx::tma_load_2d(sb, &p.tm_b[s], &full_bar[stage], k0, n0);  // box {64 k, BN n}
+              tma_ld(sb, &p.tm_b[s], &full_bar[stage], k0, n0);  // box {64 k, BN/CG n}
             } else {
 #pragma unroll
-              for (int j = 0; j < BN / 64; ++j)  // boxes {64 n, 64 k}
-                ptx::tma_load_2d(sb + j * (kBlockK * 128), &p.tm_b[s], &full_bar[stage], n0 + 64 * j, k0);
+              for (int j = 0; j < kBNLocal / 64; ++j)  // boxes {64 n, 64 k}
+                tma_ld(sb + j * (kBlockK * 128), &p.tm_b[s], &full_bar[stage], n0 + 64 * j, k0);
             }
             if (++stage == kStages) {
               stage = 0;
@@ -467,8 +500,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_bf16_kernel(const __grid_
       }
     }
   } else if (warp == 1) {
-    // ======================= MMA issuer =======================
-    if (lane == 0) {
+    // ======================= MMA issuer (rank 0 of a pair) =======================
+    if (lane == 0 && cta_rank == 0) {
       // K-major, 128B swizzle : rows of 128 B, 8-row groups 1024 B apart (SBO); a K=16 slice is 32 B along the row.
       // MN-major, 128B swizzle: 64-element MN chunks kBlockK*128 B apart (LBO); 8-k groups 1024 B apart (SBO);
       //                         a K=16 slice is two 8-k groups = 2048 B.
@@ -478,13 +511,17 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_bf16_kernel(const __grid_
       const uint32_t lbo_b = p.dbg_lbo_b ? p.dbg_lbo_b : (B_MN ? kBlockK * 128u : 16u);
       const uint32_t sbo_b = p.dbg_sbo_b ? p.dbg_sbo_b : 1024u;
       const uint32_t adv_b = p.dbg_adv_b ? p.dbg_adv_b : (B_MN ? 2048u : 32u);
-      constexpr uint32_t idesc_pos = make_idesc(kBlockM, BN, A_MN, B_MN, false);
-      constexpr uint32_t idesc_neg = make_idesc(kBlockM, BN, A_MN, B_MN, true);
+      constexpr uint32_t idesc_pos = make_idesc(kTileM, BN, A_MN, B_MN, false);
+      constexpr uint32_t idesc_neg = make_idesc(kTileM, BN, A_MN, B_MN, true);
+      auto commit = [](uint64_t* bar) {
+        if constexpr (CG == 2) ptx::mma_commit_pair(bar, 0b11);  // same-offset barrier in both CTAs
+        else ptx::mma_commit(bar);
+      };
 
       uint32_t stage = 0, phase = 0;
       uint32_t accn = 0;  // accumulator buffers handed to the epilogue so far
       const int total = p.num_seg * p.kblocks;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = unit; tile < num_tiles; tile += num_units) {
         uint32_t as = 0, d_tmem = 0;
         int it = 0;
         for (int s = 0; s < p.num_seg; ++s) {
@@ -505,17 +542,18 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_bf16_kernel(const __grid_
             const uint64_t db = make_smem_desc(sb, lbo_b, sbo_b);
 #pragma unroll
             for (int k = 0; k < kBlockK / 16; ++k) {
-              ptx::mma_bf16<1>(d_tmem, da + ((k * adv_a) >> 4), db + ((k * adv_b) >> 4), idesc,
+              if (p.dbg_flags & 2u) break;
+              ptx::mma_bf16<CG>(d_tmem, da + ((k * adv_a) >> 4), db + ((k * adv_b) >> 4), idesc,
                                (in_piece > 0 || k > 0) ? 1u : 0u);
             }
-            ptx::mma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+            commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
             if (++stage == kStages) {
               stage = 0;
               phase ^= 1u;
             }
             ++it;
             if (CH > 0 ? (it % (CH > 0 ? CH : 1) == 0 || it == total) : it == total) {
-              ptx::mma_commit(&tmem_full_bar[as]);  // this piece of the accumulation is complete
+              commit(&tmem_full_bar[as]);  // this piece of the accumulation is complete
               ++accn;
             }
           }
@@ -531,9 +569,13 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_bf16_kernel(const __grid_
     uint32_t accn = 0;
     const int total = p.num_seg * p.kblocks;
     const int pieces = CH > 0 ? (total + (CH > 0 ? CH : 1) - 1) / (CH > 0 ? CH : 1) : 1;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    auto release = [&](uint32_t as) {  // this warp has drained accumulator buffer `as`
+      if constexpr (CG == 2) ptx::mbar_arrive_cluster(&tmem_empty_bar[as], 0);
+      else ptx::mbar_arrive(&tmem_empty_bar[as]);
+    };
+    for (int tile = unit; tile < num_tiles; tile += num_units) {
       const int m_blk = tile / num_n, n_blk = tile % num_n;
-      const int row = m_blk * kBlockM + quarter * 32 + lane;
+      const int row = m_blk * kTileM + static_cast<int>(cta_rank) * kBlockM + quarter * 32 + lane;
       const bool row_ok = row < m_valid;
       float row_acc = 0.f;
       if constexpr (CH == 0) {
@@ -550,7 +592,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_bf16_kernel(const __grid_
         }
         ptx::tc_fence_before();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[as]);
+        if (lane == 0) release(as);
         ++accn;
       } else {
         float sum[kColsPerWarp];
@@ -570,7 +612,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_bf16_kernel(const __grid_
           }
           ptx::tc_fence_before();
           __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[as]);
+          if (lane == 0) release(as);
           ++accn;
         }
 #pragma unroll
@@ -588,10 +630,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_bf16_kernel(const __grid_
   }
 
   ptx::tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) ptx::cluster_sync(); else __syncthreads();  // no CTA leaves while its peer may still signal it
   if (warp == 1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc<1>(tmem_base, Cfg::kTmemCols);
+    ptx::tmem_dealloc<CG>(tmem_base, kTmemCols);
   }
 }
 

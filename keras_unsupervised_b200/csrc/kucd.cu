@@ -134,6 +134,10 @@ struct kucd_ctx {
   int num_sms = 0;
   uint64_t seed = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;  // second Gibbs chain of a split minibatch
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool split = true;               // KUCD_SPLIT=0 turns the two-chain schedule off, 2 forces it (tests)
+  bool split_force = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   kucd_timings tm{};
   void* comm = nullptr;
@@ -144,6 +148,7 @@ struct kucd_ctx {
   struct Mark {
     int cls;  // 0 = projection, 1 = dW
     size_t e0, e1;
+    int n;  // launches the interval covers
   };
   std::vector<Mark> marks;
   size_t ev_used = 0;
@@ -258,10 +263,10 @@ static void prof_collect(kucd_ctx* ctx) {
     if (cudaEventElapsedTime(&ms, ctx->ev_pool[m.e0], ctx->ev_pool[m.e1]) != cudaSuccess) continue;
     if (m.cls == 0) {
       ctx->tm.proj_ms += ms;
-      ctx->tm.proj_timed++;
+      ctx->tm.proj_timed += m.n;
     } else {
       ctx->tm.dw_ms += ms;
-      ctx->tm.dw_timed++;
+      ctx->tm.dw_timed += m.n;
     }
     ctx->tm.last_gemm_ms = ms;
   }
@@ -491,6 +496,9 @@ struct EpiArgs {
   int32_t m_valid = -1;
   const StepDyn* dyn = nullptr;
   bool a_dyn = false;  // A rows are offset by dyn->row_off (A is a whole data set)
+  int32_t row_base = 0;  // first minibatch row this launch covers (second chain of a split minibatch)
+  cudaStream_t stream = nullptr;  // default: the context stream
+  bool no_prof = false;
 };
 
 // forward: (rows,V).W + c -> (rows,H) ; backward: (rows,H).W^T + b -> (rows,V)
@@ -533,13 +541,15 @@ static int project(kucd_rbm* r, bool forward, const Planes& a, int64_t rows, con
   p.dyn = e.dyn;
   p.dyn_rows = e.dyn != nullptr ? 1 : 0;
   p.dyn_rank = ctx->rank;
+  p.dyn_row_base = e.row_base;
   p.a_dyn_mask = dyn_mask;
   std::string err;
-  const bool prof = ctx->profile && e.dyn == nullptr;
+  const bool prof = ctx->profile && e.dyn == nullptr && !e.no_prof;
   const size_t pe0 = prof ? prof_event(ctx) : 0;
-  if (!launch_gemm(p, ops, e.epi, ctx->num_sms, ctx->stream, &err, 0, r->compute == KUCD_COMPUTE_F32X3))
+  if (!launch_gemm(p, ops, e.epi, ctx->num_sms, e.stream != nullptr ? e.stream : ctx->stream, &err, 0,
+                   r->compute == KUCD_COMPUTE_F32X3))
     return fail(KUCD_ERR_CUDA, "%s", err.c_str());
-  if (prof) ctx->marks.push_back({0, pe0, prof_event(ctx)});
+  if (prof) ctx->marks.push_back({0, pe0, prof_event(ctx), 1});
   ctx->tm.gemm_launches++;
   return KUCD_OK;
 }
@@ -588,7 +598,7 @@ static int delta_w(kucd_rbm* r, const Planes& v0, const Planes& h0, const Planes
   const size_t pe0 = prof ? prof_event(ctx) : 0;
   if (!launch_gemm(p, ops, kEpiRaw, ctx->num_sms, ctx->stream, &err, 0, r->compute == KUCD_COMPUTE_F32X3))
     return fail(KUCD_ERR_CUDA, "%s", err.c_str());
-  if (prof) ctx->marks.push_back({1, pe0, prof_event(ctx)});
+  if (prof) ctx->marks.push_back({1, pe0, prof_event(ctx), 1});
   ctx->tm.gemm_launches++;
   return KUCD_OK;
 }
@@ -694,82 +704,125 @@ static int enqueue_cd(kucd_rbm* r, const Planes& v0, int64_t batch, const kucd_h
   // rows of the state buffers beyond the valid ones are written as zeros by the epilogues, so the
   // remainder minibatch contributes nothing to the batch-contracted dW
   const Planes h0 = r->h0.view(batch, r->H, 1);
-  {
-    EpiArgs e;
-    e.epi = epi_h;
-    e.out = h0;
-    e.u = inj ? inj->u_h[0] : nullptr;
-    e.ld_u = inj ? inj->ld_h[0] : 0;
-    e.colsum = r->dc();
-    e.colsum_sign = 1.f;
-    e.draw = draw0 + 0;
-    e.draw_stride = stride;
-    e.row0 = global_row0;
-    e.dyn = dyn;
-    e.a_dyn = v0_dyn;
-    KU_TRY(project(r, true, v0, batch, e));
-  }
   const int vparts = vis_parts_out(r);
   const int pparts = prob_parts_out(r);
-  Planes hcur = h0;
-  if (hp->persistent) {
-    // negative chain starts at the stored fantasy particles
-    const Planes ch = r->chains.view(batch, r->V, r->last_vk_parts);
-    EpiArgs e;
-    e.epi = epi_h;
-    e.out = r->hk.view(batch, r->H, 1);
-    e.u = inj ? inj->u_hc : nullptr;
-    e.ld_u = inj ? inj->ld_hc : 0;
-    e.draw = draw0 + 1;
-    e.draw_stride = stride;
-    e.row0 = global_row0;
-    e.dyn = dyn;
-    KU_TRY(project(r, true, ch, batch, e));
-    hcur = e.out;
-  }
-  Planes vk = r->vk.view(batch, r->V, vparts);
-  Planes hk = r->hk.view(batch, r->H, 1);
-  for (int t = 1; t <= k; ++t) {
+  const Planes vk = r->vk.view(batch, r->V, vparts);
+  const Planes hk = r->hk.view(batch, r->H, pparts);
+
+  auto rows_of = [](const Planes& p, int64_t r0, int64_t n, int parts) {
+    Planes q = p;
+    for (int i = 0; i < 3; ++i)
+      if (q.p[i] != nullptr) q.p[i] += r0 * q.ld;
+    q.rows = n;
+    q.n = parts;
+    return q;
+  };
+  auto u_at = [](const float* u, int64_t ld, int64_t r0) { return u != nullptr ? u + r0 * ld : nullptr; };
+
+  // One Gibbs chain over minibatch rows [r0, r0 + n): rows are independent given W, b, c (rbm.py:119-124).
+  auto chain = [&](int64_t r0, int64_t n, cudaStream_t st, bool timed) -> int {
+    const int64_t g0 = global_row0 + r0;
+    const int32_t base = static_cast<int32_t>(r0);
+    // v0 of a data set stays whole (the kernel offsets its TMA coordinate); a staged minibatch is sliced
+    const Planes v0s = v0_dyn ? v0 : rows_of(v0, r0, n, v0.n);
+    const Planes h0s = rows_of(h0, r0, n, 1);
+    auto common = [&](EpiArgs& e, int phase) {
+      e.draw = draw0 + phase;
+      e.draw_stride = stride;
+      e.row0 = g0;
+      e.dyn = dyn;
+      e.row_base = base;
+      e.stream = st;
+      e.no_prof = !timed;
+    };
     {
       EpiArgs e;
-      e.epi = epi_v;
-      e.out = vk;
-      e.u = inj ? inj->u_v[t] : nullptr;
-      e.ld_u = inj ? inj->ld_v[t] : 0;
-      if (t == k) {
-        e.colsum = r->db();
-        e.colsum_sign = -1.f;
-      }
-      e.draw = draw0 + 2 * t;
-      e.draw_stride = stride;
-      e.row0 = global_row0;
-      e.dyn = dyn;
-      KU_TRY(project(r, false, hcur, batch, e));
+      e.epi = epi_h;
+      e.out = h0s;
+      e.u = inj ? u_at(inj->u_h[0], inj->ld_h[0], r0) : nullptr;
+      e.ld_u = inj ? inj->ld_h[0] : 0;
+      e.colsum = r->dc();
+      e.colsum_sign = 1.f;
+      common(e, 0);
+      e.a_dyn = v0_dyn;
+      KU_TRY(project(r, true, v0s, n, e));
     }
-    {
+    Planes hcur = h0s;
+    if (hp->persistent) {
+      // negative chain starts at the stored fantasy particles
+      const Planes ch = rows_of(r->chains.view(batch, r->V, r->last_vk_parts), r0, n, r->last_vk_parts);
       EpiArgs e;
-      const bool last = t == k;
-      e.epi = last ? kEpiProb : epi_h;  // rbm.py:124: the final hidden term is the probability
-      hk = r->hk.view(batch, r->H, last ? pparts : 1);
-      e.out = hk;
-      e.u = (!last && inj) ? inj->u_h[t] : nullptr;
-      e.ld_u = (!last && inj) ? inj->ld_h[t] : 0;
-      if (last) {
-        e.colsum = r->dc();
-        e.colsum_sign = -1.f;
-      }
-      e.draw = draw0 + 2 * t + 1;
-      e.draw_stride = stride;
-      e.row0 = global_row0;
-      e.dyn = dyn;
-      KU_TRY(project(r, true, vk, batch, e));
-      hcur = hk;
+      e.epi = epi_h;
+      e.out = rows_of(hk, r0, n, 1);
+      e.u = inj ? u_at(inj->u_hc, inj->ld_hc, r0) : nullptr;
+      e.ld_u = inj ? inj->ld_hc : 0;
+      common(e, 1);
+      KU_TRY(project(r, true, ch, n, e));
+      hcur = e.out;
     }
+    const Planes vks = rows_of(vk, r0, n, vparts);
+    for (int t = 1; t <= k; ++t) {
+      {
+        EpiArgs e;
+        e.epi = epi_v;
+        e.out = vks;
+        e.u = inj ? u_at(inj->u_v[t], inj->ld_v[t], r0) : nullptr;
+        e.ld_u = inj ? inj->ld_v[t] : 0;
+        if (t == k) {
+          e.colsum = r->db();
+          e.colsum_sign = -1.f;
+        }
+        common(e, 2 * t);
+        KU_TRY(project(r, false, hcur, n, e));
+      }
+      {
+        EpiArgs e;
+        const bool last = t == k;
+        e.epi = last ? kEpiProb : epi_h;  // rbm.py:124: the final hidden term is the probability
+        e.out = rows_of(hk, r0, n, last ? pparts : 1);
+        e.u = (!last && inj) ? u_at(inj->u_h[t], inj->ld_h[t], r0) : nullptr;
+        e.ld_u = (!last && inj) ? inj->ld_h[t] : 0;
+        if (last) {
+          e.colsum = r->dc();
+          e.colsum_sign = -1.f;
+        }
+        common(e, 2 * t + 1);
+        KU_TRY(project(r, true, vks, n, e));
+        hcur = e.out;
+      }
+    }
+    return KUCD_OK;
+  };
+
+  // Two chains on two streams when each half still fills the GPU: a 128 x 256-tiled projection of a
+  // 4096-row minibatch is 512 tiles = 3.46 waves of 148 CTAs, and a lone kernel idles 13 % of the SMs in
+  // its last wave.  Split by rows, the tail of one chain's kernel is filled by the other chain's next
+  // kernel (their CTAs become resident as SMs drain), so the tensor pipes stay busy across launches.
+  const int64_t half = round_up((batch + 1) / 2, kBlockM);
+  const int64_t tiles_half = (half / kBlockM) * ((std::min(r->V, r->H) + 255) / 256);
+  const bool two = ctx->split && half < batch && (tiles_half >= ctx->num_sms || ctx->split_force);
+  const int n_proj = 2 * k + 1 + (hp->persistent ? 1 : 0);
+  if (!two) {
+    KU_TRY(chain(0, batch, ctx->stream, true));
+  } else {
+    const bool prof = ctx->profile && dyn == nullptr;
+    const size_t pe0 = prof ? prof_event(ctx) : 0;
+    CU_TRY(cudaEventRecord(ctx->ev_fork, ctx->stream));
+    CU_TRY(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
+    // interleave the enqueue order so both streams always have a kernel queued
+    int rc = chain(0, half, ctx->stream, false);
+    if (rc == KUCD_OK) rc = chain(half, batch - half, ctx->stream2, false);
+    // always re-join: a forked capture that is not joined cannot be ended
+    cudaEventRecord(ctx->ev_join, ctx->stream2);
+    cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0);
+    KU_TRY(rc);
+    if (prof) ctx->marks.push_back({0, pe0, prof_event(ctx), 2 * n_proj});
   }
   KU_TRY(delta_w(r, v0, h0, vk, hk, batch, dyn, v0_dyn));
   r->last_rows = batch;
   r->last_vk_parts = vparts;
   r->last_hk_parts = pparts;
+  (void)n_proj;
 
   if (hp->persistent) {
     for (int i = 0; i < vparts; ++i) {
@@ -909,6 +962,14 @@ int kucd_ctx_create(kucd_ctx** out, int device_id, uint64_t seed) {
   c->num_sms = prop.multiProcessorCount;
   c->seed = seed;
   CU_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CU_TRY(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+  CU_TRY(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+  CU_TRY(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+  {
+    const char* sp = getenv("KUCD_SPLIT");
+    c->split = !(sp != nullptr && sp[0] == '0');
+    c->split_force = sp != nullptr && sp[0] == '2';
+  }
   CU_TRY(cudaEventCreate(&c->ev0));
   CU_TRY(cudaEventCreate(&c->ev1));
   *out = c;
@@ -926,6 +987,9 @@ int kucd_ctx_destroy(kucd_ctx* ctx) {
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
   cudaEventDestroy(ctx->ev0);
   cudaEventDestroy(ctx->ev1);
+  cudaEventDestroy(ctx->ev_fork);
+  cudaEventDestroy(ctx->ev_join);
+  cudaStreamDestroy(ctx->stream2);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
   return KUCD_OK;

@@ -86,21 +86,39 @@ inline int pick_bn(int64_t M, int64_t N, int num_sms) {
 constexpr int kPreciseBN = 128;  // precise mode keeps BN/2 = 64 partial sums per epilogue thread in registers
 constexpr int kPreciseCH = 4;    // k-blocks (of 64) per tensor-memory accumulation piece
 
-template <int BN, bool A_MN, bool B_MN, int EPI, int CH = 0>
+template <int BN, bool A_MN, bool B_MN, int EPI, int CH = 0, int CG = 1>
 inline cudaError_t launch_one(const GemmParams& p, int num_sms, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
-  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, EPI, CH>;
+  using Cfg = GemmCfg<BN / CG>;
+  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, EPI, CH, CG>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  const int num_tiles = ((p.M + kBlockM - 1) / kBlockM) * ((p.N + BN - 1) / BN);
-  const int grid = num_tiles < num_sms ? num_tiles : num_sms;
+  const int tile_m = kBlockM * CG;
+  const int num_tiles = ((p.M + tile_m - 1) / tile_m) * ((p.N + BN - 1) / BN);
+  const int units = num_sms / CG;  // persistent: one CTA (or CTA pair) per SM (or TPC)
+  const int grid = (num_tiles < units ? num_tiles : units) * CG;
   if (grid <= 0) return cudaSuccess;
-  kern<<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(p);
-  return cudaGetLastError();
+  if constexpr (CG == 1) {
+    kern<<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(p);
+    return cudaGetLastError();
+  } else {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kNumThreads);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;  // the pair shares a TPC
+    attr[0].val.clusterDim.x = CG;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, p);
+  }
 }
 
 // Operand-major combinations the engine instantiates per epilogue (keeps the fatbin small):
@@ -115,26 +133,27 @@ constexpr bool combo_built() {
   return true;  // sample / prob: both directions
 }
 
-template <int BN, bool A_MN, bool B_MN, int EPI, int CH>
+template <int BN, bool A_MN, bool B_MN, int EPI, int CH, int CG>
 inline cudaError_t launch_if_built(const GemmParams& p, int num_sms, cudaStream_t s) {
   if constexpr (combo_built<EPI, A_MN, B_MN>())
-    return launch_one<BN, A_MN, B_MN, EPI, CH>(p, num_sms, s);
+    return launch_one<BN, A_MN, B_MN, EPI, CH, CG>(p, num_sms, s);
   else
     return cudaErrorInvalidValue;
 }
 
-template <int BN, int EPI, int CH>
+template <int BN, int EPI, int CH, int CG = 1>
 inline cudaError_t launch_major(const GemmParams& p, bool a_mn, bool b_mn, int num_sms, cudaStream_t s) {
-  if (!a_mn && !b_mn) return launch_if_built<BN, false, false, EPI, CH>(p, num_sms, s);
-  if (!a_mn && b_mn) return launch_if_built<BN, false, true, EPI, CH>(p, num_sms, s);
-  if (a_mn && b_mn) return launch_if_built<BN, true, true, EPI, CH>(p, num_sms, s);
-  return launch_if_built<BN, true, false, EPI, CH>(p, num_sms, s);
+  if (!a_mn && !b_mn) return launch_if_built<BN, false, false, EPI, CH, CG>(p, num_sms, s);
+  if (!a_mn && b_mn) return launch_if_built<BN, false, true, EPI, CH, CG>(p, num_sms, s);
+  if (a_mn && b_mn) return launch_if_built<BN, true, true, EPI, CH, CG>(p, num_sms, s);
+  return launch_if_built<BN, true, false, EPI, CH, CG>(p, num_sms, s);
 }
 
 template <int EPI>
-inline cudaError_t launch_bn(const GemmParams& p, int bn, bool precise, bool a_mn, bool b_mn, int num_sms,
+inline cudaError_t launch_bn(const GemmParams& p, int bn, bool precise, int cg, bool a_mn, bool b_mn, int num_sms,
                              cudaStream_t s) {
   if (precise) return launch_major<kPreciseBN, EPI, kPreciseCH>(p, a_mn, b_mn, num_sms, s);
+  if (cg == 2) return launch_major<256, EPI, 0, 2>(p, a_mn, b_mn, num_sms, s);
   switch (bn) {
     case 256: return launch_major<256, EPI, 0>(p, a_mn, b_mn, num_sms, s);
     case 128: return launch_major<128, EPI, 0>(p, a_mn, b_mn, num_sms, s);
@@ -143,13 +162,26 @@ inline cudaError_t launch_bn(const GemmParams& p, int bn, bool precise, bool a_m
 }
 
 // Fill the tensor maps / shape fields of `p` from `ops` (epilogue fields are the caller's) and launch.
+// cta_group::2 (256 x 256 tiles on CTA pairs) once the problem fills the chip with such tiles
+inline int pick_cg(int64_t M, int64_t N, int num_sms) {
+  static const int env = [] {
+    const char* e = getenv("KUCD_CG");
+    return e != nullptr ? atoi(e) : 0;
+  }();
+  if (env == 1 || env == 2) return env;
+  const int64_t tiles = ((M + 255) / 256) * ((N + 255) / 256);
+  return tiles >= num_sms / 2 ? 2 : 1;
+}
+
 inline bool launch_gemm(GemmParams& p, const GemmOperands& ops, int epi, int num_sms, cudaStream_t stream,
-                        std::string* err, int force_bn = 0, bool precise = false) {
+                        std::string* err, int force_bn = 0, bool precise = false, int force_cg = 0) {
   if (ops.num_seg < 1 || ops.num_seg > kMaxSeg) {
     if (err) *err = "bad segment count";
     return false;
   }
-  const int bn = precise ? kPreciseBN : (force_bn ? force_bn : pick_bn(ops.M, ops.N, num_sms));
+  int bn = precise ? kPreciseBN : (force_bn ? force_bn : pick_bn(ops.M, ops.N, num_sms));
+  int cg = precise ? 1 : (force_cg ? force_cg : ((force_bn == 0 || force_bn == 256) ? pick_cg(ops.M, ops.N, num_sms) : 1));
+  if (cg == 2) bn = 256;
   p.num_seg = ops.num_seg;
   p.neg_mask = ops.neg_mask;
   p.M = static_cast<int32_t>(ops.M);
@@ -158,16 +190,16 @@ inline bool launch_gemm(GemmParams& p, const GemmOperands& ops, int epi, int num
   if (p.m_valid <= 0 || p.m_valid > p.M) p.m_valid = p.M;
   for (int s = 0; s < ops.num_seg; ++s) {
     if (!make_tmap_bf16(&p.tm_a[s], ops.a[s], ops.a_mn ? 64u : static_cast<uint32_t>(kBlockM), err)) return false;
-    if (!make_tmap_bf16(&p.tm_b[s], ops.b[s], ops.b_mn ? 64u : static_cast<uint32_t>(bn), err)) return false;
+    if (!make_tmap_bf16(&p.tm_b[s], ops.b[s], ops.b_mn ? 64u : static_cast<uint32_t>(bn / cg), err)) return false;
   }
   cudaError_t e;
   switch (epi) {
-    case kEpiRaw: e = launch_bn<kEpiRaw>(p, bn, precise, ops.a_mn, ops.b_mn, num_sms, stream); break;
-    case kEpiSample: e = launch_bn<kEpiSample>(p, bn, precise, ops.a_mn, ops.b_mn, num_sms, stream); break;
-    case kEpiProb: e = launch_bn<kEpiProb>(p, bn, precise, ops.a_mn, ops.b_mn, num_sms, stream); break;
-    case kEpiFreeEnergy: e = launch_bn<kEpiFreeEnergy>(p, bn, precise, ops.a_mn, ops.b_mn, num_sms, stream); break;
-    case kEpiReluSample: e = launch_bn<kEpiReluSample>(p, bn, precise, ops.a_mn, ops.b_mn, num_sms, stream); break;
-    case kEpiGaussian: e = launch_bn<kEpiGaussian>(p, bn, precise, ops.a_mn, ops.b_mn, num_sms, stream); break;
+    case kEpiRaw: e = launch_bn<kEpiRaw>(p, bn, precise, cg, ops.a_mn, ops.b_mn, num_sms, stream); break;
+    case kEpiSample: e = launch_bn<kEpiSample>(p, bn, precise, cg, ops.a_mn, ops.b_mn, num_sms, stream); break;
+    case kEpiProb: e = launch_bn<kEpiProb>(p, bn, precise, cg, ops.a_mn, ops.b_mn, num_sms, stream); break;
+    case kEpiFreeEnergy: e = launch_bn<kEpiFreeEnergy>(p, bn, precise, cg, ops.a_mn, ops.b_mn, num_sms, stream); break;
+    case kEpiReluSample: e = launch_bn<kEpiReluSample>(p, bn, precise, cg, ops.a_mn, ops.b_mn, num_sms, stream); break;
+    case kEpiGaussian: e = launch_bn<kEpiGaussian>(p, bn, precise, cg, ops.a_mn, ops.b_mn, num_sms, stream); break;
     default:
       if (err) *err = "bad epilogue mode";
       return false;

@@ -6,6 +6,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import weakref
 
 import numpy as np
 
@@ -44,6 +45,7 @@ class Context:
         self.device = int(device)
         self.seed = int(seed)
         self.rank, self.world = 0, 1
+        self._children = weakref.WeakSet()  # machines / data sets: they must be destroyed before the context
 
     @classmethod
     def default(cls) -> "Context":
@@ -92,8 +94,16 @@ class Context:
 
     def close(self) -> None:
         if self.handle:
+            for child in list(self._children):
+                child.close()
             self.lib.kucd_ctx_destroy(self.handle)
             self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class Dataset:
@@ -101,6 +111,7 @@ class Dataset:
 
     def __init__(self, ctx: Context, handle):
         self.ctx, self.handle = ctx, handle
+        ctx._children.add(self)
 
     @classmethod
     def from_array(cls, ctx: Context, data, compute: int) -> "Dataset":
@@ -126,9 +137,9 @@ class Dataset:
         return out
 
     def close(self) -> None:
-        if self.handle:
+        if self.handle and self.ctx.handle:
             self.ctx.lib.kucd_dataset_destroy(self.handle)
-            self.handle = None
+        self.handle = None
 
     def __del__(self):
         try:
@@ -146,6 +157,7 @@ class Machine:
         h = C.c_void_p()
         L.check(ctx.lib.kucd_rbm_create(ctx.handle, self.V, self.H, self.mode, self.compute, C.byref(h)))
         self.handle = h
+        ctx._children.add(self)
         if seed is not None:
             self.set_seed(seed, 0)
 
@@ -301,9 +313,9 @@ class Machine:
         return Dataset(self.ctx, h)
 
     def close(self) -> None:
-        if self.handle:
+        if self.handle and self.ctx.handle:
             self.ctx.lib.kucd_rbm_destroy(self.handle)
-            self.handle = None
+        self.handle = None
 
     def __del__(self):
         try:

@@ -44,6 +44,17 @@ __global__ void ref_kernel(const __nv_bfloat16* const* a, const __nv_bfloat16* c
   c[(int64_t)m * ldc + n] = acc;
 }
 
+// SM clock actually delivered during the timing loop: cycle counter and wall clock of one SM, before and after
+__global__ void clock_probe(long long* out) {
+  unsigned smid;
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  out[0] = clock64();
+  out[1] = static_cast<long long>(t);
+  out[2] = smid;
+}
+
 static uint32_t rng_state = 12345u;
 static inline uint32_t xr() {
   rng_state ^= rng_state << 13;
@@ -79,8 +90,17 @@ int main(int argc, char** argv) {
   for (int s = 0; s < nseg; ++s) {
     std::vector<__nv_bfloat16> hA(a_rows * lda), hB(b_rows * ldb);
     // pads are filled with garbage on purpose: TMA bounds (not the pad) must make tails exact
-    for (auto& v : hA) v = __float2bfloat16((float)((int)(xr() % 5) - 2));
-    for (auto& v : hB) v = __float2bfloat16((float)((int)(xr() % 5) - 2));
+    const char* fill = getenv("KUCD_PROBE_FILL");  // "zero": all-zero operands, "rand": full-mantissa random bf16
+    if (fill != nullptr && fill[0] == 'z') {
+      for (auto& v : hA) v = __float2bfloat16(0.f);
+      for (auto& v : hB) v = __float2bfloat16(0.f);
+    } else if (fill != nullptr && fill[0] == 'r') {
+      for (auto& v : hA) v = __float2bfloat16(((int)(xr() % 65536) - 32768) / 32768.0f);
+      for (auto& v : hB) v = __float2bfloat16(((int)(xr() % 65536) - 32768) / 32768.0f);
+    } else {
+      for (auto& v : hA) v = __float2bfloat16((float)((int)(xr() % 5) - 2));
+      for (auto& v : hB) v = __float2bfloat16((float)((int)(xr() % 5) - 2));
+    }
     CK(cudaMalloc(&dA[s], hA.size() * 2));
     CK(cudaMalloc(&dB[s], hB.size() * 2));
     CK(cudaMemcpy(dA[s], hA.data(), hA.size() * 2, cudaMemcpyHostToDevice));
@@ -124,6 +144,7 @@ int main(int argc, char** argv) {
   p.dbg_lbo_b = dbg[3];
   p.dbg_sbo_b = dbg[4];
   p.dbg_adv_b = dbg[5];
+  if (const char* f = getenv("KUCD_DBG_FLAGS")) p.dbg_flags = (uint32_t)atoi(f);
   std::string err;
   if (!launch_gemm(p, ops, kEpiRaw, num_sms, 0, &err, bn)) {
     printf("LAUNCH FAIL: %s\n", err.c_str());
@@ -157,15 +178,27 @@ int main(int argc, char** argv) {
   if (bad) printf(" first=(%d,%d) got=%g want=%g", fm, fn, hC[(size_t)fm * ldc + fn], hR[(size_t)fm * ldc + fn]);
   printf("\n");
 
-  if (iters > 0 && bad == 0) {
+  if (iters > 0 && (bad == 0 || p.dbg_flags != 0 || getenv("KUCD_PROBE_FILL") != nullptr)) {
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0));
     CK(cudaEventCreate(&e1));
+    long long* dclk;
+    CK(cudaMalloc(&dclk, 6 * sizeof(long long)));
     for (int i = 0; i < 3; ++i) launch_gemm(p, ops, kEpiRaw, num_sms, 0, &err, bn);
+    clock_probe<<<1, 1>>>(dclk);
     CK(cudaEventRecord(e0));
     for (int i = 0; i < iters; ++i) launch_gemm(p, ops, kEpiRaw, num_sms, 0, &err, bn);
     CK(cudaEventRecord(e1));
+    clock_probe<<<1, 1>>>(dclk + 3);
     CK(cudaEventSynchronize(e1));
+    CK(cudaDeviceSynchronize());
+    long long hclk[6];
+    CK(cudaMemcpy(hclk, dclk, sizeof hclk, cudaMemcpyDeviceToHost));
+    if (hclk[2] == hclk[5])
+      printf("CLOCK sm %lld: %.0f MHz averaged over the timing loop\n", hclk[2],
+             1e3 * double(hclk[3] - hclk[0]) / double(hclk[4] - hclk[1]));
+    else
+      printf("CLOCK probes landed on different SMs (%lld, %lld)\n", hclk[2], hclk[5]);
     float ms = 0;
     CK(cudaEventElapsedTime(&ms, e0, e1));
     const double flop = 2.0 * M * N * (double)K * nseg;
