@@ -216,6 +216,11 @@ int kucd_rbm_fit_epoch(kucd_rbm* rbm, kucd_dataset* ds, int64_t batch, const kuc
 /* Minibatches [step_begin, step_end) of that epoch (step_end < 0: to the end). */
 int kucd_rbm_fit_range(kucd_rbm* rbm, kucd_dataset* ds, int64_t batch, const kucd_hparams* hp,
                        int64_t global_row0, int64_t step_begin, int64_t step_end, kucd_epoch_stats* stats);
+/* The same loop over a HOST-resident matrix (the numpy array RBM.fit receives, rbm.py:100): minibatch
+ * i+1 is copied to the GPU while minibatch i runs.  step_recon (nullable, one float per minibatch) receives
+ * every step's reconstruction error, read back asynchronously. */
+int kucd_rbm_fit_host(kucd_rbm* rbm, const kucd_tensor* V_all, int64_t batch, const kucd_hparams* hp,
+                      int64_t global_row0, float* step_recon, kucd_epoch_stats* stats);
 /* DBN.fit's inter-layer step (dbn.py:55): V_p <- transform(V_p) on the whole data set, on device. */
 int kucd_rbm_transform_dataset(kucd_rbm* rbm, kucd_dataset* in, kucd_dataset** out);
 int kucd_rbm_inv_transform_dataset(kucd_rbm* rbm, kucd_dataset* in, kucd_dataset** out);

@@ -103,6 +103,8 @@ SIGNATURES = {
     "kucd_rbm_fit_epoch": (C.c_int, [_P, _P, C.c_int64, C.POINTER(HParams), C.c_int64, C.POINTER(EpochStats)]),
     "kucd_rbm_fit_range": (C.c_int, [_P, _P, C.c_int64, C.POINTER(HParams), C.c_int64, C.c_int64, C.c_int64,
                                       C.POINTER(EpochStats)]),
+    "kucd_rbm_fit_host": (C.c_int, [_P, _TP, C.c_int64, C.POINTER(HParams), C.c_int64, C.POINTER(C.c_float),
+                                     C.POINTER(EpochStats)]),
     "kucd_rbm_transform_dataset": (C.c_int, [_P, _P, C.POINTER(_P)]),
     "kucd_rbm_inv_transform_dataset": (C.c_int, [_P, _P, C.POINTER(_P)]),
 }

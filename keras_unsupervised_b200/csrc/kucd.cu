@@ -136,6 +136,9 @@ struct kucd_ctx {
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;  // second Gibbs chain of a split minibatch
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaStream_t copy_stream = nullptr;  // host -> device staging of the next minibatch (fit_host)
+  cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
+  DevBuf stage_raw[2];
   bool split = true;               // KUCD_SPLIT=0 turns the two-chain schedule off, 2 forces it (tests)
   bool split_force = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -336,8 +339,11 @@ static int fetch_rows(kucd_ctx* ctx, const kucd_tensor* t, int64_t r0, int64_t n
   }
   const int64_t cols = t->shape[1];
   KU_TRY(staging.ensure(static_cast<size_t>(n) * cols * es));
-  CU_TRY(cudaMemcpy2DAsync(staging.p, cols * es, src, t->strides[0] * es, cols * es, n, cudaMemcpyHostToDevice,
-                           ctx->stream));
+  if (t->strides[0] == cols || n == 1)
+    CU_TRY(cudaMemcpyAsync(staging.p, src, static_cast<size_t>(n) * cols * es, cudaMemcpyHostToDevice, ctx->stream));
+  else
+    CU_TRY(cudaMemcpy2DAsync(staging.p, cols * es, src, t->strides[0] * es, cols * es, n, cudaMemcpyHostToDevice,
+                             ctx->stream));
   ctx->tm.h2d_bytes += n * cols * es;
   *ptr = staging.p;
   *ld = cols;
@@ -963,6 +969,11 @@ int kucd_ctx_create(kucd_ctx** out, int device_id, uint64_t seed) {
   c->seed = seed;
   CU_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CU_TRY(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+  CU_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    CU_TRY(cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
+    CU_TRY(cudaEventCreateWithFlags(&c->ev_consumed[i], cudaEventDisableTiming));
+  }
   CU_TRY(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
   CU_TRY(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
   {
@@ -987,6 +998,12 @@ int kucd_ctx_destroy(kucd_ctx* ctx) {
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
   cudaEventDestroy(ctx->ev0);
   cudaEventDestroy(ctx->ev1);
+  for (int i = 0; i < 2; ++i) {
+    cudaEventDestroy(ctx->ev_copied[i]);
+    cudaEventDestroy(ctx->ev_consumed[i]);
+    ctx->stage_raw[i].release();
+  }
+  cudaStreamDestroy(ctx->copy_stream);
   cudaEventDestroy(ctx->ev_fork);
   cudaEventDestroy(ctx->ev_join);
   cudaStreamDestroy(ctx->stream2);
@@ -1639,6 +1656,98 @@ static int fit_range_impl(kucd_rbm* r, kucd_dataset* ds, int64_t batch, const ku
     CU_TRY(cudaEventElapsedTime(&stats->device_ms, ctx->ev0, ctx->ev1));
   }
   return KUCD_OK;
+}
+
+// One pass over a HOST-resident matrix (rbm.py:163-223 with V as the caller's numpy array): the copy of
+// minibatch i+1 (copy stream, double-buffered staging) overlaps the Gibbs chain of minibatch i; every
+// step's reconstruction error is read back asynchronously into step_recon[i].
+int kucd_rbm_fit_host(kucd_rbm* r, const kucd_tensor* V_all, int64_t batch, const kucd_hparams* hp, int64_t global_row0,
+                      float* step_recon, kucd_epoch_stats* stats) {
+  if (r == nullptr) return fail(KUCD_ERR_INVALID_ARG, "rbm is NULL");
+  kucd_ctx* ctx = r->ctx;
+  CU_TRY(cudaSetDevice(ctx->device));
+  KU_TRY(check_hparams(hp));
+  KU_TRY(check_tensor(ctx, V_all, -1, r->V, "V"));
+  if (on_device(V_all)) return fail(KUCD_ERR_INVALID_ARG, "fit_host streams from host memory; use a data set for device data");
+  if (batch < 1 || batch > (1 << 22)) return fail(KUCD_ERR_INVALID_ARG, "batch_size %lld", (long long)batch);
+  const int64_t N = V_all->shape[0];
+  const int64_t steps = (N + batch - 1) / batch;  // rbm.py:110-111
+  if (stats != nullptr) memset(stats, 0, sizeof *stats);
+  if (steps == 0) return KUCD_OK;
+  KU_TRY(ensure_workspace(r, batch));
+  if (hp->persistent) KU_TRY(ensure_chains(r, std::min(batch, N)));
+  const int es = elem_size(V_all);
+  const int64_t cols = r->V;
+  for (int i = 0; i < 2; ++i) KU_TRY(ctx->stage_raw[i].ensure(static_cast<size_t>(batch) * cols * es));
+  float* host_stats = nullptr;
+  if (step_recon != nullptr) CU_TRY(cudaMallocHost(&host_stats, steps * sizeof(float)));
+  const bool x3 = r->compute == KUCD_COMPUTE_F32X3;
+  // fp32 data in fp32-grade mode is carried in all three terms (no per-step "is it exact" round trip)
+  const int live = (x3 && V_all->dtype_code == KUCD_DT_FLOAT) ? 3 : 1;
+  auto rows_of_step = [&](int64_t i) { return std::min(batch, N - i * batch); };
+  auto copy_in = [&](int64_t i) -> int {
+    const int slot = static_cast<int>(i & 1);
+    if (i >= 2) CU_TRY(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_consumed[slot], 0));
+    const char* src = static_cast<const char*>(V_all->data) + i * batch * V_all->strides[0] * es;
+    if (V_all->strides[0] == cols)  // contiguous rows: one linear DMA
+      CU_TRY(cudaMemcpyAsync(ctx->stage_raw[slot].p, src, static_cast<size_t>(rows_of_step(i)) * cols * es,
+                             cudaMemcpyHostToDevice, ctx->copy_stream));
+    else
+      CU_TRY(cudaMemcpy2DAsync(ctx->stage_raw[slot].p, cols * es, src, V_all->strides[0] * es, cols * es,
+                               rows_of_step(i), cudaMemcpyHostToDevice, ctx->copy_stream));
+    CU_TRY(cudaEventRecord(ctx->ev_copied[slot], ctx->copy_stream));
+    ctx->tm.h2d_bytes += rows_of_step(i) * cols * es;
+    return KUCD_OK;
+  };
+  int rc = KUCD_OK;
+  CU_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
+  rc = copy_in(0);
+  for (int64_t i = 0; i < steps && rc == KUCD_OK; ++i) {
+    const int slot = static_cast<int>(i & 1);
+    const int64_t n = rows_of_step(i);
+    if (i + 1 < steps) rc = copy_in(i + 1);
+    if (rc != KUCD_OK) break;
+    if (cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[slot], 0) != cudaSuccess) {
+      rc = fail(KUCD_ERR_CUDA, "stream wait failed");
+      break;
+    }
+    Planes v0 = r->vin.view(n, r->V, x3 ? 3 : 1);
+    const int grid = grid_for(ctx, n * (v0.ld / 8), 256);
+    by_dtype(V_all, [&](auto* tag) {
+      using T = std::remove_pointer_t<decltype(tag)>;
+      ingest_kernel<T><<<grid, 256, 0, ctx->stream>>>(static_cast<const T*>(ctx->stage_raw[slot].p), cols, n, cols,
+                                                      v0.p[0], v0.p[1], v0.p[2], v0.ld, x3 ? 3 : 1, nullptr);
+      return 0;
+    });
+    ctx->tm.aux_launches++;
+    cudaEventRecord(ctx->ev_consumed[slot], ctx->stream);
+    v0.n = live;
+    rc = enqueue_cd(r, v0, n, hp, nullptr, global_row0, r->step_count, nullptr, false);
+    r->step_count++;
+    if (rc == KUCD_OK && host_stats != nullptr) {
+      rc = enqueue_recon(r, v0, n);
+      if (rc == KUCD_OK &&
+          cudaMemcpyAsync(host_stats + i, r->stats.as<float>() + 1, 4, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
+        rc = fail(KUCD_ERR_CUDA, "statistic read-back failed");
+      ctx->tm.d2h_bytes += 4;
+    }
+    if (rc == KUCD_OK) rc = apply_update(r, hp, n * ctx->world);
+  }
+  cudaEventRecord(ctx->ev1, ctx->stream);
+  cudaStreamSynchronize(ctx->copy_stream);
+  const cudaError_t se = cudaStreamSynchronize(ctx->stream);
+  if (rc == KUCD_OK && se != cudaSuccess) rc = fail(KUCD_ERR_CUDA, "fit_host: %s", cudaGetErrorString(se));
+  if (host_stats != nullptr) {
+    if (rc == KUCD_OK) memcpy(step_recon, host_stats, steps * sizeof(float));
+    cudaFreeHost(host_stats);
+  }
+  if (rc == KUCD_OK && stats != nullptr) {
+    stats->steps = steps;
+    stats->rows = N;
+    cudaEventElapsedTime(&stats->device_ms, ctx->ev0, ctx->ev1);
+    if (step_recon != nullptr) stats->last_recon_err = step_recon[steps - 1];
+  }
+  return rc;
 }
 
 int kucd_rbm_fit_epoch(kucd_rbm* r, kucd_dataset* ds, int64_t batch, const kucd_hparams* hp, int64_t global_row0,

@@ -213,6 +213,20 @@ class RBM(object):
             ds, local_batch, row0, owns = V, batch, 0, False
         else:
             local, local_batch, row0 = self._shard(V, batch)
+            on_host = not (L._is_torch(local) and local.is_cuda)
+            if epochs == 1 and on_host and hps.get("stream", True):
+                # a single pass: stream the minibatches from host memory, copies overlapped with the chains
+                if verbose == 1:
+                    print(1, "/", epochs, " epochs", end="\r")
+                st = m.fit_host(local, local_batch, self._hparams(), global_row0=row0, want_recon=bool(verbose))
+                st["epoch"] = 1
+                if verbose:
+                    st["last_score"] = m.score(local[-(local.shape[0] % local_batch or local_batch):])
+                    n_step = int(st["steps"])
+                    print("\n{0:d}/{1:d}, score: {2:f}".format(n_step, n_step, st["last_score"]))
+                self.history.append(st)
+                m.ctx.sync()
+                return self
             ds, owns = Dataset.from_array(m.ctx, local, m.compute), True
         n_rows = ds.shape[0]
         num_step = int(math.ceil(n_rows / local_batch)) if n_rows else 0

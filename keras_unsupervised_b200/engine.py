@@ -302,6 +302,21 @@ class Machine:
                                                 C.byref(st) if want_stats else None))
         return {k: getattr(st, k) for k, _ in L.EpochStats._fields_}
 
+    def fit_host(self, V, batch: int, hp: L.HParams, global_row0: int = 0, want_recon: bool = True) -> dict:
+        """One pass over a host array, copies overlapped with compute; returns epoch stats + per-step recon."""
+        keep: list = []
+        t = L.tensor_of(V, keep)
+        steps = (t.shape[0] + batch - 1) // batch
+        recon = np.zeros(max(steps, 1), np.float32)
+        st = L.EpochStats()
+        L.check(self.ctx.lib.kucd_rbm_fit_host(self.handle, C.byref(t), C.c_int64(batch), C.byref(hp),
+                                               C.c_int64(global_row0),
+                                               recon.ctypes.data_as(C.POINTER(C.c_float)) if want_recon else None,
+                                               C.byref(st)))
+        out = {k: getattr(st, k) for k, _ in L.EpochStats._fields_}
+        out["step_recon_err"] = recon[:steps]
+        return out
+
     def transform_dataset(self, ds: Dataset) -> Dataset:
         h = C.c_void_p()
         L.check(self.ctx.lib.kucd_rbm_transform_dataset(self.handle, ds.handle, C.byref(h)))

@@ -370,3 +370,34 @@ def test_split_minibatch_two_chain_schedule(monkeypatch):
     assert np.abs(W - orc.W).mean() < 2e-6 and np.abs(W - orc.W).max() < 5e-3
     assert np.abs(b - orc.b).max() < 5e-3 and np.abs(c - orc.c).max() < 5e-3
     ctx2.close()
+
+
+def test_fit_host_streaming_equals_resident_fit(ctx):
+    """fit_host (minibatch i+1 copied while minibatch i runs) and fit_epoch (resident data set, graph
+    replay) draw the same Philox stream and must train the same model; per-step statistics come back."""
+    from keras_unsupervised_b200 import _lib as L
+    from keras_unsupervised_b200.engine import Dataset, Machine
+
+    rng = np.random.default_rng(97)
+    N, B, V, H, seed = 1000, 128, 300, 200, 3
+    data = _data(rng, N, V, 0.2)
+    hp = Machine.hparams(lr=1e-3, k=2)
+    a, _ = _machine(ctx, V, H, "bf16", seed=seed)
+    b, orc = _machine(ctx, V, H, "bf16", seed=seed)
+    ds = Dataset.from_array(ctx, data, L.COMPUTE_BF16)
+    a.fit_epoch(ds, B, hp)
+    before = ctx.timings(reset=True)
+    st = b.fit_host(data, B, hp)
+    t = ctx.timings()
+    assert st["steps"] == 8 and st["step_recon_err"].shape == (8,)
+    assert np.all(st["step_recon_err"] > 0) and np.all(st["step_recon_err"] < 1)
+    assert t["h2d_bytes"] == data.nbytes and t["d2h_bytes"] == 8 * 4
+    Wa, ba, ca = a.get_params()
+    Wb, bb, cb = b.get_params()
+    np.testing.assert_allclose(Wa, Wb, rtol=0, atol=2e-6)
+    np.testing.assert_allclose(ba, bb, rtol=0, atol=2e-6)
+    O.philox_fit(orc, data, B, 1, 1e-3, seed, k=2)
+    # bf16 mode: probabilities agree to ~1e-6, so over 1 M draws a couple of samples sit inside the rounding
+    # gap and flip; each flip moves one row/column of W by lr
+    assert np.abs(Wb - orc.W).mean() < 5e-5 and np.abs(Wb - orc.W).max() < 5e-3
+    ds.close()
