@@ -35,6 +35,16 @@ WORKLOADS = {
                desc="Bernoulli RBM 4096->4096, CD-10, batch 4096 per GPU, bf16 (BASELINE.json configs[2])"),
     "c1": dict(V=784, H=500, B=128, k=1, dtype="bf16", q=0.1307,
                desc="Bernoulli RBM 784->500, CD-1, batch 128 (BASELINE.json configs[0])"),
+    "c1f32": dict(V=784, H=500, B=128, k=1, dtype="f32", q=0.1307,
+                  desc="Bernoulli RBM 784->500, CD-1, batch 128, float32-grade contractions (BASELINE.json configs[0])"),
+    "c4": dict(V=16384, H=8192, B=1024, k=1, dtype="bf16", q=0.5, persistent=True,
+               desc="PCD RBM 16384->8192, 1024 rows + 1024 persistent chains per GPU (8192 over 8 GPUs), bf16 "
+                    "(BASELINE.json configs[3])"),
+    # handled by run_dbn / run_infer
+    "c2": dict(V=784, H=500, B=256, k=1, dtype="bf16", q=0.1307, layers=[784, 500, 500, 2000],
+               desc="DBN 784-500-500-2000 greedy layer-wise CD-1 pretraining, batch 256 (BASELINE.json configs[1])"),
+    "c5": dict(V=4096, H=4096, B=0, k=0, dtype="bf16", q=0.5,
+               desc="RBM transform / free-energy inference sweep, 1K..1M rows, 4096->4096 (BASELINE.json configs[4])"),
 }
 METRIC = "RBM CD-k training samples/sec"
 UNIT = "samples/s"
@@ -137,7 +147,159 @@ def cpu_arm(cfg, steps, warmup, rows):
     return dict(value=rows * steps / dt, seconds=dt, cores=cores, rows=rows, steps=steps)
 
 
+def _events(ctx, local_rank):
+    import torch
+
+    ext = torch.cuda.ExternalStream(ctx.stream_ptr(), device=torch.device("cuda", local_rank))
+    return ext, torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+
+def run_dbn(cfg, ctx, compute, steps, warmup, config):
+    """C2: greedy layer-wise pretraining of a 784-500-500-2000 DBN (dbn.py:51-55): per layer one epoch of CD-1
+    over N = steps * 256 rows, then the full-data transform that feeds the next layer - all on the GPU.  One
+    whole pass is the warm-up, a second whole pass (fresh models; includes each layer's graph capture and the
+    allocation of the inter-layer data sets, as a user's DBN.fit does) is timed."""
+    import numpy as np
+    import torch
+
+    from keras_unsupervised_b200 import _lib as L
+    from keras_unsupervised_b200.engine import Dataset, Machine
+
+    dims, B = cfg["layers"], cfg["B"]
+    N = steps * B
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(1234)
+    X = (torch.rand((N, dims[0]), device="cuda", generator=gen) < cfg["q"]).to(torch.uint8)
+    ds0 = Dataset.from_array(ctx, X, compute)
+    hp = Machine.hparams(lr=1e-3, k=1)
+    prng = np.random.default_rng(0)
+
+    def one_pass():
+        ms, cur, made = [], ds0, []
+        for i in range(len(dims) - 1):
+            m = Machine(ctx, dims[i], dims[i + 1], L.MODE_VISIBLE_BERNOULLI, compute, seed=42 + i)
+            m.set_params(prng.uniform(-0.05, 0.05, (dims[i], dims[i + 1])).astype(np.float32),
+                         prng.uniform(-0.05, 0.05, dims[i]).astype(np.float32),
+                         prng.uniform(-0.05, 0.05, dims[i + 1]).astype(np.float32))
+            ms.append(m)
+        ctx.sync()
+        ext, e0, e1 = _events(ctx, ctx.device)
+        ctx.timings(reset=True)
+        tw0 = time.time()
+        e0.record(ext)
+        for i, m in enumerate(ms):
+            m.fit_epoch(cur, B, hp, want_stats=False)
+            if i + 1 < len(ms):
+                cur = m.transform_dataset(cur)
+                made.append(cur)
+        e1.record(ext)
+        ctx.sync()
+        torch.cuda.synchronize()
+        tw1 = time.time()
+        t = ctx.timings()
+        for d in made:
+            d.close()
+        for m in ms:
+            m.close()
+        return e0.elapsed_time(e1), t, (tw0, tw1)
+
+    one_pass()
+    ms_total, t, win = one_pass()
+    flop = sum((2 * 1 + 3) * 2 * dims[i] * dims[i + 1] for i in range(len(dims) - 1)) + \
+        sum(2 * dims[i] * dims[i + 1] for i in range(len(dims) - 2))
+    config = dict(config, layers=dims, rows=N, batch_per_gpu=B, k=1)
+    return {"metric": METRIC, "value": N / (ms_total * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": steps, "warmup": warmup,
+            "ms_per_step": ms_total / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": cfg["dtype"], "data": "synthetic binarised (Bernoulli %.4g)" % cfg["q"], "config": config,
+            "gpu_launches": int(t["graph_kernel_launches"] + t["gemm_launches"] + t["aux_launches"]),
+            "note": "a sample passes through all three layers; latency-bound (0.5-2.6 GFLOP per step)",
+            "tflops": flop * N / (ms_total * 1e-3) / 1e12, "_windows": [win]}
+
+
+def run_infer(cfg, ctx, compute, steps, warmup, config):
+    """C5: transform (sampled hidden states, rbm.py:88) and free energy (rbm.py:97) over n rows resident in HBM."""
+    import numpy as np
+    import torch
+
+    from keras_unsupervised_b200 import _lib as L
+    from keras_unsupervised_b200.engine import Dataset, Machine
+
+    V, H = cfg["V"], cfg["H"]
+    m = Machine(ctx, V, H, L.MODE_VISIBLE_BERNOULLI, compute, seed=42)
+    prng = np.random.default_rng(0)
+    m.set_params(prng.uniform(-0.05, 0.05, (V, H)).astype(np.float32), prng.uniform(-0.05, 0.05, V).astype(np.float32),
+                 prng.uniform(-0.05, 0.05, H).astype(np.float32))
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(1234)
+    pk = peaks()
+    sweep, windows = [], []
+    for logn in (10, 12, 14, 16, 18, 20):
+        n = 1 << logn
+        X = torch.empty((n, V), dtype=torch.uint8, device="cuda")
+        for r0 in range(0, n, 65536):
+            r1 = min(n, r0 + 65536)
+            X[r0:r1] = (torch.rand((r1 - r0, V), device="cuda", generator=gen) < cfg["q"]).to(torch.uint8)
+        ds = Dataset.from_array(ctx, X, compute)
+        reps = max(3, min(50, (1 << 22) // n))
+        for _ in range(3):
+            m.transform_dataset(ds).close()
+        ctx.sync()
+        ext, e0, e1 = _events(ctx, ctx.device)
+        outs = []
+        tw0 = time.time()
+        e0.record(ext)
+        for _ in range(reps):
+            outs.append(m.transform_dataset(ds))
+        e1.record(ext)
+        ctx.sync()
+        torch.cuda.synchronize()
+        t_tr = e0.elapsed_time(e1) / reps
+        for o in outs:
+            o.close()
+        nfe = min(n, 1 << 18)
+        Xfe = X[:nfe]
+        m.free_energy(Xfe)
+        e0.record(ext)
+        for _ in range(3):
+            m.free_energy(Xfe)
+        e1.record(ext)
+        ctx.sync()
+        torch.cuda.synchronize()
+        t_fe = e0.elapsed_time(e1) / 3
+        windows.append((tw0, time.time()))
+        sweep.append({"rows": n, "transform_ms": t_tr, "transform_rows_per_s": n / (t_tr * 1e-3),
+                      "transform_tflops": 2.0 * n * V * H / (t_tr * 1e-3) / 1e12,
+                      "transform_frac_of_sustained": 2.0 * n * V * H / (t_tr * 1e-3) / 1e12 / pk["sustained"],
+                      "free_energy_rows": nfe, "free_energy_rows_per_s": nfe / (t_fe * 1e-3)})
+        ds.close()
+        del X
+    best = sweep[-1]
+    return {"metric": "RBM transform rows/sec", "value": best["transform_rows_per_s"], "unit": "rows/s", "n_gpus": 1,
+            "steps": steps, "warmup": warmup, "ms_per_step": best["transform_ms"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": cfg["dtype"],
+            "data": "synthetic binarised (Bernoulli %.4g)" % cfg["q"], "config": config, "sweep": sweep,
+            "note": "transform: resident data set in, resident data set out, one launch (allocation of the output "
+                    "included); free energy: device tensor in, device vector out, 32768-row chunks", "_windows": windows}
+
+
+def _claim_stdout():
+    """Libraries (NCCL's version banner, torchrun notices) write to fd 1; the contract is ONE JSON line there.
+    Everything else goes to stderr: keep the real stdout aside and point fd 1 at fd 2."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(real, "w")
+
+
 def main():
+    out = _claim_stdout()
+    try:
+        return _main(out)
+    finally:
+        out.flush()
+
+
+def _main(out):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
@@ -172,7 +334,7 @@ def main():
                                            "numpy/BLAS oracle port of ku/ebm/rbm.py" % (steps, rows, B, k)},
                 "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line))
+        print(json.dumps(line), file=out)
         return 0
 
     import numpy as np
@@ -193,6 +355,12 @@ def main():
     sampler = ClockSampler(local_rank) if rank == 0 else None
 
     compute = L.COMPUTE_BF16 if cfg["dtype"] == "bf16" else L.COMPUTE_F32X3
+    if args.workload in ("c2", "c5"):
+        fn = run_dbn if args.workload == "c2" else run_infer
+        line = fn(cfg, ctx, compute, steps, warmup, config)
+        line["clocks"] = sampler.stop(line.pop("_windows")) if sampler is not None else None
+        print(json.dumps(line), file=out)
+        return 0
     m = Machine(ctx, V, H, L.MODE_VISIBLE_BERNOULLI, compute, seed=42)
     prng = np.random.default_rng(0)
     m.set_params(prng.uniform(-0.05, 0.05, (V, H)).astype(np.float32), prng.uniform(-0.05, 0.05, V).astype(np.float32),
@@ -207,7 +375,10 @@ def main():
         X[i * B:(i + 1) * B] = (torch.rand((B, V), device="cuda", generator=gen) < cfg["q"]).to(torch.uint8)
     torch.cuda.synchronize()
     ds = Dataset.from_array(ctx, X, compute)
-    hp = Machine.hparams(lr=1e-3, k=k, normalize=True)
+    persistent = bool(cfg.get("persistent"))
+    if persistent:
+        m.set_chains((torch.rand((B, V), device="cuda", generator=gen) < 0.5).to(torch.uint8))
+    hp = Machine.hparams(lr=1e-3, k=k, normalize=True, persistent=persistent)
     row0 = rank * B
 
     def barrier():
@@ -252,7 +423,7 @@ def main():
         host = torch.empty((n_e2e * B, V), dtype=torch.float32).pin_memory()
         for i in range(n_e2e):
             host[i * B:(i + 1) * B].copy_(X[(i % n_batches) * B:((i % n_batches) + 1) * B].to(torch.float32))
-        hp_e = Machine.hparams(lr=1e-3, k=k, normalize=True)
+        hp_e = Machine.hparams(lr=1e-3, k=k, normalize=True, persistent=persistent)
         m.fit_host(host[:2 * B], B, hp_e, global_row0=row0)  # warm-up: staging buffers, pinned result buffer
         barrier()
         ctx.timings(reset=True)
@@ -281,7 +452,7 @@ def main():
         barrier()
         ctx.set_profile(True)
         ctx.timings(reset=True)
-        hp_d = Machine.hparams(lr=1e-3, k=k, normalize=True)
+        hp_d = Machine.hparams(lr=1e-3, k=k, normalize=True, persistent=persistent)
         n_prof = 3
         tw0 = time.time()
         for i in range(n_prof):
@@ -293,7 +464,7 @@ def main():
         if tp["proj_timed"] and rank == 0:
             per_launch_ms = tp["proj_ms"] / tp["proj_timed"]
             # 2k+1 projections per step; with the two-chain schedule each is launched as two row-halves
-            flop = n_prof * (2 * k + 1) * 2.0 * B * V * H / tp["proj_timed"]
+            flop = n_prof * (2 * k + 1 + (1 if persistent else 0)) * 2.0 * B * V * H / tp["proj_timed"]
             ach = flop / (per_launch_ms * 1e-3) / 1e12
             traffic = None
             tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
@@ -330,7 +501,7 @@ def main():
                 "per_gpu": {"samples_per_s": value / world,
                             "tflops": flops_per_sample(V, H, k) * value / world / 1e12,
                             "frac_of_sustained_bf16_peak": flops_per_sample(V, H, k) * value / world / 1e12 / pk["sustained"]}}
-        print(json.dumps(line))
+        print(json.dumps(line), file=out)
     if dist is not None:
         dist.destroy_process_group()
     return 0
