@@ -1,0 +1,292 @@
+// The whole Gibbs chain of one minibatch as ONE persistent kernel.
+//
+// A CD-k step is 2k+1 projections, each consuming the previous one's output:
+//   h0 = S(v0.W + c);  v1 = S(h0.W^T + b);  h1 = S(v1.W + c);  ...  vk;  hk = sigmoid(vk.W + c)   (rbm.py:119-124)
+// Launched one by one, every projection pays a launch, a prologue (barriers, tensor-memory allocation, first TMA
+// round trip), a last-epilogue tail during which the tensor pipe idles, and a partial last wave (512 tiles on 148
+// SMs = 3.46 waves).  But the dependency between consecutive projections is only per ROW BLOCK: an output tile
+// (rows R, columns C) of projection s+1 needs rows R of projection s - all its column tiles - and nothing else.
+// So the chain is flattened into one tile sequence (stage-major, row-block-major inside a stage), CTA pairs walk it
+// round-robin, and before loading the A operand of a tile the producer waits until the row block it reads has
+// been completely written: a counter per (stage, row block) in global memory, incremented by every CTA that finishes
+// a tile of that row block, read with acquire semantics.  The tail of stage s overlaps the head of stage s+1, and
+// quantisation is paid once per minibatch (5376 tiles = 72.6 waves at C3) instead of once per projection.
+//
+// Every wait is on a tile that comes EARLIER in the sequence and every pair walks the sequence in order, so the
+// smallest unfinished tile can always run: no deadlock as long as all pairs are resident (grid <= SM count).
+// Memory ordering: epilogue stores (generic proxy) -> fence.proxy.async -> CTA barrier -> __threadfence +
+// atomicAdd (release);  consumer: ld.acquire spin -> fence.proxy.async -> TMA load (async proxy).
+//
+// Same pipeline as gemm_bf16_kernel<256, ..., CG = 2>: TMA producer warp, one MMA-issuing thread on rank 0 of the
+// pair (tcgen05.mma.cta_group::2, 256 x 256 tiles), eight epilogue warps per CTA, double-buffered TMEM.
+#pragma once
+#include "gemm.cuh"
+
+namespace kucd {
+
+constexpr int kMaxChainStages = 64;  // 2k+2 with k <= 31
+constexpr int kMaxChainKinds = 8;
+constexpr int kChainBN = 256;
+
+// The few distinct projections a chain is made of (member names shared with GemmParams: epilogue_chunk reads them).
+struct ChainKind {
+  const float* bias;
+  __nv_bfloat16* out_bf16;
+  __nv_bfloat16* out_mid;
+  __nv_bfloat16* out_lo;
+  int64_t ld_bf16;
+  float* out_f32;
+  int64_t ld_f32;
+  const float* u_inject;
+  int64_t ld_u;
+  float* colsum;
+  float colsum_sign;
+  int32_t epi;  // kEpiSample or kEpiProb
+  float* rowsum;
+  int32_t M, N;
+  uint64_t seed;
+  int32_t kblocks;
+  int32_t b_mn;   // 1: W read as (K,N) (v.W), 0: W read as (N,K) (h.W^T)
+  int32_t map_a, map_b;
+  int32_t a_dyn;  // A is the resident data set: rows offset by dyn->row_off
+  int32_t num_n;
+};
+
+struct ChainStageRef {
+  int16_t kind;
+  int16_t dep;     // stage whose row block must be complete before this stage reads it (-1: none)
+  uint32_t phase;  // Philox draw id offset inside the step
+};
+
+struct alignas(64) ChainParams {
+  CUtensorMap maps[8];
+  ChainKind kinds[kMaxChainKinds];
+  ChainStageRef stages[kMaxChainStages];
+  int32_t num_stages;
+  int32_t M;        // minibatch rows (buffer capacity)
+  int32_t m_valid;  // rows that carry data
+  int32_t total_tiles;
+  uint32_t* done;   // [num_stages][num_m] tiles-finished counters, zeroed before the launch
+  uint64_t draw;
+  uint64_t draw_stride;
+  int64_t row0;
+  const StepDyn* dyn;
+  int32_t dyn_rank;
+  int32_t pad;
+};
+
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(kNumThreads, 1) chain_kernel(const __grid_constant__ ChainParams p) {
+  constexpr int BN = kChainBN, CG = 2;
+  constexpr int kBNLocal = BN / CG;
+  constexpr int kTileM = kBlockM * CG;
+  constexpr int kTmemCols = 2 * BN;
+  using Cfg = GemmCfg<kBNLocal>;
+  constexpr int kStages = Cfg::kStages;
+  const uint32_t cta_rank = ptx::cluster_ctarank();
+  const int unit = blockIdx.x / CG, num_units = gridDim.x / CG;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* ctrl = smem + kStages * Cfg::kStageBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(ctrl);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full_bar = empty_bar + kStages;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const uint32_t warp = threadIdx.x >> 5;
+  const uint32_t lane = ptx::lane_id();
+  const int num_m = (p.M + kTileM - 1) / kTileM;
+
+  int32_t dyn_row_off = 0;
+  int32_t m_valid = p.m_valid;
+  uint64_t draw_base = p.draw;
+  int64_t row0 = p.row0;
+  if (p.dyn != nullptr) {
+    row0 = static_cast<int64_t>(p.dyn_rank) * p.dyn->rows_valid;
+    dyn_row_off = static_cast<int32_t>(p.dyn->row_off);
+    m_valid = p.dyn->rows_valid < m_valid ? p.dyn->rows_valid : m_valid;
+    draw_base += p.dyn->step * p.draw_stride;
+  }
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < 8; ++i) ptx::prefetch_tensormap(&p.maps[i]);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < kStages; ++s) {
+        ptx::mbar_init(&full_bar[s], 1);
+        ptx::mbar_init(&empty_bar[s], 1);
+      }
+      for (int s = 0; s < 2; ++s) {
+        ptx::mbar_init(&tmem_full_bar[s], 1);
+        ptx::mbar_init(&tmem_empty_bar[s], kNumEpiWarps * CG);
+      }
+      ptx::fence_mbar_init();
+    }
+    __syncwarp();
+    ptx::tmem_alloc<CG>(tmem_slot, kTmemCols);
+    ptx::tmem_relinquish<CG>();
+  }
+  ptx::tc_fence_before();
+  ptx::cluster_sync();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // walk the flattened (stage, row block, column tile) sequence: q -> stage s, first tile `base` of that stage
+  auto advance = [&](int q, int& s, int& base) {
+    while (q >= base + num_m * p.kinds[p.stages[s].kind].num_n) {
+      base += num_m * p.kinds[p.stages[s].kind].num_n;
+      ++s;
+    }
+  };
+
+  if (warp == 0) {
+    // ======================= TMA producer =======================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      int s = 0, base = 0;
+      for (int q = unit; q < p.total_tiles; q += num_units) {
+        advance(q, s, base);
+        const ChainKind& kd = p.kinds[p.stages[s].kind];
+        const int t = q - base;
+        const int m_blk = t / kd.num_n, n_blk = t % kd.num_n;
+        const int dep = p.stages[s].dep;
+        if (dep >= 0) {
+          // the row block this tile reads must have been written by every column tile of stage `dep` (both CTAs)
+          const uint32_t need = static_cast<uint32_t>(p.kinds[p.stages[dep].kind].num_n) * CG;
+          const uint32_t* flag = p.done + dep * num_m + m_blk;
+          if (ld_acquire_gpu(flag) < need) {
+            const long long t0 = clock64();
+            while (ld_acquire_gpu(flag) < need) {
+              if (clock64() - t0 > KUCD_SPIN_LIMIT_CYCLES) {
+                printf("kucd: chain dependency wait timed out (block %d stage %d row block %d: %u of %u)\n", blockIdx.x,
+                       s, m_blk, ld_acquire_gpu(flag), need);
+                __trap();
+              }
+            }
+          }
+          ptx::fence_proxy_async_global();
+        }
+        const int m0 = m_blk * kTileM + static_cast<int>(cta_rank) * kBlockM + (kd.a_dyn ? dyn_row_off : 0);
+        const int n0 = n_blk * BN + static_cast<int>(cta_rank) * kBNLocal;
+        const CUtensorMap* ma = &p.maps[kd.map_a];
+        const CUtensorMap* mb = &p.maps[kd.map_b];
+        for (int kb = 0; kb < kd.kblocks; ++kb) {
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
+          if (cta_rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes * CG);
+          uint8_t* sa = smem + stage * Cfg::kStageBytes;
+          uint8_t* sb = sa + Cfg::kABytes;
+          const int k0 = kb * kBlockK;
+          ptx::tma_load_2d_pair(sa, ma, &full_bar[stage], k0, m0);  // box {64 k, 128 rows}
+          if (kd.b_mn) {
+#pragma unroll
+            for (int j = 0; j < kBNLocal / 64; ++j)  // boxes {64 n, 64 k}
+              ptx::tma_load_2d_pair(sb + j * (kBlockK * 128), mb, &full_bar[stage], n0 + 64 * j, k0);
+          } else {
+            ptx::tma_load_2d_pair(sb, mb, &full_bar[stage], k0, n0);  // box {64 k, 128 n}
+          }
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ======================= MMA issuer (rank 0 of the pair) =======================
+    if (lane == 0 && cta_rank == 0) {
+      uint32_t stage = 0, phase = 0;
+      uint32_t accn = 0;
+      int s = 0, base = 0;
+      for (int q = unit; q < p.total_tiles; q += num_units) {
+        advance(q, s, base);
+        const ChainKind& kd = p.kinds[p.stages[s].kind];
+        const bool b_mn = kd.b_mn != 0;
+        const uint32_t idesc = make_idesc(kTileM, BN, false, b_mn, false);
+        const uint32_t lbo_b = b_mn ? kBlockK * 128u : 16u;
+        const uint32_t adv_b = b_mn ? 2048u : 32u;
+        const uint32_t as = accn & 1u;
+        ptx::mbar_wait(&tmem_empty_bar[as], ((accn >> 1) & 1u) ^ 1u);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = 0; kb < kd.kblocks; ++kb) {
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::tc_fence_after();
+          const uint32_t sa = ptx::smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint32_t sb = sa + Cfg::kABytes;
+          const uint64_t da = make_smem_desc(sa, 16u, 1024u);
+          const uint64_t db = make_smem_desc(sb, lbo_b, 1024u);
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k)
+            ptx::mma_bf16<CG>(d_tmem, da + ((k * 32u) >> 4), db + ((k * adv_b) >> 4), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          ptx::mma_commit_pair(&empty_bar[stage], 0b11);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        ptx::mma_commit_pair(&tmem_full_bar[as], 0b11);
+        ++accn;
+      }
+    }
+  } else {
+    // ======================= epilogue =======================
+    const uint32_t ew = warp - 2;
+    const uint32_t quarter = warp & 3u;
+    const uint32_t half = ew >> 2;
+    constexpr int kColsPerWarp = BN / 2;
+    uint32_t accn = 0;
+    int s = 0, base = 0;
+    for (int q = unit; q < p.total_tiles; q += num_units) {
+      advance(q, s, base);
+      const ChainKind& kd = p.kinds[p.stages[s].kind];
+      const int t = q - base;
+      const int m_blk = t / kd.num_n, n_blk = t % kd.num_n;
+      const int row = m_blk * kTileM + static_cast<int>(cta_rank) * kBlockM + quarter * 32 + lane;
+      const bool row_ok = row < m_valid;
+      const uint64_t draw = draw_base + p.stages[s].phase;
+      float row_acc = 0.f;
+      const uint32_t as = accn & 1u;
+      ptx::mbar_wait(&tmem_full_bar[as], (accn >> 1) & 1u);
+      ptx::tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < kColsPerWarp; c += 32) {
+        const int coff = half * kColsPerWarp + c;
+        uint32_t acc[32];
+        ptx::tmem_ld_32x32(tmem_base + ((quarter * 32u) << 16) + as * BN + coff, acc);
+        ptx::tmem_ld_wait();
+        if (kd.epi == kEpiSample)
+          epilogue_chunk<kEpiSample>(kd, acc, row, n_blk * BN + coff, row_ok, draw, row0, lane, row_acc);
+        else
+          epilogue_chunk<kEpiProb>(kd, acc, row, n_blk * BN + coff, row_ok, draw, row0, lane, row_acc);
+      }
+      ptx::tc_fence_before();
+      ptx::fence_proxy_async_global();  // these stores will be read by other CTAs' TMA loads
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive_cluster(&tmem_empty_bar[as], 0);
+      ++accn;
+      // this CTA's part of the tile is in global memory once all eight epilogue warps got here
+      ptx::named_bar_sync(1, kNumEpiWarps * 32);
+      if (ew == 0 && lane == 0) {
+        __threadfence();
+        atomicAdd(p.done + s * num_m + m_blk, 1u);
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  ptx::cluster_sync();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<CG>(tmem_base, kTmemCols);
+  }
+}
+
+}  // namespace kucd

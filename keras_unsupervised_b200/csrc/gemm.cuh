@@ -161,8 +161,8 @@ __device__ __forceinline__ void box_muller(uint32_t b0, uint32_t b1, float& n0, 
 }
 
 // One 32-column chunk of one output row (this thread's TMEM lane).
-template <int EPI>
-__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32_t (&acc)[32], int row, int col0,
+template <int EPI, typename P>
+__device__ __forceinline__ void epilogue_chunk(const P& p, const uint32_t (&acc)[32], int row, int col0,
                                                bool row_ok, uint64_t draw, int64_t row0, uint32_t lane,
                                                float& row_acc) {
   if (col0 >= p.N) return;  // warp-uniform

@@ -29,6 +29,7 @@
 #include <vector>
 
 #include "aux_kernels.cuh"
+#include "chain.cuh"
 #include "launch.cuh"
 
 using namespace kucd;
@@ -141,6 +142,8 @@ struct kucd_ctx {
   DevBuf stage_raw[2];
   bool split = true;               // KUCD_SPLIT=0 turns the two-chain schedule off, 2 forces it (tests)
   bool split_force = false;
+  bool chain_force = false;        // KUCD_CHAIN=2: use it at any size (tests)
+  bool chain = true;               // KUCD_CHAIN=0: launch the projections one by one instead of the chain kernel
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   kucd_timings tm{};
   void* comm = nullptr;
@@ -229,6 +232,7 @@ struct kucd_rbm {
   int64_t n_chains = 0;
   DevBuf fe0, fe1, sp0, sp1, pstage, stats, flag;
   DevBuf dyn;
+  DevBuf chain_done;  // (stage, row block) completion counters of the chain kernel
   uint64_t seed = 0;  // Philox key; draws are (seed, draw id, global row, column)
   uint64_t step_count = 0, infer_draws = 0, score_draws = 0;
   int64_t last_rows = 0;
@@ -688,6 +692,118 @@ static int apply_update(kucd_rbm* r, const kucd_hparams* hp, int64_t rows_global
   return KUCD_OK;
 }
 
+// The 2k+1 (+1 with persistent chains) projections of one minibatch as one persistent kernel (chain.cuh).
+static int launch_chain(kucd_rbm* r, const Planes& v0, int64_t batch, const kucd_hparams* hp, int64_t global_row0,
+                        uint64_t draw0, uint64_t stride, const StepDyn* dyn, bool v0_dyn) {
+  kucd_ctx* ctx = r->ctx;
+  const int k = hp->k;
+  const bool pcd = hp->persistent != 0;
+  ChainParams p;
+  memset(&p, 0, sizeof p);
+  std::string err;
+  const Planes h0 = r->h0.view(batch, r->H, 1), hk = r->hk.view(batch, r->H, 1), vk = r->vk.view(batch, r->V, 1);
+  auto amap = [&](int i, const Planes& q) {
+    return make_tmap_bf16(&p.maps[i], MatView{q.p[0], q.rows, q.cols, q.ld}, kBlockM, &err);
+  };
+  bool ok = amap(0, v0) && amap(1, h0) && amap(2, hk) && amap(3, vk);
+  if (ok && pcd) ok = amap(4, r->chains.view(batch, r->V, 1));
+  if (ok && !pcd) p.maps[4] = p.maps[0];
+  const MatView Wv{r->Wp.buf[0].p, r->V, r->H, r->ldH};
+  ok = ok && make_tmap_bf16(&p.maps[5], Wv, 64u, &err)                 // v.W   : W as (K,N), boxes {64 n, 64 k}
+          && make_tmap_bf16(&p.maps[6], Wv, kChainBN / 2, &err);        // h.W^T : W as (N,K), boxes {64 k, 128 n}
+  if (!ok) return fail(KUCD_ERR_CUDA, "%s", err.c_str());
+  p.maps[7] = p.maps[6];
+
+  auto kind = [&](int i, bool fwd, int map_a, __nv_bfloat16* out, int epi, float* colsum, float sign, bool a_dyn) {
+    ChainKind& q = p.kinds[i];
+    q.bias = fwd ? r->c32.as<float>() : r->b32.as<float>();
+    q.out_bf16 = out;
+    q.ld_bf16 = fwd ? r->ldH : r->ldV;
+    q.colsum = colsum;
+    q.colsum_sign = sign;
+    q.epi = epi;
+    q.M = static_cast<int32_t>(batch);
+    q.N = static_cast<int32_t>(fwd ? r->H : r->V);
+    q.seed = r->seed;
+    q.kblocks = static_cast<int32_t>(((fwd ? r->V : r->H) + kBlockK - 1) / kBlockK);
+    q.b_mn = fwd ? 1 : 0;
+    q.map_a = map_a;
+    q.map_b = fwd ? 5 : 6;
+    q.a_dyn = a_dyn ? 1 : 0;
+    q.num_n = (q.N + kChainBN - 1) / kChainBN;
+  };
+  kind(0, true, 0, h0.p[0], kEpiSample, r->dc(), 1.f, v0_dyn);          // h_pos from v0            rbm.py:120
+  kind(1, true, 4, hk.p[0], kEpiSample, nullptr, 0.f, false);            // first h of a stored chain (PCD)
+  kind(2, false, 1, vk.p[0], kEpiSample, nullptr, 0.f, false);           // v from h_pos             rbm.py:121-123
+  kind(3, false, 2, vk.p[0], kEpiSample, nullptr, 0.f, false);           // v from a later h
+  kind(4, false, 1, vk.p[0], kEpiSample, r->db(), -1.f, false);          // last v from h_pos (k = 1)
+  kind(5, false, 2, vk.p[0], kEpiSample, r->db(), -1.f, false);          // last v from a later h
+  kind(6, true, 3, hk.p[0], kEpiSample, nullptr, 0.f, false);            // intermediate h (CD-k)
+  kind(7, true, 3, hk.p[0], kEpiProb, r->dc(), -1.f, false);             // final h: probability     rbm.py:124
+
+  int ns = 0;
+  auto stage = [&](int kd, int dep, uint32_t phase) {
+    p.stages[ns].kind = static_cast<int16_t>(kd);
+    p.stages[ns].dep = static_cast<int16_t>(dep);
+    p.stages[ns].phase = phase;
+    return ns++;
+  };
+  int hsrc = stage(0, -1, 0);
+  bool from_h0 = true;
+  if (pcd) {
+    hsrc = stage(1, -1, 1);
+    from_h0 = false;
+  }
+  for (int t = 1; t <= k; ++t) {
+    const bool last = t == k;
+    const int vs = stage(from_h0 ? (last ? 4 : 2) : (last ? 5 : 3), hsrc, 2u * t);
+    hsrc = stage(last ? 7 : 6, vs, 2u * t + 1);
+    from_h0 = false;
+  }
+  const int num_m = static_cast<int>((batch + 2 * kBlockM - 1) / (2 * kBlockM));
+  int total = 0;
+  for (int i = 0; i < ns; ++i) total += num_m * p.kinds[p.stages[i].kind].num_n;
+  p.num_stages = ns;
+  p.M = static_cast<int32_t>(batch);
+  p.m_valid = static_cast<int32_t>(batch);
+  p.total_tiles = total;
+  KU_TRY(r->chain_done.ensure(static_cast<size_t>(kMaxChainStages) * num_m * 4));
+  p.done = r->chain_done.as<uint32_t>();
+  p.draw = draw0;
+  p.draw_stride = stride;
+  p.row0 = global_row0;
+  p.dyn = dyn;
+  p.dyn_rank = ctx->rank;
+  CU_TRY(cudaMemsetAsync(p.done, 0, static_cast<size_t>(ns) * num_m * 4, ctx->stream));
+
+  using Cfg = GemmCfg<kChainBN / 2>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CU_TRY(cudaFuncSetAttribute(chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  const int units = std::min(total, ctx->num_sms / 2);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(units * 2);
+  cfg.blockDim = dim3(kNumThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = ctx->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const bool prof = ctx->profile && dyn == nullptr;
+  const size_t pe0 = prof ? prof_event(ctx) : 0;
+  CU_TRY(cudaLaunchKernelEx(&cfg, chain_kernel, p));
+  if (prof) ctx->marks.push_back({0, pe0, prof_event(ctx), ns});
+  ctx->tm.gemm_launches++;
+  ctx->tm.chain_launches++;
+  return KUCD_OK;
+}
+
 // v0: the minibatch operand (rows [0,batch) of it, or - with v0_dyn - the rows at dyn->row_off of a data set)
 static int enqueue_cd(kucd_rbm* r, const Planes& v0, int64_t batch, const kucd_hparams* hp, const StepInject* inj,
                       int64_t global_row0, uint64_t step, const StepDyn* dyn, bool v0_dyn) {
@@ -808,7 +924,14 @@ static int enqueue_cd(kucd_rbm* r, const Planes& v0, int64_t batch, const kucd_h
   const int64_t tiles_half = (half / kBlockM) * ((std::min(r->V, r->H) + 255) / 256);
   const bool two = ctx->split && half < batch && (tiles_half >= ctx->num_sms || ctx->split_force);
   const int n_proj = 2 * k + 1 + (hp->persistent ? 1 : 0);
-  if (!two) {
+  // one persistent kernel for the whole chain when every stage fills the chip with 256 x 256 tiles
+  const int64_t pair_tiles = ((batch + 255) / 256) * ((std::min(r->V, r->H) + 255) / 256);
+  const bool whole_chain = ctx->chain && r->compute == KUCD_COMPUTE_BF16 && !gaussian && inj == nullptr && v0.n == 1 &&
+                           (pair_tiles >= ctx->num_sms / 2 || ctx->chain_force) &&
+                           (!hp->persistent || r->last_vk_parts == 1);
+  if (whole_chain) {
+    KU_TRY(launch_chain(r, v0, batch, hp, global_row0, draw0, stride, dyn, v0_dyn));
+  } else if (!two) {
     KU_TRY(chain(0, batch, ctx->stream, true));
   } else {
     const bool prof = ctx->profile && dyn == nullptr;
@@ -980,6 +1103,9 @@ int kucd_ctx_create(kucd_ctx** out, int device_id, uint64_t seed) {
     const char* sp = getenv("KUCD_SPLIT");
     c->split = !(sp != nullptr && sp[0] == '0');
     c->split_force = sp != nullptr && sp[0] == '2';
+    const char* ch = getenv("KUCD_CHAIN");
+    c->chain = !(ch != nullptr && ch[0] == '0');
+    c->chain_force = ch != nullptr && ch[0] == '2';
   }
   CU_TRY(cudaEventCreate(&c->ev0));
   CU_TRY(cudaEventCreate(&c->ev1));
@@ -1121,7 +1247,7 @@ int kucd_rbm_destroy(kucd_rbm* r) {
   if (r->graph_exec != nullptr) cudaGraphExecDestroy(r->graph_exec);
   if (r->graph != nullptr) cudaGraphDestroy(r->graph);
   for (DevBuf* b : {&r->W32, &r->b32, &r->c32, &r->mW, &r->mb, &r->mc, &r->grad, &r->fe0, &r->fe1, &r->sp0, &r->sp1,
-                    &r->pstage, &r->stats, &r->flag, &r->dyn})
+                    &r->pstage, &r->stats, &r->flag, &r->dyn, &r->chain_done})
     b->release();
   for (PlaneBuf* p : {&r->Wp, &r->vin, &r->h0, &r->hk, &r->vk, &r->chains}) p->release();
   delete r;

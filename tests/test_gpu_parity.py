@@ -401,3 +401,59 @@ def test_fit_host_streaming_equals_resident_fit(ctx):
     # gap and flip; each flip moves one row/column of W by lr
     assert np.abs(Wb - orc.W).mean() < 5e-5 and np.abs(Wb - orc.W).max() < 5e-3
     ds.close()
+
+
+def test_whole_chain_kernel_equals_per_projection_launches(monkeypatch):
+    """The persistent chain kernel (all 2k+1 projections of a minibatch in one launch, row-block dataflow
+    between stages) must reproduce the launch-per-projection path bit for bit: same Philox draws, same
+    arithmetic.  Forced here at small, ragged sizes; CD-3, PCD, and graph replay with a remainder minibatch."""
+    from keras_unsupervised_b200 import _lib as L
+    from keras_unsupervised_b200.engine import Context, Dataset, Machine
+
+    monkeypatch.setenv("KUCD_CHAIN", "2")
+    c_chain = Context(device=0, seed=1)
+    monkeypatch.setenv("KUCD_CHAIN", "0")
+    c_plain = Context(device=0, seed=1)
+    rng = np.random.default_rng(101)
+    V, H, seed = 600, 520, 17
+    ms = []
+    for c in (c_chain, c_plain):
+        m, orc = _machine(c, V, H, "bf16", seed=seed)
+        ms.append(m)
+    # one step, CD-3, 700 rows (three 256-row blocks, the last ragged)
+    v = _data(rng, 700, V, 0.2)
+    hp = Machine.hparams(lr=1e-3, k=3)
+    got = []
+    for m in ms:
+        m.cd_step(v, hp)
+        got.append(m.last_stats(700))
+    t = c_chain.timings()
+    assert t["chain_launches"] == 1 and c_plain.timings()["chain_launches"] == 0
+    for key in ("h_pos", "v_neg", "h_neg", "dW", "db"):
+        assert np.array_equal(got[0][key], got[1][key]), key
+    np.testing.assert_allclose(got[0]["dc"], got[1]["dc"], rtol=0, atol=1e-3)
+    # against the oracle's regeneration of the same Philox stream
+    u_h = [O.philox_uniform(seed, O.draw_id("train", 0, 0 if t_ == 0 else 2 * t_ + 1), 0, 700, H) for t_ in range(3)]
+    u_v = [None] + [O.philox_uniform(seed, O.draw_id("train", 0, 2 * t_), 0, 700, V) for t_ in range(1, 4)]
+    st = orc.cd_stats(v, u_h, u_v, k=3)
+    assert (got[0]["h_pos"] != st["h_pos"]).mean() < 1e-4 and (got[0]["v_neg"] != st["v_neg"]).mean() < 1e-3
+
+    # persistent chains + graph replay (1000 rows in minibatches of 300: remainder of 100)
+    chains = _data(rng, 300, V, 0.5)
+    data = _data(rng, 1000, V, 0.2)
+    hp = Machine.hparams(lr=1e-3, k=2, persistent=True)
+    params = []
+    for c, m in zip((c_chain, c_plain), ms):
+        m.set_chains(chains)
+        ds = Dataset.from_array(c, data, L.COMPUTE_BF16)
+        for _ in range(2):
+            m.fit_epoch(ds, 300, hp)
+        c.sync()
+        params.append(m.get_params() + (m.get_chains(300),))
+        ds.close()
+    assert np.array_equal(params[0][3], params[1][3])                      # chains
+    np.testing.assert_allclose(params[0][0], params[1][0], rtol=0, atol=1e-6)   # W (dc/db atomics order only)
+    np.testing.assert_allclose(params[0][1], params[1][1], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(params[0][2], params[1][2], rtol=0, atol=1e-6)
+    c_chain.close()
+    c_plain.close()
