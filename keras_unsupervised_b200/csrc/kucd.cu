@@ -227,7 +227,7 @@ struct kucd_rbm {
   DevBuf grad;
   // workspaces, sized for `cap` rows
   int64_t cap = 0;
-  PlaneBuf vin, h0, hk, vk;
+  PlaneBuf vin, vin2, h0, hk, vk;  // vin2: second staging slot of the host-streaming fit
   PlaneBuf chains;  // persistent chains (n_chains, ldV)
   int64_t n_chains = 0;
   DevBuf fe0, fe1, sp0, sp1, pstage, stats, flag;
@@ -1249,7 +1249,7 @@ int kucd_rbm_destroy(kucd_rbm* r) {
   for (DevBuf* b : {&r->W32, &r->b32, &r->c32, &r->mW, &r->mb, &r->mc, &r->grad, &r->fe0, &r->fe1, &r->sp0, &r->sp1,
                     &r->pstage, &r->stats, &r->flag, &r->dyn, &r->chain_done})
     b->release();
-  for (PlaneBuf* p : {&r->Wp, &r->vin, &r->h0, &r->hk, &r->vk, &r->chains}) p->release();
+  for (PlaneBuf* p : {&r->Wp, &r->vin, &r->vin2, &r->h0, &r->hk, &r->vk, &r->chains}) p->release();
   delete r;
   return KUCD_OK;
 }
@@ -1804,25 +1804,56 @@ int kucd_rbm_fit_host(kucd_rbm* r, const kucd_tensor* V_all, int64_t batch, cons
   if (hp->persistent) KU_TRY(ensure_chains(r, std::min(batch, N)));
   const int es = elem_size(V_all);
   const int64_t cols = r->V;
-  for (int i = 0; i < 2; ++i) KU_TRY(ctx->stage_raw[i].ensure(static_cast<size_t>(batch) * cols * es));
+  const bool x3 = r->compute == KUCD_COMPUTE_F32X3;
+  const int nplanes = x3 ? 3 : 1;
+  // Default: cudaMemcpyAsync on the copy stream into a raw staging slot, converted on the compute stream.
+  // KUCD_ZEROCOPY=1 (pinned memory only): the ingest kernel reads the host array itself, straight over PCIe into
+  // the operand planes on the copy stream.  Measured at C3 next to the chain kernel: DMA 2.62 ms per step vs
+  // zero-copy 3.73 ms on one box; on another box of the pool the copy engine delivered only 4-14 GB/s under load
+  // (tools/h2d_check.py), which is when the switch is worth trying.
+  static const bool zc_env = [] {
+    const char* e = getenv("KUCD_ZEROCOPY");
+    return e != nullptr && e[0] == '1';
+  }();
+  const bool zero_copy = zc_env && V_all->device_type == KUCD_DEV_CUDA_HOST;
+  if (zero_copy) {
+    KU_TRY(r->vin2.ensure(r->cap, r->ldV, nplanes));
+  } else {
+    for (int i = 0; i < 2; ++i) KU_TRY(ctx->stage_raw[i].ensure(static_cast<size_t>(batch) * cols * es));
+  }
   float* host_stats = nullptr;
   if (step_recon != nullptr) CU_TRY(cudaMallocHost(&host_stats, steps * sizeof(float)));
-  const bool x3 = r->compute == KUCD_COMPUTE_F32X3;
   // fp32 data in fp32-grade mode is carried in all three terms (no per-step "is it exact" round trip)
   const int live = (x3 && V_all->dtype_code == KUCD_DT_FLOAT) ? 3 : 1;
   auto rows_of_step = [&](int64_t i) { return std::min(batch, N - i * batch); };
+  auto slot_planes = [&](int slot, int64_t n) { return (slot == 0 ? r->vin : r->vin2).view(n, r->V, nplanes); };
+  auto ingest = [&](const void* src, int64_t src_ld, int64_t n, const Planes& dst, cudaStream_t st) {
+    const int grid = grid_for(ctx, n * (dst.ld / 8), 256);
+    by_dtype(V_all, [&](auto* tag) {
+      using T = std::remove_pointer_t<decltype(tag)>;
+      ingest_kernel<T><<<grid, 256, 0, st>>>(static_cast<const T*>(src), src_ld, n, cols, dst.p[0], dst.p[1], dst.p[2],
+                                             dst.ld, nplanes, nullptr);
+      return 0;
+    });
+    ctx->tm.aux_launches++;
+  };
   auto copy_in = [&](int64_t i) -> int {
     const int slot = static_cast<int>(i & 1);
     if (i >= 2) CU_TRY(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_consumed[slot], 0));
     const char* src = static_cast<const char*>(V_all->data) + i * batch * V_all->strides[0] * es;
-    if (V_all->strides[0] == cols)  // contiguous rows: one linear DMA
-      CU_TRY(cudaMemcpyAsync(ctx->stage_raw[slot].p, src, static_cast<size_t>(rows_of_step(i)) * cols * es,
-                             cudaMemcpyHostToDevice, ctx->copy_stream));
-    else
-      CU_TRY(cudaMemcpy2DAsync(ctx->stage_raw[slot].p, cols * es, src, V_all->strides[0] * es, cols * es,
-                               rows_of_step(i), cudaMemcpyHostToDevice, ctx->copy_stream));
+    const int64_t n = rows_of_step(i);
+    if (zero_copy) {
+      ingest(src, V_all->strides[0], n, slot_planes(slot, n), ctx->copy_stream);
+      CU_TRY(cudaGetLastError());
+    } else if (V_all->strides[0] == cols) {  // contiguous rows: one linear DMA
+      CU_TRY(cudaMemcpyAsync(ctx->stage_raw[slot].p, src, static_cast<size_t>(n) * cols * es, cudaMemcpyHostToDevice,
+                             ctx->copy_stream));
+    } else {
+      CU_TRY(cudaMemcpy2DAsync(ctx->stage_raw[slot].p, cols * es, src, V_all->strides[0] * es, cols * es, n,
+                               cudaMemcpyHostToDevice, ctx->copy_stream));
+    }
     CU_TRY(cudaEventRecord(ctx->ev_copied[slot], ctx->copy_stream));
-    ctx->tm.h2d_bytes += rows_of_step(i) * cols * es;
+    ctx->tm.h2d_bytes += n * cols * es;
     return KUCD_OK;
   };
   int rc = KUCD_OK;
@@ -1837,16 +1868,11 @@ int kucd_rbm_fit_host(kucd_rbm* r, const kucd_tensor* V_all, int64_t batch, cons
       rc = fail(KUCD_ERR_CUDA, "stream wait failed");
       break;
     }
-    Planes v0 = r->vin.view(n, r->V, x3 ? 3 : 1);
-    const int grid = grid_for(ctx, n * (v0.ld / 8), 256);
-    by_dtype(V_all, [&](auto* tag) {
-      using T = std::remove_pointer_t<decltype(tag)>;
-      ingest_kernel<T><<<grid, 256, 0, ctx->stream>>>(static_cast<const T*>(ctx->stage_raw[slot].p), cols, n, cols,
-                                                      v0.p[0], v0.p[1], v0.p[2], v0.ld, x3 ? 3 : 1, nullptr);
-      return 0;
-    });
-    ctx->tm.aux_launches++;
-    cudaEventRecord(ctx->ev_consumed[slot], ctx->stream);
+    Planes v0 = zero_copy ? slot_planes(slot, n) : r->vin.view(n, r->V, nplanes);
+    if (!zero_copy) {
+      ingest(ctx->stage_raw[slot].p, cols, n, v0, ctx->stream);
+      cudaEventRecord(ctx->ev_consumed[slot], ctx->stream);  // the raw staging slot is free again
+    }
     v0.n = live;
     rc = enqueue_cd(r, v0, n, hp, nullptr, global_row0, r->step_count, nullptr, false);
     r->step_count++;
@@ -1857,6 +1883,7 @@ int kucd_rbm_fit_host(kucd_rbm* r, const kucd_tensor* V_all, int64_t batch, cons
         rc = fail(KUCD_ERR_CUDA, "statistic read-back failed");
       ctx->tm.d2h_bytes += 4;
     }
+    if (zero_copy) cudaEventRecord(ctx->ev_consumed[slot], ctx->stream);  // the operand planes of this slot are free
     if (rc == KUCD_OK) rc = apply_update(r, hp, n * ctx->world);
   }
   cudaEventRecord(ctx->ev1, ctx->stream);
