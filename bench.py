@@ -462,24 +462,32 @@ def _main(out):
         ctx.set_profile(False)
         windows.append((tw0, tw1))
         if tp["proj_timed"] and rank == 0:
-            per_launch_ms = tp["proj_ms"] / tp["proj_timed"]
-            # 2k+1 projections per step; with the two-chain schedule each is launched as two row-halves
-            flop = n_prof * (2 * k + 1 + (1 if persistent else 0)) * 2.0 * B * V * H / tp["proj_timed"]
+            n_proj = 2 * k + 1 + (1 if persistent else 0)
+            chain = tp["chain_launches"] > 0
+            if chain:
+                # all projections of a minibatch are ONE launch of chain_kernel: that launch is the unit
+                launches = tp["chain_launches"]
+                flop = n_proj * 2.0 * B * V * H
+                kernel = "chain_kernel (the %d projections of a CD-%d minibatch, fused epilogues, one persistent launch)" % (n_proj, k)
+            else:
+                launches = tp["proj_timed"]  # with the two-chain schedule each projection is two row-half launches
+                flop = n_prof * n_proj * 2.0 * B * V * H / launches
+                kernel = "gemm_bf16_kernel<sample epilogue> (v.W+c / h.W^T+b projection)"
+            per_launch_ms = tp["proj_ms"] / launches
             ach = flop / (per_launch_ms * 1e-3) / 1e12
             traffic = None
             tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
             if os.path.exists(tpath):
                 with open(tpath) as f:
-                    traffic = json.load(f).get(args.workload)
-            roof = {"bound": "tensor", "kernel": "gemm_bf16_kernel<sample epilogue> (v.W+c / h.W^T+b projection)",
-                    "achieved": ach, "peak": pk["sustained"], "unit": "TFLOP/s", "frac": ach / pk["sustained"],
+                    traffic = json.load(f).get(args.workload + ("_chain" if chain else ""))
+            step_tf = flops_per_sample(V, H, k) * B / (ms * 1e-3 / steps) / 1e12
+            roof = {"bound": "tensor", "kernel": kernel, "achieved": ach, "peak": pk["sustained"], "unit": "TFLOP/s",
+                    "frac": ach / pk["sustained"],
                     "peak_source": pk["source"] + ", sustained figure (kernel timed inside a long step)",
-                    "traffic": traffic, "launch_ms": per_launch_ms, "launches_timed": tp["proj_timed"],
-                    "launch_rows": int(round(flop / (2.0 * V * H))),
-                    "flop_per_launch": flop,
+                    "traffic": traffic, "launch_ms": per_launch_ms, "launches_timed": launches,
+                    "projections_per_launch": n_proj if chain else None, "flop_per_launch": flop,
                     "dw_launch_ms": (tp["dw_ms"] / tp["dw_timed"]) if tp["dw_timed"] else None,
-                    "step_tflops": flops_per_sample(V, H, k) * B / (ms * 1e-3 / steps) / 1e12,
-                    "step_frac_of_sustained": flops_per_sample(V, H, k) * B / (ms * 1e-3 / steps) / 1e12 / pk["sustained"]}
+                    "step_tflops": step_tf, "step_frac_of_sustained": step_tf / pk["sustained"]}
     clocks = sampler.stop(windows) if sampler is not None else None
 
     cpu = None
