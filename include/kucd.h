@@ -167,6 +167,8 @@ int kucd_rbm_get_params(kucd_rbm* rbm, kucd_tensor* W, kucd_tensor* b, kucd_tens
  * v_neg, 2t+1 = t-th negative h; the n-th transform / inv_transform call uses 2^63 + n; the n-th score
  * chain uses 2^62 + 2n (h) and 2^62 + 2n + 1 (v).  Defaults: the context seed, all counters 0. */
 int kucd_rbm_set_seed(kucd_rbm* rbm, uint64_t seed, uint64_t step_count);
+/* what a checkpoint needs besides the parameters: the stream position and the number of stored chains */
+int kucd_rbm_get_counters(kucd_rbm* rbm, uint64_t* seed, uint64_t* step_count, int64_t* n_chains);
 
 /* ---- inference ------------------------------------------------------------------------------------- */
 /* transform_func (rbm.py:45-48, 88-89) and RBM.call (rbm.py:80-83):  h = 1[u < sigmoid(v.W + c)]

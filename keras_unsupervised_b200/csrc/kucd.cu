@@ -1298,6 +1298,14 @@ int kucd_rbm_set_seed(kucd_rbm* r, uint64_t seed, uint64_t step_count) {
   return KUCD_OK;
 }
 
+int kucd_rbm_get_counters(kucd_rbm* r, uint64_t* seed, uint64_t* step_count, int64_t* n_chains) {
+  if (r == nullptr) return fail(KUCD_ERR_INVALID_ARG, "rbm is NULL");
+  if (seed != nullptr) *seed = r->seed;
+  if (step_count != nullptr) *step_count = r->step_count;
+  if (n_chains != nullptr) *n_chains = r->n_chains;
+  return KUCD_OK;
+}
+
 int kucd_rbm_get_params(kucd_rbm* r, kucd_tensor* W, kucd_tensor* b, kucd_tensor* c) {
   if (r == nullptr) return fail(KUCD_ERR_INVALID_ARG, "rbm is NULL");
   kucd_ctx* ctx = r->ctx;

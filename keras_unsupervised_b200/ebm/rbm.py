@@ -141,6 +141,33 @@ class RBM(object):
         W, c, b = weights
         self._machine.set_params(W, b, c)
 
+    # ---- checkpoint / resume (the reference relies on Keras HDF5 and saves no trainer state) ----
+    def save(self, path):
+        """Parameters under the reference's variable names (rbm.py:30,34,40) plus what resuming a fit needs:
+        the Philox stream position and the persistent chains."""
+        W, b, c = self._machine.get_params()
+        st = self._machine.counters()
+        extra = {}
+        if st["n_chains"] > 0:
+            extra["chains"] = self._machine.get_chains(st["n_chains"])
+        np.savez(path, rbm_weight=W, rbm_hidden_bias=c, rbm_visible_bias=b, seed=np.uint64(st["seed"]),
+                 step_count=np.uint64(st["step_count"]), mode=np.int64(self.mode), output_dim=np.int64(self.output_dim),
+                 **extra)
+
+    def load(self, path):
+        z = np.load(path if str(path).endswith(".npz") else str(path) + ".npz")
+        if not self.built:
+            self.build((None, int(z["rbm_weight"].shape[0])))
+        if z["rbm_weight"].shape != (self._machine.V, self._machine.H):
+            raise ValueError("checkpoint has rbm_weight %s, this RBM is %s" % (z["rbm_weight"].shape,
+                                                                               (self._machine.V, self._machine.H)))
+        self._machine.set_params(z["rbm_weight"], z["rbm_visible_bias"], z["rbm_hidden_bias"])
+        self._machine.set_seed(int(z["seed"]), int(z["step_count"]))
+        if "chains" in z.files:
+            self._machine.set_chains(z["chains"])
+            self._chains_set = int(z["chains"].shape[0])
+        return self
+
     # ---- inference -----------------------------------------------------------------------------
     def _wrap(self, out):
         return [out] if self.return_list else out

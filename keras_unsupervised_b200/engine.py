@@ -164,6 +164,11 @@ class Machine:
     def set_seed(self, seed: int, step_count: int = 0) -> None:
         L.check(self.ctx.lib.kucd_rbm_set_seed(self.handle, C.c_uint64(seed), C.c_uint64(step_count)))
 
+    def counters(self) -> dict:
+        seed, step, nch = C.c_uint64(), C.c_uint64(), C.c_int64()
+        L.check(self.ctx.lib.kucd_rbm_get_counters(self.handle, C.byref(seed), C.byref(step), C.byref(nch)))
+        return {"seed": seed.value, "step_count": step.value, "n_chains": nch.value}
+
     # ---- parameters ----
     def set_params(self, W=None, b=None, c=None) -> None:
         keep: list = []

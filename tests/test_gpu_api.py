@@ -115,3 +115,48 @@ def test_torch_cuda_tensors_zero_copy(ctx):
     assert np.array_equal(h.cpu().numpy(), h_np)
     hb = rbm._machine.transform(x.to(torch.bfloat16), out_dtype=torch.uint8)
     assert hb.dtype == torch.uint8 and hb.shape == (512, 256)
+
+
+def test_checkpoint_resume_is_exact(ctx, tmp_path):
+    """save/load carries parameters (under the reference's variable names), the Philox position and the
+    persistent chains: a resumed fit continues exactly where the uninterrupted one goes."""
+    from keras_unsupervised_b200.ebm import RBM, MODE_VISIBLE_BERNOULLI
+
+    rng = np.random.default_rng(7)
+    V = _structured(rng, 1024, 192)
+    hps = {"batch_size": 128, "epochs": 2, "lr": 1e-2, "dtype": "bf16", "persistent": True, "k": 2, "seed": 5}
+    a = RBM(dict(hps), 96, name="a", mode=MODE_VISIBLE_BERNOULLI, context=ctx)
+    a.fit(V, verbose=0)
+    a.save(tmp_path / "ckpt.npz")
+    z = np.load(tmp_path / "ckpt.npz")
+    assert {"rbm_weight", "rbm_hidden_bias", "rbm_visible_bias", "chains", "seed", "step_count"} <= set(z.files)
+    assert int(z["step_count"]) == 16
+    a.fit(V, verbose=0)
+    b = RBM(dict(hps), 96, name="b", mode=MODE_VISIBLE_BERNOULLI, context=ctx).load(tmp_path / "ckpt.npz")
+    b.fit(V, verbose=0)
+    np.testing.assert_allclose(a.rbm_weight, b.rbm_weight, rtol=0, atol=1e-6)
+    np.testing.assert_allclose(a.hidden_bias, b.hidden_bias, rtol=0, atol=1e-6)
+    assert np.array_equal(a._machine.get_chains(128), b._machine.get_chains(128))
+
+
+def test_gaussian_visible_rbm_runs_the_default_mode(ctx):
+    """MODE_VISIBLE_GAUSSIAN is the constructor default (rbm.py:22) and what examples/rbm uses: relu-threshold
+    hiddens, unit-variance Gaussian reconstructions drawn from the engine's Philox stream (Box-Muller)."""
+    from keras_unsupervised_b200.ebm import RBM
+
+    rng = np.random.default_rng(11)
+    seed = 21
+    X = rng.normal(0, 1, (512, 200)).astype(np.float32)
+    rbm = RBM({"batch_size": 128, "epochs": 1, "lr": 1e-4, "seed": seed}, 64, name="g", context=ctx)
+    assert rbm.mode == 1
+    rbm.build((None, 200))
+    W, b, c = rbm._machine.get_params()
+    orc = O.OracleRBM(W, b, c, mode=O.MODE_VISIBLE_GAUSSIAN)
+    hh = (rng.random((512, 64)) < 0.5).astype(np.float32)
+    v = rbm.inv_transform(hh)[0]                 # first inference draw: id 2^63 + 0, unit normals
+    n = O.philox_normal(seed, O.draw_id("infer", 0), 0, 512, 200)
+    v_ref, _ = orc.sample_v(hh, n)
+    np.testing.assert_allclose(v, v_ref, rtol=1e-5, atol=2e-5)
+    assert abs(float((v - orc.pre_v(hh)).std()) - 1.0) < 0.02
+    rbm.fit(X, verbose=0)
+    assert np.isfinite(rbm.rbm_weight).all() and not np.array_equal(rbm.rbm_weight, W)
