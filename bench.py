@@ -467,8 +467,10 @@ def _main(out):
             if chain:
                 # all projections of a minibatch are ONE launch of chain_kernel: that launch is the unit
                 launches = tp["chain_launches"]
-                flop = n_proj * 2.0 * B * V * H
-                kernel = "chain_kernel (the %d projections of a CD-%d minibatch, fused epilogues, one persistent launch)" % (n_proj, k)
+                with_dw = tp["chain_dw_launches"] > 0
+                flop = (n_proj + (2 if with_dw else 0)) * 2.0 * B * V * H
+                kernel = "chain_kernel (the %d projections of a CD-%d minibatch%s, fused epilogues, one persistent launch)" % (
+                    n_proj, k, " + the two outer products of dW" if with_dw else "")
             else:
                 launches = tp["proj_timed"]  # with the two-chain schedule each projection is two row-half launches
                 flop = n_prof * n_proj * 2.0 * B * V * H / launches

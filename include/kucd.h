@@ -120,6 +120,7 @@ typedef struct kucd_epoch_stats {
 typedef struct kucd_timings {
   int64_t gemm_launches;    /* tcgen05 contraction launches enqueued (directly or while capturing)  */
   int64_t chain_launches;   /* of those: whole-chain launches (all projections of a minibatch in one)  */
+  int64_t chain_dw_launches;/* of those: chain launches that also carried the dW contraction            */
   int64_t aux_launches;     /* update / split / reduction / conversion launches enqueued            */
   int64_t graph_launches;   /* CUDA-graph replays (each replays a whole CD step)                     */
   int64_t graph_kernel_launches; /* kernels those replays launched                                    */

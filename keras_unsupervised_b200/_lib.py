@@ -62,7 +62,8 @@ class EpochStats(C.Structure):
 
 
 class Timings(C.Structure):
-    _fields_ = [("gemm_launches", C.c_int64), ("chain_launches", C.c_int64), ("aux_launches", C.c_int64),
+    _fields_ = [("gemm_launches", C.c_int64), ("chain_launches", C.c_int64), ("chain_dw_launches", C.c_int64),
+                ("aux_launches", C.c_int64),
                 ("graph_launches", C.c_int64),
                 ("graph_kernel_launches", C.c_int64), ("allreduce_calls", C.c_int64), ("h2d_bytes", C.c_int64),
                 ("d2h_bytes", C.c_int64), ("proj_timed", C.c_int64), ("dw_timed", C.c_int64),

@@ -24,8 +24,9 @@
 
 namespace kucd {
 
-constexpr int kMaxChainStages = 64;  // 2k+2 with k <= 31
-constexpr int kMaxChainKinds = 8;
+constexpr int kMaxChainStages = 66;  // 2k+2 projections with k <= 31, + the dW contraction
+constexpr int kMaxChainKinds = 9;
+constexpr int kChainMaps = 12;
 constexpr int kChainBN = 256;
 
 // The few distinct projections a chain is made of (member names shared with GemmParams: epilogue_chunk reads them).
@@ -50,23 +51,35 @@ struct ChainKind {
   int32_t map_a, map_b;
   int32_t a_dyn;  // A is the resident data set: rows offset by dyn->row_off
   int32_t num_n;
+  int32_t num_m;       // row blocks of 256 output rows
+  int32_t batch_rows;  // 1: output rows are minibatch rows (valid-row masking, global-row draws)
+  // the dW contraction (rbm.py:125-126) as the chain's last stage: both operands MN-major (contraction over the
+  // minibatch rows), two K-segments - v0^T h0, then vk^T hk with the negate-A bit
+  int32_t a_mn;
+  int32_t nseg;
+  int32_t map_a2, map_b2;
+  int32_t dep2;        // stage that must be complete in ALL its row blocks before segment 1 is loaded
+  int32_t pad;
 };
 
 struct ChainStageRef {
   int16_t kind;
-  int16_t dep;     // stage whose row block must be complete before this stage reads it (-1: none)
+  int16_t dep;     // stage whose row block must be complete before this stage reads it (-1: none); for an
+                   // a_mn stage: ALL row blocks of that stage, before segment 0
   uint32_t phase;  // Philox draw id offset inside the step
 };
 
 struct alignas(64) ChainParams {
-  CUtensorMap maps[8];
+  CUtensorMap maps[kChainMaps];
   ChainKind kinds[kMaxChainKinds];
   ChainStageRef stages[kMaxChainStages];
   int32_t num_stages;
   int32_t M;        // minibatch rows (buffer capacity)
   int32_t m_valid;  // rows that carry data
   int32_t total_tiles;
-  uint32_t* done;   // [num_stages][num_m] tiles-finished counters, zeroed before the launch
+  uint32_t* done;   // [num_stages][done_stride] tiles-finished counters, zeroed before the launch
+  int32_t done_stride;
+  int32_t num_m_batch;  // row blocks of the minibatch
   uint64_t draw;
   uint64_t draw_stride;
   int64_t row0;
@@ -102,7 +115,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) chain_kernel(const __grid_cons
 
   const uint32_t warp = threadIdx.x >> 5;
   const uint32_t lane = ptx::lane_id();
-  const int num_m = (p.M + kTileM - 1) / kTileM;
+  const int done_stride = p.done_stride;
 
   int32_t dyn_row_off = 0;
   int32_t m_valid = p.m_valid;
@@ -116,7 +129,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) chain_kernel(const __grid_cons
   }
 
   if (warp == 0 && lane == 0) {
-    for (int i = 0; i < 8; ++i) ptx::prefetch_tensormap(&p.maps[i]);
+    for (int i = 0; i < kChainMaps; ++i) ptx::prefetch_tensormap(&p.maps[i]);
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -141,8 +154,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) chain_kernel(const __grid_cons
 
   // walk the flattened (stage, row block, column tile) sequence: q -> stage s, first tile `base` of that stage
   auto advance = [&](int q, int& s, int& base) {
-    while (q >= base + num_m * p.kinds[p.stages[s].kind].num_n) {
-      base += num_m * p.kinds[p.stages[s].kind].num_n;
+    while (q >= base + p.kinds[p.stages[s].kind].num_m * p.kinds[p.stages[s].kind].num_n) {
+      base += p.kinds[p.stages[s].kind].num_m * p.kinds[p.stages[s].kind].num_n;
       ++s;
     }
   };
@@ -157,44 +170,64 @@ __global__ void __launch_bounds__(kNumThreads, 1) chain_kernel(const __grid_cons
         const ChainKind& kd = p.kinds[p.stages[s].kind];
         const int t = q - base;
         const int m_blk = t / kd.num_n, n_blk = t % kd.num_n;
-        const int dep = p.stages[s].dep;
-        if (dep >= 0) {
-          // the row block this tile reads must have been written by every column tile of stage `dep` (both CTAs)
+        auto wait_block = [&](int dep, int mb) {
+          // row block `mb` of stage `dep` must have been written by every column tile (both CTAs of each pair)
           const uint32_t need = static_cast<uint32_t>(p.kinds[p.stages[dep].kind].num_n) * CG;
-          const uint32_t* flag = p.done + dep * num_m + m_blk;
+          const uint32_t* flag = p.done + dep * done_stride + mb;
           if (ld_acquire_gpu(flag) < need) {
             const long long t0 = clock64();
             while (ld_acquire_gpu(flag) < need) {
               if (clock64() - t0 > KUCD_SPIN_LIMIT_CYCLES) {
-                printf("kucd: chain dependency wait timed out (block %d stage %d row block %d: %u of %u)\n", blockIdx.x,
-                       s, m_blk, ld_acquire_gpu(flag), need);
+                printf("kucd: chain dependency wait timed out (block %d stage %d waits for stage %d row block %d: %u of %u)\n",
+                       blockIdx.x, s, dep, mb, ld_acquire_gpu(flag), need);
                 __trap();
               }
             }
           }
+        };
+        const int dep = p.stages[s].dep;
+        if (dep >= 0) {
+          if (kd.a_mn) {
+            for (int mb = 0; mb < p.num_m_batch; ++mb) wait_block(dep, mb);
+          } else {
+            wait_block(dep, m_blk);
+          }
           ptx::fence_proxy_async_global();
         }
-        const int m0 = m_blk * kTileM + static_cast<int>(cta_rank) * kBlockM + (kd.a_dyn ? dyn_row_off : 0);
+        const int m0 = m_blk * kTileM + static_cast<int>(cta_rank) * kBlockM;
         const int n0 = n_blk * BN + static_cast<int>(cta_rank) * kBNLocal;
-        const CUtensorMap* ma = &p.maps[kd.map_a];
-        const CUtensorMap* mb = &p.maps[kd.map_b];
-        for (int kb = 0; kb < kd.kblocks; ++kb) {
-          ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
-          if (cta_rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes * CG);
-          uint8_t* sa = smem + stage * Cfg::kStageBytes;
-          uint8_t* sb = sa + Cfg::kABytes;
-          const int k0 = kb * kBlockK;
-          ptx::tma_load_2d_pair(sa, ma, &full_bar[stage], k0, m0);  // box {64 k, 128 rows}
-          if (kd.b_mn) {
-#pragma unroll
-            for (int j = 0; j < kBNLocal / 64; ++j)  // boxes {64 n, 64 k}
-              ptx::tma_load_2d_pair(sb + j * (kBlockK * 128), mb, &full_bar[stage], n0 + 64 * j, k0);
-          } else {
-            ptx::tma_load_2d_pair(sb, mb, &full_bar[stage], k0, n0);  // box {64 k, 128 n}
+        for (int seg = 0; seg < kd.nseg; ++seg) {
+          if (seg == 1) {
+            for (int mb = 0; mb < p.num_m_batch; ++mb) wait_block(kd.dep2, mb);
+            ptx::fence_proxy_async_global();
           }
-          if (++stage == kStages) {
-            stage = 0;
-            phase ^= 1u;
+          const CUtensorMap* ma = &p.maps[seg == 0 ? kd.map_a : kd.map_a2];
+          const CUtensorMap* mb = &p.maps[seg == 0 ? kd.map_b : kd.map_b2];
+          const int a_off = (kd.a_dyn && seg == 0) ? dyn_row_off : 0;  // data-set rows: M if K-major, K if MN-major
+          for (int kb = 0; kb < kd.kblocks; ++kb) {
+            ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
+            if (cta_rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes * CG);
+            uint8_t* sa = smem + stage * Cfg::kStageBytes;
+            uint8_t* sb = sa + Cfg::kABytes;
+            const int k0 = kb * kBlockK;
+            if (!kd.a_mn) {
+              ptx::tma_load_2d_pair(sa, ma, &full_bar[stage], k0, m0 + a_off);  // box {64 k, 128 rows}
+            } else {
+#pragma unroll
+              for (int j = 0; j < kBlockM / 64; ++j)  // boxes {64 m, 64 k}
+                ptx::tma_load_2d_pair(sa + j * (kBlockK * 128), ma, &full_bar[stage], m0 + 64 * j, k0 + a_off);
+            }
+            if (kd.b_mn) {
+#pragma unroll
+              for (int j = 0; j < kBNLocal / 64; ++j)  // boxes {64 n, 64 k}
+                ptx::tma_load_2d_pair(sb + j * (kBlockK * 128), mb, &full_bar[stage], n0 + 64 * j, k0);
+            } else {
+              ptx::tma_load_2d_pair(sb, mb, &full_bar[stage], k0, n0);  // box {64 k, 128 n}
+            }
+            if (++stage == kStages) {
+              stage = 0;
+              phase ^= 1u;
+            }
           }
         }
       }
@@ -208,28 +241,33 @@ __global__ void __launch_bounds__(kNumThreads, 1) chain_kernel(const __grid_cons
       for (int q = unit; q < p.total_tiles; q += num_units) {
         advance(q, s, base);
         const ChainKind& kd = p.kinds[p.stages[s].kind];
-        const bool b_mn = kd.b_mn != 0;
-        const uint32_t idesc = make_idesc(kTileM, BN, false, b_mn, false);
-        const uint32_t lbo_b = b_mn ? kBlockK * 128u : 16u;
-        const uint32_t adv_b = b_mn ? 2048u : 32u;
+        const bool a_mn = kd.a_mn != 0, b_mn = kd.b_mn != 0;
+        const uint32_t idesc_pos = make_idesc(kTileM, BN, a_mn, b_mn, false);
+        const uint32_t idesc_neg = make_idesc(kTileM, BN, a_mn, b_mn, true);
+        const uint32_t lbo_a = a_mn ? kBlockK * 128u : 16u, adv_a = a_mn ? 2048u : 32u;
+        const uint32_t lbo_b = b_mn ? kBlockK * 128u : 16u, adv_b = b_mn ? 2048u : 32u;
         const uint32_t as = accn & 1u;
         ptx::mbar_wait(&tmem_empty_bar[as], ((accn >> 1) & 1u) ^ 1u);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
-        for (int kb = 0; kb < kd.kblocks; ++kb) {
-          ptx::mbar_wait(&full_bar[stage], phase);
-          ptx::tc_fence_after();
-          const uint32_t sa = ptx::smem_u32(smem + stage * Cfg::kStageBytes);
-          const uint32_t sb = sa + Cfg::kABytes;
-          const uint64_t da = make_smem_desc(sa, 16u, 1024u);
-          const uint64_t db = make_smem_desc(sb, lbo_b, 1024u);
+        for (int seg = 0; seg < kd.nseg; ++seg) {
+          const uint32_t idesc = seg == 1 ? idesc_neg : idesc_pos;  // second segment: -vk^T hk
+          for (int kb = 0; kb < kd.kblocks; ++kb) {
+            ptx::mbar_wait(&full_bar[stage], phase);
+            ptx::tc_fence_after();
+            const uint32_t sa = ptx::smem_u32(smem + stage * Cfg::kStageBytes);
+            const uint32_t sb = sa + Cfg::kABytes;
+            const uint64_t da = make_smem_desc(sa, lbo_a, 1024u);
+            const uint64_t db = make_smem_desc(sb, lbo_b, 1024u);
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k)
-            ptx::mma_bf16<CG>(d_tmem, da + ((k * 32u) >> 4), db + ((k * adv_b) >> 4), idesc, (kb > 0 || k > 0) ? 1u : 0u);
-          ptx::mma_commit_pair(&empty_bar[stage], 0b11);
-          if (++stage == kStages) {
-            stage = 0;
-            phase ^= 1u;
+            for (int k = 0; k < kBlockK / 16; ++k)
+              ptx::mma_bf16<CG>(d_tmem, da + ((k * adv_a) >> 4), db + ((k * adv_b) >> 4), idesc,
+                                (seg > 0 || kb > 0 || k > 0) ? 1u : 0u);
+            ptx::mma_commit_pair(&empty_bar[stage], 0b11);
+            if (++stage == kStages) {
+              stage = 0;
+              phase ^= 1u;
+            }
           }
         }
         ptx::mma_commit_pair(&tmem_full_bar[as], 0b11);
@@ -250,7 +288,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) chain_kernel(const __grid_cons
       const int t = q - base;
       const int m_blk = t / kd.num_n, n_blk = t % kd.num_n;
       const int row = m_blk * kTileM + static_cast<int>(cta_rank) * kBlockM + quarter * 32 + lane;
-      const bool row_ok = row < m_valid;
+      const bool row_ok = row < (kd.batch_rows ? m_valid : kd.M);
       const uint64_t draw = draw_base + p.stages[s].phase;
       float row_acc = 0.f;
       const uint32_t as = accn & 1u;
@@ -264,8 +302,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) chain_kernel(const __grid_cons
         ptx::tmem_ld_wait();
         if (kd.epi == kEpiSample)
           epilogue_chunk<kEpiSample>(kd, acc, row, n_blk * BN + coff, row_ok, draw, row0, lane, row_acc);
-        else
+        else if (kd.epi == kEpiProb)
           epilogue_chunk<kEpiProb>(kd, acc, row, n_blk * BN + coff, row_ok, draw, row0, lane, row_acc);
+        else
+          epilogue_chunk<kEpiRaw>(kd, acc, row, n_blk * BN + coff, row_ok, draw, row0, lane, row_acc);
       }
       ptx::tc_fence_before();
       ptx::fence_proxy_async_global();  // these stores will be read by other CTAs' TMA loads
@@ -276,7 +316,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) chain_kernel(const __grid_cons
       ptx::named_bar_sync(1, kNumEpiWarps * 32);
       if (ew == 0 && lane == 0) {
         __threadfence();
-        atomicAdd(p.done + s * num_m + m_blk, 1u);
+        atomicAdd(p.done + s * done_stride + m_blk, 1u);
       }
     }
   }

@@ -694,7 +694,7 @@ static int apply_update(kucd_rbm* r, const kucd_hparams* hp, int64_t rows_global
 
 // The 2k+1 (+1 with persistent chains) projections of one minibatch as one persistent kernel (chain.cuh).
 static int launch_chain(kucd_rbm* r, const Planes& v0, int64_t batch, const kucd_hparams* hp, int64_t global_row0,
-                        uint64_t draw0, uint64_t stride, const StepDyn* dyn, bool v0_dyn) {
+                        uint64_t draw0, uint64_t stride, const StepDyn* dyn, bool v0_dyn, bool with_dw) {
   kucd_ctx* ctx = r->ctx;
   const int k = hp->k;
   const bool pcd = hp->persistent != 0;
@@ -713,6 +713,12 @@ static int launch_chain(kucd_rbm* r, const Planes& v0, int64_t batch, const kucd
           && make_tmap_bf16(&p.maps[6], Wv, kChainBN / 2, &err);        // h.W^T : W as (N,K), boxes {64 k, 128 n}
   if (!ok) return fail(KUCD_ERR_CUDA, "%s", err.c_str());
   p.maps[7] = p.maps[6];
+  // the same matrices as MN-major operands of the dW contraction (boxes {64 units, 64 minibatch rows})
+  auto mnmap = [&](int i, const Planes& q) {
+    return make_tmap_bf16(&p.maps[i], MatView{q.p[0], q.rows, q.cols, q.ld}, 64u, &err);
+  };
+  if (!(mnmap(8, v0) && mnmap(9, h0) && mnmap(10, vk) && mnmap(11, hk))) return fail(KUCD_ERR_CUDA, "%s", err.c_str());
+  const int num_m_batch = static_cast<int>((batch + 2 * kBlockM - 1) / (2 * kBlockM));
 
   auto kind = [&](int i, bool fwd, int map_a, __nv_bfloat16* out, int epi, float* colsum, float sign, bool a_dyn) {
     ChainKind& q = p.kinds[i];
@@ -731,6 +737,9 @@ static int launch_chain(kucd_rbm* r, const Planes& v0, int64_t batch, const kucd
     q.map_b = fwd ? 5 : 6;
     q.a_dyn = a_dyn ? 1 : 0;
     q.num_n = (q.N + kChainBN - 1) / kChainBN;
+    q.num_m = num_m_batch;
+    q.batch_rows = 1;
+    q.nseg = 1;
   };
   kind(0, true, 0, h0.p[0], kEpiSample, r->dc(), 1.f, v0_dyn);          // h_pos from v0            rbm.py:120
   kind(1, true, 4, hk.p[0], kEpiSample, nullptr, 0.f, false);            // first h of a stored chain (PCD)
@@ -760,15 +769,42 @@ static int launch_chain(kucd_rbm* r, const Planes& v0, int64_t batch, const kucd
     hsrc = stage(last ? 7 : 6, vs, 2u * t + 1);
     from_h0 = false;
   }
-  const int num_m = static_cast<int>((batch + 2 * kBlockM - 1) / (2 * kBlockM));
+  if (with_dw) {
+    // dW = v0^T h0 - vk^T hk (rbm.py:125-126) as the last stage: its first K-segment only needs stage 0, so the
+    // pairs that run out of projection tiles start it while the last projection is still finishing elsewhere
+    ChainKind& q = p.kinds[8];
+    q.out_f32 = r->dW();
+    q.ld_f32 = r->ldH;
+    q.epi = kEpiRaw;
+    q.M = static_cast<int32_t>(r->V);
+    q.N = static_cast<int32_t>(r->H);
+    q.seed = r->seed;
+    q.kblocks = static_cast<int32_t>((batch + kBlockK - 1) / kBlockK);
+    q.a_mn = 1;
+    q.b_mn = 1;
+    q.nseg = 2;
+    q.map_a = 8;
+    q.map_b = 9;
+    q.map_a2 = 10;
+    q.map_b2 = 11;
+    q.a_dyn = v0_dyn ? 1 : 0;
+    q.num_n = static_cast<int32_t>((r->H + kChainBN - 1) / kChainBN);
+    q.num_m = static_cast<int32_t>((r->V + 2 * kBlockM - 1) / (2 * kBlockM));
+    q.batch_rows = 0;
+    q.dep2 = hsrc;  // the final h stage (which itself waited for the final v stage, row block by row block)
+    stage(8, 0, 0);
+  }
+  const int num_m = std::max(num_m_batch, with_dw ? p.kinds[8].num_m : 0);  // stride of the counter array
   int total = 0;
-  for (int i = 0; i < ns; ++i) total += num_m * p.kinds[p.stages[i].kind].num_n;
+  for (int i = 0; i < ns; ++i) total += p.kinds[p.stages[i].kind].num_m * p.kinds[p.stages[i].kind].num_n;
   p.num_stages = ns;
   p.M = static_cast<int32_t>(batch);
   p.m_valid = static_cast<int32_t>(batch);
   p.total_tiles = total;
   KU_TRY(r->chain_done.ensure(static_cast<size_t>(kMaxChainStages) * num_m * 4));
   p.done = r->chain_done.as<uint32_t>();
+  p.done_stride = num_m;
+  p.num_m_batch = num_m_batch;
   p.draw = draw0;
   p.draw_stride = stride;
   p.row0 = global_row0;
@@ -801,6 +837,7 @@ static int launch_chain(kucd_rbm* r, const Planes& v0, int64_t batch, const kucd
   if (prof) ctx->marks.push_back({0, pe0, prof_event(ctx), ns});
   ctx->tm.gemm_launches++;
   ctx->tm.chain_launches++;
+  if (with_dw) ctx->tm.chain_dw_launches++;
   return KUCD_OK;
 }
 
@@ -929,8 +966,15 @@ static int enqueue_cd(kucd_rbm* r, const Planes& v0, int64_t batch, const kucd_h
   const bool whole_chain = ctx->chain && r->compute == KUCD_COMPUTE_BF16 && !gaussian && inj == nullptr && v0.n == 1 &&
                            (pair_tiles >= ctx->num_sms / 2 || ctx->chain_force) &&
                            (!hp->persistent || r->last_vk_parts == 1);
+  // KUCD_CHAIN_DW=1 appends the dW contraction to the chain kernel as a final two-segment stage.  Measured: no gain
+  // at C3 (2.529 vs 2.522 ms per step) and a loss at C4 (577 k vs 605 k samples/s) - its second segment has to wait
+  // for every row block of the last projection, so it hides little - which is why it is off by default.
+  static const bool chain_dw = [] {
+    const char* e = getenv("KUCD_CHAIN_DW");
+    return e != nullptr && e[0] == '1';
+  }();
   if (whole_chain) {
-    KU_TRY(launch_chain(r, v0, batch, hp, global_row0, draw0, stride, dyn, v0_dyn));
+    KU_TRY(launch_chain(r, v0, batch, hp, global_row0, draw0, stride, dyn, v0_dyn, chain_dw));
   } else if (!two) {
     KU_TRY(chain(0, batch, ctx->stream, true));
   } else {
@@ -947,7 +991,7 @@ static int enqueue_cd(kucd_rbm* r, const Planes& v0, int64_t batch, const kucd_h
     KU_TRY(rc);
     if (prof) ctx->marks.push_back({0, pe0, prof_event(ctx), 2 * n_proj});
   }
-  KU_TRY(delta_w(r, v0, h0, vk, hk, batch, dyn, v0_dyn));
+  if (!(whole_chain && chain_dw)) KU_TRY(delta_w(r, v0, h0, vk, hk, batch, dyn, v0_dyn));
   r->last_rows = batch;
   r->last_vk_parts = vparts;
   r->last_hk_parts = pparts;

@@ -411,6 +411,7 @@ def test_whole_chain_kernel_equals_per_projection_launches(monkeypatch):
     from keras_unsupervised_b200.engine import Context, Dataset, Machine
 
     monkeypatch.setenv("KUCD_CHAIN", "2")
+    monkeypatch.setenv("KUCD_CHAIN_DW", "1")   # also carry dW inside the chain kernel (off by default)
     c_chain = Context(device=0, seed=1)
     monkeypatch.setenv("KUCD_CHAIN", "0")
     c_plain = Context(device=0, seed=1)
