@@ -143,6 +143,7 @@ struct kucd_ctx {
   bool split = true;               // KUCD_SPLIT=0 turns the two-chain schedule off, 2 forces it (tests)
   bool split_force = false;
   bool chain_force = false;        // KUCD_CHAIN=2: use it at any size (tests)
+  bool chain_dw = false;           // KUCD_CHAIN_DW=1
   bool chain = true;               // KUCD_CHAIN=0: launch the projections one by one instead of the chain kernel
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   kucd_timings tm{};
@@ -969,10 +970,7 @@ static int enqueue_cd(kucd_rbm* r, const Planes& v0, int64_t batch, const kucd_h
   // KUCD_CHAIN_DW=1 appends the dW contraction to the chain kernel as a final two-segment stage.  Measured: no gain
   // at C3 (2.529 vs 2.522 ms per step) and a loss at C4 (577 k vs 605 k samples/s) - its second segment has to wait
   // for every row block of the last projection, so it hides little - which is why it is off by default.
-  static const bool chain_dw = [] {
-    const char* e = getenv("KUCD_CHAIN_DW");
-    return e != nullptr && e[0] == '1';
-  }();
+  const bool chain_dw = ctx->chain_dw;
   if (whole_chain) {
     KU_TRY(launch_chain(r, v0, batch, hp, global_row0, draw0, stride, dyn, v0_dyn, chain_dw));
   } else if (!two) {
@@ -1150,6 +1148,8 @@ int kucd_ctx_create(kucd_ctx** out, int device_id, uint64_t seed) {
     const char* ch = getenv("KUCD_CHAIN");
     c->chain = !(ch != nullptr && ch[0] == '0');
     c->chain_force = ch != nullptr && ch[0] == '2';
+    const char* cd = getenv("KUCD_CHAIN_DW");
+    c->chain_dw = cd != nullptr && cd[0] == '1';
   }
   CU_TRY(cudaEventCreate(&c->ev0));
   CU_TRY(cudaEventCreate(&c->ev1));

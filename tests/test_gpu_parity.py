@@ -429,7 +429,7 @@ def test_whole_chain_kernel_equals_per_projection_launches(monkeypatch):
         m.cd_step(v, hp)
         got.append(m.last_stats(700))
     t = c_chain.timings()
-    assert t["chain_launches"] == 1 and c_plain.timings()["chain_launches"] == 0
+    assert t["chain_launches"] == 1 and t["chain_dw_launches"] == 1 and c_plain.timings()["chain_launches"] == 0
     for key in ("h_pos", "v_neg", "h_neg", "dW", "db"):
         assert np.array_equal(got[0][key], got[1][key]), key
     np.testing.assert_allclose(got[0]["dc"], got[1]["dc"], rtol=0, atol=1e-3)
