@@ -458,3 +458,51 @@ def test_whole_chain_kernel_equals_per_projection_launches(monkeypatch):
     np.testing.assert_allclose(params[0][2], params[1][2], rtol=0, atol=1e-6)
     c_chain.close()
     c_plain.close()
+
+
+def test_chain_kernel_dataflow_stress(monkeypatch):
+    """200 CD-5 minibatches through the chain kernel (cross-CTA row-block flags, TMA reads of rows other CTAs just
+    wrote) against the launch-per-projection path, statistics compared exactly at every step: a missed fence or a
+    premature flag shows up as a differing dW."""
+    from keras_unsupervised_b200.engine import Context, Machine
+
+    monkeypatch.setenv("KUCD_CHAIN", "2")
+    c_chain = Context(device=0, seed=1)
+    monkeypatch.setenv("KUCD_CHAIN", "0")
+    c_plain = Context(device=0, seed=1)
+    rng = np.random.default_rng(5)
+    V, H, B = 1024, 768, 2048
+    a, _ = _machine(c_chain, V, H, "bf16", seed=3)
+    b, _ = _machine(c_plain, V, H, "bf16", seed=3)
+    hp = Machine.hparams(lr=1e-3, k=5, update_mask=0)
+    import torch
+
+    g = torch.Generator(device="cuda")
+    g.manual_seed(7)
+    for step in range(200):
+        x = (torch.rand((B, V), device="cuda", generator=g) < 0.3).to(torch.uint8)
+        a.cd_step(x, hp)
+        b.cd_step(x, hp)
+        if step % 10 == 0 or step > 190:
+            sa, sb = a.last_stats(B, states=False), b.last_stats(B, states=False)
+            assert np.array_equal(sa["dW"], sb["dW"]) and np.array_equal(sa["db"], sb["db"]), step
+    assert c_chain.timings()["chain_launches"] == 200
+    c_chain.close()
+    c_plain.close()
+
+
+def test_sample_frequencies_follow_the_probabilities(ctx):
+    """Philox mode: over 256 independent draws the empirical frequency of h_j = 1 matches sigmoid(v.W + c)."""
+    rng = np.random.default_rng(13)
+    rows, V, H, n = 64, 128, 96, 256
+    m, orc = _machine(ctx, V, H, "f32", seed=99)
+    W = rng.normal(0, 0.3, (V, H)).astype(np.float32)
+    m.set_params(W=W)
+    orc.W = W
+    v = _data(rng, rows, V)
+    p = orc.prob_h(v).astype(np.float64)
+    freq = np.zeros_like(p)
+    for _ in range(n):
+        freq += m.transform(v)
+    z = (freq - n * p) / np.sqrt(n * p * (1 - p) + 1e-12)
+    assert np.abs(z).max() < 5.5 and abs(z.mean()) < 0.05 and 0.9 < z.std() < 1.1
