@@ -125,6 +125,7 @@ typedef struct kucd_timings {
   int64_t graph_launches;   /* CUDA-graph replays (each replays a whole CD step)                     */
   int64_t graph_kernel_launches; /* kernels those replays launched                                    */
   int64_t allreduce_calls;
+  int64_t fused_reduce_steps; /* steps whose dW/db/dc exchange ran over peer-mapped memory instead of NCCL  */
   int64_t h2d_bytes, d2h_bytes;
   /* per-launch CUDA-event timing of directly launched contractions, on while kucd_ctx_set_profile(1) */
   int64_t proj_timed, dw_timed; /* launches timed: projections (v.W, h.W^T), dW contractions          */
@@ -170,6 +171,17 @@ int kucd_rbm_get_params(kucd_rbm* rbm, kucd_tensor* W, kucd_tensor* b, kucd_tens
 int kucd_rbm_set_seed(kucd_rbm* rbm, uint64_t seed, uint64_t step_count);
 /* what a checkpoint needs besides the parameters: the stream position and the number of stored chains */
 int kucd_rbm_get_counters(kucd_rbm* rbm, uint64_t* seed, uint64_t* step_count, int64_t* n_chains);
+
+/* Fused reduction (optional, bf16 compute, 2..8 ranks on one NVLink domain).  After kucd_ctx_comm_init every rank
+ * calls kucd_rbm_peer_export on its model (128 bytes of CUDA IPC handles out), the ranks exchange them, and every
+ * rank calls kucd_rbm_peer_attach with all of them in rank order (world x 128 bytes).  From then on the dW
+ * contraction stores each output row directly into its owner rank's memory (reduce-scatter inside the epilogue,
+ * NVLink stores overlapped with the MMAs), the owner updates its rows and stores the refreshed bf16 rows into every
+ * rank's operand plane, and two flag barriers per step replace the NCCL all-reduce.  The sum over ranks runs in a
+ * fixed order: every rank (and every run) gets the same bits.  fp32 master rows are re-gathered (ncclBroadcast) when
+ * a training call returns. */
+int kucd_rbm_peer_export(kucd_rbm* rbm, void* handle128);
+int kucd_rbm_peer_attach(kucd_rbm* rbm, const void* handles);
 
 /* ---- inference ------------------------------------------------------------------------------------- */
 /* transform_func (rbm.py:45-48, 88-89) and RBM.call (rbm.py:80-83):  h = 1[u < sigmoid(v.W + c)]

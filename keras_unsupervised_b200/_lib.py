@@ -65,7 +65,7 @@ class Timings(C.Structure):
     _fields_ = [("gemm_launches", C.c_int64), ("chain_launches", C.c_int64), ("chain_dw_launches", C.c_int64),
                 ("aux_launches", C.c_int64),
                 ("graph_launches", C.c_int64),
-                ("graph_kernel_launches", C.c_int64), ("allreduce_calls", C.c_int64), ("h2d_bytes", C.c_int64),
+                ("graph_kernel_launches", C.c_int64), ("allreduce_calls", C.c_int64), ("fused_reduce_steps", C.c_int64), ("h2d_bytes", C.c_int64),
                 ("d2h_bytes", C.c_int64), ("proj_timed", C.c_int64), ("dw_timed", C.c_int64),
                 ("proj_ms", C.c_float), ("dw_ms", C.c_float), ("last_gemm_ms", C.c_float)]
 
@@ -88,6 +88,8 @@ SIGNATURES = {
     "kucd_rbm_destroy": (C.c_int, [_P]),
     "kucd_rbm_set_params": (C.c_int, [_P, _TP, _TP, _TP]),
     "kucd_rbm_get_params": (C.c_int, [_P, _TP, _TP, _TP]),
+    "kucd_rbm_peer_export": (C.c_int, [_P, _P]),
+    "kucd_rbm_peer_attach": (C.c_int, [_P, _P]),
     "kucd_rbm_set_seed": (C.c_int, [_P, C.c_uint64, C.c_uint64]),
     "kucd_rbm_get_counters": (C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_int64)]),
     "kucd_rbm_transform": (C.c_int, [_P, _TP, _TP, _TP, _TP]),

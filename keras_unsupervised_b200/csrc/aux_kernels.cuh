@@ -326,6 +326,114 @@ __global__ void copy_rows_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfl
     reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(src)[i];
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Data-parallel exchange over peer-mapped memory (NVLink): see kucd.cu, "fused reduction"
+// ---------------------------------------------------------------------------------------------------
+struct PeerSet {
+  float* dw_slot[8];      // rank j's dW slots: slot s (at s * slice_elems) holds rank s's contribution to rank j's rows
+  float* bias_slot[8];    // rank j's bias slots: slot s (at s * bias_len) holds rank s's [db | dc]
+  uint32_t* flags[8];     // rank j's arrival flags, one per source rank
+  __nv_bfloat16* wp[8];   // rank j's bf16 operand plane of W
+};
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// All-to-all arrival barrier between the ranks' streams: everything this rank wrote into peer memory before this
+// kernel is visible to a peer once the peer has seen this rank's flag.  One thread per peer.
+__global__ void peer_barrier_kernel(uint32_t* epoch, PeerSet ps, int me, int n) {
+  __shared__ uint32_t e_sh;
+  if (threadIdx.x == 0) e_sh = ++(*epoch);
+  __syncthreads();
+  const uint32_t e = e_sh;
+  const int j = threadIdx.x;
+  if (j >= n) return;
+  __threadfence_system();
+  st_release_sys(ps.flags[j] + me, e);
+  const uint32_t* mine = ps.flags[me] + j;
+  if (ld_acquire_sys(mine) < e) {
+    const long long t0 = clock64();
+    while (ld_acquire_sys(mine) < e) {
+      if (clock64() - t0 > 8000000000ll) {
+        printf("kucd: peer barrier timed out (rank %d waits for rank %d, epoch %u, sees %u)\n", me, j, e,
+               ld_acquire_sys(mine));
+        __trap();
+      }
+    }
+  }
+}
+
+// this rank's [db | dc] into every rank's bias slot for it
+__global__ void push_bias_kernel(const float* __restrict__ mine, PeerSet ps, int me, int n, int len) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= len) return;
+  const float v = mine[i];
+  for (int j = 0; j < n; ++j) ps.bias_slot[j][static_cast<int64_t>(me) * len + i] = v;
+}
+
+// out[i] = sum over ranks of slot s (fixed order: the result is the same on every rank and in every run)
+__global__ void reduce_bias_kernel(const float* __restrict__ slots, int n, int len, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= len) return;
+  float s = 0.f;
+  for (int j = 0; j < n; ++j) s += slots[static_cast<int64_t>(j) * len + i];
+  out[i] = s;
+}
+
+// The owner's part of the update (rbm.py:127-128 on rows [r0, r0 + rows) of W): dW = sum of the n ranks' slots (fixed
+// order), fp32 master and momentum updated locally, and the refreshed bf16 rows stored into EVERY rank's operand
+// plane - the all-gather of the new W happens inside the update kernel, as plain NVLink stores.
+__global__ void update_w_sharded_kernel(float* __restrict__ W, const float* __restrict__ slots, int64_t slice_elems,
+                                        int n, float* __restrict__ mom, PeerSet ps, int64_t elem0, int64_t n4, float lr,
+                                        float scale, float momentum, float weight_decay) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = 0; j < n; ++j) {
+      const float4 t = reinterpret_cast<const float4*>(slots + j * slice_elems)[i];
+      d.x += t.x;
+      d.y += t.y;
+      d.z += t.z;
+      d.w += t.w;
+    }
+    float4* wp = reinterpret_cast<float4*>(W + elem0) + i;
+    float4 w = *wp;
+    float4 s;
+    s.x = lr * (scale * d.x - weight_decay * w.x);
+    s.y = lr * (scale * d.y - weight_decay * w.y);
+    s.z = lr * (scale * d.z - weight_decay * w.z);
+    s.w = lr * (scale * d.w - weight_decay * w.w);
+    if (mom != nullptr) {
+      float4* mp = reinterpret_cast<float4*>(mom + elem0) + i;
+      float4 m = *mp;
+      m.x = momentum * m.x + s.x;
+      m.y = momentum * m.y + s.y;
+      m.z = momentum * m.z + s.z;
+      m.w = momentum * m.w + s.w;
+      *mp = m;
+      s = m;
+    }
+    w.x += s.x;
+    w.y += s.y;
+    w.z += s.z;
+    w.w += s.w;
+    *wp = w;
+    __nv_bfloat16 h[4];
+    h[0] = __float2bfloat16_rn(w.x);
+    h[1] = __float2bfloat16_rn(w.y);
+    h[2] = __float2bfloat16_rn(w.z);
+    h[3] = __float2bfloat16_rn(w.w);
+    const uint2 packed = *reinterpret_cast<const uint2*>(h);
+    for (int j = 0; j < n; ++j) (reinterpret_cast<uint2*>(ps.wp[j] + elem0))[i] = packed;
+  }
+}
+
 __global__ void set_dyn_kernel(StepDyn* dyn, int64_t row_off, int32_t rows_valid, uint64_t step) {
   dyn->row_off = row_off;
   dyn->rows_valid = rows_valid;

@@ -89,6 +89,12 @@ struct alignas(64) GemmParams {
   uint32_t a_dyn_mask;  // bit s: the row coordinate of segment s's A operand is offset by dyn->row_off
   const StepDyn* dyn;   // optional device-resident step state (graph replay)
   uint64_t draw_stride;  // draw += dyn->step * draw_stride
+  // ---- fused reduce-scatter of dW over NVLink (data-parallel ranks, raw epilogue only) ----
+  // Output row r belongs to rank o = r / push_rows; this rank's contribution to it is stored into
+  // push_base[o] (rank o's slot for this rank, peer-mapped memory; push_base[me] is local), row r - o * push_rows.
+  float* push_base[8];
+  int32_t push_rows;  // 0: off, rows are written to out_f32
+  int32_t push_pad;
   // ---- descriptor overrides used only by the bring-up probe (0 = default) ----
   uint32_t dbg_lbo_a, dbg_sbo_a, dbg_adv_a, dbg_lbo_b, dbg_sbo_b, dbg_adv_b;
   uint32_t dbg_flags;  // probe only: 1 = producer signals "full" without loading (MMA pacing alone),
@@ -160,6 +166,20 @@ __device__ __forceinline__ void box_muller(uint32_t b0, uint32_t b1, float& n0, 
   n1 = r * s;
 }
 
+// where the raw (fp32) epilogue writes output row `row`
+template <typename P>
+__device__ __forceinline__ float* raw_row_ptr(const P& p, int row) {
+  return p.out_f32 + static_cast<int64_t>(row) * p.ld_f32;
+}
+template <>
+__device__ __forceinline__ float* raw_row_ptr<GemmParams>(const GemmParams& p, int row) {
+  if (p.push_rows > 0) {
+    const int o = row / p.push_rows;
+    return p.push_base[o] + static_cast<int64_t>(row - o * p.push_rows) * p.ld_f32;
+  }
+  return p.out_f32 + static_cast<int64_t>(row) * p.ld_f32;
+}
+
 // One 32-column chunk of one output row (this thread's TMEM lane).
 template <int EPI, typename P>
 __device__ __forceinline__ void epilogue_chunk(const P& p, const uint32_t (&acc)[32], int row, int col0,
@@ -170,7 +190,7 @@ __device__ __forceinline__ void epilogue_chunk(const P& p, const uint32_t (&acc)
 
   if constexpr (EPI == kEpiRaw) {
     if (row_ok) {
-      float* dst = p.out_f32 + static_cast<int64_t>(row) * p.ld_f32 + col0;
+      float* dst = raw_row_ptr(p, row) + col0;
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         if (col0 + 4 * q < p.N) {

@@ -76,6 +76,9 @@ struct NcclApi {
   int (*CommInitRank)(void**, int, NcclUid, int) = nullptr;
   int (*CommDestroy)(void*) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*Broadcast)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
 };
 static NcclApi g_nccl;
@@ -96,8 +99,11 @@ static int nccl_load() {
   g_nccl.CommDestroy = reinterpret_cast<decltype(g_nccl.CommDestroy)>(dlsym(lib, "ncclCommDestroy"));
   g_nccl.AllReduce = reinterpret_cast<decltype(g_nccl.AllReduce)>(dlsym(lib, "ncclAllReduce"));
   g_nccl.GetErrorString = reinterpret_cast<decltype(g_nccl.GetErrorString)>(dlsym(lib, "ncclGetErrorString"));
+  g_nccl.Broadcast = reinterpret_cast<decltype(g_nccl.Broadcast)>(dlsym(lib, "ncclBroadcast"));
+  g_nccl.GroupStart = reinterpret_cast<decltype(g_nccl.GroupStart)>(dlsym(lib, "ncclGroupStart"));
+  g_nccl.GroupEnd = reinterpret_cast<decltype(g_nccl.GroupEnd)>(dlsym(lib, "ncclGroupEnd"));
   if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommDestroy || !g_nccl.AllReduce ||
-      !g_nccl.GetErrorString)
+      !g_nccl.GetErrorString || !g_nccl.Broadcast || !g_nccl.GroupStart || !g_nccl.GroupEnd)
     return fail(KUCD_ERR_NCCL, "libnccl lacks a required symbol");
   g_nccl.lib = lib;
   return KUCD_OK;
@@ -109,7 +115,10 @@ static int nccl_load() {
 struct DevBuf {
   void* p = nullptr;
   size_t bytes = 0;
-  int ensure(size_t n, bool zero = false) {
+  // `shareable`: the buffer may be exported with cudaIpcGetMemHandle.  The driver carves small allocations out of
+  // shared 2 MiB blocks and an IPC handle maps the whole block, so exported buffers get whole blocks of their own.
+  int ensure(size_t n, bool zero = false, bool shareable = false) {
+    if (shareable) n = std::max<size_t>((n + (2u << 20) - 1) / (2u << 20) * (2u << 20), 2u << 20);
     if (n <= bytes) return KUCD_OK;
     if (p != nullptr) cudaFree(p);
     p = nullptr;
@@ -174,8 +183,8 @@ struct Planes {
 struct PlaneBuf {
   DevBuf buf[3];
   int64_t rows = 0, ld = 0;
-  int ensure(int64_t r, int64_t ld_, int nplanes) {
-    for (int i = 0; i < nplanes; ++i) KU_TRY(buf[i].ensure(static_cast<size_t>(r) * ld_ * 2));
+  int ensure(int64_t r, int64_t ld_, int nplanes, bool shareable = false) {
+    for (int i = 0; i < nplanes; ++i) KU_TRY(buf[i].ensure(static_cast<size_t>(r) * ld_ * 2, false, shareable));
     rows = r;
     ld = ld_;
     return KUCD_OK;
@@ -234,6 +243,15 @@ struct kucd_rbm {
   DevBuf fe0, fe1, sp0, sp1, pstage, stats, flag;
   DevBuf dyn;
   DevBuf chain_done;  // (stage, row block) completion counters of the chain kernel
+  // fused reduction over peer-mapped memory (data-parallel ranks on one NVLink domain)
+  bool peer_on = false;
+  DevBuf arena;               // [n dW slots | n bias slots | flags | epoch]
+  PeerSet ps{};
+  void* peer_open[16] = {};   // pointers obtained from cudaIpcOpenMemHandle (to be closed)
+  int n_peer_open = 0;
+  int64_t rows_per = 0, slice_elems = 0;
+  int bias_len = 0;
+  uint32_t* epoch = nullptr;
   uint64_t seed = 0;  // Philox key; draws are (seed, draw id, global row, column)
   uint64_t step_count = 0, infer_draws = 0, score_draws = 0;
   int64_t last_rows = 0;
@@ -604,6 +622,10 @@ static int delta_w(kucd_rbm* r, const Planes& v0, const Planes& h0, const Planes
   p.m_valid = static_cast<int32_t>(r->V);
   p.dyn = dyn;
   p.a_dyn_mask = dyn_mask;
+  if (r->peer_on) {  // each output row goes straight into its owner's slot for this rank
+    p.push_rows = static_cast<int32_t>(r->rows_per);
+    for (int o = 0; o < ctx->world; ++o) p.push_base[o] = r->ps.dw_slot[o] + ctx->rank * r->slice_elems;
+  }
   std::string err;
   const bool prof = ctx->profile && dyn == nullptr;
   const size_t pe0 = prof ? prof_event(ctx) : 0;
@@ -668,7 +690,23 @@ static int apply_update(kucd_rbm* r, const kucd_hparams* hp, int64_t rows_global
     KU_TRY(r->mb.ensure(r->ldVb() * 4, true));
     KU_TRY(r->mc.ensure(r->ldHb() * 4, true));
   }
-  if (hp->update_mask & KUCD_UPDATE_W) {
+  if (r->peer_on) {
+    // global [db | dc] = sum of the ranks' slots; the biases are updated identically on every rank
+    const int n = ctx->world, me = ctx->rank;
+    reduce_bias_kernel<<<(r->bias_len + 255) / 256, 256, 0, ctx->stream>>>(r->ps.bias_slot[me], n, r->bias_len, r->db());
+    ctx->tm.aux_launches++;
+    if (hp->update_mask & KUCD_UPDATE_W) {
+      const int64_t r0 = me * r->rows_per;
+      const int64_t rows = std::max<int64_t>(0, std::min<int64_t>(r->rows_per, r->V - r0));
+      const int64_t n4 = rows * r->ldH / 4;
+      if (n4 > 0) {
+        update_w_sharded_kernel<<<grid_for(ctx, n4, 256), 256, 0, ctx->stream>>>(
+            r->W32.as<float>(), r->ps.dw_slot[me], r->slice_elems, n, use_mom ? r->mW.as<float>() : nullptr, r->ps,
+            r0 * r->ldH, n4, hp->lr, scale, hp->momentum, hp->weight_decay);
+        ctx->tm.aux_launches++;
+      }
+    }
+  } else if (hp->update_mask & KUCD_UPDATE_W) {
     const int64_t n4 = r->V * r->ldH / 4;
     update_w_kernel<<<grid_for(ctx, n4, 256), 256, 0, ctx->stream>>>(
         r->W32.as<float>(), r->dW(), use_mom ? r->mW.as<float>() : nullptr, r->Wp.buf[0].as<__nv_bfloat16>(),
@@ -689,7 +727,29 @@ static int apply_update(kucd_rbm* r, const kucd_hparams* hp, int64_t rows_global
                                                                      scale, hp->momentum);
     ctx->tm.aux_launches++;
   }
+  if (r->peer_on) {
+    // every rank's rows of the new bf16 W must have landed in this rank's operand plane before the next chain
+    peer_barrier_kernel<<<1, 32, 0, ctx->stream>>>(r->epoch, r->ps, ctx->rank, ctx->world);
+    ctx->tm.aux_launches++;
+  }
   CU_TRY(cudaGetLastError());
+  return KUCD_OK;
+}
+
+// fp32 master rows updated by their owners -> every rank (NCCL broadcasts, at API boundaries only)
+static int gather_master(kucd_rbm* r) {
+  kucd_ctx* ctx = r->ctx;
+  if (!r->peer_on) return KUCD_OK;
+  int rc = g_nccl.GroupStart();
+  for (int o = 0; o < ctx->world && rc == 0; ++o) {
+    const int64_t r0 = o * r->rows_per;
+    const int64_t rows = std::max<int64_t>(0, std::min<int64_t>(r->rows_per, r->V - r0));
+    if (rows == 0) continue;
+    float* slice = r->W32.as<float>() + r0 * r->ldH;
+    rc = g_nccl.Broadcast(slice, slice, static_cast<size_t>(rows * r->ldH), /*ncclFloat32*/ 7, o, ctx->comm, ctx->stream);
+  }
+  const int rc2 = g_nccl.GroupEnd();
+  if (rc != 0 || rc2 != 0) return fail(KUCD_ERR_NCCL, "ncclBroadcast: %s", g_nccl.GetErrorString(rc != 0 ? rc : rc2));
   return KUCD_OK;
 }
 
@@ -970,7 +1030,7 @@ static int enqueue_cd(kucd_rbm* r, const Planes& v0, int64_t batch, const kucd_h
   // KUCD_CHAIN_DW=1 appends the dW contraction to the chain kernel as a final two-segment stage.  Measured: no gain
   // at C3 (2.529 vs 2.522 ms per step) and a loss at C4 (577 k vs 605 k samples/s) - its second segment has to wait
   // for every row block of the last projection, so it hides little - which is why it is off by default.
-  const bool chain_dw = ctx->chain_dw;
+  const bool chain_dw = ctx->chain_dw && !r->peer_on;
   if (whole_chain) {
     KU_TRY(launch_chain(r, v0, batch, hp, global_row0, draw0, stride, dyn, v0_dyn, chain_dw));
   } else if (!two) {
@@ -1003,7 +1063,16 @@ static int enqueue_cd(kucd_rbm* r, const Planes& v0, int64_t batch, const kucd_h
     }
     CU_TRY(cudaGetLastError());
   }
-  if (ctx->comm != nullptr) {
+  if (r->peer_on) {
+    // The dW contraction has already stored every row into its owner's slot (reduce-scatter fused into the
+    // epilogue, NVLink stores overlapped with the MMAs).  Ship the small bias statistics the same way, then meet:
+    // after the barrier every slot of this rank holds this step's contributions of all ranks.
+    push_bias_kernel<<<(r->bias_len + 255) / 256, 256, 0, ctx->stream>>>(r->db(), r->ps, ctx->rank, ctx->world, r->bias_len);
+    peer_barrier_kernel<<<1, 32, 0, ctx->stream>>>(r->epoch, r->ps, ctx->rank, ctx->world);
+    ctx->tm.aux_launches += 2;
+    ctx->tm.fused_reduce_steps++;
+    CU_TRY(cudaGetLastError());
+  } else if (ctx->comm != nullptr) {
     const int rc = g_nccl.AllReduce(r->grad.p, r->grad.p, static_cast<size_t>(r->grad_elems()), /*ncclFloat32*/ 7,
                                     /*ncclSum*/ 0, ctx->comm, ctx->stream);
     if (rc != 0) return fail(KUCD_ERR_NCCL, "ncclAllReduce: %s", g_nccl.GetErrorString(rc));
@@ -1267,7 +1336,7 @@ int kucd_rbm_create(kucd_ctx* ctx, int64_t V, int64_t H, int mode, int compute, 
     if (rc == KUCD_OK) rc = x;
   };
   T(r->W32.ensure(static_cast<size_t>(V) * r->ldH * 4, true));
-  T(r->Wp.ensure(V, r->ldH, r->wparts));
+  T(r->Wp.ensure(V, r->ldH, r->wparts, /*shareable=*/true));
   for (int i = 0; i < r->wparts && rc == KUCD_OK; ++i)
     if (cudaMemset(r->Wp.buf[i].p, 0, r->Wp.buf[i].bytes) != cudaSuccess) rc = fail(KUCD_ERR_CUDA, "memset");
   T(r->b32.ensure(r->ldVb() * 4, true));
@@ -1290,6 +1359,8 @@ int kucd_rbm_destroy(kucd_rbm* r) {
   cudaStreamSynchronize(r->ctx->stream);
   if (r->graph_exec != nullptr) cudaGraphExecDestroy(r->graph_exec);
   if (r->graph != nullptr) cudaGraphDestroy(r->graph);
+  for (int i = 0; i < r->n_peer_open; ++i) cudaIpcCloseMemHandle(r->peer_open[i]);
+  r->arena.release();
   for (DevBuf* b : {&r->W32, &r->b32, &r->c32, &r->mW, &r->mb, &r->mc, &r->grad, &r->fe0, &r->fe1, &r->sp0, &r->sp1,
                     &r->pstage, &r->stats, &r->flag, &r->dyn, &r->chain_done})
     b->release();
@@ -1339,6 +1410,75 @@ int kucd_rbm_set_seed(kucd_rbm* r, uint64_t seed, uint64_t step_count) {
   r->step_count = step_count;
   r->infer_draws = 0;
   r->score_draws = 0;
+  return KUCD_OK;
+}
+
+// ---- fused reduction: peer-mapped exchange buffers ---------------------------------------------------
+int kucd_rbm_peer_export(kucd_rbm* r, void* handle128) {
+  if (r == nullptr || handle128 == nullptr) return fail(KUCD_ERR_INVALID_ARG, "NULL argument");
+  kucd_ctx* ctx = r->ctx;
+  CU_TRY(cudaSetDevice(ctx->device));
+  const int n = ctx->world;
+  if (n < 2 || n > 8) return fail(KUCD_ERR_INVALID_ARG, "the fused reduction needs 2..8 ranks (have %d)", n);
+  if (ctx->comm == nullptr) return fail(KUCD_ERR_INVALID_ARG, "join the data-parallel group first");
+  if (r->compute != KUCD_COMPUTE_BF16) return fail(KUCD_ERR_INVALID_ARG, "the fused reduction is built for bf16 compute");
+  r->rows_per = (r->V + n - 1) / n;
+  r->slice_elems = r->rows_per * r->ldH;
+  r->bias_len = static_cast<int>(r->ldVb() + r->ldHb());
+  const size_t bytes = (static_cast<size_t>(n) * r->slice_elems + static_cast<size_t>(n) * r->bias_len) * 4 + 1024;
+  KU_TRY(r->arena.ensure(bytes, false, /*shareable=*/true));
+  CU_TRY(cudaMemset(r->arena.p, 0, r->arena.bytes));
+  {  // canary checked by the attaching side: the mapping must start where this allocation starts
+    const uint32_t magic = 0x4b554344u + static_cast<uint32_t>(ctx->rank);
+    uint32_t* flags = reinterpret_cast<uint32_t*>(r->arena.as<float>() + static_cast<int64_t>(n) * r->slice_elems +
+                                                  static_cast<int64_t>(n) * r->bias_len);
+    CU_TRY(cudaMemcpy(flags + 128, &magic, 4, cudaMemcpyHostToDevice));
+  }
+  cudaIpcMemHandle_t h[2];
+  CU_TRY(cudaIpcGetMemHandle(&h[0], r->arena.p));
+  CU_TRY(cudaIpcGetMemHandle(&h[1], r->Wp.buf[0].p));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
+  memcpy(handle128, h, 128);
+  return KUCD_OK;
+}
+
+int kucd_rbm_peer_attach(kucd_rbm* r, const void* handles) {
+  if (r == nullptr || handles == nullptr) return fail(KUCD_ERR_INVALID_ARG, "NULL argument");
+  kucd_ctx* ctx = r->ctx;
+  CU_TRY(cudaSetDevice(ctx->device));
+  const int n = ctx->world, me = ctx->rank;
+  if (r->arena.p == nullptr) return fail(KUCD_ERR_INVALID_ARG, "kucd_rbm_peer_export first");
+  const char* hs = static_cast<const char*>(handles);
+  for (int j = 0; j < n; ++j) {
+    void *pa = nullptr, *pw = nullptr;
+    if (j == me) {
+      pa = r->arena.p;
+      pw = r->Wp.buf[0].p;
+    } else {
+      cudaIpcMemHandle_t h[2];
+      memcpy(h, hs + 128 * j, 128);
+      CU_TRY(cudaIpcOpenMemHandle(&pa, h[0], cudaIpcMemLazyEnablePeerAccess));
+      r->peer_open[r->n_peer_open++] = pa;
+      CU_TRY(cudaIpcOpenMemHandle(&pw, h[1], cudaIpcMemLazyEnablePeerAccess));
+      r->peer_open[r->n_peer_open++] = pw;
+    }
+    r->ps.dw_slot[j] = static_cast<float*>(pa);
+    r->ps.bias_slot[j] = r->ps.dw_slot[j] + static_cast<int64_t>(n) * r->slice_elems;
+    r->ps.flags[j] = reinterpret_cast<uint32_t*>(r->ps.bias_slot[j] + static_cast<int64_t>(n) * r->bias_len);
+    r->ps.wp[j] = static_cast<__nv_bfloat16*>(pw);
+    uint32_t magic = 0;
+    CU_TRY(cudaMemcpy(&magic, r->ps.flags[j] + 128, 4, cudaMemcpyDefault));
+    if (magic != 0x4b554344u + static_cast<uint32_t>(j))
+      return fail(KUCD_ERR_CUDA, "peer mapping of rank %d does not show its canary (got %08x)", j, magic);
+  }
+  r->epoch = r->ps.flags[me] + 64;
+  r->peer_on = true;
+  if (r->graph_exec != nullptr) {
+    cudaGraphExecDestroy(r->graph_exec);
+    cudaGraphDestroy(r->graph);
+    r->graph_exec = nullptr;
+    r->graph = nullptr;
+  }
   return KUCD_OK;
 }
 
@@ -1539,6 +1679,7 @@ int kucd_rbm_cd_step(kucd_rbm* r, const kucd_tensor* v_batch, const kucd_hparams
     if (hp->want_stats == 1) KU_TRY(enqueue_score(r, v0, rows, nullptr, 0, nullptr, 0, global_row0));
     KU_TRY(read_stats(r, stats, rows));
   }
+  KU_TRY(gather_master(r));
   const bool host_in = !on_device(v_batch) || inj != nullptr;
   if (host_in) CU_TRY(cudaStreamSynchronize(ctx->stream));
   for (auto& b : keep) b.release();
@@ -1809,6 +1950,7 @@ static int fit_range_impl(kucd_rbm* r, kucd_dataset* ds, int64_t batch, const ku
   CU_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
   for (int64_t s = 0; s < steps; ++s) CU_TRY(cudaGraphLaunch(r->graph_exec, ctx->stream));
   CU_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
+  KU_TRY(gather_master(r));
   ctx->tm.graph_launches += steps;
   ctx->tm.graph_kernel_launches += steps * r->graph_kernels;
   r->step_count += steps;
@@ -1939,6 +2081,7 @@ int kucd_rbm_fit_host(kucd_rbm* r, const kucd_tensor* V_all, int64_t batch, cons
     if (rc == KUCD_OK) rc = apply_update(r, hp, n * ctx->world);
   }
   cudaEventRecord(ctx->ev1, ctx->stream);
+  if (rc == KUCD_OK) rc = gather_master(r);
   cudaStreamSynchronize(ctx->copy_stream);
   const cudaError_t se = cudaStreamSynchronize(ctx->stream);
   if (rc == KUCD_OK && se != cudaSuccess) rc = fail(KUCD_ERR_CUDA, "fit_host: %s", cudaGetErrorString(se));

@@ -160,6 +160,22 @@ class Machine:
         ctx._children.add(self)
         if seed is not None:
             self.set_seed(seed, 0)
+        self.fused_reduce = False
+        if ctx.world > 1 and self.compute == L.COMPUTE_BF16 and ctx.world <= 8 and \
+                os.environ.get("KUCD_FUSED_REDUCE", "1") != "0":
+            self._attach_peers()
+
+    def _attach_peers(self) -> None:
+        """Collective over the data-parallel group: exchange the CUDA IPC handles of the exchange buffers so that
+        the dW contraction can store its rows straight into their owners' memory (include/kucd.h, fused reduction)."""
+        import torch.distributed as dist
+
+        mine = (C.c_char * 128)()
+        L.check(self.ctx.lib.kucd_rbm_peer_export(self.handle, mine))
+        everyone = [None] * self.ctx.world
+        dist.all_gather_object(everyone, bytes(mine))
+        L.check(self.ctx.lib.kucd_rbm_peer_attach(self.handle, b"".join(everyone)))
+        self.fused_reduce = True
 
     def set_seed(self, seed: int, step_count: int = 0) -> None:
         L.check(self.ctx.lib.kucd_rbm_set_seed(self.handle, C.c_uint64(seed), C.c_uint64(step_count)))

@@ -56,8 +56,9 @@ def main():
             O.philox_fit(orc, data, B, 2, 1e-3, seed, k=k)
             d_solo = float(np.abs(Wd - Ws).max())
             d_orc = float(np.abs(Wd - orc.W).mean())
-            print("[dp_check] %s world=%d allreduce_calls=%d  max|W_dp - W_1gpu| = %.3e  mean|W_dp - W_oracle| = %.3e"
-                  % (name, world, t["allreduce_calls"], d_solo, d_orc), flush=True)
+            print("[dp_check] %s world=%d fused_reduce=%s (steps enqueued: fused %d, nccl all-reduce %d)  "
+                  "max|W_dp - W_1gpu| = %.3e  mean|W_dp - W_oracle| = %.3e"
+                  % (name, world, m.fused_reduce, t["fused_reduce_steps"], t["allreduce_calls"], d_solo, d_orc), flush=True)
             # identical samples => only the fp32 reduction order differs
             ok &= d_solo < 2e-6 and float(np.abs(bd - bs).max()) < 2e-6 and float(np.abs(cd - cs).max()) < 2e-6
             ok &= d_orc < 5e-6
