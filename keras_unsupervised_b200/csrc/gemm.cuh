@@ -101,12 +101,14 @@ struct alignas(64) GemmParams {
                        //             2 = MMA thread commits without multiplying (TMA pacing alone)
 };
 
-template <int BN>
+constexpr int kEpiStageBytes = kNumEpiWarps * 4096;  // one 32 x 32 fp32 transpose buffer per epilogue warp
+
+template <int BN, int EXTRA = 0>
 struct GemmCfg {
   static constexpr int kABytes = kBlockM * kBlockK * 2;
   static constexpr int kBBytes = BN * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kCtrlBytes = 1024;
+  static constexpr int kCtrlBytes = 1024 + EXTRA;
   static constexpr int kSmemLimit = 232448 - 1024;  // 227 KB minus alignment slack
   static constexpr int kStagesRaw = (kSmemLimit - kCtrlBytes) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
@@ -171,6 +173,14 @@ template <typename P>
 __device__ __forceinline__ float* raw_row_ptr(const P& p, int row) {
   return p.out_f32 + static_cast<int64_t>(row) * p.ld_f32;
 }
+template <typename P>
+__device__ __forceinline__ bool pushes_rows(const P&) {
+  return false;
+}
+template <>
+__device__ __forceinline__ bool pushes_rows<GemmParams>(const GemmParams& p) {
+  return p.push_rows > 0;
+}
 template <>
 __device__ __forceinline__ float* raw_row_ptr<GemmParams>(const GemmParams& p, int row) {
   if (p.push_rows > 0) {
@@ -184,11 +194,38 @@ __device__ __forceinline__ float* raw_row_ptr<GemmParams>(const GemmParams& p, i
 template <int EPI, typename P>
 __device__ __forceinline__ void epilogue_chunk(const P& p, const uint32_t (&acc)[32], int row, int col0,
                                                bool row_ok, uint64_t draw, int64_t row0, uint32_t lane,
-                                               float& row_acc) {
+                                               float& row_acc, float* stage = nullptr) {
   if (col0 >= p.N) return;  // warp-uniform
   const bool row_st = row < p.M;  // rows in [m_valid, M) are stored as zeros: they are K-rows of the dW contraction
 
   if constexpr (EPI == kEpiRaw) {
+    if (stage != nullptr && pushes_rows(p)) {
+      // Rows may live in another GPU's memory.  A thread owns one row, so a direct store instruction would touch
+      // 32 different rows with 16 bytes each - over NVLink that is 32 tiny writes.  Transpose the warp's 32 x 32
+      // block through shared memory (XOR-swizzled, conflict-free) and store 128 contiguous bytes per 8 lanes.
+      float4* st4 = reinterpret_cast<float4*>(stage);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        float4 v = make_float4(__uint_as_float(acc[4 * q]), __uint_as_float(acc[4 * q + 1]),
+                               __uint_as_float(acc[4 * q + 2]), __uint_as_float(acc[4 * q + 3]));
+        if (col0 + 4 * q + 1 >= p.N) v.y = 0.f;
+        if (col0 + 4 * q + 2 >= p.N) v.z = 0.f;
+        if (col0 + 4 * q + 3 >= p.N) v.w = 0.f;
+        st4[lane * 8 + (q ^ (lane & 7u))] = v;
+      }
+      __syncwarp();
+      const int row_base = row - static_cast<int>(lane);
+      const int c4 = static_cast<int>(lane & 7u);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = 4 * i + static_cast<int>(lane >> 3);
+        const float4 v = st4[r * 8 + (c4 ^ (r & 7))];
+        const int grow = row_base + r;
+        if (grow < p.M && col0 + 4 * c4 < p.N) *reinterpret_cast<float4*>(raw_row_ptr(p, grow) + col0 + 4 * c4) = v;
+      }
+      __syncwarp();
+      return;
+    }
     if (row_ok) {
       float* dst = raw_row_ptr(p, row) + col0;
 #pragma unroll
@@ -406,7 +443,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_bf16_kernel(const __grid_
   constexpr int kBNLocal = BN / CG;  // B columns staged by this CTA
   constexpr int kTileM = kBlockM * CG;
   constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
-  using Cfg = GemmCfg<kBNLocal>;
+  using Cfg = GemmCfg<kBNLocal, (EPI == kEpiRaw ? kEpiStageBytes : 0)>;
   constexpr int kStages = Cfg::kStages;
   const uint32_t cta_rank = CG == 2 ? ptx::cluster_ctarank() : 0u;
   const int unit = blockIdx.x / CG, num_units = gridDim.x / CG;  // a unit = one CTA, or one CTA pair
@@ -586,6 +623,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_bf16_kernel(const __grid_
     const uint32_t quarter = warp & 3u;  // TMEM lane quarter this warp may access
     const uint32_t half = ew >> 2;       // which half of the tile's columns
     constexpr int kColsPerWarp = BN / 2;
+    float* epi_stage = EPI == kEpiRaw ? reinterpret_cast<float*>(ctrl + 1024 + ew * 4096) : nullptr;
     uint32_t accn = 0;
     const int total = p.num_seg * p.kblocks;
     const int pieces = CH > 0 ? (total + (CH > 0 ? CH : 1) - 1) / (CH > 0 ? CH : 1) : 1;
@@ -608,7 +646,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_bf16_kernel(const __grid_
           uint32_t acc[32];
           ptx::tmem_ld_32x32(tmem_base + ((quarter * 32u) << 16) + as * BN + coff, acc);
           ptx::tmem_ld_wait();
-          epilogue_chunk<EPI>(p, acc, row, n_blk * BN + coff, row_ok, draw, row0, lane, row_acc);
+          epilogue_chunk<EPI>(p, acc, row, n_blk * BN + coff, row_ok, draw, row0, lane, row_acc, epi_stage);
         }
         ptx::tc_fence_before();
         __syncwarp();
@@ -640,7 +678,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_bf16_kernel(const __grid_
           uint32_t acc[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) acc[j] = __float_as_uint(sum[c + j]);
-          epilogue_chunk<EPI>(p, acc, row, n_blk * BN + half * kColsPerWarp + c, row_ok, draw, row0, lane, row_acc);
+          epilogue_chunk<EPI>(p, acc, row, n_blk * BN + half * kColsPerWarp + c, row_ok, draw, row0, lane, row_acc, epi_stage);
         }
       }
       if constexpr (EPI == kEpiFreeEnergy) {

@@ -88,7 +88,7 @@ constexpr int kPreciseCH = 4;    // k-blocks (of 64) per tensor-memory accumulat
 
 template <int BN, bool A_MN, bool B_MN, int EPI, int CH = 0, int CG = 1>
 inline cudaError_t launch_one(const GemmParams& p, int num_sms, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN / CG>;
+  using Cfg = GemmCfg<BN / CG, (EPI == kEpiRaw ? kEpiStageBytes : 0)>;
   auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, EPI, CH, CG>;
   static bool attr_set = false;
   if (!attr_set) {
