@@ -182,6 +182,8 @@ int kucd_rbm_get_counters(kucd_rbm* rbm, uint64_t* seed, uint64_t* step_count, i
  * a training call returns. */
 int kucd_rbm_peer_export(kucd_rbm* rbm, void* handle128);
 int kucd_rbm_peer_attach(kucd_rbm* rbm, const void* handles);
+/* back to the NCCL all-reduce (every rank must do the same: the exchange is collective) */
+int kucd_rbm_peer_detach(kucd_rbm* rbm);
 
 /* ---- inference ------------------------------------------------------------------------------------- */
 /* transform_func (rbm.py:45-48, 88-89) and RBM.call (rbm.py:80-83):  h = 1[u < sigmoid(v.W + c)]

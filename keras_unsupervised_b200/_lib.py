@@ -90,6 +90,7 @@ SIGNATURES = {
     "kucd_rbm_get_params": (C.c_int, [_P, _TP, _TP, _TP]),
     "kucd_rbm_peer_export": (C.c_int, [_P, _P]),
     "kucd_rbm_peer_attach": (C.c_int, [_P, _P]),
+    "kucd_rbm_peer_detach": (C.c_int, [_P]),
     "kucd_rbm_set_seed": (C.c_int, [_P, C.c_uint64, C.c_uint64]),
     "kucd_rbm_get_counters": (C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_int64)]),
     "kucd_rbm_transform": (C.c_int, [_P, _TP, _TP, _TP, _TP]),

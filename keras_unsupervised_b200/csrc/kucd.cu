@@ -1482,6 +1482,22 @@ int kucd_rbm_peer_attach(kucd_rbm* r, const void* handles) {
   return KUCD_OK;
 }
 
+int kucd_rbm_peer_detach(kucd_rbm* r) {
+  if (r == nullptr) return fail(KUCD_ERR_INVALID_ARG, "rbm is NULL");
+  CU_TRY(cudaSetDevice(r->ctx->device));
+  CU_TRY(cudaStreamSynchronize(r->ctx->stream));
+  for (int i = 0; i < r->n_peer_open; ++i) cudaIpcCloseMemHandle(r->peer_open[i]);
+  r->n_peer_open = 0;
+  r->peer_on = false;
+  if (r->graph_exec != nullptr) {
+    cudaGraphExecDestroy(r->graph_exec);
+    cudaGraphDestroy(r->graph);
+    r->graph_exec = nullptr;
+    r->graph = nullptr;
+  }
+  return KUCD_OK;
+}
+
 int kucd_rbm_get_counters(kucd_rbm* r, uint64_t* seed, uint64_t* step_count, int64_t* n_chains) {
   if (r == nullptr) return fail(KUCD_ERR_INVALID_ARG, "rbm is NULL");
   if (seed != nullptr) *seed = r->seed;

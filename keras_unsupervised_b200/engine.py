@@ -171,11 +171,18 @@ class Machine:
         import torch.distributed as dist
 
         mine = (C.c_char * 128)()
-        L.check(self.ctx.lib.kucd_rbm_peer_export(self.handle, mine))
+        ok = self.ctx.lib.kucd_rbm_peer_export(self.handle, mine) == L.KUCD_OK
         everyone = [None] * self.ctx.world
-        dist.all_gather_object(everyone, bytes(mine))
-        L.check(self.ctx.lib.kucd_rbm_peer_attach(self.handle, b"".join(everyone)))
-        self.fused_reduce = True
+        dist.all_gather_object(everyone, bytes(mine) if ok else b"")
+        ok = all(len(h) == 128 for h in everyone)
+        if ok:
+            ok = self.ctx.lib.kucd_rbm_peer_attach(self.handle, b"".join(everyone)) == L.KUCD_OK
+        verdicts = [None] * self.ctx.world
+        dist.all_gather_object(verdicts, bool(ok))
+        if all(verdicts):
+            self.fused_reduce = True
+        else:  # some rank could not map its peers (no P2P / IPC): everybody stays on the NCCL all-reduce
+            L.check(self.ctx.lib.kucd_rbm_peer_detach(self.handle))
 
     def set_seed(self, seed: int, step_count: int = 0) -> None:
         L.check(self.ctx.lib.kucd_rbm_set_seed(self.handle, C.c_uint64(seed), C.c_uint64(step_count)))
