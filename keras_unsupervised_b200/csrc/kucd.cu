@@ -216,9 +216,10 @@ struct GraphKey {
   int64_t batch = 0, global_row0 = 0, ds_rows = 0;
   kucd_hparams hp{};
   int ds_parts = 0;
+  bool fused = false;
   bool operator==(const GraphKey& o) const {
     return ds == o.ds && batch == o.batch && global_row0 == o.global_row0 && ds_rows == o.ds_rows &&
-           ds_parts == o.ds_parts && memcmp(&hp, &o.hp, sizeof hp) == 0;
+           ds_parts == o.ds_parts && fused == o.fused && memcmp(&hp, &o.hp, sizeof hp) == 0;
   }
 };
 
@@ -244,7 +245,8 @@ struct kucd_rbm {
   DevBuf dyn;
   DevBuf chain_done;  // (stage, row block) completion counters of the chain kernel
   // fused reduction over peer-mapped memory (data-parallel ranks on one NVLink domain)
-  bool peer_on = false;
+  bool peer_on = false;    // peer memory is mapped
+  bool fused_now = false;  // the current training call exchanges through it (decided per call, see choose_exchange)
   DevBuf arena;               // [n dW slots | n bias slots | flags | epoch]
   PeerSet ps{};
   void* peer_open[16] = {};   // pointers obtained from cudaIpcOpenMemHandle (to be closed)
@@ -622,7 +624,7 @@ static int delta_w(kucd_rbm* r, const Planes& v0, const Planes& h0, const Planes
   p.m_valid = static_cast<int32_t>(r->V);
   p.dyn = dyn;
   p.a_dyn_mask = dyn_mask;
-  if (r->peer_on) {  // each output row goes straight into its owner's slot for this rank
+  if (r->fused_now) {  // each output row goes straight into its owner's slot for this rank
     p.push_rows = static_cast<int32_t>(r->rows_per);
     for (int o = 0; o < ctx->world; ++o) p.push_base[o] = r->ps.dw_slot[o] + ctx->rank * r->slice_elems;
   }
@@ -690,7 +692,7 @@ static int apply_update(kucd_rbm* r, const kucd_hparams* hp, int64_t rows_global
     KU_TRY(r->mb.ensure(r->ldVb() * 4, true));
     KU_TRY(r->mc.ensure(r->ldHb() * 4, true));
   }
-  if (r->peer_on) {
+  if (r->fused_now) {
     // global [db | dc] = sum of the ranks' slots; the biases are updated identically on every rank
     const int n = ctx->world, me = ctx->rank;
     reduce_bias_kernel<<<(r->bias_len + 255) / 256, 256, 0, ctx->stream>>>(r->ps.bias_slot[me], n, r->bias_len, r->db());
@@ -727,7 +729,7 @@ static int apply_update(kucd_rbm* r, const kucd_hparams* hp, int64_t rows_global
                                                                      scale, hp->momentum);
     ctx->tm.aux_launches++;
   }
-  if (r->peer_on) {
+  if (r->fused_now) {
     // every rank's rows of the new bf16 W must have landed in this rank's operand plane before the next chain
     peer_barrier_kernel<<<1, 32, 0, ctx->stream>>>(r->epoch, r->ps, ctx->rank, ctx->world);
     ctx->tm.aux_launches++;
@@ -736,10 +738,23 @@ static int apply_update(kucd_rbm* r, const kucd_hparams* hp, int64_t rows_global
   return KUCD_OK;
 }
 
+// Fused exchange or NCCL all-reduce for this training call?  The dW contraction can hide its NVLink stores only if
+// it runs longer than they take: time_gemm = 4 B V H / ~1.2e15 s against 4 V H (n-1)/n / ~6e11 s of stores, i.e. a
+// per-rank minibatch of ~2000 rows.  Measured: C3 (4096 rows per rank) 2.59 ms fused vs 2.76 ms NCCL at 8 ranks; C4
+// (1024 rows per rank, 512 MiB of dW) 3.13 ms fused vs 2.95 ms NCCL.  Fixed for the whole call: the two paths keep the
+// fp32 master differently between steps.  KUCD_FUSED_MIN_ROWS overrides the threshold.
+static void choose_exchange(kucd_rbm* r, int64_t rows_per_rank) {
+  static const int64_t min_rows = [] {
+    const char* e = getenv("KUCD_FUSED_MIN_ROWS");
+    return e != nullptr ? static_cast<int64_t>(atoll(e)) : static_cast<int64_t>(2048);
+  }();
+  r->fused_now = r->peer_on && rows_per_rank >= min_rows;
+}
+
 // fp32 master rows updated by their owners -> every rank (NCCL broadcasts, at API boundaries only)
 static int gather_master(kucd_rbm* r) {
   kucd_ctx* ctx = r->ctx;
-  if (!r->peer_on) return KUCD_OK;
+  if (!r->fused_now) return KUCD_OK;
   int rc = g_nccl.GroupStart();
   for (int o = 0; o < ctx->world && rc == 0; ++o) {
     const int64_t r0 = o * r->rows_per;
@@ -1030,7 +1045,7 @@ static int enqueue_cd(kucd_rbm* r, const Planes& v0, int64_t batch, const kucd_h
   // KUCD_CHAIN_DW=1 appends the dW contraction to the chain kernel as a final two-segment stage.  Measured: no gain
   // at C3 (2.529 vs 2.522 ms per step) and a loss at C4 (577 k vs 605 k samples/s) - its second segment has to wait
   // for every row block of the last projection, so it hides little - which is why it is off by default.
-  const bool chain_dw = ctx->chain_dw && !r->peer_on;
+  const bool chain_dw = ctx->chain_dw && !r->fused_now;
   if (whole_chain) {
     KU_TRY(launch_chain(r, v0, batch, hp, global_row0, draw0, stride, dyn, v0_dyn, chain_dw));
   } else if (!two) {
@@ -1063,7 +1078,7 @@ static int enqueue_cd(kucd_rbm* r, const Planes& v0, int64_t batch, const kucd_h
     }
     CU_TRY(cudaGetLastError());
   }
-  if (r->peer_on) {
+  if (r->fused_now) {
     // The dW contraction has already stored every row into its owner's slot (reduce-scatter fused into the
     // epilogue, NVLink stores overlapped with the MMAs).  Ship the small bias statistics the same way, then meet:
     // after the barrier every slot of this rank holds this step's contributions of all ranks.
@@ -1665,6 +1680,7 @@ int kucd_rbm_cd_step(kucd_rbm* r, const kucd_tensor* v_batch, const kucd_hparams
   if (rows > (1 << 22)) return fail(KUCD_ERR_INVALID_ARG, "minibatch of %lld rows", (long long)rows);
   KU_TRY(ensure_workspace(r, rows));
   if (hp->persistent) KU_TRY(ensure_chains(r, rows));
+  choose_exchange(r, rows);
   Planes v0;
   KU_TRY(ingest_batch(r, v_batch, 0, rows, &v0));
 
@@ -1905,6 +1921,7 @@ static int fit_range_impl(kucd_rbm* r, kucd_dataset* ds, int64_t batch, const ku
                 (long long)epoch_steps);
   const int64_t steps = step_end - step_begin;
   if (steps == 0) return KUCD_OK;
+  choose_exchange(r, batch);
   KU_TRY(ensure_workspace(r, batch));
   if (hp->persistent) KU_TRY(ensure_chains(r, std::min(batch, N)));
   if (hp->momentum != 0.f) {  // allocate outside the capture
@@ -1923,6 +1940,7 @@ static int fit_range_impl(kucd_rbm* r, kucd_dataset* ds, int64_t batch, const ku
   key.ds_parts = ds->nparts;
   key.hp = *hp;
   key.hp.want_stats = 0;
+  key.fused = r->fused_now;
   const Planes v0 = ds->view();
   StepDyn* dyn = r->dyn.as<StepDyn>();
   if (r->graph_exec == nullptr || !(r->graph_key == key)) {
@@ -2012,6 +2030,7 @@ int kucd_rbm_fit_host(kucd_rbm* r, const kucd_tensor* V_all, int64_t batch, cons
   if (steps == 0) return KUCD_OK;
   KU_TRY(ensure_workspace(r, batch));
   if (hp->persistent) KU_TRY(ensure_chains(r, std::min(batch, N)));
+  choose_exchange(r, batch);
   const int es = elem_size(V_all);
   const int64_t cols = r->V;
   const bool x3 = r->compute == KUCD_COMPUTE_F32X3;

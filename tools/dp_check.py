@@ -15,6 +15,7 @@ import torch.distributed as dist
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+os.environ.setdefault("KUCD_FUSED_MIN_ROWS", "1")  # exercise the fused exchange at these small minibatches too
 
 from keras_unsupervised_b200 import _lib as L  # noqa: E402
 from keras_unsupervised_b200.engine import Context, Dataset, Machine  # noqa: E402
@@ -63,6 +64,8 @@ def main():
             ok &= d_solo < 2e-6 and float(np.abs(bd - bs).max()) < 2e-6 and float(np.abs(cd - cs).max()) < 2e-6
             ok &= d_orc < 5e-6
             ok &= t["graph_launches"] == 12
+            if name == "bf16" and world <= 8 and os.environ.get("KUCD_FUSED_REDUCE", "1") != "0":
+                ok &= m.fused_reduce and t["fused_reduce_steps"] > 0 and t["allreduce_calls"] == 0
         dist.barrier()
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, src=0)
