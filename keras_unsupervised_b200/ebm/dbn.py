@@ -33,6 +33,8 @@ class DBN(object):
             self._rbm_layers.append(rbm_layer)
         else:
             self._rbm_layers = [rbm_layer]
+        if hasattr(rbm_layer, "_set_stack_index"):
+            rbm_layer._set_stack_index(len(self._rbm_layers) - 1)
 
     def _check(self):
         if hasattr(self, "_rbm_layers") != True:  # noqa: E712  (dbn.py:47-48)

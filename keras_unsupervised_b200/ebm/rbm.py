@@ -77,7 +77,7 @@ class RBM(object):
             compute = L.COMPUTE_BF16
         else:
             raise ValueError("hps['dtype'] must be 'float32' or 'bf16'")
-        seed = int(self.hps.get("seed", 42))
+        seed = self.seed
         self._machine = Machine(ctx, n_visible, int(self.output_dim), int(self.mode), compute, seed=seed)
         rng = np.random.default_rng(seed)
         W = rng.uniform(-0.05, 0.05, (n_visible, int(self.output_dim))).astype(np.float32)
@@ -87,6 +87,17 @@ class RBM(object):
         self.input_shape = (None, n_visible)
         self.output_shape = (None, int(self.output_dim))
         self.built = True
+
+    @property
+    def seed(self):
+        """Philox key / initialiser seed: hps['seed'] (42), offset per position in a DBN stack so that stacked
+        layers do not share a random stream."""
+        return int(self.hps.get("seed", 42)) + 1000003 * int(getattr(self, "_stack_index", 0))
+
+    def _set_stack_index(self, i):
+        self._stack_index = int(i)
+        if self.built:
+            self._machine.set_seed(self.seed, self._machine.counters()["step_count"])
 
     def _ensure_built(self, x):
         if not self.built:

@@ -322,6 +322,25 @@ def philox_fit(rbm: OracleRBM, V, batch_size, epochs, lr, seed, k=1, persistent=
     return step
 
 
+def philox_fit_reference(rbm: OracleRBM, V, batch_size, epochs, lr, seed, step0=0, score0=0):
+    """The engine's compat='reference' loop with its own Philox draws: per minibatch three single-parameter CD-1 runs
+    (training draw ids of three consecutive steps), then the score chain (score draw ids).  Returns the scores."""
+    step, nscore, scores = step0, score0, []
+    for _ in range(epochs):
+        for lo, hi in batches(V.shape[0], batch_size):
+            rows = hi - lo
+            v = V[lo:hi]
+            for mask in (1, 2, 4):
+                u_h = [philox_uniform(seed, draw_id("train", step, 0), 0, rows, rbm.H)]
+                u_v = [None, philox_uniform(seed, draw_id("train", step, 2), 0, rows, rbm.V)]
+                rbm.apply(rbm.cd_stats(v, u_h, u_v), lr, mask)
+                step += 1
+            scores.append(rbm.score(v, philox_uniform(seed, draw_id("score", nscore, 0), 0, rows, rbm.H),
+                                    philox_uniform(seed, draw_id("score", nscore, 1), 0, rows, rbm.V)))
+            nscore += 1
+    return scores
+
+
 def condition_margin(rbm: OracleRBM, v, u_h, u_v, k=1, margin=1e-4, rng=None, persistent=False, u_hc=None):
     """Re-draw every injected uniform that falls within `margin` of the probability it is compared with
     (walking the chain in order), so that an implementation whose probabilities differ from the oracle's

@@ -160,3 +160,55 @@ def test_gaussian_visible_rbm_runs_the_default_mode(ctx):
     assert abs(float((v - orc.pre_v(hh)).std()) - 1.0) < 0.02
     rbm.fit(X, verbose=0)
     assert np.isfinite(rbm.rbm_weight).all() and not np.array_equal(rbm.rbm_weight, W)
+
+
+def test_reference_schedule_fit_matches_oracle_replay(ctx):
+    """compat='reference' through RBM.fit: W, then c, then b with fresh draws each (rbm.py:214-216) and the printed
+    score (rbm.py:227-234), replayed by the oracle with the engine's Philox stream."""
+    from keras_unsupervised_b200.ebm import RBM, MODE_VISIBLE_BERNOULLI
+
+    rng = np.random.default_rng(31)
+    V = (rng.random((300, 200)) < 0.2).astype(np.float32)
+    hps = {"batch_size": 128, "epochs": 2, "lr": 1e-3, "compat": "reference", "seed": 77}
+    rbm = RBM(hps, 96, name="r", mode=MODE_VISIBLE_BERNOULLI, context=ctx)
+    rbm.build((None, 200))
+    W, b, c = rbm._machine.get_params()
+    orc = O.OracleRBM(W, b, c)
+    rbm.fit(V, verbose=0)
+    scores = O.philox_fit_reference(orc, V, 128, 2, 1e-3, 77)
+    got = [h["last_score"] for h in rbm.history]
+    assert len(got) == 6
+    np.testing.assert_allclose(got, scores, rtol=2e-3)          # a flipped sample moves a score slightly
+    assert np.abs(rbm.rbm_weight - orc.W).mean() < 2e-6 and np.abs(rbm.rbm_weight - orc.W).max() < 5e-3
+    assert np.abs(rbm.hidden_bias - orc.c).max() < 5e-3 and np.abs(rbm.visible_bias - orc.b).max() < 5e-3
+
+
+def test_dbn_fit_matches_oracle_replay(ctx):
+    """DBN.fit (dbn.py:51-55): layer l+1 trains on the sampled hidden states of layer l over the whole data set.
+    Replayed by the oracle layer by layer with each layer's own Philox stream (stack position offsets the seed)."""
+    from keras_unsupervised_b200.ebm import DBN, RBM, MODE_VISIBLE_BERNOULLI
+
+    rng = np.random.default_rng(37)
+    X = (rng.random((512, 160)) < 0.3).astype(np.float32)
+    dims = [160, 96, 64]
+    hps = {"batch_size": 128, "epochs": 1, "lr": 1e-3, "seed": 5}
+    dbn = DBN()
+    layers = [RBM(dict(hps), d, name="l%d" % i, mode=MODE_VISIBLE_BERNOULLI, context=ctx) for i, d in enumerate(dims[1:])]
+    for l in layers:
+        dbn.add_stack(l)
+    assert [l.seed for l in layers] == [5, 5 + 1000003]
+    for l, d in zip(layers, dims[:-1]):
+        l.build((None, d))
+    init = [l._machine.get_params() for l in layers]
+    dbn.fit(X, verbose=0)
+    cur = X
+    for l, (W, b, c) in zip(layers, init):
+        orc = O.OracleRBM(W, b, c)
+        O.philox_fit(orc, cur, 128, 1, 1e-3, l.seed)
+        assert np.abs(l.rbm_weight - orc.W).mean() < 2e-6, l.name
+        # dbn.py:55: the next layer sees this layer's sampled states of the whole data set (first inference draw)
+        cur, _ = orc.sample_h(cur, O.philox_uniform(l.seed, O.draw_id("infer", 0), 0, cur.shape[0], orc.H))
+    H = dbn.transform(X)
+    assert H.shape == (512, 64)
+    Vb = dbn.inv_transform(H)
+    assert Vb.shape == (512, 160) and set(np.unique(Vb)) <= {0.0, 1.0}
