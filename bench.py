@@ -466,16 +466,16 @@ def _main(out):
             chain = tp["chain_launches"] > 0
             if chain:
                 # all projections of a minibatch are ONE launch of chain_kernel: that launch is the unit
-                launches = tp["chain_launches"]
+                n_timed = tp["chain_launches"]
                 with_dw = tp["chain_dw_launches"] > 0
                 flop = (n_proj + (2 if with_dw else 0)) * 2.0 * B * V * H
                 kernel = "chain_kernel (the %d projections of a CD-%d minibatch%s, fused epilogues, one persistent launch)" % (
                     n_proj, k, " + the two outer products of dW" if with_dw else "")
             else:
-                launches = tp["proj_timed"]  # with the two-chain schedule each projection is two row-half launches
-                flop = n_prof * n_proj * 2.0 * B * V * H / launches
+                n_timed = tp["proj_timed"]  # with the two-chain schedule each projection is two row-half launches
+                flop = n_prof * n_proj * 2.0 * B * V * H / n_timed
                 kernel = "gemm_bf16_kernel<sample epilogue> (v.W+c / h.W^T+b projection)"
-            per_launch_ms = tp["proj_ms"] / launches
+            per_launch_ms = tp["proj_ms"] / n_timed
             ach = flop / (per_launch_ms * 1e-3) / 1e12
             traffic = None
             tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
@@ -486,7 +486,7 @@ def _main(out):
             roof = {"bound": "tensor", "kernel": kernel, "achieved": ach, "peak": pk["sustained"], "unit": "TFLOP/s",
                     "frac": ach / pk["sustained"],
                     "peak_source": pk["source"] + ", sustained figure (kernel timed inside a long step)",
-                    "traffic": traffic, "launch_ms": per_launch_ms, "launches_timed": launches,
+                    "traffic": traffic, "launch_ms": per_launch_ms, "launches_timed": n_timed,
                     "projections_per_launch": n_proj if chain else None, "flop_per_launch": flop,
                     "dw_launch_ms": (tp["dw_ms"] / tp["dw_timed"]) if tp["dw_timed"] else None,
                     "step_tflops": step_tf, "step_frac_of_sustained": step_tf / pk["sustained"]}

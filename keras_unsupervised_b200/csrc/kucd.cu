@@ -894,9 +894,8 @@ static int launch_chain(kucd_rbm* r, const Planes& v0, int64_t batch, const kucd
     CU_TRY(cudaFuncSetAttribute(chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
-  const int units = std::min(total, ctx->num_sms / 2);
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(units * 2);
+  cfg.gridDim = dim3(ctx->num_sms / 2 * 2);
   cfg.blockDim = dim3(kNumThreads);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = ctx->stream;
@@ -907,6 +906,19 @@ static int launch_chain(kucd_rbm* r, const Planes& v0, int64_t batch, const kucd
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  // The pairs wait on each other's tiles, so every pair of the grid must be resident at once: never launch more
+  // clusters than the device can hold of this kernel.
+  static int max_clusters = -1;
+  if (max_clusters < 0) {
+    int mc = 0;
+    if (cudaOccupancyMaxActiveClusters(&mc, chain_kernel, &cfg) != cudaSuccess || mc <= 0) {
+      cudaGetLastError();
+      mc = ctx->num_sms / 2;
+    }
+    max_clusters = mc;
+  }
+  const int units = std::min(total, std::min(max_clusters, ctx->num_sms / 2));
+  cfg.gridDim = dim3(units * 2);
   const bool prof = ctx->profile && dyn == nullptr;
   const size_t pe0 = prof ? prof_event(ctx) : 0;
   CU_TRY(cudaLaunchKernelEx(&cfg, chain_kernel, p));
