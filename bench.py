@@ -444,6 +444,22 @@ def _main(out):
                "last_recon_err": float(st["step_recon_err"][-1])}
         windows.append((tw0, tw1))
         del host
+        # the same pass with the binarised data handed over as uint8 (a quarter of the bytes): informational
+        host8 = torch.empty((n_e2e * B, V), dtype=torch.uint8).pin_memory()
+        for i in range(n_e2e):
+            host8[i * B:(i + 1) * B].copy_(X[(i % n_batches) * B:((i % n_batches) + 1) * B])
+        m.fit_host(host8[:2 * B], B, hp_e, global_row0=row0)
+        barrier()
+        t0 = time.perf_counter()
+        m.fit_host(host8, B, hp_e, global_row0=row0)
+        dt8 = time.perf_counter() - t0
+        if dist is not None:
+            t = torch.tensor([dt8], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt8 = float(t.item())
+        e2e["uint8_input"] = {"value": world * n_e2e * B / dt8, "unit": UNIT, "h2d_bytes_per_step": B * V,
+                              "ms_per_step": 1e3 * dt8 / n_e2e}
+        del host8
 
     # ---- roofline of the dominant kernel: per-launch CUDA events on the engine stream -------------
     roof = None

@@ -107,6 +107,22 @@ __global__ void export_f32_kernel(const float* __restrict__ src, int64_t ld, int
   }
 }
 
+// Small work folded into the weight-update launch (done by its last block) so that a latency-bound step is one
+// launch shorter per item: the two bias updates (rbm.py:129-134) and the step-state advance of graph replay.
+struct UpdateTail {
+  float* b;
+  const float* db;
+  float* mb;
+  int32_t nb;  // visible bias entries (0: skip)
+  float* c;
+  const float* dc;
+  float* mc;
+  int32_t nc;  // hidden bias entries (0: skip)
+  StepDyn* dyn;  // advance to the next minibatch (nullptr: skip)
+  int32_t adv_batch;
+  int64_t adv_total;
+};
+
 // The parameter update of rbm.py:127-134 for the weight matrix, generalised with momentum and weight
 // decay (both 0 in the reference):
 //     g = scale * dW - weight_decay * W ;  m = momentum * m + lr * g ;  W += m
@@ -115,7 +131,33 @@ __global__ void export_f32_kernel(const float* __restrict__ src, int64_t ld, int
 __global__ void update_w_kernel(float* __restrict__ W, const float* __restrict__ dW, float* __restrict__ mom,
                                 __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ mid,
                                 __nv_bfloat16* __restrict__ lo, int64_t n4, float lr, float scale, float momentum,
-                                float weight_decay) {
+                                float weight_decay, UpdateTail tail) {
+  if (blockIdx.x == gridDim.x - 1) {
+    for (int i = threadIdx.x; i < tail.nb; i += blockDim.x) {
+      float s = lr * scale * tail.db[i];
+      if (tail.mb != nullptr) {
+        s = momentum * tail.mb[i] + s;
+        tail.mb[i] = s;
+      }
+      tail.b[i] += s;
+    }
+    for (int i = threadIdx.x; i < tail.nc; i += blockDim.x) {
+      float s = lr * scale * tail.dc[i];
+      if (tail.mc != nullptr) {
+        s = momentum * tail.mc[i] + s;
+        tail.mc[i] = s;
+      }
+      tail.c[i] += s;
+    }
+    if (threadIdx.x == 0 && tail.dyn != nullptr) {
+      // next minibatch: sequential slices, remainder last (rbm.py:163,211,218)
+      const int64_t off = tail.dyn->row_off + tail.adv_batch;
+      const int64_t left = tail.adv_total - off;
+      tail.dyn->row_off = off;
+      tail.dyn->rows_valid = static_cast<int32_t>(left < 0 ? 0 : (left < tail.adv_batch ? left : tail.adv_batch));
+      tail.dyn->step += 1;
+    }
+  }
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n4;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     float4 w = reinterpret_cast<const float4*>(W)[i];
@@ -213,6 +255,66 @@ __global__ void colsum_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_b
   if (r1 > r0) {
     atomicAdd(out + c, sign * s0);
     if (c + 1 < cols) atomicAdd(out + c + 1, sign * s1);
+  }
+}
+
+// Small minibatches: each block owns 32 column pairs, its 16 warps stride over the rows and combine through shared
+// memory, so the column sums are STORED (no memset, no atomics); the same launch clears `zero` (the dc accumulator
+// the epilogues add into).  blockDim = (32, 16).
+__global__ void colsum_store_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ mid,
+                                    const __nv_bfloat16* __restrict__ lo, int64_t ld, int32_t rows, int32_t cols,
+                                    int32_t cols_pad, const StepDyn* dyn, float* __restrict__ out,
+                                    float* __restrict__ zero, int32_t zero_len) {
+  __shared__ float2 part[16][32];
+  int64_t row_off = 0;
+  if (dyn != nullptr) {
+    row_off = dyn->row_off;
+    rows = dyn->rows_valid < rows ? dyn->rows_valid : rows;
+  }
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  for (int i = blockIdx.x * 512 + tid; i < zero_len; i += gridDim.x * 512) zero[i] = 0.f;
+  const int c = 2 * (blockIdx.x * 32 + threadIdx.x);
+  float s0 = 0.f, s1 = 0.f;
+  if (c < cols) {
+    // eight independent loads in flight per thread: the rows of a minibatch are far apart in HBM
+    for (int r = threadIdx.y; r < rows; r += 128) {
+      __nv_bfloat162 h[8], m[8], l[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int rr = r + 16 * u;
+        const int64_t off = (row_off + (rr < rows ? rr : r)) * ld + c;
+        h[u] = *reinterpret_cast<const __nv_bfloat162*>(hi + off);
+        if (mid != nullptr) {
+          m[u] = *reinterpret_cast<const __nv_bfloat162*>(mid + off);
+          l[u] = *reinterpret_cast<const __nv_bfloat162*>(lo + off);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if (r + 16 * u < rows) {
+          float2 v = __bfloat1622float2(h[u]);
+          if (mid != nullptr) {
+            const float2 a = __bfloat1622float2(m[u]), b = __bfloat1622float2(l[u]);
+            v.x += a.x + b.x;
+            v.y += a.y + b.y;
+          }
+          s0 += v.x;
+          s1 += v.y;
+        }
+      }
+    }
+  }
+  part[threadIdx.y][threadIdx.x] = make_float2(s0, s1);
+  __syncthreads();
+  if (threadIdx.y == 0 && c < cols_pad) {
+    float2 t = part[0][threadIdx.x];
+#pragma unroll
+    for (int k = 1; k < 16; ++k) {
+      t.x += part[k][threadIdx.x].x;
+      t.y += part[k][threadIdx.x].y;
+    }
+    out[c] = t.x;
+    out[c + 1] = (c + 1 < cols) ? t.y : 0.f;
   }
 }
 

@@ -683,8 +683,12 @@ struct StepInject {
   int64_t ld_hc = 0;
 };
 
-static int apply_update(kucd_rbm* r, const kucd_hparams* hp, int64_t rows_global) {
+// `adv`: when the caller replays this step as a graph, the step-state advance rides on the update launch
+// (returns *adv_done = true) instead of being a launch of its own.
+static int apply_update(kucd_rbm* r, const kucd_hparams* hp, int64_t rows_global, StepDyn* adv = nullptr,
+                        int32_t adv_batch = 0, int64_t adv_total = 0, bool* adv_done = nullptr) {
   kucd_ctx* ctx = r->ctx;
+  if (adv_done != nullptr) *adv_done = false;
   const float scale = hp->normalize ? 1.0f / static_cast<float>(std::max<int64_t>(rows_global, 1)) : 1.0f;
   const bool use_mom = hp->momentum != 0.f;
   if (use_mom) {
@@ -708,15 +712,36 @@ static int apply_update(kucd_rbm* r, const kucd_hparams* hp, int64_t rows_global
         ctx->tm.aux_launches++;
       }
     }
-  } else if (hp->update_mask & KUCD_UPDATE_W) {
-    const int64_t n4 = r->V * r->ldH / 4;
-    update_w_kernel<<<grid_for(ctx, n4, 256), 256, 0, ctx->stream>>>(
+  } else {
+    // one launch: W (if selected), both biases (if selected) and, under graph replay, the step-state advance
+    const int64_t n4 = (hp->update_mask & KUCD_UPDATE_W) ? r->V * r->ldH / 4 : 0;
+    UpdateTail tail{};
+    if (hp->update_mask & KUCD_UPDATE_B) {
+      tail.b = r->b32.as<float>();
+      tail.db = r->db();
+      tail.mb = use_mom ? r->mb.as<float>() : nullptr;
+      tail.nb = static_cast<int32_t>(r->V);
+    }
+    if (hp->update_mask & KUCD_UPDATE_C) {
+      tail.c = r->c32.as<float>();
+      tail.dc = r->dc();
+      tail.mc = use_mom ? r->mc.as<float>() : nullptr;
+      tail.nc = static_cast<int32_t>(r->H);
+    }
+    tail.dyn = adv;
+    tail.adv_batch = adv_batch;
+    tail.adv_total = adv_total;
+    update_w_kernel<<<grid_for(ctx, std::max<int64_t>(n4, 1), 256), 256, 0, ctx->stream>>>(
         r->W32.as<float>(), r->dW(), use_mom ? r->mW.as<float>() : nullptr, r->Wp.buf[0].as<__nv_bfloat16>(),
         r->wparts == 3 ? r->Wp.buf[1].as<__nv_bfloat16>() : nullptr,
-        r->wparts == 3 ? r->Wp.buf[2].as<__nv_bfloat16>() : nullptr, n4, hp->lr, scale, hp->momentum,
-        hp->weight_decay);
+        r->wparts == 3 ? r->Wp.buf[2].as<__nv_bfloat16>() : nullptr, n4, hp->lr, scale, hp->momentum, hp->weight_decay,
+        tail);
     ctx->tm.aux_launches++;
+    if (adv_done != nullptr) *adv_done = adv != nullptr;
+    CU_TRY(cudaGetLastError());
+    return KUCD_OK;
   }
+  // fused exchange: the biases are updated redundantly on every rank from the reduced statistics
   if (hp->update_mask & KUCD_UPDATE_C) {
     update_bias_kernel<<<(r->H + 255) / 256, 256, 0, ctx->stream>>>(r->c32.as<float>(), r->dc(),
                                                                      use_mom ? r->mc.as<float>() : nullptr, r->H, hp->lr,
@@ -940,8 +965,24 @@ static int enqueue_cd(kucd_rbm* r, const Planes& v0, int64_t batch, const kucd_h
   const uint64_t draw0 = step * 64;
   const uint64_t stride = dyn != nullptr ? 64 : 0;
 
-  CU_TRY(cudaMemsetAsync(r->db(), 0, (r->ldVb() + r->ldHb()) * 4, ctx->stream));
-  {  // db += sum_rows v0   (rbm.py:134)
+  static const bool merge_small = [] {
+    const char* e = getenv("KUCD_MERGE");
+    return !(e != nullptr && e[0] == '0');
+  }();
+  if (batch <= 128 && merge_small) {
+    // smallest minibatches: one launch stores db = sum_rows v0 (rbm.py:134) and clears dc.  Measured (same call,
+    // KUCD_MERGE=1/0): 43.1 vs 51.2 us per step at C1 (batch 128) but 286 vs 171 us per 3-layer step at C2 (batch
+    // 256), hence the threshold.
+    const int32_t cols_pad = static_cast<int32_t>(round_up(r->V, 2));
+    const int blocks = std::max<int>(1, (cols_pad / 2 + 31) / 32);
+    colsum_store_kernel<<<blocks, dim3(32, 16), 0, ctx->stream>>>(v0.p[0], v0.mid(), v0.lo(), v0.ld, static_cast<int32_t>(batch),
+                                                           static_cast<int32_t>(r->V), cols_pad, v0_dyn ? dyn : nullptr,
+                                                           r->db(), r->dc(), static_cast<int32_t>(r->ldHb()));
+    ctx->tm.aux_launches++;
+    CU_TRY(cudaGetLastError());
+  } else {
+    CU_TRY(cudaMemsetAsync(r->db(), 0, (r->ldVb() + r->ldHb()) * 4, ctx->stream));
+    // db += sum_rows v0   (rbm.py:134)
     dim3 grid(static_cast<unsigned>((r->V / 2 + 1 + 127) / 128), static_cast<unsigned>((batch + 63) / 64));
     colsum_kernel<<<grid, 128, 0, ctx->stream>>>(v0.p[0], v0.mid(), v0.lo(), v0.ld, 0, static_cast<int32_t>(batch),
                                                  static_cast<int32_t>(r->V), v0_dyn ? dyn : nullptr, 1.f, r->db());
@@ -1966,8 +2007,9 @@ static int fit_range_impl(kucd_rbm* r, kucd_dataset* ds, int64_t batch, const ku
     const int64_t k0 = ctx->tm.gemm_launches + ctx->tm.aux_launches;
     CU_TRY(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed));
     int rc = enqueue_cd(r, v0, batch, hp, nullptr, global_row0, 0, dyn, true);
-    if (rc == KUCD_OK) rc = apply_update(r, hp, batch * ctx->world);
-    if (rc == KUCD_OK) {
+    bool advanced = false;
+    if (rc == KUCD_OK) rc = apply_update(r, hp, batch * ctx->world, dyn, static_cast<int32_t>(batch), N, &advanced);
+    if (rc == KUCD_OK && !advanced) {
       advance_dyn_kernel<<<1, 1, 0, ctx->stream>>>(dyn, static_cast<int32_t>(batch), N);
       ctx->tm.aux_launches++;
     }
