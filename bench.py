@@ -33,6 +33,8 @@ WORKLOADS = {
     # name: (V, H, batch per GPU, k, dtype, bernoulli prob of a 1)
     "c3": dict(V=4096, H=4096, B=4096, k=10, dtype="bf16", q=0.5,
                desc="Bernoulli RBM 4096->4096, CD-10, batch 4096 per GPU, bf16 (BASELINE.json configs[2])"),
+    "c3f32": dict(V=4096, H=4096, B=4096, k=10, dtype="f32", q=0.5,
+                  desc="Bernoulli RBM 4096->4096, CD-10, batch 4096 per GPU, float32-grade contractions (three bf16 terms)"),
     "c1": dict(V=784, H=500, B=128, k=1, dtype="bf16", q=0.1307,
                desc="Bernoulli RBM 784->500, CD-1, batch 128 (BASELINE.json configs[0])"),
     "c1f32": dict(V=784, H=500, B=128, k=1, dtype="f32", q=0.1307,
