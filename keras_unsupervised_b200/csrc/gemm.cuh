@@ -17,12 +17,13 @@
 // instruction descriptor) and, in f32x3 mode, the bf16 hi/mid/lo splits of
 // fp32 operands.
 //
-// Structure (one CTA per SM, persistent over output tiles):
+// Structure (one CTA per SM - or one CTA pair per TPC with CG = 2 - persistent over output tiles):
 //   warp 0      TMA producer   global -> 128B-swizzled smem ring (STAGES deep)
-//   warp 1      MMA issuer     one thread, tcgen05.mma cta_group::1, M=128, N=BN
+//   warp 1      MMA issuer     one thread, tcgen05.mma cta_group::1 (M=128) or ::2 (M=256 over the pair), N=BN
 //   warps 2..9  epilogue       tcgen05.ld TMEM -> registers -> fused math -> global
 // The fp32 accumulator is double-buffered in TMEM (2 x BN columns) so the
-// epilogue of tile i overlaps the MMAs of tile i+1.
+// epilogue of tile i overlaps the MMAs of tile i+1.  chain.cuh runs the same pipeline over the
+// flattened tile sequence of a whole Gibbs chain.
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>

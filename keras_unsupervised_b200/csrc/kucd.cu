@@ -3,16 +3,20 @@
 // What the reference does with eight K.function graph executions per minibatch
 // (/root/reference/ku/ebm/rbm.py:214-231) is here a fixed sequence of launches on one stream:
 //
-//   colsum(v0)                                    -> db            (rbm.py:134, positive half)
-//   h0 = 1[u < sigmoid(v0.W + c)]      tcgen05    -> dc += sum h0  (rbm.py:120 = :46-47)
+//   column sums of v0                              -> db            (rbm.py:134, positive half)
+//   h0 = 1[u < sigmoid(v0.W + c)]       tcgen05    -> dc += sum h0  (rbm.py:120 = :46-47)
 //   k x { v = 1[u < sigmoid(h.W^T + b)] ; h = sample or, last, sigmoid(v.W + c) }   (rbm.py:121-124)
-//   dW = v0^T h0 - vk^T hk             tcgen05, both phases in one TMEM accumulator (rbm.py:125-126)
-//   [ncclAllReduce(dW | db | dc)]                  data-parallel ranks
-//   W += lr dW ; b += lr db ; c += lr dc           fused update + bf16 plane refresh (rbm.py:127-134)
+//        - for bf16 Bernoulli training all 2k+1 projections are ONE persistent launch (chain.cuh);
+//          otherwise one launch per projection, as two row-half chains on two streams when large
+//   dW = v0^T h0 - vk^T hk              tcgen05, both phases in one TMEM accumulator (rbm.py:125-126)
+//   exchange between data-parallel ranks: dW rows stored straight into their owner's memory by the
+//        contraction's epilogue (peer-mapped, NVLink) + flag barriers, or ncclAllReduce(dW | db | dc)
+//   W += lr dW ; b += lr db ; c += lr dc           one fused launch, bf16 operand planes refreshed (rbm.py:127-134)
 //
 // Parameters, operand planes, chains and workspaces stay in HBM between calls; under fit_epoch the
 // sequence is captured once as a CUDA graph and replayed per minibatch, with the minibatch offset,
-// the remainder-row count and the Philox draw counter living in device memory (StepDyn).
+// the remainder-row count and the Philox draw counter living in device memory (StepDyn); fit_host
+// streams a host array through a double-buffered staging area, copies overlapped with the chains.
 #include "../../include/kucd.h"
 
 #include <cuda.h>

@@ -139,3 +139,17 @@ def test_dbn_oracle_stack():
     assert h.shape == (8, 5)
     v = dbn.inv_transform(h, [O.lattice_uniform(rng, (8, 12)), O.lattice_uniform(rng, (8, 20))])
     assert v.shape == (8, 20)
+
+
+def test_philox_stream_is_frozen():
+    """The engine's draw keying (seed, draw id, global row, column) -> value; frozen so that neither side drifts."""
+    u = O.philox_uniform(42, O.draw_id("train", 0, 0), 0, 2, 6)
+    want = [[0.6129598617553711, 0.46858644485473633, 0.07323169708251953, 0.340861439704895, 0.9877185821533203,
+             0.32706332206726074],
+            [0.26124143600463867, 0.49120116233825684, 0.18712186813354492, 0.41673290729522705, 0.1328660249710083,
+             0.40821826457977295]]
+    assert u.tolist() == want
+    n = O.philox_normal(42, O.draw_id("infer", 0), 0, 1, 4)
+    np.testing.assert_allclose(n, [[0.4989447295665741, -0.22053277492523193, -0.8862244486808777, 0.9142584204673767]],
+                               rtol=1e-6)
+    assert O.draw_id("train", 3, 5) == 197 and O.draw_id("infer", 2) == (1 << 63) + 2 and O.draw_id("score", 1, 1) == (1 << 62) + 3
