@@ -56,3 +56,45 @@ def test_shard_rows_layout():
     with pytest.raises(ValueError):
         shard_rows(np.zeros((9, 3)), 4, 0, 2)     # remainder of 1 row does not split over 2 ranks
     assert local_batch(4096, 8192, 8) == 512
+
+
+def test_tensor_descriptors_for_numpy_and_torch_inputs():
+    """kucd_tensor = flattened DLTensor: what the shim hands to the C ABI for the array kinds callers pass."""
+    import torch
+
+    from keras_unsupervised_b200 import _lib as L
+
+    keep = []
+    a = np.arange(12, dtype=np.float32).reshape(3, 4)
+    t = L.tensor_of(a, keep)
+    assert (t.device_type, t.dtype_code, t.bits) == (L.DEV_CPU, L.DT_FLOAT, 32)
+    assert tuple(t.shape) == (3, 4) and tuple(t.strides) == (4, 1) and t.data == a.ctypes.data   # no copy
+    sl = L.tensor_of(a[:, :2], keep)                     # row-strided view: still no copy
+    assert tuple(sl.shape) == (3, 2) and tuple(sl.strides) == (4, 1) and sl.data == a.ctypes.data
+    tr = L.tensor_of(a.T, keep)                          # innermost stride != 1: copied
+    assert tuple(tr.shape) == (4, 3) and tuple(tr.strides) == (3, 1) and tr.data != a.ctypes.data
+    v = L.tensor_of(np.zeros(5, np.float32), keep)       # vectors travel as (n, 1) with unit stride
+    assert tuple(v.shape) == (5, 1) and tuple(v.strides) == (1, 1)
+    u8 = L.tensor_of(np.ones((2, 3), np.uint8), keep)
+    assert (u8.dtype_code, u8.bits) == (L.DT_UINT, 8)
+    bl = L.tensor_of(np.ones((2, 3), np.bool_), keep)
+    assert (bl.dtype_code, bl.bits) == (L.DT_UINT, 8)
+    f64 = L.tensor_of(np.ones((2, 3), np.float64), keep) # anything else is converted to float32 (K.floatx())
+    assert (f64.dtype_code, f64.bits) == (L.DT_FLOAT, 32)
+    with pytest.raises(ValueError):
+        L.tensor_of(np.zeros((2, 2, 2), np.float32), keep)
+    tt = torch.arange(6, dtype=torch.bfloat16).reshape(2, 3)
+    tb = L.tensor_of(tt, keep)
+    assert (tb.device_type, tb.dtype_code, tb.bits) == (L.DEV_CPU, L.DT_BFLOAT, 16) and tb.data == tt.data_ptr()
+    ti = L.tensor_of(torch.ones(2, 3, dtype=torch.int64), keep)
+    assert (ti.dtype_code, ti.bits) == (L.DT_FLOAT, 32)
+
+
+def test_error_codes_map_to_python_exceptions():
+    from keras_unsupervised_b200 import _lib as L
+
+    lib = L.load()
+    assert lib.kucd_sync(None) == L.ERR_INVALID_ARG
+    with pytest.raises(ValueError, match="NULL"):
+        L.check(lib.kucd_sync(None))
+    L.check(0)
