@@ -504,6 +504,9 @@ def _main(out):
             roof = {"bound": "tensor", "kernel": kernel, "achieved": ach, "peak": pk["sustained"], "unit": "TFLOP/s",
                     "frac": ach / pk["sustained"],
                     "peak_source": pk["source"] + ", sustained figure (kernel timed inside a long step)",
+                    "measured": "CUDA events on the engine stream around each launch of %d further steps issued directly "
+                                "(same process, same data, right after the timed region; a graph replay cannot carry "
+                                "per-kernel events)" % n_prof,
                     "traffic": traffic, "launch_ms": per_launch_ms, "launches_timed": n_timed,
                     "projections_per_launch": n_proj if chain else None, "flop_per_launch": flop,
                     "dw_launch_ms": (tp["dw_ms"] / tp["dw_timed"]) if tp["dw_timed"] else None,
