@@ -8,6 +8,9 @@ sampled hidden states of layer l (dbn.py:55) are produced as an engine Dataset a
 """
 from __future__ import annotations
 
+import json
+import os
+
 import numpy as np
 
 from ..engine import Dataset
@@ -82,3 +85,36 @@ class DBN(object):
             out = rbm_layer.inv_transform(H_p)
             H_p = out[0] if isinstance(out, list) else out
         return H_p
+
+    # ---- checkpoint: one JSON file with the stack's configs + one .npz per layer (cf. ku/utility.py:7-33, which
+    # stores a JSON architecture next to an HDF5 weight file) ----
+    def save(self, directory):
+        self._check()
+        os.makedirs(directory, exist_ok=True)
+        configs = []
+        for i, layer in enumerate(self._rbm_layers):
+            cfg = layer.get_config()
+            cfg["input_dim"] = int(layer.input_shape[1]) if layer.input_shape else None
+            configs.append(cfg)
+            if layer.built:
+                layer.save(os.path.join(directory, "layer%d.npz" % i))
+        with open(os.path.join(directory, "dbn.json"), "w") as f:
+            json.dump({"layers": configs}, f, indent=1)
+
+    @classmethod
+    def load(cls, directory, layer_class=None, **kwargs):
+        if layer_class is None:
+            from .rbm import RBM as layer_class
+        with open(os.path.join(directory, "dbn.json")) as f:
+            configs = json.load(f)["layers"]
+        dbn = cls()
+        for i, cfg in enumerate(configs):
+            input_dim = cfg.pop("input_dim", None)
+            layer = layer_class.from_config(cfg, **kwargs)
+            dbn.add_stack(layer)
+            path = os.path.join(directory, "layer%d.npz" % i)
+            if os.path.exists(path):
+                if input_dim is not None and not layer.built:
+                    layer.build((None, input_dim))
+                layer.load(path)
+        return dbn

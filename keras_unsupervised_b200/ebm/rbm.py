@@ -118,6 +118,13 @@ class RBM(object):
         """rbm.py:236-242, plus `mode` (the reference drops it and reloads as Gaussian)."""
         return {"hps": self.hps, "output_dim": self.output_dim, "name": self.name, "mode": self.mode}
 
+    @classmethod
+    def from_config(cls, config, **kwargs):
+        """Inverse of get_config (the Keras convention the reference inherits from Layer)."""
+        config = dict(config)
+        return cls(config.pop("hps"), config.pop("output_dim"), name=config.pop("name", None),
+                   mode=config.pop("mode", MODE_VISIBLE_GAUSSIAN), **kwargs)
+
     # ---- parameters: same attribute names as the reference -------------------------------------
     @property
     def rbm_weight(self):

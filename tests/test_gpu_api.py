@@ -212,3 +212,23 @@ def test_dbn_fit_matches_oracle_replay(ctx):
     assert H.shape == (512, 64)
     Vb = dbn.inv_transform(H)
     assert Vb.shape == (512, 160) and set(np.unique(Vb)) <= {0.0, 1.0}
+
+
+def test_dbn_save_load_round_trip(ctx, tmp_path):
+    from keras_unsupervised_b200.ebm import DBN, RBM, MODE_VISIBLE_BERNOULLI
+
+    rng = np.random.default_rng(41)
+    X = (rng.random((256, 96)) < 0.3).astype(np.float32)
+    hps = {"batch_size": 128, "epochs": 1, "lr": 1e-3, "dtype": "bf16", "seed": 3}
+    dbn = DBN()
+    for i, d in enumerate((64, 48)):
+        dbn.add_stack(RBM(dict(hps), d, name="l%d" % i, mode=MODE_VISIBLE_BERNOULLI, context=ctx))
+    dbn.fit(X, verbose=0)
+    dbn.save(tmp_path / "ck")
+    twin = DBN.load(tmp_path / "ck", context=ctx)
+    assert len(twin._rbm_layers) == 2 and [l.seed for l in twin._rbm_layers] == [l.seed for l in dbn._rbm_layers]
+    for a, b in zip(dbn._rbm_layers, twin._rbm_layers):
+        assert np.array_equal(a.rbm_weight, b.rbm_weight) and np.array_equal(a.hidden_bias, b.hidden_bias)
+        a._machine.set_seed(a.seed, 0)
+        b._machine.set_seed(b.seed, 0)
+    assert np.array_equal(dbn.transform(X), twin.transform(X))

@@ -98,3 +98,12 @@ def test_error_codes_map_to_python_exceptions():
     with pytest.raises(ValueError, match="NULL"):
         L.check(lib.kucd_sync(None))
     L.check(0)
+
+
+def test_config_round_trip():
+    hps = {"batch_size": 64, "epochs": 3, "lr": 0.01, "k": 2}
+    rbm = RBM(hps, 32, name="x", mode=MODE_VISIBLE_BERNOULLI)
+    twin = RBM.from_config(rbm.get_config())
+    assert twin.get_config() == rbm.get_config() and twin.mode == MODE_VISIBLE_BERNOULLI and not twin.built
+    legacy = RBM.from_config({"hps": hps, "output_dim": 32, "name": "y"})   # the reference's config has no mode
+    assert legacy.mode == MODE_VISIBLE_GAUSSIAN                              # rbm.py:22 default
