@@ -94,14 +94,17 @@ __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
   return v;
 }
 
+// <256, 2>: CTA pairs on 256 x 256 tiles (large minibatches).  <64, 1>: single CTAs on 128 x 64 tiles - the
+// latency-bound sizes (C1, C2), where a stage is a handful of tiles and what matters is that projections, dW and
+// their dependencies cost no launches.
+template <int BN, int CG>
 __global__ void __launch_bounds__(kNumThreads, 1) chain_kernel(const __grid_constant__ ChainParams p) {
-  constexpr int BN = kChainBN, CG = 2;
   constexpr int kBNLocal = BN / CG;
   constexpr int kTileM = kBlockM * CG;
   constexpr int kTmemCols = 2 * BN;
   using Cfg = GemmCfg<kBNLocal>;
   constexpr int kStages = Cfg::kStages;
-  const uint32_t cta_rank = ptx::cluster_ctarank();
+  const uint32_t cta_rank = CG == 2 ? ptx::cluster_ctarank() : 0u;
   const int unit = blockIdx.x / CG, num_units = gridDim.x / CG;
 
   extern __shared__ uint8_t smem_raw[];
@@ -148,7 +151,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) chain_kernel(const __grid_cons
     ptx::tmem_relinquish<CG>();
   }
   ptx::tc_fence_before();
-  ptx::cluster_sync();
+  if constexpr (CG == 2) ptx::cluster_sync(); else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -163,6 +166,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) chain_kernel(const __grid_cons
   if (warp == 0) {
     // ======================= TMA producer =======================
     if (lane == 0) {
+      auto tma_ld = [](void* dst, const CUtensorMap* tm, uint64_t* bar, int32_t c0, int32_t c1) {
+        if constexpr (CG == 2) ptx::tma_load_2d_pair(dst, tm, bar, c0, c1);
+        else ptx::tma_load_2d(dst, tm, bar, c0, c1);
+      };
       uint32_t stage = 0, phase = 0;
       int s = 0, base = 0;
       for (int q = unit; q < p.total_tiles; q += num_units) {
@@ -211,18 +218,18 @@ __global__ void __launch_bounds__(kNumThreads, 1) chain_kernel(const __grid_cons
             uint8_t* sb = sa + Cfg::kABytes;
             const int k0 = kb * kBlockK;
             if (!kd.a_mn) {
-              ptx::tma_load_2d_pair(sa, ma, &full_bar[stage], k0, m0 + a_off);  // box {64 k, 128 rows}
+              tma_ld(sa, ma, &full_bar[stage], k0, m0 + a_off);  // box {64 k, 128 rows}
             } else {
 #pragma unroll
               for (int j = 0; j < kBlockM / 64; ++j)  // boxes {64 m, 64 k}
-                ptx::tma_load_2d_pair(sa + j * (kBlockK * 128), ma, &full_bar[stage], m0 + 64 * j, k0 + a_off);
+                tma_ld(sa + j * (kBlockK * 128), ma, &full_bar[stage], m0 + 64 * j, k0 + a_off);
             }
             if (kd.b_mn) {
 #pragma unroll
               for (int j = 0; j < kBNLocal / 64; ++j)  // boxes {64 n, 64 k}
-                ptx::tma_load_2d_pair(sb + j * (kBlockK * 128), mb, &full_bar[stage], n0 + 64 * j, k0);
+                tma_ld(sb + j * (kBlockK * 128), mb, &full_bar[stage], n0 + 64 * j, k0);
             } else {
-              ptx::tma_load_2d_pair(sb, mb, &full_bar[stage], k0, n0);  // box {64 k, 128 n}
+              tma_ld(sb, mb, &full_bar[stage], k0, n0);  // box {64 k, 128 n}
             }
             if (++stage == kStages) {
               stage = 0;
@@ -235,6 +242,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) chain_kernel(const __grid_cons
   } else if (warp == 1) {
     // ======================= MMA issuer (rank 0 of the pair) =======================
     if (lane == 0 && cta_rank == 0) {
+      auto commit = [](uint64_t* bar) {
+        if constexpr (CG == 2) ptx::mma_commit_pair(bar, 0b11);
+        else ptx::mma_commit(bar);
+      };
       uint32_t stage = 0, phase = 0;
       uint32_t accn = 0;
       int s = 0, base = 0;
@@ -263,14 +274,14 @@ __global__ void __launch_bounds__(kNumThreads, 1) chain_kernel(const __grid_cons
             for (int k = 0; k < kBlockK / 16; ++k)
               ptx::mma_bf16<CG>(d_tmem, da + ((k * adv_a) >> 4), db + ((k * adv_b) >> 4), idesc,
                                 (seg > 0 || kb > 0 || k > 0) ? 1u : 0u);
-            ptx::mma_commit_pair(&empty_bar[stage], 0b11);
+            commit(&empty_bar[stage]);
             if (++stage == kStages) {
               stage = 0;
               phase ^= 1u;
             }
           }
         }
-        ptx::mma_commit_pair(&tmem_full_bar[as], 0b11);
+        commit(&tmem_full_bar[as]);
         ++accn;
       }
     }
@@ -310,7 +321,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) chain_kernel(const __grid_cons
       ptx::tc_fence_before();
       ptx::fence_proxy_async_global();  // these stores will be read by other CTAs' TMA loads
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive_cluster(&tmem_empty_bar[as], 0);
+      if (lane == 0) {
+        if constexpr (CG == 2) ptx::mbar_arrive_cluster(&tmem_empty_bar[as], 0);
+        else ptx::mbar_arrive(&tmem_empty_bar[as]);
+      }
       ++accn;
       // this CTA's part of the tile is in global memory once all eight epilogue warps got here
       ptx::named_bar_sync(1, kNumEpiWarps * 32);
@@ -322,7 +336,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) chain_kernel(const __grid_cons
   }
 
   ptx::tc_fence_before();
-  ptx::cluster_sync();
+  if constexpr (CG == 2) ptx::cluster_sync(); else __syncthreads();
   if (warp == 1) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc<CG>(tmem_base, kTmemCols);

@@ -798,8 +798,11 @@ static int gather_master(kucd_rbm* r) {
 }
 
 // The 2k+1 (+1 with persistent chains) projections of one minibatch as one persistent kernel (chain.cuh).
+// `small`: 128 x 64 tiles on single CTAs (latency-bound sizes) instead of 256 x 256 tiles on CTA pairs.
 static int launch_chain(kucd_rbm* r, const Planes& v0, int64_t batch, const kucd_hparams* hp, int64_t global_row0,
-                        uint64_t draw0, uint64_t stride, const StepDyn* dyn, bool v0_dyn, bool with_dw) {
+                        uint64_t draw0, uint64_t stride, const StepDyn* dyn, bool v0_dyn, bool with_dw, bool small) {
+  const int bn = small ? 64 : kChainBN, cg = small ? 1 : 2;
+  const int tile_m = kBlockM * cg;
   kucd_ctx* ctx = r->ctx;
   const int k = hp->k;
   const bool pcd = hp->persistent != 0;
@@ -815,7 +818,7 @@ static int launch_chain(kucd_rbm* r, const Planes& v0, int64_t batch, const kucd
   if (ok && !pcd) p.maps[4] = p.maps[0];
   const MatView Wv{r->Wp.buf[0].p, r->V, r->H, r->ldH};
   ok = ok && make_tmap_bf16(&p.maps[5], Wv, 64u, &err)                 // v.W   : W as (K,N), boxes {64 n, 64 k}
-          && make_tmap_bf16(&p.maps[6], Wv, kChainBN / 2, &err);        // h.W^T : W as (N,K), boxes {64 k, 128 n}
+          && make_tmap_bf16(&p.maps[6], Wv, bn / cg, &err);             // h.W^T : W as (N,K), boxes {64 k, bn/cg n}
   if (!ok) return fail(KUCD_ERR_CUDA, "%s", err.c_str());
   p.maps[7] = p.maps[6];
   // the same matrices as MN-major operands of the dW contraction (boxes {64 units, 64 minibatch rows})
@@ -823,7 +826,7 @@ static int launch_chain(kucd_rbm* r, const Planes& v0, int64_t batch, const kucd
     return make_tmap_bf16(&p.maps[i], MatView{q.p[0], q.rows, q.cols, q.ld}, 64u, &err);
   };
   if (!(mnmap(8, v0) && mnmap(9, h0) && mnmap(10, vk) && mnmap(11, hk))) return fail(KUCD_ERR_CUDA, "%s", err.c_str());
-  const int num_m_batch = static_cast<int>((batch + 2 * kBlockM - 1) / (2 * kBlockM));
+  const int num_m_batch = static_cast<int>((batch + tile_m - 1) / tile_m);
 
   auto kind = [&](int i, bool fwd, int map_a, __nv_bfloat16* out, int epi, float* colsum, float sign, bool a_dyn) {
     ChainKind& q = p.kinds[i];
@@ -841,7 +844,7 @@ static int launch_chain(kucd_rbm* r, const Planes& v0, int64_t batch, const kucd
     q.map_a = map_a;
     q.map_b = fwd ? 5 : 6;
     q.a_dyn = a_dyn ? 1 : 0;
-    q.num_n = (q.N + kChainBN - 1) / kChainBN;
+    q.num_n = (q.N + bn - 1) / bn;
     q.num_m = num_m_batch;
     q.batch_rows = 1;
     q.nseg = 1;
@@ -893,8 +896,8 @@ static int launch_chain(kucd_rbm* r, const Planes& v0, int64_t batch, const kucd
     q.map_a2 = 10;
     q.map_b2 = 11;
     q.a_dyn = v0_dyn ? 1 : 0;
-    q.num_n = static_cast<int32_t>((r->H + kChainBN - 1) / kChainBN);
-    q.num_m = static_cast<int32_t>((r->V + 2 * kBlockM - 1) / (2 * kBlockM));
+    q.num_n = static_cast<int32_t>((r->H + bn - 1) / bn);
+    q.num_m = static_cast<int32_t>((r->V + tile_m - 1) / tile_m);
     q.batch_rows = 0;
     q.dep2 = hsrc;  // the final h stage (which itself waited for the final v stage, row block by row block)
     stage(8, 0, 0);
@@ -917,40 +920,57 @@ static int launch_chain(kucd_rbm* r, const Planes& v0, int64_t batch, const kucd
   p.dyn_rank = ctx->rank;
   CU_TRY(cudaMemsetAsync(p.done, 0, static_cast<size_t>(ns) * num_m * 4, ctx->stream));
 
-  using Cfg = GemmCfg<kChainBN / 2>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    CU_TRY(cudaFuncSetAttribute(chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_set = true;
-  }
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(ctx->num_sms / 2 * 2);
-  cfg.blockDim = dim3(kNumThreads);
-  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
-  cfg.stream = ctx->stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  // The pairs wait on each other's tiles, so every pair of the grid must be resident at once: never launch more
-  // clusters than the device can hold of this kernel.
-  static int max_clusters = -1;
-  if (max_clusters < 0) {
-    int mc = 0;
-    if (cudaOccupancyMaxActiveClusters(&mc, chain_kernel, &cfg) != cudaSuccess || mc <= 0) {
-      cudaGetLastError();
-      mc = ctx->num_sms / 2;
-    }
-    max_clusters = mc;
-  }
-  const int units = std::min(total, std::min(max_clusters, ctx->num_sms / 2));
-  cfg.gridDim = dim3(units * 2);
   const bool prof = ctx->profile && dyn == nullptr;
-  const size_t pe0 = prof ? prof_event(ctx) : 0;
-  CU_TRY(cudaLaunchKernelEx(&cfg, chain_kernel, p));
+  size_t pe0 = 0;
+  if (small) {
+    using Cfg = GemmCfg<64>;
+    auto kern = chain_kernel<64, 1>;
+    static bool attr_set = false;
+    if (!attr_set) {
+      CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+      attr_set = true;
+    }
+    // the CTAs wait on each other's tiles: all of them must be resident (one per SM at this shared-memory size)
+    const int grid = std::min(total, ctx->num_sms);
+    pe0 = prof ? prof_event(ctx) : 0;
+    kern<<<grid, kNumThreads, Cfg::kSmemBytes, ctx->stream>>>(p);
+    CU_TRY(cudaGetLastError());
+  } else {
+    using Cfg = GemmCfg<kChainBN / 2>;
+    auto kern = chain_kernel<kChainBN, 2>;
+    static bool attr_set = false;
+    if (!attr_set) {
+      CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+      attr_set = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(ctx->num_sms / 2 * 2);
+    cfg.blockDim = dim3(kNumThreads);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    // The pairs wait on each other's tiles, so every pair of the grid must be resident at once: never launch more
+    // clusters than the device can hold of this kernel.
+    static int max_clusters = -1;
+    if (max_clusters < 0) {
+      int mc = 0;
+      if (cudaOccupancyMaxActiveClusters(&mc, kern, &cfg) != cudaSuccess || mc <= 0) {
+        cudaGetLastError();
+        mc = ctx->num_sms / 2;
+      }
+      max_clusters = mc;
+    }
+    const int units = std::min(total, std::min(max_clusters, ctx->num_sms / 2));
+    cfg.gridDim = dim3(units * 2);
+    pe0 = prof ? prof_event(ctx) : 0;
+    CU_TRY(cudaLaunchKernelEx(&cfg, kern, p));
+  }
   if (prof) ctx->marks.push_back({0, pe0, prof_event(ctx), ns});
   ctx->tm.gemm_launches++;
   ctx->tm.chain_launches++;
@@ -1103,8 +1123,18 @@ static int enqueue_cd(kucd_rbm* r, const Planes& v0, int64_t batch, const kucd_h
   // at C3 (2.529 vs 2.522 ms per step) and a loss at C4 (577 k vs 605 k samples/s) - its second segment has to wait
   // for every row block of the last projection, so it hides little - which is why it is off by default.
   const bool chain_dw = ctx->chain_dw && !r->fused_now;
+  // latency-bound sizes: the whole step's contractions (projections and dW) as one launch of the small-tile variant
+  static const bool small_chain_env = [] {
+    const char* e = getenv("KUCD_SMALL_CHAIN");
+    return !(e != nullptr && e[0] == '0');
+  }();
+  const bool small_chain = !whole_chain && small_chain_env && ctx->chain && batch <= 512 &&
+                           r->compute == KUCD_COMPUTE_BF16 && !gaussian && inj == nullptr && v0.n == 1 &&
+                           !r->fused_now && (!hp->persistent || r->last_vk_parts == 1);
   if (whole_chain) {
-    KU_TRY(launch_chain(r, v0, batch, hp, global_row0, draw0, stride, dyn, v0_dyn, chain_dw));
+    KU_TRY(launch_chain(r, v0, batch, hp, global_row0, draw0, stride, dyn, v0_dyn, chain_dw, false));
+  } else if (small_chain) {
+    KU_TRY(launch_chain(r, v0, batch, hp, global_row0, draw0, stride, dyn, v0_dyn, true, true));
   } else if (!two) {
     KU_TRY(chain(0, batch, ctx->stream, true));
   } else {
@@ -1121,7 +1151,7 @@ static int enqueue_cd(kucd_rbm* r, const Planes& v0, int64_t batch, const kucd_h
     KU_TRY(rc);
     if (prof) ctx->marks.push_back({0, pe0, prof_event(ctx), 2 * n_proj});
   }
-  if (!(whole_chain && chain_dw)) KU_TRY(delta_w(r, v0, h0, vk, hk, batch, dyn, v0_dyn));
+  if (!((whole_chain && chain_dw) || small_chain)) KU_TRY(delta_w(r, v0, h0, vk, hk, batch, dyn, v0_dyn));
   r->last_rows = batch;
   r->last_vk_parts = vparts;
   r->last_hk_parts = pparts;

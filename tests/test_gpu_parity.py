@@ -506,3 +506,45 @@ def test_sample_frequencies_follow_the_probabilities(ctx):
         freq += m.transform(v)
     z = (freq - n * p) / np.sqrt(n * p * (1 - p) + 1e-12)
     assert np.abs(z).max() < 5.5 and abs(z.mean()) < 0.05 and 0.9 < z.std() < 1.1
+
+
+def test_small_chain_variant_equals_per_projection_launches(monkeypatch):
+    """Latency-bound sizes (minibatch <= 512): projections AND the dW contraction run as one launch of the 128 x 64-tile
+    chain kernel.  Bit-identical states / dW / chains to the launch-per-contraction path."""
+    from keras_unsupervised_b200 import _lib as L
+    from keras_unsupervised_b200.engine import Context, Dataset, Machine
+
+    monkeypatch.delenv("KUCD_CHAIN", raising=False)
+    c_small = Context(device=0, seed=1)
+    monkeypatch.setenv("KUCD_CHAIN", "0")
+    c_plain = Context(device=0, seed=1)
+    rng = np.random.default_rng(103)
+    for V, H, rows, k in ((784, 500, 128, 1), (333, 270, 300, 3)):
+        ms = [_machine(c, V, H, "bf16", seed=23)[0] for c in (c_small, c_plain)]
+        v = _data(rng, rows, V, 0.2)
+        hp = Machine.hparams(lr=1e-3, k=k)
+        got = []
+        for m in ms:
+            m.cd_step(v, hp)
+            got.append(m.last_stats(rows))
+        for key in ("h_pos", "v_neg", "h_neg", "dW", "db"):
+            assert np.array_equal(got[0][key], got[1][key]), (V, key)
+        np.testing.assert_allclose(got[0]["dc"], got[1]["dc"], rtol=0, atol=1e-3)
+        chains = _data(rng, 128, V, 0.5)
+        data = _data(rng, 600, V, 0.2)
+        hp = Machine.hparams(lr=1e-3, k=2, persistent=True)
+        params = []
+        for c, m in zip((c_small, c_plain), ms):
+            m.set_chains(chains)
+            ds = Dataset.from_array(c, data, L.COMPUTE_BF16)
+            for _ in range(2):
+                m.fit_epoch(ds, 128, hp)          # 4 full minibatches + a remainder of 88 rows
+            c.sync()
+            params.append(m.get_params() + (m.get_chains(128),))
+            ds.close()
+        assert np.array_equal(params[0][3], params[1][3])
+        for i in range(3):
+            np.testing.assert_allclose(params[0][i], params[1][i], rtol=0, atol=1e-6)
+    assert c_small.timings()["chain_dw_launches"] > 0 and c_plain.timings()["chain_launches"] == 0
+    c_small.close()
+    c_plain.close()
