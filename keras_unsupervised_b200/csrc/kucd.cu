@@ -207,8 +207,11 @@ struct PlaneBuf {
   }
 };
 
+static uint64_t g_next_dataset_id = 1;
+
 struct kucd_dataset {
   kucd_ctx* ctx = nullptr;
+  uint64_t id = g_next_dataset_id++;  // a freed data set's address may be handed out again: graphs are keyed by id
   PlaneBuf planes;
   int64_t rows = 0, dim = 0;
   int nparts = 1;  // live terms
@@ -217,12 +220,14 @@ struct kucd_dataset {
 
 struct GraphKey {
   const kucd_dataset* ds = nullptr;
+  uint64_t ds_id = 0;
+  const void* ds_ptr = nullptr;
   int64_t batch = 0, global_row0 = 0, ds_rows = 0;
   kucd_hparams hp{};
   int ds_parts = 0;
   bool fused = false;
   bool operator==(const GraphKey& o) const {
-    return ds == o.ds && batch == o.batch && global_row0 == o.global_row0 && ds_rows == o.ds_rows &&
+    return ds == o.ds && ds_id == o.ds_id && ds_ptr == o.ds_ptr && batch == o.batch && global_row0 == o.global_row0 && ds_rows == o.ds_rows &&
            ds_parts == o.ds_parts && fused == o.fused && memcmp(&hp, &o.hp, sizeof hp) == 0;
   }
 };
@@ -2021,6 +2026,8 @@ static int fit_range_impl(kucd_rbm* r, kucd_dataset* ds, int64_t batch, const ku
 
   GraphKey key;
   key.ds = ds;
+  key.ds_id = ds->id;
+  key.ds_ptr = ds->planes.buf[0].p;
   key.batch = batch;
   key.global_row0 = global_row0;
   key.ds_rows = N;

@@ -232,3 +232,25 @@ def test_dbn_save_load_round_trip(ctx, tmp_path):
         a._machine.set_seed(a.seed, 0)
         b._machine.set_seed(b.seed, 0)
     assert np.array_equal(dbn.transform(X), twin.transform(X))
+
+
+def test_refitting_with_fresh_arrays_never_replays_a_stale_graph(ctx):
+    """Every RBM.fit(array) builds a new resident data set; the captured step graph must follow it (the allocator
+    is free to hand a released data set's address out again)."""
+    from keras_unsupervised_b200.ebm import RBM, MODE_VISIBLE_BERNOULLI
+
+    rng = np.random.default_rng(51)
+    hps = {"batch_size": 128, "epochs": 2, "lr": 1e-2, "dtype": "bf16", "seed": 4}
+    data = [(rng.random((512, 192)) < q).astype(np.float32) for q in (0.1, 0.5, 0.9, 0.3)]
+    a = RBM(dict(hps), 64, name="a", mode=MODE_VISIBLE_BERNOULLI, context=ctx)
+    for X in data:
+        a.fit(X, verbose=0)
+    W, b, c = a._machine.get_params()
+    # replay with the oracle: the visible bias follows the data's mean, so stale data would be obvious
+    b0 = RBM(dict(hps), 64, name="b", mode=MODE_VISIBLE_BERNOULLI, context=ctx)
+    b0.build((None, 192))
+    orc = O.OracleRBM(*b0._machine.get_params(), compute="bf16")
+    step = 0
+    for X in data:
+        step = O.philox_fit(orc, X, 128, 2, 1e-2, 4, step0=step)
+    assert np.abs(W - orc.W).mean() < 5e-5 and np.abs(b - orc.b).max() < 2e-2
