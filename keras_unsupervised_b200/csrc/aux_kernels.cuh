@@ -107,6 +107,14 @@ __global__ void export_f32_kernel(const float* __restrict__ src, int64_t ld, int
   }
 }
 
+// normalize = mean under graph replay: the divisor is the CURRENT minibatch's global row count (the remainder
+// minibatch is shorter), which only the device knows
+__device__ __forceinline__ float step_scale(float scale, const StepDyn* sdyn, float world) {
+  if (sdyn == nullptr) return scale;
+  const int rows = sdyn->rows_valid > 0 ? sdyn->rows_valid : 1;
+  return 1.0f / (static_cast<float>(rows) * world);
+}
+
 // Small work folded into the weight-update launch (done by its last block) so that a latency-bound step is one
 // launch shorter per item: the two bias updates (rbm.py:129-134) and the step-state advance of graph replay.
 struct UpdateTail {
@@ -131,7 +139,8 @@ struct UpdateTail {
 __global__ void update_w_kernel(float* __restrict__ W, const float* __restrict__ dW, float* __restrict__ mom,
                                 __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ mid,
                                 __nv_bfloat16* __restrict__ lo, int64_t n4, float lr, float scale, float momentum,
-                                float weight_decay, UpdateTail tail) {
+                                float weight_decay, UpdateTail tail, const StepDyn* sdyn, float world) {
+  scale = step_scale(scale, sdyn, world);
   if (blockIdx.x == gridDim.x - 1) {
     for (int i = threadIdx.x; i < tail.nb; i += blockDim.x) {
       float s = lr * scale * tail.db[i];
@@ -215,9 +224,10 @@ __global__ void refresh_planes_kernel(const float* __restrict__ W, __nv_bfloat16
 
 // bias update (rbm.py:129-134): x += lr * scale * d (+ momentum), n entries
 __global__ void update_bias_kernel(float* __restrict__ x, const float* __restrict__ d, float* __restrict__ mom,
-                                   int64_t n, float lr, float scale, float momentum) {
+                                   int64_t n, float lr, float scale, float momentum, const StepDyn* sdyn, float world) {
   const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   if (i >= n) return;
+  scale = step_scale(scale, sdyn, world);
   float s = lr * scale * d[i];
   if (mom != nullptr) {
     s = momentum * mom[i] + s;
@@ -493,7 +503,9 @@ __global__ void reduce_bias_kernel(const float* __restrict__ slots, int n, int l
 // plane - the all-gather of the new W happens inside the update kernel, as plain NVLink stores.
 __global__ void update_w_sharded_kernel(float* __restrict__ W, const float* __restrict__ slots, int64_t slice_elems,
                                         int n, float* __restrict__ mom, PeerSet ps, int64_t elem0, int64_t n4, float lr,
-                                        float scale, float momentum, float weight_decay) {
+                                        float scale, float momentum, float weight_decay, const StepDyn* sdyn,
+                                        float world) {
+  scale = step_scale(scale, sdyn, world);
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n4;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     float4 d = make_float4(0.f, 0.f, 0.f, 0.f);

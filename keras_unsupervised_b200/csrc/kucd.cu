@@ -699,6 +699,11 @@ static int apply_update(kucd_rbm* r, const kucd_hparams* hp, int64_t rows_global
   kucd_ctx* ctx = r->ctx;
   if (adv_done != nullptr) *adv_done = false;
   const float scale = hp->normalize ? 1.0f / static_cast<float>(std::max<int64_t>(rows_global, 1)) : 1.0f;
+  // replayed step + mean normalisation: the kernels divide by the current minibatch's rows (device state); the
+  // step-state advance then has to be a launch of its own, after every reader
+  const StepDyn* sdyn = (hp->normalize && adv != nullptr) ? adv : nullptr;
+  const float world = static_cast<float>(ctx->world);
+  if (sdyn != nullptr) adv = nullptr;
   const bool use_mom = hp->momentum != 0.f;
   if (use_mom) {
     KU_TRY(r->mW.ensure(static_cast<size_t>(r->V) * r->ldH * 4, true));
@@ -717,7 +722,7 @@ static int apply_update(kucd_rbm* r, const kucd_hparams* hp, int64_t rows_global
       if (n4 > 0) {
         update_w_sharded_kernel<<<grid_for(ctx, n4, 256), 256, 0, ctx->stream>>>(
             r->W32.as<float>(), r->ps.dw_slot[me], r->slice_elems, n, use_mom ? r->mW.as<float>() : nullptr, r->ps,
-            r0 * r->ldH, n4, hp->lr, scale, hp->momentum, hp->weight_decay);
+            r0 * r->ldH, n4, hp->lr, scale, hp->momentum, hp->weight_decay, sdyn, world);
         ctx->tm.aux_launches++;
       }
     }
@@ -744,7 +749,7 @@ static int apply_update(kucd_rbm* r, const kucd_hparams* hp, int64_t rows_global
         r->W32.as<float>(), r->dW(), use_mom ? r->mW.as<float>() : nullptr, r->Wp.buf[0].as<__nv_bfloat16>(),
         r->wparts == 3 ? r->Wp.buf[1].as<__nv_bfloat16>() : nullptr,
         r->wparts == 3 ? r->Wp.buf[2].as<__nv_bfloat16>() : nullptr, n4, hp->lr, scale, hp->momentum, hp->weight_decay,
-        tail);
+        tail, sdyn, world);
     ctx->tm.aux_launches++;
     if (adv_done != nullptr) *adv_done = adv != nullptr;
     CU_TRY(cudaGetLastError());
@@ -754,13 +759,13 @@ static int apply_update(kucd_rbm* r, const kucd_hparams* hp, int64_t rows_global
   if (hp->update_mask & KUCD_UPDATE_C) {
     update_bias_kernel<<<(r->H + 255) / 256, 256, 0, ctx->stream>>>(r->c32.as<float>(), r->dc(),
                                                                      use_mom ? r->mc.as<float>() : nullptr, r->H, hp->lr,
-                                                                     scale, hp->momentum);
+                                                                     scale, hp->momentum, sdyn, world);
     ctx->tm.aux_launches++;
   }
   if (hp->update_mask & KUCD_UPDATE_B) {
     update_bias_kernel<<<(r->V + 255) / 256, 256, 0, ctx->stream>>>(r->b32.as<float>(), r->db(),
                                                                      use_mom ? r->mb.as<float>() : nullptr, r->V, hp->lr,
-                                                                     scale, hp->momentum);
+                                                                     scale, hp->momentum, sdyn, world);
     ctx->tm.aux_launches++;
   }
   if (r->fused_now) {
@@ -2021,8 +2026,6 @@ static int fit_range_impl(kucd_rbm* r, kucd_dataset* ds, int64_t batch, const ku
     KU_TRY(r->mb.ensure(r->ldVb() * 4, true));
     KU_TRY(r->mc.ensure(r->ldHb() * 4, true));
   }
-  if (hp->normalize && N % batch != 0)
-    return fail(KUCD_ERR_INVALID_ARG, "normalize=mean under fit_epoch needs the row count to divide by batch_size");
 
   GraphKey key;
   key.ds = ds;

@@ -303,8 +303,10 @@ def batches(n_rows: int, batch_size: int):
         yield i * batch_size, min((i + 1) * batch_size, n_rows)
 
 
-def philox_fit(rbm: OracleRBM, V, batch_size, epochs, lr, seed, k=1, persistent=False, step0=0, row0=0, **kw):
-    """The engine's fit loop with its own Philox draws (fused schedule): what fit_epoch must reproduce."""
+def philox_fit(rbm: OracleRBM, V, batch_size, epochs, lr, seed, k=1, persistent=False, step0=0, row0=0,
+               normalize=False, **kw):
+    """The engine's fit loop with its own Philox draws (fused schedule): what fit_epoch must reproduce.
+    normalize: divide the batch sums by the rows of the current minibatch (the remainder one is shorter)."""
     step = step0
     for _ in range(epochs):
         for lo, hi in batches(V.shape[0], batch_size):
@@ -317,6 +319,8 @@ def philox_fit(rbm: OracleRBM, V, batch_size, epochs, lr, seed, k=1, persistent=
                    for t in range(k)]
             u_v = [None] + [gen_v(seed, draw_id("train", step, 2 * t), row0, rows, rbm.V) for t in range(1, k + 1)]
             u_hc = philox_uniform(seed, draw_id("train", step, 1), row0, rows, rbm.H) if persistent else None
+            if normalize:
+                kw["scale"] = 1.0 / rows
             rbm.fused_step(V[lo:hi], u_h, u_v, lr, k=k, persistent=persistent, u_hc=u_hc, **kw)
             step += 1
     return step

@@ -548,3 +548,25 @@ def test_small_chain_variant_equals_per_projection_launches(monkeypatch):
     assert c_small.timings()["chain_dw_launches"] > 0 and c_plain.timings()["chain_launches"] == 0
     c_small.close()
     c_plain.close()
+
+
+def test_mean_normalisation_with_a_remainder_minibatch(ctx):
+    """normalize = mean under graph replay: the last, shorter minibatch divides by ITS row count (device-side)."""
+    from keras_unsupervised_b200 import _lib as L
+    from keras_unsupervised_b200.engine import Dataset, Machine
+
+    rng = np.random.default_rng(107)
+    N, B, V, H, seed = 300, 128, 200, 136, 19     # minibatches of 128, 128 and 44 rows
+    for compute in ("f32", "bf16"):
+        m, orc = _machine(ctx, V, H, compute, seed=seed)
+        data = _data(rng, N, V, 0.3)
+        ds = Dataset.from_array(ctx, data, L.COMPUTE_F32X3 if compute == "f32" else L.COMPUTE_BF16)
+        hp = Machine.hparams(lr=0.1, k=1, normalize=True, momentum=0.5)
+        for _ in range(2):
+            m.fit_epoch(ds, B, hp)
+        ctx.sync()
+        O.philox_fit(orc, data, B, 2, 0.1, seed, normalize=True, momentum=0.5)
+        W, b, c = m.get_params()
+        assert np.abs(W - orc.W).mean() < 2e-5 and np.abs(W - orc.W).max() < 5e-3, compute
+        assert np.abs(b - orc.b).max() < 5e-3 and np.abs(c - orc.c).max() < 5e-3
+        ds.close()
