@@ -38,7 +38,7 @@ sys.path.insert(0, HERE)
 import kshim  # noqa: E402
 
 
-def run_rbm(mode_name):
+def run_rbm(mode_name, out_dir=HERE):
     kshim.REC = kshim.Recorder(seed=7, param_seed=0)
     kshim.Function._count = 0
     kshim.install("/root/reference")
@@ -107,7 +107,7 @@ def run_rbm(mode_name):
     printed = [float(l.split("score:")[1]) for l in out.getvalue().splitlines() if "score:" in l]
     assert len(printed) == steps and np.allclose(printed, scores, atol=1e-6)
     np.savez_compressed(
-        os.path.join(HERE, "ref_rbm_%s.npz" % mode_name), X=X, W0=W0, b0=b0, c0=c0, lr=np.float32(hps["lr"]),
+        os.path.join(out_dir, "ref_rbm_%s.npz" % mode_name), X=X, W0=W0, b0=b0, c0=c0, lr=np.float32(hps["lr"]),
         batch=np.int64(B), steps=np.int64(steps), scores=np.array(scores, np.float64),
         W_final=rbm.rbm_weight.value, b_final=rbm.visible_bias.value, c_final=rbm.hidden_bias.value,
         fit_error=np.array(err), config=np.array(json.dumps(rbm.get_config(), default=str)),
@@ -115,7 +115,7 @@ def run_rbm(mode_name):
     print(mode_name, "steps executed:", steps, "| reference raised:", err, "| scores:", np.round(scores, 4))
 
 
-def run_dbn():
+def run_dbn(out_dir=HERE):
     """dbn.py at HEAD with recording mock layers: documents D7."""
     import importlib.util
 
@@ -161,7 +161,7 @@ def run_dbn():
     x = np.ones((2, 3))
     res["inv_transform_is_identity"] = bool(np.array_equal(dbn.inv_transform(x), x))
     res["constants"] = [mod.MODE_VISIBLE_BERNOULLI, mod.MODE_VISIBLE_GAUSSIAN, mod.MODE_COMPLEX]
-    with open(os.path.join(HERE, "ref_dbn.json"), "w") as f:
+    with open(os.path.join(out_dir, "ref_dbn.json"), "w") as f:
         json.dump(res, f, indent=1, sort_keys=True)
     print("dbn:", res)
 

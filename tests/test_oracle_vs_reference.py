@@ -98,3 +98,31 @@ def test_reference_dbn_defects_and_errors():
     dbn = O.OracleDBN()
     with pytest.raises(ValueError, match="Any rbm layer doesn't exist."):
         dbn.transform(np.zeros((2, 4)), [])
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/ku/ebm/rbm.py"), reason="the reference tree is only mounted in the build container")
+def test_committed_fixtures_are_what_the_reference_produces(tmp_path, capsys):
+    """Where /root/reference is mounted: re-run the generator (the unmodified ku/ebm/rbm.py on the numpy backend
+    stand-in) and compare with the committed golden vectors, array by array."""
+    import importlib.util
+    import sys
+
+    sys.path.insert(0, GOLD)
+    spec = importlib.util.spec_from_file_location("make_reference_fixtures", os.path.join(GOLD, "make_reference_fixtures.py"))
+    gen = importlib.util.module_from_spec(spec)
+    saved = {k: v for k, v in sys.modules.items() if k == "ku" or k.startswith(("ku.", "tensorflow"))}
+    try:
+        spec.loader.exec_module(gen)
+        for mode in ("bernoulli", "gaussian"):
+            gen.run_rbm(mode, out_dir=str(tmp_path))
+            new, old = np.load(tmp_path / ("ref_rbm_%s.npz" % mode)), _load("ref_rbm_%s.npz" % mode)
+            assert sorted(new.files) == sorted(old.files)
+            for key in old.files:
+                assert np.array_equal(new[key], old[key]), (mode, key)
+        gen.run_dbn(out_dir=str(tmp_path))
+        assert json.load(open(tmp_path / "ref_dbn.json")) == json.load(open(os.path.join(GOLD, "ref_dbn.json")))
+    finally:
+        for k in [k for k in sys.modules if k == "ku" or k.startswith(("ku.", "tensorflow"))]:
+            del sys.modules[k]
+        sys.modules.update(saved)
+        capsys.readouterr()
