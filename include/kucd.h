@@ -210,7 +210,8 @@ int kucd_rbm_cd_step(kucd_rbm* rbm, const kucd_tensor* v_batch, const kucd_hpara
 int kucd_rbm_score(kucd_rbm* rbm, const kucd_tensor* v_batch, const kucd_tensor* u_h,
                    const kucd_tensor* u_v, float* score_out);
 /* statistics of the most recent cd_step, for parity tests: dW (V,H), db (V), dc (H) float32 - the
- * un-scaled batch sums of rbm.py:125-126,131,134 (after the all-reduce when a group is attached);
+ * un-scaled batch sums of rbm.py:125-126,131,134 (after the all-reduce when a group is attached; under the
+ * fused exchange dW is never assembled on one rank and this call returns stale values for it - db, dc are global);
  * and the sampled states of that step: h_pos (rows,H), v_neg (rows,V), h_neg (rows,H).  Any NULL. */
 int kucd_rbm_last_stats(kucd_rbm* rbm, kucd_tensor* dW, kucd_tensor* db, kucd_tensor* dc,
                         kucd_tensor* h_pos, kucd_tensor* v_neg, kucd_tensor* h_neg);

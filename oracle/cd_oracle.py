@@ -19,7 +19,7 @@ PINNING.  The reference ships no tests or golden vectors and its arithmetic runs
 which is not installable here, so TensorFlow's own kernels are unpinned.  What IS pinned: the op
 sequence of ku/ebm/rbm.py itself.  tests/golden/make_reference_fixtures.py imports the unmodified
 /root/reference/ku/ebm/rbm.py on top of a numpy stand-in for the handful of keras-backend calls it
-makes (tools/kshim), runs RBM.build / RBM.fit / transform / inv_transform / cal_free_energy with
+makes (tests/golden/kshim.py), runs RBM.build / RBM.fit / transform / inv_transform / cal_free_energy with
 recorded random draws, and freezes inputs + outputs in tests/golden/ref_rbm_*.npz;
 tests/test_oracle_vs_reference.py replays the same draws through this oracle and demands equality.
 
