@@ -462,6 +462,30 @@ def _main(out):
         e2e["uint8_input"] = {"value": world * n_e2e * B / dt8, "unit": UNIT, "h2d_bytes_per_step": B * V,
                               "ms_per_step": 1e3 * dt8 / n_e2e}
         del host8
+        # and as packed bits (1/32 of the float32 bytes; data.PackedBits, include/kucd.h bits = 1): informational
+        from keras_unsupervised_b200.data import PackedBits
+
+        nb = (V + 7) // 8
+        hostb = torch.empty((n_e2e * B, nb), dtype=torch.uint8).pin_memory()
+        weights = (2 ** torch.arange(8, device="cuda", dtype=torch.int32)).view(1, 1, 8)
+        for i in range(n_e2e):
+            blk = X[(i % n_batches) * B:((i % n_batches) + 1) * B].to(torch.int32)
+            if V % 8:
+                blk = torch.nn.functional.pad(blk, (0, nb * 8 - V))
+            hostb[i * B:(i + 1) * B].copy_((blk.view(B, nb, 8) * weights).sum(dim=2).to(torch.uint8))
+        packed = PackedBits(hostb, V)
+        m.fit_host(packed[:2 * B], B, hp_e, global_row0=row0)
+        barrier()
+        t0 = time.perf_counter()
+        m.fit_host(packed, B, hp_e, global_row0=row0)
+        dtb = time.perf_counter() - t0
+        if dist is not None:
+            t = torch.tensor([dtb], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dtb = float(t.item())
+        e2e["packed_bits_input"] = {"value": world * n_e2e * B / dtb, "unit": UNIT, "h2d_bytes_per_step": B * nb,
+                                    "ms_per_step": 1e3 * dtb / n_e2e}
+        del hostb, packed
 
     # ---- roofline of the dominant kernel: per-launch CUDA events on the engine stream -------------
     roof = None

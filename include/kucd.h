@@ -52,7 +52,12 @@ typedef enum kucd_status {
 #define KUCD_DT_BFLOAT 4
 
 /* A 2-D (or 1-D: shape[1] = 1) strided tensor.  strides are in elements; the innermost stride must
- * be 1.  Accepted element types: float32 (the reference's K.floatx()), bfloat16 and uint8. */
+ * be 1.  Accepted element types: float32 (the reference's K.floatx()), bfloat16, uint8 and - for 0/1
+ * matrices (binarised data, sampled states) - packed bits: dtype_code = KUCD_DT_UINT, bits = 1, column j
+ * of a row is bit (j % 8) of byte (j / 8) of that row (numpy.packbits(x, axis=1, bitorder="little")),
+ * shape[1] is the number of columns and strides[0] the row pitch IN BITS (a multiple of 8).  Packed
+ * inputs are accepted wherever a visible / hidden matrix is read; packed outputs wherever the result is
+ * a 0/1 state (KUCD_ERR_UNSUPPORTED_DTYPE for probabilities, free energies, Gaussian visibles). */
 typedef struct kucd_tensor {
   void* data;
   int32_t device_type;
@@ -225,6 +230,14 @@ int kucd_dataset_create(kucd_ctx* ctx, const kucd_tensor* data, int compute, kuc
 int kucd_dataset_destroy(kucd_dataset* ds);
 int kucd_dataset_shape(kucd_dataset* ds, int64_t* rows, int64_t* dim);
 int kucd_dataset_read(kucd_dataset* ds, kucd_tensor* out);
+/* Epoch shuffling (an extension: the reference walks the rows in order, rbm.py:218).  Row i of the result
+ * is row perm(i) of `in`, perm = a keyed bijection of [0, rows): a 6-round balanced Feistel network over
+ * the smallest even-width power of two >= rows with cycle walking, round keys = the first six words of
+ * Philox4x32-10(counter = (0x53485546, j, epoch lo, epoch hi), key = seed), j = 0, 1, round function
+ * murmur3's fmix32(R ^ k_r) (restated in oracle/cd_oracle.py:feistel_permutation).  *inout == NULL: a new
+ * data set is created; otherwise *inout (same shape) is overwritten, so the captured step graph of
+ * kucd_rbm_fit_epoch, which is keyed by the data set, stays valid from epoch to epoch. */
+int kucd_dataset_shuffle(kucd_dataset* in, uint64_t seed, uint64_t epoch, kucd_dataset** inout);
 /* One epoch over sequential slices of `batch` rows, remainder last, no shuffle (rbm.py:163,211,218);
  * every step is one replay of a captured CUDA graph.  With a data-parallel group attached every rank
  * passes its own shard of every global minibatch: `batch` is the per-rank row count and

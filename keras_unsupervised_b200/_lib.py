@@ -106,6 +106,7 @@ SIGNATURES = {
     "kucd_dataset_destroy": (C.c_int, [_P]),
     "kucd_dataset_shape": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "kucd_dataset_read": (C.c_int, [_P, _TP]),
+    "kucd_dataset_shuffle": (C.c_int, [_P, C.c_uint64, C.c_uint64, C.POINTER(_P)]),
     "kucd_rbm_fit_epoch": (C.c_int, [_P, _P, C.c_int64, C.POINTER(HParams), C.c_int64, C.POINTER(EpochStats)]),
     "kucd_rbm_fit_range": (C.c_int, [_P, _P, C.c_int64, C.POINTER(HParams), C.c_int64, C.c_int64, C.c_int64,
                                       C.POINTER(EpochStats)]),
@@ -177,6 +178,13 @@ def tensor_of(x, keep: list) -> Tensor:
     """Describe a numpy array or a torch tensor (CPU, pinned or CUDA) as a kucd_tensor without copying
     when its layout allows it.  Objects that must outlive the call are appended to `keep`."""
     import numpy as np
+
+    if type(x).__name__ == "PackedBits" and hasattr(x, "n_cols"):  # data.PackedBits: one bit per unit
+        t = tensor_of(x.data, keep)  # the uint8 byte matrix
+        rows, nbytes = t.shape[0], t.shape[1]
+        pitch_bits = t.strides[0] * 8 if rows > 1 else max(nbytes, 1) * 8
+        return Tensor(t.data, t.device_type, t.device_id, DT_UINT, 1, (C.c_int64 * 2)(rows, int(x.n_cols)),
+                      (C.c_int64 * 2)(pitch_bits, 1))
 
     if _is_torch(x):
         import torch

@@ -65,6 +65,71 @@ __global__ void ingest_kernel(const T* __restrict__ src, int64_t src_ld, int64_t
   if (inexact != nullptr && bad) atomicOr(inexact, 1);
 }
 
+// Bit-packed 0/1 matrices: column j of a row is bit (j % 8) of byte (j / 8) - numpy.packbits(..., bitorder="little").
+// The two conversions below are shared by the kernels and by tools/data_path_host.cu (host-side check against the oracle).
+struct Bf16x8 {
+  uint32_t w[4];  // eight bf16 values, element 2i in the low half of w[i]
+};
+
+// one byte -> eight bf16 values in {0, 1}, only the first `valid` columns kept (bf16 1.0 = 0x3F80)
+__host__ __device__ __forceinline__ Bf16x8 bits_to_bf16x8(uint32_t b, int valid) {
+  if (valid < 8) b &= (1u << (valid > 0 ? valid : 0)) - 1u;
+  Bf16x8 v;
+  v.w[0] = ((b & 1u) ? 0x3F80u : 0u) | ((b & 2u) ? 0x3F800000u : 0u);
+  v.w[1] = ((b & 4u) ? 0x3F80u : 0u) | ((b & 8u) ? 0x3F800000u : 0u);
+  v.w[2] = ((b & 16u) ? 0x3F80u : 0u) | ((b & 32u) ? 0x3F800000u : 0u);
+  v.w[3] = ((b & 64u) ? 0x3F80u : 0u) | ((b & 128u) ? 0x3F800000u : 0u);
+  return v;
+}
+
+// eight bf16 values -> one byte: bit j = (value j != +-0), only the first `valid` columns kept
+__host__ __device__ __forceinline__ uint32_t bf16x8_to_bits(const Bf16x8& v, int valid) {
+  uint32_t b = 0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    b |= ((v.w[j] & 0x7FFFu) != 0u ? 1u : 0u) << (2 * j);
+    b |= ((v.w[j] & 0x7FFF0000u) != 0u ? 1u : 0u) << (2 * j + 1);
+  }
+  if (valid < 8) b &= (1u << (valid > 0 ? valid : 0)) - 1u;
+  return b;
+}
+
+// Packed rows -> bf16 planes.  One source byte (8 columns = one 16-byte store) per thread; 1/8 B read + 2 B written
+// per unit, against 4 + 2 B for float32 input: a binary data set crosses PCIe and HBM 32x smaller than as float32.
+__global__ void ingest_bits_kernel(const uint8_t* __restrict__ src, int64_t src_pitch, int64_t rows, int64_t cols,
+                                   __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ mid,
+                                   __nv_bfloat16* __restrict__ lo, int64_t ld, int nparts) {
+  const int64_t groups_per_row = ld / 8;
+  const int64_t total = rows * groups_per_row;
+  for (int64_t g = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; g < total;
+       g += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = g / groups_per_row, c0 = (g % groups_per_row) * 8;
+    const int64_t left = cols - c0;  // columns of this group that exist
+    const uint32_t b = left > 0 ? __ldg(src + r * src_pitch + (c0 >> 3)) : 0u;
+    const Bf16x8 v = bits_to_bf16x8(b, left >= 8 ? 8 : static_cast<int>(left));
+    *reinterpret_cast<uint4*>(hi + r * ld + c0) = make_uint4(v.w[0], v.w[1], v.w[2], v.w[3]);
+    if (nparts == 3) {
+      *reinterpret_cast<uint4*>(mid + r * ld + c0) = make_uint4(0u, 0u, 0u, 0u);
+      *reinterpret_cast<uint4*>(lo + r * ld + c0) = make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
+}
+
+// 0/1 state plane -> packed rows; one destination byte per thread
+__global__ void export_bits_kernel(const __nv_bfloat16* __restrict__ hi, int64_t ld, int64_t rows, int64_t cols,
+                                   uint8_t* __restrict__ dst, int64_t dst_pitch) {
+  const int64_t bytes_per_row = (cols + 7) / 8;
+  const int64_t total = rows * bytes_per_row;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / bytes_per_row, c0 = (i % bytes_per_row) * 8;
+    const uint4 q = *reinterpret_cast<const uint4*>(hi + r * ld + c0);  // ld is a multiple of 64: in bounds, aligned
+    const Bf16x8 v{{q.x, q.y, q.z, q.w}};
+    const int64_t left = cols - c0;
+    dst[r * dst_pitch + (c0 >> 3)] = static_cast<uint8_t>(bf16x8_to_bits(v, left >= 8 ? 8 : static_cast<int>(left)));
+  }
+}
+
 template <typename T>
 __device__ __forceinline__ void store_from_float(T* p, float x);
 template <>
@@ -436,6 +501,90 @@ __global__ void copy_rows_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfl
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x)
     reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(src)[i];
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Epoch shuffling (the reference never shuffles, rbm.py:218).  A keyed bijection of [0, n): a
+// 6-round balanced Feistel network over the smallest even-width power of two >= n, walked until it lands below n
+// (cycle walking keeps it a bijection).  Counter-based like the Philox draws: any row's source is computed from its
+// index alone - no sort, no permutation array, nothing to exchange between ranks.
+// ---------------------------------------------------------------------------------------------------
+struct FeistelKey {
+  uint32_t k[6];
+  uint32_t half_bits;  // bits per half (width = 2 * half_bits)
+  uint32_t pad;
+};
+
+__host__ __device__ __forceinline__ uint32_t fmix32(uint32_t h) {
+  h ^= h >> 16;
+  h *= 0x85EBCA6Bu;
+  h ^= h >> 13;
+  h *= 0xC2B2AE35u;
+  h ^= h >> 16;
+  return h;
+}
+
+__host__ __device__ __forceinline__ uint64_t feistel_permute(uint64_t i, uint64_t n, const FeistelKey& key) {
+  const uint32_t hb = key.half_bits;
+  const uint32_t mask = (hb >= 32u) ? 0xFFFFFFFFu : ((1u << hb) - 1u);
+  uint64_t x = i;
+  do {
+    uint32_t L = static_cast<uint32_t>(x >> hb) & mask, R = static_cast<uint32_t>(x) & mask;
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+      const uint32_t F = fmix32(R ^ key.k[r]) & mask;
+      const uint32_t t = L ^ F;
+      L = R;
+      R = t;
+    }
+    x = (static_cast<uint64_t>(L) << hb) | R;
+  } while (x >= n);
+  return x;
+}
+
+// The key of epoch `epoch`'s row permutation: six 32-bit round keys from a model-independent Philox stream
+// (counter = ("SHUF", j, epoch), key = seed), and the Feistel width for `rows` rows.
+inline FeistelKey make_feistel_key(uint64_t seed, uint64_t epoch, int64_t rows) {
+  FeistelKey key{};
+  const uint32_t k0 = static_cast<uint32_t>(seed), k1 = static_cast<uint32_t>(seed >> 32);
+  const uint32_t e0 = static_cast<uint32_t>(epoch), e1 = static_cast<uint32_t>(epoch >> 32);
+  const Philox4 a = philox4x32_10(0x53485546u, 0u, e0, e1, k0, k1);
+  const Philox4 b = philox4x32_10(0x53485546u, 1u, e0, e1, k0, k1);
+  key.k[0] = a.x;
+  key.k[1] = a.y;
+  key.k[2] = a.z;
+  key.k[3] = a.w;
+  key.k[4] = b.x;
+  key.k[5] = b.y;
+  int bits = 2;
+  while ((int64_t{1} << bits) < rows) ++bits;
+  if (bits & 1) ++bits;
+  key.half_bits = static_cast<uint32_t>(bits / 2);
+  return key;
+}
+
+// dst row i = src row perm(i), every live plane; one block per row, 16-byte copies.  2 x rows x ld x 2 B of traffic.
+__global__ void permute_rows_kernel(const __nv_bfloat16* __restrict__ s0, const __nv_bfloat16* __restrict__ s1,
+                                    const __nv_bfloat16* __restrict__ s2, __nv_bfloat16* __restrict__ d0,
+                                    __nv_bfloat16* __restrict__ d1, __nv_bfloat16* __restrict__ d2, int64_t ld,
+                                    int64_t rows, FeistelKey key) {
+  const int64_t vec = ld / 8;
+  for (int64_t i = blockIdx.x; i < rows; i += gridDim.x) {
+    const int64_t j = static_cast<int64_t>(feistel_permute(static_cast<uint64_t>(i), static_cast<uint64_t>(rows), key));
+    const uint4* a = reinterpret_cast<const uint4*>(s0 + j * ld);
+    uint4* b = reinterpret_cast<uint4*>(d0 + i * ld);
+    for (int64_t c = threadIdx.x; c < vec; c += blockDim.x) b[c] = a[c];
+    if (s1 != nullptr) {
+      const uint4* a1 = reinterpret_cast<const uint4*>(s1 + j * ld);
+      const uint4* a2 = reinterpret_cast<const uint4*>(s2 + j * ld);
+      uint4* b1 = reinterpret_cast<uint4*>(d1 + i * ld);
+      uint4* b2 = reinterpret_cast<uint4*>(d2 + i * ld);
+      for (int64_t c = threadIdx.x; c < vec; c += blockDim.x) {
+        b1[c] = a1[c];
+        b2[c] = a2[c];
+      }
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------

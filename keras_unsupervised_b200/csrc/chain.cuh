@@ -42,7 +42,7 @@ struct ChainKind {
   int64_t ld_u;
   float* colsum;
   float colsum_sign;
-  int32_t epi;  // kEpiSample or kEpiProb
+  int32_t epi;  // kEpiSample / kEpiProb / kEpiRaw; with GAUSS: kEpiReluSample / kEpiGaussian / kEpiProb / kEpiRaw
   float* rowsum;
   int32_t M, N;
   uint64_t seed;
@@ -97,7 +97,10 @@ __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
 // <256, 2>: CTA pairs on 256 x 256 tiles (large minibatches).  <64, 1>: single CTAs on 128 x 64 tiles - the
 // latency-bound sizes (C1, C2), where a stage is a handful of tiles and what matters is that projections, dW and
 // their dependencies cost no launches.
-template <int BN, int CG>
+// GAUSS: the epilogue set of the Gaussian-visible mode (relu-threshold hiddens, rbm.py:58-59; v ~ N(h.W^T + b, I),
+// rbm.py:64-66; the final hidden term stays the sigmoid, rbm.py:145) - a separate instantiation, so that the
+// Bernoulli kernel's code and register allocation are exactly what they were.
+template <int BN, int CG, bool GAUSS = false>
 __global__ void __launch_bounds__(kNumThreads, 1) chain_kernel(const __grid_constant__ ChainParams p) {
   constexpr int kBNLocal = BN / CG;
   constexpr int kTileM = kBlockM * CG;
@@ -311,12 +314,23 @@ __global__ void __launch_bounds__(kNumThreads, 1) chain_kernel(const __grid_cons
         uint32_t acc[32];
         ptx::tmem_ld_32x32(tmem_base + ((quarter * 32u) << 16) + as * BN + coff, acc);
         ptx::tmem_ld_wait();
-        if (kd.epi == kEpiSample)
-          epilogue_chunk<kEpiSample>(kd, acc, row, n_blk * BN + coff, row_ok, draw, row0, lane, row_acc);
-        else if (kd.epi == kEpiProb)
-          epilogue_chunk<kEpiProb>(kd, acc, row, n_blk * BN + coff, row_ok, draw, row0, lane, row_acc);
-        else
-          epilogue_chunk<kEpiRaw>(kd, acc, row, n_blk * BN + coff, row_ok, draw, row0, lane, row_acc);
+        if constexpr (GAUSS) {
+          if (kd.epi == kEpiReluSample)
+            epilogue_chunk<kEpiReluSample>(kd, acc, row, n_blk * BN + coff, row_ok, draw, row0, lane, row_acc);
+          else if (kd.epi == kEpiGaussian)
+            epilogue_chunk<kEpiGaussian>(kd, acc, row, n_blk * BN + coff, row_ok, draw, row0, lane, row_acc);
+          else if (kd.epi == kEpiProb)
+            epilogue_chunk<kEpiProb>(kd, acc, row, n_blk * BN + coff, row_ok, draw, row0, lane, row_acc);
+          else
+            epilogue_chunk<kEpiRaw>(kd, acc, row, n_blk * BN + coff, row_ok, draw, row0, lane, row_acc);
+        } else {
+          if (kd.epi == kEpiSample)
+            epilogue_chunk<kEpiSample>(kd, acc, row, n_blk * BN + coff, row_ok, draw, row0, lane, row_acc);
+          else if (kd.epi == kEpiProb)
+            epilogue_chunk<kEpiProb>(kd, acc, row, n_blk * BN + coff, row_ok, draw, row0, lane, row_acc);
+          else
+            epilogue_chunk<kEpiRaw>(kd, acc, row, n_blk * BN + coff, row_ok, draw, row0, lane, row_acc);
+        }
       }
       ptx::tc_fence_before();
       ptx::fence_proxy_async_global();  // these stores will be read by other CTAs' TMA loads

@@ -143,6 +143,18 @@ struct DevBuf {
   }
 };
 
+// temporaries of one API call: released on every return path
+struct ScopedBufs {
+  std::vector<DevBuf> v;
+  explicit ScopedBufs(size_t n = 0) : v(n) {}
+  ScopedBufs(const ScopedBufs&) = delete;
+  ScopedBufs& operator=(const ScopedBufs&) = delete;
+  ~ScopedBufs() {
+    for (auto& b : v) b.release();  // cudaFree waits for work that still reads the buffer
+  }
+  DevBuf& operator[](size_t i) { return v[i]; }
+};
+
 struct kucd_ctx {
   int device = 0;
   int num_sms = 0;
@@ -320,11 +332,19 @@ static int grid_for(const kucd_ctx* ctx, int64_t work_items, int threads) {
 // ------------------------------------------------------------------------------------------------
 // tensors at the boundary
 // ------------------------------------------------------------------------------------------------
-static int elem_size(const kucd_tensor* t) { return t->bits / 8; }
+// bit-packed 0/1 matrix: strides[0] counts bits (a multiple of 8), column j is bit j % 8 of byte j / 8 of its row
+static bool is_packed(const kucd_tensor* t) { return t->dtype_code == KUCD_DT_UINT && t->bits == 1; }
+// bytes from one row to the next, and bytes one row occupies
+static int64_t row_pitch_bytes(const kucd_tensor* t) {
+  return is_packed(t) ? t->strides[0] / 8 : t->strides[0] * (t->bits / 8);
+}
+static int64_t row_bytes(const kucd_tensor* t) {
+  return is_packed(t) ? (t->shape[1] + 7) / 8 : t->shape[1] * (t->bits / 8);
+}
 
 static bool dtype_ok(const kucd_tensor* t) {
   return (t->dtype_code == KUCD_DT_FLOAT && t->bits == 32) || (t->dtype_code == KUCD_DT_BFLOAT && t->bits == 16) ||
-         (t->dtype_code == KUCD_DT_UINT && t->bits == 8);
+         (t->dtype_code == KUCD_DT_UINT && t->bits == 8) || is_packed(t);
 }
 
 // vectors may arrive as (n,1) with unit stride: view them as one row of n
@@ -344,8 +364,10 @@ static int check_tensor(const kucd_ctx* ctx, const kucd_tensor* t, int64_t rows,
   if (t == nullptr) return fail(KUCD_ERR_INVALID_ARG, "%s is NULL", name);
   if (t->data == nullptr && t->shape[0] * t->shape[1] != 0) return fail(KUCD_ERR_INVALID_ARG, "%s has no data", name);
   if (!dtype_ok(t))
-    return fail(KUCD_ERR_UNSUPPORTED_DTYPE, "%s: dtype code %d / %d bits is not float32, bfloat16 or uint8", name,
-                t->dtype_code, t->bits);
+    return fail(KUCD_ERR_UNSUPPORTED_DTYPE, "%s: dtype code %d / %d bits is not float32, bfloat16, uint8 or packed bits",
+                name, t->dtype_code, t->bits);
+  if (is_packed(t) && (t->strides[0] % 8 != 0 || t->strides[0] < t->shape[1]) && t->shape[0] > 1)
+    return fail(KUCD_ERR_INVALID_ARG, "%s: rows of a bit-packed matrix must start on byte boundaries", name);
   if (f32_only && !(t->dtype_code == KUCD_DT_FLOAT && t->bits == 32))
     return fail(KUCD_ERR_UNSUPPORTED_DTYPE, "%s must be float32", name);
   if (t->device_type != KUCD_DEV_CPU && t->device_type != KUCD_DEV_CUDA && t->device_type != KUCD_DEV_CUDA_HOST)
@@ -364,23 +386,21 @@ static bool on_device(const kucd_tensor* t) { return t->device_type == KUCD_DEV_
 // rows [r0, r0+n) of a caller tensor as a device pointer + row stride (elements)
 static int fetch_rows(kucd_ctx* ctx, const kucd_tensor* t, int64_t r0, int64_t n, DevBuf& staging, const void** ptr,
                       int64_t* ld) {
-  const int es = elem_size(t);
-  const char* src = static_cast<const char*>(t->data) + r0 * t->strides[0] * es;
+  const int64_t pitch = row_pitch_bytes(t), rb = row_bytes(t);
+  const char* src = static_cast<const char*>(t->data) + r0 * pitch;
   if (on_device(t)) {
     *ptr = src;
     *ld = t->strides[0];
     return KUCD_OK;
   }
-  const int64_t cols = t->shape[1];
-  KU_TRY(staging.ensure(static_cast<size_t>(n) * cols * es));
-  if (t->strides[0] == cols || n == 1)
-    CU_TRY(cudaMemcpyAsync(staging.p, src, static_cast<size_t>(n) * cols * es, cudaMemcpyHostToDevice, ctx->stream));
+  KU_TRY(staging.ensure(static_cast<size_t>(n) * rb));
+  if (pitch == rb || n == 1)
+    CU_TRY(cudaMemcpyAsync(staging.p, src, static_cast<size_t>(n) * rb, cudaMemcpyHostToDevice, ctx->stream));
   else
-    CU_TRY(cudaMemcpy2DAsync(staging.p, cols * es, src, t->strides[0] * es, cols * es, n, cudaMemcpyHostToDevice,
-                             ctx->stream));
-  ctx->tm.h2d_bytes += n * cols * es;
+    CU_TRY(cudaMemcpy2DAsync(staging.p, rb, src, pitch, rb, n, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->tm.h2d_bytes += n * rb;
   *ptr = staging.p;
-  *ld = cols;
+  *ld = is_packed(t) ? rb * 8 : t->shape[1];  // elements (bits, when packed) from one staged row to the next
   return KUCD_OK;
 }
 
@@ -400,6 +420,13 @@ static int ingest_rows(kucd_ctx* ctx, const kucd_tensor* t, int64_t r0, int64_t 
   KU_TRY(fetch_rows(ctx, t, r0, n, ctx->stage_in, &src, &ld));
   const int64_t groups = n * (dst.ld / 8);
   const int grid = grid_for(ctx, groups, 256);
+  if (is_packed(t)) {
+    ingest_bits_kernel<<<grid, 256, 0, ctx->stream>>>(static_cast<const uint8_t*>(src), ld / 8, n, t->shape[1], dst.p[0],
+                                                      dst.p[1], dst.p[2], dst.ld, nparts);
+    ctx->tm.aux_launches++;
+    CU_TRY(cudaGetLastError());
+    return KUCD_OK;
+  }
   by_dtype(t, [&](auto* tag) {
     using T = std::remove_pointer_t<decltype(tag)>;
     ingest_kernel<T><<<grid, 256, 0, ctx->stream>>>(static_cast<const T*>(src), ld, n, t->shape[1], dst.p[0], dst.p[1],
@@ -414,29 +441,34 @@ static int ingest_rows(kucd_ctx* ctx, const kucd_tensor* t, int64_t r0, int64_t 
 // device rows -> caller tensor rows [r0, r0+n)
 static int deliver_planes(kucd_ctx* ctx, const Planes& src, int64_t n, kucd_tensor* out, int64_t r0) {
   if (n == 0) return KUCD_OK;
-  const int es = elem_size(out);
+  const int64_t pitch = row_pitch_bytes(out), rb = row_bytes(out);
   const int64_t cols = out->shape[1];
-  char* dst = static_cast<char*>(out->data) + r0 * out->strides[0] * es;
+  char* dst = static_cast<char*>(out->data) + r0 * pitch;
   void* kdst = dst;
-  int64_t kld = out->strides[0];
+  int64_t kpitch = pitch;  // bytes
   if (!on_device(out)) {
-    KU_TRY(ctx->stage_out.ensure(static_cast<size_t>(n) * cols * es));
+    KU_TRY(ctx->stage_out.ensure(static_cast<size_t>(n) * rb));
     kdst = ctx->stage_out.p;
-    kld = cols;
+    kpitch = rb;
   }
-  const int grid = grid_for(ctx, n * cols, 256);
-  by_dtype(out, [&](auto* tag) {
-    using T = std::remove_pointer_t<decltype(tag)>;
-    export_kernel<T><<<grid, 256, 0, ctx->stream>>>(src.p[0], src.mid(), src.lo(), src.ld, n, cols, static_cast<T*>(kdst),
-                                                    kld);
-    return 0;
-  });
+  if (is_packed(out)) {  // 0/1 states as bits
+    export_bits_kernel<<<grid_for(ctx, n * rb, 256), 256, 0, ctx->stream>>>(src.p[0], src.ld, n, cols,
+                                                                            static_cast<uint8_t*>(kdst), kpitch);
+  } else {
+    const int grid = grid_for(ctx, n * cols, 256);
+    const int64_t kld = kpitch / (out->bits / 8);
+    by_dtype(out, [&](auto* tag) {
+      using T = std::remove_pointer_t<decltype(tag)>;
+      export_kernel<T><<<grid, 256, 0, ctx->stream>>>(src.p[0], src.mid(), src.lo(), src.ld, n, cols, static_cast<T*>(kdst),
+                                                      kld);
+      return 0;
+    });
+  }
   ctx->tm.aux_launches++;
   CU_TRY(cudaGetLastError());
   if (!on_device(out)) {
-    CU_TRY(cudaMemcpy2DAsync(dst, out->strides[0] * es, kdst, cols * es, cols * es, n, cudaMemcpyDeviceToHost,
-                             ctx->stream));
-    ctx->tm.d2h_bytes += n * cols * es;
+    CU_TRY(cudaMemcpy2DAsync(dst, pitch, kdst, rb, rb, n, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->tm.d2h_bytes += n * rb;
     CU_TRY(cudaStreamSynchronize(ctx->stream));  // stage_out is reused by the next delivery
   }
   return KUCD_OK;
@@ -444,7 +476,8 @@ static int deliver_planes(kucd_ctx* ctx, const Planes& src, int64_t n, kucd_tens
 
 static int deliver_f32(kucd_ctx* ctx, const float* src, int64_t ld, int64_t n, kucd_tensor* out, int64_t r0) {
   if (n == 0) return KUCD_OK;
-  const int es = elem_size(out);
+  if (is_packed(out)) return fail(KUCD_ERR_UNSUPPORTED_DTYPE, "real-valued outputs cannot be delivered as packed bits");
+  const int es = out->bits / 8;
   const int64_t cols = out->shape[1];
   char* dst = static_cast<char*>(out->data) + r0 * out->strides[0] * es;
   if (cols == 1 && ld == 1 && out->strides[0] == 1 && out->dtype_code == KUCD_DT_FLOAT) {  // a plain vector
@@ -807,6 +840,52 @@ static int gather_master(kucd_rbm* r) {
   return KUCD_OK;
 }
 
+// One launch of chain_kernel<BN, CG, GAUSS>.  Its CTAs (CTA pairs) wait on each other's tiles, so all of them must be
+// resident at once: one per SM (pair per TPC) at this shared-memory size, never more than the device can hold.
+template <int BN, int CG, bool GAUSS>
+static int launch_chain_kernel(kucd_ctx* ctx, const ChainParams& p, int total, bool prof, size_t* pe0) {
+  using Cfg = GemmCfg<BN / CG>;
+  auto kern = chain_kernel<BN, CG, GAUSS>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  if constexpr (CG == 1) {
+    const int grid = std::min(total, ctx->num_sms);
+    *pe0 = prof ? prof_event(ctx) : 0;
+    kern<<<grid, kNumThreads, Cfg::kSmemBytes, ctx->stream>>>(p);
+    CU_TRY(cudaGetLastError());
+  } else {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(ctx->num_sms / 2 * 2);
+    cfg.blockDim = dim3(kNumThreads);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    static int max_clusters = -1;
+    if (max_clusters < 0) {
+      int mc = 0;
+      if (cudaOccupancyMaxActiveClusters(&mc, kern, &cfg) != cudaSuccess || mc <= 0) {
+        cudaGetLastError();
+        mc = ctx->num_sms / 2;
+      }
+      max_clusters = mc;
+    }
+    const int units = std::min(total, std::min(max_clusters, ctx->num_sms / 2));
+    cfg.gridDim = dim3(units * 2);
+    *pe0 = prof ? prof_event(ctx) : 0;
+    CU_TRY(cudaLaunchKernelEx(&cfg, kern, p));
+  }
+  return KUCD_OK;
+}
+
 // The 2k+1 (+1 with persistent chains) projections of one minibatch as one persistent kernel (chain.cuh).
 // `small`: 128 x 64 tiles on single CTAs (latency-bound sizes) instead of 256 x 256 tiles on CTA pairs.
 static int launch_chain(kucd_rbm* r, const Planes& v0, int64_t batch, const kucd_hparams* hp, int64_t global_row0,
@@ -859,13 +938,16 @@ static int launch_chain(kucd_rbm* r, const Planes& v0, int64_t batch, const kucd
     q.batch_rows = 1;
     q.nseg = 1;
   };
-  kind(0, true, 0, h0.p[0], kEpiSample, r->dc(), 1.f, v0_dyn);          // h_pos from v0            rbm.py:120
-  kind(1, true, 4, hk.p[0], kEpiSample, nullptr, 0.f, false);            // first h of a stored chain (PCD)
-  kind(2, false, 1, vk.p[0], kEpiSample, nullptr, 0.f, false);           // v from h_pos             rbm.py:121-123
-  kind(3, false, 2, vk.p[0], kEpiSample, nullptr, 0.f, false);           // v from a later h
-  kind(4, false, 1, vk.p[0], kEpiSample, r->db(), -1.f, false);          // last v from h_pos (k = 1)
-  kind(5, false, 2, vk.p[0], kEpiSample, r->db(), -1.f, false);          // last v from a later h
-  kind(6, true, 3, hk.p[0], kEpiSample, nullptr, 0.f, false);            // intermediate h (CD-k)
+  // Gaussian-visible mode (rbm.py:139-145): relu-threshold hiddens, v = mean + N(0,1), final h still the sigmoid
+  const bool gaussian = r->mode == KUCD_MODE_VISIBLE_GAUSSIAN;
+  const int eh = gaussian ? kEpiReluSample : kEpiSample, ev = gaussian ? kEpiGaussian : kEpiSample;
+  kind(0, true, 0, h0.p[0], eh, r->dc(), 1.f, v0_dyn);                  // h_pos from v0            rbm.py:120
+  kind(1, true, 4, hk.p[0], eh, nullptr, 0.f, false);                    // first h of a stored chain (PCD)
+  kind(2, false, 1, vk.p[0], ev, nullptr, 0.f, false);                   // v from h_pos             rbm.py:121-123
+  kind(3, false, 2, vk.p[0], ev, nullptr, 0.f, false);                   // v from a later h
+  kind(4, false, 1, vk.p[0], ev, r->db(), -1.f, false);                  // last v from h_pos (k = 1)
+  kind(5, false, 2, vk.p[0], ev, r->db(), -1.f, false);                  // last v from a later h
+  kind(6, true, 3, hk.p[0], eh, nullptr, 0.f, false);                    // intermediate h (CD-k)
   kind(7, true, 3, hk.p[0], kEpiProb, r->dc(), -1.f, false);             // final h: probability     rbm.py:124
 
   int ns = 0;
@@ -932,55 +1014,14 @@ static int launch_chain(kucd_rbm* r, const Planes& v0, int64_t batch, const kucd
 
   const bool prof = ctx->profile && dyn == nullptr;
   size_t pe0 = 0;
-  if (small) {
-    using Cfg = GemmCfg<64>;
-    auto kern = chain_kernel<64, 1>;
-    static bool attr_set = false;
-    if (!attr_set) {
-      CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-      attr_set = true;
-    }
-    // the CTAs wait on each other's tiles: all of them must be resident (one per SM at this shared-memory size)
-    const int grid = std::min(total, ctx->num_sms);
-    pe0 = prof ? prof_event(ctx) : 0;
-    kern<<<grid, kNumThreads, Cfg::kSmemBytes, ctx->stream>>>(p);
-    CU_TRY(cudaGetLastError());
-  } else {
-    using Cfg = GemmCfg<kChainBN / 2>;
-    auto kern = chain_kernel<kChainBN, 2>;
-    static bool attr_set = false;
-    if (!attr_set) {
-      CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-      attr_set = true;
-    }
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(ctx->num_sms / 2 * 2);
-    cfg.blockDim = dim3(kNumThreads);
-    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
-    cfg.stream = ctx->stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    // The pairs wait on each other's tiles, so every pair of the grid must be resident at once: never launch more
-    // clusters than the device can hold of this kernel.
-    static int max_clusters = -1;
-    if (max_clusters < 0) {
-      int mc = 0;
-      if (cudaOccupancyMaxActiveClusters(&mc, kern, &cfg) != cudaSuccess || mc <= 0) {
-        cudaGetLastError();
-        mc = ctx->num_sms / 2;
-      }
-      max_clusters = mc;
-    }
-    const int units = std::min(total, std::min(max_clusters, ctx->num_sms / 2));
-    cfg.gridDim = dim3(units * 2);
-    pe0 = prof ? prof_event(ctx) : 0;
-    CU_TRY(cudaLaunchKernelEx(&cfg, kern, p));
-  }
+  int rc;
+  if (small)
+    rc = gaussian ? launch_chain_kernel<64, 1, true>(ctx, p, total, prof, &pe0)
+                  : launch_chain_kernel<64, 1, false>(ctx, p, total, prof, &pe0);
+  else
+    rc = gaussian ? launch_chain_kernel<kChainBN, 2, true>(ctx, p, total, prof, &pe0)
+                  : launch_chain_kernel<kChainBN, 2, false>(ctx, p, total, prof, &pe0);
+  KU_TRY(rc);
   if (prof) ctx->marks.push_back({0, pe0, prof_event(ctx), ns});
   ctx->tm.gemm_launches++;
   ctx->tm.chain_launches++;
@@ -1126,7 +1167,7 @@ static int enqueue_cd(kucd_rbm* r, const Planes& v0, int64_t batch, const kucd_h
   const int n_proj = 2 * k + 1 + (hp->persistent ? 1 : 0);
   // one persistent kernel for the whole chain when every stage fills the chip with 256 x 256 tiles
   const int64_t pair_tiles = ((batch + 255) / 256) * ((std::min(r->V, r->H) + 255) / 256);
-  const bool whole_chain = ctx->chain && r->compute == KUCD_COMPUTE_BF16 && !gaussian && inj == nullptr && v0.n == 1 &&
+  const bool whole_chain = ctx->chain && r->compute == KUCD_COMPUTE_BF16 && inj == nullptr && v0.n == 1 &&
                            (pair_tiles >= ctx->num_sms / 2 || ctx->chain_force) &&
                            (!hp->persistent || r->last_vk_parts == 1);
   // KUCD_CHAIN_DW=1 appends the dW contraction to the chain kernel as a final two-segment stage.  Measured: no gain
@@ -1139,7 +1180,7 @@ static int enqueue_cd(kucd_rbm* r, const Planes& v0, int64_t batch, const kucd_h
     return !(e != nullptr && e[0] == '0');
   }();
   const bool small_chain = !whole_chain && small_chain_env && ctx->chain && batch <= 512 &&
-                           r->compute == KUCD_COMPUTE_BF16 && !gaussian && inj == nullptr && v0.n == 1 &&
+                           r->compute == KUCD_COMPUTE_BF16 && inj == nullptr && v0.n == 1 &&
                            !r->fused_now && (!hp->persistent || r->last_vk_parts == 1);
   if (whole_chain) {
     KU_TRY(launch_chain(r, v0, batch, hp, global_row0, draw0, stride, dyn, v0_dyn, chain_dw, false));
@@ -1313,15 +1354,28 @@ int kucd_ctx_create(kucd_ctx** out, int device_id, uint64_t seed) {
   c->device = device_id;
   c->num_sms = prop.multiProcessorCount;
   c->seed = seed;
-  CU_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-  CU_TRY(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
-  CU_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-  for (int i = 0; i < 2; ++i) {
-    CU_TRY(cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
-    CU_TRY(cudaEventCreateWithFlags(&c->ev_consumed[i], cudaEventDisableTiming));
+  auto init = [&]() -> int {
+    CU_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CU_TRY(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+    CU_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      CU_TRY(cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
+      CU_TRY(cudaEventCreateWithFlags(&c->ev_consumed[i], cudaEventDisableTiming));
+    }
+    CU_TRY(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    CU_TRY(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+    CU_TRY(cudaEventCreate(&c->ev0));
+    CU_TRY(cudaEventCreate(&c->ev1));
+    return KUCD_OK;
+  };
+  const int rc = init();
+  if (rc != KUCD_OK) {
+    const std::string why = g_err;
+    kucd_ctx_destroy(c);  // tolerates the handles that were never created
+    cudaGetLastError();
+    g_err = why;
+    return rc;
   }
-  CU_TRY(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
-  CU_TRY(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
   {
     const char* sp = getenv("KUCD_SPLIT");
     c->split = !(sp != nullptr && sp[0] == '0');
@@ -1332,8 +1386,6 @@ int kucd_ctx_create(kucd_ctx** out, int device_id, uint64_t seed) {
     const char* cd = getenv("KUCD_CHAIN_DW");
     c->chain_dw = cd != nullptr && cd[0] == '1';
   }
-  CU_TRY(cudaEventCreate(&c->ev0));
-  CU_TRY(cudaEventCreate(&c->ev1));
   *out = c;
   return KUCD_OK;
 }
@@ -1341,24 +1393,30 @@ int kucd_ctx_create(kucd_ctx** out, int device_id, uint64_t seed) {
 int kucd_ctx_destroy(kucd_ctx* ctx) {
   if (ctx == nullptr) return KUCD_OK;
   cudaSetDevice(ctx->device);
-  cudaStreamSynchronize(ctx->stream);
+  if (ctx->stream != nullptr) cudaStreamSynchronize(ctx->stream);
   if (ctx->comm != nullptr && g_nccl.CommDestroy != nullptr) g_nccl.CommDestroy(ctx->comm);
   ctx->stage_in.release();
   ctx->stage_u.release();
   ctx->stage_out.release();
-  for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
-  cudaEventDestroy(ctx->ev0);
-  cudaEventDestroy(ctx->ev1);
+  auto drop_event = [](cudaEvent_t e) {
+    if (e != nullptr) cudaEventDestroy(e);
+  };
+  auto drop_stream = [](cudaStream_t s) {
+    if (s != nullptr) cudaStreamDestroy(s);
+  };
+  for (cudaEvent_t e : ctx->ev_pool) drop_event(e);
+  drop_event(ctx->ev0);
+  drop_event(ctx->ev1);
   for (int i = 0; i < 2; ++i) {
-    cudaEventDestroy(ctx->ev_copied[i]);
-    cudaEventDestroy(ctx->ev_consumed[i]);
+    drop_event(ctx->ev_copied[i]);
+    drop_event(ctx->ev_consumed[i]);
     ctx->stage_raw[i].release();
   }
-  cudaStreamDestroy(ctx->copy_stream);
-  cudaEventDestroy(ctx->ev_fork);
-  cudaEventDestroy(ctx->ev_join);
-  cudaStreamDestroy(ctx->stream2);
-  cudaStreamDestroy(ctx->stream);
+  drop_event(ctx->ev_fork);
+  drop_event(ctx->ev_join);
+  drop_stream(ctx->copy_stream);
+  drop_stream(ctx->stream2);
+  drop_stream(ctx->stream);
   delete ctx;
   return KUCD_OK;
 }
@@ -1655,6 +1713,10 @@ static int sample_api(kucd_rbm* r, bool forward, const kucd_tensor* in, kucd_ten
   const int64_t rows = in->shape[0];
   if (s_out != nullptr) KU_TRY(check_tensor(ctx, s_out, rows, N, "sample output"));
   if (p_out != nullptr) KU_TRY(check_tensor(ctx, p_out, rows, N, "probability output"));
+  if (p_out != nullptr && is_packed(p_out))
+    return fail(KUCD_ERR_UNSUPPORTED_DTYPE, "probabilities cannot be delivered as packed bits");
+  if (s_out != nullptr && is_packed(s_out) && !forward && r->mode == KUCD_MODE_VISIBLE_GAUSSIAN)
+    return fail(KUCD_ERR_UNSUPPORTED_DTYPE, "Gaussian visible units are real-valued: no packed-bit output");
   if (u != nullptr) KU_TRY(check_tensor(ctx, u, rows, N, "injected draws", true));
   const bool gaussian = r->mode == KUCD_MODE_VISIBLE_GAUSSIAN;
   const uint64_t draw = (1ull << 63) | r->infer_draws++;
@@ -1783,9 +1845,8 @@ int kucd_rbm_cd_step(kucd_rbm* r, const kucd_tensor* v_batch, const kucd_hparams
 
   // injected draws: each node's array is staged to the device up front
   StepInject si;
-  std::vector<DevBuf> keep;
+  ScopedBufs keep(inj != nullptr ? 2 * KUCD_MAX_K + 1 : 0);
   if (inj != nullptr) {
-    keep.resize(2 * KUCD_MAX_K + 1);
     int slot = 0;
     auto stage = [&](const kucd_tensor* u, int64_t cols, const float** p, int64_t* ld) -> int {
       if (u == nullptr) return KUCD_OK;
@@ -1811,7 +1872,6 @@ int kucd_rbm_cd_step(kucd_rbm* r, const kucd_tensor* v_batch, const kucd_hparams
   KU_TRY(gather_master(r));
   const bool host_in = !on_device(v_batch) || inj != nullptr;
   if (host_in) CU_TRY(cudaStreamSynchronize(ctx->stream));
-  for (auto& b : keep) b.release();
   return KUCD_OK;
 }
 
@@ -1829,7 +1889,8 @@ int kucd_rbm_score(kucd_rbm* r, const kucd_tensor* v_batch, const kucd_tensor* u
   KU_TRY(ensure_workspace(r, rows));
   Planes v0;
   KU_TRY(ingest_batch(r, v_batch, 0, rows, &v0));
-  DevBuf ku_h, ku_v;
+  ScopedBufs ku(2);
+  DevBuf &ku_h = ku[0], &ku_v = ku[1];
   const float *ph = nullptr, *pv = nullptr;
   int64_t ldh = 0, ldv = 0;
   if (u_h != nullptr) {
@@ -1848,8 +1909,6 @@ int kucd_rbm_score(kucd_rbm* r, const kucd_tensor* v_batch, const kucd_tensor* u
   kucd_step_stats st;
   KU_TRY(read_stats(r, &st, rows));
   *score_out = st.score;
-  ku_h.release();
-  ku_v.release();
   return KUCD_OK;
 }
 
@@ -1880,10 +1939,13 @@ int kucd_rbm_last_stats(kucd_rbm* r, kucd_tensor* dW, kucd_tensor* db, kucd_tens
   }
   if (v_neg != nullptr) {
     KU_TRY(check_tensor(ctx, v_neg, rows, r->V, "v_neg"));
+    if (is_packed(v_neg) && r->mode == KUCD_MODE_VISIBLE_GAUSSIAN)
+      return fail(KUCD_ERR_UNSUPPORTED_DTYPE, "Gaussian visible units are real-valued: no packed-bit output");
     KU_TRY(deliver_planes(ctx, r->vk.view(rows, r->V, r->last_vk_parts), rows, v_neg, 0));
   }
   if (h_neg != nullptr) {
     KU_TRY(check_tensor(ctx, h_neg, rows, r->H, "h_neg"));
+    if (is_packed(h_neg)) return fail(KUCD_ERR_UNSUPPORTED_DTYPE, "h_neg holds probabilities: no packed-bit output");
     KU_TRY(deliver_planes(ctx, r->hk.view(rows, r->H, r->last_hk_parts), rows, h_neg, 0));
   }
   CU_TRY(cudaStreamSynchronize(ctx->stream));
@@ -1918,6 +1980,8 @@ int kucd_rbm_get_chains(kucd_rbm* r, kucd_tensor* v_chains) {
   kucd_ctx* ctx = r->ctx;
   CU_TRY(cudaSetDevice(ctx->device));
   KU_TRY(check_tensor(ctx, v_chains, r->n_chains, r->V, "v_chains"));
+  if (is_packed(v_chains) && r->mode == KUCD_MODE_VISIBLE_GAUSSIAN)
+    return fail(KUCD_ERR_UNSUPPORTED_DTYPE, "Gaussian visible units are real-valued: no packed-bit output");
   KU_TRY(deliver_planes(ctx, r->chains.view(r->n_chains, r->V, vis_parts_out(r)), r->n_chains, v_chains, 0));
   CU_TRY(cudaStreamSynchronize(ctx->stream));
   return KUCD_OK;
@@ -1987,6 +2051,8 @@ int kucd_dataset_read(kucd_dataset* ds, kucd_tensor* out) {
   kucd_ctx* ctx = ds->ctx;
   CU_TRY(cudaSetDevice(ctx->device));
   KU_TRY(check_tensor(ctx, out, ds->rows, ds->dim, "out"));
+  if (is_packed(out) && ds->nparts != 1)
+    return fail(KUCD_ERR_UNSUPPORTED_DTYPE, "this data set holds real values: no packed-bit output");
   for (int64_t r0 = 0; r0 < ds->rows; r0 += kChunkRows) {
     const int64_t n = std::min(kChunkRows, ds->rows - r0);
     Planes src = ds->view();
@@ -1995,6 +2061,50 @@ int kucd_dataset_read(kucd_dataset* ds, kucd_tensor* out) {
     KU_TRY(deliver_planes(ctx, src, n, out, r0));
   }
   CU_TRY(cudaStreamSynchronize(ctx->stream));
+  return KUCD_OK;
+}
+
+int kucd_dataset_shuffle(kucd_dataset* in, uint64_t seed, uint64_t epoch, kucd_dataset** inout) {
+  if (in == nullptr || inout == nullptr) return fail(KUCD_ERR_INVALID_ARG, "NULL argument");
+  kucd_ctx* ctx = in->ctx;
+  CU_TRY(cudaSetDevice(ctx->device));
+  kucd_dataset* out = *inout;
+  if (out == in) return fail(KUCD_ERR_INVALID_ARG, "a data set cannot be shuffled in place");
+  if (out != nullptr && (out->ctx != ctx || out->rows != in->rows || out->dim != in->dim || out->planes.ld != in->planes.ld))
+    return fail(KUCD_ERR_SHAPE_MISMATCH, "the destination data set has another shape");
+  bool created = false;
+  if (out == nullptr) {
+    out = new (std::nothrow) kucd_dataset();
+    if (out == nullptr) return fail(KUCD_ERR_INVALID_ARG, "out of host memory");
+    out->ctx = ctx;
+    out->rows = in->rows;
+    out->dim = in->dim;
+    created = true;
+  }
+  int rc = KUCD_OK;
+  if (created || out->nparts < in->nparts)
+    rc = out->planes.ensure(std::max<int64_t>(in->rows, 1), in->planes.ld, in->nparts);
+  if (rc == KUCD_OK && in->rows > 0) {
+    const FeistelKey key = make_feistel_key(seed, epoch, in->rows);
+    const bool three = in->nparts == 3;
+    const int grid = static_cast<int>(std::min<int64_t>(in->rows, static_cast<int64_t>(ctx->num_sms) * 16));
+    permute_rows_kernel<<<grid, 128, 0, ctx->stream>>>(
+        in->planes.buf[0].as<__nv_bfloat16>(), three ? in->planes.buf[1].as<__nv_bfloat16>() : nullptr,
+        three ? in->planes.buf[2].as<__nv_bfloat16>() : nullptr, out->planes.buf[0].as<__nv_bfloat16>(),
+        three ? out->planes.buf[1].as<__nv_bfloat16>() : nullptr, three ? out->planes.buf[2].as<__nv_bfloat16>() : nullptr,
+        in->planes.ld, in->rows, key);
+    ctx->tm.aux_launches++;
+    if (cudaGetLastError() != cudaSuccess) rc = fail(KUCD_ERR_CUDA, "permute_rows_kernel launch failed");
+  }
+  if (rc != KUCD_OK) {
+    if (created) {
+      out->planes.release();
+      delete out;
+    }
+    return rc;
+  }
+  out->nparts = in->nparts;
+  *inout = out;
   return KUCD_OK;
 }
 
@@ -2129,7 +2239,8 @@ int kucd_rbm_fit_host(kucd_rbm* r, const kucd_tensor* V_all, int64_t batch, cons
   KU_TRY(ensure_workspace(r, batch));
   if (hp->persistent) KU_TRY(ensure_chains(r, std::min(batch, N)));
   choose_exchange(r, batch);
-  const int es = elem_size(V_all);
+  const int64_t pitch = row_pitch_bytes(V_all), rb = row_bytes(V_all);  // source row pitch / staged row size (bytes)
+  const bool packed = is_packed(V_all);
   const int64_t cols = r->V;
   const bool x3 = r->compute == KUCD_COMPUTE_F32X3;
   const int nplanes = x3 ? 3 : 1;
@@ -2146,7 +2257,7 @@ int kucd_rbm_fit_host(kucd_rbm* r, const kucd_tensor* V_all, int64_t batch, cons
   if (zero_copy) {
     KU_TRY(r->vin2.ensure(r->cap, r->ldV, nplanes));
   } else {
-    for (int i = 0; i < 2; ++i) KU_TRY(ctx->stage_raw[i].ensure(static_cast<size_t>(batch) * cols * es));
+    for (int i = 0; i < 2; ++i) KU_TRY(ctx->stage_raw[i].ensure(static_cast<size_t>(batch) * rb));
   }
   float* host_stats = nullptr;
   if (step_recon != nullptr) CU_TRY(cudaMallocHost(&host_stats, steps * sizeof(float)));
@@ -2154,8 +2265,15 @@ int kucd_rbm_fit_host(kucd_rbm* r, const kucd_tensor* V_all, int64_t batch, cons
   const int live = (x3 && V_all->dtype_code == KUCD_DT_FLOAT) ? 3 : 1;
   auto rows_of_step = [&](int64_t i) { return std::min(batch, N - i * batch); };
   auto slot_planes = [&](int slot, int64_t n) { return (slot == 0 ? r->vin : r->vin2).view(n, r->V, nplanes); };
+  // src_ld: elements (bits, when packed) from one source row to the next
   auto ingest = [&](const void* src, int64_t src_ld, int64_t n, const Planes& dst, cudaStream_t st) {
     const int grid = grid_for(ctx, n * (dst.ld / 8), 256);
+    if (packed) {
+      ingest_bits_kernel<<<grid, 256, 0, st>>>(static_cast<const uint8_t*>(src), src_ld / 8, n, cols, dst.p[0], dst.p[1],
+                                               dst.p[2], dst.ld, nplanes);
+      ctx->tm.aux_launches++;
+      return;
+    }
     by_dtype(V_all, [&](auto* tag) {
       using T = std::remove_pointer_t<decltype(tag)>;
       ingest_kernel<T><<<grid, 256, 0, st>>>(static_cast<const T*>(src), src_ld, n, cols, dst.p[0], dst.p[1], dst.p[2],
@@ -2167,25 +2285,24 @@ int kucd_rbm_fit_host(kucd_rbm* r, const kucd_tensor* V_all, int64_t batch, cons
   auto copy_in = [&](int64_t i) -> int {
     const int slot = static_cast<int>(i & 1);
     if (i >= 2) CU_TRY(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_consumed[slot], 0));
-    const char* src = static_cast<const char*>(V_all->data) + i * batch * V_all->strides[0] * es;
+    const char* src = static_cast<const char*>(V_all->data) + i * batch * pitch;
     const int64_t n = rows_of_step(i);
     if (zero_copy) {
       ingest(src, V_all->strides[0], n, slot_planes(slot, n), ctx->copy_stream);
       CU_TRY(cudaGetLastError());
-    } else if (V_all->strides[0] == cols) {  // contiguous rows: one linear DMA
-      CU_TRY(cudaMemcpyAsync(ctx->stage_raw[slot].p, src, static_cast<size_t>(n) * cols * es, cudaMemcpyHostToDevice,
+    } else if (pitch == rb) {  // contiguous rows: one linear DMA
+      CU_TRY(cudaMemcpyAsync(ctx->stage_raw[slot].p, src, static_cast<size_t>(n) * rb, cudaMemcpyHostToDevice,
                              ctx->copy_stream));
     } else {
-      CU_TRY(cudaMemcpy2DAsync(ctx->stage_raw[slot].p, cols * es, src, V_all->strides[0] * es, cols * es, n,
-                               cudaMemcpyHostToDevice, ctx->copy_stream));
+      CU_TRY(cudaMemcpy2DAsync(ctx->stage_raw[slot].p, rb, src, pitch, rb, n, cudaMemcpyHostToDevice, ctx->copy_stream));
     }
     CU_TRY(cudaEventRecord(ctx->ev_copied[slot], ctx->copy_stream));
-    ctx->tm.h2d_bytes += n * cols * es;
+    ctx->tm.h2d_bytes += n * rb;
     return KUCD_OK;
   };
   int rc = KUCD_OK;
-  CU_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
-  rc = copy_in(0);
+  if (cudaEventRecord(ctx->ev0, ctx->stream) != cudaSuccess) rc = fail(KUCD_ERR_CUDA, "event record failed");
+  if (rc == KUCD_OK) rc = copy_in(0);
   for (int64_t i = 0; i < steps && rc == KUCD_OK; ++i) {
     const int slot = static_cast<int>(i & 1);
     const int64_t n = rows_of_step(i);
@@ -2197,7 +2314,7 @@ int kucd_rbm_fit_host(kucd_rbm* r, const kucd_tensor* V_all, int64_t batch, cons
     }
     Planes v0 = zero_copy ? slot_planes(slot, n) : r->vin.view(n, r->V, nplanes);
     if (!zero_copy) {
-      ingest(ctx->stage_raw[slot].p, cols, n, v0, ctx->stream);
+      ingest(ctx->stage_raw[slot].p, packed ? rb * 8 : cols, n, v0, ctx->stream);
       cudaEventRecord(ctx->ev_consumed[slot], ctx->stream);  // the raw staging slot is free again
     }
     v0.n = live;

@@ -10,7 +10,8 @@ minibatch is the remaining rows, `transform`/`inv_transform` stay methods, `get_
 
 `hps` keeps the reference's keys `batch_size`, `epochs`, `lr` (rbm.py:46,110,113,128).  Optional keys,
 whose defaults reproduce the reference: `k` (1), `persistent` (False), `momentum` (0), `weight_decay`
-(0), `normalize` ('sum' | 'mean'), `dtype` ('float32' = fp32-grade three-term contractions | 'bf16'),
+(0), `normalize` ('sum' | 'mean'), `shuffle` (False; True: a fresh keyed row permutation per epoch, `shuffle_seed`),
+`dtype` ('float32' = fp32-grade three-term contractions | 'bf16'),
 `compat` ('fused': one chain updates W, b, c | 'reference': the three sequential single-parameter
 runs + per-step score of rbm.py:214-234), `seed` (42), `score_every` (0: once per epoch).
 
@@ -23,6 +24,7 @@ import math
 import numpy as np
 
 from .. import _lib as L
+from ..data import PackedBits
 from ..engine import Context, Dataset, Machine
 from ..parallel import shard_rows
 
@@ -60,6 +62,7 @@ class RBM(object):
         self.input_shape = None
         self.output_shape = None
         self.history = []
+        self._epochs_done = 0  # epochs trained so far: numbers the shuffling permutations
         if input_shape is not None:
             self.build((None,) + tuple(input_shape))
         elif input_dim is not None:
@@ -170,7 +173,7 @@ class RBM(object):
             extra["chains"] = self._machine.get_chains(st["n_chains"])
         np.savez(path, rbm_weight=W, rbm_hidden_bias=c, rbm_visible_bias=b, seed=np.uint64(st["seed"]),
                  step_count=np.uint64(st["step_count"]), mode=np.int64(self.mode), output_dim=np.int64(self.output_dim),
-                 **extra)
+                 epochs_done=np.int64(self._epochs_done), **extra)
 
     def load(self, path):
         z = np.load(path if str(path).endswith(".npz") else str(path) + ".npz")
@@ -181,6 +184,8 @@ class RBM(object):
                                                                                (self._machine.V, self._machine.H)))
         self._machine.set_params(z["rbm_weight"], z["rbm_visible_bias"], z["rbm_hidden_bias"])
         self._machine.set_seed(int(z["seed"]), int(z["step_count"]))
+        if "epochs_done" in z.files:
+            self._epochs_done = int(z["epochs_done"])
         if "chains" in z.files:
             self._machine.set_chains(z["chains"])
             self._chains_set = int(z["chains"].shape[0])
@@ -190,22 +195,23 @@ class RBM(object):
     def _wrap(self, out):
         return [out] if self.return_list else out
 
-    def transform(self, v, u=None):
-        """rbm.py:88-89 -> transform_func (:45-48): h = 1[u < sigmoid(v.W + c)], sampled, float32."""
+    def transform(self, v, u=None, out_dtype=None):
+        """rbm.py:88-89 -> transform_func (:45-48): h = 1[u < sigmoid(v.W + c)], sampled, float32.
+        out_dtype='bits' returns the states as data.PackedBits (one bit per unit)."""
         v = _unwrap(v)
         self._ensure_built(v)
         if isinstance(v, Dataset):
             return self._machine.transform_dataset(v)
-        return self._wrap(self._machine.transform(v, u=u))
+        return self._wrap(self._machine.transform(v, u=u, out_dtype=out_dtype))
 
-    def inv_transform(self, h, u=None):
+    def inv_transform(self, h, u=None, out_dtype=None):
         """rbm.py:91-92 -> inv_transform_func (:51-54 / :64-67)."""
         h = _unwrap(h)
         if not self.built:
             raise ValueError("inv_transform needs a built RBM (the visible dimension is unknown)")
         if isinstance(h, Dataset):
             return self._machine.inv_transform_dataset(h)
-        return self._wrap(self._machine.inv_transform(h, u=u))
+        return self._wrap(self._machine.inv_transform(h, u=u, out_dtype=out_dtype))
 
     def cal_free_energy(self, v):
         """rbm.py:97-98 -> free_energy_func (:73-76)."""
@@ -250,16 +256,19 @@ class RBM(object):
         if hps.get("persistent", False) and m.ctx is not None:
             self._ensure_chains(batch)
         if compat == "reference":
-            return self._fit_reference(np.asarray(V, dtype=np.float32), batch, epochs, verbose)
+            dense = V.to_dense() if isinstance(V, PackedBits) else np.asarray(V, dtype=np.float32)
+            return self._fit_reference(dense, batch, epochs, verbose)
         if compat != "fused":
             raise ValueError("hps['compat'] must be 'fused' or 'reference'")
+        shuffle = bool(hps.get("shuffle", False))  # extension: the reference walks the rows in order (rbm.py:218)
 
         if isinstance(V, Dataset):
             ds, local_batch, row0, owns = V, batch, 0, False
         else:
             local, local_batch, row0 = self._shard(V, batch)
-            on_host = not (L._is_torch(local) and local.is_cuda)
-            if epochs == 1 and on_host and hps.get("stream", True):
+            raw = local.data if isinstance(local, PackedBits) else local
+            on_host = not (L._is_torch(raw) and raw.is_cuda)
+            if epochs == 1 and on_host and hps.get("stream", True) and not shuffle:
                 # a single pass: stream the minibatches from host memory, copies overlapped with the chains
                 if verbose == 1:
                     print(1, "/", epochs, " epochs", end="\r")
@@ -276,13 +285,22 @@ class RBM(object):
         n_rows = ds.shape[0]
         num_step = int(math.ceil(n_rows / local_batch)) if n_rows else 0
         hp = self._hparams()
+        # hps['shuffle']: every epoch trains on the rows in a fresh keyed pseudo-random order (a device-side gather into
+        # one reused buffer, so the captured step graph survives).  Under data parallelism each rank permutes its own
+        # shard: global minibatch i is then made of every rank's i-th shuffled slice.
+        order = None
         try:
             for k in range(epochs):
                 if verbose == 1:
                     print(k + 1, "/", epochs, " epochs", end="\r")  # rbm.py:115
                 want = bool(verbose)
                 hp.want_stats = int(want)
-                st = m.fit_epoch(ds, local_batch, hp, global_row0=row0, want_stats=True)
+                cur = ds
+                if shuffle:
+                    order = ds.shuffled(int(hps.get("shuffle_seed", self.seed)), self._epochs_done, into=order)
+                    cur = order
+                st = m.fit_epoch(cur, local_batch, hp, global_row0=row0, want_stats=True)
+                self._epochs_done += 1
                 st["epoch"] = k + 1
                 self.history.append(st)
                 if want:
@@ -290,6 +308,8 @@ class RBM(object):
                     print("\n{0:d}/{1:d}, score: {2:f}".format(num_step, num_step, st["last_score"]))
         finally:
             m.ctx.sync()
+            if order is not None:
+                order.close()
             if owns:
                 ds.close()
         return self

@@ -11,10 +11,18 @@ import weakref
 import numpy as np
 
 from . import _lib as L
+from .data import PackedBits
 
 
 def _out_like(x, rows: int, cols: int, dtype=None):
-    """Allocate the output next to the input: numpy in -> numpy out, torch in -> torch out (same device)."""
+    """Allocate the output next to the input: numpy in -> numpy out, torch in -> torch out (same device);
+    dtype="bits": a host PackedBits (0/1 states, one bit per unit)."""
+    if isinstance(dtype, str):
+        if dtype != "bits":
+            raise ValueError("out_dtype must be a numpy / torch dtype or 'bits'")
+        return PackedBits(np.empty((rows, (cols + 7) // 8), dtype=np.uint8), cols)
+    if isinstance(x, PackedBits):
+        x = x.data
     if L._is_torch(x):
         import torch
 
@@ -24,6 +32,8 @@ def _out_like(x, rows: int, cols: int, dtype=None):
 
 def _sync_producer(x) -> None:
     """Device tensors are produced on the caller's stream; the engine reads them on its own."""
+    if isinstance(x, PackedBits):
+        x = x.data
     if L._is_torch(x) and x.is_cuda:
         import torch
 
@@ -127,6 +137,22 @@ class Dataset:
         r, d = C.c_int64(), C.c_int64()
         L.check(self.ctx.lib.kucd_dataset_shape(self.handle, C.byref(r), C.byref(d)))
         return (r.value, d.value)
+
+    def shuffled(self, seed: int, epoch: int, into: "Dataset | None" = None) -> "Dataset":
+        """The rows in the pseudo-random order of (seed, epoch) - include/kucd.h:kucd_dataset_shuffle.  `into`
+        (a data set this method returned earlier) is overwritten instead of allocating a new one."""
+        h = C.c_void_p(into.handle.value) if into is not None else C.c_void_p()
+        L.check(self.ctx.lib.kucd_dataset_shuffle(self.handle, C.c_uint64(seed), C.c_uint64(epoch), C.byref(h)))
+        return into if into is not None else Dataset(self.ctx, h)
+
+    def packed(self) -> PackedBits:
+        """A 0/1 data set read back one bit per unit."""
+        rows, dim = self.shape
+        out = PackedBits(np.empty((rows, (dim + 7) // 8), dtype=np.uint8), dim)
+        keep: list = []
+        t = L.tensor_of(out, keep)
+        L.check(self.ctx.lib.kucd_dataset_read(self.handle, C.byref(t)))
+        return out
 
     def numpy(self) -> np.ndarray:
         rows, dim = self.shape

@@ -27,6 +27,9 @@ def shard_rows(V, batch_size: int, rank: int, world: int):
     n_rows, dim = V.shape
     b = local_batch(batch_size, n_rows, world)
     full = n_rows // batch_size
+    if type(V).__name__ == "PackedBits":  # rows are byte strings: shard the byte matrix, keep the column count
+        data, _, row0 = shard_rows(V.data, batch_size, rank, world)
+        return type(V)(data, V.n_cols), b, row0
     parts = []
     if full:
         parts.append(V[:full * batch_size].reshape(full, world, b, dim)[:, rank].reshape(full * b, dim))

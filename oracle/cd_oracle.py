@@ -128,6 +128,74 @@ def draw_id(kind: str, n: int = 0, phase: int = 0) -> int:
 
 
 # --------------------------------------------------------------------------------------------
+# epoch shuffling (an extension; the reference never shuffles, rbm.py:218) and bit-packed data
+# --------------------------------------------------------------------------------------------
+def _fmix32(h):
+    """murmur3's 32-bit finaliser on uint64 arrays holding 32-bit values."""
+    h = h & _MASK
+    h ^= h >> np.uint64(16)
+    h = (h * np.uint64(0x85EBCA6B)) & _MASK
+    h ^= h >> np.uint64(13)
+    h = (h * np.uint64(0xC2B2AE35)) & _MASK
+    h ^= h >> np.uint64(16)
+    return h
+
+
+def feistel_keys(seed: int, epoch: int):
+    """Six round keys: Philox4x32-10(counter = (0x53485546 'SHUF', j, epoch lo, epoch hi), key = seed), j = 0, 1."""
+    words = []
+    for j in (0, 1):
+        x = philox4x32_10(np.uint64(0x53485546), np.uint64(j), np.uint64(epoch & 0xFFFFFFFF),
+                          np.uint64((epoch >> 32) & 0xFFFFFFFF), seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+        words += [int(w) for w in x]
+    return words[:6]
+
+
+def feistel_permutation(n: int, seed: int, epoch: int) -> np.ndarray:
+    """perm[i] = source row of shuffled row i (include/kucd.h:kucd_dataset_shuffle): a 6-round balanced Feistel
+    network over the smallest even-width power of two >= n, round function fmix32(R ^ k_r), walked until the value
+    lands below n (cycle walking: the restriction of a bijection of [0, 2^w) to [0, n) stays a bijection)."""
+    if n <= 0:
+        return np.zeros(0, dtype=np.int64)
+    bits = 2
+    while (1 << bits) < n:
+        bits += 1
+    bits += bits & 1
+    hb = np.uint64(bits // 2)
+    mask = np.uint64((1 << (bits // 2)) - 1)
+    keys = [np.uint64(k) for k in feistel_keys(seed, epoch)]
+    x = np.arange(n, dtype=np.uint64)
+    todo = np.ones(n, dtype=bool)  # every index takes at least one pass
+    while todo.any():
+        v = x[todo]
+        L, R = (v >> hb) & mask, v & mask
+        for k in keys:
+            L, R = R, L ^ (_fmix32(R ^ k) & mask)
+        v = (L << hb) | R
+        x[todo] = v
+        todo[todo] = v >= np.uint64(n)
+    return x.astype(np.int64)
+
+
+def pack_bits(x) -> np.ndarray:
+    """0/1 matrix -> bytes, column j = bit j % 8 of byte j // 8 (the layout of include/kucd.h's packed tensors)."""
+    x = np.asarray(x)
+    rows, cols = x.shape
+    out = np.zeros((rows, (cols + 7) // 8), dtype=np.uint8)
+    for j in range(cols):
+        out[:, j // 8] |= ((x[:, j] != 0).astype(np.uint8) << np.uint8(j % 8))
+    return out
+
+
+def unpack_bits(packed, cols: int) -> np.ndarray:
+    packed = np.asarray(packed, dtype=np.uint8)
+    out = np.zeros((packed.shape[0], cols), dtype=np.float32)
+    for j in range(cols):
+        out[:, j] = (packed[:, j // 8] >> np.uint8(j % 8)) & np.uint8(1)
+    return out
+
+
+# --------------------------------------------------------------------------------------------
 # elementwise maths in the working precision (float32 like K.floatx(), rbm.py:39)
 # --------------------------------------------------------------------------------------------
 def sigmoid(x):
