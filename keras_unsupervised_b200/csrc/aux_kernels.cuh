@@ -50,11 +50,24 @@ __global__ void ingest_kernel(const T* __restrict__ src, int64_t src_ld, int64_t
        g += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int64_t r = g / groups_per_row, c0 = (g % groups_per_row) * 8;
     __align__(16) __nv_bfloat16 h[8], m[8], l[8];
+    float x[8];
+    const T* row = src + r * src_ld + c0;
+    if (sizeof(T) == 1 && c0 + 8 <= cols && (reinterpret_cast<uintptr_t>(row) & 7u) == 0) {
+      // uint8 input: the group's eight bytes in one load (eight byte loads per thread made this kernel LSU-bound)
+      const uint2 q = __ldg(reinterpret_cast<const uint2*>(row));
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        x[j] = static_cast<float>((q.x >> (8 * j)) & 0xFFu);
+        x[4 + j] = static_cast<float>((q.y >> (8 * j)) & 0xFFu);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[j] = (c0 + j < cols) ? load_as_float<T>(row + j) : 0.f;
+    }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float x = (c0 + j < cols) ? load_as_float<T>(src + r * src_ld + c0 + j) : 0.f;
-      split3(x, h[j], m[j], l[j]);
-      bad |= (__bfloat162float(h[j]) != x);
+      split3(x[j], h[j], m[j], l[j]);
+      bad |= (__bfloat162float(h[j]) != x[j]);
     }
     *reinterpret_cast<uint4*>(hi + r * ld + c0) = *reinterpret_cast<const uint4*>(h);
     if (nparts == 3) {
@@ -94,39 +107,73 @@ __host__ __device__ __forceinline__ uint32_t bf16x8_to_bits(const Bf16x8& v, int
   return b;
 }
 
-// Packed rows -> bf16 planes.  One source byte (8 columns = one 16-byte store) per thread; 1/8 B read + 2 B written
-// per unit, against 4 + 2 B for float32 input: a binary data set crosses PCIe and HBM 32x smaller than as float32.
+// Packed rows -> bf16 planes.  One source byte (8 columns = one 16-byte store) per thread and iteration, four
+// iterations' loads in flight; 1/8 B read + 2 B written per unit, against 4 + 2 B for float32 input: a binary data
+// set crosses PCIe and HBM 32x smaller than as float32.
 __global__ void ingest_bits_kernel(const uint8_t* __restrict__ src, int64_t src_pitch, int64_t rows, int64_t cols,
                                    __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ mid,
                                    __nv_bfloat16* __restrict__ lo, int64_t ld, int nparts) {
   const int64_t groups_per_row = ld / 8;
   const int64_t total = rows * groups_per_row;
-  for (int64_t g = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; g < total;
-       g += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int64_t r = g / groups_per_row, c0 = (g % groups_per_row) * 8;
-    const int64_t left = cols - c0;  // columns of this group that exist
-    const uint32_t b = left > 0 ? __ldg(src + r * src_pitch + (c0 >> 3)) : 0u;
-    const Bf16x8 v = bits_to_bf16x8(b, left >= 8 ? 8 : static_cast<int>(left));
-    *reinterpret_cast<uint4*>(hi + r * ld + c0) = make_uint4(v.w[0], v.w[1], v.w[2], v.w[3]);
-    if (nparts == 3) {
-      *reinterpret_cast<uint4*>(mid + r * ld + c0) = make_uint4(0u, 0u, 0u, 0u);
-      *reinterpret_cast<uint4*>(lo + r * ld + c0) = make_uint4(0u, 0u, 0u, 0u);
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t g0 = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; g0 < total; g0 += 4 * stride) {
+    uint32_t b[4];
+    int64_t off[4];
+    int valid[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t g = g0 + u * stride;
+      b[u] = 0u;
+      valid[u] = -1;  // -1: no such group
+      if (g < total) {
+        const int64_t r = g / groups_per_row, c0 = (g % groups_per_row) * 8;
+        const int64_t left = cols - c0;  // columns of this group that exist
+        if (left > 0) b[u] = __ldg(src + r * src_pitch + (c0 >> 3));
+        valid[u] = left >= 8 ? 8 : (left > 0 ? static_cast<int>(left) : 0);
+        off[u] = r * ld + c0;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (valid[u] < 0) continue;
+      const Bf16x8 v = bits_to_bf16x8(b[u], valid[u]);
+      *reinterpret_cast<uint4*>(hi + off[u]) = make_uint4(v.w[0], v.w[1], v.w[2], v.w[3]);
+      if (nparts == 3) {
+        *reinterpret_cast<uint4*>(mid + off[u]) = make_uint4(0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(lo + off[u]) = make_uint4(0u, 0u, 0u, 0u);
+      }
     }
   }
 }
 
-// 0/1 state plane -> packed rows; one destination byte per thread
+// 0/1 state plane -> packed rows; one destination byte per thread and iteration, four 16-byte loads in flight
 __global__ void export_bits_kernel(const __nv_bfloat16* __restrict__ hi, int64_t ld, int64_t rows, int64_t cols,
                                    uint8_t* __restrict__ dst, int64_t dst_pitch) {
   const int64_t bytes_per_row = (cols + 7) / 8;
   const int64_t total = rows * bytes_per_row;
-  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int64_t r = i / bytes_per_row, c0 = (i % bytes_per_row) * 8;
-    const uint4 q = *reinterpret_cast<const uint4*>(hi + r * ld + c0);  // ld is a multiple of 64: in bounds, aligned
-    const Bf16x8 v{{q.x, q.y, q.z, q.w}};
-    const int64_t left = cols - c0;
-    dst[r * dst_pitch + (c0 >> 3)] = static_cast<uint8_t>(bf16x8_to_bits(v, left >= 8 ? 8 : static_cast<int>(left)));
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i0 = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i0 < total; i0 += 4 * stride) {
+    uint4 q[4];
+    int64_t out[4];
+    int valid[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t i = i0 + u * stride;
+      valid[u] = -1;
+      if (i < total) {
+        const int64_t r = i / bytes_per_row, c0 = (i % bytes_per_row) * 8;
+        q[u] = *reinterpret_cast<const uint4*>(hi + r * ld + c0);  // ld is a multiple of 64: in bounds, aligned
+        const int64_t left = cols - c0;
+        valid[u] = left >= 8 ? 8 : static_cast<int>(left);
+        out[u] = r * dst_pitch + (c0 >> 3);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (valid[u] < 0) continue;
+      const Bf16x8 v{{q[u].x, q[u].y, q[u].z, q[u].w}};
+      dst[out[u]] = static_cast<uint8_t>(bf16x8_to_bits(v, valid[u]));
+    }
   }
 }
 

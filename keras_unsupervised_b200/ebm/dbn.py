@@ -21,6 +21,15 @@ MODE_VISIBLE_GAUSSIAN = 1
 MODE_COMPLEX = 2  # TODO
 
 
+def _visible_dim(layer):
+    """A layer's input dimension if it is known yet (a Keras Layer's `input_shape` raises until the layer is called)."""
+    n = getattr(layer, "_n_visible", None)
+    if n is not None:
+        return int(n)
+    shape = getattr(layer, "input_shape", None)
+    return int(shape[1]) if shape else None
+
+
 class DBN(object):
     """Deep belief network."""
 
@@ -29,7 +38,7 @@ class DBN(object):
         if hasattr(self, "_rbm_layers"):
             prev = self._rbm_layers[-1]
             prev_out = prev.output_dim
-            next_in = rbm_layer.input_shape[1] if getattr(rbm_layer, "input_shape", None) else None
+            next_in = _visible_dim(rbm_layer)
             if next_in is not None and int(prev_out) != int(next_in):
                 raise ValueError("A previous RBM layer's output dimension must"
                                  + "be equal to a next one's input dimension.")  # dbn.py:29-30
@@ -94,7 +103,7 @@ class DBN(object):
         configs = []
         for i, layer in enumerate(self._rbm_layers):
             cfg = layer.get_config()
-            cfg["input_dim"] = int(layer.input_shape[1]) if layer.input_shape else None
+            cfg["input_dim"] = _visible_dim(layer)
             configs.append(cfg)
             if layer.built:
                 layer.save(os.path.join(directory, "layer%d.npz" % i))

@@ -20,6 +20,7 @@ Every array method calls libkucd.so; nothing is computed in Python and there is 
 from __future__ import annotations
 
 import math
+import os
 
 import numpy as np
 
@@ -34,6 +35,25 @@ MODE_VISIBLE_GAUSSIAN = 1
 MODE_COMPLEX = 2  # TODO in the reference as well
 
 
+def _keras_layer_base():
+    """The reference's RBM is a Keras Layer (rbm.py:19: `class RBM(Layer)`), so that it can sit inside a
+    `tf.keras.Model` (examples/rbm/rbm_softmax_mnist.py:48-64).  When TensorFlow is importable the class below
+    subclasses `tf.keras.layers.Layer` too; otherwise it is a plain object with the same surface.
+    KUCD_KERAS=0 forces the plain class."""
+    if os.environ.get("KUCD_KERAS", "1") == "0":
+        return object
+    try:
+        import tensorflow as tf
+
+        return tf.keras.layers.Layer
+    except Exception:  # not installed, or broken: the engine itself never needs TensorFlow
+        return object
+
+
+_Base = _keras_layer_base()
+IS_KERAS_LAYER = _Base is not object
+
+
 def _unwrap(x):
     """K.function takes and returns lists of one array (rbm.py:89,211,230); accept both."""
     if isinstance(x, (list, tuple)) and len(x) == 1:
@@ -41,26 +61,35 @@ def _unwrap(x):
     return x
 
 
-class RBM(object):
+class RBM(_Base):
     """Restricted Boltzmann machine with the reference's API."""
 
     def __init__(self, hps, output_dim, name=None, mode=MODE_VISIBLE_GAUSSIAN, **kwargs):
-        self.hps = hps
-        self.output_dim = output_dim
-        self.name = name
-        self.mode = mode
         if mode not in (MODE_VISIBLE_BERNOULLI, MODE_VISIBLE_GAUSSIAN):
             raise ValueError("mode must be MODE_VISIBLE_BERNOULLI or MODE_VISIBLE_GAUSSIAN "
                              "(MODE_COMPLEX is a TODO in the reference, rbm.py:16,68-70)")
-        self._context = kwargs.pop("context", None)
-        self.return_list = kwargs.pop("return_list", True)
+        context = kwargs.pop("context", None)
+        return_list = kwargs.pop("return_list", True)
         input_shape = kwargs.pop("input_shape", None)
         input_dim = kwargs.pop("input_dim", None)
+        if IS_KERAS_LAYER:
+            # rbm.py:25-27 with defect D6 resolved: the name goes through the base class (a Layer's `name`,
+            # `input_shape`, `output_shape` are read-only properties and are never assigned here)
+            super().__init__(name=name, **kwargs)
+        else:
+            self.name = name
+            self.built = False
+            self.input_shape = None
+            self.output_shape = None
+        self.hps = hps
+        self.output_dim = output_dim
+        self.mode = mode
+        self._context = context
+        self.return_list = return_list
         self._kwargs = kwargs
-        self.built = False
         self._machine = None
-        self.input_shape = None
-        self.output_shape = None
+        self._n_visible = None
+        self._keras_vars = None  # (rbm_weight, rbm_hidden_bias, rbm_visible_bias) Keras variables, Layer mode only
         self.history = []
         self._epochs_done = 0  # epochs trained so far: numbers the shuffling permutations
         if input_shape is not None:
@@ -82,14 +111,40 @@ class RBM(object):
             raise ValueError("hps['dtype'] must be 'float32' or 'bf16'")
         seed = self.seed
         self._machine = Machine(ctx, n_visible, int(self.output_dim), int(self.mode), compute, seed=seed)
-        rng = np.random.default_rng(seed)
-        W = rng.uniform(-0.05, 0.05, (n_visible, int(self.output_dim))).astype(np.float32)
-        b = rng.uniform(-0.05, 0.05, n_visible).astype(np.float32)
-        c = rng.uniform(-0.05, 0.05, int(self.output_dim)).astype(np.float32)
+        if IS_KERAS_LAYER:
+            # the reference's variables, under its names (rbm.py:30-40); the engine trains its own copies on the GPU and
+            # writes them back after every fit (_to_keras), so Model.save / save_weights see the trained values
+            kW = self.add_weight(name="rbm_weight", shape=(n_visible, int(self.output_dim)), initializer="uniform",
+                                 trainable=True)
+            kc = self.add_weight(name="rbm_hidden_bias", shape=(int(self.output_dim),), initializer="uniform",
+                                 trainable=True)
+            kb = self.add_weight(name="rbm_visible_bias", shape=(n_visible,), initializer="uniform", trainable=False)
+            self._keras_vars = (kW, kc, kb)
+            W, c, b = (np.asarray(v.numpy(), dtype=np.float32) for v in self._keras_vars)
+        else:
+            rng = np.random.default_rng(seed)
+            W = rng.uniform(-0.05, 0.05, (n_visible, int(self.output_dim))).astype(np.float32)
+            b = rng.uniform(-0.05, 0.05, n_visible).astype(np.float32)
+            c = rng.uniform(-0.05, 0.05, int(self.output_dim)).astype(np.float32)
+            self.input_shape = (None, n_visible)
+            self.output_shape = (None, int(self.output_dim))
         self._machine.set_params(W, b, c)
-        self.input_shape = (None, n_visible)
-        self.output_shape = (None, int(self.output_dim))
+        self._n_visible = n_visible
         self.built = True
+
+    def _to_keras(self):
+        """engine -> Keras variables (Layer mode): after training, before a Keras save."""
+        if self._keras_vars is not None:
+            W, b, c = self._machine.get_params()
+            for var, val in zip(self._keras_vars, (W, c, b)):
+                var.assign(val)
+
+    def sync_from_keras(self):
+        """Keras variables -> engine (Layer mode): after `Model.load_weights`, which writes the variables directly."""
+        if self._keras_vars is not None:
+            W, c, b = (np.asarray(v.numpy(), dtype=np.float32) for v in self._keras_vars)
+            self._machine.set_params(W, b, c)
+        return self
 
     @property
     def seed(self):
@@ -107,11 +162,22 @@ class RBM(object):
             shape = x.shape if not isinstance(x, Dataset) else x.shape
             self.build((None, int(shape[1])))
 
-    def __call__(self, x):
-        return self.call(x)
+    if not IS_KERAS_LAYER:
+        def __call__(self, x):
+            return self.call(x)
 
     def call(self, x):
-        """rbm.py:80-86: the layer's forward pass is the sampled hidden state."""
+        """rbm.py:80-86: the layer's forward pass is the sampled hidden state.  Inside a Keras model the input is a
+        TensorFlow tensor: the engine is called through tf.numpy_function (no gradient flows through the sampling,
+        as in the reference, whose K.less / K.cast have none)."""
+        if IS_KERAS_LAYER and type(x).__module__.split(".")[0] in ("tensorflow", "keras", "tf_keras"):
+            import tensorflow as tf
+
+            self._ensure_built(x)
+            out = tf.numpy_function(lambda a: np.asarray(_unwrap(self.transform(a)), dtype=np.float32), [x], tf.float32)
+            if hasattr(out, "set_shape"):
+                out.set_shape((None, int(self.output_dim)))
+            return out
         return _unwrap(self.transform(x))
 
     def compute_output_shape(self, input_shape):
@@ -136,6 +202,7 @@ class RBM(object):
     @rbm_weight.setter
     def rbm_weight(self, W):
         self._machine.set_params(W=W)
+        self._to_keras()
 
     @property
     def visible_bias(self):
@@ -144,6 +211,7 @@ class RBM(object):
     @visible_bias.setter
     def visible_bias(self, b):
         self._machine.set_params(b=b)
+        self._to_keras()
 
     @property
     def hidden_bias(self):
@@ -152,6 +220,7 @@ class RBM(object):
     @hidden_bias.setter
     def hidden_bias(self, c):
         self._machine.set_params(c=c)
+        self._to_keras()
 
     def get_weights(self):
         """Keras order of creation: rbm_weight, rbm_hidden_bias, rbm_visible_bias (rbm.py:30,34,38)."""
@@ -161,6 +230,7 @@ class RBM(object):
     def set_weights(self, weights):
         W, c, b = weights
         self._machine.set_params(W, b, c)
+        self._to_keras()
 
     # ---- checkpoint / resume (the reference relies on Keras HDF5 and saves no trainer state) ----
     def save(self, path):
@@ -183,6 +253,7 @@ class RBM(object):
             raise ValueError("checkpoint has rbm_weight %s, this RBM is %s" % (z["rbm_weight"].shape,
                                                                                (self._machine.V, self._machine.H)))
         self._machine.set_params(z["rbm_weight"], z["rbm_visible_bias"], z["rbm_hidden_bias"])
+        self._to_keras()
         self._machine.set_seed(int(z["seed"]), int(z["step_count"]))
         if "epochs_done" in z.files:
             self._epochs_done = int(z["epochs_done"])
@@ -240,6 +311,13 @@ class RBM(object):
         return shard_rows(V, batch, ctx.rank, ctx.world)
 
     def fit(self, V, verbose=1):
+        """Train RBM with the data V (rbm.py:100-234); see _fit.  In Layer mode the trained parameters are then
+        written back into the Keras variables."""
+        self._fit(V, verbose)
+        self._to_keras()
+        return self
+
+    def _fit(self, V, verbose=1):
         """Train RBM with the data V (rbm.py:100-234).
 
         V : 2d array (rows x input_dim), or an engine Dataset already resident on the GPU.

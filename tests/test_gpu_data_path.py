@@ -45,6 +45,25 @@ def test_packed_data_set_equals_dense_data_set(ctx, rows, V):
     dense.close()
 
 
+@pytest.mark.parametrize("V", [784, 130, 8, 5])
+def test_uint8_and_bool_ingest(ctx, V):
+    """ingest_kernel<uint8_t>: the eight-bytes-per-load path (rows of 784 start 8-byte aligned) and the byte path
+    (rows of 130 or 5 do not), bool arrays, and a row-strided view."""
+    from keras_unsupervised_b200 import _lib as L
+    from keras_unsupervised_b200.engine import Dataset
+
+    rng = np.random.default_rng(V)
+    x = rng.integers(0, 2, (203, V), dtype=np.uint8)
+    for form in (x, x.astype(bool), np.ascontiguousarray(np.pad(x, ((0, 0), (0, 3))))[:, :V]):
+        ds = Dataset.from_array(ctx, form, L.COMPUTE_BF16)
+        assert np.array_equal(ds.numpy(), x.astype(np.float32))
+        ds.close()
+    big = rng.integers(0, 256, (64, V), dtype=np.uint8)                      # any byte value, exactly (<= 8 bits)
+    ds = Dataset.from_array(ctx, big, L.COMPUTE_BF16)
+    assert np.array_equal(ds.numpy(), big.astype(np.float32))
+    ds.close()
+
+
 def test_packed_rows_with_a_pitch(ctx):
     """strides[0] is the row pitch in bits: rows cut out of a wider byte matrix."""
     from keras_unsupervised_b200 import _lib as L
@@ -81,7 +100,8 @@ def test_packed_input_and_output_of_transform(ctx, compute):
     m.set_seed(3, 0)
     v_bits = m.inv_transform(h_bits, out_dtype="bits")
     assert np.array_equal(v_bits.to_dense(), v_dense)
-    np.testing.assert_array_equal(m.free_energy(PackedBits.from_dense(v)), m.free_energy(v))
+    # the softplus row sums are accumulated across column tiles with atomics: equal up to the order of fp32 adds
+    np.testing.assert_allclose(m.free_energy(PackedBits.from_dense(v)), m.free_energy(v), rtol=2e-6, atol=0)
     with pytest.raises(ValueError):                                          # probabilities are not bits
         keep = []
         from keras_unsupervised_b200 import _lib as L
@@ -206,24 +226,26 @@ def test_gaussian_visible_chain_kernels_equal_per_projection_launches(monkeypatc
             m.cd_step(v, hp)
             got.append(m.last_stats(rows))
         assert c_chain.timings()["chain_launches"] == 1 and c_plain.timings()["chain_launches"] == 0
-        for key in ("h_pos", "v_neg", "h_neg", "dW"):
+        for key in ("h_pos", "v_neg", "h_neg"):
             assert np.array_equal(got[0][key], got[1][key]), (V, key)
+        np.testing.assert_allclose(got[0]["dW"], got[1]["dW"], rtol=0, atol=1e-3)   # real-valued operands
         np.testing.assert_allclose(got[0]["db"], got[1]["db"], rtol=0, atol=2e-3)   # real-valued sums, atomics order
         np.testing.assert_allclose(got[0]["dc"], got[1]["dc"], rtol=0, atol=2e-3)
         # the sampled visibles really are mean + unit normal of the engine's stream (oracle regeneration)
         n1 = O.philox_normal(29, O.draw_id("train", 0, 2 * k), 0, rows, V)
         assert abs(float(np.corrcoef((got[0]["v_neg"]).ravel(), n1.ravel())[0, 1])) > 0.9
         data = rng.normal(0, 1, (5 * rows // 2, V)).astype(np.float32)          # 2 full minibatches + half a one
+        hp_fit = Machine.hparams(lr=1e-3, k=k, normalize=True)   # batch means: a sum-updated Gaussian RBM diverges here
         params = []
         for c, m in zip((c_chain, c_plain), ms):
             ds = Dataset.from_array(c, data, L.COMPUTE_BF16)
             for _ in range(2):
-                m.fit_epoch(ds, rows, hp)
+                m.fit_epoch(ds, rows, hp_fit)
             c.sync()
             params.append(m.get_params())
             ds.close()
         for i in range(3):
-            np.testing.assert_allclose(params[0][i], params[1][i], rtol=0, atol=1e-6)
-        assert np.isfinite(params[0][0]).all()
+            np.testing.assert_allclose(params[0][i], params[1][i], rtol=1e-5, atol=1e-6)
+        assert np.isfinite(params[0][0]).all() and np.abs(params[0][0]).max() < 1.0
         c_chain.close()
         c_plain.close()
