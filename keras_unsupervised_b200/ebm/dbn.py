@@ -95,6 +95,35 @@ class DBN(object):
             H_p = out[0] if isinstance(out, list) else out
         return H_p
 
+    def generate(self, n_samples, gibbs_steps=100, seed=0, h_init=None):
+        """Draw visible samples from the trained stack (what the reference's top-down pass, dbn.py:77-96, is for; SURVEY.md
+        8f rank 4): alternating Gibbs sampling in the top RBM for `gibbs_steps` sweeps (h -> v -> h, the associative
+        memory of a DBN), starting from `h_init` or Bernoulli(0.5) hidden states, then one top-down pass through
+        the lower layers (inv_transform, top layer first).  Everything between the first upload and the final read-back
+        stays on the GPU as engine Datasets."""
+        self._check()
+        top = self._rbm_layers[-1]
+        if not top.built:
+            raise ValueError("generate needs a trained (built) stack")
+        m = top._machine
+        if h_init is None:
+            rng = np.random.default_rng(seed)
+            h_init = (rng.random((int(n_samples), int(top.output_dim))) < 0.5).astype(np.float32)
+        h = Dataset.from_array(m.ctx, np.asarray(h_init, dtype=np.float32), m.compute)
+        for _ in range(int(gibbs_steps)):
+            v = m.inv_transform_dataset(h)
+            h.close()
+            h = m.transform_dataset(v)
+            v.close()
+        cur = h
+        for rbm_layer in reversed(self._rbm_layers):
+            nxt = rbm_layer._machine.inv_transform_dataset(cur)
+            cur.close()
+            cur = nxt
+        out = cur.numpy()
+        cur.close()
+        return out
+
     # ---- checkpoint: one JSON file with the stack's configs + one .npz per layer (cf. ku/utility.py:7-33, which
     # stores a JSON architecture next to an HDF5 weight file) ----
     def save(self, directory):
