@@ -185,6 +185,8 @@ struct kucd_ctx {
   std::vector<Mark> marks;
   size_t ev_used = 0;
   DevBuf stage_in, stage_u, stage_out;  // raw caller-dtype staging for host tensors
+  float* pinned_stats = nullptr;        // page-locked landing area of fit_host's per-step statistics (grown, never shrunk)
+  size_t pinned_stats_cap = 0;          // floats
 };
 
 // up to three bf16 term planes of one (rows, cols) matrix, leading dimension ld
@@ -1398,6 +1400,7 @@ int kucd_ctx_destroy(kucd_ctx* ctx) {
   ctx->stage_in.release();
   ctx->stage_u.release();
   ctx->stage_out.release();
+  if (ctx->pinned_stats != nullptr) cudaFreeHost(ctx->pinned_stats);
   auto drop_event = [](cudaEvent_t e) {
     if (e != nullptr) cudaEventDestroy(e);
   };
@@ -2260,7 +2263,17 @@ int kucd_rbm_fit_host(kucd_rbm* r, const kucd_tensor* V_all, int64_t batch, cons
     for (int i = 0; i < 2; ++i) KU_TRY(ctx->stage_raw[i].ensure(static_cast<size_t>(batch) * rb));
   }
   float* host_stats = nullptr;
-  if (step_recon != nullptr) CU_TRY(cudaMallocHost(&host_stats, steps * sizeof(float)));
+  if (step_recon != nullptr) {
+    if (ctx->pinned_stats_cap < static_cast<size_t>(steps)) {  // a page-locked allocation costs ~1 ms: keep it
+      if (ctx->pinned_stats != nullptr) cudaFreeHost(ctx->pinned_stats);
+      ctx->pinned_stats = nullptr;
+      ctx->pinned_stats_cap = 0;
+      const size_t cap = std::max<size_t>(static_cast<size_t>(steps), 1024);
+      CU_TRY(cudaMallocHost(&ctx->pinned_stats, cap * sizeof(float)));
+      ctx->pinned_stats_cap = cap;
+    }
+    host_stats = ctx->pinned_stats;
+  }
   // fp32 data in fp32-grade mode is carried in all three terms (no per-step "is it exact" round trip)
   const int live = (x3 && V_all->dtype_code == KUCD_DT_FLOAT) ? 3 : 1;
   auto rows_of_step = [&](int64_t i) { return std::min(batch, N - i * batch); };
@@ -2335,10 +2348,7 @@ int kucd_rbm_fit_host(kucd_rbm* r, const kucd_tensor* V_all, int64_t batch, cons
   cudaStreamSynchronize(ctx->copy_stream);
   const cudaError_t se = cudaStreamSynchronize(ctx->stream);
   if (rc == KUCD_OK && se != cudaSuccess) rc = fail(KUCD_ERR_CUDA, "fit_host: %s", cudaGetErrorString(se));
-  if (host_stats != nullptr) {
-    if (rc == KUCD_OK) memcpy(step_recon, host_stats, steps * sizeof(float));
-    cudaFreeHost(host_stats);
-  }
+  if (host_stats != nullptr && rc == KUCD_OK) memcpy(step_recon, host_stats, steps * sizeof(float));
   if (rc == KUCD_OK && stats != nullptr) {
     stats->steps = steps;
     stats->rows = N;

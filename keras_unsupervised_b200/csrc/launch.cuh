@@ -38,7 +38,31 @@ inline EncodeTiledFn get_encode_tiled() {
 
 // Tensor map over a row-major bf16 matrix with a {64 x box_rows} box and 128B swizzle.
 // Out-of-bounds elements read as zero, which is what makes ragged M/N/K tails exact.
+//
+// A descriptor is a pure function of (address, shape, leading dimension, box), and a training loop asks for the same
+// dozen of them at every step (cuTensorMapEncodeTiled costs 1-2 us each, 12 per chain launch: a fifth of a
+// latency-bound step's host time), so the last encodings are kept per host thread.
+struct TmapCache {
+  static constexpr int kSlots = 64;
+  struct Key {
+    const void* ptr;
+    int64_t rows, cols, ld;
+    uint32_t box_rows;
+  };
+  Key keys[kSlots];
+  CUtensorMap maps[kSlots];
+  int used = 0, next = 0;
+};
+
 inline bool make_tmap_bf16(CUtensorMap* tm, const MatView& m, uint32_t box_rows, std::string* err) {
+  static thread_local TmapCache cache;
+  for (int i = 0; i < cache.used; ++i) {
+    const TmapCache::Key& k = cache.keys[i];
+    if (k.ptr == m.ptr && k.rows == m.rows && k.cols == m.cols && k.ld == m.ld && k.box_rows == box_rows) {
+      memcpy(tm, &cache.maps[i], sizeof(CUtensorMap));
+      return true;
+    }
+  }
   EncodeTiledFn enc = get_encode_tiled();
   if (enc == nullptr) {
     if (err) *err = "cuTensorMapEncodeTiled unavailable";
@@ -60,6 +84,9 @@ inline bool make_tmap_bf16(CUtensorMap* tm, const MatView& m, uint32_t box_rows,
     }
     return false;
   }
+  const int slot = cache.used < TmapCache::kSlots ? cache.used++ : (cache.next++ % TmapCache::kSlots);
+  cache.keys[slot] = TmapCache::Key{m.ptr, m.rows, m.cols, m.ld, box_rows};
+  memcpy(&cache.maps[slot], tm, sizeof(CUtensorMap));
   return true;
 }
 

@@ -96,18 +96,15 @@ def test_dbn_greedy_pretraining(ctx, capsys):
         dbn.add_stack(bad)                           # dbn.py:27-30
 
 
-def test_one_epoch_fit_feeding_policy(ctx):
-    """A one-epoch RBM.fit of a host array is streamed when the steps are long and uploaded + graph-replayed when they are
-    short (prefers_streaming); both ways train the same parameters."""
+def test_one_epoch_fit_streamed_or_resident(ctx):
+    """A one-epoch RBM.fit of a host array is streamed (kucd_rbm_fit_host) unless hps['stream'] is False (upload, then
+    graph replay); both ways train the same parameters."""
     from keras_unsupervised_b200.ebm import RBM, MODE_VISIBLE_BERNOULLI
-    from keras_unsupervised_b200.ebm.rbm import prefers_streaming
 
-    assert not prefers_streaming(60000, 784, 128) and prefers_streaming(40 * 4096, 4096, 4096)
-    assert prefers_streaming(1 << 24, 784, 128)                               # too big to keep resident
     rng = np.random.default_rng(41)
     X = (rng.random((1000, 200)) < 0.2).astype(np.float32)
     out = []
-    for stream in (None, True, False):
+    for stream in (None, False):
         hps = {"batch_size": 128, "epochs": 1, "lr": 1e-3, "dtype": "bf16", "seed": 9}
         if stream is not None:
             hps["stream"] = stream
@@ -115,10 +112,9 @@ def test_one_epoch_fit_feeding_policy(ctx):
         t0 = ctx.timings()["graph_launches"]
         r.fit(X, verbose=0)
         out.append((r.rbm_weight, r.hidden_bias, ctx.timings()["graph_launches"] - t0))
-    assert out[0][2] == 8 and out[1][2] == 0 and out[2][2] == 8               # default here: resident + replay
-    for W, c, _ in out[1:]:
-        np.testing.assert_allclose(W, out[0][0], rtol=0, atol=1e-6)
-        np.testing.assert_allclose(c, out[0][1], rtol=0, atol=1e-6)
+    assert out[0][2] == 0 and out[1][2] == 8
+    np.testing.assert_allclose(out[1][0], out[0][0], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(out[1][1], out[0][1], rtol=0, atol=1e-6)
 
 
 def test_dbn_generate_top_down(ctx):
