@@ -449,46 +449,47 @@ def _main(out):
         windows.append((tw0, tw1))
         del host
     if e2e is not None:
-        # the same pass with the binarised data handed over as uint8 (a quarter of the bytes): informational
-        host8 = torch.empty((n_e2e * B, V), dtype=torch.uint8).pin_memory()
-        for i in range(n_e2e):
-            host8[i * B:(i + 1) * B].copy_(X[(i % n_batches) * B:((i % n_batches) + 1) * B])
-        m.fit_host(host8[:2 * B], B, hp_e, global_row0=row0)
-        barrier()
-        t0 = time.perf_counter()
-        m.fit_host(host8, B, hp_e, global_row0=row0)
-        dt8 = time.perf_counter() - t0
-        if dist is not None:
-            t = torch.tensor([dt8], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt8 = float(t.item())
-        e2e["uint8_input"] = {"value": world * n_e2e * B / dt8, "unit": UNIT, "h2d_bytes_per_step": B * V,
-                              "ms_per_step": 1e3 * dt8 / n_e2e}
-        del host8
-        # and as packed bits (1/32 of the float32 bytes; data.PackedBits, include/kucd.h bits = 1): informational
-        from keras_unsupervised_b200.data import PackedBits
+        # The same pass with the binarised data handed over as uint8 (a quarter of the bytes) and as packed bits (1/32 of
+        # them; data.PackedBits, include/kucd.h bits = 1).  Informational: a failure here must not cost the line.
+        def timed_pass(arr):
+            m.fit_host(arr[:2 * B], B, hp_e, global_row0=row0)
+            barrier()
+            t0 = time.perf_counter()
+            m.fit_host(arr, B, hp_e, global_row0=row0)
+            dt_ = time.perf_counter() - t0
+            if dist is not None:
+                t = torch.tensor([dt_], device="cuda", dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dt_ = float(t.item())
+            return dt_
 
-        nb = (V + 7) // 8
-        hostb = torch.empty((n_e2e * B, nb), dtype=torch.uint8).pin_memory()
-        weights = (2 ** torch.arange(8, device="cuda", dtype=torch.int32)).view(1, 1, 8)
-        for i in range(n_e2e):
-            blk = X[(i % n_batches) * B:((i % n_batches) + 1) * B].to(torch.int32)
-            if V % 8:
-                blk = torch.nn.functional.pad(blk, (0, nb * 8 - V))
-            hostb[i * B:(i + 1) * B].copy_((blk.view(B, nb, 8) * weights).sum(dim=2).to(torch.uint8))
-        packed = PackedBits(hostb, V)
-        m.fit_host(packed[:2 * B], B, hp_e, global_row0=row0)
-        barrier()
-        t0 = time.perf_counter()
-        m.fit_host(packed, B, hp_e, global_row0=row0)
-        dtb = time.perf_counter() - t0
-        if dist is not None:
-            t = torch.tensor([dtb], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dtb = float(t.item())
-        e2e["packed_bits_input"] = {"value": world * n_e2e * B / dtb, "unit": UNIT, "h2d_bytes_per_step": B * nb,
-                                    "ms_per_step": 1e3 * dtb / n_e2e}
-        del hostb, packed
+        try:
+            host8 = torch.empty((n_e2e * B, V), dtype=torch.uint8).pin_memory()
+            for i in range(n_e2e):
+                host8[i * B:(i + 1) * B].copy_(X[(i % n_batches) * B:((i % n_batches) + 1) * B])
+            dt8 = timed_pass(host8)
+            e2e["uint8_input"] = {"value": world * n_e2e * B / dt8, "unit": UNIT, "h2d_bytes_per_step": B * V,
+                                  "ms_per_step": 1e3 * dt8 / n_e2e}
+            del host8
+        except Exception as exc:  # noqa: BLE001
+            e2e["uint8_input"] = {"error": repr(exc)}
+        try:
+            from keras_unsupervised_b200.data import PackedBits
+
+            nb = (V + 7) // 8
+            hostb = torch.empty((n_e2e * B, nb), dtype=torch.uint8).pin_memory()
+            weights = (2 ** torch.arange(8, device="cuda", dtype=torch.int32)).view(1, 1, 8)
+            for i in range(n_e2e):
+                blk = X[(i % n_batches) * B:((i % n_batches) + 1) * B].to(torch.int32)
+                if V % 8:
+                    blk = torch.nn.functional.pad(blk, (0, nb * 8 - V))
+                hostb[i * B:(i + 1) * B].copy_((blk.view(B, nb, 8) * weights).sum(dim=2).to(torch.uint8))
+            dtb = timed_pass(PackedBits(hostb, V))
+            e2e["packed_bits_input"] = {"value": world * n_e2e * B / dtb, "unit": UNIT, "h2d_bytes_per_step": B * nb,
+                                        "ms_per_step": 1e3 * dtb / n_e2e}
+            del hostb
+        except Exception as exc:  # noqa: BLE001
+            e2e["packed_bits_input"] = {"error": repr(exc)}
 
     # ---- roofline of the dominant kernel: per-launch CUDA events on the engine stream -------------
     roof = None
