@@ -36,19 +36,47 @@ __device__ __forceinline__ float load_as_float<uint8_t>(const uint8_t* p) {
   return static_cast<float>(__ldg(p));
 }
 
+// Grid-stride walk over (row, item-in-row) pairs without a division per element: the position of item index g is
+// computed once, then advanced by a constant stride (64-bit divisions per element made the byte-sized kernels
+// instruction-bound).
+struct RowWalker {
+  // 32-bit state (the launches cover at most 2^22 rows of at most 2^21 items): five registers, so the kernels keep the
+  // occupancy that hides their load latency
+  int32_t r, rem;          // current row, item inside the row
+  int32_t dr, drem, per;   // per-step advance, items per row
+  __device__ __forceinline__ RowWalker(int64_t g, int64_t step, int64_t per_row) {
+    per = static_cast<int32_t>(per_row);
+    const int64_t r0 = g / per_row, d0 = step / per_row;
+    r = static_cast<int32_t>(r0 < 0x7fffffff ? r0 : 0x7fffffff);  // beyond the matrix anyway: the caller tests g < total
+    rem = static_cast<int32_t>(g - r0 * per_row);
+    dr = static_cast<int32_t>(d0 < 0x3fffffff ? d0 : 0x3fffffff);
+    drem = static_cast<int32_t>(step - d0 * per_row);
+  }
+  __device__ __forceinline__ void advance() {
+    r += dr;
+    rem += drem;
+    if (rem >= per) {
+      rem -= per;
+      ++r;
+    }
+  }
+};
+
 // Caller matrix (rows, cols), row stride `src_ld` elements -> `nparts` bf16 planes (rows, ld), columns
 // [cols, ld) zeroed.  *inexact is raised when some value is not a bf16 number, which tells the host
 // whether the first plane alone carries the data exactly (binary data always does).
 template <typename T>
-__global__ void ingest_kernel(const T* __restrict__ src, int64_t src_ld, int64_t rows, int64_t cols,
+__global__ void __launch_bounds__(256, 8) ingest_kernel(const T* __restrict__ src, int64_t src_ld, int64_t rows, int64_t cols,
                               __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ mid,
                               __nv_bfloat16* __restrict__ lo, int64_t ld, int nparts, int* inexact) {
   const int64_t groups_per_row = ld / 8;
   const int64_t total = rows * groups_per_row;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  const bool full = nparts == 3 || inexact != nullptr;  // otherwise only the leading term is wanted
   bool bad = false;
-  for (int64_t g = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; g < total;
-       g += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int64_t r = g / groups_per_row, c0 = (g % groups_per_row) * 8;
+  int64_t g = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  for (RowWalker w(g, stride, groups_per_row); g < total; g += stride, w.advance()) {
+    const int64_t r = w.r, c0 = static_cast<int64_t>(w.rem) * 8;
     __align__(16) __nv_bfloat16 h[8], m[8], l[8];
     float x[8];
     const T* row = src + r * src_ld + c0;
@@ -64,10 +92,15 @@ __global__ void ingest_kernel(const T* __restrict__ src, int64_t src_ld, int64_t
 #pragma unroll
       for (int j = 0; j < 8; ++j) x[j] = (c0 + j < cols) ? load_as_float<T>(row + j) : 0.f;
     }
+    if (full) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      split3(x[j], h[j], m[j], l[j]);
-      bad |= (__bfloat162float(h[j]) != x[j]);
+      for (int j = 0; j < 8; ++j) {
+        split3(x[j], h[j], m[j], l[j]);
+        bad |= (__bfloat162float(h[j]) != x[j]);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) h[j] = __float2bfloat16_rn(x[j]);
     }
     *reinterpret_cast<uint4*>(hi + r * ld + c0) = *reinterpret_cast<const uint4*>(h);
     if (nparts == 3) {
@@ -116,7 +149,11 @@ __global__ void ingest_bits_kernel(const uint8_t* __restrict__ src, int64_t src_
   const int64_t groups_per_row = ld / 8;
   const int64_t total = rows * groups_per_row;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-  for (int64_t g0 = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; g0 < total; g0 += 4 * stride) {
+  int64_t g0 = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  RowWalker w[4] = {RowWalker(g0, 4 * stride, groups_per_row), RowWalker(g0 + stride, 4 * stride, groups_per_row),
+                    RowWalker(g0 + 2 * stride, 4 * stride, groups_per_row),
+                    RowWalker(g0 + 3 * stride, 4 * stride, groups_per_row)};
+  for (; g0 < total; g0 += 4 * stride) {
     uint32_t b[4];
     int64_t off[4];
     int valid[4];
@@ -126,12 +163,13 @@ __global__ void ingest_bits_kernel(const uint8_t* __restrict__ src, int64_t src_
       b[u] = 0u;
       valid[u] = -1;  // -1: no such group
       if (g < total) {
-        const int64_t r = g / groups_per_row, c0 = (g % groups_per_row) * 8;
+        const int64_t r = w[u].r, c0 = static_cast<int64_t>(w[u].rem) * 8;
         const int64_t left = cols - c0;  // columns of this group that exist
         if (left > 0) b[u] = __ldg(src + r * src_pitch + (c0 >> 3));
         valid[u] = left >= 8 ? 8 : (left > 0 ? static_cast<int>(left) : 0);
         off[u] = r * ld + c0;
       }
+      w[u].advance();
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
@@ -152,7 +190,11 @@ __global__ void export_bits_kernel(const __nv_bfloat16* __restrict__ hi, int64_t
   const int64_t bytes_per_row = (cols + 7) / 8;
   const int64_t total = rows * bytes_per_row;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-  for (int64_t i0 = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i0 < total; i0 += 4 * stride) {
+  int64_t i0 = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  RowWalker w[4] = {RowWalker(i0, 4 * stride, bytes_per_row), RowWalker(i0 + stride, 4 * stride, bytes_per_row),
+                    RowWalker(i0 + 2 * stride, 4 * stride, bytes_per_row),
+                    RowWalker(i0 + 3 * stride, 4 * stride, bytes_per_row)};
+  for (; i0 < total; i0 += 4 * stride) {
     uint4 q[4];
     int64_t out[4];
     int valid[4];
@@ -161,12 +203,13 @@ __global__ void export_bits_kernel(const __nv_bfloat16* __restrict__ hi, int64_t
       const int64_t i = i0 + u * stride;
       valid[u] = -1;
       if (i < total) {
-        const int64_t r = i / bytes_per_row, c0 = (i % bytes_per_row) * 8;
+        const int64_t r = w[u].r, c0 = static_cast<int64_t>(w[u].rem) * 8;
         q[u] = *reinterpret_cast<const uint4*>(hi + r * ld + c0);  // ld is a multiple of 64: in bounds, aligned
         const int64_t left = cols - c0;
         valid[u] = left >= 8 ? 8 : static_cast<int>(left);
         out[u] = r * dst_pitch + (c0 >> 3);
       }
+      w[u].advance();
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
