@@ -180,3 +180,21 @@ def test_engine_bit_expansion_equals_the_oracle(host_tool):
     expect = enc[:, 0::2] | (enc[:, 1::2] << 16)
     assert np.array_equal(words, expect)
     assert np.array_equal(back, (b & ((1 << valid) - 1)))
+
+
+def test_formats_match_the_committed_fixture():
+    """tests/golden/data_path.json (made by tests/golden/make_data_path_fixtures.py): the packed layout and the
+    shuffling stream must not drift - checkpoints and packed data sets written by one round are read by the next."""
+    import json
+
+    with open(os.path.join(ROOT, "tests", "golden", "data_path.json")) as f:
+        gold = json.load(f)
+    dense = np.array(gold["pack"]["dense"], dtype=np.uint8)
+    assert O.pack_bits(dense).tolist() == gold["pack"]["packed"]
+    assert PackedBits.from_dense(dense).data.tolist() == gold["pack"]["packed"]
+    for k in gold["keys"]:
+        assert O.feistel_keys(k["seed"], k["epoch"]) == k["keys"]
+    for p in gold["perm"]:
+        perm = O.feistel_permutation(p["rows"], p["seed"], p["epoch"])
+        assert perm[:16].tolist() == p["head"]
+        assert int((perm * (np.arange(p["rows"]) + 1)).sum() % (2**61 - 1)) == p["checksum"]
