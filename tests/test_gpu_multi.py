@@ -15,7 +15,7 @@ def test_two_gpu_fit_matches_single_gpu_and_oracle():
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (run under `gpurun --gpus 2`)")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
-           "127.0.0.1", "--master-port", "29517", os.path.join(ROOT, "tools", "dp_check.py")]
+           "127.0.0.1", "--master-port", "29517", os.path.join(ROOT, "tests", "dp_check.py")]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     sys.stdout.write(res.stdout[-4000:])
     assert res.returncode == 0, res.stdout[-4000:] + res.stderr[-4000:]
