@@ -107,3 +107,34 @@ def test_config_round_trip():
     assert twin.get_config() == rbm.get_config() and twin.mode == MODE_VISIBLE_BERNOULLI and not twin.built
     legacy = RBM.from_config({"hps": hps, "output_dim": 32, "name": "y"})   # the reference's config has no mode
     assert legacy.mode == MODE_VISIBLE_GAUSSIAN                              # rbm.py:22 default
+
+
+def test_reference_import_lines_resolve_to_the_engine():
+    """install_as_ku(): `from ku.ebm.rbm import RBM` (examples/rbm/rbm_softmax_mnist.py:24) and `from ku.ebm import
+    RBM, DBN` (ku/ebm/__init__.py:1-2) work unchanged; run in a subprocess so the alias does not leak."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import keras_unsupervised_b200 as kucd\n"
+        "kucd.install_as_ku()\n"
+        "from ku.ebm.rbm import RBM\n"
+        "from ku.ebm import RBM as R2, DBN\n"
+        "from ku.ebm.rbm import MODE_VISIBLE_BERNOULLI, MODE_VISIBLE_GAUSSIAN, MODE_COMPLEX\n"
+        "from ku.ebm.dbn import DBN as D2\n"
+        "import ku.ebm\n"
+        "assert RBM is R2 is kucd.ebm.RBM and DBN is D2 is kucd.ebm.DBN\n"
+        "r = RBM({'batch_size': 128, 'epochs': 1, 'lr': 0.001}, 128, name='rbm')\n"
+        "assert r.mode == MODE_VISIBLE_GAUSSIAN and (MODE_VISIBLE_BERNOULLI, MODE_COMPLEX) == (0, 2)\n"
+        "try:\n"
+        "    import ku.backprop\n"
+        "    raise SystemExit('out-of-scope subpackage resolved')\n"
+        "except ImportError:\n"
+        "    pass\n"
+        "kucd.install_as_ku()\n"
+        "print('ok')\n")
+    res = subprocess.run([sys.executable, "-c", code], cwd=root, capture_output=True, text=True, timeout=300,
+                         env=dict(os.environ, PYTHONPATH=root))
+    assert res.returncode == 0 and res.stdout.strip().endswith("ok"), res.stdout + res.stderr
