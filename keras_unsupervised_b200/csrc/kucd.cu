@@ -246,6 +246,20 @@ struct GraphKey {
   }
 };
 
+// key of the captured step that a streamed fit (kucd_rbm_fit_host) replays over its full minibatches
+struct HostGraphKey {
+  int64_t batch = 0, global_row0 = 0;
+  kucd_hparams hp{};
+  bool fused = false;
+  int live = 0;
+  const void* vin = nullptr;
+  const void* log = nullptr;
+  bool operator==(const HostGraphKey& o) const {
+    return batch == o.batch && global_row0 == o.global_row0 && fused == o.fused && live == o.live && vin == o.vin &&
+           log == o.log && memcmp(&hp, &o.hp, sizeof hp) == 0;
+  }
+};
+
 struct kucd_rbm {
   kucd_ctx* ctx = nullptr;
   int64_t V = 0, H = 0, ldV = 0, ldH = 0;
@@ -286,6 +300,11 @@ struct kucd_rbm {
   cudaGraphExec_t graph_exec = nullptr;
   GraphKey graph_key;
   int64_t graph_kernels = 0;  // kernels one replay launches
+  // captured step of the streamed fit (reads the staged minibatch in `vin`)
+  cudaGraph_t hgraph = nullptr;
+  cudaGraphExec_t hgraph_exec = nullptr;
+  HostGraphKey hgraph_key;
+  int64_t hgraph_kernels = 0;
 
   float* dW() const { return grad.as<float>(); }
   float* db() const { return grad.as<float>() + V * ldH; }
@@ -294,6 +313,13 @@ struct kucd_rbm {
   int64_t ldHb() const { return round_up(H, 256) + 256; }
   int64_t grad_elems() const { return V * ldH + ldVb() + ldHb(); }
 };
+
+static void drop_host_graph(kucd_rbm* r) {
+  if (r->hgraph_exec != nullptr) cudaGraphExecDestroy(r->hgraph_exec);
+  if (r->hgraph != nullptr) cudaGraphDestroy(r->hgraph);
+  r->hgraph_exec = nullptr;
+  r->hgraph = nullptr;
+}
 
 static size_t prof_event(kucd_ctx* ctx) {
   if (ctx->ev_used == ctx->ev_pool.size()) {
@@ -701,6 +727,7 @@ static int ensure_workspace(kucd_rbm* r, int64_t rows) {
   KU_TRY(r->pstage.ensure(static_cast<size_t>(cap) * std::max(r->ldV, r->ldH) * 4));
   r->cap = cap;
   // a captured graph holds the old pointers
+  drop_host_graph(r);
   if (r->graph_exec != nullptr) {
     cudaGraphExecDestroy(r->graph_exec);
     cudaGraphDestroy(r->graph);
@@ -1532,6 +1559,7 @@ int kucd_rbm_destroy(kucd_rbm* r) {
   cudaStreamSynchronize(r->ctx->stream);
   if (r->graph_exec != nullptr) cudaGraphExecDestroy(r->graph_exec);
   if (r->graph != nullptr) cudaGraphDestroy(r->graph);
+  drop_host_graph(r);
   for (int i = 0; i < r->n_peer_open; ++i) cudaIpcCloseMemHandle(r->peer_open[i]);
   r->arena.release();
   for (DevBuf* b : {&r->W32, &r->b32, &r->c32, &r->mW, &r->mb, &r->mc, &r->grad, &r->fe0, &r->fe1, &r->sp0, &r->sp1,
@@ -1646,6 +1674,7 @@ int kucd_rbm_peer_attach(kucd_rbm* r, const void* handles) {
   }
   r->epoch = r->ps.flags[me] + 64;
   r->peer_on = true;
+  drop_host_graph(r);
   if (r->graph_exec != nullptr) {
     cudaGraphExecDestroy(r->graph_exec);
     cudaGraphDestroy(r->graph);
@@ -1662,6 +1691,7 @@ int kucd_rbm_peer_detach(kucd_rbm* r) {
   for (int i = 0; i < r->n_peer_open; ++i) cudaIpcCloseMemHandle(r->peer_open[i]);
   r->n_peer_open = 0;
   r->peer_on = false;
+  drop_host_graph(r);
   if (r->graph_exec != nullptr) {
     cudaGraphExecDestroy(r->graph_exec);
     cudaGraphDestroy(r->graph);
@@ -1704,6 +1734,8 @@ int kucd_rbm_get_params(kucd_rbm* r, kucd_tensor* W, kucd_tensor* b, kucd_tensor
 
 // ---- inference -------------------------------------------------------------------------------------
 static const int64_t kChunkRows = 32768;
+// streamed fits replay a captured step for latency-bound minibatches (see kucd_rbm_fit_host); KUCD_STREAM_GRAPH overrides
+static const bool kStreamGraphDefault = false;
 
 // forward = transform (rbm.py:45-48), !forward = inv_transform (rbm.py:51-54)
 static int sample_api(kucd_rbm* r, bool forward, const kucd_tensor* in, kucd_tensor* s_out, kucd_tensor* p_out,
@@ -1968,6 +2000,7 @@ int kucd_rbm_set_chains(kucd_rbm* r, const kucd_tensor* v_chains) {
   KU_TRY(ingest_rows(ctx, v_chains, 0, n, r->chains.view(n, r->V, np), np, nullptr));
   r->n_chains = n;
   r->last_vk_parts = np;
+  drop_host_graph(r);
   if (r->graph_exec != nullptr) {  // chain buffers may have moved
     cudaGraphExecDestroy(r->graph_exec);
     cudaGraphDestroy(r->graph);
@@ -2313,6 +2346,75 @@ int kucd_rbm_fit_host(kucd_rbm* r, const kucd_tensor* V_all, int64_t batch, cons
     ctx->tm.h2d_bytes += n * rb;
     return KUCD_OK;
   };
+  // Latency-bound minibatches: everything of a step after the ingest (column sums, chain, dW, statistic, update) is
+  // captured once and replayed per full minibatch - one graph launch instead of nine dependent kernel launches - with
+  // the draw counter in device memory (StepDyn) exactly as in kucd_rbm_fit_range.  The remainder minibatch runs through
+  // the direct launches below.  KUCD_STREAM_GRAPH=1 turns it on for every size, 0 off.
+  static const int graph_env = [] {
+    const char* e = getenv("KUCD_STREAM_GRAPH");
+    return e == nullptr ? -1 : atoi(e);
+  }();
+  const int64_t full_steps = N / batch;
+  const bool use_graph = !zero_copy && full_steps >= 2 &&
+                         (graph_env == 1 || (graph_env == -1 && kStreamGraphDefault && batch * cols < (1 << 20)));
+  StepDyn* dyn = r->dyn.as<StepDyn>();
+  if (use_graph) {
+    if (hp->momentum != 0.f) {  // allocate outside the capture
+      KU_TRY(r->mW.ensure(static_cast<size_t>(r->V) * r->ldH * 4, true));
+      KU_TRY(r->mb.ensure(r->ldVb() * 4, true));
+      KU_TRY(r->mc.ensure(r->ldHb() * 4, true));
+    }
+    HostGraphKey key;
+    key.batch = batch;
+    key.global_row0 = global_row0;
+    key.hp = *hp;
+    key.hp.want_stats = 0;
+    key.fused = r->fused_now;
+    key.live = live;
+    key.vin = r->vin.buf[0].p;
+    key.log = host_stats;
+    if (r->hgraph_exec == nullptr || !(r->hgraph_key == key)) {
+      drop_host_graph(r);
+      CU_TRY(cudaStreamSynchronize(ctx->stream));
+      const int64_t k0 = ctx->tm.gemm_launches + ctx->tm.aux_launches;
+      const int64_t no_end = int64_t{1} << 60;  // the replayed steps are full minibatches: rows_valid stays `batch`
+      CU_TRY(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed));
+      Planes v0 = r->vin.view(batch, r->V, nplanes);
+      v0.n = live;
+      int crc = enqueue_cd(r, v0, batch, hp, nullptr, global_row0, 0, dyn, false);
+      if (crc == KUCD_OK && host_stats != nullptr) {
+        crc = enqueue_recon(r, v0, batch);
+        log_stat_kernel<<<1, 1, 0, ctx->stream>>>(r->stats.as<float>() + 1, dyn, static_cast<int32_t>(batch), host_stats);
+        ctx->tm.aux_launches++;
+      }
+      bool advanced = false;
+      if (crc == KUCD_OK) crc = apply_update(r, hp, batch * ctx->world, dyn, static_cast<int32_t>(batch), no_end, &advanced);
+      if (crc == KUCD_OK && !advanced) {
+        advance_dyn_kernel<<<1, 1, 0, ctx->stream>>>(dyn, static_cast<int32_t>(batch), no_end);
+        ctx->tm.aux_launches++;
+      }
+      cudaGraph_t g = nullptr;
+      const cudaError_t ce = cudaStreamEndCapture(ctx->stream, &g);
+      if (crc != KUCD_OK) {
+        if (g != nullptr) cudaGraphDestroy(g);
+        return crc;
+      }
+      if (ce != cudaSuccess) return fail(KUCD_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
+      cudaGraphExec_t ge = nullptr;
+      const cudaError_t ie = cudaGraphInstantiate(&ge, g, 0);
+      if (ie != cudaSuccess) {
+        cudaGraphDestroy(g);
+        return fail(KUCD_ERR_CUDA, "graph instantiation failed: %s", cudaGetErrorString(ie));
+      }
+      r->hgraph = g;
+      r->hgraph_exec = ge;
+      r->hgraph_key = key;
+      r->hgraph_kernels = ctx->tm.gemm_launches + ctx->tm.aux_launches - k0;  // recorded while capturing, not run
+    }
+    set_dyn_kernel<<<1, 1, 0, ctx->stream>>>(dyn, 0, static_cast<int32_t>(batch), r->step_count);
+    ctx->tm.aux_launches++;
+    CU_TRY(cudaGetLastError());
+  }
   int rc = KUCD_OK;
   if (cudaEventRecord(ctx->ev0, ctx->stream) != cudaSuccess) rc = fail(KUCD_ERR_CUDA, "event record failed");
   if (rc == KUCD_OK) rc = copy_in(0);
@@ -2331,6 +2433,14 @@ int kucd_rbm_fit_host(kucd_rbm* r, const kucd_tensor* V_all, int64_t batch, cons
       cudaEventRecord(ctx->ev_consumed[slot], ctx->stream);  // the raw staging slot is free again
     }
     v0.n = live;
+    if (use_graph && n == batch) {  // the rest of the step is one replay
+      if (cudaGraphLaunch(r->hgraph_exec, ctx->stream) != cudaSuccess) rc = fail(KUCD_ERR_CUDA, "graph launch failed");
+      r->step_count++;
+      ctx->tm.graph_launches++;
+      ctx->tm.graph_kernel_launches += r->hgraph_kernels;
+      if (host_stats != nullptr) ctx->tm.d2h_bytes += 4;
+      continue;
+    }
     rc = enqueue_cd(r, v0, n, hp, nullptr, global_row0, r->step_count, nullptr, false);
     r->step_count++;
     if (rc == KUCD_OK && host_stats != nullptr) {

@@ -112,7 +112,7 @@ def test_one_epoch_fit_streamed_or_resident(ctx):
         t0 = ctx.timings()["graph_launches"]
         r.fit(X, verbose=0)
         out.append((r.rbm_weight, r.hidden_bias, ctx.timings()["graph_launches"] - t0))
-    assert out[0][2] == 0 and out[1][2] == 8
+    assert out[0][2] in (0, 7) and out[1][2] == 8        # 7: KUCD_STREAM_GRAPH=1 replays the full minibatches of a streamed fit
     np.testing.assert_allclose(out[1][0], out[0][0], rtol=0, atol=1e-6)
     np.testing.assert_allclose(out[1][1], out[0][1], rtol=0, atol=1e-6)
 
