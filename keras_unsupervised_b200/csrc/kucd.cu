@@ -24,6 +24,7 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -221,7 +222,7 @@ struct PlaneBuf {
   }
 };
 
-static uint64_t g_next_dataset_id = 1;
+static std::atomic<uint64_t> g_next_dataset_id{1};  // contexts on different host threads create data sets concurrently
 
 struct kucd_dataset {
   kucd_ctx* ctx = nullptr;
@@ -875,10 +876,11 @@ template <int BN, int CG, bool GAUSS>
 static int launch_chain_kernel(kucd_ctx* ctx, const ChainParams& p, int total, bool prof, size_t* pe0) {
   using Cfg = GemmCfg<BN / CG>;
   auto kern = chain_kernel<BN, CG, GAUSS>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[kMaxDevices] = {};  // a function attribute belongs to the device it was set on
+  const int dev = current_device_slot();
+  if (!attr_set[dev]) {
     CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_set = true;
+    attr_set[dev] = true;
   }
   if constexpr (CG == 1) {
     const int grid = std::min(total, ctx->num_sms);

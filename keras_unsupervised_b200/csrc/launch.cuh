@@ -101,6 +101,14 @@ struct GemmOperands {
   int64_t M = 0, N = 0, K = 0;
 };
 
+constexpr int kMaxDevices = 64;
+// index of the calling thread's current device (contexts on several GPUs may live in one process)
+inline int current_device_slot() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) dev = 0;
+  return dev;
+}
+
 inline int pick_bn(int64_t M, int64_t N, int num_sms) {
   // Prefer the widest tile that still gives every SM a tile; small problems take narrower tiles.
   const int64_t m_tiles = (M + kBlockM - 1) / kBlockM;
@@ -117,11 +125,12 @@ template <int BN, bool A_MN, bool B_MN, int EPI, int CH = 0, int CG = 1>
 inline cudaError_t launch_one(const GemmParams& p, int num_sms, cudaStream_t stream) {
   using Cfg = GemmCfg<BN / CG, (EPI == kEpiRaw ? kEpiStageBytes : 0)>;
   auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, EPI, CH, CG>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[kMaxDevices] = {};  // a function attribute belongs to the device it was set on
+  const int dev = current_device_slot();
+  if (!attr_set[dev]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) return e;
-    attr_set = true;
+    attr_set[dev] = true;
   }
   const int tile_m = kBlockM * CG;
   const int num_tiles = ((p.M + tile_m - 1) / tile_m) * ((p.N + BN - 1) / BN);
