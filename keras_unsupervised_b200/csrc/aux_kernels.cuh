@@ -740,6 +740,9 @@ __global__ void reduce_bias_kernel(const float* __restrict__ slots, int n, int l
 // The owner's part of the update (rbm.py:127-128 on rows [r0, r0 + rows) of W): dW = sum of the n ranks' slots (fixed
 // order), fp32 master and momentum updated locally, and the refreshed bf16 rows stored into EVERY rank's operand
 // plane - the all-gather of the new W happens inside the update kernel, as plain NVLink stores.
+// W16: the slots hold bf16 partial sums (kEpiRawPush16; `slots` is then a __nv_bfloat16 array, slot pitch slice_elems
+// elements as before); they are widened and summed in fp32, in rank order.
+template <bool W16>
 __global__ void update_w_sharded_kernel(float* __restrict__ W, const float* __restrict__ slots, int64_t slice_elems,
                                         int n, float* __restrict__ mom, PeerSet ps, int64_t elem0, int64_t n4, float lr,
                                         float scale, float momentum, float weight_decay, const StepDyn* sdyn,
@@ -749,7 +752,14 @@ __global__ void update_w_sharded_kernel(float* __restrict__ W, const float* __re
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int j = 0; j < n; ++j) {
-      const float4 t = reinterpret_cast<const float4*>(slots + j * slice_elems)[i];
+      float4 t;
+      if constexpr (W16) {
+        const uint2 h = reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(slots) + j * slice_elems)[i];
+        t = make_float4(__uint_as_float(h.x << 16), __uint_as_float(h.x & 0xFFFF0000u), __uint_as_float(h.y << 16),
+                        __uint_as_float(h.y & 0xFFFF0000u));
+      } else {
+        t = reinterpret_cast<const float4*>(slots + j * slice_elems)[i];
+      }
       d.x += t.x;
       d.y += t.y;
       d.z += t.z;

@@ -47,7 +47,12 @@ enum EpiMode : int {
   kEpiFreeEnergy = 3,  // rowsum[m] += sum_n softplus(D + bias)
   kEpiReluSample = 4,  // s = 1[u < relu(D + bias)]   (Gaussian-visible mode, rbm.py:58-59)
   kEpiGaussian = 5,    // x = D + bias + N(0,1)       (Gaussian-visible mode, rbm.py:64-66) -> out_bf16 splits + out_f32
+  kEpiRawPush16 = 6,   // D rounded to bf16 (RNE) into the owning rank's slot: the fused exchange with bf16 partial sums on
+                       // the wire (opt-in, KUCD_WIRE_BF16=1; push_rows > 0 and BN >= 128 required)
 };
+
+// epilogues that transpose their tile through a per-warp shared-memory buffer
+__host__ __device__ constexpr bool epi_stages(int epi) { return epi == kEpiRaw || epi == kEpiRawPush16; }
 
 // Per-step quantities that live in device memory so that a captured CUDA graph of one CD step can be
 // replayed for every minibatch of an epoch: the kernels read them, a one-thread kernel advances them.
@@ -93,6 +98,8 @@ struct alignas(64) GemmParams {
   // ---- fused reduce-scatter of dW over NVLink (data-parallel ranks, raw epilogue only) ----
   // Output row r belongs to rank o = r / push_rows; this rank's contribution to it is stored into
   // push_base[o] (rank o's slot for this rank, peer-mapped memory; push_base[me] is local), row r - o * push_rows.
+  // With kEpiRawPush16 the slots hold bf16 rows of the same pitch (ld_f32 elements) and push_base[] carries
+  // __nv_bfloat16 pointers (cast): half the bytes cross NVLink, the owner still sums the ranks' parts in fp32.
   float* push_base[8];
   int32_t push_rows;  // 0: off, rows are written to out_f32
   int32_t push_pad;
@@ -189,6 +196,48 @@ __device__ __forceinline__ float* raw_row_ptr<GemmParams>(const GemmParams& p, i
     return p.push_base[o] + static_cast<int64_t>(row - o * p.push_rows) * p.ld_f32;
   }
   return p.out_f32 + static_cast<int64_t>(row) * p.ld_f32;
+}
+
+// kEpiRawPush16: 64 columns (two tensor-memory chunks) of this warp's 32 rows, rounded to bf16 and stored into the
+// owner's slot.  A thread owns one row; the 32 x 64 bf16 block is transposed through shared memory (32 rows of eight
+// 16-byte units, unit index XOR row so that neither pass has bank conflicts) and leaves as one 128-byte store per row
+// per eight lanes - the same NVLink write size as the fp32 path, for half the bytes.
+__device__ __forceinline__ void push16_chunk(const GemmParams& p, const uint32_t (&a0)[32], const uint32_t (&a1)[32],
+                                             int row, int col0, uint32_t lane, float* stage) {
+  if (col0 >= p.N) return;  // warp-uniform
+  uint4* st = reinterpret_cast<uint4*>(stage);
+  auto unit = [&](const uint32_t (&a)[32], int q, int c0) {  // columns c0 + 8 q .. + 8 of this row, zero beyond N
+    uint32_t w[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int c = c0 + 8 * q + 2 * e;
+      const float lo = c < p.N ? __uint_as_float(a[8 * q + 2 * e]) : 0.f;
+      const float hi = c + 1 < p.N ? __uint_as_float(a[8 * q + 2 * e + 1]) : 0.f;
+      w[e] = pack_bf16x2(lo, hi);
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+  };
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    st[lane * 8 + (static_cast<uint32_t>(q) ^ (lane & 7u))] = unit(a0, q, col0);
+    st[lane * 8 + (static_cast<uint32_t>(q + 4) ^ (lane & 7u))] = unit(a1, q, col0 + 32);
+  }
+  __syncwarp();
+  const int row_base = row - static_cast<int>(lane);
+  const int u = static_cast<int>(lane & 7u);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {  // eight lanes per row, four rows per instruction
+    const int r = 4 * i + static_cast<int>(lane >> 3);
+    const uint4 v = st[r * 8 + (u ^ (r & 7))];
+    const int grow = row_base + r;
+    if (grow < p.M && col0 + 8 * u < p.N) {
+      const int o = grow / p.push_rows;
+      __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.push_base[o]) +
+                           static_cast<int64_t>(grow - o * p.push_rows) * p.ld_f32 + col0 + 8 * u;
+      *reinterpret_cast<uint4*>(dst) = v;
+    }
+  }
+  __syncwarp();
 }
 
 // One 32-column chunk of one output row (this thread's TMEM lane).
@@ -444,7 +493,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_bf16_kernel(const __grid_
   constexpr int kBNLocal = BN / CG;  // B columns staged by this CTA
   constexpr int kTileM = kBlockM * CG;
   constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
-  using Cfg = GemmCfg<kBNLocal, (EPI == kEpiRaw ? kEpiStageBytes : 0)>;
+  using Cfg = GemmCfg<kBNLocal, (epi_stages(EPI) ? kEpiStageBytes : 0)>;
   constexpr int kStages = Cfg::kStages;
   const uint32_t cta_rank = CG == 2 ? ptx::cluster_ctarank() : 0u;
   const int unit = blockIdx.x / CG, num_units = gridDim.x / CG;  // a unit = one CTA, or one CTA pair
@@ -624,7 +673,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_bf16_kernel(const __grid_
     const uint32_t quarter = warp & 3u;  // TMEM lane quarter this warp may access
     const uint32_t half = ew >> 2;       // which half of the tile's columns
     constexpr int kColsPerWarp = BN / 2;
-    float* epi_stage = EPI == kEpiRaw ? reinterpret_cast<float*>(ctrl + 1024 + ew * 4096) : nullptr;
+    float* epi_stage = epi_stages(EPI) ? reinterpret_cast<float*>(ctrl + 1024 + ew * 4096) : nullptr;
     uint32_t accn = 0;
     const int total = p.num_seg * p.kblocks;
     const int pieces = CH > 0 ? (total + (CH > 0 ? CH : 1) - 1) / (CH > 0 ? CH : 1) : 1;
@@ -637,7 +686,25 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_bf16_kernel(const __grid_
       const int row = m_blk * kTileM + static_cast<int>(cta_rank) * kBlockM + quarter * 32 + lane;
       const bool row_ok = row < m_valid;
       float row_acc = 0.f;
-      if constexpr (CH == 0) {
+      if constexpr (EPI == kEpiRawPush16) {
+        static_assert(CH == 0 && kColsPerWarp % 64 == 0, "bf16 partial sums leave as 64-column (128-byte) row pieces");
+        const uint32_t as = accn & 1u;
+        ptx::mbar_wait(&tmem_full_bar[as], (accn >> 1) & 1u);
+        ptx::tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < kColsPerWarp; c += 64) {
+          const int coff = half * kColsPerWarp + c;
+          uint32_t a0[32], a1[32];
+          ptx::tmem_ld_32x32(tmem_base + ((quarter * 32u) << 16) + as * BN + coff, a0);
+          ptx::tmem_ld_32x32(tmem_base + ((quarter * 32u) << 16) + as * BN + coff + 32, a1);
+          ptx::tmem_ld_wait();
+          push16_chunk(p, a0, a1, row, n_blk * BN + coff, lane, epi_stage);
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) release(as);
+        ++accn;
+      } else if constexpr (CH == 0) {
         const uint32_t as = accn & 1u;
         ptx::mbar_wait(&tmem_full_bar[as], (accn >> 1) & 1u);
         ptx::tc_fence_after();

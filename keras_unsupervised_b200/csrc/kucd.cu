@@ -285,6 +285,7 @@ struct kucd_rbm {
   // fused reduction over peer-mapped memory (data-parallel ranks on one NVLink domain)
   bool peer_on = false;    // peer memory is mapped
   bool fused_now = false;  // the current training call exchanges through it (decided per call, see choose_exchange)
+  bool wire16 = false;     // partial dW sums cross NVLink as bf16 (KUCD_WIRE_BF16=1 at peer attach; changes the arithmetic)
   DevBuf arena;               // [n dW slots | n bias slots | flags | epoch]
   PeerSet ps{};
   void* peer_open[16] = {};   // pointers obtained from cudaIpcOpenMemHandle (to be closed)
@@ -695,14 +696,22 @@ static int delta_w(kucd_rbm* r, const Planes& v0, const Planes& h0, const Planes
   p.m_valid = static_cast<int32_t>(r->V);
   p.dyn = dyn;
   p.a_dyn_mask = dyn_mask;
+  int epi = kEpiRaw;
   if (r->fused_now) {  // each output row goes straight into its owner's slot for this rank
     p.push_rows = static_cast<int32_t>(r->rows_per);
-    for (int o = 0; o < ctx->world; ++o) p.push_base[o] = r->ps.dw_slot[o] + ctx->rank * r->slice_elems;
+    for (int o = 0; o < ctx->world; ++o) {
+      if (r->wire16)  // bf16 slots: same element pitch, half the bytes
+        p.push_base[o] = reinterpret_cast<float*>(reinterpret_cast<__nv_bfloat16*>(r->ps.dw_slot[o]) +
+                                                  ctx->rank * r->slice_elems);
+      else
+        p.push_base[o] = r->ps.dw_slot[o] + ctx->rank * r->slice_elems;
+    }
+    if (r->wire16) epi = kEpiRawPush16;
   }
   std::string err;
   const bool prof = ctx->profile && dyn == nullptr;
   const size_t pe0 = prof ? prof_event(ctx) : 0;
-  if (!launch_gemm(p, ops, kEpiRaw, ctx->num_sms, ctx->stream, &err, 0, r->compute == KUCD_COMPUTE_F32X3))
+  if (!launch_gemm(p, ops, epi, ctx->num_sms, ctx->stream, &err, 0, r->compute == KUCD_COMPUTE_F32X3))
     return fail(KUCD_ERR_CUDA, "%s", err.c_str());
   if (prof) ctx->marks.push_back({1, pe0, prof_event(ctx), 1});
   ctx->tm.gemm_launches++;
@@ -783,7 +792,8 @@ static int apply_update(kucd_rbm* r, const kucd_hparams* hp, int64_t rows_global
       const int64_t rows = std::max<int64_t>(0, std::min<int64_t>(r->rows_per, r->V - r0));
       const int64_t n4 = rows * r->ldH / 4;
       if (n4 > 0) {
-        update_w_sharded_kernel<<<grid_for(ctx, n4, 256), 256, 0, ctx->stream>>>(
+        auto kern = r->wire16 ? update_w_sharded_kernel<true> : update_w_sharded_kernel<false>;
+        kern<<<grid_for(ctx, n4, 256), 256, 0, ctx->stream>>>(
             r->W32.as<float>(), r->ps.dw_slot[me], r->slice_elems, n, use_mom ? r->mW.as<float>() : nullptr, r->ps,
             r0 * r->ldH, n4, hp->lr, scale, hp->momentum, hp->weight_decay, sdyn, world);
         ctx->tm.aux_launches++;
@@ -845,11 +855,13 @@ static int apply_update(kucd_rbm* r, const kucd_hparams* hp, int64_t rows_global
 // per-rank minibatch of ~2000 rows.  Measured: C3 (4096 rows per rank) 2.59 ms fused vs 2.76 ms NCCL at 8 ranks; C4
 // (1024 rows per rank, 512 MiB of dW) 3.13 ms fused vs 2.95 ms NCCL.  Fixed for the whole call: the two paths keep the
 // fp32 master differently between steps.  KUCD_FUSED_MIN_ROWS overrides the threshold.
+// With bf16 partial sums (KUCD_WIRE_BF16=1) half the bytes cross, so the break-even moves to ~1000 rows per rank.
 static void choose_exchange(kucd_rbm* r, int64_t rows_per_rank) {
-  static const int64_t min_rows = [] {
+  static const int64_t min_rows_env = [] {
     const char* e = getenv("KUCD_FUSED_MIN_ROWS");
-    return e != nullptr ? static_cast<int64_t>(atoll(e)) : static_cast<int64_t>(2048);
+    return e != nullptr ? static_cast<int64_t>(atoll(e)) : static_cast<int64_t>(-1);
   }();
+  const int64_t min_rows = min_rows_env >= 0 ? min_rows_env : (r->wire16 ? 1024 : 2048);
   r->fused_now = r->peer_on && rows_per_rank >= min_rows;
 }
 
@@ -1676,6 +1688,10 @@ int kucd_rbm_peer_attach(kucd_rbm* r, const void* handles) {
   }
   r->epoch = r->ps.flags[me] + 64;
   r->peer_on = true;
+  {  // opt-in, fixed for the life of the mapping (the slots are laid out for one element size)
+    const char* e = getenv("KUCD_WIRE_BF16");
+    r->wire16 = e != nullptr && e[0] == '1';
+  }
   drop_host_graph(r);
   if (r->graph_exec != nullptr) {
     cudaGraphExecDestroy(r->graph_exec);

@@ -123,7 +123,7 @@ constexpr int kPreciseCH = 4;    // k-blocks (of 64) per tensor-memory accumulat
 
 template <int BN, bool A_MN, bool B_MN, int EPI, int CH = 0, int CG = 1>
 inline cudaError_t launch_one(const GemmParams& p, int num_sms, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN / CG, (EPI == kEpiRaw ? kEpiStageBytes : 0)>;
+  using Cfg = GemmCfg<BN / CG, (epi_stages(EPI) ? kEpiStageBytes : 0)>;
   auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, EPI, CH, CG>;
   static bool attr_set[kMaxDevices] = {};  // a function attribute belongs to the device it was set on
   const int dev = current_device_slot();
@@ -230,6 +230,15 @@ inline bool launch_gemm(GemmParams& p, const GemmOperands& ops, int epi, int num
   }
   cudaError_t e;
   switch (epi) {
+    case kEpiRawPush16:  // the dW contraction of the fused exchange with bf16 partial sums: MN-major operands, BN >= 128
+      if (precise || !ops.a_mn || !ops.b_mn || p.push_rows <= 0) {
+        if (err) *err = "bf16 partial sums: bf16 compute, MN-major operands and a peer-mapped destination only";
+        return false;
+      }
+      if (cg == 2) e = launch_one<256, true, true, kEpiRawPush16, 0, 2>(p, num_sms, stream);
+      else if (bn == 256) e = launch_one<256, true, true, kEpiRawPush16, 0, 1>(p, num_sms, stream);
+      else e = launch_one<128, true, true, kEpiRawPush16, 0, 1>(p, num_sms, stream);
+      break;
     case kEpiRaw: e = launch_bn<kEpiRaw>(p, bn, precise, cg, ops.a_mn, ops.b_mn, num_sms, stream); break;
     case kEpiSample: e = launch_bn<kEpiSample>(p, bn, precise, cg, ops.a_mn, ops.b_mn, num_sms, stream); break;
     case kEpiProb: e = launch_bn<kEpiProb>(p, bn, precise, cg, ops.a_mn, ops.b_mn, num_sms, stream); break;

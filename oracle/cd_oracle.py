@@ -285,8 +285,12 @@ class OracleRBM:
         return (-(vb + softplus(self.pre_h(v)).sum(axis=-1))).astype(F32)
 
     # ---- CD statistics ----
-    def cd_stats(self, v, u_h, u_v, k=1, persistent=False, u_hc=None):
+    def cd_stats(self, v, u_h, u_v, k=1, persistent=False, u_hc=None, wire_shards=0):
         """rbm.py:119-126,131,134 generalised to CD-k / PCD.
+
+        wire_shards = n > 0 models the engine's opt-in "bf16 partial sums on the wire" exchange: the minibatch rows
+        are n contiguous shards (one per data-parallel rank), each shard's part of dW is rounded to bf16 (RNE) and
+        the n parts are summed in rank order in float32.
 
         u_h[0] draws h_pos; u_v[t] (t = 1..k) draws the t-th v_neg; u_h[t] (t = 1..k-1) the intermediate
         hidden samples; the final hidden term is the probability (rbm.py:124).  With `persistent` the
@@ -313,7 +317,17 @@ class OracleRBM:
         else:
             hn_mm, v0_mm, vn_mm = h_neg, v, v_neg
         f = np.float32 if self.compute == "f32" else np.float64
-        dW = (v0_mm.astype(f).T @ h_pos.astype(f) - vn_mm.astype(f).T @ hn_mm.astype(f)).astype(F32)  # :125-126
+        if wire_shards and wire_shards > 0:
+            if rows % wire_shards:
+                raise ValueError("rows must divide by wire_shards")
+            rb = rows // wire_shards
+            dW = np.zeros((self.V, self.H), dtype=F32)
+            for s in range(wire_shards):
+                sl = slice(s * rb, (s + 1) * rb)
+                part = v0_mm[sl].astype(f).T @ h_pos[sl].astype(f) - vn_mm[sl].astype(f).T @ hn_mm[sl].astype(f)
+                dW = (dW + bf16_round(part.astype(F32))).astype(F32)
+        else:
+            dW = (v0_mm.astype(f).T @ h_pos.astype(f) - vn_mm.astype(f).T @ hn_mm.astype(f)).astype(F32)  # :125-126
         dc = (h_pos.astype(f).sum(0) - h_neg.astype(f).sum(0)).astype(F32)  # :131 (the fp32 probabilities)
         db = (v0_mm.astype(f).sum(0) - vn_mm.astype(f).sum(0)).astype(F32)                             # :134
         return dict(h_pos=h_pos, p_h_pos=p_h_pos, v_neg=v_neg, h_neg=h_neg, dW=dW, dc=dc, db=db, rows=rows)
@@ -341,7 +355,8 @@ class OracleRBM:
         """One chain, all three parameters from the same statistics (the engine's timed schedule)."""
         persistent = kw.pop("persistent", False)
         u_hc = kw.pop("u_hc", None)
-        st = self.cd_stats(v, u_h, u_v, k=k, persistent=persistent, u_hc=u_hc)
+        wire_shards = kw.pop("wire_shards", 0)
+        st = self.cd_stats(v, u_h, u_v, k=k, persistent=persistent, u_hc=u_hc, wire_shards=wire_shards)
         self.apply(st, lr, 7, **kw)
         return st
 

@@ -53,16 +53,25 @@ def main():
                 solo.fit_epoch(sds, B, hp, want_stats=False)
             solo_ctx.sync()
             Ws, bs, cs = solo.get_params()
+            # KUCD_WIRE_BF16=1 (opt-in): each rank's part of dW is rounded to bf16 before it crosses NVLink; the oracle
+            # models exactly that, the single-GPU run does not
+            wire16 = name == "bf16" and os.environ.get("KUCD_WIRE_BF16", "0") == "1" and m.fused_reduce
             orc = O.OracleRBM(W, b, c, compute="f64" if name == "f32" else "bf16")
-            O.philox_fit(orc, data, B, 2, 1e-3, seed, k=k)
+            O.philox_fit(orc, data, B, 2, 1e-3, seed, k=k, wire_shards=world if wire16 else 0)
             d_solo = float(np.abs(Wd - Ws).max())
             d_orc = float(np.abs(Wd - orc.W).mean())
-            print("[dp_check] %s world=%d fused_reduce=%s (steps enqueued: fused %d, nccl all-reduce %d)  "
+            print("[dp_check] %s world=%d fused_reduce=%s wire_bf16=%s (steps enqueued: fused %d, nccl all-reduce %d)  "
                   "max|W_dp - W_1gpu| = %.3e  mean|W_dp - W_oracle| = %.3e"
-                  % (name, world, m.fused_reduce, t["fused_reduce_steps"], t["allreduce_calls"], d_solo, d_orc), flush=True)
+                  % (name, world, m.fused_reduce, wire16, t["fused_reduce_steps"], t["allreduce_calls"], d_solo, d_orc), flush=True)
             # identical samples => only the fp32 reduction order differs
-            ok &= d_solo < 2e-6 and float(np.abs(bd - bs).max()) < 2e-6 and float(np.abs(cd - cs).max()) < 2e-6
-            ok &= d_orc < 5e-6
+            if wire16:
+                # the rounded parts move W by up to a bf16 ulp of a partial sum (~0.25) times lr per step, after which
+                # a few samples differ from the single-GPU run: the yardstick is the oracle's model of the rounding
+                ok &= d_solo < 2e-2 and d_orc < 5e-6
+                ok &= float(np.abs(bd - orc.b).mean()) < 1e-5 and float(np.abs(cd - orc.c).mean()) < 1e-5
+            else:
+                ok &= d_solo < 2e-6 and d_orc < 5e-6
+                ok &= float(np.abs(bd - bs).max()) < 2e-6 and float(np.abs(cd - cs).max()) < 2e-6
             ok &= t["graph_launches"] == 12
             if name == "bf16" and world <= 8 and os.environ.get("KUCD_FUSED_REDUCE", "1") != "0":
                 ok &= m.fused_reduce and t["fused_reduce_steps"] > 0 and t["allreduce_calls"] == 0

@@ -153,3 +153,40 @@ def test_philox_stream_is_frozen():
     np.testing.assert_allclose(n, [[0.4989447295665741, -0.22053277492523193, -0.8862244486808777, 0.9142584204673767]],
                                rtol=1e-6)
     assert O.draw_id("train", 3, 5) == 197 and O.draw_id("infer", 2) == (1 << 63) + 2 and O.draw_id("score", 1, 1) == (1 << 62) + 3
+
+
+def test_wire_shards_model_of_bf16_partial_sums():
+    """cd_stats(wire_shards=n): every shard's part of dW is rounded to bf16 and the parts are added in float32.  With
+    8 rows per shard the binary positive term is an integer <= 8 (exact in bf16), so the only rounding is that of the
+    negative term's partial sums: the result stays within one bf16 ulp per shard of the unsharded dW, equals it when
+    the probabilities are dyadic, and equals the explicit per-shard computation."""
+    rng = np.random.default_rng(11)
+    V, H, B, n = 24, 16, 32, 4
+    W, b, c = O.OracleRBM.init_params(V, H, seed=3)
+    x = (rng.random((B, V)) < 0.4).astype(np.float32)
+    u_h, u_v = O.lattice_uniform(rng, (B, H)), O.lattice_uniform(rng, (B, V))
+    plain = O.OracleRBM(W, b, c, compute="bf16").cd_stats(x, [u_h], [None, u_v])
+    wired = O.OracleRBM(W, b, c, compute="bf16").cd_stats(x, [u_h], [None, u_v], wire_shards=n)
+    for key in ("h_pos", "v_neg", "h_neg", "db", "dc"):
+        assert np.array_equal(plain[key], wired[key])
+    # explicit per-shard computation
+    rb = B // n
+    hn = O.bf16_round(plain["h_neg"]).astype(np.float64)
+    acc = np.zeros((V, H), np.float32)
+    for s in range(n):
+        sl = slice(s * rb, (s + 1) * rb)
+        part = x[sl].astype(np.float64).T @ plain["h_pos"][sl].astype(np.float64) - \
+            plain["v_neg"][sl].astype(np.float64).T @ hn[sl]
+        acc = (acc + O.bf16_round(part.astype(np.float32))).astype(np.float32)
+    assert np.array_equal(acc, wired["dW"])
+    # within n bf16 ulps (2^-8 relative each) of partial sums bounded by rb
+    assert np.abs(wired["dW"] - plain["dW"]).max() <= n * rb * 2.0 ** -8
+    assert np.abs(wired["dW"] - plain["dW"]).max() > 0  # the rounding is visible at these sizes
+    # zero weights and biases: every probability is exactly 1/2, the parts are multiples of 1/2 below 2^8 -> exact
+    z = O.OracleRBM(np.zeros_like(W), np.zeros_like(b), np.zeros_like(c), compute="bf16")
+    a = z.cd_stats(x, [u_h], [None, u_v])
+    z2 = O.OracleRBM(np.zeros_like(W), np.zeros_like(b), np.zeros_like(c), compute="bf16")
+    w = z2.cd_stats(x, [u_h], [None, u_v], wire_shards=n)
+    assert np.array_equal(a["dW"], w["dW"])
+    with pytest.raises(ValueError):
+        O.OracleRBM(W, b, c).cd_stats(x[:30], [u_h[:30]], [None, u_v[:30]], wire_shards=4)
