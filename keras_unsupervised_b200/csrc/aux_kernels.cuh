@@ -799,14 +799,15 @@ __global__ void update_w_sharded_kernel(float* __restrict__ W, const float* __re
 
 // Streamed fit under graph replay: the step's statistic goes straight into the caller-visible page-locked array (a
 // 4-byte posted write over PCIe), slot = index of the minibatch inside this pass (row_off advances by `batch` per step).
+// A chunked fit restarts row_off at every chunk; dyn->pad then carries the index of the chunk's first minibatch.
 __global__ void log_stat_kernel(const float* __restrict__ stat, const StepDyn* dyn, int32_t batch, float* host_log) {
-  host_log[dyn->row_off / batch] = *stat;
+  host_log[dyn->pad + dyn->row_off / batch] = *stat;
 }
 
-__global__ void set_dyn_kernel(StepDyn* dyn, int64_t row_off, int32_t rows_valid, uint64_t step) {
+__global__ void set_dyn_kernel(StepDyn* dyn, int64_t row_off, int32_t rows_valid, uint64_t step, int32_t slot_base = 0) {
   dyn->row_off = row_off;
   dyn->rows_valid = rows_valid;
-  dyn->pad = 0;
+  dyn->pad = slot_base;
   dyn->step = step;
 }
 

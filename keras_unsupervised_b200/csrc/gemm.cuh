@@ -59,7 +59,7 @@ __host__ __device__ constexpr bool epi_stages(int epi) { return epi == kEpiRaw |
 struct StepDyn {
   int64_t row_off;     // first data-set row of the current minibatch
   int32_t rows_valid;  // rows of the current minibatch (< batch on the remainder step, rbm.py:211)
-  int32_t pad;
+  int32_t pad;         // chunked streaming: index of the first minibatch of the current chunk (log_stat_kernel); else 0
   uint64_t step;       // minibatch counter: offsets the Philox draw id
 };
 

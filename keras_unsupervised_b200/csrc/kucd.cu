@@ -255,9 +255,10 @@ struct HostGraphKey {
   int live = 0;
   const void* vin = nullptr;
   const void* log = nullptr;
+  int64_t chunk_rows = 0;  // > 0: the step reads a resident chunk of that many rows at StepDyn::row_off
   bool operator==(const HostGraphKey& o) const {
     return batch == o.batch && global_row0 == o.global_row0 && fused == o.fused && live == o.live && vin == o.vin &&
-           log == o.log && memcmp(&hp, &o.hp, sizeof hp) == 0;
+           log == o.log && chunk_rows == o.chunk_rows && memcmp(&hp, &o.hp, sizeof hp) == 0;
   }
 };
 
@@ -277,6 +278,7 @@ struct kucd_rbm {
   // workspaces, sized for `cap` rows
   int64_t cap = 0;
   PlaneBuf vin, vin2, h0, hk, vk;  // vin2: second staging slot of the host-streaming fit
+  PlaneBuf chunk;   // chunked streaming (KUCD_STREAM_CHUNK): operand planes of several staged minibatches
   PlaneBuf chains;  // persistent chains (n_chains, ldV)
   int64_t n_chains = 0;
   DevBuf fe0, fe1, sp0, sp1, pstage, stats, flag;
@@ -1334,15 +1336,16 @@ static int enqueue_score(kucd_rbm* r, const Planes& v0, int64_t rows, const floa
   return KUCD_OK;
 }
 
-static int enqueue_recon(kucd_rbm* r, const Planes& v0, int64_t rows) {
+// v0_dyn != nullptr: v0 is a resident block of rows and the minibatch starts at v0_dyn->row_off (graph replay)
+static int enqueue_recon(kucd_rbm* r, const Planes& v0, int64_t rows, const StepDyn* v0_dyn = nullptr) {
   kucd_ctx* ctx = r->ctx;
   float* acc = r->stats.as<float>() + 8;
   CU_TRY(cudaMemsetAsync(acc, 0, 4, ctx->stream));
   const Planes vk = r->vk.view(rows, r->V, r->last_vk_parts);
   recon_kernel<<<grid_for(ctx, rows * r->V, 256), 256, 0, ctx->stream>>>(
       v0.p[0], v0.mid(), v0.lo(), v0.ld, 0, vk.p[0], vk.mid(), vk.lo(), vk.ld, static_cast<int32_t>(rows),
-      static_cast<int32_t>(r->V), nullptr, acc);
-  recon_finish_kernel<<<1, 1, 0, ctx->stream>>>(acc, static_cast<int32_t>(rows), static_cast<int32_t>(r->V), nullptr,
+      static_cast<int32_t>(r->V), v0_dyn, acc);
+  recon_finish_kernel<<<1, 1, 0, ctx->stream>>>(acc, static_cast<int32_t>(rows), static_cast<int32_t>(r->V), v0_dyn,
                                                 r->stats.as<float>());
   ctx->tm.aux_launches += 2;
   CU_TRY(cudaGetLastError());
@@ -1579,7 +1582,7 @@ int kucd_rbm_destroy(kucd_rbm* r) {
   for (DevBuf* b : {&r->W32, &r->b32, &r->c32, &r->mW, &r->mb, &r->mc, &r->grad, &r->fe0, &r->fe1, &r->sp0, &r->sp1,
                     &r->pstage, &r->stats, &r->flag, &r->dyn, &r->chain_done})
     b->release();
-  for (PlaneBuf* p : {&r->Wp, &r->vin, &r->vin2, &r->h0, &r->hk, &r->vk, &r->chains}) p->release();
+  for (PlaneBuf* p : {&r->Wp, &r->vin, &r->vin2, &r->chunk, &r->h0, &r->hk, &r->vk, &r->chains}) p->release();
   delete r;
   return KUCD_OK;
 }
@@ -2274,6 +2277,163 @@ static int fit_range_impl(kucd_rbm* r, kucd_dataset* ds, int64_t batch, const ku
   return KUCD_OK;
 }
 
+// Chunked variant of the streamed fit for latency-bound minibatches (KUCD_STREAM_CHUNK = C > 1, off by default until
+// measured): C minibatches travel per copy, one ingest launch expands them into resident operand planes, and their
+// steps replay the captured graph of kucd_rbm_fit_range (minibatch offset, draw counter in StepDyn) - one copy ->
+// ingest -> step hand-over per C steps instead of per step.  The raw staging is double-buffered, so the copy of
+// chunk j+1 overlaps the steps of chunk j.  The remainder minibatch (at most one, rbm.py:211) runs as direct
+// launches.  Same draws, same arithmetic, same per-step statistics as the per-minibatch stream.
+static int fit_host_chunked(kucd_rbm* r, const kucd_tensor* V_all, int64_t batch, const kucd_hparams* hp,
+                            int64_t global_row0, float* host_stats, int64_t chunk_steps) {
+  kucd_ctx* ctx = r->ctx;
+  const int64_t N = V_all->shape[0];
+  const int64_t steps = (N + batch - 1) / batch;
+  const int64_t pitch = row_pitch_bytes(V_all), rb = row_bytes(V_all);
+  const bool packed = is_packed(V_all);
+  const int64_t cols = r->V;
+  const bool x3 = r->compute == KUCD_COMPUTE_F32X3;
+  const int nplanes = x3 ? 3 : 1;
+  const int live = (x3 && V_all->dtype_code == KUCD_DT_FLOAT) ? 3 : 1;
+  const int64_t chunk_rows = chunk_steps * batch;
+  const int64_t nchunks = (N + chunk_rows - 1) / chunk_rows;
+  for (int i = 0; i < 2; ++i) KU_TRY(ctx->stage_raw[i].ensure(static_cast<size_t>(chunk_rows) * rb));
+  KU_TRY(r->chunk.ensure(chunk_rows, r->ldV, nplanes));
+  if (hp->momentum != 0.f) {  // allocate outside the capture
+    KU_TRY(r->mW.ensure(static_cast<size_t>(r->V) * r->ldH * 4, true));
+    KU_TRY(r->mb.ensure(r->ldVb() * 4, true));
+    KU_TRY(r->mc.ensure(r->ldHb() * 4, true));
+  }
+  StepDyn* dyn = r->dyn.as<StepDyn>();
+  Planes block = r->chunk.view(chunk_rows, r->V, nplanes);
+  block.n = live;
+
+  HostGraphKey key;
+  key.batch = batch;
+  key.global_row0 = global_row0;
+  key.hp = *hp;
+  key.hp.want_stats = 0;
+  key.fused = r->fused_now;
+  key.live = live;
+  key.vin = r->chunk.buf[0].p;
+  key.log = host_stats;
+  key.chunk_rows = chunk_rows;
+  if (r->hgraph_exec == nullptr || !(r->hgraph_key == key)) {
+    drop_host_graph(r);
+    CU_TRY(cudaStreamSynchronize(ctx->stream));
+    const int64_t k0 = ctx->tm.gemm_launches + ctx->tm.aux_launches;
+    const int64_t no_end = int64_t{1} << 60;  // replayed steps are full minibatches: rows_valid stays `batch`
+    CU_TRY(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed));
+    int crc = enqueue_cd(r, block, batch, hp, nullptr, global_row0, 0, dyn, true);
+    if (crc == KUCD_OK && host_stats != nullptr) {
+      crc = enqueue_recon(r, block, batch, dyn);
+      log_stat_kernel<<<1, 1, 0, ctx->stream>>>(r->stats.as<float>() + 1, dyn, static_cast<int32_t>(batch), host_stats);
+      ctx->tm.aux_launches++;
+    }
+    bool advanced = false;
+    if (crc == KUCD_OK) crc = apply_update(r, hp, batch * ctx->world, dyn, static_cast<int32_t>(batch), no_end, &advanced);
+    if (crc == KUCD_OK && !advanced) {
+      advance_dyn_kernel<<<1, 1, 0, ctx->stream>>>(dyn, static_cast<int32_t>(batch), no_end);
+      ctx->tm.aux_launches++;
+    }
+    cudaGraph_t g = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(ctx->stream, &g);
+    if (crc != KUCD_OK) {
+      if (g != nullptr) cudaGraphDestroy(g);
+      return crc;
+    }
+    if (ce != cudaSuccess) return fail(KUCD_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
+    cudaGraphExec_t ge = nullptr;
+    const cudaError_t ie = cudaGraphInstantiate(&ge, g, 0);
+    if (ie != cudaSuccess) {
+      cudaGraphDestroy(g);
+      return fail(KUCD_ERR_CUDA, "graph instantiation failed: %s", cudaGetErrorString(ie));
+    }
+    r->hgraph = g;
+    r->hgraph_exec = ge;
+    r->hgraph_key = key;
+    r->hgraph_kernels = ctx->tm.gemm_launches + ctx->tm.aux_launches - k0;  // recorded while capturing, not run
+  }
+
+  auto rows_of_chunk = [&](int64_t j) { return std::min(chunk_rows, N - j * chunk_rows); };
+  auto copy_in = [&](int64_t j) -> int {
+    const int slot = static_cast<int>(j & 1);
+    if (j >= 2) CU_TRY(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_consumed[slot], 0));
+    const char* src = static_cast<const char*>(V_all->data) + j * chunk_rows * pitch;
+    const int64_t n = rows_of_chunk(j);
+    if (pitch == rb) {
+      CU_TRY(cudaMemcpyAsync(ctx->stage_raw[slot].p, src, static_cast<size_t>(n) * rb, cudaMemcpyHostToDevice,
+                             ctx->copy_stream));
+    } else {
+      CU_TRY(cudaMemcpy2DAsync(ctx->stage_raw[slot].p, rb, src, pitch, rb, n, cudaMemcpyHostToDevice, ctx->copy_stream));
+    }
+    CU_TRY(cudaEventRecord(ctx->ev_copied[slot], ctx->copy_stream));
+    ctx->tm.h2d_bytes += n * rb;
+    return KUCD_OK;
+  };
+  auto ingest = [&](const void* src, int64_t n) {
+    const int grid = grid_for(ctx, n * (block.ld / 8), 256);
+    if (packed) {
+      ingest_bits_kernel<<<grid, 256, 0, ctx->stream>>>(static_cast<const uint8_t*>(src), rb, n, cols, block.p[0],
+                                                        block.p[1], block.p[2], block.ld, nplanes);
+    } else {
+      by_dtype(V_all, [&](auto* tag) {
+        using T = std::remove_pointer_t<decltype(tag)>;
+        ingest_kernel<T><<<grid, 256, 0, ctx->stream>>>(static_cast<const T*>(src), cols, n, cols, block.p[0], block.p[1],
+                                                        block.p[2], block.ld, nplanes, nullptr);
+        return 0;
+      });
+    }
+    ctx->tm.aux_launches++;
+  };
+
+  int rc = KUCD_OK;
+  if (cudaEventRecord(ctx->ev0, ctx->stream) != cudaSuccess) rc = fail(KUCD_ERR_CUDA, "event record failed");
+  if (rc == KUCD_OK) rc = copy_in(0);
+  for (int64_t j = 0; j < nchunks && rc == KUCD_OK; ++j) {
+    const int slot = static_cast<int>(j & 1);
+    const int64_t n = rows_of_chunk(j);
+    if (j + 1 < nchunks) rc = copy_in(j + 1);
+    if (rc != KUCD_OK) break;
+    if (cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[slot], 0) != cudaSuccess) {
+      rc = fail(KUCD_ERR_CUDA, "stream wait failed");
+      break;
+    }
+    ingest(ctx->stage_raw[slot].p, n);  // ordered after the previous chunk's steps: they read the same planes
+    cudaEventRecord(ctx->ev_consumed[slot], ctx->stream);  // the raw staging slot is free again
+    const int64_t full = n / batch;
+    if (full > 0) {
+      set_dyn_kernel<<<1, 1, 0, ctx->stream>>>(dyn, 0, static_cast<int32_t>(batch), r->step_count,
+                                               static_cast<int32_t>(j * chunk_steps));
+      ctx->tm.aux_launches++;
+      for (int64_t s2 = 0; s2 < full && rc == KUCD_OK; ++s2)
+        if (cudaGraphLaunch(r->hgraph_exec, ctx->stream) != cudaSuccess) rc = fail(KUCD_ERR_CUDA, "graph launch failed");
+      r->step_count += full;
+      ctx->tm.graph_launches += full;
+      ctx->tm.graph_kernel_launches += full * r->hgraph_kernels;
+      if (host_stats != nullptr) ctx->tm.d2h_bytes += 4 * full;
+    }
+    const int64_t rem = n - full * batch;
+    if (rem > 0 && rc == KUCD_OK) {  // the remainder minibatch (last chunk only)
+      Planes v0 = block;
+      for (int i = 0; i < 3; ++i)
+        if (v0.p[i] != nullptr) v0.p[i] += full * batch * v0.ld;
+      v0.rows = rem;
+      rc = enqueue_cd(r, v0, rem, hp, nullptr, global_row0, r->step_count, nullptr, false);
+      r->step_count++;
+      if (rc == KUCD_OK && host_stats != nullptr) {
+        rc = enqueue_recon(r, v0, rem);
+        if (rc == KUCD_OK && cudaMemcpyAsync(host_stats + (steps - 1), r->stats.as<float>() + 1, 4, cudaMemcpyDeviceToHost,
+                                             ctx->stream) != cudaSuccess)
+          rc = fail(KUCD_ERR_CUDA, "statistic read-back failed");
+        ctx->tm.d2h_bytes += 4;
+      }
+      if (rc == KUCD_OK) rc = apply_update(r, hp, rem * ctx->world);
+    }
+  }
+  if (rc == KUCD_OK && cudaGetLastError() != cudaSuccess) rc = fail(KUCD_ERR_CUDA, "chunked fit: launch failed");
+  return rc;
+}
+
 // One pass over a HOST-resident matrix (rbm.py:163-223 with V as the caller's numpy array): the copy of
 // minibatch i+1 (copy stream, double-buffered staging) overlaps the Gibbs chain of minibatch i; every
 // step's reconstruction error is read back asynchronously into step_recon[i].
@@ -2324,6 +2484,27 @@ int kucd_rbm_fit_host(kucd_rbm* r, const kucd_tensor* V_all, int64_t batch, cons
       ctx->pinned_stats_cap = cap;
     }
     host_stats = ctx->pinned_stats;
+  }
+  // KUCD_STREAM_CHUNK = C > 1: latency-bound minibatches travel and are ingested C at a time (fit_host_chunked)
+  static const int64_t chunk_env = [] {
+    const char* e = getenv("KUCD_STREAM_CHUNK");
+    return e == nullptr ? int64_t{0} : static_cast<int64_t>(atoll(e));
+  }();
+  if (chunk_env > 1 && !zero_copy && N >= 2 * batch && batch * cols < (1 << 20)) {
+    int rc = fit_host_chunked(r, V_all, batch, hp, global_row0, host_stats, std::min<int64_t>(chunk_env, 4096));
+    cudaEventRecord(ctx->ev1, ctx->stream);
+    if (rc == KUCD_OK) rc = gather_master(r);
+    cudaStreamSynchronize(ctx->copy_stream);
+    const cudaError_t se = cudaStreamSynchronize(ctx->stream);
+    if (rc == KUCD_OK && se != cudaSuccess) rc = fail(KUCD_ERR_CUDA, "fit_host: %s", cudaGetErrorString(se));
+    if (host_stats != nullptr && rc == KUCD_OK) memcpy(step_recon, host_stats, steps * sizeof(float));
+    if (rc == KUCD_OK && stats != nullptr) {
+      stats->steps = steps;
+      stats->rows = N;
+      cudaEventElapsedTime(&stats->device_ms, ctx->ev0, ctx->ev1);
+      if (step_recon != nullptr) stats->last_recon_err = step_recon[steps - 1];
+    }
+    return rc;
   }
   // fp32 data in fp32-grade mode is carried in all three terms (no per-step "is it exact" round trip)
   const int live = (x3 && V_all->dtype_code == KUCD_DT_FLOAT) ? 3 : 1;

@@ -1,0 +1,68 @@
+#!/bin/bash
+# First GPU call of the next round: the two opt-in paths that were written without a GPU at the end of round 1
+# (both compile, neither has run).  Each is checked for parity first, then measured on / off inside this one call.
+#
+#   KUCD_STREAM_CHUNK=C   chunked streaming of latency-bound minibatches (kucd.cu: fit_host_chunked)
+#   KUCD_WIRE_BF16=1      bf16 partial sums of dW on the wire in the fused exchange (gemm.cuh: kEpiRawPush16)
+#
+#   gpurun --timeout 900 -- 'bash tools/run_round2_switches.sh single'          (one GPU)
+#   gpurun --gpus 8 --timeout 900 -- 'bash tools/run_round2_switches.sh multi'  (needs >= 2 GPUs; C4 is quoted on 8)
+set -u
+mkdir -p gpurun_out
+MODE=${1:-single}
+TR="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1"
+
+if [ "$MODE" = single ]; then
+  LOG=gpurun_out/r02_stream_chunk.log
+  : > $LOG
+  # parity: every test that streams from host arrays, with the chunked path forced (4 minibatches per chunk leaves a
+  # partial last chunk and a remainder minibatch at the tests' sizes)
+  echo "== parity, KUCD_STREAM_CHUNK=4" >> $LOG
+  KUCD_STREAM_CHUNK=4 timeout 600 python -m pytest tests -m gpu -x -q \
+      -k "stream or fit_host or packed or one_epoch or keras or shuffl" >> $LOG 2>&1
+  echo "rc=$?" >> $LOG
+  # measurement: one epoch of the C1 shape through kucd_rbm_fit_host, per chunk size (0 = per-minibatch stream)
+  for c in 0 4 8 16 32 64; do
+    echo "== bench c1, KUCD_STREAM_CHUNK=$c" >> $LOG
+    KUCD_STREAM_CHUNK=$c timeout 300 python bench.py --workload c1 --steps 469 --warmup 5 --no-cpu-baseline \
+        > gpurun_out/r02_bench_c1_chunk$c.json 2>> $LOG
+    python - "$c" >> $LOG <<'EOF'
+import json, sys
+try:
+    d = json.loads(open("gpurun_out/r02_bench_c1_chunk%s.json" % sys.argv[1]).read().strip().splitlines()[-1])
+    print("chunk=%s value=%.0f e2e=%.0f samples/s (e2e %.1f us per step)" % (
+        sys.argv[1], d["value"], d["e2e"]["value"], 1e3 * d["e2e"].get("ms_per_step", float("nan"))))
+except Exception as e:  # noqa: BLE001
+    print("chunk=%s: no line (%s)" % (sys.argv[1], e))
+EOF
+  done
+  cat $LOG
+else
+  N=$(python -c 'import torch; print(torch.cuda.device_count())')
+  LOG=gpurun_out/r02_wire_bf16.log
+  : > $LOG
+  echo "== dp_check, $N ranks, KUCD_WIRE_BF16=1 (oracle models the rounded partial sums)" >> $LOG
+  KUCD_WIRE_BF16=1 timeout 600 $TR --nproc-per-node $N --master-port 29531 tests/dp_check.py >> $LOG 2>&1
+  echo "rc=$?" >> $LOG
+  echo "== dp_check, $N ranks, default (must stay bit-identical to one GPU)" >> $LOG
+  timeout 600 $TR --nproc-per-node $N --master-port 29532 tests/dp_check.py >> $LOG 2>&1
+  echo "rc=$?" >> $LOG
+  for w in c4 c3; do
+    for v in "nccl KUCD_FUSED_REDUCE=0" "fused32 KUCD_FUSED_MIN_ROWS=1" "fused16 KUCD_WIRE_BF16=1"; do
+      set -- $v
+      echo "== bench $w at $N GPUs, $1 ($2)" >> $LOG
+      env $2 timeout 600 $TR --nproc-per-node $N --master-port 29533 bench.py --gpus $N --workload $w --steps 100 \
+          --warmup 5 --no-cpu-baseline --no-e2e > gpurun_out/r02_bench_${w}_n${N}_$1.json 2>> $LOG
+      python - "$w" "$N" "$1" >> $LOG <<'EOF'
+import json, sys
+w, n, v = sys.argv[1:4]
+try:
+    d = json.loads(open("gpurun_out/r02_bench_%s_n%s_%s.json" % (w, n, v)).read().strip().splitlines()[-1])
+    print("%s n=%s %s: %.3f M samples/s, %.4f ms per step" % (w, n, v, d["value"] / 1e6, d["ms_per_step"]))
+except Exception as e:  # noqa: BLE001
+    print("%s n=%s %s: no line (%s)" % (w, n, v, e))
+EOF
+    done
+  done
+  cat $LOG
+fi
