@@ -291,6 +291,8 @@ struct UpdateTail {
 //     g = scale * dW - weight_decay * W ;  m = momentum * m + lr * g ;  W += m
 // and, in the same pass, the refresh of the bf16 operand planes the contractions read.  One float4
 // of W per thread per iteration: 4 B (dW) + 4 B (W) read, 4 B (W) + 2 B per plane written per weight.
+// D16: dW is a bf16 array (the result of the bf16 all-reduce, KUCD_WIRE_BF16=1), widened here.
+template <bool D16>
 __global__ void update_w_kernel(float* __restrict__ W, const float* __restrict__ dW, float* __restrict__ mom,
                                 __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ mid,
                                 __nv_bfloat16* __restrict__ lo, int64_t n4, float lr, float scale, float momentum,
@@ -325,7 +327,14 @@ __global__ void update_w_kernel(float* __restrict__ W, const float* __restrict__
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n4;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     float4 w = reinterpret_cast<const float4*>(W)[i];
-    const float4 d = reinterpret_cast<const float4*>(dW)[i];
+    float4 d;
+    if constexpr (D16) {
+      const uint2 h = reinterpret_cast<const uint2*>(dW)[i];
+      d = make_float4(__uint_as_float(h.x << 16), __uint_as_float(h.x & 0xFFFF0000u), __uint_as_float(h.y << 16),
+                      __uint_as_float(h.y & 0xFFFF0000u));
+    } else {
+      d = reinterpret_cast<const float4*>(dW)[i];
+    }
     float4 s;
     s.x = lr * (scale * d.x - weight_decay * w.x);
     s.y = lr * (scale * d.y - weight_decay * w.y);

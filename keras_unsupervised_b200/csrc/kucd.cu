@@ -287,7 +287,9 @@ struct kucd_rbm {
   // fused reduction over peer-mapped memory (data-parallel ranks on one NVLink domain)
   bool peer_on = false;    // peer memory is mapped
   bool fused_now = false;  // the current training call exchanges through it (decided per call, see choose_exchange)
-  bool wire16 = false;     // partial dW sums cross NVLink as bf16 (KUCD_WIRE_BF16=1 at peer attach; changes the arithmetic)
+  bool wire16 = false;     // partial dW sums cross NVLink as bf16 (KUCD_WIRE_BF16=1 at creation, bf16 compute; changes the
+                           // arithmetic): bf16 slots in the fused exchange, a bf16 ncclAllReduce otherwise
+  DevBuf grad16;           // (V, ldH) bf16 dW of this rank for the bf16 all-reduce
   DevBuf arena;               // [n dW slots | n bias slots | flags | epoch]
   PeerSet ps{};
   void* peer_open[16] = {};   // pointers obtained from cudaIpcOpenMemHandle (to be closed)
@@ -324,6 +326,9 @@ static void drop_host_graph(kucd_rbm* r) {
   r->hgraph_exec = nullptr;
   r->hgraph = nullptr;
 }
+
+// this training call all-reduces dW as bf16 through NCCL (the fused exchange has its own bf16 slots)
+static bool nccl16(const kucd_rbm* r) { return r->wire16 && !r->fused_now && r->ctx->comm != nullptr; }
 
 static size_t prof_event(kucd_ctx* ctx) {
   if (ctx->ev_used == ctx->ev_pool.size()) {
@@ -709,6 +714,10 @@ static int delta_w(kucd_rbm* r, const Planes& v0, const Planes& h0, const Planes
         p.push_base[o] = r->ps.dw_slot[o] + ctx->rank * r->slice_elems;
     }
     if (r->wire16) epi = kEpiRawPush16;
+  } else if (nccl16(r)) {  // the whole dW as bf16 into the local all-reduce buffer: one "owner" holding every row
+    p.push_rows = static_cast<int32_t>(r->V);
+    p.push_base[0] = reinterpret_cast<float*>(r->grad16.p);
+    epi = kEpiRawPush16;
   }
   std::string err;
   const bool prof = ctx->profile && dyn == nullptr;
@@ -820,8 +829,11 @@ static int apply_update(kucd_rbm* r, const kucd_hparams* hp, int64_t rows_global
     tail.dyn = adv;
     tail.adv_batch = adv_batch;
     tail.adv_total = adv_total;
-    update_w_kernel<<<grid_for(ctx, std::max<int64_t>(n4, 1), 256), 256, 0, ctx->stream>>>(
-        r->W32.as<float>(), r->dW(), use_mom ? r->mW.as<float>() : nullptr, r->Wp.buf[0].as<__nv_bfloat16>(),
+    const bool d16 = nccl16(r);
+    auto kern = d16 ? update_w_kernel<true> : update_w_kernel<false>;
+    kern<<<grid_for(ctx, std::max<int64_t>(n4, 1), 256), 256, 0, ctx->stream>>>(
+        r->W32.as<float>(), d16 ? r->grad16.as<float>() : r->dW(), use_mom ? r->mW.as<float>() : nullptr,
+        r->Wp.buf[0].as<__nv_bfloat16>(),
         r->wparts == 3 ? r->Wp.buf[1].as<__nv_bfloat16>() : nullptr,
         r->wparts == 3 ? r->Wp.buf[2].as<__nv_bfloat16>() : nullptr, n4, hp->lr, scale, hp->momentum, hp->weight_decay,
         tail, sdyn, world);
@@ -865,6 +877,13 @@ static void choose_exchange(kucd_rbm* r, int64_t rows_per_rank) {
   }();
   const int64_t min_rows = min_rows_env >= 0 ? min_rows_env : (r->wire16 ? 1024 : 2048);
   r->fused_now = r->peer_on && rows_per_rank >= min_rows;
+}
+
+// what the chosen exchange needs allocated before a step is enqueued (or captured)
+static int prepare_exchange(kucd_rbm* r, int64_t rows_per_rank) {
+  choose_exchange(r, rows_per_rank);
+  if (nccl16(r)) KU_TRY(r->grad16.ensure(static_cast<size_t>(r->V) * r->ldH * 2, true));
+  return KUCD_OK;
 }
 
 // fp32 master rows updated by their owners -> every rank (NCCL broadcasts, at API boundaries only)
@@ -1218,7 +1237,7 @@ static int enqueue_cd(kucd_rbm* r, const Planes& v0, int64_t batch, const kucd_h
   // KUCD_CHAIN_DW=1 appends the dW contraction to the chain kernel as a final two-segment stage.  Measured: no gain
   // at C3 (2.529 vs 2.522 ms per step) and a loss at C4 (577 k vs 605 k samples/s) - its second segment has to wait
   // for every row block of the last projection, so it hides little - which is why it is off by default.
-  const bool chain_dw = ctx->chain_dw && !r->fused_now;
+  const bool chain_dw = ctx->chain_dw && !r->fused_now && !nccl16(r);
   // latency-bound sizes: the whole step's contractions (projections and dW) as one launch of the small-tile variant
   static const bool small_chain_env = [] {
     const char* e = getenv("KUCD_SMALL_CHAIN");
@@ -1226,7 +1245,7 @@ static int enqueue_cd(kucd_rbm* r, const Planes& v0, int64_t batch, const kucd_h
   }();
   const bool small_chain = !whole_chain && small_chain_env && ctx->chain && batch <= 512 &&
                            r->compute == KUCD_COMPUTE_BF16 && inj == nullptr && v0.n == 1 &&
-                           !r->fused_now && (!hp->persistent || r->last_vk_parts == 1);
+                           !r->fused_now && !nccl16(r) && (!hp->persistent || r->last_vk_parts == 1);
   if (whole_chain) {
     KU_TRY(launch_chain(r, v0, batch, hp, global_row0, draw0, stride, dyn, v0_dyn, chain_dw, false));
   } else if (small_chain) {
@@ -1271,8 +1290,21 @@ static int enqueue_cd(kucd_rbm* r, const Planes& v0, int64_t batch, const kucd_h
     ctx->tm.fused_reduce_steps++;
     CU_TRY(cudaGetLastError());
   } else if (ctx->comm != nullptr) {
-    const int rc = g_nccl.AllReduce(r->grad.p, r->grad.p, static_cast<size_t>(r->grad_elems()), /*ncclFloat32*/ 7,
-                                    /*ncclSum*/ 0, ctx->comm, ctx->stream);
+    int rc;
+    if (nccl16(r)) {  // dW as bf16 (half the bytes; NCCL adds in bf16), the small bias statistics as fp32, one group
+      rc = g_nccl.GroupStart();
+      if (rc == 0)
+        rc = g_nccl.AllReduce(r->grad16.p, r->grad16.p, static_cast<size_t>(r->V * r->ldH), /*ncclBfloat16*/ 9,
+                              /*ncclSum*/ 0, ctx->comm, ctx->stream);
+      if (rc == 0)
+        rc = g_nccl.AllReduce(r->db(), r->db(), static_cast<size_t>(r->ldVb() + r->ldHb()), /*ncclFloat32*/ 7,
+                              /*ncclSum*/ 0, ctx->comm, ctx->stream);
+      const int rc2 = g_nccl.GroupEnd();
+      if (rc == 0) rc = rc2;
+    } else {
+      rc = g_nccl.AllReduce(r->grad.p, r->grad.p, static_cast<size_t>(r->grad_elems()), /*ncclFloat32*/ 7,
+                            /*ncclSum*/ 0, ctx->comm, ctx->stream);
+    }
     if (rc != 0) return fail(KUCD_ERR_NCCL, "ncclAllReduce: %s", g_nccl.GetErrorString(rc));
     ctx->tm.allreduce_calls++;
   }
@@ -1548,6 +1580,10 @@ int kucd_rbm_create(kucd_ctx* ctx, int64_t V, int64_t H, int mode, int compute, 
   r->mode = mode;
   r->compute = compute;
   r->wparts = compute == KUCD_COMPUTE_F32X3 ? 3 : 1;
+  {  // opt-in, fixed for the life of the model (exchange slots and graphs are laid out for one element size)
+    const char* e = getenv("KUCD_WIRE_BF16");
+    r->wire16 = e != nullptr && e[0] == '1' && compute == KUCD_COMPUTE_BF16;
+  }
   int rc = KUCD_OK;
   auto T = [&](int x) {
     if (rc == KUCD_OK) rc = x;
@@ -1580,7 +1616,7 @@ int kucd_rbm_destroy(kucd_rbm* r) {
   for (int i = 0; i < r->n_peer_open; ++i) cudaIpcCloseMemHandle(r->peer_open[i]);
   r->arena.release();
   for (DevBuf* b : {&r->W32, &r->b32, &r->c32, &r->mW, &r->mb, &r->mc, &r->grad, &r->fe0, &r->fe1, &r->sp0, &r->sp1,
-                    &r->pstage, &r->stats, &r->flag, &r->dyn, &r->chain_done})
+                    &r->pstage, &r->stats, &r->flag, &r->dyn, &r->chain_done, &r->grad16})
     b->release();
   for (PlaneBuf* p : {&r->Wp, &r->vin, &r->vin2, &r->chunk, &r->h0, &r->hk, &r->vk, &r->chains}) p->release();
   delete r;
@@ -1691,10 +1727,7 @@ int kucd_rbm_peer_attach(kucd_rbm* r, const void* handles) {
   }
   r->epoch = r->ps.flags[me] + 64;
   r->peer_on = true;
-  {  // opt-in, fixed for the life of the mapping (the slots are laid out for one element size)
-    const char* e = getenv("KUCD_WIRE_BF16");
-    r->wire16 = e != nullptr && e[0] == '1';
-  }
+
   drop_host_graph(r);
   if (r->graph_exec != nullptr) {
     cudaGraphExecDestroy(r->graph_exec);
@@ -1895,7 +1928,7 @@ int kucd_rbm_cd_step(kucd_rbm* r, const kucd_tensor* v_batch, const kucd_hparams
   if (rows > (1 << 22)) return fail(KUCD_ERR_INVALID_ARG, "minibatch of %lld rows", (long long)rows);
   KU_TRY(ensure_workspace(r, rows));
   if (hp->persistent) KU_TRY(ensure_chains(r, rows));
-  choose_exchange(r, rows);
+  KU_TRY(prepare_exchange(r, rows));
   Planes v0;
   KU_TRY(ingest_batch(r, v_batch, 0, rows, &v0));
 
@@ -2185,7 +2218,7 @@ static int fit_range_impl(kucd_rbm* r, kucd_dataset* ds, int64_t batch, const ku
                 (long long)epoch_steps);
   const int64_t steps = step_end - step_begin;
   if (steps == 0) return KUCD_OK;
-  choose_exchange(r, batch);
+  KU_TRY(prepare_exchange(r, batch));
   KU_TRY(ensure_workspace(r, batch));
   if (hp->persistent) KU_TRY(ensure_chains(r, std::min(batch, N)));
   if (hp->momentum != 0.f) {  // allocate outside the capture
@@ -2452,7 +2485,7 @@ int kucd_rbm_fit_host(kucd_rbm* r, const kucd_tensor* V_all, int64_t batch, cons
   if (steps == 0) return KUCD_OK;
   KU_TRY(ensure_workspace(r, batch));
   if (hp->persistent) KU_TRY(ensure_chains(r, std::min(batch, N)));
-  choose_exchange(r, batch);
+  KU_TRY(prepare_exchange(r, batch));
   const int64_t pitch = row_pitch_bytes(V_all), rb = row_bytes(V_all);  // source row pitch / staged row size (bytes)
   const bool packed = is_packed(V_all);
   const int64_t cols = r->V;

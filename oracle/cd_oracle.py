@@ -285,12 +285,13 @@ class OracleRBM:
         return (-(vb + softplus(self.pre_h(v)).sum(axis=-1))).astype(F32)
 
     # ---- CD statistics ----
-    def cd_stats(self, v, u_h, u_v, k=1, persistent=False, u_hc=None, wire_shards=0):
+    def cd_stats(self, v, u_h, u_v, k=1, persistent=False, u_hc=None, wire_shards=0, wire_sum_bf16=False):
         """rbm.py:119-126,131,134 generalised to CD-k / PCD.
 
         wire_shards = n > 0 models the engine's opt-in "bf16 partial sums on the wire" exchange: the minibatch rows
         are n contiguous shards (one per data-parallel rank), each shard's part of dW is rounded to bf16 (RNE) and
-        the n parts are summed in rank order in float32.
+        the n parts are summed in rank order in float32.  wire_sum_bf16 additionally rounds the running sum to bf16
+        after every addition: a bf16 all-reduce (exact model for two ranks; for more, NCCL's order is its own).
 
         u_h[0] draws h_pos; u_v[t] (t = 1..k) draws the t-th v_neg; u_h[t] (t = 1..k-1) the intermediate
         hidden samples; the final hidden term is the probability (rbm.py:124).  With `persistent` the
@@ -326,6 +327,8 @@ class OracleRBM:
                 sl = slice(s * rb, (s + 1) * rb)
                 part = v0_mm[sl].astype(f).T @ h_pos[sl].astype(f) - vn_mm[sl].astype(f).T @ hn_mm[sl].astype(f)
                 dW = (dW + bf16_round(part.astype(F32))).astype(F32)
+                if wire_sum_bf16:
+                    dW = bf16_round(dW)
         else:
             dW = (v0_mm.astype(f).T @ h_pos.astype(f) - vn_mm.astype(f).T @ hn_mm.astype(f)).astype(F32)  # :125-126
         dc = (h_pos.astype(f).sum(0) - h_neg.astype(f).sum(0)).astype(F32)  # :131 (the fp32 probabilities)
@@ -356,7 +359,9 @@ class OracleRBM:
         persistent = kw.pop("persistent", False)
         u_hc = kw.pop("u_hc", None)
         wire_shards = kw.pop("wire_shards", 0)
-        st = self.cd_stats(v, u_h, u_v, k=k, persistent=persistent, u_hc=u_hc, wire_shards=wire_shards)
+        wire_sum_bf16 = kw.pop("wire_sum_bf16", False)
+        st = self.cd_stats(v, u_h, u_v, k=k, persistent=persistent, u_hc=u_hc, wire_shards=wire_shards,
+                           wire_sum_bf16=wire_sum_bf16)
         self.apply(st, lr, 7, **kw)
         return st
 

@@ -55,9 +55,11 @@ def main():
             Ws, bs, cs = solo.get_params()
             # KUCD_WIRE_BF16=1 (opt-in): each rank's part of dW is rounded to bf16 before it crosses NVLink; the oracle
             # models exactly that, the single-GPU run does not
-            wire16 = name == "bf16" and os.environ.get("KUCD_WIRE_BF16", "0") == "1" and m.fused_reduce
+            # (fused exchange: parts summed in fp32 by the owner; NCCL: a bf16 all-reduce, modelled exactly for 2 ranks)
+            wire16 = name == "bf16" and os.environ.get("KUCD_WIRE_BF16", "0") == "1"
             orc = O.OracleRBM(W, b, c, compute="f64" if name == "f32" else "bf16")
-            O.philox_fit(orc, data, B, 2, 1e-3, seed, k=k, wire_shards=world if wire16 else 0)
+            O.philox_fit(orc, data, B, 2, 1e-3, seed, k=k, wire_shards=world if wire16 else 0,
+                         wire_sum_bf16=wire16 and not m.fused_reduce)
             d_solo = float(np.abs(Wd - Ws).max())
             d_orc = float(np.abs(Wd - orc.W).mean())
             print("[dp_check] %s world=%d fused_reduce=%s wire_bf16=%s (steps enqueued: fused %d, nccl all-reduce %d)  "
@@ -67,7 +69,7 @@ def main():
             if wire16:
                 # the rounded parts move W by up to a bf16 ulp of a partial sum (~0.25) times lr per step, after which
                 # a few samples differ from the single-GPU run: the yardstick is the oracle's model of the rounding
-                ok &= d_solo < 2e-2 and d_orc < 5e-6
+                ok &= d_solo < 2e-2 and d_orc < (5e-6 if (m.fused_reduce or world == 2) else 2e-4)
                 ok &= float(np.abs(bd - orc.b).mean()) < 1e-5 and float(np.abs(cd - orc.c).mean()) < 1e-5
             else:
                 ok &= d_solo < 2e-6 and d_orc < 5e-6

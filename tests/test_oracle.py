@@ -188,5 +188,9 @@ def test_wire_shards_model_of_bf16_partial_sums():
     z2 = O.OracleRBM(np.zeros_like(W), np.zeros_like(b), np.zeros_like(c), compute="bf16")
     w = z2.cd_stats(x, [u_h], [None, u_v], wire_shards=n)
     assert np.array_equal(a["dW"], w["dW"])
+    # bf16 all-reduce model: the running sum is rounded too, so every entry of dW is a bf16 number
+    red = O.OracleRBM(W, b, c, compute="bf16").cd_stats(x, [u_h], [None, u_v], wire_shards=n, wire_sum_bf16=True)
+    assert np.array_equal(red["dW"], O.bf16_round(red["dW"])) and not np.array_equal(red["dW"], wired["dW"])
+    assert np.abs(red["dW"] - plain["dW"]).max() <= 2 * n * rb * 2.0 ** -8
     with pytest.raises(ValueError):
         O.OracleRBM(W, b, c).cd_stats(x[:30], [u_h[:30]], [None, u_v[:30]], wire_shards=4)
