@@ -164,6 +164,10 @@ struct kucd_ctx {
   cudaStream_t stream2 = nullptr;  // second Gibbs chain of a split minibatch
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaStream_t copy_stream = nullptr;  // host -> device staging of the next minibatch (fit_host)
+  // slab-pipelined all-reduce (KUCD_AR_SLABS): dW leaves in row slabs on comm_stream while the next slab is contracted
+  static constexpr int kMaxSlabs = 16;
+  cudaStream_t comm_stream = nullptr;
+  cudaEvent_t ev_slab[kMaxSlabs] = {}, ev_red[kMaxSlabs] = {};
   cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
   DevBuf stage_raw[2];
   bool split = true;               // KUCD_SPLIT=0 turns the two-chain schedule off, 2 forces it (tests)
@@ -290,6 +294,9 @@ struct kucd_rbm {
   bool wire16 = false;     // partial dW sums cross NVLink as bf16 (KUCD_WIRE_BF16=1 at creation, bf16 compute; changes the
                            // arithmetic): bf16 slots in the fused exchange, a bf16 ncclAllReduce otherwise
   DevBuf grad16;           // (V, ldH) bf16 dW of this rank for the bf16 all-reduce
+  int slabs_now = 1;       // > 1: this training call contracts, all-reduces and applies dW in that many row slabs
+  int64_t slab_rows = 0;   // rows of W per slab (multiple of 256)
+  int slabs_inflight = 0;  // slabs whose all-reduce was enqueued by enqueue_cd and not yet joined by apply_update
   DevBuf arena;               // [n dW slots | n bias slots | flags | epoch]
   PeerSet ps{};
   void* peer_open[16] = {};   // pointers obtained from cudaIpcOpenMemHandle (to be closed)
@@ -666,13 +673,16 @@ static int project(kucd_rbm* r, bool forward, const Planes& a, int64_t rows, con
 
 // dW = v0^T h0 - vk^T hk   (rbm.py:125-126): contraction over the minibatch rows, every operand read
 // in place (MN-major descriptors), both phases accumulated into the same tensor-memory tile.
+// [w_row0, w_row0 + w_rows): the rows of W this launch covers (a column range of the visible states); sm_reserve: SMs
+// left to a concurrent collective (slab-pipelined all-reduce).
 static int delta_w(kucd_rbm* r, const Planes& v0, const Planes& h0, const Planes& vk, const Planes& hk, int64_t rows,
-                   const StepDyn* dyn, bool v0_dyn) {
+                   const StepDyn* dyn, bool v0_dyn, int64_t w_row0 = 0, int64_t w_rows = -1, int sm_reserve = 0) {
   kucd_ctx* ctx = r->ctx;
+  if (w_rows < 0) w_rows = r->V - w_row0;
   GemmOperands ops;
   ops.a_mn = true;
   ops.b_mn = true;
-  ops.M = r->V;
+  ops.M = w_rows;
   ops.N = r->H;
   ops.K = rows;
   int pairs[9][2];
@@ -682,14 +692,14 @@ static int delta_w(kucd_rbm* r, const Planes& v0, const Planes& h0, const Planes
     int np = term_pairs(v0.n, h0.n, pairs, order);
     if (ns + np > kMaxSeg) return fail(KUCD_ERR_INVALID_ARG, "too many operand terms");
     for (int s = 0; s < np; ++s, ++ns) {
-      ops.a[ns] = MatView{v0.p[pairs[s][0]], v0.rows, v0.cols, v0.ld};
+      ops.a[ns] = MatView{v0.p[pairs[s][0]] + w_row0, v0.rows, w_rows, v0.ld};
       ops.b[ns] = MatView{h0.p[pairs[s][1]], h0.rows, h0.cols, h0.ld};
       if (v0_dyn) dyn_mask |= 1u << ns;
     }
     np = term_pairs(vk.n, hk.n, pairs, order);
     if (ns + np > kMaxSeg) return fail(KUCD_ERR_INVALID_ARG, "too many operand terms");
     for (int s = 0; s < np; ++s, ++ns) {
-      ops.a[ns] = MatView{vk.p[pairs[s][0]], vk.rows, vk.cols, vk.ld};
+      ops.a[ns] = MatView{vk.p[pairs[s][0]] + w_row0, vk.rows, w_rows, vk.ld};
       ops.b[ns] = MatView{hk.p[pairs[s][1]], hk.rows, hk.cols, hk.ld};
       neg |= 1u << ns;
     }
@@ -698,13 +708,13 @@ static int delta_w(kucd_rbm* r, const Planes& v0, const Planes& h0, const Planes
   ops.neg_mask = neg;
   GemmParams p;
   memset(&p, 0, sizeof p);
-  p.out_f32 = r->dW();
+  p.out_f32 = r->dW() + w_row0 * r->ldH;
   p.ld_f32 = r->ldH;
-  p.m_valid = static_cast<int32_t>(r->V);
+  p.m_valid = static_cast<int32_t>(w_rows);
   p.dyn = dyn;
   p.a_dyn_mask = dyn_mask;
   int epi = kEpiRaw;
-  if (r->fused_now) {  // each output row goes straight into its owner's slot for this rank
+  if (r->fused_now) {  // each output row goes straight into its owner's slot for this rank (whole-matrix launches only)
     p.push_rows = static_cast<int32_t>(r->rows_per);
     for (int o = 0; o < ctx->world; ++o) {
       if (r->wire16)  // bf16 slots: same element pitch, half the bytes
@@ -715,14 +725,15 @@ static int delta_w(kucd_rbm* r, const Planes& v0, const Planes& h0, const Planes
     }
     if (r->wire16) epi = kEpiRawPush16;
   } else if (nccl16(r)) {  // the whole dW as bf16 into the local all-reduce buffer: one "owner" holding every row
-    p.push_rows = static_cast<int32_t>(r->V);
-    p.push_base[0] = reinterpret_cast<float*>(r->grad16.p);
+    p.push_rows = static_cast<int32_t>(w_rows);
+    p.push_base[0] = reinterpret_cast<float*>(r->grad16.as<__nv_bfloat16>() + w_row0 * r->ldH);
     epi = kEpiRawPush16;
   }
   std::string err;
   const bool prof = ctx->profile && dyn == nullptr;
   const size_t pe0 = prof ? prof_event(ctx) : 0;
-  if (!launch_gemm(p, ops, epi, ctx->num_sms, ctx->stream, &err, 0, r->compute == KUCD_COMPUTE_F32X3))
+  if (!launch_gemm(p, ops, epi, std::max(2, ctx->num_sms - sm_reserve), ctx->stream, &err, 0,
+                   r->compute == KUCD_COMPUTE_F32X3))
     return fail(KUCD_ERR_CUDA, "%s", err.c_str());
   if (prof) ctx->marks.push_back({1, pe0, prof_event(ctx), 1});
   ctx->tm.gemm_launches++;
@@ -831,6 +842,30 @@ static int apply_update(kucd_rbm* r, const kucd_hparams* hp, int64_t rows_global
     tail.adv_total = adv_total;
     const bool d16 = nccl16(r);
     auto kern = d16 ? update_w_kernel<true> : update_w_kernel<false>;
+    if (r->slabs_inflight > 0) {
+      // slab-pipelined exchange: slab i is updated as soon as its all-reduce (comm stream) is done, while the later
+      // slabs are still on the wire; the bias statistics travelled with slab 0, the tail rides on the last slab
+      const int S = r->slabs_inflight;
+      r->slabs_inflight = 0;
+      if (n4 == 0) {  // W is not updated by this call: just join the collective stream
+        CU_TRY(cudaStreamWaitEvent(ctx->stream, ctx->ev_red[S - 1], 0));
+      } else {
+        for (int i = 0; i < S; ++i) {
+          CU_TRY(cudaStreamWaitEvent(ctx->stream, ctx->ev_red[i], 0));
+          const int64_t w0 = i * r->slab_rows, wn = std::min<int64_t>(r->slab_rows, r->V - w0);
+          const int64_t off = w0 * r->ldH, m4 = wn * r->ldH / 4;
+          const float* dsrc = d16 ? reinterpret_cast<const float*>(r->grad16.as<__nv_bfloat16>() + off) : r->dW() + off;
+          kern<<<grid_for(ctx, m4, 256), 256, 0, ctx->stream>>>(
+              r->W32.as<float>() + off, dsrc, use_mom ? r->mW.as<float>() + off : nullptr,
+              r->Wp.buf[0].as<__nv_bfloat16>() + off, nullptr, nullptr, m4, hp->lr, scale, hp->momentum, hp->weight_decay,
+              i == S - 1 ? tail : UpdateTail{}, sdyn, world);
+          ctx->tm.aux_launches++;
+        }
+        if (adv_done != nullptr) *adv_done = adv != nullptr;
+        CU_TRY(cudaGetLastError());
+        return KUCD_OK;
+      }
+    }
     kern<<<grid_for(ctx, std::max<int64_t>(n4, 1), 256), 256, 0, ctx->stream>>>(
         r->W32.as<float>(), d16 ? r->grad16.as<float>() : r->dW(), use_mom ? r->mW.as<float>() : nullptr,
         r->Wp.buf[0].as<__nv_bfloat16>(),
@@ -880,9 +915,34 @@ static void choose_exchange(kucd_rbm* r, int64_t rows_per_rank) {
 }
 
 // what the chosen exchange needs allocated before a step is enqueued (or captured)
+//
+// KUCD_AR_SLABS = S > 1 (NCCL path; off by default until measured): the dW contraction runs as S launches over row slabs
+// of W, each slab's ncclAllReduce is enqueued on a second stream as soon as its contraction is, and the update kernel
+// follows slab by slab - contraction, all-reduce and update overlap instead of running back to back (at C4 the three
+// are 0.45 + 1.24 + 0.3 ms of a 2.95 ms step).  The contraction leaves KUCD_AR_RESERVE_SMS SMs (default 16) to NCCL.
 static int prepare_exchange(kucd_rbm* r, int64_t rows_per_rank) {
+  kucd_ctx* ctx = r->ctx;
   choose_exchange(r, rows_per_rank);
   if (nccl16(r)) KU_TRY(r->grad16.ensure(static_cast<size_t>(r->V) * r->ldH * 2, true));
+  static const int slabs_env = [] {
+    const char* e = getenv("KUCD_AR_SLABS");
+    return e != nullptr ? atoi(e) : 1;
+  }();
+  r->slabs_now = 1;
+  if (slabs_env > 1 && !r->fused_now && ctx->comm != nullptr && r->compute == KUCD_COMPUTE_BF16) {
+    const int want = std::min(slabs_env, kucd_ctx::kMaxSlabs);
+    const int64_t rows = round_up((r->V + want - 1) / want, 256);
+    const int n = static_cast<int>((r->V + rows - 1) / rows);
+    if (n > 1) {
+      if (ctx->comm_stream == nullptr) CU_TRY(cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
+      for (int i = 0; i < n; ++i) {
+        if (ctx->ev_slab[i] == nullptr) CU_TRY(cudaEventCreateWithFlags(&ctx->ev_slab[i], cudaEventDisableTiming));
+        if (ctx->ev_red[i] == nullptr) CU_TRY(cudaEventCreateWithFlags(&ctx->ev_red[i], cudaEventDisableTiming));
+      }
+      r->slabs_now = n;
+      r->slab_rows = rows;
+    }
+  }
   return KUCD_OK;
 }
 
@@ -1237,7 +1297,8 @@ static int enqueue_cd(kucd_rbm* r, const Planes& v0, int64_t batch, const kucd_h
   // KUCD_CHAIN_DW=1 appends the dW contraction to the chain kernel as a final two-segment stage.  Measured: no gain
   // at C3 (2.529 vs 2.522 ms per step) and a loss at C4 (577 k vs 605 k samples/s) - its second segment has to wait
   // for every row block of the last projection, so it hides little - which is why it is off by default.
-  const bool chain_dw = ctx->chain_dw && !r->fused_now && !nccl16(r);
+  const bool slabbed = r->slabs_now > 1 && !r->fused_now && ctx->comm != nullptr;
+  const bool chain_dw = ctx->chain_dw && !r->fused_now && !nccl16(r) && !slabbed;
   // latency-bound sizes: the whole step's contractions (projections and dW) as one launch of the small-tile variant
   static const bool small_chain_env = [] {
     const char* e = getenv("KUCD_SMALL_CHAIN");
@@ -1245,7 +1306,7 @@ static int enqueue_cd(kucd_rbm* r, const Planes& v0, int64_t batch, const kucd_h
   }();
   const bool small_chain = !whole_chain && small_chain_env && ctx->chain && batch <= 512 &&
                            r->compute == KUCD_COMPUTE_BF16 && inj == nullptr && v0.n == 1 &&
-                           !r->fused_now && !nccl16(r) && (!hp->persistent || r->last_vk_parts == 1);
+                           !r->fused_now && !nccl16(r) && !slabbed && (!hp->persistent || r->last_vk_parts == 1);
   if (whole_chain) {
     KU_TRY(launch_chain(r, v0, batch, hp, global_row0, draw0, stride, dyn, v0_dyn, chain_dw, false));
   } else if (small_chain) {
@@ -1266,7 +1327,45 @@ static int enqueue_cd(kucd_rbm* r, const Planes& v0, int64_t batch, const kucd_h
     KU_TRY(rc);
     if (prof) ctx->marks.push_back({0, pe0, prof_event(ctx), 2 * n_proj});
   }
-  if (!((whole_chain && chain_dw) || small_chain)) KU_TRY(delta_w(r, v0, h0, vk, hk, batch, dyn, v0_dyn));
+  if (slabbed) {
+    // contraction of slab i+1 (compute stream, a few SMs left free) overlaps the all-reduce of slab i (comm stream)
+    static const int reserve = [] {
+      const char* e = getenv("KUCD_AR_RESERVE_SMS");
+      return e != nullptr ? std::max(0, atoi(e)) : 16;
+    }();
+    const bool d16 = nccl16(r);
+    const int S = r->slabs_now;
+    for (int i = 0; i < S; ++i) {
+      const int64_t w0 = i * r->slab_rows, wn = std::min<int64_t>(r->slab_rows, r->V - w0);
+      KU_TRY(delta_w(r, v0, h0, vk, hk, batch, dyn, v0_dyn, w0, wn, reserve));
+      CU_TRY(cudaEventRecord(ctx->ev_slab[i], ctx->stream));
+      CU_TRY(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_slab[i], 0));
+      const size_t off = static_cast<size_t>(w0) * r->ldH, cnt = static_cast<size_t>(wn) * r->ldH;
+      int rc = i == 0 ? g_nccl.GroupStart() : 0;
+      if (rc == 0) {
+        if (d16) {
+          __nv_bfloat16* g = r->grad16.as<__nv_bfloat16>() + off;
+          rc = g_nccl.AllReduce(g, g, cnt, /*ncclBfloat16*/ 9, /*ncclSum*/ 0, ctx->comm, ctx->comm_stream);
+        } else {
+          float* g = r->dW() + off;
+          rc = g_nccl.AllReduce(g, g, cnt, /*ncclFloat32*/ 7, /*ncclSum*/ 0, ctx->comm, ctx->comm_stream);
+        }
+      }
+      if (i == 0) {  // the bias statistics are final since the chain ended: they travel with the first slab
+        if (rc == 0)
+          rc = g_nccl.AllReduce(r->db(), r->db(), static_cast<size_t>(r->ldVb() + r->ldHb()), /*ncclFloat32*/ 7,
+                                /*ncclSum*/ 0, ctx->comm, ctx->comm_stream);
+        const int rc2 = g_nccl.GroupEnd();
+        if (rc == 0) rc = rc2;
+      }
+      if (rc != 0) return fail(KUCD_ERR_NCCL, "ncclAllReduce (slab %d): %s", i, g_nccl.GetErrorString(rc));
+      CU_TRY(cudaEventRecord(ctx->ev_red[i], ctx->comm_stream));
+    }
+    r->slabs_inflight = S;
+    ctx->tm.allreduce_calls++;
+  } else if (!((whole_chain && chain_dw) || small_chain)) {
+    KU_TRY(delta_w(r, v0, h0, vk, hk, batch, dyn, v0_dyn));
+  }
   r->last_rows = batch;
   r->last_vk_parts = vparts;
   r->last_hk_parts = pparts;
@@ -1289,7 +1388,7 @@ static int enqueue_cd(kucd_rbm* r, const Planes& v0, int64_t batch, const kucd_h
     ctx->tm.aux_launches += 2;
     ctx->tm.fused_reduce_steps++;
     CU_TRY(cudaGetLastError());
-  } else if (ctx->comm != nullptr) {
+  } else if (ctx->comm != nullptr && !slabbed) {
     int rc;
     if (nccl16(r)) {  // dW as bf16 (half the bytes; NCCL adds in bf16), the small bias statistics as fp32, one group
       rc = g_nccl.GroupStart();
@@ -1493,6 +1592,11 @@ int kucd_ctx_destroy(kucd_ctx* ctx) {
   }
   drop_event(ctx->ev_fork);
   drop_event(ctx->ev_join);
+  for (int i = 0; i < kucd_ctx::kMaxSlabs; ++i) {
+    drop_event(ctx->ev_slab[i]);
+    drop_event(ctx->ev_red[i]);
+  }
+  drop_stream(ctx->comm_stream);
   drop_stream(ctx->copy_stream);
   drop_stream(ctx->stream2);
   drop_stream(ctx->stream);

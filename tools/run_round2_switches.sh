@@ -6,6 +6,8 @@
 #   KUCD_WIRE_BF16=1      bf16 partial sums of dW on the wire: bf16 slots in the fused exchange, a bf16 ncclAllReduce
 #                         otherwise (gemm.cuh: kEpiRawPush16)
 #
+#   KUCD_AR_SLABS=S       dW contracted, all-reduced (NCCL, second stream) and applied in S row slabs that overlap
+#
 #   gpurun --timeout 900 -- 'bash tools/run_round2_switches.sh single'          (one GPU)
 #   gpurun --gpus 8 --timeout 900 -- 'bash tools/run_round2_switches.sh multi'  (needs >= 2 GPUs; C4 is quoted on 8)
 set -u
@@ -48,15 +50,21 @@ else
   echo "== dp_check, $N ranks, KUCD_WIRE_BF16=1, bf16 ncclAllReduce (exact model at 2 ranks, tolerance beyond)" >> $LOG
   KUCD_WIRE_BF16=1 KUCD_FUSED_REDUCE=0 timeout 600 $TR --nproc-per-node $N --master-port 29534 tests/dp_check.py >> $LOG 2>&1
   echo "rc=$?" >> $LOG
+  echo "== dp_check, $N ranks, KUCD_AR_SLABS=2, fp32 ncclAllReduce in row slabs (same bar as the default)" >> $LOG
+  KUCD_AR_SLABS=2 KUCD_FUSED_REDUCE=0 timeout 600 $TR --nproc-per-node $N --master-port 29535 tests/dp_check.py >> $LOG 2>&1
+  echo "rc=$?" >> $LOG
   echo "== dp_check, $N ranks, default (must stay bit-identical to one GPU)" >> $LOG
   timeout 600 $TR --nproc-per-node $N --master-port 29532 tests/dp_check.py >> $LOG 2>&1
   echo "rc=$?" >> $LOG
   for w in c4 c3; do
     for v in "nccl32 KUCD_FUSED_REDUCE=0 KUCD_WIRE_BF16=0" "nccl16 KUCD_FUSED_REDUCE=0 KUCD_WIRE_BF16=1" \
-             "fused32 KUCD_FUSED_MIN_ROWS=1 KUCD_WIRE_BF16=0" "fused16 KUCD_FUSED_MIN_ROWS=1 KUCD_WIRE_BF16=1"; do
+             "fused32 KUCD_FUSED_MIN_ROWS=1 KUCD_WIRE_BF16=0" "fused16 KUCD_FUSED_MIN_ROWS=1 KUCD_WIRE_BF16=1" \
+             "nccl32s4 KUCD_FUSED_REDUCE=0 KUCD_AR_SLABS=4" "nccl32s8 KUCD_FUSED_REDUCE=0 KUCD_AR_SLABS=8" \
+             "nccl16s4 KUCD_FUSED_REDUCE=0 KUCD_AR_SLABS=4 KUCD_WIRE_BF16=1" \
+             "nccl16s8 KUCD_FUSED_REDUCE=0 KUCD_AR_SLABS=8 KUCD_WIRE_BF16=1"; do
       set -- $v
-      echo "== bench $w at $N GPUs, $1 ($2 $3)" >> $LOG
-      env $2 $3 timeout 600 $TR --nproc-per-node $N --master-port 29533 bench.py --gpus $N --workload $w --steps 100 \
+      echo "== bench $w at $N GPUs, $1 ($2 $3 ${4:-})" >> $LOG
+      env $2 $3 ${4:-X_UNUSED=0} timeout 600 $TR --nproc-per-node $N --master-port 29533 bench.py --gpus $N --workload $w --steps 100 \
           --warmup 5 --no-cpu-baseline --no-e2e > gpurun_out/r02_bench_${w}_n${N}_$1.json 2>> $LOG
       python - "$w" "$N" "$1" >> $LOG <<'EOF'
 import json, sys
