@@ -339,6 +339,10 @@ def _main(out):
         print(json.dumps(line), file=out)
         return 0
 
+    switches = {k_: v_ for k_, v_ in sorted(os.environ.items()) if k_.startswith("KUCD_")}
+    if switches:  # a line measured off the defaults says so ("Switches")
+        config["switches"] = switches
+
     import numpy as np
     import torch
 
