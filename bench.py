@@ -149,6 +149,42 @@ def cpu_arm(cfg, steps, warmup, rows):
     return dict(value=rows * steps / dt, seconds=dt, cores=cores, rows=rows, steps=steps)
 
 
+def parse_cpulist(txt):
+    """'0-3,8,10-11' (sysfs cpulist format) -> {0, 1, 2, 3, 8, 10, 11}"""
+    cpus = set()
+    for part in txt.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_near_gpu(local_rank):
+    """One process per GPU on a multi-socket host: keep this rank's host threads - and with them (first touch) its
+    page-locked staging memory - on the CPUs local to its GPU, so that eight ranks streaming minibatches do not all pull
+    through one socket.  Returns the CPU list it bound to, or None (single NUMA node, restricted cpuset, no sysfs ...).
+    KUCD_BENCH_NUMA=0 turns it off."""
+    if os.environ.get("KUCD_BENCH_NUMA", "1") == "0":
+        return None
+    try:
+        import torch
+
+        p = torch.cuda.get_device_properties(local_rank)
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/local_cpulist" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        with open(path) as f:
+            txt = f.read().strip()
+        cpus = parse_cpulist(txt)
+        cur = os.sched_getaffinity(0)
+        keep = cpus & cur
+        if len(keep) < 4 or keep == cur:
+            return None
+        os.sched_setaffinity(0, keep)
+        return txt
+    except Exception:  # noqa: BLE001 - a placement hint, never an error
+        return None
+
+
 def _events(ctx, local_rank):
     import torch
 
@@ -350,6 +386,7 @@ def _main(out):
     from keras_unsupervised_b200.engine import Context, Dataset, Machine
 
     torch.cuda.set_device(local_rank)
+    host_cpus = bind_near_gpu(local_rank) if world > 1 else None  # before any host buffer of this rank exists
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -450,6 +487,8 @@ def _main(out):
                "input": "float32 pinned host matrix, one pass of kucd_rbm_fit_host (copy of minibatch i+1 overlapped "
                         "with minibatch i); result read per step: recon_err; wall clock around the call",
                "last_recon_err": float(st["step_recon_err"][-1])}
+        if host_cpus is not None:
+            e2e["host_cpus"] = "rank 0 bound to the CPUs local to its GPU (%s); every rank does the same" % host_cpus
         windows.append((tw0, tw1))
         del host
     if e2e is not None:

@@ -29,3 +29,15 @@ def test_other_ranks_of_the_reference_arm_exit_quietly():
     res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
                          capture_output=True, text=True, timeout=120, env=env)
     assert res.returncode == 0 and res.stdout.strip() == ""
+
+
+def test_numa_placement_hint_is_harmless_without_a_gpu():
+    """bench.bind_near_gpu (multi-GPU arm): parses sysfs cpulists, and is a no-op when the device cannot be queried."""
+    sys.path.insert(0, ROOT)
+    import bench
+
+    assert bench.parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert bench.parse_cpulist("5") == {5} and bench.parse_cpulist("") == set()
+    before = os.sched_getaffinity(0)
+    assert bench.bind_near_gpu(0) is None           # no GPU here: nothing is queried, nothing changes
+    assert os.sched_getaffinity(0) == before
