@@ -220,6 +220,16 @@ int kucd_rbm_score(kucd_rbm* rbm, const kucd_tensor* v_batch, const kucd_tensor*
  * and the sampled states of that step: h_pos (rows,H), v_neg (rows,V), h_neg (rows,H).  Any NULL. */
 int kucd_rbm_last_stats(kucd_rbm* rbm, kucd_tensor* dW, kucd_tensor* db, kucd_tensor* dc,
                         kucd_tensor* h_pos, kucd_tensor* v_neg, kucd_tensor* h_neg);
+/* Fine-tuning after the path (an extension: the reference stops at greedy pretraining, dbn.py:34-55).  One delta-rule
+ * step of a directed sigmoid layer that shares the RBM's parameter layout - the building block of the up-down
+ * (wake-sleep) fine-tuning of a stack (Hinton, Osindero & Teh 2006, appendix B):
+ *   forward != 0:  p = sigmoid(in.W + c)     W += lr in^T (target - p)     c += lr sum_rows (target - p)
+ *   forward == 0:  p = sigmoid(in.W^T + b)   W += lr (target - p)^T in     b += lr sum_rows (target - p)
+ * in: (rows, V) forward, (rows, H) backward; target: (rows, H) forward, (rows, V) backward; normalize != 0 divides
+ * the sums by rows.  Runs the CD path's own kernels (projection with the probability epilogue, the two-segment dW
+ * contraction, the update).  Single rank. */
+int kucd_rbm_delta_rule(kucd_rbm* rbm, int forward, const kucd_tensor* in, const kucd_tensor* target, float lr,
+                        int normalize);
 /* persistent chains (PCD): (n_chains, V) states; get/set for checkpointing and parity */
 int kucd_rbm_set_chains(kucd_rbm* rbm, const kucd_tensor* v_chains);
 int kucd_rbm_get_chains(kucd_rbm* rbm, kucd_tensor* v_chains);

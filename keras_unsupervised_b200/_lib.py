@@ -100,6 +100,7 @@ SIGNATURES = {
                                     C.POINTER(StepStats)]),
     "kucd_rbm_score": (C.c_int, [_P, _TP, _TP, _TP, C.POINTER(C.c_float)]),
     "kucd_rbm_last_stats": (C.c_int, [_P, _TP, _TP, _TP, _TP, _TP, _TP]),
+    "kucd_rbm_delta_rule": (C.c_int, [_P, C.c_int, _TP, _TP, C.c_float, C.c_int]),
     "kucd_rbm_set_chains": (C.c_int, [_P, _TP]),
     "kucd_rbm_get_chains": (C.c_int, [_P, _TP]),
     "kucd_dataset_create": (C.c_int, [_P, _TP, C.c_int, C.POINTER(_P)]),

@@ -283,6 +283,7 @@ struct kucd_rbm {
   int64_t cap = 0;
   PlaneBuf vin, vin2, h0, hk, vk;  // vin2: second staging slot of the host-streaming fit
   PlaneBuf chunk;   // chunked streaming (KUCD_STREAM_CHUNK): operand planes of several staged minibatches
+  PlaneBuf ft_in, ft_t, ft_p;  // kucd_rbm_delta_rule: input states, targets, predicted probabilities
   PlaneBuf chains;  // persistent chains (n_chains, ldV)
   int64_t n_chains = 0;
   DevBuf fe0, fe1, sp0, sp1, pstage, stats, flag;
@@ -1722,7 +1723,9 @@ int kucd_rbm_destroy(kucd_rbm* r) {
   for (DevBuf* b : {&r->W32, &r->b32, &r->c32, &r->mW, &r->mb, &r->mc, &r->grad, &r->fe0, &r->fe1, &r->sp0, &r->sp1,
                     &r->pstage, &r->stats, &r->flag, &r->dyn, &r->chain_done, &r->grad16})
     b->release();
-  for (PlaneBuf* p : {&r->Wp, &r->vin, &r->vin2, &r->chunk, &r->h0, &r->hk, &r->vk, &r->chains}) p->release();
+  for (PlaneBuf* p : {&r->Wp, &r->vin, &r->vin2, &r->chunk, &r->ft_in, &r->ft_t, &r->ft_p, &r->h0, &r->hk, &r->vk,
+                      &r->chains})
+    p->release();
   delete r;
   return KUCD_OK;
 }
@@ -2065,6 +2068,85 @@ int kucd_rbm_cd_step(kucd_rbm* r, const kucd_tensor* v_batch, const kucd_hparams
   KU_TRY(gather_master(r));
   const bool host_in = !on_device(v_batch) || inj != nullptr;
   if (host_in) CU_TRY(cudaStreamSynchronize(ctx->stream));
+  return KUCD_OK;
+}
+
+// Fine-tuning after the path.  One delta-rule step of a directed sigmoid layer laid out like the
+// RBM: p = sigmoid(in.W + c) [forward] or sigmoid(in.W^T + b) [backward], then W += lr in^T (t - p) [or (t - p)^T in]
+// and the matching bias += lr sum_rows (t - p).  in^T t - in^T p is the CD statistic v0^T h0 - vk^T hk with
+// (v0, h0, vk, hk) = (in, t, in, p) [forward] or (t, in, p, in) [backward], so the step is the projection kernel with
+// the probability epilogue, the two-segment dW contraction and the update kernel of the CD path.
+int kucd_rbm_delta_rule(kucd_rbm* r, int forward, const kucd_tensor* in, const kucd_tensor* target, float lr,
+                        int normalize) {
+  if (r == nullptr) return fail(KUCD_ERR_INVALID_ARG, "rbm is NULL");
+  kucd_ctx* ctx = r->ctx;
+  CU_TRY(cudaSetDevice(ctx->device));
+  if (ctx->comm != nullptr) return fail(KUCD_ERR_INVALID_ARG, "delta_rule runs on a single rank (no data-parallel group)");
+  if (r->mode != KUCD_MODE_VISIBLE_BERNOULLI && !forward)
+    return fail(KUCD_ERR_INVALID_ARG, "delta_rule towards Gaussian visible units is not implemented (sigmoid units only)");
+  const int64_t K = forward ? r->V : r->H, N = forward ? r->H : r->V;
+  KU_TRY(check_tensor(ctx, in, -1, K, "in"));
+  const int64_t rows = in->shape[0];
+  KU_TRY(check_tensor(ctx, target, rows, N, "target"));
+  if (rows == 0) return KUCD_OK;
+  if (rows > (1 << 22)) return fail(KUCD_ERR_INVALID_ARG, "minibatch of %lld rows", (long long)rows);
+  const bool x3 = r->compute == KUCD_COMPUTE_F32X3;
+  const int np = x3 ? 3 : 1;
+  const int64_t cap = round_up(rows, 128);
+  KU_TRY(r->ft_in.ensure(cap, forward ? r->ldV : r->ldH, np));
+  KU_TRY(r->ft_t.ensure(cap, forward ? r->ldH : r->ldV, np));
+  KU_TRY(r->ft_p.ensure(cap, forward ? r->ldH : r->ldV, np));
+  // caller rows -> operand planes; in fp32-grade mode float data is checked for being exact in one bf16 term (0/1
+  // states are), which keeps the contraction at 1 + 3 term products
+  auto ingest = [&](const kucd_tensor* t, PlaneBuf& buf, int64_t cols, Planes* out) -> int {
+    Planes dst = buf.view(rows, cols, np);
+    const bool maybe_inexact = x3 && t->dtype_code == KUCD_DT_FLOAT;
+    if (maybe_inexact) CU_TRY(cudaMemsetAsync(r->flag.p, 0, 4, ctx->stream));
+    KU_TRY(ingest_rows(ctx, t, 0, rows, dst, np, maybe_inexact ? r->flag.as<int>() : nullptr));
+    int live = 1;
+    if (maybe_inexact) {
+      int flag = 0;
+      CU_TRY(cudaMemcpyAsync(&flag, r->flag.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+      CU_TRY(cudaStreamSynchronize(ctx->stream));
+      live = flag ? 3 : 1;
+    }
+    dst.n = live;
+    *out = dst;
+    return KUCD_OK;
+  };
+  Planes A, T;
+  KU_TRY(ingest(in, r->ft_in, K, &A));
+  KU_TRY(ingest(target, r->ft_t, N, &T));
+  CU_TRY(cudaMemsetAsync(r->db(), 0, (r->ldVb() + r->ldHb()) * 4, ctx->stream));
+  float* bias_stat = forward ? r->dc() : r->db();
+  const Planes P = r->ft_p.view(rows, N, np);
+  {
+    EpiArgs e;
+    e.epi = kEpiProb;
+    e.out = P;
+    e.colsum = bias_stat;
+    e.colsum_sign = -1.f;  // - sum_rows p
+    KU_TRY(project(r, forward != 0, A, rows, e));
+  }
+  {  // + sum_rows t
+    dim3 grid(static_cast<unsigned>((N / 2 + 1 + 127) / 128), static_cast<unsigned>((rows + 63) / 64));
+    colsum_kernel<<<grid, 128, 0, ctx->stream>>>(T.p[0], T.mid(), T.lo(), T.ld, 0, static_cast<int32_t>(rows),
+                                                 static_cast<int32_t>(N), nullptr, 1.f, bias_stat);
+    ctx->tm.aux_launches++;
+    CU_TRY(cudaGetLastError());
+  }
+  r->fused_now = false;
+  r->slabs_now = 1;
+  r->slabs_inflight = 0;
+  if (forward) KU_TRY(delta_w(r, A, T, A, P, rows, nullptr, false));
+  else KU_TRY(delta_w(r, T, A, P, A, rows, nullptr, false));
+  kucd_hparams hp{};
+  hp.lr = lr;
+  hp.k = 1;
+  hp.normalize = normalize ? 1 : 0;
+  hp.update_mask = KUCD_UPDATE_W | (forward ? KUCD_UPDATE_C : KUCD_UPDATE_B);
+  KU_TRY(apply_update(r, &hp, rows));
+  if (!on_device(in) || !on_device(target)) CU_TRY(cudaStreamSynchronize(ctx->stream));
   return KUCD_OK;
 }
 

@@ -86,14 +86,91 @@ class DBN(object):
         return V_p
 
     def inv_transform(self, H):
-        """Transform the hidden unit (dbn.py:77-96), top layer first."""
+        """Transform the hidden unit (dbn.py:77-96), top layer first.  After fine_tune the layers below the top one
+        go down through their own generative weights."""
         self._check()
         H_p = H[0] if isinstance(H, (list, tuple)) and len(H) == 1 else H
         H_p = H_p.copy() if isinstance(H_p, np.ndarray) else H_p
-        for rbm_layer in reversed(self._rbm_layers):
-            out = rbm_layer.inv_transform(H_p)
+        gen = getattr(self, "_gen", None)
+        for i in reversed(range(len(self._rbm_layers))):
+            rbm_layer = self._rbm_layers[i]
+            if gen is not None and i < len(gen):
+                out = gen[i].inv_transform_dataset(H_p) if isinstance(H_p, Dataset) else gen[i].inv_transform(H_p)
+            else:
+                out = rbm_layer.inv_transform(H_p)
             H_p = out[0] if isinstance(out, list) else out
         return H_p
+
+    # ---- fine-tuning after the greedy pass (SURVEY.md 8f rank 4; the reference stops at dbn.py:34-55) ----
+    def untie(self):
+        """Give every layer below the top one its own generative parameters: a second engine model initialised with the
+        layer's W, b, c.  The layer itself keeps the recognition direction (v.W + c), the copy the generative one
+        (h.W^T + b); the top RBM stays undirected.  Idempotent."""
+        self._check()
+        gen = getattr(self, "_gen", None)
+        if gen is None or len(gen) != len(self._rbm_layers) - 1:
+            from ..engine import Machine
+
+            gen = []
+            for layer in self._rbm_layers[:-1]:
+                if not layer.built:
+                    raise ValueError("untie needs a trained (built) stack")
+                m = layer._machine
+                g = Machine(m.ctx, m.V, m.H, m.mode, m.compute, seed=layer.seed + 500009)
+                g.set_params(*m.get_params())
+                gen.append(g)
+            self._gen = gen
+        return self._gen
+
+    def fine_tune(self, V, epochs=1, batch_size=None, lr=None, k=1, normalize=None, verbose=0):
+        """Up-down (contrastive wake-sleep) fine-tuning of a greedily trained stack (Hinton, Osindero & Teh 2006,
+        appendix B; the CPU restatement the tests compare with is OracleDBN.up_down_step).  Per minibatch:
+          wake    s_l = sampled hidden states of the recognition layers, bottom-up (RBM.transform)
+          top     CD-k of the top RBM on s_{L-1}; t_{L-1} = the visible state its chain ends in
+          sleep   t_{l-1} = sampled through the generative weights, top-down
+          update  generative weights predict s_{l-1} from s_l, recognition weights predict t_l from t_{l-1}
+                  (kucd_rbm_delta_rule: the CD path's projection, dW contraction and update kernels)
+        Bernoulli layers only.  V: a host array (rows, input_dim).  Returns self."""
+        from ..engine import Machine
+
+        self._check()
+        layers = self._rbm_layers
+        if len(layers) < 2:
+            raise ValueError("fine_tune needs at least two stacked layers")
+        if any(not l.built for l in layers):
+            raise ValueError("fine_tune needs a trained (built) stack: call fit first")
+        if any(int(l.mode) != MODE_VISIBLE_BERNOULLI for l in layers):
+            raise ValueError("fine_tune is implemented for Bernoulli (sigmoid) layers")
+        V = V[0] if isinstance(V, (list, tuple)) and len(V) == 1 else V
+        V = V.numpy() if isinstance(V, Dataset) else np.asarray(V)
+        top = layers[-1]
+        batch = int(batch_size or top.hps["batch_size"])
+        lr = float(lr if lr is not None else top.hps["lr"])
+        if normalize is None:
+            normalize = top.hps.get("normalize", "sum") in ("mean", True, 1)
+        gen = self.untie()
+        hp = Machine.hparams(lr=lr, k=int(k), normalize=bool(normalize))
+        n = V.shape[0]
+        for epoch in range(int(epochs)):
+            for lo in range(0, n, batch):                          # sequential slices, remainder last (rbm.py:211,218)
+                s = [V[lo:lo + batch]]
+                rows = s[0].shape[0]
+                for layer in layers[:-1]:
+                    s.append(layer._machine.transform(s[-1]))
+                top._machine.cd_step(s[-1], hp)
+                t = [None] * len(layers)
+                t[-1] = top._machine.last_stats(rows, states=True, grads=False)["v_neg"]
+                for i in range(len(layers) - 2, -1, -1):
+                    t[i] = gen[i].inv_transform(t[i + 1])
+                for i in range(len(layers) - 1):
+                    gen[i].delta_rule(False, s[i + 1], s[i], lr, normalize)
+                    layers[i]._machine.delta_rule(True, t[i], t[i + 1], lr, normalize)
+            if verbose:
+                print("fine-tune epoch {0:d} done.".format(epoch + 1))
+        for layer in layers:
+            if hasattr(layer, "_to_keras"):
+                layer._to_keras()
+        return self
 
     def generate(self, n_samples, gibbs_steps=100, seed=0, h_init=None):
         """Draw visible samples from the trained stack (what the reference's top-down pass, dbn.py:77-96, is for; SURVEY.md
@@ -116,8 +193,10 @@ class DBN(object):
             h = m.transform_dataset(v)
             v.close()
         cur = h
-        for rbm_layer in reversed(self._rbm_layers):
-            nxt = rbm_layer._machine.inv_transform_dataset(cur)
+        gen = getattr(self, "_gen", None)
+        for i in reversed(range(len(self._rbm_layers))):
+            down = gen[i] if gen is not None and i < len(gen) else self._rbm_layers[i]._machine
+            nxt = down.inv_transform_dataset(cur)
             cur.close()
             cur = nxt
         out = cur.numpy()

@@ -312,13 +312,17 @@ class Machine:
                                             C.byref(tvv) if tvv is not None else None, C.byref(out)))
         return out.value
 
-    def last_stats(self, rows: int, states: bool = True) -> dict:
-        dW = np.empty((self.V, self.H), np.float32)
-        db = np.empty((self.V,), np.float32)
-        dc = np.empty((self.H,), np.float32)
+    def last_stats(self, rows: int, states: bool = True, grads: bool = True) -> dict:
         keep: list = []
-        args = [C.byref(L.tensor_of(x, keep)) for x in (dW, db, dc)]
-        out = {"dW": dW, "db": db, "dc": dc}
+        out = {}
+        if grads:
+            dW = np.empty((self.V, self.H), np.float32)
+            db = np.empty((self.V,), np.float32)
+            dc = np.empty((self.H,), np.float32)
+            args = [C.byref(L.tensor_of(x, keep)) for x in (dW, db, dc)]
+            out.update(dW=dW, db=db, dc=dc)
+        else:
+            args = [None, None, None]
         if states:
             hp_, vn, hn = (np.empty((rows, self.H), np.float32), np.empty((rows, self.V), np.float32),
                            np.empty((rows, self.H), np.float32))
@@ -328,6 +332,17 @@ class Machine:
             args += [None, None, None]
         L.check(self.ctx.lib.kucd_rbm_last_stats(self.handle, *args))
         return out
+
+    def delta_rule(self, forward: bool, x, target, lr: float, normalize: bool = False) -> None:
+        """One delta-rule step of the directed layer that shares this RBM's parameters (include/kucd.h:
+        kucd_rbm_delta_rule): forward - p = sigmoid(x.W + c), W += lr x^T (target - p), c += lr sum (target - p);
+        backward - p = sigmoid(x.W^T + b), W += lr (target - p)^T x, b += lr sum (target - p)."""
+        keep: list = []
+        _sync_producer(x)
+        _sync_producer(target)
+        tx, tt = L.tensor_of(x, keep), L.tensor_of(target, keep)
+        L.check(self.ctx.lib.kucd_rbm_delta_rule(self.handle, int(bool(forward)), C.byref(tx), C.byref(tt),
+                                                 C.c_float(lr), int(bool(normalize))))
 
     def set_chains(self, v) -> None:
         keep: list = []

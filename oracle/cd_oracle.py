@@ -354,6 +354,29 @@ class OracleRBM:
         if mask & 4:
             self.b, self.mb = step(self.b, st["db"], self.mb, F32(0))
 
+    def delta_rule(self, forward, x, target, lr, scale=1.0):
+        """include/kucd.h: kucd_rbm_delta_rule - one delta-rule step of the directed sigmoid layer that shares this
+        RBM's parameters (the reference has no fine-tuning; Hinton, Osindero & Teh 2006, appendix B):
+          forward:  p = sigmoid(x.W + c),   W += lr x^T (t - p),  c += lr sum_rows (t - p)
+          backward: p = sigmoid(x.W^T + b), W += lr (t - p)^T x,  b += lr sum_rows (t - p)
+        Computed as the engine does, as x^T t - x^T p with the operands rounded to bf16 in bf16 mode (p like the
+        h_neg operand of rbm.py:126) and the bias statistic from the unrounded probabilities.  Returns p."""
+        x, t = np.asarray(x, F32), np.asarray(target, F32)
+        p = self.prob_h(x) if forward else self.prob_v(x)
+        if self.compute == "bf16":
+            x_mm, t_mm, p_mm = bf16_round(x), bf16_round(t), bf16_round(p)
+        else:
+            x_mm, t_mm, p_mm = x, t, p
+        f = np.float32 if self.compute == "f32" else np.float64
+        if forward:
+            dW = (x_mm.astype(f).T @ t_mm.astype(f) - x_mm.astype(f).T @ p_mm.astype(f)).astype(F32)
+        else:
+            dW = (t_mm.astype(f).T @ x_mm.astype(f) - p_mm.astype(f).T @ x_mm.astype(f)).astype(F32)
+        dbias = (t_mm.astype(f).sum(0) - p.astype(f).sum(0)).astype(F32)
+        st = {"dW": dW, "dc": dbias, "db": dbias}
+        self.apply(st, lr, 1 | (2 if forward else 4), scale=scale)
+        return p
+
     def fused_step(self, v, u_h, u_v, lr, k=1, **kw):
         """One chain, all three parameters from the same statistics (the engine's timed schedule)."""
         persistent = kw.pop("persistent", False)
@@ -494,3 +517,40 @@ class OracleDBN:
         for rbm, u in zip(reversed(self.layers), draws):
             x, _ = rbm.sample_v(x, u)
         return x
+
+    # ---- up-down fine-tuning (an extension: the reference stops at greedy pretraining, dbn.py:34-55) ----
+    def untie(self):
+        """Give every layer below the top one its own generative parameters (a copy of W, b), as the up-down
+        algorithm does before fine-tuning: `layers[l]` keeps the recognition direction (W, c), `gen[l]` the
+        generative one (W, b).  The top RBM stays undirected."""
+        if not hasattr(self, "gen") or len(self.gen) != len(self.layers) - 1:
+            self.gen = [OracleRBM(r.W.copy(), r.b.copy(), r.c.copy(), mode=r.mode, compute=r.compute)
+                        for r in self.layers[:-1]]
+        return self.gen
+
+    def up_down_step(self, v, draws, lr, k=1, scale=1.0):
+        """One minibatch of the up-down algorithm (Hinton, Osindero & Teh 2006, appendix B), what DBN.fine_tune runs:
+          wake    s_0 = v;  s_l = 1[u < sigmoid(s_{l-1} W_l + c_l)]                     l = 1 .. L-1   (draws["up"][l-1])
+          top     CD-k of the top RBM on s_{L-1} (draws["top"] = (u_h, u_v) as for cd_stats); t_{L-1} = its last v_neg
+          sleep   t_{l-1} = 1[u < sigmoid(t_l G_l^T + b_l)]                                l = L-1 .. 1   (draws["down"][l-1])
+          generative weights, from the wake states:   gen[l-1].delta_rule(backward, s_l -> s_{l-1})
+          recognition weights, from the sleep states: layers[l-1].delta_rule(forward, t_{l-1} -> t_l)
+        Returns the wake and sleep states."""
+        L = len(self.layers)
+        if L < 2:
+            raise ValueError("up-down fine-tuning needs at least two layers")
+        gen = self.untie()
+        s = [np.asarray(v, F32)]
+        for l in range(1, L):
+            h, _ = self.layers[l - 1].sample_h(s[-1], draws["up"][l - 1])
+            s.append(h)
+        u_h, u_v = draws["top"]
+        st = self.layers[-1].fused_step(s[-1], u_h, u_v, lr, k=k, scale=scale)
+        t = [None] * L
+        t[L - 1] = st["v_neg"]
+        for l in range(L - 1, 0, -1):
+            t[l - 1], _ = gen[l - 1].sample_v(t[l], draws["down"][l - 1])
+        for l in range(1, L):
+            gen[l - 1].delta_rule(False, s[l], s[l - 1], lr, scale=scale)
+            self.layers[l - 1].delta_rule(True, t[l - 1], t[l], lr, scale=scale)
+        return s, t

@@ -24,6 +24,9 @@ if [ "$MODE" = single ]; then
   KUCD_STREAM_CHUNK=4 timeout 600 python -m pytest tests -m gpu -x -q \
       -k "stream or fit_host or packed or one_epoch or keras or shuffl" >> $LOG 2>&1
   echo "rc=$?" >> $LOG
+  echo "== kucd_rbm_delta_rule / DBN.fine_tune against the oracle (written without a GPU)" >> $LOG
+  KUCD_TEST_UNVERIFIED=1 timeout 600 python -m pytest tests/test_fine_tune.py -m gpu -q >> $LOG 2>&1
+  echo "rc=$?" >> $LOG
   # measurement: one epoch of the C1 shape through kucd_rbm_fit_host, per chunk size (0 = per-minibatch stream)
   for c in 0 4 8 16 32 64; do
     echo "== bench c1, KUCD_STREAM_CHUNK=$c" >> $LOG
