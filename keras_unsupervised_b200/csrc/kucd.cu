@@ -164,6 +164,9 @@ struct kucd_ctx {
   cudaStream_t stream2 = nullptr;  // second Gibbs chain of a split minibatch
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaStream_t copy_stream = nullptr;  // host -> device staging of the next minibatch (fit_host)
+  // KUCD_PLANE_POOL=1: plane buffers of destroyed data sets, kept for the next data set (see pool_take / pool_give)
+  std::vector<DevBuf> plane_pool;
+  size_t plane_pool_bytes = 0;
   // slab-pipelined all-reduce (KUCD_AR_SLABS): dW leaves in row slabs on comm_stream while the next slab is contracted
   static constexpr int kMaxSlabs = 16;
   cudaStream_t comm_stream = nullptr;
@@ -333,6 +336,54 @@ static void drop_host_graph(kucd_rbm* r) {
   if (r->hgraph != nullptr) cudaGraphDestroy(r->hgraph);
   r->hgraph_exec = nullptr;
   r->hgraph = nullptr;
+}
+
+// Free list of data-set plane buffers (KUCD_PLANE_POOL=1; off by default until measured).  A transform of a small
+// data set is 30-120 us of contraction behind ~0.4 ms of cudaMalloc for its output (and a device-wide cudaFree when the
+// result is closed).  Every kernel that touches data-set planes runs in order on the context's stream (forked work
+// joins it before a step ends), so a buffer given back can be handed out again without waiting for anything.
+static bool plane_pool_on() {
+  static const bool on = [] {
+    const char* e = getenv("KUCD_PLANE_POOL");
+    return e != nullptr && e[0] == '1';
+  }();
+  return on;
+}
+static constexpr size_t kPlanePoolCap = size_t{2} << 30;  // bytes kept at most
+static void pool_take(kucd_ctx* ctx, DevBuf& b, size_t need) {
+  if (!plane_pool_on() || b.bytes >= need) return;
+  int best = -1;
+  for (size_t i = 0; i < ctx->plane_pool.size(); ++i) {
+    const size_t have = ctx->plane_pool[i].bytes;
+    if (have >= need && have <= 2 * need + (size_t{1} << 20) &&
+        (best < 0 || have < ctx->plane_pool[static_cast<size_t>(best)].bytes))
+      best = static_cast<int>(i);
+  }
+  if (best < 0) return;
+  b.release();
+  b = ctx->plane_pool[static_cast<size_t>(best)];
+  ctx->plane_pool_bytes -= b.bytes;
+  ctx->plane_pool.erase(ctx->plane_pool.begin() + best);
+}
+static void pool_give(kucd_ctx* ctx, DevBuf& b) {
+  if (b.p == nullptr) return;
+  if (plane_pool_on() && b.bytes <= kPlanePoolCap / 4 && ctx->plane_pool_bytes + b.bytes <= kPlanePoolCap &&
+      ctx->plane_pool.size() < 64) {
+    ctx->plane_pool.push_back(b);
+    ctx->plane_pool_bytes += b.bytes;
+    b.p = nullptr;
+    b.bytes = 0;
+    return;
+  }
+  b.release();
+}
+// the planes of a data set: from the free list when one fits, else cudaMalloc
+static int dataset_planes(kucd_ctx* ctx, PlaneBuf& pb, int64_t rows, int64_t ld, int nplanes) {
+  for (int i = 0; i < nplanes; ++i) pool_take(ctx, pb.buf[i], static_cast<size_t>(rows) * ld * 2);
+  return pb.ensure(rows, ld, nplanes);
+}
+static void dataset_planes_release(kucd_ctx* ctx, PlaneBuf& pb) {
+  for (auto& b : pb.buf) pool_give(ctx, b);
 }
 
 // this training call all-reduces dW as bf16 through NCCL (the fused exchange has its own bf16 slots)
@@ -1573,6 +1624,8 @@ int kucd_ctx_destroy(kucd_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->stream != nullptr) cudaStreamSynchronize(ctx->stream);
   if (ctx->comm != nullptr && g_nccl.CommDestroy != nullptr) g_nccl.CommDestroy(ctx->comm);
+  for (auto& b : ctx->plane_pool) b.release();
+  ctx->plane_pool.clear();
   ctx->stage_in.release();
   ctx->stage_u.release();
   ctx->stage_out.release();
@@ -2278,7 +2331,7 @@ int kucd_dataset_create(kucd_ctx* ctx, const kucd_tensor* data, int compute, kuc
   ds->dim = dim;
   const bool x3 = compute == KUCD_COMPUTE_F32X3 && data->dtype_code == KUCD_DT_FLOAT;
   const int np = x3 ? 3 : 1;
-  int rc = ds->planes.ensure(std::max<int64_t>(rows, 1), round_up(dim, 64), np);
+  int rc = dataset_planes(ctx, ds->planes, std::max<int64_t>(rows, 1), round_up(dim, 64), np);
   DevBuf flag;
   if (rc == KUCD_OK) rc = flag.ensure(16, true);
   for (int64_t r0 = 0; r0 < rows && rc == KUCD_OK; r0 += kChunkRows) {
@@ -2297,7 +2350,7 @@ int kucd_dataset_create(kucd_ctx* ctx, const kucd_tensor* data, int compute, kuc
   }
   flag.release();
   if (rc != KUCD_OK) {
-    ds->planes.release();
+    dataset_planes_release(ctx, ds->planes);
     delete ds;
     return rc;
   }
@@ -2309,8 +2362,12 @@ int kucd_dataset_create(kucd_ctx* ctx, const kucd_tensor* data, int compute, kuc
 int kucd_dataset_destroy(kucd_dataset* ds) {
   if (ds == nullptr) return KUCD_OK;
   cudaSetDevice(ds->ctx->device);
-  cudaStreamSynchronize(ds->ctx->stream);
-  ds->planes.release();
+  if (plane_pool_on()) {
+    dataset_planes_release(ds->ctx, ds->planes);  // stream order protects the next user of these buffers
+  } else {
+    cudaStreamSynchronize(ds->ctx->stream);
+    ds->planes.release();
+  }
   delete ds;
   return KUCD_OK;
 }
@@ -2359,7 +2416,7 @@ int kucd_dataset_shuffle(kucd_dataset* in, uint64_t seed, uint64_t epoch, kucd_d
   }
   int rc = KUCD_OK;
   if (created || out->nparts < in->nparts)
-    rc = out->planes.ensure(std::max<int64_t>(in->rows, 1), in->planes.ld, in->nparts);
+    rc = dataset_planes(ctx, out->planes, std::max<int64_t>(in->rows, 1), in->planes.ld, in->nparts);
   if (rc == KUCD_OK && in->rows > 0) {
     const FeistelKey key = make_feistel_key(seed, epoch, in->rows);
     const bool three = in->nparts == 3;
@@ -2374,7 +2431,7 @@ int kucd_dataset_shuffle(kucd_dataset* in, uint64_t seed, uint64_t epoch, kucd_d
   }
   if (rc != KUCD_OK) {
     if (created) {
-      out->planes.release();
+      dataset_planes_release(ctx, out->planes);
       delete out;
     }
     return rc;
@@ -2913,7 +2970,7 @@ static int map_dataset(kucd_rbm* r, bool forward, kucd_dataset* in, kucd_dataset
   const bool gaussian = r->mode == KUCD_MODE_VISIBLE_GAUSSIAN;
   const int np = forward ? 1 : vis_parts_out(r);
   ds->nparts = np;
-  int rc = ds->planes.ensure(std::max<int64_t>(in->rows, 1), round_up(N, 64), np);
+  int rc = dataset_planes(ctx, ds->planes, std::max<int64_t>(in->rows, 1), round_up(N, 64), np);
   if (rc == KUCD_OK && in->rows > 0) {
     EpiArgs e;
     e.epi = forward ? (gaussian ? kEpiReluSample : kEpiSample) : (gaussian ? kEpiGaussian : kEpiSample);
@@ -2922,7 +2979,7 @@ static int map_dataset(kucd_rbm* r, bool forward, kucd_dataset* in, kucd_dataset
     rc = project(r, forward, in->view(), in->rows, e);
   }
   if (rc != KUCD_OK) {
-    ds->planes.release();
+    dataset_planes_release(ctx, ds->planes);
     delete ds;
     return rc;
   }

@@ -6,6 +6,7 @@
 #   KUCD_WIRE_BF16=1      bf16 partial sums of dW on the wire: bf16 slots in the fused exchange, a bf16 ncclAllReduce
 #                         otherwise (gemm.cuh: kEpiRawPush16)
 #
+#   KUCD_PLANE_POOL=1     free list of data-set plane buffers (no cudaMalloc / cudaFree per transform_dataset)
 #   KUCD_AR_SLABS=S       dW contracted, all-reduced (NCCL, second stream) and applied in S row slabs that overlap
 #
 #   gpurun --timeout 900 -- 'bash tools/run_round2_switches.sh single'          (one GPU)
@@ -40,6 +41,22 @@ try:
         sys.argv[1], d["value"], d["e2e"]["value"], 1e3 * d["e2e"].get("ms_per_step", float("nan"))))
 except Exception as e:  # noqa: BLE001
     print("chunk=%s: no line (%s)" % (sys.argv[1], e))
+EOF
+  done
+  # KUCD_PLANE_POOL=1: free list of data-set plane buffers (small-batch inference is cudaMalloc-bound without it)
+  echo "== parity, KUCD_PLANE_POOL=1 (every GPU test that creates data sets)" >> $LOG
+  KUCD_PLANE_POOL=1 timeout 900 python -m pytest tests -m gpu -x -q >> $LOG 2>&1
+  echo "rc=$?" >> $LOG
+  for v in 0 1; do
+    echo "== bench c5, KUCD_PLANE_POOL=$v" >> $LOG
+    KUCD_PLANE_POOL=$v timeout 600 python bench.py --workload c5 > gpurun_out/r02_bench_c5_pool$v.json 2>> $LOG
+    python - "$v" >> $LOG <<'EOF'
+import json, sys
+try:
+    d = json.loads(open("gpurun_out/r02_bench_c5_pool%s.json" % sys.argv[1]).read().strip().splitlines()[-1])
+    print("pool=%s " % sys.argv[1] + "  ".join("n=%d: %.3f ms" % (r["rows"], r["transform_ms"]) for r in d["sweep"]))
+except Exception as e:  # noqa: BLE001
+    print("pool=%s: no line (%s)" % (sys.argv[1], e))
 EOF
   done
   cat $LOG
