@@ -1,16 +1,17 @@
 #!/bin/bash
-# First GPU call of the next round: the two opt-in paths that were written without a GPU at the end of round 1
-# (both compile, neither has run).  Each is checked for parity first, then measured on / off inside this one call.
+# First GPU calls of the next round: the opt-in paths that were written without a GPU at the end of round 1
+# (all compile, none has run).  Each is checked for parity first, then measured on / off inside one call.
 #
 #   KUCD_STREAM_CHUNK=C   chunked streaming of latency-bound minibatches (kucd.cu: fit_host_chunked)
+#   KUCD_PLANE_POOL=1     free list of data-set plane buffers (no cudaMalloc / cudaFree per transform_dataset)
+#   kucd_rbm_delta_rule   DBN.fine_tune's building block (tests/test_fine_tune.py, KUCD_TEST_UNVERIFIED=1)
 #   KUCD_WIRE_BF16=1      bf16 partial sums of dW on the wire: bf16 slots in the fused exchange, a bf16 ncclAllReduce
 #                         otherwise (gemm.cuh: kEpiRawPush16)
-#
-#   KUCD_PLANE_POOL=1     free list of data-set plane buffers (no cudaMalloc / cudaFree per transform_dataset)
 #   KUCD_AR_SLABS=S       dW contracted, all-reduced (NCCL, second stream) and applied in S row slabs that overlap
 #
 #   gpurun --timeout 900 -- 'bash tools/run_round2_switches.sh single'          (one GPU)
-#   gpurun --gpus 8 --timeout 900 -- 'bash tools/run_round2_switches.sh multi'  (needs >= 2 GPUs; C4 is quoted on 8)
+#   gpurun --gpus 2 --timeout 600 -- 'bash tools/run_round2_switches.sh multi check'
+#   gpurun --gpus 8 --timeout 600 -- 'bash tools/run_round2_switches.sh multi bench [c4|c3]'   (C4 is quoted on 8 GPUs)
 set -u
 mkdir -p gpurun_out
 MODE=${1:-single}
@@ -61,31 +62,36 @@ EOF
   done
   cat $LOG
 else
+  # multi check : the four data-parallel parity runs (2 GPUs are enough: gpurun --gpus 2, charged twice the box time)
+  # multi bench : C4 on every GPU of the box, six exchange variants, ~35 s each (gpurun --gpus 8: ~30 GPU-minutes)
+  WHAT=${2:-check}
   N=$(python -c 'import torch; print(torch.cuda.device_count())')
-  LOG=gpurun_out/r02_wire_bf16.log
+  LOG=gpurun_out/r02_exchange_$WHAT.log
   : > $LOG
-  echo "== dp_check, $N ranks, KUCD_WIRE_BF16=1, fused exchange (oracle models the rounded partial sums)" >> $LOG
-  KUCD_WIRE_BF16=1 timeout 600 $TR --nproc-per-node $N --master-port 29531 tests/dp_check.py >> $LOG 2>&1
-  echo "rc=$?" >> $LOG
-  echo "== dp_check, $N ranks, KUCD_WIRE_BF16=1, bf16 ncclAllReduce (exact model at 2 ranks, tolerance beyond)" >> $LOG
-  KUCD_WIRE_BF16=1 KUCD_FUSED_REDUCE=0 timeout 600 $TR --nproc-per-node $N --master-port 29534 tests/dp_check.py >> $LOG 2>&1
-  echo "rc=$?" >> $LOG
-  echo "== dp_check, $N ranks, KUCD_AR_SLABS=2, fp32 ncclAllReduce in row slabs (same bar as the default)" >> $LOG
-  KUCD_AR_SLABS=2 KUCD_FUSED_REDUCE=0 timeout 600 $TR --nproc-per-node $N --master-port 29535 tests/dp_check.py >> $LOG 2>&1
-  echo "rc=$?" >> $LOG
-  echo "== dp_check, $N ranks, default (must stay bit-identical to one GPU)" >> $LOG
-  timeout 600 $TR --nproc-per-node $N --master-port 29532 tests/dp_check.py >> $LOG 2>&1
-  echo "rc=$?" >> $LOG
-  for w in c4 c3; do
+  if [ "$WHAT" = check ]; then
+    echo "== dp_check, $N ranks, KUCD_WIRE_BF16=1, fused exchange (oracle models the rounded partial sums)" >> $LOG
+    KUCD_WIRE_BF16=1 timeout 600 $TR --nproc-per-node $N --master-port 29531 tests/dp_check.py >> $LOG 2>&1
+    echo "rc=$?" >> $LOG
+    echo "== dp_check, $N ranks, KUCD_WIRE_BF16=1, bf16 ncclAllReduce (exact model at 2 ranks, tolerance beyond)" >> $LOG
+    KUCD_WIRE_BF16=1 KUCD_FUSED_REDUCE=0 timeout 600 $TR --nproc-per-node $N --master-port 29534 tests/dp_check.py >> $LOG 2>&1
+    echo "rc=$?" >> $LOG
+    echo "== dp_check, $N ranks, KUCD_AR_SLABS=2, fp32 ncclAllReduce in row slabs (same bar as the default)" >> $LOG
+    KUCD_AR_SLABS=2 KUCD_FUSED_REDUCE=0 timeout 600 $TR --nproc-per-node $N --master-port 29535 tests/dp_check.py >> $LOG 2>&1
+    echo "rc=$?" >> $LOG
+    echo "== dp_check, $N ranks, default (must stay bit-identical to one GPU)" >> $LOG
+    timeout 600 $TR --nproc-per-node $N --master-port 29532 tests/dp_check.py >> $LOG 2>&1
+    echo "rc=$?" >> $LOG
+  else
+    w=${3:-c4}
     for v in "nccl32 KUCD_FUSED_REDUCE=0 KUCD_WIRE_BF16=0" "nccl16 KUCD_FUSED_REDUCE=0 KUCD_WIRE_BF16=1" \
-             "fused32 KUCD_FUSED_MIN_ROWS=1 KUCD_WIRE_BF16=0" "fused16 KUCD_FUSED_MIN_ROWS=1 KUCD_WIRE_BF16=1" \
-             "nccl32s4 KUCD_FUSED_REDUCE=0 KUCD_AR_SLABS=4" "nccl32s8 KUCD_FUSED_REDUCE=0 KUCD_AR_SLABS=8" \
+             "fused16 KUCD_FUSED_MIN_ROWS=1 KUCD_WIRE_BF16=1" \
+             "nccl32s4 KUCD_FUSED_REDUCE=0 KUCD_AR_SLABS=4" \
              "nccl16s4 KUCD_FUSED_REDUCE=0 KUCD_AR_SLABS=4 KUCD_WIRE_BF16=1" \
              "nccl16s8 KUCD_FUSED_REDUCE=0 KUCD_AR_SLABS=8 KUCD_WIRE_BF16=1"; do
       set -- $v
       echo "== bench $w at $N GPUs, $1 ($2 $3 ${4:-})" >> $LOG
-      env $2 $3 ${4:-X_UNUSED=0} timeout 600 $TR --nproc-per-node $N --master-port 29533 bench.py --gpus $N --workload $w --steps 100 \
-          --warmup 5 --no-cpu-baseline --no-e2e > gpurun_out/r02_bench_${w}_n${N}_$1.json 2>> $LOG
+      env $2 $3 ${4:-X_UNUSED=0} timeout 300 $TR --nproc-per-node $N --master-port 29533 bench.py --gpus $N --workload $w \
+          --steps 60 --warmup 5 --no-cpu-baseline --no-e2e > gpurun_out/r02_bench_${w}_n${N}_$1.json 2>> $LOG
       python - "$w" "$N" "$1" >> $LOG <<'EOF'
 import json, sys
 w, n, v = sys.argv[1:4]
@@ -96,6 +102,6 @@ except Exception as e:  # noqa: BLE001
     print("%s n=%s %s: no line (%s)" % (w, n, v, e))
 EOF
     done
-  done
+  fi
   cat $LOG
 fi
