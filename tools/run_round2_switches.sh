@@ -44,6 +44,13 @@ except Exception as e:  # noqa: BLE001
     print("chunk=%s: no line (%s)" % (sys.argv[1], e))
 EOF
   done
+  # where a latency-bound step spends its time: kernel durations of the C1 graph replay (3 launches per step); what is
+  # left of the 43 us per step is launch gaps - the case for programmatic dependent launch (what comes next)
+  echo "== ncu launch list, bench c1 (cold-cache, serialised: shares only)" >> $LOG
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv \
+      --log-file gpurun_out/r02_c1_launches.csv python bench.py --workload c1 --steps 40 --warmup 5 --no-cpu-baseline \
+      --no-e2e > gpurun_out/r02_c1_ncu.log 2>&1
+  echo "rc=$?" >> $LOG
   # KUCD_PLANE_POOL=1: free list of data-set plane buffers (small-batch inference is cudaMalloc-bound without it)
   echo "== parity, KUCD_PLANE_POOL=1 (every GPU test that creates data sets)" >> $LOG
   KUCD_PLANE_POOL=1 timeout 900 python -m pytest tests -m gpu -x -q >> $LOG 2>&1
