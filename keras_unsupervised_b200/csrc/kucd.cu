@@ -899,8 +899,30 @@ static int apply_update(kucd_rbm* r, const kucd_hparams* hp, int64_t rows_global
       // slabs are still on the wire; the bias statistics travelled with slab 0, the tail rides on the last slab
       const int S = r->slabs_inflight;
       r->slabs_inflight = 0;
+      const bool solo = ctx->comm == nullptr;
       if (n4 == 0) {  // W is not updated by this call: just join the collective stream
-        CU_TRY(cudaStreamWaitEvent(ctx->stream, ctx->ev_red[S - 1], 0));
+        if (!solo) CU_TRY(cudaStreamWaitEvent(ctx->stream, ctx->ev_red[S - 1], 0));
+      } else if (solo) {
+        // single rank: the update of slab i goes to the second stream behind that slab's contraction, so it streams
+        // through HBM while the tensor cores contract the later slabs.  The last one carries the bias update and the
+        // step-state advance, so it also waits for everything enqueued so far (statistics that read the step state).
+        CU_TRY(cudaEventRecord(ctx->ev_fork, ctx->stream));
+        for (int i = 0; i < S; ++i) {
+          CU_TRY(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_slab[i], 0));
+          if (i == S - 1) CU_TRY(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_fork, 0));
+          const int64_t w0 = i * r->slab_rows, wn = std::min<int64_t>(r->slab_rows, r->V - w0);
+          const int64_t off = w0 * r->ldH, m4 = wn * r->ldH / 4;
+          kern<<<grid_for(ctx, m4, 256), 256, 0, ctx->comm_stream>>>(
+              r->W32.as<float>() + off, r->dW() + off, use_mom ? r->mW.as<float>() + off : nullptr,
+              r->Wp.buf[0].as<__nv_bfloat16>() + off, nullptr, nullptr, m4, hp->lr, scale, hp->momentum, hp->weight_decay,
+              i == S - 1 ? tail : UpdateTail{}, sdyn, world);
+          ctx->tm.aux_launches++;
+        }
+        CU_TRY(cudaEventRecord(ctx->ev_red[0], ctx->comm_stream));
+        CU_TRY(cudaStreamWaitEvent(ctx->stream, ctx->ev_red[0], 0));
+        if (adv_done != nullptr) *adv_done = adv != nullptr;
+        CU_TRY(cudaGetLastError());
+        return KUCD_OK;
       } else {
         for (int i = 0; i < S; ++i) {
           CU_TRY(cudaStreamWaitEvent(ctx->stream, ctx->ev_red[i], 0));
@@ -981,7 +1003,13 @@ static int prepare_exchange(kucd_rbm* r, int64_t rows_per_rank) {
     return e != nullptr ? atoi(e) : 1;
   }();
   r->slabs_now = 1;
-  if (slabs_env > 1 && !r->fused_now && ctx->comm != nullptr && r->compute == KUCD_COMPUTE_BF16) {
+  // (single rank: no all-reduce, but the HBM-bound update of slab i still overlaps the tensor-bound contraction of slab
+  // i+1 - at C4's share the update is 0.29 ms of a 1.71 ms step; pointless below a few MiB of weights)
+  static const int64_t slab_min_elems = [] {  // tests lower it to exercise the path at small sizes
+    const char* e = getenv("KUCD_AR_SLABS_MIN_ELEMS");
+    return e != nullptr ? static_cast<int64_t>(atoll(e)) : (int64_t{1} << 22);
+  }();
+  if (slabs_env > 1 && !r->fused_now && r->compute == KUCD_COMPUTE_BF16 && r->V * r->ldH >= slab_min_elems) {
     const int want = std::min(slabs_env, kucd_ctx::kMaxSlabs);
     const int64_t rows = round_up((r->V + want - 1) / want, 256);
     const int n = static_cast<int>((r->V + rows - 1) / rows);
@@ -1349,7 +1377,7 @@ static int enqueue_cd(kucd_rbm* r, const Planes& v0, int64_t batch, const kucd_h
   // KUCD_CHAIN_DW=1 appends the dW contraction to the chain kernel as a final two-segment stage.  Measured: no gain
   // at C3 (2.529 vs 2.522 ms per step) and a loss at C4 (577 k vs 605 k samples/s) - its second segment has to wait
   // for every row block of the last projection, so it hides little - which is why it is off by default.
-  const bool slabbed = r->slabs_now > 1 && !r->fused_now && ctx->comm != nullptr;
+  const bool slabbed = r->slabs_now > 1 && !r->fused_now;
   const bool chain_dw = ctx->chain_dw && !r->fused_now && !nccl16(r) && !slabbed;
   // latency-bound sizes: the whole step's contractions (projections and dW) as one launch of the small-tile variant
   static const bool small_chain_env = [] {
@@ -1387,10 +1415,12 @@ static int enqueue_cd(kucd_rbm* r, const Planes& v0, int64_t batch, const kucd_h
     }();
     const bool d16 = nccl16(r);
     const int S = r->slabs_now;
+    const bool solo = ctx->comm == nullptr;  // nothing to exchange: apply_update runs the slab updates on the second stream
     for (int i = 0; i < S; ++i) {
       const int64_t w0 = i * r->slab_rows, wn = std::min<int64_t>(r->slab_rows, r->V - w0);
-      KU_TRY(delta_w(r, v0, h0, vk, hk, batch, dyn, v0_dyn, w0, wn, reserve));
+      KU_TRY(delta_w(r, v0, h0, vk, hk, batch, dyn, v0_dyn, w0, wn, solo ? 0 : reserve));
       CU_TRY(cudaEventRecord(ctx->ev_slab[i], ctx->stream));
+      if (solo) continue;
       CU_TRY(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_slab[i], 0));
       const size_t off = static_cast<size_t>(w0) * r->ldH, cnt = static_cast<size_t>(wn) * r->ldH;
       int rc = i == 0 ? g_nccl.GroupStart() : 0;
@@ -1414,7 +1444,7 @@ static int enqueue_cd(kucd_rbm* r, const Planes& v0, int64_t batch, const kucd_h
       CU_TRY(cudaEventRecord(ctx->ev_red[i], ctx->comm_stream));
     }
     r->slabs_inflight = S;
-    ctx->tm.allreduce_calls++;
+    if (!solo) ctx->tm.allreduce_calls++;
   } else if (!((whole_chain && chain_dw) || small_chain)) {
     KU_TRY(delta_w(r, v0, h0, vk, hk, batch, dyn, v0_dyn));
   }

@@ -44,6 +44,26 @@ except Exception as e:  # noqa: BLE001
     print("chunk=%s: no line (%s)" % (sys.argv[1], e))
 EOF
   done
+  # KUCD_AR_SLABS on one GPU: the update of dW slab i (second stream, HBM-bound) overlaps the contraction of slab i+1
+  echo "== parity, KUCD_AR_SLABS=3 forced at test sizes (training tests: parameters must not change)" >> $LOG
+  KUCD_AR_SLABS=3 KUCD_AR_SLABS_MIN_ELEMS=1 timeout 900 python -m pytest tests -m gpu -x -q \
+      -k "cd_step or fit or chain or persistent or momentum or dbn or stream" >> $LOG 2>&1
+  echo "rc=$?" >> $LOG
+  for sl in 1 2 4 8; do
+    for w in c4 c3; do
+      echo "== bench $w, one GPU, KUCD_AR_SLABS=$sl" >> $LOG
+      KUCD_AR_SLABS=$sl timeout 300 python bench.py --workload $w --steps 60 --warmup 5 --no-cpu-baseline --no-e2e \
+          > gpurun_out/r02_bench_${w}_slabs$sl.json 2>> $LOG
+      python - "$w" "$sl" >> $LOG <<'EOF'
+import json, sys
+try:
+    d = json.loads(open("gpurun_out/r02_bench_%s_slabs%s.json" % (sys.argv[1], sys.argv[2])).read().strip().splitlines()[-1])
+    print("%s slabs=%s: %.4f ms per step, %.3f M samples/s" % (sys.argv[1], sys.argv[2], d["ms_per_step"], d["value"] / 1e6))
+except Exception as e:  # noqa: BLE001
+    print("%s slabs=%s: no line (%s)" % (sys.argv[1], sys.argv[2], e))
+EOF
+    done
+  done
   # where a latency-bound step spends its time: kernel durations of the C1 graph replay (3 launches per step); what is
   # left of the 43 us per step is launch gaps - the case for programmatic dependent launch (what comes next)
   echo "== ncu launch list, bench c1 (cold-cache, serialised: shares only)" >> $LOG
@@ -83,7 +103,7 @@ else
     KUCD_WIRE_BF16=1 KUCD_FUSED_REDUCE=0 timeout 600 $TR --nproc-per-node $N --master-port 29534 tests/dp_check.py >> $LOG 2>&1
     echo "rc=$?" >> $LOG
     echo "== dp_check, $N ranks, KUCD_AR_SLABS=2, fp32 ncclAllReduce in row slabs (same bar as the default)" >> $LOG
-    KUCD_AR_SLABS=2 KUCD_FUSED_REDUCE=0 timeout 600 $TR --nproc-per-node $N --master-port 29535 tests/dp_check.py >> $LOG 2>&1
+    KUCD_AR_SLABS=2 KUCD_AR_SLABS_MIN_ELEMS=1 KUCD_FUSED_REDUCE=0 timeout 600 $TR --nproc-per-node $N --master-port 29535 tests/dp_check.py >> $LOG 2>&1
     echo "rc=$?" >> $LOG
     echo "== dp_check, $N ranks, default (must stay bit-identical to one GPU)" >> $LOG
     timeout 600 $TR --nproc-per-node $N --master-port 29532 tests/dp_check.py >> $LOG 2>&1
