@@ -1,0 +1,183 @@
+"""Runs one scenario of the engine's HOST side against the fake CUDA runtime (tools/dryrun/fake_cudart.cpp) and prints a
+JSON summary: the recorded launches, the nodes of the last captured graph, allocation counters and every complaint of the
+fake (out-of-bounds copies, invalid tensor-map arguments, kernels pointed outside their buffers).  Executed in a process of
+its own by tests/test_host_dryrun.py - no torch, no GPU; environment switches of the scenario are set by the caller."""
+import ctypes as C
+import json
+import os
+import re
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+DRY = os.path.join(ROOT, "build", "dryrun")
+os.environ["KUCD_NCCL_LIB"] = os.path.join(DRY, "libfakecudart.so")
+
+import numpy as np  # noqa: E402
+
+from keras_unsupervised_b200 import _lib as L  # noqa: E402
+
+L.LIB_PATH = os.path.join(DRY, "libkucd_dry.so")
+from keras_unsupervised_b200.engine import Context, Dataset, Machine  # noqa: E402
+
+fake = C.CDLL(os.path.join(DRY, "libfakecudart.so"), mode=C.RTLD_GLOBAL)
+fake.fake_counter.restype = C.c_longlong
+
+
+def _lines(size_fn, line_fn):
+    out, buf = [], C.create_string_buffer(1024)
+    for i in range(size_fn()):
+        line_fn(i, buf, 1024)
+        out.append(buf.value.decode())
+    return out
+
+
+def _kernel(line):
+    """'launch _ZN4kucd15update_w_kernelILb0EE... grid=..' -> 'update_w_kernel<0>' style short name"""
+    m = re.match(r"launch (\S+)", line)
+    if not m:
+        return line.split()[0]
+    name = m.group(1)
+    short = re.sub(r"^_ZN4kucd\d+", "", name)
+    base = re.match(r"[a-z_0-9]+", short)
+    base = base.group(0) if base else short
+    targs = re.findall(r"(?:Li|Lb)(\d+)E", short.split("EEv")[0]) if "I" in short[len(base):len(base) + 1] else []
+    return base + ("<" + ",".join(targs) + ">" if targs else "")
+
+
+def snapshot():
+    log = _lines(fake.fake_log_size, fake.fake_log_line)
+    return {"log": log, "kernels": [_kernel(x) for x in log if x.startswith("launch") or x.startswith("graph_launch")
+                                    or x.startswith("allreduce") or x.startswith("broadcast")],
+            "graph": [_kernel(x) for x in _lines(fake.fake_last_graph_size, fake.fake_last_graph_line)],
+            "graph_raw": _lines(fake.fake_last_graph_size, fake.fake_last_graph_line),
+            "errors": _lines(fake.fake_error_count, fake.fake_error_line),
+            "mallocs": fake.fake_counter(0), "frees": fake.fake_counter(1), "live_bytes": fake.fake_counter(2),
+            "peak_bytes": fake.fake_counter(3)}
+
+
+def machine(ctx, V, H, compute=L.COMPUTE_BF16, mode=L.MODE_VISIBLE_BERNOULLI):
+    m = Machine(ctx, V, H, mode, compute, seed=3)
+    rng = np.random.default_rng(0)
+    m.set_params(rng.uniform(-0.05, 0.05, (V, H)).astype(np.float32), np.zeros(V, np.float32), np.zeros(H, np.float32))
+    return m
+
+
+def data(n, V, seed=1):
+    return (np.random.default_rng(seed).random((n, V)) < 0.3).astype(np.float32)
+
+
+def scenario(name):
+    out = {}
+    if name == "cd_step":
+        ctx = Context(device=0, seed=1)
+        for compute in (L.COMPUTE_BF16, L.COMPUTE_F32X3):
+            m = machine(ctx, 333, 130, compute)
+            fake.fake_reset()
+            m.cd_step(data(200, 333), Machine.hparams(lr=1e-3, k=2))
+            out["bf16" if compute == L.COMPUTE_BF16 else "f32"] = snapshot()
+    elif name == "fit_epoch":
+        ctx = Context(device=0, seed=1)
+        m = machine(ctx, 784, 500)
+        ds = Dataset.from_array(ctx, data(1000, 784), L.COMPUTE_BF16)
+        fake.fake_reset()
+        st = m.fit_epoch(ds, 128, Machine.hparams(lr=1e-3, k=1))
+        out = snapshot()
+        out["steps"] = st["steps"]
+        out["timings"] = ctx.timings()
+    elif name == "fit_host":  # KUCD_STREAM_CHUNK / KUCD_STREAM_GRAPH are read from the environment
+        ctx = Context(device=0, seed=1)
+        m = machine(ctx, 300, 200)
+        X = data(1000, 300)
+        fake.fake_reset()
+        st = m.fit_host(X, 128, Machine.hparams(lr=1e-3, k=2))
+        out = snapshot()
+        out["steps"] = st["steps"]
+        out["timings"] = ctx.timings()
+        fake.fake_reset()
+        st = m.fit_host(X, 128, Machine.hparams(lr=1e-3, k=2))          # a second pass reuses the captured step
+        out["second"] = snapshot()
+    elif name == "transform_loop":  # KUCD_PLANE_POOL
+        ctx = Context(device=0, seed=1)
+        m = machine(ctx, 512, 256)
+        ds = Dataset.from_array(ctx, data(1024, 512), L.COMPUTE_BF16)
+        m.transform_dataset(ds).close()
+        fake.fake_reset()
+        for _ in range(10):
+            h = m.transform_dataset(ds)
+            v = m.inv_transform_dataset(h)
+            h.close()
+            v.close()
+        out = snapshot()
+        ds.close()
+        ctx.close()
+        out["live_after_close"] = fake.fake_counter(4)
+    elif name == "slabs":  # KUCD_AR_SLABS (+ KUCD_AR_SLABS_MIN_ELEMS=1), one rank
+        ctx = Context(device=0, seed=1)
+        m = machine(ctx, 784, 500)
+        ds = Dataset.from_array(ctx, data(512, 784), L.COMPUTE_BF16)
+        fake.fake_reset()
+        m.fit_epoch(ds, 128, Machine.hparams(lr=1e-3, k=1, momentum=0.5))
+        out = snapshot()
+        fake.fake_reset()
+        m.cd_step(data(1024, 784), Machine.hparams(lr=1e-3, k=1))            # large-tile chain + slabs, direct launches
+        out["direct"] = snapshot()
+        fake.fake_reset()
+        m.cd_step(data(100, 784), Machine.hparams(lr=1e-3, k=1, update_mask=L.UPDATE_C | L.UPDATE_B))
+        out["no_w"] = snapshot()
+    elif name == "delta_rule":
+        ctx = Context(device=0, seed=1)
+        for compute in (L.COMPUTE_BF16, L.COMPUTE_F32X3):
+            m = machine(ctx, 333, 130, compute)
+            key = "bf16" if compute == L.COMPUTE_BF16 else "f32"
+            fake.fake_reset()
+            m.delta_rule(True, data(200, 333), data(200, 130, seed=2), 1e-2)
+            out[key + "_fwd"] = snapshot()
+            fake.fake_reset()
+            m.delta_rule(False, data(200, 130, seed=2), data(200, 333), 1e-2, normalize=True)
+            out[key + "_bwd"] = snapshot()
+    elif name == "two_ranks":  # KUCD_WIRE_BF16 / KUCD_AR_SLABS / KUCD_FUSED_REDUCE from the environment
+        # two contexts of this one process act as rank 0 and rank 1: the fake NCCL hands out communicators without
+        # talking to anybody, the fake IPC passes pointers through, so the exchange buffers really are each other's
+        ctxs = [Context(device=r, seed=1) for r in range(2)]
+        uid = (C.c_char * 128)()
+        L.check(ctxs[0].lib.kucd_comm_unique_id(uid))
+        for r, c in enumerate(ctxs):
+            L.check(c.lib.kucd_ctx_comm_init(c.handle, bytes(uid), r, 2))
+            c.rank, c.world = r, 2
+        V, H = 784, 500
+        ms = []
+        for c in ctxs:
+            m = Machine.__new__(Machine)
+            m.ctx, m.V, m.H, m.mode, m.compute = c, V, H, L.MODE_VISIBLE_BERNOULLI, L.COMPUTE_BF16
+            h = C.c_void_p()
+            L.check(c.lib.kucd_rbm_create(c.handle, V, H, m.mode, m.compute, C.byref(h)))
+            m.handle, m.fused_reduce = h, False
+            c._children.add(m)
+            m.set_params(np.zeros((V, H), np.float32), np.zeros(V, np.float32), np.zeros(H, np.float32))
+            ms.append(m)
+        fused = os.environ.get("KUCD_FUSED_REDUCE", "1") != "0"
+        if fused:
+            handles = []
+            for m in ms:
+                buf = (C.c_char * 128)()
+                L.check(m.ctx.lib.kucd_rbm_peer_export(m.handle, buf))
+                handles.append(bytes(buf))
+            # the fake's canary check reads through the "mapped" pointer: fine, it is the same memory
+            for m in ms:
+                L.check(m.ctx.lib.kucd_rbm_peer_attach(m.handle, b"".join(handles)))
+                m.fused_reduce = True
+        dss = [Dataset.from_array(c, data(256, V, seed=5 + r), L.COMPUTE_BF16) for r, c in enumerate(ctxs)]
+        fake.fake_reset()
+        hp = Machine.hparams(lr=1e-3, k=1)
+        for r, m in enumerate(ms):
+            m.fit_epoch(dss[r], 64, hp, global_row0=64 * r, want_stats=False)
+        out = snapshot()
+        out["timings"] = [c.timings() for c in ctxs]
+    else:
+        raise SystemExit("unknown scenario " + name)
+    return out
+
+
+if __name__ == "__main__":
+    print(json.dumps(scenario(sys.argv[1])))

@@ -1,0 +1,198 @@
+"""The engine's HOST logic on the CPU: csrc/kucd.cu linked against a fake CUDA runtime (tools/dryrun/fake_cudart.cpp) that
+records kernel launches instead of running them and checks every copy, memset, tensor-map descriptor and NCCL buffer
+against its allocation table.  Nothing numerical happens here - that is what the GPU parity tests are for - but the
+sequencing, the pointer arithmetic and the resource handling of every training entry point run for real, including the
+opt-in paths that were written when no GPU was available ("Switches"): the launch sequences below are what the
+first GPU run has to reproduce, and a descriptor or a slab pointer that leaves its buffer fails here first.
+
+Each scenario runs tests/dryrun_driver.py in a process of its own (environment switches are read once per process).
+The dry-run library is a test artefact under build/dryrun; the product only ever loads keras_unsupervised_b200/libkucd.so."""
+import json
+import os
+import subprocess
+import sys
+from collections import Counter
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DRY = os.path.join(ROOT, "build", "dryrun")
+CSRC = os.path.join(ROOT, "keras_unsupervised_b200", "csrc")
+FAKE_SRC = os.path.join(ROOT, "tools", "dryrun", "fake_cudart.cpp")
+
+
+def _newer(target, sources):
+    return os.path.exists(target) and all(os.path.getmtime(target) >= os.path.getmtime(s) for s in sources)
+
+
+@pytest.fixture(scope="session")
+def dry_build():
+    """g++ the fake runtime, nvcc the engine against it (-cudart none): ~1 minute when the sources changed."""
+    os.makedirs(DRY, exist_ok=True)
+    fake = os.path.join(DRY, "libfakecudart.so")
+    eng = os.path.join(DRY, "libkucd_dry.so")
+    if not _newer(fake, [FAKE_SRC]):
+        subprocess.run(["g++", "-std=c++17", "-O1", "-shared", "-fPIC", "-I/usr/local/cuda/include", "-o", fake, FAKE_SRC],
+                       check=True)
+    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(ROOT, "include", "kucd.h"), fake]
+    if not _newer(eng, srcs):
+        subprocess.run(["nvcc", "-std=c++17", "-O1", "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "none",
+                        "-shared", "-Xcompiler", "-fPIC", "-o", eng, os.path.join(CSRC, "kucd.cu"), "-L" + DRY,
+                        "-lfakecudart", "-ldl", "-Xlinker", "-rpath=$ORIGIN"], check=True)
+    return eng
+
+
+def run(scenario, **env):
+    e = {k: v for k, v in os.environ.items() if not k.startswith("KUCD_")}
+    e.update({k: str(v) for k, v in env.items()})
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "dryrun_driver.py"), scenario], env=e,
+                         capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
+    return json.loads(res.stdout.strip().splitlines()[-1])
+
+
+def clean(snap):
+    assert snap["errors"] == [], snap["errors"]
+    return snap
+
+
+CHAIN_SMALL = "chain_kernel<64,1,0>"
+DW = "gemm_bf16_kernel<64,1,1,0,0,1>"          # A MN-major, B MN-major, raw epilogue: the dW contraction
+DW16 = "gemm_bf16_kernel<128,1,1,6,0,1>"       # ... with the bf16 push epilogue (BN >= 128)
+PROJ = ["gemm_bf16_kernel<64,0,1,1,0,1>", "gemm_bf16_kernel<64,0,0,1,0,1>", "gemm_bf16_kernel<64,0,1,2,0,1>"]  # h, v, h prob
+
+
+def test_default_paths_launch_what_design_md_says(dry_build):
+    d = run("cd_step")
+    assert clean(d["bf16"])["kernels"] == ["ingest_kernel", "colsum_kernel", CHAIN_SMALL, "update_w_kernel<0>"]
+    f32 = clean(d["f32"])["kernels"]                     # float32-grade: one launch per contraction, piecewise (CH = 4)
+    assert f32[:2] == ["ingest_kernel", "colsum_kernel"] and f32[-1] == "update_w_kernel<0>"
+    assert len(f32) == 2 + 5 + 1 + 1 and all(k.endswith(",4,1>") for k in f32[2:-1])      # CD-2: 5 projections + dW
+    e = clean(run("fit_epoch"))
+    assert e["graph"] == ["colsum_store_kernel", "memset", CHAIN_SMALL, "update_w_kernel<0>"]   # 3 kernels per replay
+    assert e["kernels"] == ["set_dyn_kernel"] + ["graph_launch"] * 8 and e["steps"] == 8
+    assert e["timings"]["graph_kernel_launches"] == 24
+
+
+def test_streamed_fit_per_minibatch_and_chunked(dry_build):
+    plain = clean(run("fit_host"))
+    c = Counter(plain["kernels"])
+    assert c["ingest_kernel"] == 8 and c[CHAIN_SMALL] == 8 and c["update_w_kernel<0>"] == 8 and "graph_launch" not in c
+    assert plain["timings"]["h2d_bytes"] == 1000 * 300 * 4 and plain["timings"]["d2h_bytes"] == 8 * 4
+    assert clean(plain["second"])["mallocs"] == 0                       # a second pass allocates nothing
+    chunked = clean(run("fit_host", KUCD_STREAM_CHUNK=4))               # 1000 rows, batch 128: chunks of 512 and 488 rows
+    c = Counter(chunked["kernels"])
+    assert c["ingest_kernel"] == 2 and c["set_dyn_kernel"] == 2 and c["graph_launch"] == 7
+    assert c[CHAIN_SMALL] == 1 and c["update_w_kernel<0>"] == 1 and c["recon_kernel"] == 1     # the 104-row remainder
+    assert chunked["graph"] == ["colsum_store_kernel", "memset", CHAIN_SMALL, "memset", "recon_kernel",
+                                "recon_finish_kernel", "log_stat_kernel", "update_w_kernel<0>"]
+    assert chunked["timings"]["h2d_bytes"] == plain["timings"]["h2d_bytes"]
+    assert chunked["timings"]["d2h_bytes"] == plain["timings"]["d2h_bytes"] and chunked["steps"] == 8
+    second = clean(chunked["second"])
+    assert second["mallocs"] == 0 and Counter(second["kernels"])["graph_launch"] == 7          # the captured step is kept
+
+
+def test_plane_pool_replaces_allocations(dry_build):
+    off = clean(run("transform_loop"))
+    assert off["mallocs"] == 20 and off["frees"] == 20 and off["live_after_close"] == 0
+    on = clean(run("transform_loop", KUCD_PLANE_POOL=1))
+    assert on["mallocs"] <= 2 and on["frees"] == 0 and on["live_after_close"] == 0     # nothing leaks at context close
+    assert on["kernels"] == off["kernels"]
+
+
+def test_delta_rule_is_projection_colsum_dw_update(dry_build):
+    d = run("delta_rule")
+    for key, proj in (("bf16_fwd", "gemm_bf16_kernel<64,0,1,2,0,1>"), ("bf16_bwd", "gemm_bf16_kernel<64,0,0,2,0,1>"),
+                      ("f32_fwd", "gemm_bf16_kernel<128,0,1,2,4,1>"), ("f32_bwd", "gemm_bf16_kernel<128,0,0,2,4,1>")):
+        k = clean(d[key])["kernels"]
+        assert k[:2] == ["ingest_kernel", "ingest_kernel"] and k[2] == proj and k[3] == "colsum_kernel"
+        assert k[4].startswith("gemm_bf16_kernel<") and ",1,1,0," in k[4] and k[5] == "update_w_kernel<0>" and len(k) == 6
+
+
+def test_single_rank_slabs(dry_build):
+    d = run("slabs", KUCD_AR_SLABS=3, KUCD_AR_SLABS_MIN_ELEMS=1)        # 784 rows of W -> slabs of 512 and 272 rows
+    g = clean(d)["graph"]
+    assert g == ["colsum_store_kernel"] + PROJ + [DW, DW, "update_w_kernel<0>", "update_w_kernel<0>"]
+    assert clean(d["direct"])["kernels"][-4:] == [DW, DW, "update_w_kernel<0>", "update_w_kernel<0>"]
+    assert clean(d["no_w"])["kernels"][-3:] == [DW, DW, "update_w_kernel<0>"]     # biases only: one (tail) launch
+    off = clean(run("slabs"))                                            # the switch unset: the default step
+    assert off["graph"] == ["colsum_store_kernel", "memset", CHAIN_SMALL, "update_w_kernel<0>"]
+    small = clean(run("slabs", KUCD_AR_SLABS=3))                         # below the size floor: ignored
+    assert small["graph"] == off["graph"]
+
+
+@pytest.mark.parametrize("env,dw,exchange,update", [
+    (dict(KUCD_FUSED_MIN_ROWS=1), [DW],
+     ["push_bias_kernel", "peer_barrier_kernel", "reduce_bias_kernel"], ["update_w_sharded_kernel<0>"]),
+    (dict(KUCD_FUSED_MIN_ROWS=1, KUCD_WIRE_BF16=1), [DW16],
+     ["push_bias_kernel", "peer_barrier_kernel", "reduce_bias_kernel"], ["update_w_sharded_kernel<1>"]),
+    (dict(KUCD_FUSED_REDUCE=0, KUCD_WIRE_BF16=1), [DW16], ["allreduce", "allreduce"], ["update_w_kernel<1>"]),
+    (dict(KUCD_FUSED_REDUCE=0, KUCD_AR_SLABS=2, KUCD_AR_SLABS_MIN_ELEMS=1), [DW, "allreduce", "allreduce", DW], ["allreduce"],
+     ["update_w_kernel<0>", "update_w_kernel<0>"]),
+    (dict(KUCD_FUSED_REDUCE=0, KUCD_AR_SLABS=2, KUCD_AR_SLABS_MIN_ELEMS=1, KUCD_WIRE_BF16=1),
+     [DW16, "allreduce", "allreduce", DW16], ["allreduce"], ["update_w_kernel<1>", "update_w_kernel<1>"]),
+])
+def test_two_rank_exchange_variants(dry_build, env, dw, exchange, update):
+    d = clean(run("two_ranks", **env))
+    g = d["graph"]
+    assert g[:4] == ["colsum_store_kernel"] + PROJ
+    assert g[4:4 + len(dw) + len(exchange) + len(update)] == dw + exchange + update
+    for t in d["timings"]:
+        assert t["graph_launches"] == 4
+    if "allreduce" in exchange + dw:
+        assert d["timings"][0]["allreduce_calls"] == 1 and d["timings"][0]["fused_reduce_steps"] == 0
+    else:
+        assert d["timings"][0]["fused_reduce_steps"] == 1 and d["timings"][0]["allreduce_calls"] == 0
+
+
+def _allreduces(d):
+    """(count, nccl dtype) of every all-reduce of the captured step"""
+    out = []
+    for line in d["graph_raw"]:
+        if line.startswith("allreduce"):
+            f = dict(x.split("=") for x in line.split()[1:])
+            out.append((int(f["count"]), int(f["dtype"])))
+    return out
+
+
+def test_what_the_all_reduces_carry(dry_build):
+    V, H, ldH = 784, 500, 512
+    bias = (1024 + 256) + (512 + 256)                                   # [db | dc], each padded to 256 + 256 (kucd.cu)
+    F32, BF16 = 7, 9                                                    # ncclFloat32, ncclBfloat16
+    d = clean(run("two_ranks", KUCD_FUSED_REDUCE=0))
+    assert d["graph"] == ["colsum_store_kernel", "memset", CHAIN_SMALL, "allreduce", "update_w_kernel<0>"]
+    assert _allreduces(d) == [(V * ldH + bias, F32)]                    # one call over the whole block [dW | db | dc]
+    d = clean(run("two_ranks", KUCD_FUSED_REDUCE=0, KUCD_WIRE_BF16=1))
+    assert _allreduces(d) == [(V * ldH, BF16), (bias, F32)]             # dW as bf16, the small statistics as float32
+    d = clean(run("two_ranks", KUCD_FUSED_REDUCE=0, KUCD_AR_SLABS=2, KUCD_AR_SLABS_MIN_ELEMS=1, KUCD_WIRE_BF16=1))
+    assert _allreduces(d) == [(512 * ldH, BF16), (bias, F32), ((V - 512) * ldH, BF16)]   # slabs of 512 and 272 rows
+    d = clean(run("two_ranks", KUCD_FUSED_REDUCE=0, KUCD_AR_SLABS=2, KUCD_AR_SLABS_MIN_ELEMS=1))
+    assert _allreduces(d) == [(512 * ldH, F32), (bias, F32), ((V - 512) * ldH, F32)]
+
+
+def test_the_fake_runtime_does_catch_a_bad_descriptor(dry_build):
+    """The checker checks: a tensor map whose extent leaves its allocation is refused."""
+    import ctypes as C
+
+    fake = C.CDLL(os.path.join(DRY, "libfakecudart.so"))
+    fake.fake_reset()
+    p = C.c_void_p()
+    assert fake.cudaMalloc(C.byref(p), C.c_size_t(64 * 128 * 2)) == 0
+    fn = C.c_void_p()
+    res = C.c_int()
+    assert fake.cudaGetDriverEntryPoint(b"cuTensorMapEncodeTiled", C.byref(fn), C.c_ulonglong(0), C.byref(res)) == 0
+    enc = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
+                      C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_int, C.c_int, C.c_int, C.c_int)(fn.value)
+    tm = C.create_string_buffer(128 + 64)
+    tm_aligned = (C.addressof(tm) + 63) & ~63
+    ones = (C.c_uint32 * 2)(1, 1)
+    box = (C.c_uint32 * 2)(64, 64)
+    strides = (C.c_uint64 * 1)(128 * 2)
+    BF16, SW128 = 9, 3                                                  # CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, SWIZZLE_128B
+    good = (C.c_uint64 * 2)(128, 64)
+    assert enc(tm_aligned, BF16, 2, p, good, strides, box, ones, 0, SW128, 2, 0) == 0
+    bad_rows = (C.c_uint64 * 2)(128, 65)                                # one row more than was allocated
+    assert enc(tm_aligned, BF16, 2, p, bad_rows, strides, box, ones, 0, SW128, 2, 0) != 0
+    assert enc(tm_aligned, BF16, 2, C.c_void_p(p.value + 8), good, strides, box, ones, 0, SW128, 2, 0) != 0   # misaligned
+    assert fake.fake_error_count() == 2
+    assert fake.cudaFree(p) == 0

@@ -1,0 +1,547 @@
+// A stand-in for libcudart (and libnccl) that lets the HOST side of libkucd run without a GPU.
+//
+// Test infrastructure, not product: tests/test_host_dryrun.py links csrc/kucd.cu against this library instead of the
+// CUDA runtime and drives the engine's entry points on the CPU.  "Device" memory is host memory, copies and memsets
+// really happen, streams / events / graphs are book-keeping, and a kernel launch is RECORDED instead of executed:
+//   - every launch (kernel name, grid, block, dynamic shared memory, stream, captured or direct) goes to a log the test
+//     reads back, so launch sequences and counts of a training call can be asserted;
+//   - cudaMemcpy* / cudaMemset* ranges that touch a cudaMalloc'ed block must lie inside it;
+//   - cuTensorMapEncodeTiled (handed out through cudaGetDriverEntryPoint) checks its arguments the way the driver
+//     would: 16-byte aligned base inside an allocation, the described extent inside that allocation, strides multiples
+//     of 16 bytes, box sizes 1..256, inner box of at most 128 bytes for the 128-byte swizzle;
+//   - for the kernels whose parameter layout is simple (update_w_kernel, update_w_sharded_kernel) the pointer / length
+//     arguments are checked against the allocation table too;
+//   - ncclAllReduce / ncclBroadcast are recorded with type, count and stream, buffers bounds-checked;
+//   - cudaIpcGetMemHandle / OpenMemHandle pass the pointer through, so two contexts of ONE process can attach to each
+//     other's exchange buffers as rank 0 and rank 1.
+// Nothing numerical is computed: outputs of a dry run are meaningless, only the host logic is exercised.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+namespace {
+
+std::mutex g_mu;
+std::map<uintptr_t, size_t> g_allocs;       // base -> bytes
+std::map<const void*, std::string> g_funcs;  // host stub -> mangled kernel name
+std::vector<std::string> g_log;
+std::vector<std::string> g_errors;
+size_t g_malloc_calls = 0, g_free_calls = 0, g_live_bytes = 0, g_peak_bytes = 0;
+int g_device = 0;
+int g_capturing = 0;  // streams are not distinguished: one capture at a time is all the engine does
+std::vector<std::string> g_capture;          // launches of the capture in progress
+std::map<uintptr_t, std::vector<std::string>> g_graphs;
+uintptr_t g_next_handle = 0x1000;
+
+struct CallCfg {
+  dim3 grid, block;
+  size_t smem;
+  cudaStream_t stream;
+};
+thread_local std::vector<CallCfg> g_cfg;
+
+void err(const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_errors.push_back(buf);
+}
+
+void logf(const char* fmt, ...) {
+  char buf[768];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (g_capturing) g_capture.push_back(buf);
+  else g_log.push_back(buf);
+}
+
+// the allocation that contains p, or g_allocs.end()
+std::map<uintptr_t, size_t>::iterator owner(const void* p) {
+  const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+  auto it = g_allocs.upper_bound(a);
+  if (it == g_allocs.begin()) return g_allocs.end();
+  --it;
+  return a < it->first + it->second ? it : g_allocs.end();
+}
+
+// a range that starts inside a device allocation must end inside it (host ranges are not tracked)
+void check_range(const void* p, size_t bytes, const char* what) {
+  if (p == nullptr || bytes == 0) return;
+  auto it = owner(p);
+  if (it == g_allocs.end()) return;
+  const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+  if (a + bytes > it->first + it->second)
+    err("%s: %zu bytes at offset %zu overrun an allocation of %zu bytes", what, bytes, static_cast<size_t>(a - it->first),
+        it->second);
+}
+
+// [p, p + bytes) must be device memory
+void check_device_range(const void* p, size_t bytes, const char* what) {
+  if (bytes == 0) return;
+  if (p == nullptr || owner(p) == g_allocs.end()) {
+    err("%s: %p is not inside a device allocation", what, p);
+    return;
+  }
+  check_range(p, bytes, what);
+}
+
+const char* kname(const void* func) {
+  auto it = g_funcs.find(func);
+  return it == g_funcs.end() ? "?" : it->second.c_str();
+}
+
+// kernels whose first arguments are plain (pointer, ..., length) - checked against the allocation table
+void check_kernel_args(const std::string& name, void** args) {
+  if (args == nullptr) return;
+  auto ptr = [&](int i) { return *reinterpret_cast<void**>(args[i]); };
+  if (name.find("update_w_kernel") != std::string::npos) {
+    // (W, dW, mom, hi, mid, lo, n4, ...): n4 float4 of W / dW (uint2 when dW is bf16), n4 uint2 of each plane
+    const int64_t n4 = *reinterpret_cast<int64_t*>(args[6]);
+    const bool d16 = name.find("ILb1") != std::string::npos;
+    if (n4 > 0) {
+      check_device_range(ptr(0), static_cast<size_t>(n4) * 16, "update_w_kernel W");
+      check_device_range(ptr(1), static_cast<size_t>(n4) * (d16 ? 8 : 16), "update_w_kernel dW");
+      if (ptr(2) != nullptr) check_device_range(ptr(2), static_cast<size_t>(n4) * 16, "update_w_kernel momentum");
+      check_device_range(ptr(3), static_cast<size_t>(n4) * 8, "update_w_kernel bf16 plane");
+      if (ptr(4) != nullptr) check_device_range(ptr(4), static_cast<size_t>(n4) * 8, "update_w_kernel mid plane");
+      if (ptr(5) != nullptr) check_device_range(ptr(5), static_cast<size_t>(n4) * 8, "update_w_kernel lo plane");
+    }
+  }
+}
+
+void record_launch(const void* func, dim3 grid, dim3 block, size_t smem, cudaStream_t stream, void** args, int cluster) {
+  const std::string name = kname(func);
+  if (grid.x == 0 || grid.y == 0 || grid.z == 0 || block.x * block.y * block.z == 0 || block.x * block.y * block.z > 1024)
+    err("launch of %s with grid (%u,%u,%u) block (%u,%u,%u)", name.c_str(), grid.x, grid.y, grid.z, block.x, block.y, block.z);
+  if (smem > 232448) err("launch of %s with %zu bytes of dynamic shared memory", name.c_str(), smem);
+  if (cluster > 1 && grid.x % cluster != 0) err("launch of %s: grid %u is not a multiple of the cluster size %d", name.c_str(), grid.x, cluster);
+  check_kernel_args(name, args);
+  logf("launch %s grid=%u,%u,%u block=%u,%u,%u smem=%zu stream=%p cluster=%d", name.c_str(), grid.x, grid.y, grid.z,
+       block.x, block.y, block.z, smem, static_cast<void*>(stream), cluster);
+}
+
+// ---- cuTensorMapEncodeTiled stand-in --------------------------------------------------------------------------
+CUresult fake_encode_tiled(CUtensorMap* tm, CUtensorMapDataType dtype, cuuint32_t rank, void* base, const cuuint64_t* dims,
+                           const cuuint64_t* strides, const cuuint32_t* box, const cuuint32_t* estr,
+                           CUtensorMapInterleave, CUtensorMapSwizzle swizzle, CUtensorMapL2promotion,
+                           CUtensorMapFloatOOBfill) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  const size_t esz = (dtype == CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 || dtype == CU_TENSOR_MAP_DATA_TYPE_FLOAT16) ? 2 : 4;
+  bool ok = tm != nullptr && rank >= 1 && rank <= 5 && base != nullptr;
+  if (ok && (reinterpret_cast<uintptr_t>(base) & 15u)) {
+    err("tensor map: base %p is not 16-byte aligned", base);
+    ok = false;
+  }
+  for (cuuint32_t i = 0; ok && i < rank; ++i) {
+    if (dims[i] == 0 || dims[i] > (1ull << 32)) {
+      err("tensor map: dim[%u] = %llu", i, (unsigned long long)dims[i]);
+      ok = false;
+    }
+    if (box[i] == 0 || box[i] > 256) {
+      err("tensor map: box[%u] = %u", i, box[i]);
+      ok = false;
+    }
+    if (estr[i] == 0 || estr[i] > 8) ok = false;
+    if (i + 1 < rank && (strides[i] % 16 != 0 || strides[i] == 0)) {
+      err("tensor map: stride[%u] = %llu bytes is not a positive multiple of 16", i, (unsigned long long)strides[i]);
+      ok = false;
+    }
+  }
+  if (ok && swizzle == CU_TENSOR_MAP_SWIZZLE_128B && box[0] * esz > 128) {
+    err("tensor map: inner box of %zu bytes with the 128-byte swizzle", box[0] * esz);
+    ok = false;
+  }
+  if (ok && rank == 2) {
+    if (dims[0] * esz > strides[0]) {
+      err("tensor map: rows of %llu bytes overlap (pitch %llu)", (unsigned long long)(dims[0] * esz), (unsigned long long)strides[0]);
+      ok = false;
+    }
+    // the last row ends inside the allocation the base points into
+    const size_t extent = static_cast<size_t>(dims[1] - 1) * strides[0] + static_cast<size_t>(dims[0]) * esz;
+    auto it = owner(base);
+    if (it == g_allocs.end()) {
+      err("tensor map: base %p is not device memory", base);
+      ok = false;
+    } else if (reinterpret_cast<uintptr_t>(base) + extent > it->first + it->second) {
+      err("tensor map: %llu x %llu (pitch %llu) at offset %zu overruns an allocation of %zu bytes", (unsigned long long)dims[1],
+          (unsigned long long)dims[0], (unsigned long long)strides[0],
+          static_cast<size_t>(reinterpret_cast<uintptr_t>(base) - it->first), it->second);
+      ok = false;
+    }
+  }
+  if (!ok) return CUDA_ERROR_INVALID_VALUE;
+  memset(tm, 0, sizeof *tm);
+  memcpy(tm, &base, sizeof base);
+  return CUDA_SUCCESS;
+}
+
+}  // namespace
+
+#define LOCK std::lock_guard<std::mutex> lk(g_mu)
+
+extern "C" {
+
+// ---- test interface -------------------------------------------------------------------------------------------
+void fake_reset() {
+  LOCK;
+  g_log.clear();
+  g_errors.clear();
+  g_malloc_calls = g_free_calls = 0;
+  g_peak_bytes = g_live_bytes;
+}
+int fake_log_size() {
+  LOCK;
+  return static_cast<int>(g_log.size());
+}
+int fake_log_line(int i, char* buf, int n) {
+  LOCK;
+  if (i < 0 || i >= static_cast<int>(g_log.size())) return -1;
+  snprintf(buf, n, "%s", g_log[i].c_str());
+  return 0;
+}
+int fake_error_count() {
+  LOCK;
+  return static_cast<int>(g_errors.size());
+}
+int fake_error_line(int i, char* buf, int n) {
+  LOCK;
+  if (i < 0 || i >= static_cast<int>(g_errors.size())) return -1;
+  snprintf(buf, n, "%s", g_errors[i].c_str());
+  return 0;
+}
+long long fake_counter(int which) {  // 0 cudaMalloc calls, 1 cudaFree calls, 2 live bytes, 3 peak bytes, 4 live allocations
+  LOCK;
+  switch (which) {
+    case 0: return static_cast<long long>(g_malloc_calls);
+    case 1: return static_cast<long long>(g_free_calls);
+    case 2: return static_cast<long long>(g_live_bytes);
+    case 3: return static_cast<long long>(g_peak_bytes);
+    default: return static_cast<long long>(g_allocs.size());
+  }
+}
+
+// ---- registration of the kernels (called by the nvcc-generated module constructor) --------------------------
+void** __cudaRegisterFatBinary(void*) {
+  static void* handle = nullptr;
+  return &handle;
+}
+void __cudaRegisterFatBinaryEnd(void**) {}
+void __cudaUnregisterFatBinary(void**) {}
+void __cudaRegisterFunction(void**, const char* hostFun, char*, const char* deviceName, int, uint3*, uint3*, dim3*, dim3*, int*) {
+  LOCK;
+  g_funcs[hostFun] = deviceName;
+}
+void __cudaRegisterVar(void**, char*, char*, const char*, int, size_t, int, int) {}
+unsigned __cudaPushCallConfiguration(dim3 grid, dim3 block, size_t smem, cudaStream_t stream) {
+  g_cfg.push_back({grid, block, smem, stream});
+  return 0;
+}
+cudaError_t __cudaPopCallConfiguration(dim3* grid, dim3* block, size_t* smem, void* stream) {
+  if (g_cfg.empty()) return cudaErrorInvalidConfiguration;
+  const CallCfg c = g_cfg.back();
+  g_cfg.pop_back();
+  *grid = c.grid;
+  *block = c.block;
+  *smem = c.smem;
+  *static_cast<cudaStream_t*>(stream) = c.stream;
+  return cudaSuccess;
+}
+
+// ---- devices ------------------------------------------------------------------------------------------------
+cudaError_t cudaGetDeviceCount(int* n) {
+  const char* e = getenv("FAKE_CUDA_DEVICES");
+  *n = e != nullptr ? atoi(e) : 2;
+  return cudaSuccess;
+}
+cudaError_t cudaSetDevice(int d) {
+  g_device = d;
+  return cudaSuccess;
+}
+cudaError_t cudaGetDevice(int* d) {
+  *d = g_device;
+  return cudaSuccess;
+}
+cudaError_t cudaGetDeviceProperties_v2(cudaDeviceProp* p, int) {
+  memset(p, 0, sizeof *p);
+  snprintf(p->name, sizeof p->name, "dry-run sm_100 (no GPU)");
+  p->major = 10;
+  p->minor = 0;
+  p->multiProcessorCount = 148;
+  p->totalGlobalMem = 180ull << 30;
+  return cudaSuccess;
+}
+cudaError_t cudaGetLastError() { return cudaSuccess; }
+const char* cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : "dry-run error"; }
+cudaError_t cudaFuncSetAttribute(const void*, cudaFuncAttribute, int value) {
+  if (value > 232448) {
+    LOCK;
+    err("cudaFuncSetAttribute: %d bytes of dynamic shared memory", value);
+    return cudaErrorInvalidValue;
+  }
+  return cudaSuccess;
+}
+cudaError_t cudaOccupancyMaxActiveClusters(int* n, const void*, const cudaLaunchConfig_t*) {
+  *n = 74;
+  return cudaSuccess;
+}
+cudaError_t cudaGetDriverEntryPoint(const char* symbol, void** fn, unsigned long long, cudaDriverEntryPointQueryResult* res) {
+  if (strcmp(symbol, "cuTensorMapEncodeTiled") == 0) {
+    *fn = reinterpret_cast<void*>(&fake_encode_tiled);
+    if (res != nullptr) *res = cudaDriverEntryPointSuccess;
+    return cudaSuccess;
+  }
+  if (res != nullptr) *res = cudaDriverEntryPointSymbolNotFound;
+  return cudaErrorNotSupported;
+}
+
+// ---- memory -------------------------------------------------------------------------------------------------
+cudaError_t cudaMalloc(void** p, size_t n) {
+  LOCK;
+  void* q = nullptr;
+  if (posix_memalign(&q, 512, n == 0 ? 512 : n) != 0) return cudaErrorMemoryAllocation;
+  // pages are not touched here: a dry run of a C4-sized model must not need C4-sized RAM
+  g_allocs[reinterpret_cast<uintptr_t>(q)] = n;
+  g_malloc_calls++;
+  g_live_bytes += n;
+  if (g_live_bytes > g_peak_bytes) g_peak_bytes = g_live_bytes;
+  *p = q;
+  return cudaSuccess;
+}
+cudaError_t cudaFree(void* p) {
+  if (p == nullptr) return cudaSuccess;
+  LOCK;
+  auto it = g_allocs.find(reinterpret_cast<uintptr_t>(p));
+  if (it == g_allocs.end()) {
+    err("cudaFree of %p, which is not the base of a live allocation", p);
+    return cudaErrorInvalidValue;
+  }
+  g_live_bytes -= it->second;
+  g_allocs.erase(it);
+  g_free_calls++;
+  free(p);
+  return cudaSuccess;
+}
+cudaError_t cudaHostAlloc(void** p, size_t n, unsigned) {
+  *p = malloc(n == 0 ? 1 : n);
+  return *p != nullptr ? cudaSuccess : cudaErrorMemoryAllocation;
+}
+cudaError_t cudaFreeHost(void* p) {
+  free(p);
+  return cudaSuccess;
+}
+static const size_t kTouchLimit = size_t{64} << 20;  // larger copies / fills are checked but not performed
+cudaError_t cudaMemset(void* p, int v, size_t n) {
+  LOCK;
+  check_device_range(p, n, "cudaMemset");
+  if (n <= kTouchLimit && owner(p) != g_allocs.end()) memset(p, v, n);
+  return cudaSuccess;
+}
+cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) {
+  LOCK;
+  check_device_range(p, n, "cudaMemsetAsync");
+  if (g_capturing) {
+    logf("memset %zu", n);
+    return cudaSuccess;
+  }
+  if (n <= kTouchLimit && owner(p) != g_allocs.end()) memset(p, v, n);
+  return cudaSuccess;
+}
+static cudaError_t do_copy(void* d, const void* s, size_t n, const char* what) {
+  LOCK;
+  check_range(d, n, what);
+  check_range(s, n, what);
+  if (g_capturing) {
+    logf("memcpy %zu", n);
+    return cudaSuccess;
+  }
+  if (n <= kTouchLimit) memmove(d, s, n);
+  return cudaSuccess;
+}
+cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { return do_copy(d, s, n, "cudaMemcpy"); }
+cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) {
+  return do_copy(d, s, n, "cudaMemcpyAsync");
+}
+cudaError_t cudaMemcpy2DAsync(void* d, size_t dp, const void* s, size_t sp, size_t w, size_t h, cudaMemcpyKind, cudaStream_t) {
+  LOCK;
+  if (h == 0 || w == 0) return cudaSuccess;
+  if (w > dp || w > sp) {
+    err("cudaMemcpy2DAsync: width %zu exceeds a pitch (%zu, %zu)", w, dp, sp);
+    return cudaErrorInvalidValue;
+  }
+  check_range(d, (h - 1) * dp + w, "cudaMemcpy2DAsync dst");
+  check_range(s, (h - 1) * sp + w, "cudaMemcpy2DAsync src");
+  if (w * h <= kTouchLimit)
+    for (size_t r = 0; r < h; ++r) memmove(static_cast<char*>(d) + r * dp, static_cast<const char*>(s) + r * sp, w);
+  return cudaSuccess;
+}
+cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p) {
+  memset(h, 0, sizeof *h);
+  memcpy(h, &p, sizeof p);
+  return cudaSuccess;
+}
+cudaError_t cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t h, unsigned) {
+  memcpy(p, &h, sizeof *p);
+  return cudaSuccess;
+}
+cudaError_t cudaIpcCloseMemHandle(void*) { return cudaSuccess; }
+
+// ---- streams, events, graphs --------------------------------------------------------------------------------
+cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) {
+  LOCK;
+  *s = reinterpret_cast<cudaStream_t>(g_next_handle += 16);
+  return cudaSuccess;
+}
+cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }
+cudaError_t cudaStreamSynchronize(cudaStream_t) {
+  LOCK;
+  if (g_capturing) {
+    err("cudaStreamSynchronize while a capture is in progress");
+    return cudaErrorStreamCaptureUnsupported;
+  }
+  return cudaSuccess;
+}
+cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t e, unsigned) {
+  LOCK;
+  if (e == nullptr) {
+    err("cudaStreamWaitEvent on a NULL event");
+    return cudaErrorInvalidResourceHandle;
+  }
+  return cudaSuccess;
+}
+cudaError_t cudaEventCreate(cudaEvent_t* e) {
+  LOCK;
+  *e = reinterpret_cast<cudaEvent_t>(g_next_handle += 16);
+  return cudaSuccess;
+}
+cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { return cudaEventCreate(e); }
+cudaError_t cudaEventDestroy(cudaEvent_t) { return cudaSuccess; }
+cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t) {
+  LOCK;
+  if (e == nullptr) {
+    err("cudaEventRecord on a NULL event");
+    return cudaErrorInvalidResourceHandle;
+  }
+  return cudaSuccess;
+}
+cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) {
+  *ms = 0.f;
+  return cudaSuccess;
+}
+cudaError_t cudaStreamBeginCapture(cudaStream_t, cudaStreamCaptureMode) {
+  LOCK;
+  if (g_capturing) {
+    err("nested stream capture");
+    return cudaErrorIllegalState;
+  }
+  g_capturing = 1;
+  g_capture.clear();
+  return cudaSuccess;
+}
+cudaError_t cudaStreamEndCapture(cudaStream_t, cudaGraph_t* g) {
+  LOCK;
+  if (!g_capturing) return cudaErrorIllegalState;
+  g_capturing = 0;
+  const uintptr_t h = (g_next_handle += 16);
+  g_graphs[h] = g_capture;
+  *g = reinterpret_cast<cudaGraph_t>(h);
+  return cudaSuccess;
+}
+cudaError_t cudaGraphInstantiate(cudaGraphExec_t* ge, cudaGraph_t g, unsigned long long) {
+  *ge = reinterpret_cast<cudaGraphExec_t>(g);
+  return cudaSuccess;
+}
+cudaError_t cudaGraphLaunch(cudaGraphExec_t ge, cudaStream_t) {
+  LOCK;
+  auto it = g_graphs.find(reinterpret_cast<uintptr_t>(ge));
+  if (it == g_graphs.end()) {
+    err("cudaGraphLaunch of an unknown or destroyed graph");
+    return cudaErrorInvalidValue;
+  }
+  g_log.push_back("graph_launch nodes=" + std::to_string(it->second.size()));
+  return cudaSuccess;
+}
+cudaError_t cudaGraphDestroy(cudaGraph_t g) {
+  LOCK;
+  g_graphs.erase(reinterpret_cast<uintptr_t>(g));
+  return cudaSuccess;
+}
+cudaError_t cudaGraphExecDestroy(cudaGraphExec_t) { return cudaSuccess; }
+
+// the nodes of a captured graph, for the test (graph = the handle cudaStreamEndCapture returned most recently)
+int fake_last_graph_size() {
+  LOCK;
+  return g_graphs.empty() ? -1 : static_cast<int>(g_graphs.rbegin()->second.size());
+}
+int fake_last_graph_line(int i, char* buf, int n) {
+  LOCK;
+  if (g_graphs.empty()) return -1;
+  const auto& v = g_graphs.rbegin()->second;
+  if (i < 0 || i >= static_cast<int>(v.size())) return -1;
+  snprintf(buf, n, "%s", v[i].c_str());
+  return 0;
+}
+
+// ---- launches -----------------------------------------------------------------------------------------------
+cudaError_t cudaLaunchKernel(const void* func, dim3 grid, dim3 block, void** args, size_t smem, cudaStream_t stream) {
+  LOCK;
+  record_launch(func, grid, block, smem, stream, args, 1);
+  return cudaSuccess;
+}
+cudaError_t cudaLaunchKernelExC(const cudaLaunchConfig_t* cfg, const void* func, void** args) {
+  LOCK;
+  int cluster = 1;
+  for (unsigned i = 0; i < cfg->numAttrs; ++i)
+    if (cfg->attrs[i].id == cudaLaunchAttributeClusterDimension) cluster = static_cast<int>(cfg->attrs[i].val.clusterDim.x);
+  record_launch(func, cfg->gridDim, cfg->blockDim, cfg->dynamicSmemBytes, cfg->stream, args, cluster);
+  return cudaSuccess;
+}
+
+// ---- NCCL (KUCD_NCCL_LIB points at this library) --------------------------------------------------------------
+struct FakeUid {
+  char internal[128];
+};
+int ncclGetUniqueId(FakeUid* id) {
+  memset(id, 7, sizeof *id);
+  return 0;
+}
+int ncclCommInitRank(void** comm, int world, FakeUid, int rank) {
+  *comm = reinterpret_cast<void*>(static_cast<uintptr_t>(0x7000 + world * 16 + rank));
+  return 0;
+}
+int ncclCommDestroy(void*) { return 0; }
+static size_t nccl_esize(int dtype) { return dtype == 9 || dtype == 6 ? 2 : (dtype == 8 || dtype == 4 || dtype == 5 ? 8 : (dtype <= 1 ? 1 : 4)); }
+int ncclAllReduce(const void* s, void* d, size_t count, int dtype, int op, void* comm, cudaStream_t stream) {
+  LOCK;
+  if (comm == nullptr) err("ncclAllReduce without a communicator");
+  check_device_range(s, count * nccl_esize(dtype), "ncclAllReduce send");
+  check_device_range(d, count * nccl_esize(dtype), "ncclAllReduce recv");
+  logf("allreduce count=%zu dtype=%d op=%d stream=%p", count, dtype, op, static_cast<void*>(stream));
+  return 0;
+}
+int ncclBroadcast(const void* s, void* d, size_t count, int dtype, int root, void* comm, cudaStream_t stream) {
+  LOCK;
+  if (comm == nullptr) err("ncclBroadcast without a communicator");
+  check_device_range(d, count * nccl_esize(dtype), "ncclBroadcast recv");
+  (void)s;
+  logf("broadcast count=%zu dtype=%d root=%d stream=%p", count, dtype, root, static_cast<void*>(stream));
+  return 0;
+}
+int ncclGroupStart() { return 0; }
+int ncclGroupEnd() { return 0; }
+const char* ncclGetErrorString(int) { return "dry-run nccl"; }
+
+}  // extern "C"
