@@ -85,6 +85,13 @@ def scenario(name):
         out = snapshot()
         out["steps"] = st["steps"]
         out["timings"] = ctx.timings()
+    elif name == "split":  # KUCD_SPLIT=2 KUCD_CHAIN=0: two Gibbs chains on two streams, forked and joined inside the capture
+        ctx = Context(device=0, seed=1)
+        m = machine(ctx, 784, 500)
+        ds = Dataset.from_array(ctx, data(1024, 784), L.COMPUTE_BF16)
+        fake.fake_reset()
+        m.fit_epoch(ds, 512, Machine.hparams(lr=1e-3, k=2, persistent=False))
+        out = snapshot()
     elif name == "fit_host":  # KUCD_STREAM_CHUNK / KUCD_STREAM_GRAPH are read from the environment
         ctx = Context(device=0, seed=1)
         m = machine(ctx, 300, 200)

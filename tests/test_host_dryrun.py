@@ -74,6 +74,16 @@ def test_default_paths_launch_what_design_md_says(dry_build):
     assert e["timings"]["graph_kernel_launches"] == 24
 
 
+def test_two_chain_split_forks_and_joins_inside_the_capture(dry_build):
+    d = clean(run("split", KUCD_SPLIT=2, KUCD_CHAIN=0))      # no capture-isolation / unjoined-work complaint from the fake
+    g = d["graph"]
+    assert d["kernels"] == ["set_dyn_kernel", "graph_launch", "graph_launch"]          # nothing escaped the capture
+    assert len([k for k in g if k.startswith("gemm_bf16_kernel<64,0,")]) == 10        # 2 chains x (2k + 1) projections
+    assert g[-2:] == [DW, "update_w_kernel<0>"]
+    streams = {line.split("stream=")[1].split()[0] for line in d["graph_raw"] if line.startswith("launch")}
+    assert len(streams) == 2                                                           # both streams are in the graph
+
+
 def test_streamed_fit_per_minibatch_and_chunked(dry_build):
     plain = clean(run("fit_host"))
     c = Counter(plain["kernels"])

@@ -37,7 +37,25 @@ std::vector<std::string> g_log;
 std::vector<std::string> g_errors;
 size_t g_malloc_calls = 0, g_free_calls = 0, g_live_bytes = 0, g_peak_bytes = 0;
 int g_device = 0;
-int g_capturing = 0;  // streams are not distinguished: one capture at a time is all the engine does
+// Stream capture, modelled on the rules the engine relies on: a capture starts on one stream; another stream joins it by
+// waiting on an event recorded inside the capture (fork) and must hand its work back through an event the capture waits
+// on (join) before the capture ends; a capturing stream cannot wait on an event recorded outside the capture; work on a
+// stream that is not part of the capture is NOT captured - it runs (is logged) directly, which is how a forgotten fork
+// shows up in a test.
+int g_capturing = 0;                         // id of the capture in progress (0: none); one at a time is all the engine does
+int g_capture_seq = 0;
+cudaStream_t g_capture_origin = nullptr;
+struct Member {
+  long work = 0;    // pieces of work captured on this stream
+  long joined = 0;  // ... of which this many are behind an event that a member of the capture has waited for
+};
+std::map<cudaStream_t, Member> g_capture_streams;
+struct EventState {
+  int capture;      // capture id at its last record (0: recorded outside any capture)
+  cudaStream_t stream;
+  long work;        // the recording stream's work count at that moment
+};
+std::map<cudaEvent_t, EventState> g_event_state;
 std::vector<std::string> g_capture;          // launches of the capture in progress
 std::map<uintptr_t, std::vector<std::string>> g_graphs;
 uintptr_t g_next_handle = 0x1000;
@@ -58,14 +76,21 @@ void err(const char* fmt, ...) {
   g_errors.push_back(buf);
 }
 
-void logf(const char* fmt, ...) {
+bool captured(cudaStream_t s) { return g_capturing != 0 && g_capture_streams.count(s) != 0; }
+
+// work enqueued on stream s: into the capture when s is part of it, else it "runs"
+void logw(cudaStream_t s, const char* fmt, ...) {
   char buf[768];
   va_list ap;
   va_start(ap, fmt);
   vsnprintf(buf, sizeof buf, fmt, ap);
   va_end(ap);
-  if (g_capturing) g_capture.push_back(buf);
-  else g_log.push_back(buf);
+  if (captured(s)) {
+    g_capture.push_back(buf);
+    g_capture_streams[s].work++;
+  } else {
+    g_log.push_back(buf);
+  }
 }
 
 // the allocation that contains p, or g_allocs.end()
@@ -129,7 +154,7 @@ void record_launch(const void* func, dim3 grid, dim3 block, size_t smem, cudaStr
   if (smem > 232448) err("launch of %s with %zu bytes of dynamic shared memory", name.c_str(), smem);
   if (cluster > 1 && grid.x % cluster != 0) err("launch of %s: grid %u is not a multiple of the cluster size %d", name.c_str(), grid.x, cluster);
   check_kernel_args(name, args);
-  logf("launch %s grid=%u,%u,%u block=%u,%u,%u smem=%zu stream=%p cluster=%d", name.c_str(), grid.x, grid.y, grid.z,
+  logw(stream, "launch %s grid=%u,%u,%u block=%u,%u,%u smem=%zu stream=%p cluster=%d", name.c_str(), grid.x, grid.y, grid.z,
        block.x, block.y, block.z, smem, static_cast<void*>(stream), cluster);
 }
 
@@ -349,30 +374,33 @@ cudaError_t cudaMemset(void* p, int v, size_t n) {
   if (n <= kTouchLimit && owner(p) != g_allocs.end()) memset(p, v, n);
   return cudaSuccess;
 }
-cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) {
+cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t st) {
   LOCK;
   check_device_range(p, n, "cudaMemsetAsync");
-  if (g_capturing) {
-    logf("memset %zu", n);
+  if (captured(st)) {
+    logw(st, "memset %zu", n);
     return cudaSuccess;
   }
   if (n <= kTouchLimit && owner(p) != g_allocs.end()) memset(p, v, n);
   return cudaSuccess;
 }
-static cudaError_t do_copy(void* d, const void* s, size_t n, const char* what) {
+static cudaError_t do_copy(void* d, const void* s, size_t n, const char* what, cudaStream_t st, bool async) {
   LOCK;
   check_range(d, n, what);
   check_range(s, n, what);
-  if (g_capturing) {
-    logf("memcpy %zu", n);
+  if (async && captured(st)) {
+    logw(st, "memcpy %zu", n);
     return cudaSuccess;
   }
+  if (!async && g_capturing) err("%s (synchronous) while a capture is in progress", what);
   if (n <= kTouchLimit) memmove(d, s, n);
   return cudaSuccess;
 }
-cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { return do_copy(d, s, n, "cudaMemcpy"); }
-cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) {
-  return do_copy(d, s, n, "cudaMemcpyAsync");
+cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) {
+  return do_copy(d, s, n, "cudaMemcpy", nullptr, false);
+}
+cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t st) {
+  return do_copy(d, s, n, "cudaMemcpyAsync", st, true);
 }
 cudaError_t cudaMemcpy2DAsync(void* d, size_t dp, const void* s, size_t sp, size_t w, size_t h, cudaMemcpyKind, cudaStream_t) {
   LOCK;
@@ -405,19 +433,38 @@ cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) {
   return cudaSuccess;
 }
 cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }
-cudaError_t cudaStreamSynchronize(cudaStream_t) {
+cudaError_t cudaStreamSynchronize(cudaStream_t st) {
   LOCK;
-  if (g_capturing) {
-    err("cudaStreamSynchronize while a capture is in progress");
+  if (captured(st)) {
+    err("cudaStreamSynchronize on a capturing stream");
     return cudaErrorStreamCaptureUnsupported;
   }
   return cudaSuccess;
 }
-cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t e, unsigned) {
+cudaError_t cudaStreamWaitEvent(cudaStream_t st, cudaEvent_t e, unsigned) {
   LOCK;
   if (e == nullptr) {
     err("cudaStreamWaitEvent on a NULL event");
     return cudaErrorInvalidResourceHandle;
+  }
+  auto it = g_event_state.find(e);
+  if (it == g_event_state.end()) {
+    err("cudaStreamWaitEvent on an event that was never recorded (the wait orders nothing)");
+    return cudaSuccess;
+  }
+  const int ev_capture = it->second.capture;
+  const cudaStream_t ev_stream = it->second.stream;
+  if (g_capturing && ev_capture == g_capturing) {
+    // an event of this capture: the waiting stream becomes (or stays) part of it, and the recording stream's work
+    // up to that event is now depended upon
+    g_capture_streams[st];
+    Member& m = g_capture_streams[ev_stream];
+    if (st != ev_stream && it->second.work > m.joined) m.joined = it->second.work;
+    return cudaSuccess;
+  }
+  if (captured(st)) {
+    err("a capturing stream waits on an event recorded outside the capture (cudaErrorStreamCaptureIsolation)");
+    return cudaErrorStreamCaptureIsolation;
   }
   return cudaSuccess;
 }
@@ -428,12 +475,13 @@ cudaError_t cudaEventCreate(cudaEvent_t* e) {
 }
 cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { return cudaEventCreate(e); }
 cudaError_t cudaEventDestroy(cudaEvent_t) { return cudaSuccess; }
-cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t) {
+cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t st) {
   LOCK;
   if (e == nullptr) {
     err("cudaEventRecord on a NULL event");
     return cudaErrorInvalidResourceHandle;
   }
+  g_event_state[e] = {captured(st) ? g_capturing : 0, st, captured(st) ? g_capture_streams[st].work : 0};
   return cudaSuccess;
 }
 cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
@@ -441,20 +489,28 @@ cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) {
   *ms = 0.f;
   return cudaSuccess;
 }
-cudaError_t cudaStreamBeginCapture(cudaStream_t, cudaStreamCaptureMode) {
+cudaError_t cudaStreamBeginCapture(cudaStream_t st, cudaStreamCaptureMode) {
   LOCK;
   if (g_capturing) {
     err("nested stream capture");
     return cudaErrorIllegalState;
   }
-  g_capturing = 1;
+  g_capturing = ++g_capture_seq;
+  g_capture_origin = st;
+  g_capture_streams.clear();
+  g_capture_streams[st];
   g_capture.clear();
   return cudaSuccess;
 }
-cudaError_t cudaStreamEndCapture(cudaStream_t, cudaGraph_t* g) {
+cudaError_t cudaStreamEndCapture(cudaStream_t st, cudaGraph_t* g) {
   LOCK;
   if (!g_capturing) return cudaErrorIllegalState;
+  if (st != g_capture_origin) err("cudaStreamEndCapture on a stream that did not begin the capture");
+  for (const auto& kv : g_capture_streams)
+    if (kv.first != g_capture_origin && kv.second.work > kv.second.joined)
+      err("the capture ends with work on a forked stream that was never joined (cudaErrorStreamCaptureUnjoined)");
   g_capturing = 0;
+  g_capture_streams.clear();
   const uintptr_t h = (g_next_handle += 16);
   g_graphs[h] = g_capture;
   *g = reinterpret_cast<cudaGraph_t>(h);
@@ -529,7 +585,7 @@ int ncclAllReduce(const void* s, void* d, size_t count, int dtype, int op, void*
   if (comm == nullptr) err("ncclAllReduce without a communicator");
   check_device_range(s, count * nccl_esize(dtype), "ncclAllReduce send");
   check_device_range(d, count * nccl_esize(dtype), "ncclAllReduce recv");
-  logf("allreduce count=%zu dtype=%d op=%d stream=%p", count, dtype, op, static_cast<void*>(stream));
+  logw(stream, "allreduce count=%zu dtype=%d op=%d stream=%p", count, dtype, op, static_cast<void*>(stream));
   return 0;
 }
 int ncclBroadcast(const void* s, void* d, size_t count, int dtype, int root, void* comm, cudaStream_t stream) {
@@ -537,7 +593,7 @@ int ncclBroadcast(const void* s, void* d, size_t count, int dtype, int root, voi
   if (comm == nullptr) err("ncclBroadcast without a communicator");
   check_device_range(d, count * nccl_esize(dtype), "ncclBroadcast recv");
   (void)s;
-  logf("broadcast count=%zu dtype=%d root=%d stream=%p", count, dtype, root, static_cast<void*>(stream));
+  logw(stream, "broadcast count=%zu dtype=%d root=%d stream=%p", count, dtype, root, static_cast<void*>(stream));
   return 0;
 }
 int ncclGroupStart() { return 0; }
