@@ -206,3 +206,45 @@ def test_the_fake_runtime_does_catch_a_bad_descriptor(dry_build):
     assert enc(tm_aligned, BF16, 2, C.c_void_p(p.value + 8), good, strides, box, ones, 0, SW128, 2, 0) != 0   # misaligned
     assert fake.fake_error_count() == 2
     assert fake.cudaFree(p) == 0
+
+
+def test_the_fake_runtime_does_catch_capture_mistakes(dry_build):
+    """Unjoined forked work, waiting on an event from outside the capture, and waiting on a never-recorded event."""
+    import ctypes as C
+
+    fake = C.CDLL(os.path.join(DRY, "libfakecudart.so"))
+    fake.fake_reset()
+    a, b = C.c_void_p(), C.c_void_p()
+    e_in, e_out, e_never, g = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+    p = C.c_void_p()
+    for s in (a, b):
+        assert fake.cudaStreamCreateWithFlags(C.byref(s), 1) == 0
+    for e in (e_in, e_out, e_never):
+        assert fake.cudaEventCreate(C.byref(e)) == 0
+    assert fake.cudaMalloc(C.byref(p), C.c_size_t(4096)) == 0
+    assert fake.cudaEventRecord(e_out, b) == 0                               # recorded before the capture
+    assert fake.cudaStreamBeginCapture(a, 2) == 0
+    assert fake.cudaStreamWaitEvent(a, e_out, 0) != 0                        # isolation
+    assert fake.cudaStreamWaitEvent(a, e_never, 0) == 0                      # legal, but orders nothing: reported
+    assert fake.cudaEventRecord(e_in, a) == 0
+    assert fake.cudaStreamWaitEvent(b, e_in, 0) == 0                         # fork
+    assert fake.cudaMemsetAsync(p, 0, C.c_size_t(4096), b) == 0              # captured work on the forked stream ...
+    assert fake.cudaStreamEndCapture(a, C.byref(g)) == 0                     # ... never joined
+    assert fake.fake_error_count() == 3
+    msgs = []
+    buf = C.create_string_buffer(512)
+    for i in range(3):
+        fake.fake_error_line(i, buf, 512)
+        msgs.append(buf.value.decode())
+    assert "Isolation" in msgs[0] and "never recorded" in msgs[1] and "Unjoined" in msgs[2]
+    # the same with a join is clean
+    fake.fake_reset()
+    assert fake.cudaStreamBeginCapture(a, 2) == 0
+    assert fake.cudaEventRecord(e_in, a) == 0
+    assert fake.cudaStreamWaitEvent(b, e_in, 0) == 0
+    assert fake.cudaMemsetAsync(p, 0, C.c_size_t(4096), b) == 0
+    assert fake.cudaEventRecord(e_out, b) == 0
+    assert fake.cudaStreamWaitEvent(a, e_out, 0) == 0
+    assert fake.cudaStreamEndCapture(a, C.byref(g)) == 0
+    assert fake.fake_error_count() == 0 and fake.fake_last_graph_size() == 1
+    assert fake.cudaFree(p) == 0
