@@ -85,6 +85,49 @@ def scenario(name):
         out = snapshot()
         out["steps"] = st["steps"]
         out["timings"] = ctx.timings()
+    elif name == "full_size":  # BASELINE.json's C3 and C4 shapes: descriptors, bounds and kernel choice at full size
+        ctx = Context(device=0, seed=1)
+        for key, V, H, B, k, pcd in (("c3", 4096, 4096, 4096, 10, False), ("c4", 16384, 8192, 1024, 1, True)):
+            m = Machine(ctx, V, H, L.MODE_VISIBLE_BERNOULLI, L.COMPUTE_BF16, seed=3)
+            X = np.zeros((2 * B, V), np.uint8)
+            ds = Dataset.from_array(ctx, X, L.COMPUTE_BF16)
+            if pcd:
+                m.set_chains(np.zeros((B, V), np.uint8))
+            fake.fake_reset()
+            m.fit_epoch(ds, B, Machine.hparams(lr=1e-3, k=k, persistent=pcd, normalize=True), want_stats=False)
+            out[key] = snapshot()
+            ds.close()
+            m.close()
+    elif name == "python_surface":  # the reference-facing classes end to end (values are meaningless in a dry run)
+        from keras_unsupervised_b200.ebm import DBN, RBM, MODE_VISIBLE_BERNOULLI
+
+        ctx = Context(device=0, seed=1)
+        X = data(600, 784)
+        hps = {"batch_size": 128, "epochs": 2, "lr": 1e-3, "dtype": "bf16"}
+        dbn = DBN()
+        for i, h in enumerate((500, 500, 2000)):
+            dbn.add_stack(RBM(dict(hps), h, name="rbm%d" % i, mode=MODE_VISIBLE_BERNOULLI, context=ctx))
+        fake.fake_reset()
+        dbn.fit(X, verbose=0)
+        out["fit"] = snapshot()
+        fake.fake_reset()
+        H = dbn.transform(X[:64])
+        V2 = dbn.inv_transform(H)
+        out["shapes"] = [list(H.shape), list(V2.shape)]
+        out["transform"] = snapshot()
+        fake.fake_reset()
+        dbn.fine_tune(X[:256], epochs=1, lr=1e-3, k=1)
+        out["fine_tune"] = snapshot()
+        fake.fake_reset()
+        g = dbn.generate(16, gibbs_steps=3)
+        out["generate_shape"] = list(g.shape)
+        out["generate"] = snapshot()
+        one = RBM({"batch_size": 128, "epochs": 1, "lr": 1e-3}, 96, name="one", mode=MODE_VISIBLE_BERNOULLI, context=ctx)
+        fake.fake_reset()
+        one.fit(data(1000, 200), verbose=0)                                  # float32-grade, one epoch: streamed
+        fe = one.cal_free_energy(data(50, 200))[0]
+        out["fe_shape"] = list(np.asarray(fe).shape)
+        out["one_epoch_f32"] = snapshot()
     elif name == "split":  # KUCD_SPLIT=2 KUCD_CHAIN=0: two Gibbs chains on two streams, forked and joined inside the capture
         ctx = Context(device=0, seed=1)
         m = machine(ctx, 784, 500)

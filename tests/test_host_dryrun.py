@@ -248,3 +248,44 @@ def test_the_fake_runtime_does_catch_capture_mistakes(dry_build):
     assert fake.cudaStreamEndCapture(a, C.byref(g)) == 0
     assert fake.fake_error_count() == 0 and fake.fake_last_graph_size() == 1
     assert fake.cudaFree(p) == 0
+
+
+def test_full_size_shapes(dry_build):
+    """BASELINE.json's C3 (4096 -> 4096, batch 4096, CD-10) and C4 (PCD 16384 -> 8192, 1024 rows per GPU): every
+    descriptor and pointer stays inside its buffer at full size, and the step is the whole-chain kernel on CTA pairs, the
+    dW contraction on CTA pairs and the update."""
+    d = run("full_size")
+    c3, c4 = clean(d["c3"]), clean(d["c4"])
+    chain, dw = "chain_kernel<256,2,0>", "gemm_bf16_kernel<256,1,1,0,0,2>"
+    assert c3["graph"] == ["memset", "colsum_kernel", "memset", chain, dw, "update_w_kernel<0>", "advance_dyn_kernel"]
+    assert c4["graph"] == ["memset", "colsum_kernel", "memset", chain, dw, "copy_rows_kernel", "update_w_kernel<0>",
+                           "advance_dyn_kernel"]
+    lines = [x for x in c3["graph_raw"] if "chain_kernel" in x]
+    assert "grid=148,1,1" in lines[0] and "block=320,1,1" in lines[0] and "cluster=2" in lines[0]   # 74 CTA pairs
+    # C4's share with the update in slabs behind the contraction (KUCD_AR_SLABS on one rank): 4 slabs of 4096 rows
+    s = clean(run("full_size", KUCD_AR_SLABS=4)["c4"])
+    assert s["graph"] == ["memset", "colsum_kernel", "memset", chain] + [dw] * 4 + ["copy_rows_kernel"] + \
+        ["update_w_kernel<0>"] * 4 + ["advance_dyn_kernel"]
+    upd = [x for x in s["graph_raw"] if "update_w_kernel" in x]
+    con = [x for x in s["graph_raw"] if "gemm_bf16_kernel" in x]
+    assert len({x.split("stream=")[1].split()[0] for x in upd}) == 1 and len({x.split("stream=")[1].split()[0] for x in con}) == 1
+    assert upd[0].split("stream=")[1].split()[0] != con[0].split("stream=")[1].split()[0]        # updates on the 2nd stream
+
+
+def test_reference_facing_classes_end_to_end(dry_build):
+    """DBN.fit / transform / inv_transform / fine_tune / generate and a one-epoch float32 RBM.fit + free energy through the
+    real ctypes layer and the real host code (values are meaningless: no kernel runs)."""
+    d = run("python_surface")
+    for key in ("fit", "transform", "fine_tune", "generate", "one_epoch_f32"):
+        clean(d[key])
+    assert d["shapes"] == [[64, 2000], [64, 784]] and d["generate_shape"] == [16, 784] and d["fe_shape"] == [50]
+    fit = Counter(d["fit"]["kernels"])
+    assert fit["graph_launch"] == 3 * 2 * 5                 # 3 layers x 2 epochs x ceil(600 / 128) replayed steps
+    assert fit["gemm_bf16_kernel<64,0,1,1,0,1>"] == 2       # the two inter-layer transforms of the whole data set (dbn.py:55)
+    ft = Counter(d["fine_tune"]["kernels"])                 # 256 rows = 2 minibatches, 3 layers
+    assert ft[CHAIN_SMALL] == 2                             # CD in the top RBM
+    assert ft[DW] == 8 and ft["colsum_kernel"] == 8         # 2 lower layers x (generative + recognition) x 2 minibatches
+    assert ft["gemm_bf16_kernel<64,0,1,2,0,1>"] == 4 and ft["gemm_bf16_kernel<64,0,0,2,0,1>"] == 4   # their predictions
+    assert ft["update_w_kernel<0>"] == 10
+    f32 = Counter(d["one_epoch_f32"]["kernels"])            # 1000 rows, batch 128: 8 streamed float32-grade steps
+    assert f32["update_w_kernel<0>"] == 8 and f32["gemm_bf16_kernel<128,1,1,0,4,1>"] == 8
