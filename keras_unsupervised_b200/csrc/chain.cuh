@@ -24,69 +24,7 @@
 
 namespace kucd {
 
-constexpr int kMaxChainStages = 66;  // 2k+2 projections with k <= 31, + the dW contraction
-constexpr int kMaxChainKinds = 9;
-constexpr int kChainMaps = 12;
 constexpr int kChainBN = 256;
-
-// The few distinct projections a chain is made of (member names shared with GemmParams: epilogue_chunk reads them).
-struct ChainKind {
-  const float* bias;
-  __nv_bfloat16* out_bf16;
-  __nv_bfloat16* out_mid;
-  __nv_bfloat16* out_lo;
-  int64_t ld_bf16;
-  float* out_f32;
-  int64_t ld_f32;
-  const float* u_inject;
-  int64_t ld_u;
-  float* colsum;
-  float colsum_sign;
-  int32_t epi;  // kEpiSample / kEpiProb / kEpiRaw; with GAUSS: kEpiReluSample / kEpiGaussian / kEpiProb / kEpiRaw
-  float* rowsum;
-  int32_t M, N;
-  uint64_t seed;
-  int32_t kblocks;
-  int32_t b_mn;   // 1: W read as (K,N) (v.W), 0: W read as (N,K) (h.W^T)
-  int32_t map_a, map_b;
-  int32_t a_dyn;  // A is the resident data set: rows offset by dyn->row_off
-  int32_t num_n;
-  int32_t num_m;       // row blocks of 256 output rows
-  int32_t batch_rows;  // 1: output rows are minibatch rows (valid-row masking, global-row draws)
-  // the dW contraction (rbm.py:125-126) as the chain's last stage: both operands MN-major (contraction over the
-  // minibatch rows), two K-segments - v0^T h0, then vk^T hk with the negate-A bit
-  int32_t a_mn;
-  int32_t nseg;
-  int32_t map_a2, map_b2;
-  int32_t dep2;        // stage that must be complete in ALL its row blocks before segment 1 is loaded
-  int32_t pad;
-};
-
-struct ChainStageRef {
-  int16_t kind;
-  int16_t dep;     // stage whose row block must be complete before this stage reads it (-1: none); for an
-                   // a_mn stage: ALL row blocks of that stage, before segment 0
-  uint32_t phase;  // Philox draw id offset inside the step
-};
-
-struct alignas(64) ChainParams {
-  CUtensorMap maps[kChainMaps];
-  ChainKind kinds[kMaxChainKinds];
-  ChainStageRef stages[kMaxChainStages];
-  int32_t num_stages;
-  int32_t M;        // minibatch rows (buffer capacity)
-  int32_t m_valid;  // rows that carry data
-  int32_t total_tiles;
-  uint32_t* done;   // [num_stages][done_stride] tiles-finished counters, zeroed before the launch
-  int32_t done_stride;
-  int32_t num_m_batch;  // row blocks of the minibatch
-  uint64_t draw;
-  uint64_t draw_stride;
-  int64_t row0;
-  const StepDyn* dyn;
-  int32_t dyn_rank;
-  int32_t pad;
-};
 
 __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
   uint32_t v;

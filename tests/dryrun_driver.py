@@ -52,7 +52,7 @@ def snapshot():
             "graph": [_kernel(x) for x in _lines(fake.fake_last_graph_size, fake.fake_last_graph_line)],
             "graph_raw": _lines(fake.fake_last_graph_size, fake.fake_last_graph_line),
             "errors": _lines(fake.fake_error_count, fake.fake_error_line),
-            "mallocs": fake.fake_counter(0), "frees": fake.fake_counter(1), "live_bytes": fake.fake_counter(2),
+            "decoded": fake.fake_counter(5), "mallocs": fake.fake_counter(0), "frees": fake.fake_counter(1), "live_bytes": fake.fake_counter(2),
             "peak_bytes": fake.fake_counter(3)}
 
 

@@ -56,6 +56,32 @@ def clean(snap):
     return snap
 
 
+def test_every_contraction_launch_is_decoded_and_checked(dry_build):
+    """The fake reads GemmParams / ChainParams (csrc/params.h) out of each launch and checks what the epilogue may touch:
+    bias (a whole 32-column chunk is read), state / probability planes, raw tiles or owner slots, column / row sums,
+    injected draws, the chain's completion counters.  Live: the counter moves - and a block with nothing behind its
+    pointers is refused."""
+    d = run("cd_step")
+    assert clean(d["bf16"])["decoded"] == 1 and clean(d["f32"])["decoded"] == 6    # one chain launch; 5 projections + dW
+    import ctypes as C
+
+    fake = C.CDLL(os.path.join(DRY, "libfakecudart.so"))
+    fake.fake_reset()
+    name = b"_ZN4kucd16gemm_bf16_kernelILi64ELb0ELb1ELi3ELi0ELi1EEEvNS_10GemmParamsE"      # free-energy epilogue
+    stub = C.create_string_buffer(8)                                        # any unique address stands for the host stub
+    fake.__cudaRegisterFunction(None, stub, None, name, -1, None, None, None, None, None)
+    blob = (C.c_char * 4096)()
+    C.memmove(C.addressof(blob) + 2560, (C.c_int32 * 6)(1, 0, 64, 64, 1, 0), 24)     # num_seg, neg_mask, M, N, kblocks, pad
+    args = (C.c_void_p * 1)(C.addressof(blob))
+
+    class Dim3(C.Structure):
+        _fields_ = [("x", C.c_uint), ("y", C.c_uint), ("z", C.c_uint)]
+
+    fake.cudaLaunchKernel.argtypes = [C.c_void_p, Dim3, Dim3, C.c_void_p, C.c_size_t, C.c_void_p]
+    assert fake.cudaLaunchKernel(C.addressof(stub), Dim3(1, 1, 1), Dim3(320, 1, 1), args, 1024, None) == 0
+    assert fake.fake_counter(5) == 1 and fake.fake_error_count() == 2      # bias and rowsum point nowhere
+
+
 CHAIN_SMALL = "chain_kernel<64,1,0>"
 DW = "gemm_bf16_kernel<64,1,1,0,0,1>"          # A MN-major, B MN-major, raw epilogue: the dW contraction
 DW16 = "gemm_bf16_kernel<128,1,1,6,0,1>"       # ... with the bf16 push epilogue (BN >= 128)

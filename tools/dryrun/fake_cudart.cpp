@@ -18,11 +18,14 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include "../../keras_unsupervised_b200/csrc/params.h"  // GemmParams / ChainParams: plain data, no device code
+
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <map>
 #include <mutex>
 #include <string>
@@ -36,6 +39,7 @@ std::map<const void*, std::string> g_funcs;  // host stub -> mangled kernel name
 std::vector<std::string> g_log;
 std::vector<std::string> g_errors;
 size_t g_malloc_calls = 0, g_free_calls = 0, g_live_bytes = 0, g_peak_bytes = 0;
+size_t g_decoded_launches = 0;  // contraction launches whose parameter block was decoded and checked
 int g_device = 0;
 // Stream capture, modelled on the rules the engine relies on: a capture starts on one stream; another stream joins it by
 // waiting on an event recorded inside the capture (fork) and must hand its work back through an event the capture waits
@@ -128,10 +132,113 @@ const char* kname(const void* func) {
   return it == g_funcs.end() ? "?" : it->second.c_str();
 }
 
-// kernels whose first arguments are plain (pointer, ..., length) - checked against the allocation table
+// template arguments of a mangled kernel name, in order: ..ILi256ELb1ELb1ELi6ELi0ELi2EEEv.. -> {256, 1, 1, 6, 0, 2}
+std::vector<long> template_args(const std::string& name) {
+  std::vector<long> out;
+  const size_t end = name.find("EEv");
+  for (size_t i = name.find('I'); i != std::string::npos && i + 2 < name.size() && (end == std::string::npos || i < end); ++i) {
+    if (name[i] == 'L' && (name[i + 1] == 'i' || name[i + 1] == 'b')) {
+      size_t j = i + 2;
+      long v = 0;
+      while (j < name.size() && name[j] >= '0' && name[j] <= '9') v = 10 * v + (name[j++] - '0');
+      if (j < name.size() && name[j] == 'E' && j > i + 2) out.push_back(v);
+      i = j;
+    }
+  }
+  return out;
+}
+
+long round_up_l(long x, long m) { return (x + m - 1) / m * m; }
+
+// What one contraction's epilogue may touch, from the fields the kernel reads (gemm.cuh: epilogue_chunk / push16_chunk).
+// P is GemmParams or a ChainKind (same member names).
+template <typename P>
+void check_epilogue(const char* kernel, const P& p, int epi, long M, long N, const float* const* push_base, long push_rows) {
+  char what[160];
+  auto W = [&](const char* field) {
+    snprintf(what, sizeof what, "%s: %s", kernel, field);
+    return what;
+  };
+  if (M <= 0 || N <= 0) return;
+  const long n8 = round_up_l(N, 8), n4 = round_up_l(N, 4);
+  if (epi != kucd::kEpiRaw && epi != kucd::kEpiRawPush16)
+    check_device_range(p.bias, static_cast<size_t>(round_up_l(N, 32)) * 4, W("bias (read a whole 32-column chunk at a time)"));
+  if (epi == kucd::kEpiSample || epi == kucd::kEpiReluSample || epi == kucd::kEpiProb || epi == kucd::kEpiGaussian) {
+    const size_t ext = (static_cast<size_t>(M - 1) * p.ld_bf16 + n8) * 2;
+    check_device_range(p.out_bf16, ext, W("out_bf16"));
+    if (p.out_mid != nullptr) check_device_range(p.out_mid, ext, W("out_mid"));
+    if (p.out_lo != nullptr) check_device_range(p.out_lo, ext, W("out_lo"));
+    if (p.ld_bf16 % 8 != 0 || p.ld_bf16 < n8) err("%s: ld_bf16 = %lld for %ld columns", kernel, (long long)p.ld_bf16, N);
+    if (p.out_f32 != nullptr)
+      check_device_range(p.out_f32, (static_cast<size_t>(M - 1) * p.ld_f32 + n4) * 4, W("out_f32 (probabilities)"));
+    if (p.u_inject != nullptr)
+      check_device_range(p.u_inject, (static_cast<size_t>(M - 1) * p.ld_u + N) * 4, W("u_inject"));
+  }
+  if (epi == kucd::kEpiFreeEnergy) check_device_range(p.rowsum, static_cast<size_t>(M) * 4, W("rowsum"));
+  if (epi == kucd::kEpiRaw || epi == kucd::kEpiRawPush16) {
+    const size_t esz = epi == kucd::kEpiRaw ? 4 : 2;
+    const long ncols = epi == kucd::kEpiRaw ? n4 : n8;
+    if (p.ld_f32 % (epi == kucd::kEpiRaw ? 4 : 8) != 0 || p.ld_f32 < ncols)
+      err("%s: output pitch %lld for %ld columns", kernel, (long long)p.ld_f32, N);
+    if (push_rows > 0 && push_base != nullptr) {
+      const long owners = (M + push_rows - 1) / push_rows;
+      if (owners > 8) err("%s: %ld owners of %ld rows for %ld rows", kernel, owners, push_rows, M);
+      for (long o = 0; o < owners && o < 8; ++o) {
+        const long rows = std::min(push_rows, M - o * push_rows);
+        check_device_range(push_base[o], (static_cast<size_t>(rows - 1) * p.ld_f32 + ncols) * esz, W("owner slot (push_base)"));
+      }
+    } else if (epi == kucd::kEpiRawPush16) {
+      err("%s: the bf16 push epilogue without a destination", kernel);
+    } else {
+      check_device_range(p.out_f32, (static_cast<size_t>(M - 1) * p.ld_f32 + ncols) * 4, W("out_f32 (raw tile)"));
+    }
+  }
+  if (p.colsum != nullptr) check_device_range(p.colsum, static_cast<size_t>(N) * 4, W("colsum"));
+}
+
+// kernels whose arguments are decoded and checked against the allocation table
 void check_kernel_args(const std::string& name, void** args) {
   if (args == nullptr) return;
   auto ptr = [&](int i) { return *reinterpret_cast<void**>(args[i]); };
+  if (name.find("gemm_bf16_kernel") != std::string::npos) {
+    const std::vector<long> t = template_args(name);  // BN, A_MN, B_MN, EPI, CH, CG
+    const kucd::GemmParams& p = *reinterpret_cast<const kucd::GemmParams*>(args[0]);
+    if (t.size() != 6) err("gemm: could not read the template arguments of %s", name.c_str());
+    if (t.size() == 6) {
+      g_decoded_launches++;
+      if (p.num_seg < 1 || p.num_seg > kucd::kMaxSeg || p.kblocks < 1) err("gemm: %d segments of %d k-blocks", p.num_seg, p.kblocks);
+      if (t[3] == kucd::kEpiRawPush16 && t[0] < 128) err("gemm: the bf16 push epilogue needs BN >= 128");
+      check_epilogue("gemm_bf16_kernel", p, static_cast<int>(t[3]), p.M, p.N, p.push_base, p.push_rows);
+      if (p.dyn != nullptr) check_device_range(p.dyn, sizeof(kucd::StepDyn), "gemm_bf16_kernel: dyn");
+    }
+    return;
+  }
+  if (name.find("chain_kernel") != std::string::npos) {
+    const kucd::ChainParams& p = *reinterpret_cast<const kucd::ChainParams*>(args[0]);
+    if (p.num_stages < 1 || p.num_stages > kucd::kMaxChainStages) {
+      err("chain: %d stages", p.num_stages);
+      return;
+    }
+    g_decoded_launches++;
+    check_device_range(p.done, static_cast<size_t>(p.num_stages) * p.done_stride * 4, "chain_kernel: completion counters");
+    if (p.dyn != nullptr) check_device_range(p.dyn, sizeof(kucd::StepDyn), "chain_kernel: dyn");
+    long tiles = 0;
+    for (int s2 = 0; s2 < p.num_stages; ++s2) {
+      const int kd = p.stages[s2].kind;
+      if (kd < 0 || kd >= kucd::kMaxChainKinds) {
+        err("chain: stage %d has kind %d", s2, kd);
+        return;
+      }
+      const kucd::ChainKind& q = p.kinds[kd];
+      if (p.stages[s2].dep >= s2) err("chain: stage %d waits for stage %d (must be an earlier one)", s2, p.stages[s2].dep);
+      if (q.nseg == 2 && q.dep2 >= s2) err("chain: stage %d's second segment waits for stage %d", s2, q.dep2);
+      if (q.num_m > p.done_stride) err("chain: stage %d has %d row blocks, the counter stride is %d", s2, q.num_m, p.done_stride);
+      tiles += static_cast<long>(q.num_m) * q.num_n;
+      check_epilogue("chain_kernel", q, q.epi, q.M, q.N, nullptr, 0);
+    }
+    if (tiles != p.total_tiles) err("chain: the stages have %ld tiles, total_tiles = %d", tiles, p.total_tiles);
+    return;
+  }
   if (name.find("update_w_kernel") != std::string::npos) {
     // (W, dW, mom, hi, mid, lo, n4, ...): n4 float4 of W / dW (uint2 when dW is bf16), n4 uint2 of each plane
     const int64_t n4 = *reinterpret_cast<int64_t*>(args[6]);
@@ -225,6 +332,7 @@ void fake_reset() {
   g_log.clear();
   g_errors.clear();
   g_malloc_calls = g_free_calls = 0;
+  g_decoded_launches = 0;
   g_peak_bytes = g_live_bytes;
 }
 int fake_log_size() {
@@ -247,13 +355,15 @@ int fake_error_line(int i, char* buf, int n) {
   snprintf(buf, n, "%s", g_errors[i].c_str());
   return 0;
 }
-long long fake_counter(int which) {  // 0 cudaMalloc calls, 1 cudaFree calls, 2 live bytes, 3 peak bytes, 4 live allocations
+long long fake_counter(int which) {  // 0 cudaMalloc calls, 1 cudaFree calls, 2 live bytes, 3 peak bytes, 4 live allocations,
+                                     // 5 contraction launches whose parameters were decoded
   LOCK;
   switch (which) {
     case 0: return static_cast<long long>(g_malloc_calls);
     case 1: return static_cast<long long>(g_free_calls);
     case 2: return static_cast<long long>(g_live_bytes);
     case 3: return static_cast<long long>(g_peak_bytes);
+    case 5: return static_cast<long long>(g_decoded_launches);
     default: return static_cast<long long>(g_allocs.size());
   }
 }
