@@ -128,6 +128,43 @@ def scenario(name):
         fe = one.cal_free_energy(data(50, 200))[0]
         out["fe_shape"] = list(np.asarray(fe).shape)
         out["one_epoch_f32"] = snapshot()
+    elif name == "data_formats":  # packed bits, uint8, shuffle, Gaussian visibles, PCD, injected draws, score
+        from keras_unsupervised_b200.data import PackedBits
+
+        ctx = Context(device=0, seed=1)
+        V, H = 333, 130
+        X = data(500, V)
+        P = PackedBits(np.packbits(X.astype(np.uint8), axis=1, bitorder="little"), V)
+        m = machine(ctx, V, H)
+        fake.fake_reset()
+        m.fit_host(P, 128, Machine.hparams(lr=1e-3, k=1))
+        m.fit_host(X.astype(np.uint8), 128, Machine.hparams(lr=1e-3, k=1))
+        ds = Dataset.from_array(ctx, P, L.COMPUTE_BF16)
+        sh = ds.shuffled(seed=5, epoch=0)
+        sh = ds.shuffled(seed=5, epoch=1, into=sh)
+        back = sh.packed()
+        dense = ds.numpy()
+        out["shapes"] = [list(back.data.shape), list(dense.shape)]
+        h = m.transform(P, out_dtype="bits")
+        out["bits_out"] = [list(h.data.shape), h.n_cols]
+        out["packed"] = snapshot()
+        g = machine(ctx, V, H, mode=L.MODE_VISIBLE_GAUSSIAN)
+        fake.fake_reset()
+        g.cd_step(np.random.default_rng(2).standard_normal((200, V)).astype(np.float32), Machine.hparams(lr=1e-3, k=2))
+        g32 = machine(ctx, V, H, compute=L.COMPUTE_F32X3, mode=L.MODE_VISIBLE_GAUSSIAN)
+        g32.cd_step(np.random.default_rng(2).standard_normal((200, V)).astype(np.float32), Machine.hparams(lr=1e-3, k=1))
+        out["gaussian"] = snapshot()
+        fake.fake_reset()
+        m.set_chains(data(128, V, seed=9))
+        m.cd_step(X[:128], Machine.hparams(lr=1e-3, k=1, persistent=True))
+        rng = np.random.default_rng(4)
+        f = machine(ctx, V, H, compute=L.COMPUTE_F32X3)
+        u_h = [rng.random((96, H)).astype(np.float32)]
+        u_v = [None, rng.random((96, V)).astype(np.float32)]
+        st = f.cd_step(X[:96], Machine.hparams(lr=1e-3, k=1, want_stats=True), u_h=u_h, u_v=u_v)
+        f.last_stats(96)
+        f.score(X[:96])
+        out["pcd_inject_score"] = snapshot()
     elif name == "split":  # KUCD_SPLIT=2 KUCD_CHAIN=0: two Gibbs chains on two streams, forked and joined inside the capture
         ctx = Context(device=0, seed=1)
         m = machine(ctx, 784, 500)

@@ -315,3 +315,20 @@ def test_reference_facing_classes_end_to_end(dry_build):
     assert ft["update_w_kernel<0>"] == 10
     f32 = Counter(d["one_epoch_f32"]["kernels"])            # 1000 rows, batch 128: 8 streamed float32-grade steps
     assert f32["update_w_kernel<0>"] == 8 and f32["gemm_bf16_kernel<128,1,1,0,4,1>"] == 8
+
+
+def test_data_formats_gaussian_pcd_injection_score(dry_build):
+    """The formats either side of the path (packed bits in and out, uint8, the epoch shuffle into a new and into an existing
+    data set), Gaussian visibles in both compute modes, persistent chains, injected draws, statistics and the score chain:
+    every ingest / export / permute / copy launch has its source and destination extents checked by the fake."""
+    d = run("data_formats")
+    p = Counter(clean(d["packed"])["kernels"])
+    assert d["shapes"] == [[500, 42], [500, 333]] and d["bits_out"] == [[500, 17], 130]
+    assert p["ingest_bits_kernel"] == 4 + 1 + 1             # 4 streamed minibatches, the data set, the transform input
+    assert p["ingest_kernel"] == 4 and p["permute_rows_kernel"] == 2 and p["export_bits_kernel"] == 2
+    assert p[CHAIN_SMALL] == 8 and p["update_w_kernel<0>"] == 8
+    g = Counter(clean(d["gaussian"])["kernels"])
+    assert g["chain_kernel<64,1,1>"] == 1                   # the Gaussian instantiation of the small chain kernel
+    assert g["gemm_bf16_kernel<128,0,1,4,4,1>"] == 1 and g["gemm_bf16_kernel<128,0,0,5,4,1>"] == 1   # relu / normal epilogues
+    s = Counter(clean(d["pcd_inject_score"])["kernels"])
+    assert s["copy_rows_kernel"] == 1 and s["score_kernel"] == 2 and s["free_energy_finish_kernel"] == 4

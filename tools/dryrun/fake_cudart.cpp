@@ -239,6 +239,127 @@ void check_kernel_args(const std::string& name, void** args) {
     if (tiles != p.total_tiles) err("chain: the stages have %ld tiles, total_tiles = %d", tiles, p.total_tiles);
     return;
   }
+  auto i64 = [&](int i) { return *reinterpret_cast<int64_t*>(args[i]); };
+  auto i32 = [&](int i) { return *reinterpret_cast<int32_t*>(args[i]); };
+  auto planes = [&](int first, size_t bytes, const char* what) {  // hi must exist, mid / lo are optional
+    check_device_range(ptr(first), bytes, what);
+    if (ptr(first + 1) != nullptr) check_device_range(ptr(first + 1), bytes, what);
+    if (ptr(first + 2) != nullptr) check_device_range(ptr(first + 2), bytes, what);
+  };
+  if (name.find("ingest_kernel") != std::string::npos) {
+    // (src, src_ld, rows, cols, hi, mid, lo, ld, nparts, inexact): whole padded rows of the planes are written
+    const size_t esz = name.find("ingest_kernelIfE") != std::string::npos ? 4 : (name.find("ingest_kernelIhE") != std::string::npos ? 1 : 2);
+    const int64_t src_ld = i64(1), rows = i64(2), cols = i64(3), ld = i64(7);
+    if (rows > 0) {
+      check_range(ptr(0), (static_cast<size_t>(rows - 1) * src_ld + cols) * esz, "ingest_kernel source");
+      const int np = *reinterpret_cast<int*>(args[8]);
+      for (int k2 = 0; k2 < np && k2 < 3; ++k2)
+        check_device_range(ptr(4 + k2), static_cast<size_t>(rows) * ld * 2, "ingest_kernel plane");
+      if (ld % 8 != 0 || ld < cols) err("ingest_kernel: ld = %lld for %lld columns", (long long)ld, (long long)cols);
+    }
+    return;
+  }
+  if (name.find("ingest_bits_kernel") != std::string::npos) {  // (src, src_pitch, rows, cols, hi, mid, lo, ld, nparts)
+    const int64_t pitch = i64(1), rows = i64(2), cols = i64(3), ld = i64(7);
+    if (rows > 0) {
+      check_range(ptr(0), static_cast<size_t>(rows - 1) * pitch + (cols + 7) / 8, "ingest_bits_kernel source");
+      const int np = *reinterpret_cast<int*>(args[8]);
+      for (int k2 = 0; k2 < np && k2 < 3; ++k2)
+        check_device_range(ptr(4 + k2), static_cast<size_t>(rows) * ld * 2, "ingest_bits_kernel plane");
+    }
+    return;
+  }
+  if (name.find("export_bits_kernel") != std::string::npos) {  // (hi, ld, rows, cols, dst, dst_pitch)
+    const int64_t ld = i64(1), rows = i64(2), cols = i64(3), pitch = i64(5);
+    if (rows > 0) {
+      check_device_range(ptr(0), (static_cast<size_t>(rows - 1) * ld + cols) * 2, "export_bits_kernel plane");
+      check_range(ptr(4), static_cast<size_t>(rows - 1) * pitch + (cols + 7) / 8, "export_bits_kernel destination");
+    }
+    return;
+  }
+  if (name.find("export_kernel") != std::string::npos) {  // (hi, mid, lo, ld, rows, cols, dst, dst_ld)
+    const size_t esz = name.find("export_kernelIfE") != std::string::npos ? 4 : (name.find("export_kernelIhE") != std::string::npos ? 1 : 2);
+    const int64_t ld = i64(3), rows = i64(4), cols = i64(5), dst_ld = i64(7);
+    if (rows > 0) {
+      planes(0, (static_cast<size_t>(rows - 1) * ld + cols) * 2, "export_kernel plane");
+      check_range(ptr(6), (static_cast<size_t>(rows - 1) * dst_ld + cols) * esz, "export_kernel destination");
+    }
+    return;
+  }
+  if (name.find("copy_rows_kernel") != std::string::npos) {  // (src, dst, ld, rows, dyn)
+    const int64_t ld = i64(2);
+    const int32_t rows = i32(3);
+    if (rows > 0) {
+      check_device_range(ptr(0), static_cast<size_t>(rows) * ld * 2, "copy_rows_kernel source");
+      check_device_range(ptr(1), static_cast<size_t>(rows) * ld * 2, "copy_rows_kernel destination");
+    }
+    return;
+  }
+  if (name.find("permute_rows_kernel") != std::string::npos) {  // (s0, s1, s2, d0, d1, d2, ld, rows, key)
+    const int64_t ld = i64(6), rows = i64(7);
+    if (rows > 0) {
+      planes(0, static_cast<size_t>(rows) * ld * 2, "permute_rows_kernel source");
+      planes(3, static_cast<size_t>(rows) * ld * 2, "permute_rows_kernel destination");
+      if ((ptr(1) == nullptr) != (ptr(4) == nullptr)) err("permute_rows_kernel: source and destination differ in planes");
+    }
+    return;
+  }
+  if (name.find("refresh_planes_kernel") != std::string::npos) {  // (W, hi, mid, lo, n4)
+    const int64_t n4 = i64(4);
+    check_device_range(ptr(0), static_cast<size_t>(n4) * 16, "refresh_planes_kernel W");
+    planes(1, static_cast<size_t>(n4) * 8, "refresh_planes_kernel plane");
+    return;
+  }
+  if (name.find("update_bias_kernel") != std::string::npos) {  // (x, d, mom, n, ...)
+    const int64_t n = i64(3);
+    check_device_range(ptr(0), static_cast<size_t>(n) * 4, "update_bias_kernel bias");
+    check_device_range(ptr(1), static_cast<size_t>(n) * 4, "update_bias_kernel statistic");
+    if (ptr(2) != nullptr) check_device_range(ptr(2), static_cast<size_t>(n) * 4, "update_bias_kernel momentum");
+    return;
+  }
+  if (name.find("colsum_store_kernel") != std::string::npos) {
+    // (hi, mid, lo, ld, rows, cols, cols_pad, dyn, out, zero, zero_len): with dyn the rows start at dyn->row_off (unknown here)
+    const int64_t ld = i64(3);
+    const int32_t rows = i32(4), cols = i32(5), cols_pad = i32(6);
+    if (ptr(7) == nullptr && rows > 0) planes(0, (static_cast<size_t>(rows - 1) * ld + cols) * 2, "colsum_store_kernel plane");
+    check_device_range(ptr(8), static_cast<size_t>(cols_pad) * 4, "colsum_store_kernel sums");
+    if (ptr(9) != nullptr) check_device_range(ptr(9), static_cast<size_t>(i32(10)) * 4, "colsum_store_kernel cleared block");
+    return;
+  }
+  if (name.find("colsum_kernel") != std::string::npos) {  // (hi, mid, lo, ld, row_off, rows, cols, dyn, sign, out)
+    const int64_t ld = i64(3), row_off = i64(4);
+    const int32_t rows = i32(5), cols = i32(6);
+    if (ptr(7) == nullptr && rows > 0)
+      planes(0, (static_cast<size_t>(row_off + rows - 1) * ld + cols) * 2, "colsum_kernel plane");
+    check_device_range(ptr(9), static_cast<size_t>(cols) * 4, "colsum_kernel sums");
+    return;
+  }
+  if (name.find("update_w_sharded_kernel") != std::string::npos) {
+    // (W, slots, slice_elems, n, mom, PeerSet, elem0, n4, ...): the owner's rows of W, its n slots, every rank's plane
+    struct PeerSetMirror {
+      float* dw_slot[8];
+      float* bias_slot[8];
+      uint32_t* flags[8];
+      void* wp[8];
+    };
+    const bool w16 = name.find("ILb1") != std::string::npos;
+    const int64_t slice = i64(2), elem0 = i64(6), n4 = i64(7);
+    const int n = *reinterpret_cast<int*>(args[3]);
+    const PeerSetMirror& ps = *reinterpret_cast<const PeerSetMirror*>(args[5]);
+    if (n4 > 0 && n >= 1 && n <= 8) {
+      check_device_range(static_cast<char*>(ptr(0)) + elem0 * 4, static_cast<size_t>(n4) * 16, "update_w_sharded_kernel W rows");
+      if (ptr(4) != nullptr)
+        check_device_range(static_cast<char*>(ptr(4)) + elem0 * 4, static_cast<size_t>(n4) * 16, "update_w_sharded_kernel momentum");
+      const size_t esz = w16 ? 2 : 4;
+      for (int j = 0; j < n; ++j) {
+        check_device_range(static_cast<char*>(ptr(1)) + static_cast<size_t>(j) * slice * esz, static_cast<size_t>(n4) * 4 * esz,
+                           "update_w_sharded_kernel slot");
+        check_device_range(static_cast<char*>(ps.wp[j]) + elem0 * 2, static_cast<size_t>(n4) * 8,
+                           "update_w_sharded_kernel operand plane of a rank");
+      }
+    }
+    return;
+  }
   if (name.find("update_w_kernel") != std::string::npos) {
     // (W, dW, mom, hi, mid, lo, n4, ...): n4 float4 of W / dW (uint2 when dW is bf16), n4 uint2 of each plane
     const int64_t n4 = *reinterpret_cast<int64_t*>(args[6]);
