@@ -165,6 +165,39 @@ def scenario(name):
         f.last_stats(96)
         f.score(X[:96])
         out["pcd_inject_score"] = snapshot()
+    elif name == "sweep":  # many shapes / options through whatever switches the environment sets; only complaints matter
+        from keras_unsupervised_b200.data import PackedBits
+
+        ctx = Context(device=0, seed=1)
+        fake.fake_reset()
+        runs = 0
+        rng = np.random.default_rng(0)
+        for V, H in ((784, 500), (333, 130), (72, 1000), (1024, 64)):
+            for compute in (L.COMPUTE_BF16, L.COMPUTE_F32X3):
+                m = machine(ctx, V, H, compute)
+                for N, B in ((1000, 128), (512, 128), (100, 128), (130, 64), (2048, 512)):
+                    X = data(N, V)
+                    for kw in (dict(k=1), dict(k=3, momentum=0.5, normalize=True), dict(k=1, persistent=True)):
+                        if kw.get("persistent"):
+                            m.set_chains(data(min(B, N), V, seed=3))
+                        hp = Machine.hparams(lr=1e-3, **kw)
+                        m.fit_host(X, B, hp)
+                        m.fit_host(X[:, ::1].astype(np.uint8), B, hp)
+                        wide = np.zeros((N, V + 24), np.float32)      # rows with a pitch: the 2-D copy path
+                        wide[:, :V] = X
+                        m.fit_host(wide[:, :V], B, hp)
+                        m.fit_host(PackedBits(np.packbits(X.astype(np.uint8), axis=1, bitorder="little"), V), B, hp)
+                        ds = Dataset.from_array(ctx, X, compute)
+                        m.fit_epoch(ds, B, hp, want_stats=bool(runs % 2))
+                        m.fit_range(ds, B, hp, 1, -1) if N > B else None
+                        ds.close()
+                        m.cd_step(X[:B], hp)
+                        runs += 7
+                m.close()
+        out = snapshot()
+        out["runs"] = runs
+        out.pop("log")
+        out["kernels"] = len(out["kernels"])
     elif name == "split":  # KUCD_SPLIT=2 KUCD_CHAIN=0: two Gibbs chains on two streams, forked and joined inside the capture
         ctx = Context(device=0, seed=1)
         m = machine(ctx, 784, 500)

@@ -332,3 +332,18 @@ def test_data_formats_gaussian_pcd_injection_score(dry_build):
     assert g["gemm_bf16_kernel<128,0,1,4,4,1>"] == 1 and g["gemm_bf16_kernel<128,0,0,5,4,1>"] == 1   # relu / normal epilogues
     s = Counter(clean(d["pcd_inject_score"])["kernels"])
     assert s["copy_rows_kernel"] == 1 and s["score_kernel"] == 2 and s["free_energy_finish_kernel"] == 4
+
+
+@pytest.mark.parametrize("env", [
+    {}, {"KUCD_STREAM_CHUNK": 4}, {"KUCD_STREAM_CHUNK": 64}, {"KUCD_STREAM_GRAPH": 1},
+    {"KUCD_AR_SLABS": 3, "KUCD_AR_SLABS_MIN_ELEMS": 1}, {"KUCD_PLANE_POOL": 1}, {"KUCD_CHAIN": 0}, {"KUCD_SMALL_CHAIN": 0},
+    {"KUCD_CHAIN": 2}, {"KUCD_SPLIT": 2, "KUCD_CHAIN": 0}, {"KUCD_MERGE": 0}, {"KUCD_CG": 1}, {"KUCD_CHAIN_DW": 1},
+], ids=lambda e: " ".join("%s=%s" % kv for kv in e.items()) or "defaults")
+def test_sweep_of_shapes_and_options_under_every_switch(dry_build, env):
+    """840 training calls - four model shapes (ragged and tile-sized), both compute modes, five data-set / minibatch size
+    pairs (remainders, fewer rows than one minibatch), CD-1 / CD-3 with momentum and mean normalisation / PCD, host rows
+    as float32, uint8, pitched and bit-packed, resident data sets, partial ranges, single steps - under each schedule
+    switch: no copy, descriptor, epilogue buffer, data-path kernel, capture or event complaint from the fake."""
+    d = run("sweep", **env)
+    assert d["errors"] == [], d["errors"][:10]
+    assert d["runs"] == 840 and d["decoded"] > 2000
