@@ -198,6 +198,56 @@ def scenario(name):
         out["runs"] = runs
         out.pop("log")
         out["kernels"] = len(out["kernels"])
+    elif name == "ranks_sweep":  # DRY_RANKS contexts of this process as the ranks of one group, several shapes
+        n = int(os.environ.get("DRY_RANKS", "2"))
+        os.environ["FAKE_CUDA_DEVICES"] = str(n)
+        ctxs = [Context(device=r, seed=1) for r in range(n)]
+        uid = (C.c_char * 128)()
+        L.check(ctxs[0].lib.kucd_comm_unique_id(uid))
+        for r, c in enumerate(ctxs):
+            L.check(c.lib.kucd_ctx_comm_init(c.handle, bytes(uid), r, n))
+            c.rank, c.world = r, n
+        fused = os.environ.get("KUCD_FUSED_REDUCE", "1") != "0"
+        fake.fake_reset()
+        runs = 0
+        for V, H in ((784, 500), (333, 130), (130, 72), (1024, 256)):
+            ms = []
+            for c in ctxs:
+                m = Machine.__new__(Machine)
+                m.ctx, m.V, m.H, m.mode, m.compute = c, V, H, L.MODE_VISIBLE_BERNOULLI, L.COMPUTE_BF16
+                h = C.c_void_p()
+                L.check(c.lib.kucd_rbm_create(c.handle, V, H, m.mode, m.compute, C.byref(h)))
+                m.handle, m.fused_reduce = h, False
+                c._children.add(m)
+                m.set_params(np.zeros((V, H), np.float32), np.zeros(V, np.float32), np.zeros(H, np.float32))
+                ms.append(m)
+            if fused:
+                handles = []
+                for m in ms:
+                    buf = (C.c_char * 128)()
+                    L.check(m.ctx.lib.kucd_rbm_peer_export(m.handle, buf))
+                    handles.append(bytes(buf))
+                for m in ms:
+                    L.check(m.ctx.lib.kucd_rbm_peer_attach(m.handle, b"".join(handles)))
+            for b, steps in ((64, 3), (256, 2)):
+                for kw in (dict(k=1), dict(k=2, momentum=0.5, normalize=True)):
+                    hp = Machine.hparams(lr=1e-3, **kw)
+                    for r, m in enumerate(ms):
+                        X = data(b * steps + b // 2, V, seed=r)                  # full minibatches + a remainder
+                        ds = Dataset.from_array(m.ctx, X, L.COMPUTE_BF16)
+                        m.fit_epoch(ds, b, hp, global_row0=b * r, want_stats=False)
+                        m.fit_host(X, b, hp, global_row0=b * r)
+                        m.cd_step(X[:b], hp, global_row0=b * r)
+                        m.get_params()
+                        ds.close()
+                        runs += 3
+            for m in ms:
+                m.close()
+        out = snapshot()
+        out["runs"] = runs
+        out.pop("log")
+        out["kernels"] = len(out["kernels"])
+        out["timings"] = ctxs[0].timings()
     elif name == "split":  # KUCD_SPLIT=2 KUCD_CHAIN=0: two Gibbs chains on two streams, forked and joined inside the capture
         ctx = Context(device=0, seed=1)
         m = machine(ctx, 784, 500)

@@ -347,3 +347,27 @@ def test_sweep_of_shapes_and_options_under_every_switch(dry_build, env):
     d = run("sweep", **env)
     assert d["errors"] == [], d["errors"][:10]
     assert d["runs"] == 840 and d["decoded"] > 2000
+
+
+@pytest.mark.parametrize("env,fused", [
+    (dict(DRY_RANKS=2, KUCD_FUSED_MIN_ROWS=1), True), (dict(DRY_RANKS=2, KUCD_FUSED_MIN_ROWS=1, KUCD_WIRE_BF16=1), True),
+    (dict(DRY_RANKS=8, KUCD_FUSED_MIN_ROWS=1), True), (dict(DRY_RANKS=8, KUCD_FUSED_MIN_ROWS=1, KUCD_WIRE_BF16=1), True),
+    (dict(DRY_RANKS=3, KUCD_FUSED_MIN_ROWS=1, KUCD_WIRE_BF16=1), True),
+    (dict(DRY_RANKS=2), False),                                     # 64 / 256 rows per rank: below the fused threshold
+    (dict(DRY_RANKS=4, KUCD_FUSED_REDUCE=0), False), (dict(DRY_RANKS=4, KUCD_FUSED_REDUCE=0, KUCD_WIRE_BF16=1), False),
+    (dict(DRY_RANKS=4, KUCD_FUSED_REDUCE=0, KUCD_AR_SLABS=3, KUCD_AR_SLABS_MIN_ELEMS=1), False),
+    (dict(DRY_RANKS=4, KUCD_FUSED_REDUCE=0, KUCD_AR_SLABS=3, KUCD_AR_SLABS_MIN_ELEMS=1, KUCD_WIRE_BF16=1), False),
+], ids=lambda e: " ".join("%s=%s" % kv for kv in e.items()) if isinstance(e, dict) else str(e))
+def test_sweep_of_the_exchange_variants_over_in_process_ranks(dry_build, env, fused):
+    """2, 3, 4 and 8 contexts of one process as the ranks of a group (the fake NCCL talks to nobody, the fake IPC passes
+    pointers through, so the owners' slots of the fused exchange really are each other's memory): four model shapes -
+    visible counts that do and do not divide by the rank count - resident fits with a remainder minibatch, streamed fits,
+    single steps, CD-1 and CD-2 with momentum and mean normalisation; fused exchange with fp32 and bf16 slots, NCCL with
+    fp32 and bf16 payloads, slab-pipelined.  Every slot pointer, slab pointer and all-reduce buffer stays inside its
+    allocation."""
+    d = run("ranks_sweep", **env)
+    assert d["errors"] == [], d["errors"][:10]
+    assert d["runs"] == 48 * int(env["DRY_RANKS"])
+    t = d["timings"]
+    assert (t["fused_reduce_steps"] > 0 and t["allreduce_calls"] == 0) if fused else \
+        (t["fused_reduce_steps"] == 0 and t["allreduce_calls"] > 0)
