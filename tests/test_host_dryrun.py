@@ -79,7 +79,8 @@ def test_every_contraction_launch_is_decoded_and_checked(dry_build):
 
     fake.cudaLaunchKernel.argtypes = [C.c_void_p, Dim3, Dim3, C.c_void_p, C.c_size_t, C.c_void_p]
     assert fake.cudaLaunchKernel(C.addressof(stub), Dim3(1, 1, 1), Dim3(320, 1, 1), args, 1024, None) == 0
-    assert fake.fake_counter(5) == 1 and fake.fake_error_count() == 2      # bias and rowsum point nowhere
+    # the two operand descriptors were never encoded; bias and rowsum point nowhere
+    assert fake.fake_counter(5) == 1 and fake.fake_error_count() == 4
 
 
 CHAIN_SMALL = "chain_kernel<64,1,0>"
@@ -371,3 +372,20 @@ def test_sweep_of_the_exchange_variants_over_in_process_ranks(dry_build, env, fu
     t = d["timings"]
     assert (t["fused_reduce_steps"] > 0 and t["allreduce_calls"] == 0) if fused else \
         (t["fused_reduce_steps"] == 0 and t["allreduce_calls"] > 0)
+
+
+def test_the_fake_runtime_does_catch_a_replay_into_freed_memory(dry_build):
+    import ctypes as C
+
+    fake = C.CDLL(os.path.join(DRY, "libfakecudart.so"))
+    fake.fake_reset()
+    a, g, ge, p = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+    assert fake.cudaStreamCreateWithFlags(C.byref(a), 1) == 0
+    assert fake.cudaMalloc(C.byref(p), C.c_size_t(4096)) == 0
+    assert fake.cudaStreamBeginCapture(a, 2) == 0
+    assert fake.cudaMemsetAsync(p, 0, C.c_size_t(4096), a) == 0
+    assert fake.cudaStreamEndCapture(a, C.byref(g)) == 0
+    assert fake.cudaGraphInstantiate(C.byref(ge), g, C.c_ulonglong(0)) == 0
+    assert fake.cudaGraphLaunch(ge, a) == 0 and fake.fake_error_count() == 0
+    assert fake.cudaFree(p) == 0
+    assert fake.cudaGraphLaunch(ge, a) == 0 and fake.fake_error_count() == 1       # the buffer behind the graph is gone

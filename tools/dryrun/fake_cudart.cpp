@@ -117,9 +117,14 @@ void check_range(const void* p, size_t bytes, const char* what) {
         it->second);
 }
 
+// device ranges a captured launch was checked against: re-validated at every replay of the graph
+std::vector<std::pair<uintptr_t, size_t>> g_capture_ranges;
+std::map<uintptr_t, std::vector<std::pair<uintptr_t, size_t>>> g_graph_ranges;
+
 // [p, p + bytes) must be device memory
 void check_device_range(const void* p, size_t bytes, const char* what) {
   if (bytes == 0) return;
+  if (g_capturing != 0 && p != nullptr) g_capture_ranges.emplace_back(reinterpret_cast<uintptr_t>(p), bytes);
   if (p == nullptr || owner(p) == g_allocs.end()) {
     err("%s: %p is not inside a device allocation", what, p);
     return;
@@ -196,6 +201,19 @@ void check_epilogue(const char* kernel, const P& p, int epi, long M, long N, con
   if (p.colsum != nullptr) check_device_range(p.colsum, static_cast<size_t>(N) * 4, W("colsum"));
 }
 
+// a descriptor produced by fake_encode_tiled: what it describes must (still) be device memory
+void check_tensor_map(const CUtensorMap& tm, const char* what) {
+  uint64_t base, extent, magic;
+  memcpy(&base, reinterpret_cast<const char*>(&tm), 8);
+  memcpy(&extent, reinterpret_cast<const char*>(&tm) + 8, 8);
+  memcpy(&magic, reinterpret_cast<const char*>(&tm) + 16, 8);
+  if (magic != 0x74656e736f726d61ull) {
+    err("%s: not a descriptor made by cuTensorMapEncodeTiled", what);
+    return;
+  }
+  check_device_range(reinterpret_cast<const void*>(base), extent, what);
+}
+
 // kernels whose arguments are decoded and checked against the allocation table
 void check_kernel_args(const std::string& name, void** args) {
   if (args == nullptr) return;
@@ -208,6 +226,10 @@ void check_kernel_args(const std::string& name, void** args) {
       g_decoded_launches++;
       if (p.num_seg < 1 || p.num_seg > kucd::kMaxSeg || p.kblocks < 1) err("gemm: %d segments of %d k-blocks", p.num_seg, p.kblocks);
       if (t[3] == kucd::kEpiRawPush16 && t[0] < 128) err("gemm: the bf16 push epilogue needs BN >= 128");
+      for (int sg = 0; sg < p.num_seg && sg < kucd::kMaxSeg; ++sg) {
+        check_tensor_map(p.tm_a[sg], "gemm_bf16_kernel: A operand descriptor");
+        check_tensor_map(p.tm_b[sg], "gemm_bf16_kernel: B operand descriptor");
+      }
       check_epilogue("gemm_bf16_kernel", p, static_cast<int>(t[3]), p.M, p.N, p.push_base, p.push_rows);
       if (p.dyn != nullptr) check_device_range(p.dyn, sizeof(kucd::StepDyn), "gemm_bf16_kernel: dyn");
     }
@@ -234,6 +256,16 @@ void check_kernel_args(const std::string& name, void** args) {
       if (q.nseg == 2 && q.dep2 >= s2) err("chain: stage %d's second segment waits for stage %d", s2, q.dep2);
       if (q.num_m > p.done_stride) err("chain: stage %d has %d row blocks, the counter stride is %d", s2, q.num_m, p.done_stride);
       tiles += static_cast<long>(q.num_m) * q.num_n;
+      if (q.map_a < 0 || q.map_a >= kucd::kChainMaps || q.map_b < 0 || q.map_b >= kucd::kChainMaps) {
+        err("chain: stage %d uses descriptors %d / %d", s2, q.map_a, q.map_b);
+        return;
+      }
+      check_tensor_map(p.maps[q.map_a], "chain_kernel: A operand descriptor");
+      check_tensor_map(p.maps[q.map_b], "chain_kernel: B operand descriptor");
+      if (q.nseg == 2) {
+        check_tensor_map(p.maps[q.map_a2], "chain_kernel: A operand descriptor (second segment)");
+        check_tensor_map(p.maps[q.map_b2], "chain_kernel: B operand descriptor (second segment)");
+      }
       check_epilogue("chain_kernel", q, q.epi, q.M, q.N, nullptr, 0);
     }
     if (tiles != p.total_tiles) err("chain: the stages have %ld tiles, total_tiles = %d", tiles, p.total_tiles);
@@ -436,8 +468,14 @@ CUresult fake_encode_tiled(CUtensorMap* tm, CUtensorMapDataType dtype, cuuint32_
     }
   }
   if (!ok) return CUDA_ERROR_INVALID_VALUE;
+  // the fake descriptor remembers what it describes, so that a launch (and a later graph replay) can be checked against
+  // the allocations that are live at that moment
   memset(tm, 0, sizeof *tm);
-  memcpy(tm, &base, sizeof base);
+  const uint64_t extent = rank == 2 ? static_cast<uint64_t>(dims[1] - 1) * strides[0] + dims[0] * esz : dims[0] * esz;
+  const uint64_t magic = 0x74656e736f726d61ull;
+  memcpy(reinterpret_cast<char*>(tm), &base, 8);
+  memcpy(reinterpret_cast<char*>(tm) + 8, &extent, 8);
+  memcpy(reinterpret_cast<char*>(tm) + 16, &magic, 8);
   return CUDA_SUCCESS;
 }
 
@@ -731,6 +769,7 @@ cudaError_t cudaStreamBeginCapture(cudaStream_t st, cudaStreamCaptureMode) {
   g_capture_streams.clear();
   g_capture_streams[st];
   g_capture.clear();
+  g_capture_ranges.clear();
   return cudaSuccess;
 }
 cudaError_t cudaStreamEndCapture(cudaStream_t st, cudaGraph_t* g) {
@@ -744,6 +783,7 @@ cudaError_t cudaStreamEndCapture(cudaStream_t st, cudaGraph_t* g) {
   g_capture_streams.clear();
   const uintptr_t h = (g_next_handle += 16);
   g_graphs[h] = g_capture;
+  g_graph_ranges[h] = g_capture_ranges;
   *g = reinterpret_cast<cudaGraph_t>(h);
   return cudaSuccess;
 }
@@ -758,12 +798,22 @@ cudaError_t cudaGraphLaunch(cudaGraphExec_t ge, cudaStream_t) {
     err("cudaGraphLaunch of an unknown or destroyed graph");
     return cudaErrorInvalidValue;
   }
+  // what the captured launches were pointed at must still be device memory: a graph kept across a reallocation of one
+  // of its buffers replays into freed memory
+  for (const auto& r : g_graph_ranges[it->first]) {
+    auto o = owner(reinterpret_cast<const void*>(r.first));
+    if (o == g_allocs.end() || r.first + r.second > o->first + o->second) {
+      err("cudaGraphLaunch: a captured launch points at %zu bytes that are no longer inside a live allocation", r.second);
+      break;
+    }
+  }
   g_log.push_back("graph_launch nodes=" + std::to_string(it->second.size()));
   return cudaSuccess;
 }
 cudaError_t cudaGraphDestroy(cudaGraph_t g) {
   LOCK;
   g_graphs.erase(reinterpret_cast<uintptr_t>(g));
+  g_graph_ranges.erase(reinterpret_cast<uintptr_t>(g));
   return cudaSuccess;
 }
 cudaError_t cudaGraphExecDestroy(cudaGraphExec_t) { return cudaSuccess; }
