@@ -248,6 +248,51 @@ def scenario(name):
         out.pop("log")
         out["kernels"] = len(out["kernels"])
         out["timings"] = ctxs[0].timings()
+    elif name == "errors":  # argument errors of the C ABI: the message, the exception type, nothing leaked, nothing launched
+        ctx = Context(device=0, seed=1)
+        m = machine(ctx, 64, 32)
+        ds = Dataset.from_array(ctx, data(256, 64), L.COMPUTE_BF16)
+        m.fit_epoch(ds, 64, Machine.hparams(lr=1e-3))
+        m.cd_step(data(64, 64), Machine.hparams(lr=1e-3))
+        fake.fake_reset()
+        live0 = fake.fake_counter(4)
+        seen = []
+
+        def expect(kind, fn):
+            try:
+                fn()
+                seen.append(("no error", ""))
+            except kind as e:  # noqa: PERF203
+                seen.append((kind.__name__, str(e)[:90]))
+            except Exception as e:  # noqa: BLE001
+                seen.append(("other " + type(e).__name__, str(e)[:90]))
+
+        expect(ValueError, lambda: m.cd_step(data(64, 65), Machine.hparams(lr=1e-3)))                 # wrong column count
+        expect(ValueError, lambda: m.transform(data(8, 63)))
+        expect(ValueError, lambda: m.inv_transform(data(8, 33)))
+        expect(ValueError, lambda: m.free_energy(data(8, 1)))
+        expect(ValueError, lambda: m.cd_step(data(64, 64), Machine.hparams(lr=1e-3, k=0)))            # k out of range
+        expect(ValueError, lambda: m.cd_step(data(64, 64), Machine.hparams(lr=1e-3, k=40)))
+        expect(ValueError, lambda: m.cd_step(data(64, 64), Machine.hparams(lr=1e-3, persistent=True)))  # no chains set
+        expect(ValueError, lambda: m.fit_epoch(ds, 0, Machine.hparams(lr=1e-3)))                      # batch size
+        expect(ValueError, lambda: m.fit_range(ds, 64, Machine.hparams(lr=1e-3), 3, 2))               # empty / reversed range
+        expect(ValueError, lambda: m.fit_range(ds, 64, Machine.hparams(lr=1e-3), 0, 99))
+        expect(ValueError, lambda: m.set_params(W=np.zeros((64, 31), np.float32)))
+        expect(ValueError, lambda: m.cd_step(data(64, 64).astype(np.float64).view(np.int64), Machine.hparams(lr=1e-3))
+               if False else m.cd_step(np.zeros((64, 64), np.int16).view(np.uint16), Machine.hparams(lr=1e-3)))
+        expect(ValueError, lambda: m.delta_rule(True, data(16, 64), data(16, 31), 0.1))               # target shape
+        expect(ValueError, lambda: m.delta_rule(False, data(16, 64), data(16, 64), 0.1))              # input is (rows, H) backward
+        other = machine(ctx, 48, 32)
+        expect(ValueError, lambda: other.fit_epoch(ds, 64, Machine.hparams(lr=1e-3)))                 # data set of another width
+        expect(ValueError, lambda: ds.shuffled(1, 0, into=ds))                                        # in place
+        expect(ValueError, lambda: Machine(ctx, 0, 32, L.MODE_VISIBLE_BERNOULLI, L.COMPUTE_BF16))
+        expect(ValueError, lambda: Machine(ctx, 16, 32, 2, L.COMPUTE_BF16))                           # MODE_COMPLEX
+        expect(ValueError, lambda: Context(device=7))                                                 # 2 fake devices
+        m.cd_step(data(0, 64), Machine.hparams(lr=1e-3))                                              # empty minibatch: a no-op
+        out = snapshot()
+        out["seen"] = seen
+        other.close()
+        out["leaked"] = fake.fake_counter(4) - live0
     elif name == "split":  # KUCD_SPLIT=2 KUCD_CHAIN=0: two Gibbs chains on two streams, forked and joined inside the capture
         ctx = Context(device=0, seed=1)
         m = machine(ctx, 784, 500)

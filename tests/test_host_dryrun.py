@@ -389,3 +389,20 @@ def test_the_fake_runtime_does_catch_a_replay_into_freed_memory(dry_build):
     assert fake.cudaGraphLaunch(ge, a) == 0 and fake.fake_error_count() == 0
     assert fake.cudaFree(p) == 0
     assert fake.cudaGraphLaunch(ge, a) == 0 and fake.fake_error_count() == 1       # the buffer behind the graph is gone
+
+
+def test_argument_errors_of_the_c_abi(dry_build):
+    """Shape, range and state errors come back as KUCD_ERR_INVALID_ARG / SHAPE_MISMATCH -> ValueError with the message of
+    kucd_last_error (the reference raises ValueError for its own argument errors, dbn.py:29,48), before anything is
+    launched, and nothing stays allocated behind a failed call."""
+    d = clean(run("errors"))
+    seen = d["seen"]
+    accepted = [i for i, (kind, _) in enumerate(seen) if kind == "no error"]
+    assert accepted == [11]                                  # an integer array: the ctypes shim converts it to float32
+    assert all(kind == "ValueError" for i, (kind, _) in enumerate(seen) if i != 11), seen
+    msgs = [m for _, m in seen]
+    assert "expected (-1, 64)" in msgs[0] and "k = 0 is outside" in msgs[4] and "chains" in msgs[6]
+    assert "shuffled in place" in msgs[15] and "MODE_COMPLEX" in msgs[17] and msgs[18] == "device 7 of 2"
+    assert d["leaked"] == 0
+    assert d["kernels"] == ["ingest_kernel", "colsum_store_kernel", "chain_kernel<64,1,0>", "update_w_kernel<0>",
+                            "refresh_planes_kernel"]          # the accepted call, and the second model's set_params
