@@ -293,6 +293,38 @@ def scenario(name):
         out["seen"] = seen
         other.close()
         out["leaked"] = fake.fake_counter(4) - live0
+    elif name == "oom":  # the n-th cudaMalloc of a whole session fails, for n = 1 .. 45: an error, no crash, no leak
+        fake.fake_fail_malloc_in.argtypes = [C.c_long]
+        results = []
+        X = data(300, 96)
+        for n in range(1, 46):
+            fake.fake_reset()
+            live0 = fake.fake_counter(4)
+            fake.fake_fail_malloc_in(n)
+            objs, outcome = [], "ok"
+            try:
+                ctx = Context(device=0, seed=1)
+                objs.append(ctx)
+                m = machine(ctx, 96, 40, L.COMPUTE_F32X3 if n % 2 else L.COMPUTE_BF16)
+                ds = Dataset.from_array(ctx, X, m.compute)
+                m.fit_epoch(ds, 128, Machine.hparams(lr=1e-3, momentum=0.5))
+                h = m.transform_dataset(ds)
+                sh = ds.shuffled(1, 0)
+                m.fit_host(X, 128, Machine.hparams(lr=1e-3))
+                m.delta_rule(True, X[:64], data(64, 40, seed=2), 0.1)
+                m.transform(X[:32])
+                m.free_energy(X[:32])
+            except L.KucdError as e:
+                outcome = "KucdError"
+                if "cudaMalloc" not in str(e) and "memory" not in str(e).lower():
+                    outcome = "KucdError (other): " + str(e)[:80]
+            except Exception as e:  # noqa: BLE001
+                outcome = type(e).__name__ + ": " + str(e)[:80]
+            fake.fake_fail_malloc_in(0)
+            for o in objs:
+                o.close()                      # closes the machines / data sets it still tracks, then the context
+            results.append((n, outcome, fake.fake_counter(4) - live0, fake.fake_error_count()))
+        out = {"results": results}
     elif name == "split":  # KUCD_SPLIT=2 KUCD_CHAIN=0: two Gibbs chains on two streams, forked and joined inside the capture
         ctx = Context(device=0, seed=1)
         m = machine(ctx, 784, 500)

@@ -406,3 +406,13 @@ def test_argument_errors_of_the_c_abi(dry_build):
     assert d["leaked"] == 0
     assert d["kernels"] == ["ingest_kernel", "colsum_store_kernel", "chain_kernel<64,1,0>", "update_w_kernel<0>",
                             "refresh_planes_kernel"]          # the accepted call, and the second model's set_params
+
+
+def test_allocation_failures_anywhere_in_a_session(dry_build):
+    """Fault injection: the n-th cudaMalloc of a session (context, model, data set, resident fit with momentum, data-set
+    transform, shuffle, streamed fit, delta rule, transform, free energy; both compute modes) fails, for n = 1 .. 45.  The
+    call that hits it raises KucdError (KUCD_ERR_CUDA), the process survives, closing the context gives everything back."""
+    d = run("oom")
+    outcomes = Counter(r[1] for r in d["results"])
+    assert set(outcomes) <= {"KucdError", "ok"} and outcomes["KucdError"] >= 35, d["results"]
+    assert all(leak == 0 and complaints == 0 for _, _, leak, complaints in d["results"]), d["results"]

@@ -39,6 +39,7 @@ std::map<const void*, std::string> g_funcs;  // host stub -> mangled kernel name
 std::vector<std::string> g_log;
 std::vector<std::string> g_errors;
 size_t g_malloc_calls = 0, g_free_calls = 0, g_live_bytes = 0, g_peak_bytes = 0;
+long g_fail_malloc_in = 0;  // > 0: that many cudaMalloc calls from now, one fails (fault injection for the error paths)
 size_t g_decoded_launches = 0;  // contraction launches whose parameter block was decoded and checked
 int g_device = 0;
 // Stream capture, modelled on the rules the engine relies on: a capture starts on one stream; another stream joins it by
@@ -527,6 +528,11 @@ long long fake_counter(int which) {  // 0 cudaMalloc calls, 1 cudaFree calls, 2 
   }
 }
 
+void fake_fail_malloc_in(long n) {
+  LOCK;
+  g_fail_malloc_in = n;
+}
+
 // ---- registration of the kernels (called by the nvcc-generated module constructor) --------------------------
 void** __cudaRegisterFatBinary(void*) {
   static void* handle = nullptr;
@@ -604,6 +610,10 @@ cudaError_t cudaGetDriverEntryPoint(const char* symbol, void** fn, unsigned long
 // ---- memory -------------------------------------------------------------------------------------------------
 cudaError_t cudaMalloc(void** p, size_t n) {
   LOCK;
+  if (g_fail_malloc_in > 0 && --g_fail_malloc_in == 0) {
+    *p = nullptr;
+    return cudaErrorMemoryAllocation;
+  }
   void* q = nullptr;
   if (posix_memalign(&q, 512, n == 0 ? 512 : n) != 0) return cudaErrorMemoryAllocation;
   // pages are not touched here: a dry run of a C4-sized model must not need C4-sized RAM
