@@ -49,7 +49,8 @@ def snapshot():
     log = _lines(fake.fake_log_size, fake.fake_log_line)
     return {"log": log, "kernels": [_kernel(x) for x in log if x.startswith("launch") or x.startswith("graph_launch")
                                     or x.startswith("allreduce") or x.startswith("broadcast")],
-            "graph": [_kernel(x) for x in _lines(fake.fake_last_graph_size, fake.fake_last_graph_line)],
+            "graph": [_kernel(x) for x in _lines(fake.fake_last_graph_size, fake.fake_last_graph_line)
+                      if not x.startswith("event_")],
             "graph_raw": _lines(fake.fake_last_graph_size, fake.fake_last_graph_line),
             "errors": _lines(fake.fake_error_count, fake.fake_error_line),
             "decoded": fake.fake_counter(5), "mallocs": fake.fake_counter(0), "frees": fake.fake_counter(1), "live_bytes": fake.fake_counter(2),

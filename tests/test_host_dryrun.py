@@ -416,3 +416,50 @@ def test_allocation_failures_anywhere_in_a_session(dry_build):
     outcomes = Counter(r[1] for r in d["results"])
     assert set(outcomes) <= {"KucdError", "ok"} and outcomes["KucdError"] >= 35, d["results"]
     assert all(leak == 0 and complaints == 0 for _, _, leak, complaints in d["results"]), d["results"]
+
+
+def _order(graph_raw):
+    """The captured step as (what, stream, event) triples with streams / events renamed s0, s1 .. / e0, e1 .. by appearance."""
+    import re
+
+    names = {}
+
+    def nm(h, prefix):
+        return names.setdefault((prefix, h), "%s%d" % (prefix, sum(1 for k in names if k[0] == prefix)))
+
+    out = []
+    for line in graph_raw:
+        st = re.search(r"stream=(\S+)", line)
+        ev = re.search(r"event=(\S+)", line)
+        what = line.split()[0]
+        if what == "launch":
+            what = re.sub(r"^_ZN4kucd\d+", "", line.split()[1])
+            what = re.match(r"[a-z_0-9]+", what).group(0)
+        out.append((what, nm(st.group(1), "s") if st else None, nm(ev.group(1), "e") if ev else None))
+    return out
+
+
+def test_slab_ordering_inside_the_captured_step(dry_build):
+    """One rank, C4's share, two slabs: each slab's update sits on the second stream behind that slab's contraction (and
+    only that one), the last update - which carries the bias update and the step advance - also behind everything the
+    step enqueued before it, and the compute stream rejoins before the next step's state is touched."""
+    o = _order(clean(run("full_size", KUCD_AR_SLABS=2)["c4"])["graph_raw"])
+    o = [x for x in o if x[0] not in ("memset", "colsum_kernel")]
+    assert o == [("chain_kernel", "s0", None),
+                 ("gemm_bf16_kernel", "s0", None), ("event_record", "s0", "e0"),
+                 ("gemm_bf16_kernel", "s0", None), ("event_record", "s0", "e1"),
+                 ("copy_rows_kernel", "s0", None), ("event_record", "s0", "e2"),
+                 ("event_wait", "s1", "e0"), ("update_w_kernel", "s1", None),
+                 ("event_wait", "s1", "e1"), ("event_wait", "s1", "e2"), ("update_w_kernel", "s1", None),
+                 ("event_record", "s1", "e3"), ("event_wait", "s0", "e3"),
+                 ("advance_dyn_kernel", "s0", None)]
+    # two ranks, NCCL: the all-reduce of slab i sits on the second stream behind contraction i, update i behind all-reduce i
+    d = clean(run("two_ranks", KUCD_FUSED_REDUCE=0, KUCD_AR_SLABS=2, KUCD_AR_SLABS_MIN_ELEMS=1))
+    o = [x for x in _order(d["graph_raw"]) if x[0] in ("gemm_bf16_kernel", "allreduce", "update_w_kernel", "event_record", "event_wait")]
+    o = o[3:]                                                # the three projections
+    assert o == [("gemm_bf16_kernel", "s0", None), ("event_record", "s0", "e0"), ("event_wait", "s1", "e0"),
+                 ("allreduce", "s1", None), ("allreduce", "s1", None), ("event_record", "s1", "e1"),
+                 ("gemm_bf16_kernel", "s0", None), ("event_record", "s0", "e2"), ("event_wait", "s1", "e2"),
+                 ("allreduce", "s1", None), ("event_record", "s1", "e3"),
+                 ("event_wait", "s0", "e1"), ("update_w_kernel", "s0", None),
+                 ("event_wait", "s0", "e3"), ("update_w_kernel", "s0", None)]

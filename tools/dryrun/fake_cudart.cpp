@@ -736,6 +736,11 @@ cudaError_t cudaStreamWaitEvent(cudaStream_t st, cudaEvent_t e, unsigned) {
   if (g_capturing && ev_capture == g_capturing) {
     // an event of this capture: the waiting stream becomes (or stays) part of it, and the recording stream's work
     // up to that event is now depended upon
+    {
+      char buf[160];
+      snprintf(buf, sizeof buf, "event_wait event=%p stream=%p", static_cast<void*>(e), static_cast<void*>(st));
+      g_capture.push_back(buf);
+    }
     g_capture_streams[st];
     Member& m = g_capture_streams[ev_stream];
     if (st != ev_stream && it->second.work > m.joined) m.joined = it->second.work;
@@ -761,6 +766,11 @@ cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t st) {
     return cudaErrorInvalidResourceHandle;
   }
   g_event_state[e] = {captured(st) ? g_capturing : 0, st, captured(st) ? g_capture_streams[st].work : 0};
+  if (captured(st)) {
+    char buf[160];
+    snprintf(buf, sizeof buf, "event_record event=%p stream=%p", static_cast<void*>(e), static_cast<void*>(st));
+    g_capture.push_back(buf);
+  }
   return cudaSuccess;
 }
 cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
