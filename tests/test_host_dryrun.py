@@ -273,7 +273,7 @@ def test_the_fake_runtime_does_catch_capture_mistakes(dry_build):
     assert fake.cudaEventRecord(e_out, b) == 0
     assert fake.cudaStreamWaitEvent(a, e_out, 0) == 0
     assert fake.cudaStreamEndCapture(a, C.byref(g)) == 0
-    assert fake.fake_error_count() == 0 and fake.fake_last_graph_size() == 1
+    assert fake.fake_error_count() == 0 and fake.fake_last_graph_size() == 5      # the memset + 2 records + 2 waits
     assert fake.cudaFree(p) == 0
 
 
