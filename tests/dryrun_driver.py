@@ -326,6 +326,25 @@ def scenario(name):
                 o.close()                      # closes the machines / data sets it still tracks, then the context
             results.append((n, outcome, fake.fake_counter(4) - live0, fake.fake_error_count()))
         out = {"results": results}
+    elif name == "rbm_options":  # RBM.fit under the optional hps keys (values are meaningless in a dry run)
+        from keras_unsupervised_b200.ebm import RBM, MODE_VISIBLE_BERNOULLI, MODE_VISIBLE_GAUSSIAN
+
+        ctx = Context(device=0, seed=1)
+        X = data(600, 200)
+        for key, hps, mode in (
+                ("shuffle", {"epochs": 3, "shuffle": True, "dtype": "bf16"}, MODE_VISIBLE_BERNOULLI),
+                ("reference", {"epochs": 1, "compat": "reference"}, MODE_VISIBLE_BERNOULLI),
+                ("pcd", {"epochs": 2, "persistent": True, "k": 2, "dtype": "bf16", "momentum": 0.5, "weight_decay": 1e-4,
+                         "normalize": "mean"}, MODE_VISIBLE_BERNOULLI),
+                ("gaussian_default", {"epochs": 1}, MODE_VISIBLE_GAUSSIAN),
+                ("resident_one_epoch", {"epochs": 1, "stream": False, "dtype": "bf16"}, MODE_VISIBLE_BERNOULLI)):
+            base = {"batch_size": 128, "lr": 1e-3}
+            base.update(hps)
+            r = RBM(base, 64, name=key, mode=mode, context=ctx)
+            fake.fake_reset()
+            r.fit(X, verbose=0)
+            out[key] = snapshot()
+            out[key]["history"] = len(r.history)
     elif name == "split":  # KUCD_SPLIT=2 KUCD_CHAIN=0: two Gibbs chains on two streams, forked and joined inside the capture
         ctx = Context(device=0, seed=1)
         m = machine(ctx, 784, 500)

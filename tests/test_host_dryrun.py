@@ -463,3 +463,22 @@ def test_slab_ordering_inside_the_captured_step(dry_build):
                  ("allreduce", "s1", None), ("event_record", "s1", "e3"),
                  ("event_wait", "s0", "e1"), ("update_w_kernel", "s0", None),
                  ("event_wait", "s0", "e3"), ("update_w_kernel", "s0", None)]
+
+
+def test_rbm_fit_under_the_optional_hps_keys(dry_build):
+    """RBM.fit through the real ctypes layer and host code: shuffling epochs, the reference's three single-parameter runs +
+    score chain per minibatch (rbm.py:214-234), persistent chains with momentum / weight decay / mean normalisation, the
+    constructor-default Gaussian mode in float32-grade arithmetic, and a one-epoch fit of an uploaded array."""
+    d = run("rbm_options")
+    sh = Counter(clean(d["shuffle"])["kernels"])
+    assert sh["permute_rows_kernel"] == 3 and sh["graph_launch"] == 3 * 5 and d["shuffle"]["history"] == 3
+    ref = Counter(clean(d["reference"])["kernels"])          # 600 rows / 128 = 5 minibatches
+    assert ref["update_w_kernel<0>"] == 15                   # runs A, B, C: one parameter each (rbm.py:214-216)
+    assert ref["gemm_bf16_kernel<128,1,1,0,4,1>"] == 15      # each with its own chain and statistics
+    assert ref["score_kernel"] == 5 and ref["free_energy_finish_kernel"] == 10     # run D: F(v), F(v_neg) (rbm.py:227-233)
+    pcd = Counter(clean(d["pcd"])["kernels"])
+    assert pcd["graph_launch"] == 10 and pcd["ingest_kernel"] == 2                 # the data set and the chains' start
+    g = Counter(clean(d["gaussian_default"])["kernels"])
+    assert g["gemm_bf16_kernel<128,0,1,4,4,1>"] == 5 and g["gemm_bf16_kernel<128,0,0,5,4,1>"] == 5
+    one = Counter(clean(d["resident_one_epoch"])["kernels"])
+    assert one["graph_launch"] == 5 and one["ingest_kernel"] == 1
