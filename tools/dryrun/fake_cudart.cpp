@@ -646,7 +646,11 @@ cudaError_t cudaFreeHost(void* p) {
   free(p);
   return cudaSuccess;
 }
-static const size_t kTouchLimit = size_t{64} << 20;  // larger copies / fills are checked but not performed
+// larger copies / fills are checked but not performed; FAKE_TOUCH_LIMIT=0 performs none (host-cost measurements)
+static const size_t kTouchLimit = [] {
+  const char* e = getenv("FAKE_TOUCH_LIMIT");
+  return e != nullptr ? static_cast<size_t>(atoll(e)) : size_t{64} << 20;
+}();
 cudaError_t cudaMemset(void* p, int v, size_t n) {
   LOCK;
   check_device_range(p, n, "cudaMemset");
