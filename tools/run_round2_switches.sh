@@ -114,10 +114,11 @@ else
              "fused16 KUCD_FUSED_MIN_ROWS=1 KUCD_WIRE_BF16=1" \
              "nccl32s4 KUCD_FUSED_REDUCE=0 KUCD_AR_SLABS=4" \
              "nccl16s4 KUCD_FUSED_REDUCE=0 KUCD_AR_SLABS=4 KUCD_WIRE_BF16=1" \
-             "nccl16s8 KUCD_FUSED_REDUCE=0 KUCD_AR_SLABS=8 KUCD_WIRE_BF16=1"; do
+             "nccl16s8 KUCD_FUSED_REDUCE=0 KUCD_AR_SLABS=8 KUCD_WIRE_BF16=1" \
+             "nccl16s4r32 KUCD_FUSED_REDUCE=0 KUCD_AR_SLABS=4 KUCD_WIRE_BF16=1 KUCD_AR_RESERVE_SMS=32"; do
       set -- $v
-      echo "== bench $w at $N GPUs, $1 ($2 $3 ${4:-})" >> $LOG
-      env $2 $3 ${4:-X_UNUSED=0} timeout 300 $TR --nproc-per-node $N --master-port 29533 bench.py --gpus $N --workload $w \
+      echo "== bench $w at $N GPUs, $1 ($2 $3 ${4:-} ${5:-})" >> $LOG
+      env $2 $3 ${4:-X_UNUSED=0} ${5:-X_UNUSED2=0} timeout 300 $TR --nproc-per-node $N --master-port 29533 bench.py --gpus $N --workload $w \
           --steps 60 --warmup 5 --no-cpu-baseline --no-e2e > gpurun_out/r02_bench_${w}_n${N}_$1.json 2>> $LOG
       python - "$w" "$N" "$1" >> $LOG <<'EOF'
 import json, sys
