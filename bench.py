@@ -115,17 +115,51 @@ class ClockSampler:
                 "window": "timed regions" if used is inside else "under load (timed region shorter than the sampling period)"}
 
 
-def cpu_fused_step(orc, O, x, k, rng):
-    """One fused CD-k minibatch of the oracle port in float32, drawing its uniforms as TF would."""
+def cpu_threads_setup():
+    """torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm is the reference's path "with all the host
+    threads it can use".  Called before numpy (OpenBLAS) is first imported."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    for var in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[var] = str(n)
+    return n
+
+
+def blas_threads():
+    try:
+        from threadpoolctl import threadpool_info
+
+        return max([int(i.get("num_threads", 1)) for i in threadpool_info() if i.get("user_api") == "blas"] or [1])
+    except Exception:  # noqa: BLE001
+        return None
+
+
+def cpu_step(orc, x, k, rng, schedule):
+    """One CD-k minibatch of the oracle port in float32, drawing its uniforms as TF would.
+    schedule 'fused': one chain, W / b / c from the same statistics (the engine's schedule; 2k+3 contractions).
+    schedule 'reference': what ku/ebm/rbm.py:214-233 executes per minibatch - three sequential single-parameter
+    runs with fresh draws, two free energies and a fourth chain for the printed score (6k+8 contractions; 14 at
+    k = 1)."""
     import numpy as np
 
     rows = x.shape[0]
-    u_h = [rng.random((rows, orc.H), dtype=np.float32) for _ in range(k)]
-    u_v = [None] + [rng.random((rows, orc.V), dtype=np.float32) for _ in range(k)]
-    orc.fused_step(x, u_h, u_v, lr=1e-3, k=k, scale=1.0 / rows)
+
+    def draws():
+        return ([rng.random((rows, orc.H), dtype=np.float32) for _ in range(k)],
+                [None] + [rng.random((rows, orc.V), dtype=np.float32) for _ in range(k)])
+
+    if schedule == "fused":
+        u_h, u_v = draws()
+        orc.fused_step(x, u_h, u_v, lr=1e-3, k=k, scale=1.0 / rows)
+    else:
+        d = [draws() for _ in range(3)]
+        d.append((rng.random((rows, orc.H), dtype=np.float32), rng.random((rows, orc.V), dtype=np.float32)))
+        orc.reference_step(x, d, lr=1e-3, k=k, scale=1.0 / rows)
 
 
-def cpu_arm(cfg, steps, warmup, rows):
+def cpu_arm(cfg, steps, warmup, rows, schedule="fused"):
     """The reference's CPU path: the oracle port of ku/ebm/rbm.py (TensorFlow is not installable),
     float32 numpy/BLAS on all host cores, `rows` rows per step (a bounded sample of the minibatch)."""
     import numpy as np
@@ -137,16 +171,34 @@ def cpu_arm(cfg, steps, warmup, rows):
     orc = O.OracleRBM(W, b, c, compute="f32")
     x = (np.random.default_rng(1234).random((rows, cfg["V"])) < cfg["q"]).astype(np.float32)
     for _ in range(warmup):
-        cpu_fused_step(orc, O, x, cfg["k"], rng)
+        cpu_step(orc, x, cfg["k"], rng, schedule)
     t0 = time.perf_counter()
     for _ in range(steps):
-        cpu_fused_step(orc, O, x, cfg["k"], rng)
+        cpu_step(orc, x, cfg["k"], rng, schedule)
     dt = time.perf_counter() - t0
     try:
         cores = len(os.sched_getaffinity(0))
     except AttributeError:
         cores = os.cpu_count()
-    return dict(value=rows * steps / dt, seconds=dt, cores=cores, rows=rows, steps=steps)
+    return dict(value=rows * steps / dt, seconds=dt, cores=cores, rows=rows, steps=steps, schedule=schedule,
+                blas_threads=blas_threads())
+
+
+def cpu_baseline_obj(cfg, steps, rows, B):
+    """Both CPU figures BASELINE.md section 4 promises: `value` is the reference's own schedule (rbm.py:214-233), the
+    fused one rides along so that the ratio is not inflated by the reference's redundant passes."""
+    k = cfg["k"]
+    ref = cpu_arm(cfg, steps, 1, rows, "reference")
+    fused = cpu_arm(cfg, steps, 1, rows, "fused")
+    return {"value": ref["value"], "unit": UNIT, "cores": ref["cores"], "kind": "port",
+            "blas_threads": ref["blas_threads"],
+            "sample": "%d steps of %d rows (of the %d-row minibatch), float32 numpy/BLAS oracle port of ku/ebm/rbm.py, "
+                      "the reference's schedule (rbm.py:214-233: runs A, B, C with fresh draws, two free energies, score "
+                      "chain = %d contractions per minibatch at CD-%d), %.1f s" % (ref["steps"], rows, B, 6 * k + 8, k,
+                                                                                   ref["seconds"]),
+            "fused_schedule": {"value": fused["value"], "unit": UNIT,
+                               "sample": "same rows, one chain with W / b / c from the same statistics (%d contractions, "
+                                         "the schedule the GPU arm runs), %.1f s" % (2 * k + 3, fused["seconds"])}}
 
 
 def parse_cpulist(txt):
@@ -346,6 +398,10 @@ def _main(out):
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: the workload's minibatch PER GPU (default, what the metric is quoted on); strong: that "
+                         "minibatch is the GLOBAL one, split by rows over the GPUs (SURVEY.md 8d: report both - the weak "
+                         "line carries the strong figure as `strong_scaling` when N > 1)")
     args = ap.parse_args()
     cfg = WORKLOADS[args.workload]
     V, H, B, k = cfg["V"], cfg["H"], cfg["B"], cfg["k"]
@@ -353,7 +409,13 @@ def _main(out):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     steps, warmup = max(1, args.steps), max(0, args.warmup)
-    config = {"workload": cfg["desc"], "n_visible": V, "n_hidden": H, "batch_per_gpu": B, "global_batch": B * world,
+    B_global = B * world   # weak scaling: the workload's minibatch on every GPU
+    if args.scaling == "strong" and world > 1 and B:
+        if B % (world * 128):
+            raise SystemExit("--scaling strong: the %d-row minibatch does not split into %d shards of whole 128-row blocks"
+                             % (B, world))
+        B_global, B = B, B // world
+    config = {"workload": cfg["desc"], "n_visible": V, "n_hidden": H, "batch_per_gpu": B, "global_batch": B_global,
               "k": k, "schedule": "fused single chain (W, b, c from the same statistics)",
               "parallelism": "dp%d" % world,
               "l2": "every step reads a different minibatch; the resident data set is far larger than L2"}
@@ -361,16 +423,29 @@ def _main(out):
     if args.impl == "reference":
         if rank != 0:
             return 0
-        rows = 256 if args.workload == "c3" else B
-        r = cpu_arm(cfg, steps, min(warmup, 2), rows)
-        line = {"metric": METRIC, "value": r["value"], "unit": UNIT, "impl": "reference", "n_gpus": args.gpus,
-                "steps": steps, "warmup": min(warmup, 2), "ms_per_step": 1e3 * r["seconds"] / steps,
+        cpu_threads_setup()
+        rows = 256 if args.workload in ("c3", "c3f32") else min(B, 1024)
+        n = max(1, min(steps, 20))
+        ref = cpu_arm(cfg, n, min(warmup, 1), rows, "reference")
+        fused = cpu_arm(cfg, n, min(warmup, 1), rows, "fused")
+        sample = ("%d steps of %d rows (a bounded sample of the %d-row global minibatch: rows are independent, so CPU "
+                  "samples/s does not depend on it), float32 numpy/BLAS oracle port of ku/ebm/rbm.py on %d host threads, "
+                  "the reference's own schedule rbm.py:214-233 (three sequential single-parameter runs, two free energies, "
+                  "score chain: %d contractions per minibatch at CD-%d)" % (n, rows, B * world, ref["blas_threads"] or
+                                                                            ref["cores"], 6 * k + 8, k))
+        line = {"metric": METRIC, "value": ref["value"], "unit": UNIT, "impl": "reference", "n_gpus": args.gpus,
+                "steps": n, "warmup": min(warmup, 1), "ms_per_step": 1e3 * ref["seconds"] / n,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": config,
-                "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
-                                 "sample": "%d steps of %d rows (of the %d-row minibatch), fused CD-%d, float32 "
-                                           "numpy/BLAS oracle port of ku/ebm/rbm.py" % (steps, rows, B, k)},
-                "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "cpu_baseline": {"value": ref["value"], "unit": UNIT, "cores": ref["cores"], "kind": "port",
+                                 "blas_threads": ref["blas_threads"], "sample": sample,
+                                 "fused_schedule": {"value": fused["value"], "unit": UNIT,
+                                                    "sample": "same rows, the GPU arm's schedule (one chain, %d "
+                                                              "contractions)" % (2 * k + 3)}},
+                "e2e": {"value": ref["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "note": "one host, all of its threads, whatever --gpus says: the CPU path does not scale with GPUs; the "
+                        "reference computes in float32, the GPU arm's default workload in bf16 (its float32-grade figure "
+                        "is the `f32_grade` key of the GPU line)",
                 "gpu_launches": 0}
         print(json.dumps(line), file=out)
         return 0
@@ -431,31 +506,56 @@ def _main(out):
             dist.barrier()
 
     # ---- warm-up (captures the step graph), then exactly K timed steps -----------------------------
-    done = 0
-    while done < warmup:
-        n = min(warmup - done, n_batches)
-        m.fit_range(ds, B, hp, 0, n, global_row0=row0)
-        done += n
-    barrier()
     ext = torch.cuda.ExternalStream(ctx.stream_ptr(), device=torch.device("cuda", local_rank))
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ctx.timings(reset=True)
-    t_wall0 = time.time()
-    e0.record(ext)
-    m.fit_range(ds, B, hp, 0, steps, global_row0=row0)
-    e1.record(ext)
-    ctx.sync()
-    torch.cuda.synchronize()
-    t_wall1 = time.time()
-    ms = e0.elapsed_time(e1)
-    tm = ctx.timings()
+
+    def timed_region(b_loc, g_row0):
+        """W warm-up steps, then K timed steps of b_loc rows per rank; CUDA events on the engine stream, max over ranks."""
+        done = 0
+        while done < warmup:
+            n = min(warmup - done, n_batches)
+            m.fit_range(ds, b_loc, hp, 0, n, global_row0=g_row0)
+            done += n
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ctx.timings(reset=True)
+        tw0 = time.time()
+        e0.record(ext)
+        m.fit_range(ds, b_loc, hp, 0, steps, global_row0=g_row0)
+        e1.record(ext)
+        ctx.sync()
+        torch.cuda.synchronize()
+        tw1 = time.time()
+        ms_ = e0.elapsed_time(e1)
+        tm_ = ctx.timings()
+        if dist is not None:
+            t = torch.tensor([ms_], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_ = float(t.item())
+        return ms_, tm_, (tw0, tw1)
+
+    def exchange_of(tm_):
+        if world == 1:
+            return "none (one GPU)"
+        if tm_["fused_reduce_steps"]:
+            return "fused: dW rows stored into their owners' memory by the contraction epilogue (NVLink), flag barriers"
+        return "ncclAllReduce(dW | db | dc)"
+
+    ms, tm, win = timed_region(B, row0)
     launches = tm["graph_kernel_launches"] + 1  # + the step-state initialisation kernel
-    if dist is not None:
-        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
     value = world * steps * B / (ms * 1e-3)
-    windows = [(t_wall0, t_wall1)]
+    windows = [win]
+    config["exchange"] = exchange_of(tm)
+
+    # ---- strong scaling beside the weak line (N > 1): the workload's minibatch as the GLOBAL one, split by rows ----
+    strong = None
+    if args.scaling == "weak" and world > 1 and B % (world * 128) == 0 and not persistent:
+        bs = B // world
+        ms_s, tm_s, win_s = timed_region(bs, rank * bs)
+        strong = {"value": steps * B / (ms_s * 1e-3), "unit": UNIT, "ms_per_step": ms_s / steps, "global_batch": B,
+                  "batch_per_gpu": bs, "exchange": exchange_of(tm_s), "steps": steps,
+                  "note": "same minibatch as one GPU's, split by rows: per-GPU compute shrinks by N while the dW exchange "
+                          "stays %d MiB" % (V * H * 4 >> 20)}
+        windows.append(win_s)
 
     # ---- end to end: float32 HOST minibatches through the reference-facing path (what RBM.fit(V) with a numpy
     # V runs for one epoch): kucd_rbm_fit_host copies minibatch i+1 from pinned host memory while minibatch i
@@ -572,37 +672,77 @@ def _main(out):
                 with open(tpath) as f:
                     traffic = json.load(f).get(args.workload + ("_chain" if chain else ""))
             step_tf = flops_per_sample(V, H, k) * B / (ms * 1e-3 / steps) / 1e12
-            roof = {"bound": "tensor", "kernel": kernel, "achieved": ach, "peak": pk["sustained"], "unit": "TFLOP/s",
-                    "frac": ach / pk["sustained"],
-                    "peak_source": pk["source"] + ", sustained figure (kernel timed inside a long step)",
+            # Which measured peak applies (MEASURED_PEAKS.json: `bf16_tflops` is the best of 10 single matmuls - a burst at
+            # full clocks -, `bf16_tflops_sustained` 4 s of back-to-back matmuls under the power cap)?  A timed region of
+            # less than a second never reaches the steady power-capped state: burst.  Both fractions are printed.
+            regime = "burst" if ms * 1e-3 < 1.0 else "sustained"
+            peak = pk[regime]
+            roof = {"bound": "tensor", "kernel": kernel, "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+                    "frac": ach / peak, "regime": regime,
+                    "frac_of_burst_peak": ach / pk["burst"], "frac_of_sustained_peak": ach / pk["sustained"],
+                    "peak_source": pk["source"] + ": %s figure, because the timed region lasted %.3f s (burst below 1 s, "
+                                                  "sustained above)" % (regime, ms * 1e-3),
                     "measured": "CUDA events on the engine stream around each launch of %d further steps issued directly "
                                 "(same process, same data, right after the timed region; a graph replay cannot carry "
                                 "per-kernel events)" % n_prof,
                     "traffic": traffic, "launch_ms": per_launch_ms, "launches_timed": n_timed,
                     "projections_per_launch": n_proj if chain else None, "flop_per_launch": flop,
                     "dw_launch_ms": (tp["dw_ms"] / tp["dw_timed"]) if tp["dw_timed"] else None,
-                    "step_tflops": step_tf, "step_frac_of_sustained": step_tf / pk["sustained"]}
+                    "step_tflops": step_tf, "step_frac": step_tf / peak,
+                    "step_frac_of_burst_peak": step_tf / pk["burst"],
+                    "step_frac_of_sustained_peak": step_tf / pk["sustained"]}
+
+    # ---- the reference's own precision beside the bf16 headline (rbm.py:39 K.floatx() = float32): the same workload
+    # with float32-grade contractions (three bf16 terms per operand), a few steps -----------------------------------
+    f32_grade = None
+    if args.workload == "c3" and world == 1:
+        try:
+            barrier()
+            m32 = Machine(ctx, V, H, L.MODE_VISIBLE_BERNOULLI, L.COMPUTE_F32X3, seed=42)
+            m32.set_params(*m.get_params())
+            n32 = max(3, min(steps, 10))
+            ds32 = Dataset.from_array(ctx, X[:n32 * B], L.COMPUTE_F32X3)
+            m32.fit_range(ds32, B, hp, 0, min(3, n32), global_row0=row0)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            tw0 = time.time()
+            e0.record(ext)
+            m32.fit_range(ds32, B, hp, 0, n32, global_row0=row0)
+            e1.record(ext)
+            ctx.sync()
+            torch.cuda.synchronize()
+            ms32 = e0.elapsed_time(e1)
+            windows.append((tw0, time.time()))
+            f32_grade = {"value": n32 * B / (ms32 * 1e-3), "unit": UNIT, "ms_per_step": ms32 / n32, "steps": n32,
+                         "dtype": "f32 (three bf16 terms per operand, fp32 accumulation: 1e-5 relative to float64)",
+                         "tflops": flops_per_sample(V, H, k) * n32 * B / (ms32 * 1e-3) / 1e12}
+            ds32.close()
+            m32.close()
+        except Exception as exc:  # noqa: BLE001 - informational: must not cost the line
+            f32_grade = {"error": repr(exc)}
     clocks = sampler.stop(windows) if sampler is not None else None
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        rows = 512 if args.workload == "c3" else B
-        r = cpu_arm(cfg, 2 if args.workload == "c3" else 20, 1, rows)
-        cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
-               "sample": "%d steps of %d rows (of the %d-row minibatch), fused CD-%d, float32 numpy/BLAS oracle port of "
-                         "ku/ebm/rbm.py, %.1f s" % (r["steps"], rows, B, k, r["seconds"])}
+        big = args.workload in ("c3", "c3f32", "c4")
+        cpu = cpu_baseline_obj(cfg, 3 if big else 20, 512 if big else B, B)
 
     if dist is not None:
         dist.barrier()
     if rank == 0:
+        tf_gpu = flops_per_sample(V, H, k) * value / world / 1e12
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
-                "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "ms_per_step": ms / steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
                 "dtype": cfg["dtype"], "data": "synthetic binarised (Bernoulli %.4g), U(-0.05,0.05) weights" % cfg["q"],
                 "config": config, "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "roofline": roof,
                 "cpu_baseline": cpu,
-                "per_gpu": {"samples_per_s": value / world,
-                            "tflops": flops_per_sample(V, H, k) * value / world / 1e12,
-                            "frac_of_sustained_bf16_peak": flops_per_sample(V, H, k) * value / world / 1e12 / pk["sustained"]}}
+                "per_gpu": {"samples_per_s": value / world, "tflops": tf_gpu,
+                            "frac_of_burst_bf16_peak": tf_gpu / pk["burst"],
+                            "frac_of_sustained_bf16_peak": tf_gpu / pk["sustained"]}}
+        if strong is not None:
+            line["strong_scaling"] = strong
+        if f32_grade is not None:
+            line["f32_grade"] = f32_grade
         print(json.dumps(line), file=out)
     if dist is not None:
         dist.destroy_process_group()

@@ -285,7 +285,7 @@ class OracleRBM:
         return (-(vb + softplus(self.pre_h(v)).sum(axis=-1))).astype(F32)
 
     # ---- CD statistics ----
-    def cd_stats(self, v, u_h, u_v, k=1, persistent=False, u_hc=None, wire_shards=0, wire_sum_bf16=False):
+    def cd_stats(self, v, u_h, u_v, k=1, persistent=False, u_hc=None, wire_shards=0, wire_sum_bf16=False, need=7):
         """rbm.py:119-126,131,134 generalised to CD-k / PCD.
 
         wire_shards = n > 0 models the engine's opt-in "bf16 partial sums on the wire" exchange: the minibatch rows
@@ -296,29 +296,54 @@ class OracleRBM:
         u_h[0] draws h_pos; u_v[t] (t = 1..k) draws the t-th v_neg; u_h[t] (t = 1..k-1) the intermediate
         hidden samples; the final hidden term is the probability (rbm.py:124).  With `persistent` the
         negative chain starts from self.chains[:rows] (first hidden sample drawn with u_hc) and the final
-        v_neg is stored back."""
+        v_neg is stored back.
+
+        need (bits as in `apply`: 1 = dW, 2 = dc, 4 = db): the statistics to compute.  The reference builds one graph
+        per parameter (rbm.py:127-134) and each evaluates only what its update depends on: the c graph stops after
+        h_neg (no outer products), the b graph after v_neg (no final hidden projection either) - 5 + 3 + 2 contractions
+        per minibatch, which is what its CPU time is made of."""
         v = np.asarray(v, dtype=np.float32)
         rows = v.shape[0]
+        # row_margin: the smallest |u - p| over every Bernoulli draw of a row's chain.  A row whose margin exceeds the
+        # rounding difference between two sigmoid implementations has a uniquely determined chain (tests use it to
+        # tell apart "differs from the oracle" and "a draw sat inside the rounding gap")
+        margin = np.full(rows, np.inf)
+
+        def note(u, p):
+            np.minimum(margin, np.abs(np.asarray(u, np.float64) - p).min(axis=1), out=margin)
+
         h_pos, p_h_pos = self.sample_h(v, u_h[0])
+        note(u_h[0], p_h_pos)
         if persistent:
-            h, _ = self.sample_h(self.chains[:rows], u_hc)
+            h, p_ = self.sample_h(self.chains[:rows], u_hc)
+            note(u_hc, p_)
         else:
             h = h_pos
         v_neg = h_neg = None
         for t in range(1, k + 1):
-            v_neg, _ = self.sample_v(h, u_v[t])
+            v_neg, p_ = self.sample_v(h, u_v[t])
+            if self.mode == MODE_VISIBLE_BERNOULLI:
+                note(u_v[t], p_)
             if t < k:
-                h, _ = self.sample_h(v_neg, u_h[t])
-            else:
+                h, p_ = self.sample_h(v_neg, u_h[t])
+                note(u_h[t], p_)
+            elif need & 3:
                 h_neg = self.prob_h(v_neg)  # always the logistic, also in Gaussian mode (rbm.py:145)
         if persistent:
             self.chains[:rows] = v_neg
+        if not need & 3:
+            db = (v.astype(np.float64).sum(0) - v_neg.astype(np.float64).sum(0)).astype(F32) if self.compute != "bf16" \
+                else (bf16_round(v).astype(np.float64).sum(0) - bf16_round(v_neg).astype(np.float64).sum(0)).astype(F32)
+            return dict(h_pos=h_pos, p_h_pos=p_h_pos, v_neg=v_neg, h_neg=None, dW=None, dc=None, db=db, rows=rows,
+                        row_margin=margin)
         if self.compute == "bf16":
             hn_mm, v0_mm, vn_mm = bf16_round(h_neg), bf16_round(v), bf16_round(v_neg)
         else:
             hn_mm, v0_mm, vn_mm = h_neg, v, v_neg
         f = np.float32 if self.compute == "f32" else np.float64
-        if wire_shards and wire_shards > 0:
+        if not need & 1:
+            dW = None
+        elif wire_shards and wire_shards > 0:
             if rows % wire_shards:
                 raise ValueError("rows must divide by wire_shards")
             rb = rows // wire_shards
@@ -333,7 +358,8 @@ class OracleRBM:
             dW = (v0_mm.astype(f).T @ h_pos.astype(f) - vn_mm.astype(f).T @ hn_mm.astype(f)).astype(F32)  # :125-126
         dc = (h_pos.astype(f).sum(0) - h_neg.astype(f).sum(0)).astype(F32)  # :131 (the fp32 probabilities)
         db = (v0_mm.astype(f).sum(0) - vn_mm.astype(f).sum(0)).astype(F32)                             # :134
-        return dict(h_pos=h_pos, p_h_pos=p_h_pos, v_neg=v_neg, h_neg=h_neg, dW=dW, dc=dc, db=db, rows=rows)
+        return dict(h_pos=h_pos, p_h_pos=p_h_pos, v_neg=v_neg, h_neg=h_neg, dW=dW, dc=dc, db=db, rows=rows,
+                    row_margin=margin)
 
     def apply(self, st, lr, mask=7, momentum=0.0, weight_decay=0.0, scale=1.0):
         """rbm.py:127-134: parameter += lr * batch SUM (scale = 1).  Extensions: momentum, weight decay
@@ -388,14 +414,18 @@ class OracleRBM:
         self.apply(st, lr, 7, **kw)
         return st
 
-    def reference_step(self, v, draws, lr):
+    def reference_step(self, v, draws, lr, k=1, scale=1.0):
         """rbm.py:214-233 as written: run A updates W, run B (fresh draws, new W) updates c, run C
-        (fresh draws, new W and c) updates b, then the score with a fourth chain (run D).
-        draws = [(u_h, u_v)] * 4."""
+        (fresh draws, new W and c) updates b, then the score with a fourth chain (run D): 5 + 3 + 2 contractions,
+        two free energies and the score chain's two = 14 per minibatch.
+        draws = [(u_h, u_v)] * 4.  With k > 1 (the reference only has CD-1) u_h / u_v of runs A-C are the lists
+        `cd_stats` takes and every run walks the whole CD-k chain: (2k+3) + (2k+1) + 2k + 4 = 6k + 8 contractions."""
         (ah, av), (bh, bv), (ch, cv), (dh, dv) = draws
-        self.apply(self.cd_stats(v, [ah], [None, av]), lr, 1)   # rbm_weight_update_func      :214/:221
-        self.apply(self.cd_stats(v, [bh], [None, bv]), lr, 2)   # hidden_bias_update_func     :215/:222
-        self.apply(self.cd_stats(v, [ch], [None, cv]), lr, 4)   # visible_bias_update_func    :216/:223
+        if k == 1 and not isinstance(ah, (list, tuple)):
+            ah, av, bh, bv, ch, cv = [ah], [None, av], [bh], [None, bv], [ch], [None, cv]
+        self.apply(self.cd_stats(v, ah, av, k=k, need=1), lr, 1, scale=scale)   # rbm_weight_update_func   :214/:221
+        self.apply(self.cd_stats(v, bh, bv, k=k, need=2), lr, 2, scale=scale)   # hidden_bias_update_func  :215/:222
+        self.apply(self.cd_stats(v, ch, cv, k=k, need=4), lr, 4, scale=scale)   # visible_bias_update_func :216/:223
         return self.score(v, dh, dv)
 
     def score(self, v, u_h, u_v):

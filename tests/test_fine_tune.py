@@ -5,9 +5,7 @@ the stack's reconstruction error; (2) DBN.fine_tune drives the engine layer in t
 OracleDBN.up_down_step prescribes - checked by putting an oracle-backed stand-in behind the Machine interface (same
 Philox draw ids as include/kucd.h documents) and comparing the parameters with the oracle's own replay.
 
-GPU part (bottom, `-m gpu`): kucd_rbm_delta_rule against the oracle, and DBN.fine_tune against the oracle replay.  The
-entry point was written after the round's GPU budget was spent, so these run only with KUCD_TEST_UNVERIFIED=1 until the
-first GPU call of the next round has seen them pass (tools/run_round2_switches.sh single)."""
+GPU part (bottom, `-m gpu`): kucd_rbm_delta_rule against the oracle, and DBN.fine_tune against the oracle replay."""
 import os
 
 import numpy as np
@@ -281,10 +279,8 @@ def test_fine_tune_argument_errors(oracle_engine):
 
 
 # ---------------------------------------------------------------------------------------------------------------
-# GPU (unverified until the first GPU call of the next round; see the module docstring)
+# GPU
 # ---------------------------------------------------------------------------------------------------------------
-_unverified = pytest.mark.skipif(os.environ.get("KUCD_TEST_UNVERIFIED", "0") != "1",
-                                 reason="written without a GPU; run with KUCD_TEST_UNVERIFIED=1")
 
 
 @pytest.fixture(scope="module")
@@ -293,7 +289,6 @@ def ctx():
 
 
 @pytest.mark.gpu
-@_unverified
 @pytest.mark.parametrize("dtype,tol", [("f32", 1e-5), ("bf16", 2e-2)])
 @pytest.mark.parametrize("forward", [True, False])
 def test_gpu_delta_rule_matches_the_oracle(ctx, dtype, tol, forward):
@@ -319,7 +314,6 @@ def test_gpu_delta_rule_matches_the_oracle(ctx, dtype, tol, forward):
 
 
 @pytest.mark.gpu
-@_unverified
 def test_gpu_fine_tune_matches_the_oracle_replay(ctx):
     rng = np.random.default_rng(2)
     dims, B, N, k = [200, 96, 64], 64, 160, 1               # 2 full minibatches + a remainder of 32
