@@ -536,6 +536,10 @@ def _main(out):
     def exchange_of(tm_):
         if world == 1:
             return "none (one GPU)"
+        if tm_.get("unit_steps"):
+            return ("unit-sharded: every rank computes its slice of the units for the whole global minibatch, 0/1 states "
+                    "cross NVLink as bits after each projection, dW and the update stay local (%d bit exchanges per step)"
+                    % (tm_["unit_exchanges"] // max(tm_["unit_steps"], 1)))
         if tm_["fused_reduce_steps"]:
             return "fused: dW rows stored into their owners' memory by the contraction epilogue (NVLink), flag barriers"
         return "ncclAllReduce(dW | db | dc)"

@@ -136,6 +136,8 @@ typedef struct kucd_timings {
   int64_t proj_timed, dw_timed; /* launches timed: projections (v.W, h.W^T), dW contractions          */
   float proj_ms, dw_ms;         /* their summed device time                                           */
   float last_gemm_ms;
+  int64_t unit_steps;     /* steps that ran unit-sharded (states exchanged as bits, no dW on the wire)          */
+  int64_t unit_exchanges; /* bit exchanges those steps enqueued (pack + peer stores, flag barrier, expansion)   */
 } kucd_timings;
 
 typedef struct kucd_ctx kucd_ctx;

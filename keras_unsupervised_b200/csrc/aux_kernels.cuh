@@ -694,7 +694,10 @@ struct PeerSet {
   float* bias_slot[8];    // rank j's bias slots: slot s (at s * bias_len) holds rank s's [db | dc]
   uint32_t* flags[8];     // rank j's arrival flags, one per source rank
   __nv_bfloat16* wp[8];   // rank j's bf16 operand plane of W
+  uint8_t* bits[8];       // rank j's bit slots of the unit-sharded exchange (two slots of kBitSlotBytes; nullptr: none)
 };
+
+constexpr int64_t kBitSlotBytes = int64_t{32} << 20;  // 2^28 units: one gathered 0/1 matrix (rows x units) per slot
 
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -803,6 +806,98 @@ __global__ void update_w_sharded_kernel(float* __restrict__ W, const float* __re
     h[3] = __float2bfloat16_rn(w.w);
     const uint2 packed = *reinterpret_cast<const uint2*>(h);
     for (int j = 0; j < n; ++j) (reinterpret_cast<uint2*>(ps.wp[j] + elem0))[i] = packed;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Unit-sharded exchange (kucd.cu, enqueue_cd_units): every rank computes a slice of a layer's units for ALL rows of the
+// global minibatch, and the 0/1 states travel between the ranks as BITS - 1/16 of their bf16 size, 1/32 of float32.
+// ---------------------------------------------------------------------------------------------------
+// The rectangle rows [0, rows) x units [col_lo, col_lo + cols) of a bf16 0/1 plane, packed (unit j of a row = bit j % 8
+// of byte j / 8, as everywhere in this engine) and stored into EVERY rank's slot at rows dst_row0 + r of the gathered
+// (*, pitch_bytes * 8) bit matrix.  A thread packs 8 units (one 16-byte load, coalesced); the block's 256 bytes leave as
+// sixteen 16-byte stores per destination.  cols and col_lo are multiples of 128, so a 16-byte piece never straddles rows.
+// `dyn` (graph replay): the source rows start at dyn->row_off of a resident data set.
+__global__ void __launch_bounds__(256) pack_push_kernel(const __nv_bfloat16* __restrict__ src, int64_t ld,
+                                                        const StepDyn* dyn, int64_t rows, int64_t col_lo, int64_t cols,
+                                                        PeerSet ps, int n, int slot, int64_t dst_row0,
+                                                        int64_t pitch_bytes) {
+  __shared__ __align__(16) uint8_t sh[256];
+  const int64_t row_off = dyn != nullptr ? dyn->row_off : 0;
+  const int64_t groups_per_row = cols / 8;  // bytes of one row of the rectangle
+  const int64_t total = rows * groups_per_row;
+  for (int64_t base = static_cast<int64_t>(blockIdx.x) * 256; base < total; base += static_cast<int64_t>(gridDim.x) * 256) {
+    const int64_t g = base + threadIdx.x;
+    uint32_t b = 0;
+    if (g < total) {
+      const int64_t r = g / groups_per_row, c8 = g - r * groups_per_row;
+      const uint4 q = *reinterpret_cast<const uint4*>(src + (row_off + r) * ld + col_lo + 8 * c8);
+      const Bf16x8 v{{q.x, q.y, q.z, q.w}};
+      b = bf16x8_to_bits(v, 8);
+    }
+    sh[threadIdx.x] = static_cast<uint8_t>(b);
+    __syncthreads();
+    if (threadIdx.x < 16) {
+      const int64_t g16 = base + 16 * threadIdx.x;  // first byte of this 16-byte piece
+      if (g16 < total) {
+        const int64_t r = g16 / groups_per_row, c8 = g16 - r * groups_per_row;
+        const uint4 piece = reinterpret_cast<const uint4*>(sh)[threadIdx.x];
+        const int64_t off = static_cast<int64_t>(slot) * kBitSlotBytes + (dst_row0 + r) * pitch_bytes + (col_lo >> 3) + c8;
+        for (int j = 0; j < n; ++j) *reinterpret_cast<uint4*>(ps.bits[j] + off) = piece;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// The unit-sharded update (rbm.py:127-128 on the columns [h_lo, h_lo + hs) of W that this rank owns): fp32 master and
+// momentum updated locally, the refreshed bf16 values stored into this rank's operand plane (it projects onto these
+// hidden units) and into the plane of the rank that owns visible unit v = row (it projects back onto that visible
+// unit and needs the whole row): the all-to-all that keeps the row slices current is the update kernel's own store
+// stream - V x hs x 2 bytes leave per rank and step instead of a reduce-scatter of V x H partial sums.
+__global__ void update_w_units_kernel(float* __restrict__ W, const float* __restrict__ dW, float* __restrict__ mom,
+                                      PeerSet ps, int me, int64_t ld, int64_t rows, int64_t h_lo, int64_t hs,
+                                      int64_t rows_per_rank, float lr, float scale, float momentum, float weight_decay,
+                                      const StepDyn* sdyn, float world) {
+  scale = step_scale(scale, sdyn, world);
+  const int64_t q_per_row = hs / 4;
+  const int64_t n4 = rows * q_per_row;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t v = i / q_per_row, c4 = i - v * q_per_row;
+    const int64_t off = v * ld + h_lo + 4 * c4;
+    const float4 d = *reinterpret_cast<const float4*>(dW + off);
+    float4* wp = reinterpret_cast<float4*>(W + off);
+    float4 w = *wp;
+    float4 s;
+    s.x = lr * (scale * d.x - weight_decay * w.x);
+    s.y = lr * (scale * d.y - weight_decay * w.y);
+    s.z = lr * (scale * d.z - weight_decay * w.z);
+    s.w = lr * (scale * d.w - weight_decay * w.w);
+    if (mom != nullptr) {
+      float4* mp = reinterpret_cast<float4*>(mom + off);
+      float4 m = *mp;
+      m.x = momentum * m.x + s.x;
+      m.y = momentum * m.y + s.y;
+      m.z = momentum * m.z + s.z;
+      m.w = momentum * m.w + s.w;
+      *mp = m;
+      s = m;
+    }
+    w.x += s.x;
+    w.y += s.y;
+    w.z += s.z;
+    w.w += s.w;
+    *wp = w;
+    __nv_bfloat16 h[4];
+    h[0] = __float2bfloat16_rn(w.x);
+    h[1] = __float2bfloat16_rn(w.y);
+    h[2] = __float2bfloat16_rn(w.z);
+    h[3] = __float2bfloat16_rn(w.w);
+    const uint2 packed = *reinterpret_cast<const uint2*>(h);
+    *reinterpret_cast<uint2*>(ps.wp[me] + off) = packed;
+    const int owner = static_cast<int>(v / rows_per_rank);
+    if (owner != me) *reinterpret_cast<uint2*>(ps.wp[owner] + off) = packed;
   }
 }
 

@@ -277,7 +277,7 @@ __device__ __forceinline__ void epilogue_chunk(const P& p, const uint32_t (&acc)
       const uint32_t d0 = static_cast<uint32_t>(draw), d1 = static_cast<uint32_t>(draw >> 32);
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
-        const Philox4 r = philox4x32_10(static_cast<uint32_t>((col0 >> 2) + q), grow, d0, d1, k0, k1);
+        const Philox4 r = philox4x32_10(static_cast<uint32_t>(((p.col_off + col0) >> 2) + q), grow, d0, d1, k0, k1);
         bits |= (u01_from_bits(r.x) < x[4 * q + 0] ? 1u : 0u) << (4 * q + 0);
         bits |= (u01_from_bits(r.y) < x[4 * q + 1] ? 1u : 0u) << (4 * q + 1);
         bits |= (u01_from_bits(r.z) < x[4 * q + 2] ? 1u : 0u) << (4 * q + 2);
@@ -334,7 +334,7 @@ __device__ __forceinline__ void epilogue_chunk(const P& p, const uint32_t (&acc)
       } else {
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-          const Philox4 r = philox4x32_10(static_cast<uint32_t>((col0 >> 2) + q), grow, d0, d1, k0, k1);
+          const Philox4 r = philox4x32_10(static_cast<uint32_t>(((p.col_off + col0) >> 2) + q), grow, d0, d1, k0, k1);
           float n0, n1, n2, n3;
           box_muller(r.x, r.y, n0, n1);
           box_muller(r.z, r.w, n2, n3);
@@ -506,6 +506,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_bf16_kernel(const __grid_
           const int a_off = ((p.a_dyn_mask >> s) & 1u) ? dyn_row_off : 0;  // A rows: M if K-major, K if MN-major
           for (int kb = 0; kb < p.kblocks; ++kb) {
             ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
+#ifdef KUCD_PROBE
             if (p.dbg_flags & 1u) {
               if (cta_rank == 0) ptx::mbar_arrive(&full_bar[stage]);
               if (++stage == kStages) {
@@ -514,6 +515,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_bf16_kernel(const __grid_
               }
               continue;
             }
+#endif
             if (cta_rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes * CG);
             uint8_t* sa = smem + stage * Cfg::kStageBytes;
             uint8_t* sb = sa + Cfg::kABytes;
@@ -546,12 +548,17 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_bf16_kernel(const __grid_
       // K-major, 128B swizzle : rows of 128 B, 8-row groups 1024 B apart (SBO); a K=16 slice is 32 B along the row.
       // MN-major, 128B swizzle: 64-element MN chunks kBlockK*128 B apart (LBO); 8-k groups 1024 B apart (SBO);
       //                         a K=16 slice is two 8-k groups = 2048 B.
+#ifdef KUCD_PROBE
       const uint32_t lbo_a = p.dbg_lbo_a ? p.dbg_lbo_a : (A_MN ? kBlockK * 128u : 16u);
       const uint32_t sbo_a = p.dbg_sbo_a ? p.dbg_sbo_a : 1024u;
       const uint32_t adv_a = p.dbg_adv_a ? p.dbg_adv_a : (A_MN ? 2048u : 32u);
       const uint32_t lbo_b = p.dbg_lbo_b ? p.dbg_lbo_b : (B_MN ? kBlockK * 128u : 16u);
       const uint32_t sbo_b = p.dbg_sbo_b ? p.dbg_sbo_b : 1024u;
       const uint32_t adv_b = p.dbg_adv_b ? p.dbg_adv_b : (B_MN ? 2048u : 32u);
+#else
+      constexpr uint32_t lbo_a = A_MN ? kBlockK * 128u : 16u, sbo_a = 1024u, adv_a = A_MN ? 2048u : 32u;
+      constexpr uint32_t lbo_b = B_MN ? kBlockK * 128u : 16u, sbo_b = 1024u, adv_b = B_MN ? 2048u : 32u;
+#endif
       constexpr uint32_t idesc_pos = make_idesc(kTileM, BN, A_MN, B_MN, false);
       constexpr uint32_t idesc_neg = make_idesc(kTileM, BN, A_MN, B_MN, true);
       auto commit = [](uint64_t* bar) {
@@ -583,7 +590,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_bf16_kernel(const __grid_
             const uint64_t db = make_smem_desc(sb, lbo_b, sbo_b);
 #pragma unroll
             for (int k = 0; k < kBlockK / 16; ++k) {
+#ifdef KUCD_PROBE
               if (p.dbg_flags & 2u) break;
+#endif
               ptx::mma_bf16<CG>(d_tmem, da + ((k * adv_a) >> 4), db + ((k * adv_b) >> 4), idesc,
                                (in_piece > 0 || k > 0) ? 1u : 0u);
             }

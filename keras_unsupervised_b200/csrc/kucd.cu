@@ -82,6 +82,7 @@ struct NcclApi {
   int (*CommDestroy)(void*) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
   int (*Broadcast)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
   int (*GroupStart)() = nullptr;
   int (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
@@ -105,10 +106,11 @@ static int nccl_load() {
   g_nccl.AllReduce = reinterpret_cast<decltype(g_nccl.AllReduce)>(dlsym(lib, "ncclAllReduce"));
   g_nccl.GetErrorString = reinterpret_cast<decltype(g_nccl.GetErrorString)>(dlsym(lib, "ncclGetErrorString"));
   g_nccl.Broadcast = reinterpret_cast<decltype(g_nccl.Broadcast)>(dlsym(lib, "ncclBroadcast"));
+  g_nccl.AllGather = reinterpret_cast<decltype(g_nccl.AllGather)>(dlsym(lib, "ncclAllGather"));
   g_nccl.GroupStart = reinterpret_cast<decltype(g_nccl.GroupStart)>(dlsym(lib, "ncclGroupStart"));
   g_nccl.GroupEnd = reinterpret_cast<decltype(g_nccl.GroupEnd)>(dlsym(lib, "ncclGroupEnd"));
   if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommDestroy || !g_nccl.AllReduce ||
-      !g_nccl.GetErrorString || !g_nccl.Broadcast || !g_nccl.GroupStart || !g_nccl.GroupEnd)
+      !g_nccl.GetErrorString || !g_nccl.Broadcast || !g_nccl.AllGather || !g_nccl.GroupStart || !g_nccl.GroupEnd)
     return fail(KUCD_ERR_NCCL, "libnccl lacks a required symbol");
   g_nccl.lib = lib;
   return KUCD_OK;
@@ -248,9 +250,12 @@ struct GraphKey {
   kucd_hparams hp{};
   int ds_parts = 0;
   bool fused = false;
+  bool units = false;
+  const void* chains_g = nullptr;
   bool operator==(const GraphKey& o) const {
     return ds == o.ds && ds_id == o.ds_id && ds_ptr == o.ds_ptr && batch == o.batch && global_row0 == o.global_row0 && ds_rows == o.ds_rows &&
-           ds_parts == o.ds_parts && fused == o.fused && memcmp(&hp, &o.hp, sizeof hp) == 0;
+           ds_parts == o.ds_parts && fused == o.fused && units == o.units && chains_g == o.chains_g &&
+           memcmp(&hp, &o.hp, sizeof hp) == 0;
   }
 };
 
@@ -307,6 +312,15 @@ struct kucd_rbm {
   int n_peer_open = 0;
   int64_t rows_per = 0, slice_elems = 0;
   int bias_len = 0;
+  // unit-sharded exchange (enqueue_cd_units): this rank computes the hidden units [me*H/n, (me+1)*H/n) and the visible
+  // units [me*V/n, (me+1)*V/n) for ALL rows of the global minibatch; 0/1 states travel between the ranks as bits
+  bool units_ok = false;     // the arena has bit slots and V, H split into whole 128-unit groups per rank
+  bool units_now = false;    // the current training call runs unit-sharded (decided per call, see choose_exchange)
+  PlaneBuf chains_g;         // persistent chains of the GLOBAL minibatch (every rank holds all of them in this mode)
+  bool chains_g_valid = false;
+  int64_t chains_g_rows = 0;
+  bool units_pcd = false;    // the last unit-sharded step ran persistent chains (its v_neg lives in chains_g)
+  DevBuf gtmp;               // staging of the master gather at the end of a unit-sharded training call
   uint32_t* epoch = nullptr;
   uint64_t seed = 0;  // Philox key; draws are (seed, draw id, global row, column)
   uint64_t step_count = 0, infer_draws = 0, score_draws = 0;
@@ -317,6 +331,7 @@ struct kucd_rbm {
   cudaGraphExec_t graph_exec = nullptr;
   GraphKey graph_key;
   int64_t graph_kernels = 0;  // kernels one replay launches
+  int64_t graph_unit_ex = 0, graph_fused = 0, graph_ar = 0;  // bit exchanges / fused exchanges / all-reduces per replay
   // captured step of the streamed fit (reads the staged minibatch in `vin`)
   cudaGraph_t hgraph = nullptr;
   cudaGraphExec_t hgraph_exec = nullptr;
@@ -387,7 +402,7 @@ static void dataset_planes_release(kucd_ctx* ctx, PlaneBuf& pb) {
 }
 
 // this training call all-reduces dW as bf16 through NCCL (the fused exchange has its own bf16 slots)
-static bool nccl16(const kucd_rbm* r) { return r->wire16 && !r->fused_now && r->ctx->comm != nullptr; }
+static bool nccl16(const kucd_rbm* r) { return r->wire16 && !r->fused_now && !r->units_now && r->ctx->comm != nullptr; }
 
 static size_t prof_event(kucd_ctx* ctx) {
   if (ctx->ev_used == ctx->ev_pool.size()) {
@@ -668,6 +683,12 @@ struct EpiArgs {
   int32_t row_base = 0;  // first minibatch row this launch covers (second chain of a split minibatch)
   cudaStream_t stream = nullptr;  // default: the context stream
   bool no_prof = false;
+  // unit-sharded launches: only the output units [n_lo, n_lo + n_cnt) are computed (n_cnt = 0: all of them); `out`,
+  // the bias and the column sums are still addressed by absolute unit index.  static_rows: with `dyn` set, only the
+  // draw counter comes from the device-resident step state - rows and row indices are the host's (the launch covers the
+  // gathered GLOBAL minibatch, not this rank's shard).
+  int64_t n_lo = 0, n_cnt = 0;
+  bool static_rows = false;
 };
 
 // forward: (rows,V).W + c -> (rows,H) ; backward: (rows,H).W^T + b -> (rows,V)
@@ -677,7 +698,9 @@ static int project(kucd_rbm* r, bool forward, const Planes& a, int64_t rows, con
   ops.a_mn = false;
   ops.b_mn = forward;  // W is (V,H) row-major: (K,N) forward, (N,K) backward
   ops.M = rows;
-  ops.N = forward ? r->H : r->V;
+  const int64_t n_all = forward ? r->H : r->V;
+  const int64_t n_lo = e.n_cnt > 0 ? e.n_lo : 0, n_cnt = e.n_cnt > 0 ? e.n_cnt : n_all;
+  ops.N = n_cnt;
   ops.K = forward ? r->V : r->H;
   int pairs[9][2];
   const int np = term_pairs(a.n, r->wparts, pairs);
@@ -685,21 +708,24 @@ static int project(kucd_rbm* r, bool forward, const Planes& a, int64_t rows, con
   uint32_t dyn_mask = 0;
   for (int s = 0; s < np; ++s) {
     ops.a[s] = MatView{a.p[pairs[s][0]], a.rows, a.cols, a.ld};
-    ops.b[s] = MatView{r->Wp.buf[pairs[s][1]].p, r->V, r->H, r->ldH};
+    const __nv_bfloat16* w = r->Wp.buf[pairs[s][1]].as<__nv_bfloat16>();
+    // the units of this launch: columns of W going forward ((K, N) view), rows of W going back ((N, K) view)
+    ops.b[s] = forward ? MatView{w + n_lo, r->V, n_cnt, r->ldH} : MatView{w + n_lo * r->ldH, n_cnt, r->H, r->ldH};
     if (e.a_dyn) dyn_mask |= 1u << s;
   }
   GemmParams p;
   memset(&p, 0, sizeof p);
-  p.bias = forward ? r->c32.as<float>() : r->b32.as<float>();
-  p.out_bf16 = e.out.p[0];
-  p.out_mid = (e.out.n == 3) ? e.out.p[1] : nullptr;
-  p.out_lo = (e.out.n == 3) ? e.out.p[2] : nullptr;
+  p.bias = (forward ? r->c32.as<float>() : r->b32.as<float>()) + n_lo;
+  p.col_off = static_cast<int32_t>(n_lo);
+  p.out_bf16 = e.out.p[0] + n_lo;
+  p.out_mid = (e.out.n == 3) ? e.out.p[1] + n_lo : nullptr;
+  p.out_lo = (e.out.n == 3) ? e.out.p[2] + n_lo : nullptr;
   p.ld_bf16 = e.out.ld;
-  p.out_f32 = e.out_f32;
+  p.out_f32 = e.out_f32 != nullptr ? e.out_f32 + n_lo : nullptr;
   p.ld_f32 = e.ld_f32;
   p.u_inject = e.u;
   p.ld_u = e.ld_u;
-  p.colsum = e.colsum;
+  p.colsum = e.colsum != nullptr ? e.colsum + n_lo : nullptr;
   p.colsum_sign = e.colsum_sign;
   p.rowsum = e.rowsum;
   p.seed = r->seed;
@@ -708,7 +734,7 @@ static int project(kucd_rbm* r, bool forward, const Planes& a, int64_t rows, con
   p.row0 = e.row0;
   p.m_valid = e.m_valid < 0 ? static_cast<int32_t>(rows) : e.m_valid;
   p.dyn = e.dyn;
-  p.dyn_rows = e.dyn != nullptr ? 1 : 0;
+  p.dyn_rows = (e.dyn != nullptr && !e.static_rows) ? 1 : 0;
   p.dyn_rank = ctx->rank;
   p.dyn_row_base = e.row_base;
   p.a_dyn_mask = dyn_mask;
@@ -728,14 +754,16 @@ static int project(kucd_rbm* r, bool forward, const Planes& a, int64_t rows, con
 // [w_row0, w_row0 + w_rows): the rows of W this launch covers (a column range of the visible states); sm_reserve: SMs
 // left to a concurrent collective (slab-pipelined all-reduce).
 static int delta_w(kucd_rbm* r, const Planes& v0, const Planes& h0, const Planes& vk, const Planes& hk, int64_t rows,
-                   const StepDyn* dyn, bool v0_dyn, int64_t w_row0 = 0, int64_t w_rows = -1, int sm_reserve = 0) {
+                   const StepDyn* dyn, bool v0_dyn, int64_t w_row0 = 0, int64_t w_rows = -1, int sm_reserve = 0,
+                   int64_t h_lo = 0, int64_t h_cnt = -1) {
   kucd_ctx* ctx = r->ctx;
   if (w_rows < 0) w_rows = r->V - w_row0;
+  if (h_cnt < 0) h_cnt = r->H - h_lo;  // [h_lo, h_lo + h_cnt): the columns of W this launch covers (unit-sharded exchange)
   GemmOperands ops;
   ops.a_mn = true;
   ops.b_mn = true;
   ops.M = w_rows;
-  ops.N = r->H;
+  ops.N = h_cnt;
   ops.K = rows;
   int pairs[9][2];
   int ns = 0;
@@ -745,14 +773,14 @@ static int delta_w(kucd_rbm* r, const Planes& v0, const Planes& h0, const Planes
     if (ns + np > kMaxSeg) return fail(KUCD_ERR_INVALID_ARG, "too many operand terms");
     for (int s = 0; s < np; ++s, ++ns) {
       ops.a[ns] = MatView{v0.p[pairs[s][0]] + w_row0, v0.rows, w_rows, v0.ld};
-      ops.b[ns] = MatView{h0.p[pairs[s][1]], h0.rows, h0.cols, h0.ld};
+      ops.b[ns] = MatView{h0.p[pairs[s][1]] + h_lo, h0.rows, h_cnt, h0.ld};
       if (v0_dyn) dyn_mask |= 1u << ns;
     }
     np = term_pairs(vk.n, hk.n, pairs, order);
     if (ns + np > kMaxSeg) return fail(KUCD_ERR_INVALID_ARG, "too many operand terms");
     for (int s = 0; s < np; ++s, ++ns) {
       ops.a[ns] = MatView{vk.p[pairs[s][0]] + w_row0, vk.rows, w_rows, vk.ld};
-      ops.b[ns] = MatView{hk.p[pairs[s][1]], hk.rows, hk.cols, hk.ld};
+      ops.b[ns] = MatView{hk.p[pairs[s][1]] + h_lo, hk.rows, h_cnt, hk.ld};
       neg |= 1u << ns;
     }
   }
@@ -760,7 +788,7 @@ static int delta_w(kucd_rbm* r, const Planes& v0, const Planes& h0, const Planes
   ops.neg_mask = neg;
   GemmParams p;
   memset(&p, 0, sizeof p);
-  p.out_f32 = r->dW() + w_row0 * r->ldH;
+  p.out_f32 = r->dW() + w_row0 * r->ldH + h_lo;
   p.ld_f32 = r->ldH;
   p.m_valid = static_cast<int32_t>(w_rows);
   p.dyn = dyn;
@@ -855,6 +883,36 @@ static int apply_update(kucd_rbm* r, const kucd_hparams* hp, int64_t rows_global
     KU_TRY(r->mW.ensure(static_cast<size_t>(r->V) * r->ldH * 4, true));
     KU_TRY(r->mb.ensure(r->ldVb() * 4, true));
     KU_TRY(r->mc.ensure(r->ldHb() * 4, true));
+  }
+  if (r->units_now) {
+    // unit-sharded step: this rank owns the columns [h_lo, h_lo + Hs) of W, c[h_lo ...] and b[v_lo ...]; its statistics
+    // for them already cover the whole global minibatch, so there is nothing to reduce
+    const int n = ctx->world, me = ctx->rank;
+    const int64_t Hs = r->H / n, Vs = r->V / n, h_lo = me * Hs, v_lo = me * Vs;
+    if (hp->update_mask & KUCD_UPDATE_W) {
+      update_w_units_kernel<<<grid_for(ctx, r->V * Hs / 4, 256), 256, 0, ctx->stream>>>(
+          r->W32.as<float>(), r->dW(), use_mom ? r->mW.as<float>() : nullptr, r->ps, me, r->ldH, r->V, h_lo, Hs, Vs, hp->lr,
+          scale, hp->momentum, hp->weight_decay, sdyn, world);
+      ctx->tm.aux_launches++;
+    }
+    if (hp->update_mask & KUCD_UPDATE_C) {
+      update_bias_kernel<<<(Hs + 255) / 256, 256, 0, ctx->stream>>>(r->c32.as<float>() + h_lo, r->dc() + h_lo,
+                                                                    use_mom ? r->mc.as<float>() + h_lo : nullptr, Hs, hp->lr,
+                                                                    scale, hp->momentum, sdyn, world);
+      ctx->tm.aux_launches++;
+    }
+    if (hp->update_mask & KUCD_UPDATE_B) {
+      update_bias_kernel<<<(Vs + 255) / 256, 256, 0, ctx->stream>>>(r->b32.as<float>() + v_lo, r->db() + v_lo,
+                                                                    use_mom ? r->mb.as<float>() + v_lo : nullptr, Vs, hp->lr,
+                                                                    scale, hp->momentum, sdyn, world);
+      ctx->tm.aux_launches++;
+    }
+    // closes the step: every rank's weights for this rank's back-projection have landed, and every rank is done with the
+    // bit slots (the next step starts again at slot 0)
+    peer_barrier_kernel<<<1, 32, 0, ctx->stream>>>(r->epoch, r->ps, me, n);
+    ctx->tm.aux_launches++;
+    CU_TRY(cudaGetLastError());
+    return KUCD_OK;
   }
   if (r->fused_now) {
     // global [db | dc] = sum of the ranks' slots; the biases are updated identically on every rank
@@ -979,13 +1037,44 @@ static int apply_update(kucd_rbm* r, const kucd_hparams* hp, int64_t rows_global
 // (1024 rows per rank, 512 MiB of dW) 3.13 ms fused vs 2.95 ms NCCL.  Fixed for the whole call: the two paths keep the
 // fp32 master differently between steps.  KUCD_FUSED_MIN_ROWS overrides the threshold.
 // With bf16 partial sums (KUCD_WIRE_BF16=1) half the bytes cross, so the break-even moves to ~1000 rows per rank.
-static void choose_exchange(kucd_rbm* r, int64_t rows_per_rank) {
+//
+// Third option, the UNIT-SHARDED step (enqueue_cd_units): no dW crosses the wire at all.  Rank r computes the hidden units
+// [r H/n, (r+1) H/n) and the visible units [r V/n, (r+1) V/n) for all rows of the GLOBAL minibatch, the sampled 0/1
+// states are exchanged as bits after every projection, dW and the update are local to the owned columns of W, and only
+// the refreshed bf16 weights a peer needs for its back-projection travel (V x H/n x 2 bytes per rank and step).  Against
+// the reduce-scatter + all-gather of V x H partial sums it wins when W is large next to the minibatch - BASELINE's C4
+// (16384 x 8192, 8192 rows over 8 GPUs: 512 MiB of fp32 dW per rank and step against ~60 MiB of bits and weights) - and
+// loses when the minibatch is (C3 weak scaling: 21 exchanges of a 32768-row state matrix).  The estimate below compares
+// the two; KUCD_EXCHANGE=units|dp overrides it.  `hp` == nullptr or !uniform (a remainder minibatch in the range, injected
+// draws, statistics requested): data-parallel.
+static void choose_exchange(kucd_rbm* r, int64_t rows_per_rank, const kucd_hparams* hp = nullptr, bool uniform = false) {
   static const int64_t min_rows_env = [] {
     const char* e = getenv("KUCD_FUSED_MIN_ROWS");
     return e != nullptr ? static_cast<int64_t>(atoll(e)) : static_cast<int64_t>(-1);
   }();
+  const int units_env = [] {  // -1 auto, 0 data-parallel, 1 unit-sharded wherever it can run (read per training call)
+    const char* e = getenv("KUCD_EXCHANGE");
+    if (e == nullptr) return -1;
+    return strcmp(e, "units") == 0 ? 1 : (strcmp(e, "dp") == 0 ? 0 : -1);
+  }();
   const int64_t min_rows = min_rows_env >= 0 ? min_rows_env : (r->wire16 ? 1024 : 2048);
   r->fused_now = r->peer_on && rows_per_rank >= min_rows;
+  r->units_now = false;
+  const int n = r->ctx->world;
+  const int64_t Bg = rows_per_rank * n;
+  if (r->units_ok && hp != nullptr && uniform && units_env != 0 && rows_per_rank % 128 == 0 &&
+      Bg * std::max(r->V, r->H) / 8 <= kBitSlotBytes) {
+    const int k = hp->k, pcd = hp->persistent ? 1 : 0;
+    // data-parallel: (4 + 2) V H (n-1)/n bytes over NVLink at the ~350 GB/s the epilogue stores / NCCL reached at C4
+    const double t_dp = 6.0 * r->V * r->H * (n - 1) / n / 350e9;
+    // unit-sharded: every exchanged state matrix is expanded to bf16 once (HBM writes), plus ~20 us per exchange
+    const double t_un = 2.0 * Bg * (static_cast<double>(r->V) * (k + 1) + static_cast<double>(r->H) * (k + pcd)) / 4e12 +
+                        (2 * k + 2 + pcd) * 20e-6;
+    if (units_env == 1 || t_un < t_dp) {
+      r->units_now = true;
+      r->fused_now = false;
+    }
+  }
 }
 
 // what the chosen exchange needs allocated before a step is enqueued (or captured)
@@ -994,9 +1083,9 @@ static void choose_exchange(kucd_rbm* r, int64_t rows_per_rank) {
 // of W, each slab's ncclAllReduce is enqueued on a second stream as soon as its contraction is, and the update kernel
 // follows slab by slab - contraction, all-reduce and update overlap instead of running back to back (at C4 the three
 // are 0.45 + 1.24 + 0.3 ms of a 2.95 ms step).  The contraction leaves KUCD_AR_RESERVE_SMS SMs (default 16) to NCCL.
-static int prepare_exchange(kucd_rbm* r, int64_t rows_per_rank) {
+static int prepare_exchange(kucd_rbm* r, int64_t rows_per_rank, const kucd_hparams* hp = nullptr, bool uniform = false) {
   kucd_ctx* ctx = r->ctx;
-  choose_exchange(r, rows_per_rank);
+  choose_exchange(r, rows_per_rank, hp, uniform);
   if (nccl16(r)) KU_TRY(r->grad16.ensure(static_cast<size_t>(r->V) * r->ldH * 2, true));
   static const int slabs_env = [] {
     const char* e = getenv("KUCD_AR_SLABS");
@@ -1009,7 +1098,7 @@ static int prepare_exchange(kucd_rbm* r, int64_t rows_per_rank) {
     const char* e = getenv("KUCD_AR_SLABS_MIN_ELEMS");
     return e != nullptr ? static_cast<int64_t>(atoll(e)) : (int64_t{1} << 22);
   }();
-  if (slabs_env > 1 && !r->fused_now && r->compute == KUCD_COMPUTE_BF16 && r->V * r->ldH >= slab_min_elems) {
+  if (slabs_env > 1 && !r->fused_now && !r->units_now && r->compute == KUCD_COMPUTE_BF16 && r->V * r->ldH >= slab_min_elems) {
     const int want = std::min(slabs_env, kucd_ctx::kMaxSlabs);
     const int64_t rows = round_up((r->V + want - 1) / want, 256);
     const int n = static_cast<int>((r->V + rows - 1) / rows);
@@ -1027,8 +1116,58 @@ static int prepare_exchange(kucd_rbm* r, int64_t rows_per_rank) {
 }
 
 // fp32 master rows updated by their owners -> every rank (NCCL broadcasts, at API boundaries only)
+static int refresh_planes(kucd_rbm* r) {
+  kucd_ctx* ctx = r->ctx;
+  const int64_t n4 = r->V * r->ldH / 4;
+  refresh_planes_kernel<<<grid_for(ctx, n4, 256), 256, 0, ctx->stream>>>(
+      r->W32.as<float>(), r->Wp.buf[0].as<__nv_bfloat16>(), r->wparts == 3 ? r->Wp.buf[1].as<__nv_bfloat16>() : nullptr,
+      r->wparts == 3 ? r->Wp.buf[2].as<__nv_bfloat16>() : nullptr, n4);
+  ctx->tm.aux_launches++;
+  CU_TRY(cudaGetLastError());
+  return KUCD_OK;
+}
+
+
+// end of a unit-sharded training call: every rank holds the current values of the columns of W (and the slices of b, c)
+// it owns; bring the fp32 masters and the bf16 operand plane of every rank up to date (API boundary only)
+static int gather_units(kucd_rbm* r) {
+  kucd_ctx* ctx = r->ctx;
+  const int n = ctx->world, me = ctx->rank;
+  const int64_t Hs = r->H / n, Vs = r->V / n;
+  const size_t slice = static_cast<size_t>(r->V) * Hs;  // floats
+  KU_TRY(r->gtmp.ensure(slice * 4 * (n + 1)));
+  float* mine = r->gtmp.as<float>();
+  float* all = mine + slice;
+  CU_TRY(cudaMemcpy2DAsync(mine, Hs * 4, r->W32.as<float>() + me * Hs, r->ldH * 4, Hs * 4, r->V, cudaMemcpyDeviceToDevice,
+                           ctx->stream));
+  int rc = g_nccl.GroupStart();
+  if (rc == 0) rc = g_nccl.AllGather(mine, all, slice, /*ncclFloat32*/ 7, ctx->comm, ctx->stream);
+  if (rc == 0)
+    rc = g_nccl.AllGather(r->b32.as<float>() + me * Vs, r->b32.as<float>(), static_cast<size_t>(Vs), 7, ctx->comm, ctx->stream);
+  if (rc == 0)
+    rc = g_nccl.AllGather(r->c32.as<float>() + me * Hs, r->c32.as<float>(), static_cast<size_t>(Hs), 7, ctx->comm, ctx->stream);
+  const int rc2 = g_nccl.GroupEnd();
+  if (rc != 0 || rc2 != 0) return fail(KUCD_ERR_NCCL, "ncclAllGather: %s", g_nccl.GetErrorString(rc != 0 ? rc : rc2));
+  for (int j = 0; j < n; ++j) {
+    if (j == me) continue;
+    CU_TRY(cudaMemcpy2DAsync(r->W32.as<float>() + j * Hs, r->ldH * 4, all + j * slice, Hs * 4, Hs * 4, r->V,
+                             cudaMemcpyDeviceToDevice, ctx->stream));
+  }
+  KU_TRY(refresh_planes(r));
+  if (r->chains_g_valid && r->n_chains > 0) {  // this rank's chains back into the buffer the API reads
+    const int64_t b = r->chains_g_rows / n;
+    CU_TRY(cudaMemcpyAsync(r->chains.buf[0].p, r->chains_g.buf[0].as<__nv_bfloat16>() + me * b * r->ldV,
+                           static_cast<size_t>(std::min(b, r->n_chains)) * r->ldV * 2, cudaMemcpyDeviceToDevice, ctx->stream));
+    r->chains_g_valid = false;  // the next unit-sharded call gathers them again (the caller may set new ones)
+  }
+  // nobody may start overwriting a plane that a slower rank's refresh... each rank refreshes its OWN plane from its own
+  // master: no cross-rank hazard; the next training call starts with its own barrier
+  return KUCD_OK;
+}
+
 static int gather_master(kucd_rbm* r) {
   kucd_ctx* ctx = r->ctx;
+  if (r->units_now) return gather_units(r);
   if (!r->fused_now) return KUCD_OK;
   int rc = g_nccl.GroupStart();
   for (int o = 0; o < ctx->world && rc == 0; ++o) {
@@ -1233,6 +1372,97 @@ static int launch_chain(kucd_rbm* r, const Planes& v0, int64_t batch, const kucd
   return KUCD_OK;
 }
 
+// One exchange of the unit-sharded step: the rectangle (rows x [col_lo, col_lo + cols)) of `src` goes as bits into every
+// rank's slot, the ranks meet, and the whole gathered bit matrix is expanded into the bf16 plane G (all rows, all units).
+static int units_exchange(kucd_rbm* r, int& ex, const __nv_bfloat16* src, int64_t src_ld, const StepDyn* src_dyn,
+                          int64_t rows, int64_t dst_row0, int64_t col_lo, int64_t cols, const Planes& G) {
+  kucd_ctx* ctx = r->ctx;
+  const int slot = ex++ & 1;
+  const int64_t pitch = G.cols / 8;
+  const int64_t total = rows * cols / 8;
+  pack_push_kernel<<<grid_for(ctx, total, 256), 256, 0, ctx->stream>>>(src, src_ld, src_dyn, rows, col_lo, cols, r->ps,
+                                                                      ctx->world, slot, dst_row0, pitch);
+  peer_barrier_kernel<<<1, 32, 0, ctx->stream>>>(r->epoch, r->ps, ctx->rank, ctx->world);
+  ingest_bits_kernel<<<grid_for(ctx, G.rows * (G.ld / 8), 256), 256, 0, ctx->stream>>>(
+      r->ps.bits[ctx->rank] + static_cast<int64_t>(slot) * kBitSlotBytes, pitch, G.rows, G.cols, G.p[0], nullptr, nullptr,
+      G.ld, 1);
+  ctx->tm.aux_launches += 3;
+  ctx->tm.unit_exchanges++;
+  CU_TRY(cudaGetLastError());
+  return KUCD_OK;
+}
+
+// The CD step of rbm.py:119-126 sharded by UNITS instead of rows (see choose_exchange).  v0_local: this rank's b rows
+// of the global minibatch (rank-contiguous shards: global row = rank * b + i).  Every projection below covers all n*b
+// rows but only this rank's slice of the output units; Philox draws are keyed by (global row, absolute unit), so the
+// sampled states equal a single-GPU run's bit for bit.
+static int enqueue_cd_units(kucd_rbm* r, const Planes& v0_local, int64_t b, const kucd_hparams* hp, int64_t global_row0,
+                            uint64_t step, const StepDyn* dyn, bool v0_dyn) {
+  kucd_ctx* ctx = r->ctx;
+  const int n = ctx->world, me = ctx->rank, k = hp->k;
+  const bool pcd = hp->persistent != 0;
+  const int64_t Bg = b * n, Hs = r->H / n, Vs = r->V / n, h_lo = me * Hs, v_lo = me * Vs;
+  const int64_t base_row0 = global_row0 - me * b;
+  const uint64_t draw0 = step * 64, stride = dyn != nullptr ? 64 : 0;
+  const Planes Gv0 = r->vin.view(Bg, r->V, 1), Gh0 = r->h0.view(Bg, r->H, 1), Ghk = r->hk.view(Bg, r->H, 1);
+  // with persistent chains the negative phase's visible states ARE the chains: the chain's first projection reads them,
+  // the last back-projection overwrites them - no copy
+  const Planes Gvk = pcd ? r->chains_g.view(Bg, r->V, 1) : r->vk.view(Bg, r->V, 1);
+  int ex = 0;
+  // the global minibatch on every rank
+  KU_TRY(units_exchange(r, ex, v0_local.p[0], v0_local.ld, v0_dyn ? dyn : nullptr, b, me * b, 0, r->V, Gv0));
+  CU_TRY(cudaMemsetAsync(r->db(), 0, (r->ldVb() + r->ldHb()) * 4, ctx->stream));
+  {  // db[own visibles] += sum_rows v0   (rbm.py:134)
+    dim3 grid(static_cast<unsigned>((Vs / 2 + 1 + 127) / 128), static_cast<unsigned>((Bg + 63) / 64));
+    colsum_kernel<<<grid, 128, 0, ctx->stream>>>(Gv0.p[0] + v_lo, nullptr, nullptr, Gv0.ld, 0, static_cast<int32_t>(Bg),
+                                                 static_cast<int32_t>(Vs), nullptr, 1.f, r->db() + v_lo);
+    ctx->tm.aux_launches++;
+    CU_TRY(cudaGetLastError());
+  }
+  auto stage = [&](bool forward, const Planes& a, const Planes& out, int epi, int phase, float* colsum, float sign) -> int {
+    EpiArgs e;
+    e.epi = epi;
+    e.out = out;
+    e.colsum = colsum;
+    e.colsum_sign = sign;
+    e.draw = draw0 + phase;
+    e.draw_stride = stride;
+    e.row0 = base_row0;
+    e.dyn = dyn;
+    e.static_rows = true;
+    e.n_lo = forward ? h_lo : v_lo;
+    e.n_cnt = forward ? Hs : Vs;
+    return project(r, forward, a, Bg, e);
+  };
+  auto share_h = [&](const Planes& G) { return units_exchange(r, ex, G.p[0], G.ld, nullptr, Bg, 0, h_lo, Hs, G); };
+  auto share_v = [&](const Planes& G) { return units_exchange(r, ex, G.p[0], G.ld, nullptr, Bg, 0, v_lo, Vs, G); };
+
+  KU_TRY(stage(true, Gv0, Gh0, kEpiSample, 0, r->dc(), 1.f));  // h_pos   rbm.py:120
+  KU_TRY(share_h(Gh0));
+  Planes hcur = Gh0;
+  if (pcd) {  // the negative chain starts at the stored fantasy particles
+    KU_TRY(stage(true, Gvk, Ghk, kEpiSample, 1, nullptr, 0.f));
+    KU_TRY(share_h(Ghk));
+    hcur = Ghk;
+  }
+  for (int t = 1; t <= k; ++t) {
+    const bool last = t == k;
+    KU_TRY(stage(false, hcur, Gvk, kEpiSample, 2 * t, last ? r->db() : nullptr, -1.f));  // rbm.py:121-123
+    KU_TRY(share_v(Gvk));
+    KU_TRY(stage(true, Gvk, Ghk, last ? kEpiProb : kEpiSample, 2 * t + 1, last ? r->dc() : nullptr, -1.f));  // :124
+    if (!last) KU_TRY(share_h(Ghk));
+    hcur = Ghk;
+  }
+  // dW[:, own hidden units] = v0^T h0 - vk^T hk over the whole global minibatch   (rbm.py:125-126)
+  KU_TRY(delta_w(r, Gv0, Gh0, Gvk, Ghk, Bg, nullptr, false, 0, -1, 0, h_lo, Hs));
+  r->last_rows = Bg;
+  r->last_vk_parts = 1;
+  r->last_hk_parts = 1;
+  r->units_pcd = pcd;
+  ctx->tm.unit_steps++;
+  return KUCD_OK;
+}
+
 // v0: the minibatch operand (rows [0,batch) of it, or - with v0_dyn - the rows at dyn->row_off of a data set)
 static int enqueue_cd(kucd_rbm* r, const Planes& v0, int64_t batch, const kucd_hparams* hp, const StepInject* inj,
                       int64_t global_row0, uint64_t step, const StepDyn* dyn, bool v0_dyn) {
@@ -1243,6 +1473,7 @@ static int enqueue_cd(kucd_rbm* r, const Planes& v0, int64_t batch, const kucd_h
   const int epi_v = gaussian ? kEpiGaussian : kEpiSample;
   const uint64_t draw0 = step * 64;
   const uint64_t stride = dyn != nullptr ? 64 : 0;
+  if (r->units_now) return enqueue_cd_units(r, v0, batch, hp, global_row0, step, dyn, v0_dyn);
 
   static const bool merge_small = [] {
     const char* e = getenv("KUCD_MERGE");
@@ -1549,12 +1780,28 @@ static int enqueue_score(kucd_rbm* r, const Planes& v0, int64_t rows, const floa
   return KUCD_OK;
 }
 
+// Before a unit-sharded training call (never inside a capture): workspaces for the GLOBAL minibatch and, with persistent
+// chains, every rank's chains gathered on every rank (chains_g).
+static int prepare_units(kucd_rbm* r, int64_t b, const kucd_hparams* hp);
+static int ensure_chains(kucd_rbm* r, int64_t rows) {
+  if (r->n_chains >= rows) return KUCD_OK;
+  return fail(KUCD_ERR_INVALID_ARG,
+              "persistent CD needs %lld chains but %lld are set (kucd_rbm_set_chains first)", (long long)rows,
+              (long long)r->n_chains);
+}
+
+
 // v0_dyn != nullptr: v0 is a resident block of rows and the minibatch starts at v0_dyn->row_off (graph replay)
 static int enqueue_recon(kucd_rbm* r, const Planes& v0, int64_t rows, const StepDyn* v0_dyn = nullptr) {
   kucd_ctx* ctx = r->ctx;
   float* acc = r->stats.as<float>() + 8;
   CU_TRY(cudaMemsetAsync(acc, 0, 4, ctx->stream));
-  const Planes vk = r->vk.view(rows, r->V, r->last_vk_parts);
+  Planes vk = r->vk.view(rows, r->V, r->last_vk_parts);
+  if (r->units_now) {  // the last step's v_neg of the GLOBAL minibatch: this rank's rows sit at rank * rows
+    vk = (r->chains_g_rows == r->last_rows && r->chains_g.buf[0].p != nullptr && r->units_pcd ? r->chains_g : r->vk)
+             .view(rows, r->V, 1);
+    vk.p[0] += static_cast<int64_t>(ctx->rank) * (r->last_rows / ctx->world) * vk.ld;
+  }
   recon_kernel<<<grid_for(ctx, rows * r->V, 256), 256, 0, ctx->stream>>>(
       v0.p[0], v0.mid(), v0.lo(), v0.ld, 0, vk.p[0], vk.mid(), vk.lo(), vk.ld, static_cast<int32_t>(rows),
       static_cast<int32_t>(r->V), v0_dyn, acc);
@@ -1562,6 +1809,36 @@ static int enqueue_recon(kucd_rbm* r, const Planes& v0, int64_t rows, const Step
                                                 r->stats.as<float>());
   ctx->tm.aux_launches += 2;
   CU_TRY(cudaGetLastError());
+  return KUCD_OK;
+}
+
+static int prepare_units(kucd_rbm* r, int64_t b, const kucd_hparams* hp) {
+  kucd_ctx* ctx = r->ctx;
+  const int n = ctx->world, me = ctx->rank;
+  const int64_t Bg = b * n;
+  KU_TRY(ensure_workspace(r, Bg));
+  if (!hp->persistent) return KUCD_OK;
+  if (r->chains_g_valid && r->chains_g_rows == Bg) return KUCD_OK;
+  KU_TRY(ensure_chains(r, b));
+  if (r->last_vk_parts != 1) return fail(KUCD_ERR_INVALID_ARG, "unit-sharded steps need 0/1 chains");
+  CU_TRY(cudaStreamSynchronize(ctx->stream));
+  const void* before = r->chains_g.buf[0].p;
+  KU_TRY(r->chains_g.ensure(round_up(Bg, 128), r->ldV, 1));
+  if (before != r->chains_g.buf[0].p && r->graph_exec != nullptr) {  // a captured step holds the old pointer
+    cudaGraphExecDestroy(r->graph_exec);
+    cudaGraphDestroy(r->graph);
+    r->graph_exec = nullptr;
+    r->graph = nullptr;
+  }
+  int ex = 0;
+  const Planes G = r->chains_g.view(Bg, r->V, 1);
+  KU_TRY(units_exchange(r, ex, r->chains.buf[0].as<__nv_bfloat16>(), r->ldV, nullptr, b, me * b, 0, r->V, G));
+  // slot parity restarts at 0 inside the step: close this exchange like a step is closed
+  peer_barrier_kernel<<<1, 32, 0, ctx->stream>>>(r->epoch, r->ps, me, n);
+  ctx->tm.aux_launches++;
+  CU_TRY(cudaGetLastError());
+  r->chains_g_valid = true;
+  r->chains_g_rows = Bg;
   return KUCD_OK;
 }
 
@@ -1804,23 +2081,12 @@ int kucd_rbm_destroy(kucd_rbm* r) {
   for (int i = 0; i < r->n_peer_open; ++i) cudaIpcCloseMemHandle(r->peer_open[i]);
   r->arena.release();
   for (DevBuf* b : {&r->W32, &r->b32, &r->c32, &r->mW, &r->mb, &r->mc, &r->grad, &r->fe0, &r->fe1, &r->sp0, &r->sp1,
-                    &r->pstage, &r->stats, &r->flag, &r->dyn, &r->chain_done, &r->grad16})
+                    &r->pstage, &r->stats, &r->flag, &r->dyn, &r->chain_done, &r->grad16, &r->gtmp})
     b->release();
   for (PlaneBuf* p : {&r->Wp, &r->vin, &r->vin2, &r->chunk, &r->ft_in, &r->ft_t, &r->ft_p, &r->h0, &r->hk, &r->vk,
-                      &r->chains})
+                      &r->chains, &r->chains_g})
     p->release();
   delete r;
-  return KUCD_OK;
-}
-
-static int refresh_planes(kucd_rbm* r) {
-  kucd_ctx* ctx = r->ctx;
-  const int64_t n4 = r->V * r->ldH / 4;
-  refresh_planes_kernel<<<grid_for(ctx, n4, 256), 256, 0, ctx->stream>>>(
-      r->W32.as<float>(), r->Wp.buf[0].as<__nv_bfloat16>(), r->wparts == 3 ? r->Wp.buf[1].as<__nv_bfloat16>() : nullptr,
-      r->wparts == 3 ? r->Wp.buf[2].as<__nv_bfloat16>() : nullptr, n4);
-  ctx->tm.aux_launches++;
-  CU_TRY(cudaGetLastError());
   return KUCD_OK;
 }
 
@@ -1869,7 +2135,11 @@ int kucd_rbm_peer_export(kucd_rbm* r, void* handle128) {
   r->rows_per = (r->V + n - 1) / n;
   r->slice_elems = r->rows_per * r->ldH;
   r->bias_len = static_cast<int>(r->ldVb() + r->ldHb());
-  const size_t bytes = (static_cast<size_t>(n) * r->slice_elems + static_cast<size_t>(n) * r->bias_len) * 4 + 1024;
+  // unit-sharded exchange: possible when every rank gets whole 128-unit groups of both layers (a 16-byte piece of a
+  // packed row then never straddles two ranks' slices); costs two bit slots in the arena
+  r->units_ok = r->mode == KUCD_MODE_VISIBLE_BERNOULLI && r->V % (128 * n) == 0 && r->H % (128 * n) == 0;
+  const size_t bytes = (static_cast<size_t>(n) * r->slice_elems + static_cast<size_t>(n) * r->bias_len) * 4 + 1024 +
+                       (r->units_ok ? 2 * static_cast<size_t>(kBitSlotBytes) : 0);
   KU_TRY(r->arena.ensure(bytes, false, /*shareable=*/true));
   CU_TRY(cudaMemset(r->arena.p, 0, r->arena.bytes));
   {  // canary checked by the attaching side: the mapping must start where this allocation starts
@@ -1909,6 +2179,7 @@ int kucd_rbm_peer_attach(kucd_rbm* r, const void* handles) {
     r->ps.dw_slot[j] = static_cast<float*>(pa);
     r->ps.bias_slot[j] = r->ps.dw_slot[j] + static_cast<int64_t>(n) * r->slice_elems;
     r->ps.flags[j] = reinterpret_cast<uint32_t*>(r->ps.bias_slot[j] + static_cast<int64_t>(n) * r->bias_len);
+    r->ps.bits[j] = r->units_ok ? reinterpret_cast<uint8_t*>(r->ps.flags[j]) + 1024 : nullptr;
     r->ps.wp[j] = static_cast<__nv_bfloat16*>(pw);
     uint32_t magic = 0;
     CU_TRY(cudaMemcpy(&magic, r->ps.flags[j] + 128, 4, cudaMemcpyDefault));
@@ -1935,6 +2206,7 @@ int kucd_rbm_peer_detach(kucd_rbm* r) {
   for (int i = 0; i < r->n_peer_open; ++i) cudaIpcCloseMemHandle(r->peer_open[i]);
   r->n_peer_open = 0;
   r->peer_on = false;
+  r->units_ok = false;
   drop_host_graph(r);
   if (r->graph_exec != nullptr) {
     cudaGraphExecDestroy(r->graph_exec);
@@ -2087,13 +2359,6 @@ static int check_hparams(const kucd_hparams* hp) {
   return KUCD_OK;
 }
 
-static int ensure_chains(kucd_rbm* r, int64_t rows) {
-  if (r->n_chains >= rows) return KUCD_OK;
-  return fail(KUCD_ERR_INVALID_ARG,
-              "persistent CD needs %lld chains but %lld are set (kucd_rbm_set_chains first)", (long long)rows,
-              (long long)r->n_chains);
-}
-
 static int read_stats(kucd_rbm* r, kucd_step_stats* stats, int64_t rows) {
   float host[4];
   CU_TRY(cudaMemcpyAsync(host, r->stats.p, sizeof host, cudaMemcpyDeviceToHost, r->ctx->stream));
@@ -2118,9 +2383,18 @@ int kucd_rbm_cd_step(kucd_rbm* r, const kucd_tensor* v_batch, const kucd_hparams
   if (rows > (1 << 22)) return fail(KUCD_ERR_INVALID_ARG, "minibatch of %lld rows", (long long)rows);
   KU_TRY(ensure_workspace(r, rows));
   if (hp->persistent) KU_TRY(ensure_chains(r, rows));
-  KU_TRY(prepare_exchange(r, rows));
+  // (unit-sharded only without injected draws and per-step statistics; every rank passes a shard of the same size)
+  KU_TRY(prepare_exchange(r, rows, hp, inj == nullptr && !(stats != nullptr && hp->want_stats)));
   Planes v0;
-  KU_TRY(ingest_batch(r, v_batch, 0, rows, &v0));
+  if (r->units_now) {
+    // the gathered global minibatch lives in `vin`; this rank's rows are staged in `vin2`
+    KU_TRY(prepare_units(r, rows, hp));
+    KU_TRY(r->vin2.ensure(round_up(rows, 128), r->ldV, 1));
+    v0 = r->vin2.view(rows, r->V, 1);
+    KU_TRY(ingest_rows(ctx, v_batch, 0, rows, v0, 1, nullptr));
+  } else {
+    KU_TRY(ingest_batch(r, v_batch, 0, rows, &v0));
+  }
 
   // injected draws: each node's array is staged to the device up front
   StepInject si;
@@ -2219,6 +2493,7 @@ int kucd_rbm_delta_rule(kucd_rbm* r, int forward, const kucd_tensor* in, const k
     CU_TRY(cudaGetLastError());
   }
   r->fused_now = false;
+  r->units_now = false;
   r->slabs_now = 1;
   r->slabs_inflight = 0;
   if (forward) KU_TRY(delta_w(r, A, T, A, P, rows, nullptr, false));
@@ -2322,6 +2597,7 @@ int kucd_rbm_set_chains(kucd_rbm* r, const kucd_tensor* v_chains) {
   for (int i = 0; i < np; ++i) CU_TRY(cudaMemsetAsync(r->chains.buf[i].p, 0, r->chains.buf[i].bytes, ctx->stream));
   KU_TRY(ingest_rows(ctx, v_chains, 0, n, r->chains.view(n, r->V, np), np, nullptr));
   r->n_chains = n;
+  r->chains_g_valid = false;
   r->last_vk_parts = np;
   drop_host_graph(r);
   if (r->graph_exec != nullptr) {  // chain buffers may have moved
@@ -2491,9 +2767,11 @@ static int fit_range_impl(kucd_rbm* r, kucd_dataset* ds, int64_t batch, const ku
                 (long long)epoch_steps);
   const int64_t steps = step_end - step_begin;
   if (steps == 0) return KUCD_OK;
-  KU_TRY(prepare_exchange(r, batch));
+  // unit-sharded only when every minibatch of the range is a full one and the data set is a single 0/1 plane
+  KU_TRY(prepare_exchange(r, batch, hp, step_end * batch <= N && ds->nparts == 1));
   KU_TRY(ensure_workspace(r, batch));
   if (hp->persistent) KU_TRY(ensure_chains(r, std::min(batch, N)));
+  if (r->units_now) KU_TRY(prepare_units(r, batch, hp));
   if (hp->momentum != 0.f) {  // allocate outside the capture
     KU_TRY(r->mW.ensure(static_cast<size_t>(r->V) * r->ldH * 4, true));
     KU_TRY(r->mb.ensure(r->ldVb() * 4, true));
@@ -2511,6 +2789,8 @@ static int fit_range_impl(kucd_rbm* r, kucd_dataset* ds, int64_t batch, const ku
   key.hp = *hp;
   key.hp.want_stats = 0;
   key.fused = r->fused_now;
+  key.units = r->units_now;
+  key.chains_g = r->units_now ? r->chains_g.buf[0].p : nullptr;
   const Planes v0 = ds->view();
   StepDyn* dyn = r->dyn.as<StepDyn>();
   if (r->graph_exec == nullptr || !(r->graph_key == key)) {
@@ -2522,6 +2802,7 @@ static int fit_range_impl(kucd_rbm* r, kucd_dataset* ds, int64_t batch, const ku
     }
     CU_TRY(cudaStreamSynchronize(ctx->stream));
     const int64_t k0 = ctx->tm.gemm_launches + ctx->tm.aux_launches;
+    const kucd_timings t0 = ctx->tm;
     CU_TRY(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed));
     int rc = enqueue_cd(r, v0, batch, hp, nullptr, global_row0, 0, dyn, true);
     bool advanced = false;
@@ -2548,6 +2829,14 @@ static int fit_range_impl(kucd_rbm* r, kucd_dataset* ds, int64_t batch, const ku
     r->graph_key = key;
     // the launches counted while capturing were recorded, not run: they are what one replay launches
     r->graph_kernels = ctx->tm.gemm_launches + ctx->tm.aux_launches - k0;
+    // the exchange counters were bumped by the capture, which ran nothing: they count executed steps (below)
+    r->graph_unit_ex = ctx->tm.unit_exchanges - t0.unit_exchanges;
+    r->graph_fused = ctx->tm.fused_reduce_steps - t0.fused_reduce_steps;
+    r->graph_ar = ctx->tm.allreduce_calls - t0.allreduce_calls;
+    ctx->tm.unit_exchanges = t0.unit_exchanges;
+    ctx->tm.unit_steps = t0.unit_steps;
+    ctx->tm.fused_reduce_steps = t0.fused_reduce_steps;
+    ctx->tm.allreduce_calls = t0.allreduce_calls;
   }
   set_dyn_kernel<<<1, 1, 0, ctx->stream>>>(dyn, step_begin * batch,
                                            static_cast<int32_t>(std::min(batch, N - step_begin * batch)), r->step_count);
@@ -2558,8 +2847,12 @@ static int fit_range_impl(kucd_rbm* r, kucd_dataset* ds, int64_t batch, const ku
   KU_TRY(gather_master(r));
   ctx->tm.graph_launches += steps;
   ctx->tm.graph_kernel_launches += steps * r->graph_kernels;
+  ctx->tm.unit_exchanges += steps * r->graph_unit_ex;
+  ctx->tm.unit_steps += r->graph_unit_ex > 0 ? steps : 0;
+  ctx->tm.fused_reduce_steps += steps * r->graph_fused;
+  ctx->tm.allreduce_calls += steps * r->graph_ar;
   r->step_count += steps;
-  r->last_rows = batch;
+  r->last_rows = r->units_now ? batch * ctx->world : batch;
   if (stats != nullptr) {
     stats->steps = steps;
     stats->rows = N;

@@ -69,11 +69,16 @@ struct alignas(64) GemmParams {
   // __nv_bfloat16 pointers (cast): half the bytes cross NVLink, the owner still sums the ranks' parts in fp32.
   float* push_base[8];
   int32_t push_rows;  // 0: off, rows are written to out_f32
-  int32_t push_pad;
-  // ---- descriptor overrides used only by the bring-up probe (0 = default) ----
+  int32_t col_off;    // index of output column 0 among the layer's units: a launch that computes a SLICE of the units
+                      // (unit-sharded exchange) draws what the whole-layer launch draws (Philox is keyed by unit index)
+#ifdef KUCD_PROBE
+  // ---- only in the bring-up probe's build (tools/probe_gemm.cu defines KUCD_PROBE): descriptor overrides (0 = default)
+  // and switches that skip work.  libkucd.so is compiled without them: no field of the product's parameter block can
+  // make a timed kernel skip its loads or its MMAs.
   uint32_t dbg_lbo_a, dbg_sbo_a, dbg_adv_a, dbg_lbo_b, dbg_sbo_b, dbg_adv_b;
-  uint32_t dbg_flags;  // probe only: 1 = producer signals "full" without loading (MMA pacing alone),
-                       //             2 = MMA thread commits without multiplying (TMA pacing alone)
+  uint32_t dbg_flags;  // 1 = producer signals "full" without loading (MMA pacing alone),
+                       // 2 = MMA thread commits without multiplying (TMA pacing alone)
+#endif
 };
 
 constexpr int kMaxChainStages = 66;  // 2k+2 projections with k <= 31, + the dW contraction
@@ -110,7 +115,7 @@ struct ChainKind {
   int32_t nseg;
   int32_t map_a2, map_b2;
   int32_t dep2;        // stage that must be complete in ALL its row blocks before segment 1 is loaded
-  int32_t pad;
+  int32_t col_off;     // as GemmParams::col_off (always 0: chain launches cover whole layers)
 };
 
 struct ChainStageRef {

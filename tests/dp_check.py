@@ -23,6 +23,66 @@ from keras_unsupervised_b200.parallel import shard_rows  # noqa: E402
 from oracle import cd_oracle as O  # noqa: E402
 
 
+def units_check(rank, world, local):
+    """The unit-sharded step (KUCD_EXCHANGE=units forced; kucd.cu: enqueue_cd_units): every rank computes a slice of the
+    hidden / visible units for all rows of the global minibatch, states cross as bits, no dW on the wire.  Same draws
+    (global row, absolute unit) and the same fp32 contraction over the whole minibatch as one GPU: parameters must
+    agree with a single-GPU run to reduction-order rounding, and with the oracle.  CD-2, then persistent chains."""
+    os.environ["KUCD_EXCHANGE"] = "units"
+    V, H, b, steps, seed = 2048, 1024, 128, 3, 33          # both layers split into whole 128-unit groups up to 8 ranks
+    B = b * world
+    N = B * steps
+    data = (np.random.default_rng(5).random((N, V)) < 0.3).astype(np.float32)
+    chains0 = (np.random.default_rng(6).random((B, V)) < 0.5).astype(np.float32)
+    W, bb, c = O.OracleRBM.init_params(V, H, seed=7)
+    ok = True
+    for name, hp_kw in (("cd2", dict(k=2)), ("pcd", dict(k=1, persistent=True, momentum=0.5))):
+        ctx = Context(device=local, seed=seed)
+        ctx.join_group(rank, world)
+        m = Machine(ctx, V, H, 0, L.COMPUTE_BF16, seed=seed)
+        m.set_params(W, bb, c)
+        loc, lb, row0 = shard_rows(data, B, rank, world)
+        ds = Dataset.from_array(ctx, loc, L.COMPUTE_BF16)
+        hp = Machine.hparams(lr=1e-3, **hp_kw)
+        if hp_kw.get("persistent"):
+            m.set_chains(chains0[rank * b:(rank + 1) * b])
+        for _ in range(2):
+            m.fit_epoch(ds, lb, hp, global_row0=row0, want_stats=False)
+        m.cd_step(loc[:lb], hp, global_row0=row0)          # a directly launched step after the replayed ones
+        ctx.sync()
+        Wd, bd, cd = m.get_params()
+        ch = m.get_chains(b) if hp_kw.get("persistent") else None
+        t = ctx.timings()
+        if rank == 0:
+            solo_ctx = Context(device=local, seed=seed)
+            solo = Machine(solo_ctx, V, H, 0, L.COMPUTE_BF16, seed=seed)
+            solo.set_params(W, bb, c)
+            sds = Dataset.from_array(solo_ctx, data, L.COMPUTE_BF16)
+            if hp_kw.get("persistent"):
+                solo.set_chains(chains0)
+            for _ in range(2):
+                solo.fit_epoch(sds, B, hp, want_stats=False)
+            solo.cd_step(data[:B], hp)
+            solo_ctx.sync()
+            Ws, bs, cs = solo.get_params()
+            d_solo = float(np.abs(Wd - Ws).max())
+            d_b = max(float(np.abs(bd - bs).max()), float(np.abs(cd - cs).max()))
+            same_chains = True
+            if ch is not None:
+                same_chains = bool(np.array_equal(ch, solo.get_chains(B)[:b]))
+            print("[dp_check] units %s world=%d (unit-sharded steps %d, bit exchanges %d, all-reduces %d)  "
+                  "max|W_units - W_1gpu| = %.3e  max|bias diff| = %.3e  chains equal: %s"
+                  % (name, world, t["unit_steps"], t["unit_exchanges"], t["allreduce_calls"], d_solo, d_b, same_chains),
+                  flush=True)
+            ok &= d_solo < 2e-6 and d_b < 2e-6 and same_chains
+            ok &= t["unit_steps"] == 2 * steps + 1 and t["allreduce_calls"] == 0 and t["fused_reduce_steps"] == 0
+            solo_ctx.close()
+        dist.barrier()
+        ctx.close()
+    os.environ.pop("KUCD_EXCHANGE", None)
+    return ok
+
+
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -78,6 +138,7 @@ def main():
             if name == "bf16" and world <= 8 and os.environ.get("KUCD_FUSED_REDUCE", "1") != "0":
                 ok &= m.fused_reduce and t["fused_reduce_steps"] > 0 and t["allreduce_calls"] == 0
         dist.barrier()
+    ok &= units_check(rank, world, local)
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, src=0)
     dist.destroy_process_group()

@@ -441,6 +441,54 @@ def scenario(name):
             m.fit_epoch(dss[r], 64, hp, global_row0=64 * r, want_stats=False)
         out = snapshot()
         out["timings"] = [c.timings() for c in ctxs]
+    elif name == "units":  # KUCD_EXCHANGE=units: the unit-sharded step over DRY_RANKS in-process ranks
+        n = int(os.environ.get("DRY_RANKS", "2"))
+        os.environ["FAKE_CUDA_DEVICES"] = str(n)
+        ctxs = [Context(device=r, seed=1) for r in range(n)]
+        uid = (C.c_char * 128)()
+        L.check(ctxs[0].lib.kucd_comm_unique_id(uid))
+        for r, c in enumerate(ctxs):
+            L.check(c.lib.kucd_ctx_comm_init(c.handle, bytes(uid), r, n))
+            c.rank, c.world = r, n
+        V, H, b = 128 * n * 2, 128 * n, 128
+        ms = []
+        for c in ctxs:
+            m = Machine.__new__(Machine)
+            m.ctx, m.V, m.H, m.mode, m.compute = c, V, H, L.MODE_VISIBLE_BERNOULLI, L.COMPUTE_BF16
+            h = C.c_void_p()
+            L.check(c.lib.kucd_rbm_create(c.handle, V, H, m.mode, m.compute, C.byref(h)))
+            m.handle, m.fused_reduce = h, False
+            c._children.add(m)
+            m.set_params(np.zeros((V, H), np.float32), np.zeros(V, np.float32), np.zeros(H, np.float32))
+            ms.append(m)
+        handles = []
+        for m in ms:
+            buf = (C.c_char * 128)()
+            L.check(m.ctx.lib.kucd_rbm_peer_export(m.handle, buf))
+            handles.append(bytes(buf))
+        for m in ms:
+            L.check(m.ctx.lib.kucd_rbm_peer_attach(m.handle, b"".join(handles)))
+        dss = [Dataset.from_array(c, data(3 * b, V, seed=5 + r), L.COMPUTE_BF16) for r, c in enumerate(ctxs)]
+        fake.fake_reset()
+        for r, m in enumerate(ms):
+            m.fit_epoch(dss[r], b, Machine.hparams(lr=1e-3, k=2), global_row0=b * r, want_stats=False)
+        out = snapshot()
+        fake.fake_reset()
+        for r, m in enumerate(ms):   # persistent chains, momentum, statistics of the last minibatch, then single steps
+            m.set_chains(data(b, V, seed=9 + r))
+            m.fit_epoch(dss[r], b, Machine.hparams(lr=1e-3, k=1, persistent=True, momentum=0.5, normalize=True),
+                        global_row0=b * r, want_stats=True)
+            m.cd_step(data(b, V, seed=20 + r), Machine.hparams(lr=1e-3, k=1, persistent=True), global_row0=b * r)
+            m.get_chains(b)
+            m.get_params()
+        out["pcd"] = snapshot()
+        fake.fake_reset()
+        for r, m in enumerate(ms):   # a range with a remainder minibatch falls back to the data-parallel exchange
+            ds = Dataset.from_array(m.ctx, data(2 * b + 64, V, seed=30 + r), L.COMPUTE_BF16)
+            m.fit_epoch(ds, b, Machine.hparams(lr=1e-3, k=1), global_row0=b * r, want_stats=False)
+            ds.close()
+        out["remainder"] = snapshot()
+        out["timings"] = [c.timings() for c in ctxs]
     else:
         raise SystemExit("unknown scenario " + name)
     return out

@@ -176,10 +176,31 @@ def test_two_rank_exchange_variants(dry_build, env, dw, exchange, update):
     assert g[4:4 + len(dw) + len(exchange) + len(update)] == dw + exchange + update
     for t in d["timings"]:
         assert t["graph_launches"] == 4
-    if "allreduce" in exchange + dw:
-        assert d["timings"][0]["allreduce_calls"] == 1 and d["timings"][0]["fused_reduce_steps"] == 0
+    if "allreduce" in exchange + dw:   # the counters count executed steps (4 replays), not the one capture
+        assert d["timings"][0]["allreduce_calls"] == 4 and d["timings"][0]["fused_reduce_steps"] == 0
     else:
-        assert d["timings"][0]["fused_reduce_steps"] == 1 and d["timings"][0]["allreduce_calls"] == 0
+        assert d["timings"][0]["fused_reduce_steps"] == 4 and d["timings"][0]["allreduce_calls"] == 0
+
+
+@pytest.mark.parametrize("ranks", [2, 4, 8])
+def test_unit_sharded_step_over_in_process_ranks(dry_build, ranks):
+    """KUCD_EXCHANGE=units (kucd.cu: enqueue_cd_units): per projection one launch over the rank's slice of the units and all
+    rows of the global minibatch, then pack + peer stores, flag barrier, expansion; dW over the owned columns, the
+    unit-sharded update, a closing barrier.  Every tensor map, slice pointer, bias chunk and column-sum pointer of the
+    sliced launches passes the fake's checks; a range with a remainder minibatch falls back to the all-reduce."""
+    d = run("units", KUCD_EXCHANGE="units", DRY_RANKS=ranks)
+    for part in (d, d["pcd"], d["remainder"]):
+        assert part["errors"] == [], part["errors"][:10]
+    ex = ["pack_push_kernel", "peer_barrier_kernel", "ingest_bits_kernel"]
+    g = [k.split("<")[0] for k in d["graph"]]
+    gemm = "gemm_bf16_kernel"
+    assert g == ex + ["memset", "colsum_kernel", gemm] + ex + [gemm] + ex + [gemm] + ex + [gemm] + ex + [gemm, gemm] + \
+        ["update_w_units_kernel", "update_bias_kernel", "update_bias_kernel", "peer_barrier_kernel", "advance_dyn_kernel"]
+    gp = [k.split("<")[0] for k in d["pcd"]["graph"]]
+    assert gp.count("pack_push_kernel") == 4 and gp.count(gemm) == 5 and "copy_rows_kernel" not in gp
+    assert "allreduce" in d["remainder"]["graph"] and "pack_push_kernel" not in d["remainder"]["graph"]
+    t = d["timings"][0]
+    assert t["unit_steps"] == 3 + 3 + 1 and t["unit_exchanges"] == 3 * 5 + 3 * 4 + 4 + 2   # + one gather of the chains per training call
 
 
 def _allreduces(d):

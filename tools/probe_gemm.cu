@@ -6,6 +6,7 @@
 //
 // One configuration per process: a protocol bug traps the context, and the next
 // case must start from a clean one.
+#define KUCD_PROBE 1  // the descriptor overrides and work-skipping switches exist only in this binary
 #include <cuda_runtime.h>
 
 #include <cstdio>
