@@ -143,9 +143,12 @@ __host__ __device__ __forceinline__ uint32_t bf16x8_to_bits(const Bf16x8& v, int
 // Packed rows -> bf16 planes.  One source byte (8 columns = one 16-byte store) per thread and iteration, four
 // iterations' loads in flight; 1/8 B read + 2 B written per unit, against 4 + 2 B for float32 input: a binary data
 // set crosses PCIe and HBM 32x smaller than as float32.
+// [skip_lo, skip_hi): columns (multiples of 8) that are left untouched - the unit-sharded exchange expands the peers'
+// slices of a gathered state matrix around the slice this rank computed itself, which is already in place.
 __global__ void ingest_bits_kernel(const uint8_t* __restrict__ src, int64_t src_pitch, int64_t rows, int64_t cols,
                                    __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ mid,
-                                   __nv_bfloat16* __restrict__ lo, int64_t ld, int nparts) {
+                                   __nv_bfloat16* __restrict__ lo, int64_t ld, int nparts, int64_t skip_lo = 0,
+                                   int64_t skip_hi = 0) {
   const int64_t groups_per_row = ld / 8;
   const int64_t total = rows * groups_per_row;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
@@ -165,9 +168,11 @@ __global__ void ingest_bits_kernel(const uint8_t* __restrict__ src, int64_t src_
       if (g < total) {
         const int64_t r = w[u].r, c0 = static_cast<int64_t>(w[u].rem) * 8;
         const int64_t left = cols - c0;  // columns of this group that exist
-        if (left > 0) b[u] = __ldg(src + r * src_pitch + (c0 >> 3));
-        valid[u] = left >= 8 ? 8 : (left > 0 ? static_cast<int>(left) : 0);
-        off[u] = r * ld + c0;
+        if (c0 < skip_lo || c0 >= skip_hi) {
+          if (left > 0) b[u] = __ldg(src + r * src_pitch + (c0 >> 3));
+          valid[u] = left >= 8 ? 8 : (left > 0 ? static_cast<int>(left) : 0);
+          off[u] = r * ld + c0;
+        }
       }
       w[u].advance();
     }

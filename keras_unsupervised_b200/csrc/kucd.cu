@@ -135,10 +135,26 @@ struct DevBuf {
     if (zero) CU_TRY(cudaMemset(p, 0, n));
     return KUCD_OK;
   }
+  // Stream-ordered variant (data-set planes): cudaMallocAsync / cudaFreeAsync on the engine stream.  The device's memory
+  // pool keeps freed blocks (release threshold = unlimited, set at context creation), so a transform of a small data set
+  // does not pay ~0.3 ms of cudaMalloc + a device-wide synchronising cudaFree around a 30 us contraction.
+  cudaStream_t pool_stream = nullptr;
+  int ensure_async(size_t n, cudaStream_t st) {
+    if (n <= bytes) return KUCD_OK;
+    release();
+    CU_TRY(cudaMallocAsync(&p, n, st));
+    bytes = n;
+    pool_stream = st;
+    return KUCD_OK;
+  }
   void release() {
-    if (p != nullptr) cudaFree(p);
+    if (p != nullptr) {
+      if (pool_stream != nullptr) cudaFreeAsync(p, pool_stream);  // ordered after every kernel enqueued so far
+      else cudaFree(p);
+    }
     p = nullptr;
     bytes = 0;
+    pool_stream = nullptr;
   }
   template <typename T>
   T* as() const {
@@ -166,9 +182,6 @@ struct kucd_ctx {
   cudaStream_t stream2 = nullptr;  // second Gibbs chain of a split minibatch
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaStream_t copy_stream = nullptr;  // host -> device staging of the next minibatch (fit_host)
-  // KUCD_PLANE_POOL=1: plane buffers of destroyed data sets, kept for the next data set (see pool_take / pool_give)
-  std::vector<DevBuf> plane_pool;
-  size_t plane_pool_bytes = 0;
   // slab-pipelined all-reduce (KUCD_AR_SLABS): dW leaves in row slabs on comm_stream while the next slab is contracted
   static constexpr int kMaxSlabs = 16;
   cudaStream_t comm_stream = nullptr;
@@ -353,53 +366,16 @@ static void drop_host_graph(kucd_rbm* r) {
   r->hgraph = nullptr;
 }
 
-// Free list of data-set plane buffers (KUCD_PLANE_POOL=1; off by default until measured).  A transform of a small
-// data set is 30-120 us of contraction behind ~0.4 ms of cudaMalloc for its output (and a device-wide cudaFree when the
-// result is closed).  Every kernel that touches data-set planes runs in order on the context's stream (forked work
-// joins it before a step ends), so a buffer given back can be handed out again without waiting for anything.
-static bool plane_pool_on() {
-  static const bool on = [] {
-    const char* e = getenv("KUCD_PLANE_POOL");
-    return e != nullptr && e[0] == '1';
-  }();
-  return on;
-}
-static constexpr size_t kPlanePoolCap = size_t{2} << 30;  // bytes kept at most
-static void pool_take(kucd_ctx* ctx, DevBuf& b, size_t need) {
-  if (!plane_pool_on() || b.bytes >= need) return;
-  int best = -1;
-  for (size_t i = 0; i < ctx->plane_pool.size(); ++i) {
-    const size_t have = ctx->plane_pool[i].bytes;
-    if (have >= need && have <= 2 * need + (size_t{1} << 20) &&
-        (best < 0 || have < ctx->plane_pool[static_cast<size_t>(best)].bytes))
-      best = static_cast<int>(i);
-  }
-  if (best < 0) return;
-  b.release();
-  b = ctx->plane_pool[static_cast<size_t>(best)];
-  ctx->plane_pool_bytes -= b.bytes;
-  ctx->plane_pool.erase(ctx->plane_pool.begin() + best);
-}
-static void pool_give(kucd_ctx* ctx, DevBuf& b) {
-  if (b.p == nullptr) return;
-  if (plane_pool_on() && b.bytes <= kPlanePoolCap / 4 && ctx->plane_pool_bytes + b.bytes <= kPlanePoolCap &&
-      ctx->plane_pool.size() < 64) {
-    ctx->plane_pool.push_back(b);
-    ctx->plane_pool_bytes += b.bytes;
-    b.p = nullptr;
-    b.bytes = 0;
-    return;
-  }
-  b.release();
-}
-// the planes of a data set: from the free list when one fits, else cudaMalloc
+// The planes of a data set come from the device's stream-ordered memory pool (DevBuf::ensure_async).  Every kernel that
+// touches data-set planes runs in order on the context's stream (forked work joins it before a step ends), so a block
+// freed in stream order can be handed out again without waiting for anything.
 static int dataset_planes(kucd_ctx* ctx, PlaneBuf& pb, int64_t rows, int64_t ld, int nplanes) {
-  for (int i = 0; i < nplanes; ++i) pool_take(ctx, pb.buf[i], static_cast<size_t>(rows) * ld * 2);
-  return pb.ensure(rows, ld, nplanes);
+  for (int i = 0; i < nplanes; ++i) KU_TRY(pb.buf[i].ensure_async(static_cast<size_t>(rows) * ld * 2, ctx->stream));
+  pb.rows = rows;
+  pb.ld = ld;
+  return KUCD_OK;
 }
-static void dataset_planes_release(kucd_ctx* ctx, PlaneBuf& pb) {
-  for (auto& b : pb.buf) pool_give(ctx, b);
-}
+static void dataset_planes_release(kucd_ctx*, PlaneBuf& pb) { pb.release(); }
 
 // this training call all-reduces dW as bf16 through NCCL (the fused exchange has its own bf16 slots)
 static bool nccl16(const kucd_rbm* r) { return r->wire16 && !r->fused_now && !r->units_now && r->ctx->comm != nullptr; }
@@ -1374,8 +1350,10 @@ static int launch_chain(kucd_rbm* r, const Planes& v0, int64_t batch, const kucd
 
 // One exchange of the unit-sharded step: the rectangle (rows x [col_lo, col_lo + cols)) of `src` goes as bits into every
 // rank's slot, the ranks meet, and the whole gathered bit matrix is expanded into the bf16 plane G (all rows, all units).
+// in_place: the rectangle was computed into G itself (a slice of the units, all rows) - it is not expanded again.
 static int units_exchange(kucd_rbm* r, int& ex, const __nv_bfloat16* src, int64_t src_ld, const StepDyn* src_dyn,
-                          int64_t rows, int64_t dst_row0, int64_t col_lo, int64_t cols, const Planes& G) {
+                          int64_t rows, int64_t dst_row0, int64_t col_lo, int64_t cols, const Planes& G,
+                          bool in_place = false) {
   kucd_ctx* ctx = r->ctx;
   const int slot = ex++ & 1;
   const int64_t pitch = G.cols / 8;
@@ -1385,7 +1363,7 @@ static int units_exchange(kucd_rbm* r, int& ex, const __nv_bfloat16* src, int64_
   peer_barrier_kernel<<<1, 32, 0, ctx->stream>>>(r->epoch, r->ps, ctx->rank, ctx->world);
   ingest_bits_kernel<<<grid_for(ctx, G.rows * (G.ld / 8), 256), 256, 0, ctx->stream>>>(
       r->ps.bits[ctx->rank] + static_cast<int64_t>(slot) * kBitSlotBytes, pitch, G.rows, G.cols, G.p[0], nullptr, nullptr,
-      G.ld, 1);
+      G.ld, 1, in_place ? col_lo : 0, in_place ? col_lo + cols : 0);
   ctx->tm.aux_launches += 3;
   ctx->tm.unit_exchanges++;
   CU_TRY(cudaGetLastError());
@@ -1434,8 +1412,8 @@ static int enqueue_cd_units(kucd_rbm* r, const Planes& v0_local, int64_t b, cons
     e.n_cnt = forward ? Hs : Vs;
     return project(r, forward, a, Bg, e);
   };
-  auto share_h = [&](const Planes& G) { return units_exchange(r, ex, G.p[0], G.ld, nullptr, Bg, 0, h_lo, Hs, G); };
-  auto share_v = [&](const Planes& G) { return units_exchange(r, ex, G.p[0], G.ld, nullptr, Bg, 0, v_lo, Vs, G); };
+  auto share_h = [&](const Planes& G) { return units_exchange(r, ex, G.p[0], G.ld, nullptr, Bg, 0, h_lo, Hs, G, true); };
+  auto share_v = [&](const Planes& G) { return units_exchange(r, ex, G.p[0], G.ld, nullptr, Bg, 0, v_lo, Vs, G, true); };
 
   KU_TRY(stage(true, Gv0, Gh0, kEpiSample, 0, r->dc(), 1.f));  // h_pos   rbm.py:120
   KU_TRY(share_h(Gh0));
@@ -1885,6 +1863,14 @@ int kucd_ctx_create(kucd_ctx** out, int device_id, uint64_t seed) {
     return fail(KUCD_ERR_NOT_SM100, "device %d (%s) is sm_%d%d; the kernels are sm_100a only", device_id, prop.name,
                 prop.major, prop.minor);
   CU_TRY(cudaSetDevice(device_id));
+  {  // freed data-set planes stay in the device's pool for the next data set (see dataset_planes)
+    cudaMemPool_t pool = nullptr;
+    if (cudaDeviceGetDefaultMemPool(&pool, device_id) == cudaSuccess && pool != nullptr) {
+      uint64_t keep = UINT64_MAX;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    cudaGetLastError();
+  }
   kucd_ctx* c = new (std::nothrow) kucd_ctx();
   if (c == nullptr) return fail(KUCD_ERR_INVALID_ARG, "out of host memory");
   c->device = device_id;
@@ -1931,8 +1917,6 @@ int kucd_ctx_destroy(kucd_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->stream != nullptr) cudaStreamSynchronize(ctx->stream);
   if (ctx->comm != nullptr && g_nccl.CommDestroy != nullptr) g_nccl.CommDestroy(ctx->comm);
-  for (auto& b : ctx->plane_pool) b.release();
-  ctx->plane_pool.clear();
   ctx->stage_in.release();
   ctx->stage_u.release();
   ctx->stage_out.release();
@@ -2668,12 +2652,7 @@ int kucd_dataset_create(kucd_ctx* ctx, const kucd_tensor* data, int compute, kuc
 int kucd_dataset_destroy(kucd_dataset* ds) {
   if (ds == nullptr) return KUCD_OK;
   cudaSetDevice(ds->ctx->device);
-  if (plane_pool_on()) {
-    dataset_planes_release(ds->ctx, ds->planes);  // stream order protects the next user of these buffers
-  } else {
-    cudaStreamSynchronize(ds->ctx->stream);
-    ds->planes.release();
-  }
+  dataset_planes_release(ds->ctx, ds->planes);  // freed in stream order: no synchronisation
   delete ds;
   return KUCD_OK;
 }

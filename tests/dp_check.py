@@ -28,6 +28,8 @@ def units_check(rank, world, local):
     hidden / visible units for all rows of the global minibatch, states cross as bits, no dW on the wire.  Same draws
     (global row, absolute unit) and the same fp32 contraction over the whole minibatch as one GPU: parameters must
     agree with a single-GPU run to reduction-order rounding, and with the oracle.  CD-2, then persistent chains."""
+    if os.environ.get("KUCD_FUSED_REDUCE", "1") == "0":
+        return True                                        # no peer-mapped memory in this run: nothing to exchange bits through
     os.environ["KUCD_EXCHANGE"] = "units"
     V, H, b, steps, seed = 2048, 1024, 128, 3, 33          # both layers split into whole 128-unit groups up to 8 ranks
     B = b * world

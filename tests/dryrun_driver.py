@@ -54,7 +54,7 @@ def snapshot():
             "graph_raw": _lines(fake.fake_last_graph_size, fake.fake_last_graph_line),
             "errors": _lines(fake.fake_error_count, fake.fake_error_line),
             "decoded": fake.fake_counter(5), "mallocs": fake.fake_counter(0), "frees": fake.fake_counter(1), "live_bytes": fake.fake_counter(2),
-            "peak_bytes": fake.fake_counter(3)}
+            "peak_bytes": fake.fake_counter(3), "async_allocs": fake.fake_counter(6)}
 
 
 def machine(ctx, V, H, compute=L.COMPUTE_BF16, mode=L.MODE_VISIBLE_BERNOULLI):
@@ -364,7 +364,7 @@ def scenario(name):
         fake.fake_reset()
         st = m.fit_host(X, 128, Machine.hparams(lr=1e-3, k=2))          # a second pass reuses the captured step
         out["second"] = snapshot()
-    elif name == "transform_loop":  # KUCD_PLANE_POOL
+    elif name == "transform_loop":  # data-set planes from the stream-ordered pool
         ctx = Context(device=0, seed=1)
         m = machine(ctx, 512, 256)
         ds = Dataset.from_array(ctx, data(1024, 512), L.COMPUTE_BF16)

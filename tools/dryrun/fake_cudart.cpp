@@ -39,6 +39,7 @@ std::map<const void*, std::string> g_funcs;  // host stub -> mangled kernel name
 std::vector<std::string> g_log;
 std::vector<std::string> g_errors;
 size_t g_malloc_calls = 0, g_free_calls = 0, g_live_bytes = 0, g_peak_bytes = 0;
+long g_async_allocs = 0;  // cudaMallocAsync calls
 long g_fail_malloc_in = 0;  // > 0: that many cudaMalloc calls from now, one fails (fault injection for the error paths)
 size_t g_decoded_launches = 0;  // contraction launches whose parameter block was decoded and checked
 int g_device = 0;
@@ -492,6 +493,7 @@ void fake_reset() {
   g_log.clear();
   g_errors.clear();
   g_malloc_calls = g_free_calls = 0;
+  g_async_allocs = 0;
   g_decoded_launches = 0;
   g_peak_bytes = g_live_bytes;
 }
@@ -524,6 +526,7 @@ long long fake_counter(int which) {  // 0 cudaMalloc calls, 1 cudaFree calls, 2 
     case 2: return static_cast<long long>(g_live_bytes);
     case 3: return static_cast<long long>(g_peak_bytes);
     case 5: return static_cast<long long>(g_decoded_launches);
+    case 6: return static_cast<long long>(g_async_allocs);
     default: return static_cast<long long>(g_allocs.size());
   }
 }
@@ -638,6 +641,29 @@ cudaError_t cudaFree(void* p) {
   free(p);
   return cudaSuccess;
 }
+// stream-ordered allocation: the same table (bounds checks see these blocks), separate call counters
+cudaError_t cudaMallocAsync(void** p, size_t n, cudaStream_t) {
+  const cudaError_t e = cudaMalloc(p, n);
+  if (e == cudaSuccess) {
+    LOCK;
+    g_malloc_calls--;
+    g_async_allocs++;
+  }
+  return e;
+}
+cudaError_t cudaFreeAsync(void* p, cudaStream_t) {
+  const cudaError_t e = cudaFree(p);
+  if (e == cudaSuccess && p != nullptr) {
+    LOCK;
+    g_free_calls--;
+  }
+  return e;
+}
+cudaError_t cudaDeviceGetDefaultMemPool(cudaMemPool_t* pool, int) {
+  *pool = reinterpret_cast<cudaMemPool_t>(static_cast<uintptr_t>(0x9000));
+  return cudaSuccess;
+}
+cudaError_t cudaMemPoolSetAttribute(cudaMemPool_t, cudaMemPoolAttr, void*) { return cudaSuccess; }
 cudaError_t cudaHostAlloc(void** p, size_t n, unsigned) {
   *p = malloc(n == 0 ? 1 : n);
   return *p != nullptr ? cudaSuccess : cudaErrorMemoryAllocation;
