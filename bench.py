@@ -692,6 +692,12 @@ def _main(out):
                     "traffic": traffic, "launch_ms": per_launch_ms, "launches_timed": n_timed,
                     "projections_per_launch": n_proj if chain else None, "flop_per_launch": flop,
                     "dw_launch_ms": (tp["dw_ms"] / tp["dw_timed"]) if tp["dw_timed"] else None,
+                    "step_breakdown_ms": {
+                        "what": "device time per directly launched step, by kernel class (CUDA events around each class; "
+                                "the replayed step of the timed region runs the same kernels)",
+                        "projections": tp["proj_ms"] / n_prof, "dW": tp["dw_ms"] / n_prof,
+                        "bit_exchanges": tp.get("xchg_ms", 0.0) / n_prof, "n_bit_exchanges": tp.get("xchg_timed", 0) // n_prof,
+                        "update_and_closing_barrier": tp.get("upd_ms", 0.0) / n_prof},
                     "step_tflops": step_tf, "step_frac": step_tf / peak,
                     "step_frac_of_burst_peak": step_tf / pk["burst"],
                     "step_frac_of_sustained_peak": step_tf / pk["sustained"]}

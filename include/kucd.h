@@ -138,6 +138,8 @@ typedef struct kucd_timings {
   float last_gemm_ms;
   int64_t unit_steps;     /* steps that ran unit-sharded (states exchanged as bits, no dW on the wire)          */
   int64_t unit_exchanges; /* bit exchanges those steps enqueued (pack + peer stores, flag barrier, expansion)   */
+  int64_t xchg_timed, upd_timed; /* with kucd_ctx_set_profile(1): bit exchanges / parameter updates timed        */
+  float xchg_ms, upd_ms;         /* their summed device time (pack + barrier + expansion; update kernels + barrier) */
 } kucd_timings;
 
 typedef struct kucd_ctx kucd_ctx;

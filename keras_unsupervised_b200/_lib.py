@@ -68,7 +68,8 @@ class Timings(C.Structure):
                 ("graph_kernel_launches", C.c_int64), ("allreduce_calls", C.c_int64), ("fused_reduce_steps", C.c_int64), ("h2d_bytes", C.c_int64),
                 ("d2h_bytes", C.c_int64), ("proj_timed", C.c_int64), ("dw_timed", C.c_int64),
                 ("proj_ms", C.c_float), ("dw_ms", C.c_float), ("last_gemm_ms", C.c_float),
-                ("unit_steps", C.c_int64), ("unit_exchanges", C.c_int64)]
+                ("unit_steps", C.c_int64), ("unit_exchanges", C.c_int64), ("xchg_timed", C.c_int64),
+                ("upd_timed", C.c_int64), ("xchg_ms", C.c_float), ("upd_ms", C.c_float)]
 
 
 _P = C.c_void_p

@@ -38,7 +38,11 @@ __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
 // GAUSS: the epilogue set of the Gaussian-visible mode (relu-threshold hiddens, rbm.py:58-59; v ~ N(h.W^T + b, I),
 // rbm.py:64-66; the final hidden term stays the sigmoid, rbm.py:145) - a separate instantiation, so that the
 // Bernoulli kernel's code and register allocation are exactly what they were.
-template <int BN, int CG, bool GAUSS = false>
+// CH > 0: float32-grade mode (three bf16 term planes of W, see gemm.cuh): a projection is kd.nseg K-segments over the
+// same A operand and the planes kd.map_b (smallest term first), kd.map_b2, kd.map_b3, and the accumulation is cut every
+// CH k-blocks - each piece accumulates from zero in one of the two tensor-memory buffers, the epilogue warps add the
+// pieces in registers with IEEE fp32 adds (BN / 2 partial sums per thread) and run the fused epilogue on the total.
+template <int BN, int CG, bool GAUSS = false, int CH = 0>
 __global__ void __launch_bounds__(kNumThreads, 1) chain_kernel(const __grid_constant__ ChainParams p) {
   constexpr int kBNLocal = BN / CG;
   constexpr int kTileM = kBlockM * CG;
@@ -72,7 +76,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) chain_kernel(const __grid_cons
     draw_base += p.dyn->step * p.draw_stride;
   }
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0 && lane == 0 && p.total_tiles > 0) {  // (an empty launch - the host's cooperative-launch probe - has no maps)
     for (int i = 0; i < kChainMaps; ++i) ptx::prefetch_tensormap(&p.maps[i]);
   }
   if (warp == 1) {
@@ -145,13 +149,15 @@ __global__ void __launch_bounds__(kNumThreads, 1) chain_kernel(const __grid_cons
         const int m0 = m_blk * kTileM + static_cast<int>(cta_rank) * kBlockM;
         const int n0 = n_blk * BN + static_cast<int>(cta_rank) * kBNLocal;
         for (int seg = 0; seg < kd.nseg; ++seg) {
-          if (seg == 1) {
+          if (CH == 0 && seg == 1) {
             for (int mb = 0; mb < p.num_m_batch; ++mb) wait_block(kd.dep2, mb);
             ptx::fence_proxy_async_global();
           }
-          const CUtensorMap* ma = &p.maps[seg == 0 ? kd.map_a : kd.map_a2];
-          const CUtensorMap* mb = &p.maps[seg == 0 ? kd.map_b : kd.map_b2];
-          const int a_off = (kd.a_dyn && seg == 0) ? dyn_row_off : 0;  // data-set rows: M if K-major, K if MN-major
+          const CUtensorMap* ma = &p.maps[(CH > 0 || seg == 0) ? kd.map_a : kd.map_a2];
+          const CUtensorMap* mb = &p.maps[seg == 0 ? kd.map_b : (seg == 1 ? kd.map_b2 : kd.map_b3)];
+          // data-set rows: M if K-major, K if MN-major (the dW stage reads the data set in its first segment only; at
+          // float32 grade every segment multiplies the same A operand)
+          const int a_off = (kd.a_dyn && (CH > 0 || seg == 0)) ? dyn_row_off : 0;
           for (int kb = 0; kb < kd.kblocks; ++kb) {
             ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
             if (cta_rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes * CG);
@@ -198,13 +204,45 @@ __global__ void __launch_bounds__(kNumThreads, 1) chain_kernel(const __grid_cons
         const uint32_t idesc_neg = make_idesc(kTileM, BN, a_mn, b_mn, true);
         const uint32_t lbo_a = a_mn ? kBlockK * 128u : 16u, adv_a = a_mn ? 2048u : 32u;
         const uint32_t lbo_b = b_mn ? kBlockK * 128u : 16u, adv_b = b_mn ? 2048u : 32u;
-        const uint32_t as = accn & 1u;
-        ptx::mbar_wait(&tmem_empty_bar[as], ((accn >> 1) & 1u) ^ 1u);
-        ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * BN;
-        for (int seg = 0; seg < kd.nseg; ++seg) {
-          const uint32_t idesc = seg == 1 ? idesc_neg : idesc_pos;  // second segment: -vk^T hk
-          for (int kb = 0; kb < kd.kblocks; ++kb) {
+        if constexpr (CH == 0) {
+          const uint32_t as = accn & 1u;
+          ptx::mbar_wait(&tmem_empty_bar[as], ((accn >> 1) & 1u) ^ 1u);
+          ptx::tc_fence_after();
+          const uint32_t d_tmem = tmem_base + as * BN;
+          for (int seg = 0; seg < kd.nseg; ++seg) {
+            const uint32_t idesc = seg == 1 ? idesc_neg : idesc_pos;  // second segment: -vk^T hk
+            for (int kb = 0; kb < kd.kblocks; ++kb) {
+              ptx::mbar_wait(&full_bar[stage], phase);
+              ptx::tc_fence_after();
+              const uint32_t sa = ptx::smem_u32(smem + stage * Cfg::kStageBytes);
+              const uint32_t sb = sa + Cfg::kABytes;
+              const uint64_t da = make_smem_desc(sa, lbo_a, 1024u);
+              const uint64_t db = make_smem_desc(sb, lbo_b, 1024u);
+#pragma unroll
+              for (int k = 0; k < kBlockK / 16; ++k)
+                ptx::mma_bf16<CG>(d_tmem, da + ((k * adv_a) >> 4), db + ((k * adv_b) >> 4), idesc,
+                                  (seg > 0 || kb > 0 || k > 0) ? 1u : 0u);
+              commit(&empty_bar[stage]);
+              if (++stage == kStages) {
+                stage = 0;
+                phase ^= 1u;
+              }
+            }
+          }
+          commit(&tmem_full_bar[as]);
+          ++accn;
+        } else {
+          // pieces of CH k-blocks, alternating between the two accumulator buffers
+          const int total = kd.nseg * kd.kblocks;
+          uint32_t as = 0, d_tmem = 0;
+          for (int it = 0; it < total; ++it) {
+            const int in_piece = it % (CH > 0 ? CH : 1);
+            if (in_piece == 0) {
+              as = accn & 1u;
+              ptx::mbar_wait(&tmem_empty_bar[as], ((accn >> 1) & 1u) ^ 1u);
+              ptx::tc_fence_after();
+              d_tmem = tmem_base + as * BN;
+            }
             ptx::mbar_wait(&full_bar[stage], phase);
             ptx::tc_fence_after();
             const uint32_t sa = ptx::smem_u32(smem + stage * Cfg::kStageBytes);
@@ -213,17 +251,19 @@ __global__ void __launch_bounds__(kNumThreads, 1) chain_kernel(const __grid_cons
             const uint64_t db = make_smem_desc(sb, lbo_b, 1024u);
 #pragma unroll
             for (int k = 0; k < kBlockK / 16; ++k)
-              ptx::mma_bf16<CG>(d_tmem, da + ((k * adv_a) >> 4), db + ((k * adv_b) >> 4), idesc,
-                                (seg > 0 || kb > 0 || k > 0) ? 1u : 0u);
+              ptx::mma_bf16<CG>(d_tmem, da + ((k * adv_a) >> 4), db + ((k * adv_b) >> 4), idesc_pos,
+                                (in_piece > 0 || k > 0) ? 1u : 0u);
             commit(&empty_bar[stage]);
             if (++stage == kStages) {
               stage = 0;
               phase ^= 1u;
             }
+            if ((it + 1) % (CH > 0 ? CH : 1) == 0 || it + 1 == total) {
+              commit(&tmem_full_bar[as]);
+              ++accn;
+            }
           }
         }
-        commit(&tmem_full_bar[as]);
-        ++accn;
       }
     }
   } else {
@@ -243,15 +283,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) chain_kernel(const __grid_cons
       const bool row_ok = row < (kd.batch_rows ? m_valid : kd.M);
       const uint64_t draw = draw_base + p.stages[s].phase;
       float row_acc = 0.f;
-      const uint32_t as = accn & 1u;
-      ptx::mbar_wait(&tmem_full_bar[as], (accn >> 1) & 1u);
-      ptx::tc_fence_after();
-#pragma unroll 1
-      for (int c = 0; c < kColsPerWarp; c += 32) {
-        const int coff = half * kColsPerWarp + c;
-        uint32_t acc[32];
-        ptx::tmem_ld_32x32(tmem_base + ((quarter * 32u) << 16) + as * BN + coff, acc);
-        ptx::tmem_ld_wait();
+      auto run_epilogue = [&](const uint32_t (&acc)[32], int coff) {
         if constexpr (GAUSS) {
           if (kd.epi == kEpiReluSample)
             epilogue_chunk<kEpiReluSample>(kd, acc, row, n_blk * BN + coff, row_ok, draw, row0, lane, row_acc);
@@ -269,15 +301,61 @@ __global__ void __launch_bounds__(kNumThreads, 1) chain_kernel(const __grid_cons
           else
             epilogue_chunk<kEpiRaw>(kd, acc, row, n_blk * BN + coff, row_ok, draw, row0, lane, row_acc);
         }
-      }
-      ptx::tc_fence_before();
-      ptx::fence_proxy_async_global();  // these stores will be read by other CTAs' TMA loads
-      __syncwarp();
-      if (lane == 0) {
+      };
+      auto release = [&](uint32_t as) {
         if constexpr (CG == 2) ptx::mbar_arrive_cluster(&tmem_empty_bar[as], 0);
         else ptx::mbar_arrive(&tmem_empty_bar[as]);
+      };
+      if constexpr (CH == 0) {
+        const uint32_t as = accn & 1u;
+        ptx::mbar_wait(&tmem_full_bar[as], (accn >> 1) & 1u);
+        ptx::tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < kColsPerWarp; c += 32) {
+          const int coff = half * kColsPerWarp + c;
+          uint32_t acc[32];
+          ptx::tmem_ld_32x32(tmem_base + ((quarter * 32u) << 16) + as * BN + coff, acc);
+          ptx::tmem_ld_wait();
+          run_epilogue(acc, coff);
+        }
+        ptx::tc_fence_before();
+        ptx::fence_proxy_async_global();  // these stores will be read by other CTAs' TMA loads
+        __syncwarp();
+        if (lane == 0) release(as);
+        ++accn;
+      } else {
+        float sum[kColsPerWarp];
+#pragma unroll
+        for (int j = 0; j < kColsPerWarp; ++j) sum[j] = 0.f;
+        const int total = kd.nseg * kd.kblocks;
+        const int pieces = (total + (CH > 0 ? CH : 1) - 1) / (CH > 0 ? CH : 1);
+        for (int piece = 0; piece < pieces; ++piece) {
+          const uint32_t as = accn & 1u;
+          ptx::mbar_wait(&tmem_full_bar[as], (accn >> 1) & 1u);
+          ptx::tc_fence_after();
+#pragma unroll
+          for (int c = 0; c < kColsPerWarp; c += 32) {
+            uint32_t acc[32];
+            ptx::tmem_ld_32x32(tmem_base + ((quarter * 32u) << 16) + as * BN + half * kColsPerWarp + c, acc);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sum[c + j] += __uint_as_float(acc[j]);
+          }
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) release(as);
+          ++accn;
+        }
+#pragma unroll
+        for (int c = 0; c < kColsPerWarp; c += 32) {
+          uint32_t acc[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[j] = __float_as_uint(sum[c + j]);
+          run_epilogue(acc, half * kColsPerWarp + c);
+        }
+        ptx::fence_proxy_async_global();
+        __syncwarp();
       }
-      ++accn;
       // this CTA's part of the tile is in global memory once all eight epilogue warps got here
       ptx::named_bar_sync(1, kNumEpiWarps * 32);
       if (ew == 0 && lane == 0) {

@@ -201,7 +201,7 @@ struct kucd_ctx {
   bool profile = false;
   std::vector<cudaEvent_t> ev_pool;
   struct Mark {
-    int cls;  // 0 = projection, 1 = dW
+    int cls;  // 0 = projection, 1 = dW, 2 = bit exchange, 3 = parameter update
     size_t e0, e1;
     int n;  // launches the interval covers
   };
@@ -380,6 +380,15 @@ static void dataset_planes_release(kucd_ctx*, PlaneBuf& pb) { pb.release(); }
 // this training call all-reduces dW as bf16 through NCCL (the fused exchange has its own bf16 slots)
 static bool nccl16(const kucd_rbm* r) { return r->wire16 && !r->fused_now && !r->units_now && r->ctx->comm != nullptr; }
 
+static bool capturing(const kucd_ctx* ctx) {
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(ctx->stream, &st) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return st != cudaStreamCaptureStatusNone;
+}
+
 static size_t prof_event(kucd_ctx* ctx) {
   if (ctx->ev_used == ctx->ev_pool.size()) {
     cudaEvent_t e;
@@ -400,9 +409,15 @@ static void prof_collect(kucd_ctx* ctx) {
     if (m.cls == 0) {
       ctx->tm.proj_ms += ms;
       ctx->tm.proj_timed += m.n;
-    } else {
+    } else if (m.cls == 1) {
       ctx->tm.dw_ms += ms;
       ctx->tm.dw_timed += m.n;
+    } else if (m.cls == 2) {
+      ctx->tm.xchg_ms += ms;
+      ctx->tm.xchg_timed += m.n;
+    } else {
+      ctx->tm.upd_ms += ms;
+      ctx->tm.upd_timed += m.n;
     }
     ctx->tm.last_gemm_ms = ms;
   }
@@ -865,6 +880,8 @@ static int apply_update(kucd_rbm* r, const kucd_hparams* hp, int64_t rows_global
     // for them already cover the whole global minibatch, so there is nothing to reduce
     const int n = ctx->world, me = ctx->rank;
     const int64_t Hs = r->H / n, Vs = r->V / n, h_lo = me * Hs, v_lo = me * Vs;
+    const bool prof = ctx->profile && !capturing(ctx);
+    const size_t pe0 = prof ? prof_event(ctx) : 0;
     if (hp->update_mask & KUCD_UPDATE_W) {
       update_w_units_kernel<<<grid_for(ctx, r->V * Hs / 4, 256), 256, 0, ctx->stream>>>(
           r->W32.as<float>(), r->dW(), use_mom ? r->mW.as<float>() : nullptr, r->ps, me, r->ldH, r->V, h_lo, Hs, Vs, hp->lr,
@@ -887,6 +904,7 @@ static int apply_update(kucd_rbm* r, const kucd_hparams* hp, int64_t rows_global
     // bit slots (the next step starts again at slot 0)
     peer_barrier_kernel<<<1, 32, 0, ctx->stream>>>(r->epoch, r->ps, me, n);
     ctx->tm.aux_launches++;
+    if (prof) ctx->marks.push_back({3, pe0, prof_event(ctx), 1});
     CU_TRY(cudaGetLastError());
     return KUCD_OK;
   }
@@ -1160,48 +1178,73 @@ static int gather_master(kucd_rbm* r) {
 
 // One launch of chain_kernel<BN, CG, GAUSS>.  Its CTAs (CTA pairs) wait on each other's tiles, so all of them must be
 // resident at once: one per SM (pair per TPC) at this shared-memory size, never more than the device can hold.
-template <int BN, int CG, bool GAUSS>
+template <int BN, int CG, bool GAUSS, int CH = 0>
 static int launch_chain_kernel(kucd_ctx* ctx, const ChainParams& p, int total, bool prof, size_t* pe0) {
   using Cfg = GemmCfg<BN / CG>;
-  auto kern = chain_kernel<BN, CG, GAUSS>;
-  static bool attr_set[kMaxDevices] = {};  // a function attribute belongs to the device it was set on
+  auto kern = chain_kernel<BN, CG, GAUSS, CH>;
   const int dev = current_device_slot();
-  if (!attr_set[dev]) {
-    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_set[dev] = true;
+  // per device: 0 = not prepared, 1 = plain launches, 2 = cooperative launches
+  static int state[kMaxDevices] = {};
+  static int max_clusters[kMaxDevices] = {};
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(kNumThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if constexpr (CG == 2) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
   }
-  if constexpr (CG == 1) {
-    const int grid = std::min(total, ctx->num_sms);
-    *pe0 = prof ? prof_event(ctx) : 0;
-    kern<<<grid, kNumThreads, Cfg::kSmemBytes, ctx->stream>>>(p);
-    CU_TRY(cudaGetLastError());
-  } else {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(ctx->num_sms / 2 * 2);
-    cfg.blockDim = dim3(kNumThreads);
-    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
-    cfg.stream = ctx->stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    static int max_clusters = -1;
-    if (max_clusters < 0) {
+  cfg.attrs = attr;
+  if (state[dev] == 0) {
+    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    if constexpr (CG == 2) {
+      cfg.gridDim = dim3(ctx->num_sms / 2 * 2);
+      cfg.numAttrs = na;
       int mc = 0;
       if (cudaOccupancyMaxActiveClusters(&mc, kern, &cfg) != cudaSuccess || mc <= 0) {
         cudaGetLastError();
         mc = ctx->num_sms / 2;
       }
-      max_clusters = mc;
+      max_clusters[dev] = mc;
     }
-    const int units = std::min(total, std::min(max_clusters, ctx->num_sms / 2));
-    cfg.gridDim = dim3(units * 2);
-    *pe0 = prof ? prof_event(ctx) : 0;
-    CU_TRY(cudaLaunchKernelEx(&cfg, kern, p));
+    // The CTAs of this kernel wait on each other's tiles, so all of them must be resident at once.  A COOPERATIVE launch
+    // makes the driver guarantee that (the grid is gang-scheduled: if other work holds SMs the launch waits instead of
+    // running a part of the grid that would spin on the rest).  Whether this device / driver accepts the attribute for this
+    // kernel - together with the cluster dimension - is found out once, with an empty launch (no tiles: every role falls
+    // through) on a side stream, so that a refusal can never hit a stream that is being captured.  KUCD_COOP=0: plain.
+    state[dev] = 1;
+    const char* e = getenv("KUCD_COOP");
+    int coop_ok = 0;
+    if (!(e != nullptr && e[0] == '0') &&
+        cudaDeviceGetAttribute(&coop_ok, cudaDevAttrCooperativeLaunch, ctx->device) == cudaSuccess && coop_ok) {
+      ChainParams empty;
+      memset(&empty, 0, sizeof empty);
+      attr[na].id = cudaLaunchAttributeCooperative;
+      attr[na].val.cooperative = 1;
+      cfg.numAttrs = na + 1;
+      cfg.gridDim = dim3(CG);
+      cfg.stream = ctx->copy_stream;
+      if (cudaLaunchKernelEx(&cfg, kern, empty) == cudaSuccess && cudaStreamSynchronize(ctx->copy_stream) == cudaSuccess)
+        state[dev] = 2;
+      cudaGetLastError();
+    }
   }
+  int units = std::min(total, ctx->num_sms / CG);
+  if constexpr (CG == 2) units = std::min(units, max_clusters[dev]);
+  if (state[dev] == 2) {
+    attr[na].id = cudaLaunchAttributeCooperative;
+    attr[na].val.cooperative = 1;
+    ++na;
+  }
+  cfg.numAttrs = na;
+  cfg.gridDim = dim3(units * CG);
+  cfg.stream = ctx->stream;
+  *pe0 = prof ? prof_event(ctx) : 0;
+  CU_TRY(cudaLaunchKernelEx(&cfg, kern, p));
   return KUCD_OK;
 }
 
@@ -1229,6 +1272,16 @@ static int launch_chain(kucd_rbm* r, const Planes& v0, int64_t batch, const kucd
           && make_tmap_bf16(&p.maps[6], Wv, bn / cg, &err);             // h.W^T : W as (N,K), boxes {64 k, bn/cg n}
   if (!ok) return fail(KUCD_ERR_CUDA, "%s", err.c_str());
   p.maps[7] = p.maps[6];
+  const bool f32 = r->compute == KUCD_COMPUTE_F32X3;  // three term planes of W: W = hi + mid + lo (float32-grade mode)
+  if (f32) {
+    for (int t = 1; t <= 2 && ok; ++t) {
+      const MatView Wt{r->Wp.buf[t].p, r->V, r->H, r->ldH};
+      ok = make_tmap_bf16(&p.maps[11 + t], Wt, 64u, &err) && make_tmap_bf16(&p.maps[13 + t], Wt, bn / cg, &err);
+    }
+    if (!ok) return fail(KUCD_ERR_CUDA, "%s", err.c_str());
+  } else {
+    for (int i = 12; i < kChainMaps; ++i) p.maps[i] = p.maps[5];
+  }
   // the same matrices as MN-major operands of the dW contraction (boxes {64 units, 64 minibatch rows})
   auto mnmap = [&](int i, const Planes& q) {
     return make_tmap_bf16(&p.maps[i], MatView{q.p[0], q.rows, q.cols, q.ld}, 64u, &err);
@@ -1256,6 +1309,12 @@ static int launch_chain(kucd_rbm* r, const Planes& v0, int64_t batch, const kucd
     q.num_m = num_m_batch;
     q.batch_rows = 1;
     q.nseg = 1;
+    if (f32) {  // smallest term of W first (term_pairs): lo, mid, hi
+      q.nseg = 3;
+      q.map_b = fwd ? 13 : 15;
+      q.map_b2 = fwd ? 12 : 14;
+      q.map_b3 = fwd ? 5 : 6;
+    }
   };
   // Gaussian-visible mode (rbm.py:139-145): relu-threshold hiddens, v = mean + N(0,1), final h still the sigmoid
   const bool gaussian = r->mode == KUCD_MODE_VISIBLE_GAUSSIAN;
@@ -1268,6 +1327,10 @@ static int launch_chain(kucd_rbm* r, const Planes& v0, int64_t batch, const kucd
   kind(5, false, 2, vk.p[0], ev, r->db(), -1.f, false);                  // last v from a later h
   kind(6, true, 3, hk.p[0], eh, nullptr, 0.f, false);                    // intermediate h (CD-k)
   kind(7, true, 3, hk.p[0], kEpiProb, r->dc(), -1.f, false);             // final h: probability     rbm.py:124
+  if (f32) {  // the probability leaves as three bf16 terms: the dW contraction multiplies it at float32 grade
+    p.kinds[7].out_mid = r->hk.buf[1].as<__nv_bfloat16>();
+    p.kinds[7].out_lo = r->hk.buf[2].as<__nv_bfloat16>();
+  }
 
   int ns = 0;
   auto stage = [&](int kd, int dep, uint32_t phase) {
@@ -1334,7 +1397,10 @@ static int launch_chain(kucd_rbm* r, const Planes& v0, int64_t batch, const kucd
   const bool prof = ctx->profile && dyn == nullptr;
   size_t pe0 = 0;
   int rc;
-  if (small)
+  if (f32)
+    rc = small ? launch_chain_kernel<64, 1, false, kPreciseCH>(ctx, p, total, prof, &pe0)
+               : launch_chain_kernel<kChainBN, 2, false, kPreciseCH>(ctx, p, total, prof, &pe0);
+  else if (small)
     rc = gaussian ? launch_chain_kernel<64, 1, true>(ctx, p, total, prof, &pe0)
                   : launch_chain_kernel<64, 1, false>(ctx, p, total, prof, &pe0);
   else
@@ -1358,6 +1424,8 @@ static int units_exchange(kucd_rbm* r, int& ex, const __nv_bfloat16* src, int64_
   const int slot = ex++ & 1;
   const int64_t pitch = G.cols / 8;
   const int64_t total = rows * cols / 8;
+  const bool prof = ctx->profile && !capturing(ctx);
+  const size_t pe0 = prof ? prof_event(ctx) : 0;
   pack_push_kernel<<<grid_for(ctx, total, 256), 256, 0, ctx->stream>>>(src, src_ld, src_dyn, rows, col_lo, cols, r->ps,
                                                                       ctx->world, slot, dst_row0, pitch);
   peer_barrier_kernel<<<1, 32, 0, ctx->stream>>>(r->epoch, r->ps, ctx->rank, ctx->world);
@@ -1366,6 +1434,7 @@ static int units_exchange(kucd_rbm* r, int& ex, const __nv_bfloat16* src, int64_
       G.ld, 1, in_place ? col_lo : 0, in_place ? col_lo + cols : 0);
   ctx->tm.aux_launches += 3;
   ctx->tm.unit_exchanges++;
+  if (prof) ctx->marks.push_back({2, pe0, prof_event(ctx), 1});
   CU_TRY(cudaGetLastError());
   return KUCD_OK;
 }
@@ -1416,7 +1485,8 @@ static int enqueue_cd_units(kucd_rbm* r, const Planes& v0_local, int64_t b, cons
   auto share_v = [&](const Planes& G) { return units_exchange(r, ex, G.p[0], G.ld, nullptr, Bg, 0, v_lo, Vs, G, true); };
 
   KU_TRY(stage(true, Gv0, Gh0, kEpiSample, 0, r->dc(), 1.f));  // h_pos   rbm.py:120
-  KU_TRY(share_h(Gh0));
+  // (with persistent chains nobody back-projects h_pos: only this rank's slice of it is ever read, by dW and dc)
+  if (!pcd) KU_TRY(share_h(Gh0));
   Planes hcur = Gh0;
   if (pcd) {  // the negative chain starts at the stored fantasy particles
     KU_TRY(stage(true, Gvk, Ghk, kEpiSample, 1, nullptr, 0.f));
@@ -1580,26 +1650,30 @@ static int enqueue_cd(kucd_rbm* r, const Planes& v0, int64_t batch, const kucd_h
   const int n_proj = 2 * k + 1 + (hp->persistent ? 1 : 0);
   // one persistent kernel for the whole chain when every stage fills the chip with 256 x 256 tiles
   const int64_t pair_tiles = ((batch + 255) / 256) * ((std::min(r->V, r->H) + 255) / 256);
-  const bool whole_chain = ctx->chain && r->compute == KUCD_COMPUTE_BF16 && inj == nullptr && v0.n == 1 &&
-                           (pair_tiles >= ctx->num_sms / 2 || ctx->chain_force) &&
-                           (!hp->persistent || r->last_vk_parts == 1);
+  // (float32-grade mode: Bernoulli visibles only - every state operand is then a single exact bf16 plane and a
+  // projection is the three term planes of W as three K-segments, accumulated piecewise; chain.cuh, CH > 0)
+  const bool f32 = r->compute == KUCD_COMPUTE_F32X3;
+  const bool chain_able = ctx->chain && inj == nullptr && v0.n == 1 && (!f32 || !gaussian) &&
+                          (!hp->persistent || r->last_vk_parts == 1);
+  const bool whole_chain = chain_able && (pair_tiles >= ctx->num_sms / 2 || ctx->chain_force);
   // KUCD_CHAIN_DW=1 appends the dW contraction to the chain kernel as a final two-segment stage.  Measured: no gain
   // at C3 (2.529 vs 2.522 ms per step) and a loss at C4 (577 k vs 605 k samples/s) - its second segment has to wait
   // for every row block of the last projection, so it hides little - which is why it is off by default.
   const bool slabbed = r->slabs_now > 1 && !r->fused_now;
-  const bool chain_dw = ctx->chain_dw && !r->fused_now && !nccl16(r) && !slabbed;
+  const bool chain_dw = ctx->chain_dw && !r->fused_now && !nccl16(r) && !slabbed && !f32;
   // latency-bound sizes: the whole step's contractions (projections and dW) as one launch of the small-tile variant
   static const bool small_chain_env = [] {
     const char* e = getenv("KUCD_SMALL_CHAIN");
     return !(e != nullptr && e[0] == '0');
   }();
-  const bool small_chain = !whole_chain && small_chain_env && ctx->chain && batch <= 512 &&
-                           r->compute == KUCD_COMPUTE_BF16 && inj == nullptr && v0.n == 1 &&
-                           !r->fused_now && !nccl16(r) && !slabbed && (!hp->persistent || r->last_vk_parts == 1);
+  const bool small_chain = !whole_chain && small_chain_env && chain_able && batch <= 512 &&
+                           !r->fused_now && !nccl16(r) && !slabbed;
+  // the small-tile variant carries the dW contraction as its last stage, except at float32 grade (four term products)
+  const bool small_dw = small_chain && !f32;
   if (whole_chain) {
     KU_TRY(launch_chain(r, v0, batch, hp, global_row0, draw0, stride, dyn, v0_dyn, chain_dw, false));
   } else if (small_chain) {
-    KU_TRY(launch_chain(r, v0, batch, hp, global_row0, draw0, stride, dyn, v0_dyn, true, true));
+    KU_TRY(launch_chain(r, v0, batch, hp, global_row0, draw0, stride, dyn, v0_dyn, small_dw, true));
   } else if (!two) {
     KU_TRY(chain(0, batch, ctx->stream, true));
   } else {
@@ -1654,7 +1728,7 @@ static int enqueue_cd(kucd_rbm* r, const Planes& v0, int64_t batch, const kucd_h
     }
     r->slabs_inflight = S;
     if (!solo) ctx->tm.allreduce_calls++;
-  } else if (!((whole_chain && chain_dw) || small_chain)) {
+  } else if (!((whole_chain && chain_dw) || small_dw)) {
     KU_TRY(delta_w(r, v0, h0, vk, hk, batch, dyn, v0_dyn));
   }
   r->last_rows = batch;
@@ -2855,8 +2929,8 @@ static int fit_range_impl(kucd_rbm* r, kucd_dataset* ds, int64_t batch, const ku
   return KUCD_OK;
 }
 
-// Chunked variant of the streamed fit for latency-bound minibatches (KUCD_STREAM_CHUNK = C > 1, off by default until
-// measured): C minibatches travel per copy, one ingest launch expands them into resident operand planes, and their
+// Chunked variant of the streamed fit for latency-bound minibatches (C = 8 by default, KUCD_STREAM_CHUNK): C minibatches
+// travel per copy, one ingest launch expands them into resident operand planes, and their
 // steps replay the captured graph of kucd_rbm_fit_range (minibatch offset, draw counter in StepDyn) - one copy ->
 // ingest -> step hand-over per C steps instead of per step.  The raw staging is double-buffered, so the copy of
 // chunk j+1 overlaps the steps of chunk j.  The remainder minibatch (at most one, rbm.py:211) runs as direct
@@ -3063,10 +3137,13 @@ int kucd_rbm_fit_host(kucd_rbm* r, const kucd_tensor* V_all, int64_t batch, cons
     }
     host_stats = ctx->pinned_stats;
   }
-  // KUCD_STREAM_CHUNK = C > 1: latency-bound minibatches travel and are ingested C at a time (fit_host_chunked)
+  // Latency-bound minibatches travel and are ingested C at a time (fit_host_chunked): one copy -> ingest -> step
+  // hand-over per C steps instead of per step.  Measured at the C1 shape (60000 x 784 float32 rows, minibatches of 128,
+  // profiles/r02_switches.md): 75.7 us per step unchunked, 61.5 / 61.1 / 61.6 / 61.4 us at C = 4 / 8 / 16 / 32.
+  // KUCD_STREAM_CHUNK overrides C (0 or 1: per-minibatch stream).
   static const int64_t chunk_env = [] {
     const char* e = getenv("KUCD_STREAM_CHUNK");
-    return e == nullptr ? int64_t{0} : static_cast<int64_t>(atoll(e));
+    return e == nullptr ? int64_t{8} : static_cast<int64_t>(atoll(e));
   }();
   if (chunk_env > 1 && !zero_copy && N >= 2 * batch && batch * cols < (1 << 20)) {
     int rc = fit_host_chunked(r, V_all, batch, hp, global_row0, host_stats, std::min<int64_t>(chunk_env, 4096));

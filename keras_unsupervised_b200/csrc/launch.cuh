@@ -188,6 +188,7 @@ inline cudaError_t launch_major(const GemmParams& p, bool a_mn, bool b_mn, int n
 template <int EPI>
 inline cudaError_t launch_bn(const GemmParams& p, int bn, bool precise, int cg, bool a_mn, bool b_mn, int num_sms,
                              cudaStream_t s) {
+  if (precise && cg == 2) return launch_major<256, EPI, kPreciseCH, 2>(p, a_mn, b_mn, num_sms, s);
   if (precise) return launch_major<kPreciseBN, EPI, kPreciseCH>(p, a_mn, b_mn, num_sms, s);
   if (cg == 2) return launch_major<256, EPI, 0, 2>(p, a_mn, b_mn, num_sms, s);
   switch (bn) {
@@ -216,7 +217,8 @@ inline bool launch_gemm(GemmParams& p, const GemmOperands& ops, int epi, int num
     return false;
   }
   int bn = precise ? kPreciseBN : (force_bn ? force_bn : pick_bn(ops.M, ops.N, num_sms));
-  int cg = precise ? 1 : (force_cg ? force_cg : ((force_bn == 0 || force_bn == 256) ? pick_cg(ops.M, ops.N, num_sms) : 1));
+  // (precise mode on CTA pairs: 256 x 256 tiles, each epilogue thread keeps 128 partial sums in registers)
+  int cg = force_cg ? force_cg : ((force_bn == 0 || force_bn == 256) ? pick_cg(ops.M, ops.N, num_sms) : 1);
   if (cg == 2) bn = 256;
   p.num_seg = ops.num_seg;
   p.neg_mask = ops.neg_mask;

@@ -83,7 +83,7 @@ struct alignas(64) GemmParams {
 
 constexpr int kMaxChainStages = 66;  // 2k+2 projections with k <= 31, + the dW contraction
 constexpr int kMaxChainKinds = 9;
-constexpr int kChainMaps = 12;
+constexpr int kChainMaps = 16;  // 5 state operands, 3 views of W, 4 operands of dW, 4 more term planes of W (fp32-grade)
 
 // The few distinct projections a chain is made of (member names shared with GemmParams: epilogue_chunk reads them).
 struct ChainKind {
@@ -114,6 +114,8 @@ struct ChainKind {
   int32_t a_mn;
   int32_t nseg;
   int32_t map_a2, map_b2;
+  int32_t map_b3;      // float32-grade chain kernel: third term plane of W (map_b, map_b2, map_b3 = smallest term first)
+  int32_t pad3;
   int32_t dep2;        // stage that must be complete in ALL its row blocks before segment 1 is loaded
   int32_t col_off;     // as GemmParams::col_off (always 0: chain launches cover whole layers)
 };

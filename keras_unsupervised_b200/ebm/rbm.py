@@ -235,20 +235,38 @@ class RBM(_Base):
         self._to_keras()
 
     # ---- checkpoint / resume (the reference relies on Keras HDF5 and saves no trainer state) ----
+    @staticmethod
+    def _rank_path(path, rank, world):
+        """Data-parallel ranks hold identical parameters but different persistent chains: rank r > 0 writes its own
+        file next to rank 0's (`model.npz`, `model.rank1.npz`, ...)."""
+        path = str(path)
+        if world <= 1 or rank == 0:
+            return path
+        stem = path[:-4] if path.endswith(".npz") else path
+        return "%s.rank%d.npz" % (stem, rank)
+
     def save(self, path):
         """Parameters under the reference's variable names (rbm.py:30,34,40) plus what resuming a fit needs:
-        the Philox stream position and the persistent chains."""
+        the Philox stream position and the persistent chains.  Under data parallelism every rank calls this; the chains
+        stored are the rank's own shard."""
         W, b, c = self._machine.get_params()
         st = self._machine.counters()
+        ctx = self._machine.ctx
         extra = {}
         if st["n_chains"] > 0:
             extra["chains"] = self._machine.get_chains(st["n_chains"])
-        np.savez(path, rbm_weight=W, rbm_hidden_bias=c, rbm_visible_bias=b, seed=np.uint64(st["seed"]),
-                 step_count=np.uint64(st["step_count"]), mode=np.int64(self.mode), output_dim=np.int64(self.output_dim),
-                 epochs_done=np.int64(self._epochs_done), **extra)
+        np.savez(self._rank_path(path, ctx.rank, ctx.world), rbm_weight=W, rbm_hidden_bias=c, rbm_visible_bias=b,
+                 seed=np.uint64(st["seed"]), step_count=np.uint64(st["step_count"]), mode=np.int64(self.mode),
+                 output_dim=np.int64(self.output_dim), epochs_done=np.int64(self._epochs_done),
+                 rank=np.int64(ctx.rank), world=np.int64(ctx.world), **extra)
 
     def load(self, path):
+        ctx = getattr(getattr(self, "_machine", None), "ctx", None) or self._context or Context.default()
+        path = self._rank_path(path, ctx.rank, ctx.world)
         z = np.load(path if str(path).endswith(".npz") else str(path) + ".npz")
+        if "world" in z.files and int(z["world"]) != ctx.world and "chains" in z.files:
+            raise ValueError("checkpoint with persistent chains was written by %d ranks, this group has %d"
+                             % (int(z["world"]), ctx.world))
         if not self.built:
             self.build((None, int(z["rbm_weight"].shape[0])))
         if z["rbm_weight"].shape != (self._machine.V, self._machine.H):
@@ -336,6 +354,12 @@ class RBM(_Base):
         if hps.get("persistent", False) and m.ctx is not None:
             self._ensure_chains(batch)
         if compat == "reference":
+            if m.ctx.world > 1:
+                # the reference's schedule walks the whole minibatch through three sequential single-parameter runs on
+                # one device; sharding it would need its own row bookkeeping (every rank would otherwise add the same
+                # gradient world times)
+                raise ValueError("hps['compat'] = 'reference' runs on a single rank (world size is %d); "
+                                 "use the default compat='fused' for data-parallel training" % m.ctx.world)
             dense = V.to_dense() if isinstance(V, PackedBits) else np.asarray(V, dtype=np.float32)
             return self._fit_reference(dense, batch, epochs, verbose)
         if compat != "fused":
@@ -353,7 +377,9 @@ class RBM(_Base):
                 if verbose == 1:
                     print(1, "/", epochs, " epochs", end="\r")
                 st = m.fit_host(local, local_batch, self._hparams(), global_row0=row0, want_recon=bool(verbose))
+                self._epochs_done += 1                 # numbers the shuffle permutations, saved in checkpoints
                 st["epoch"] = 1
+                st.setdefault("last_score", 0.0)       # same entry shape as the resident path below
                 if verbose:
                     st["last_score"] = m.score(local[-(local.shape[0] % local_batch or local_batch):])
                     n_step = int(st["steps"])
@@ -395,15 +421,17 @@ class RBM(_Base):
         return self
 
     def _ensure_chains(self, batch):
+        """Persistent chains for a GLOBAL minibatch of `batch` rows; this rank stores its batch / world of them.
+        `_chains_set` counts the rows stored on THIS rank (what `save` writes and `load` restores)."""
         m = self._machine
-        if getattr(self, "_chains_set", 0) >= batch:
-            return
-        rng = np.random.default_rng(int(self.hps.get("chain_seed", 99)))
         ctx = m.ctx
         rows = batch // ctx.world if ctx.world > 1 else batch
+        if getattr(self, "_chains_set", 0) >= rows:
+            return
+        rng = np.random.default_rng(int(self.hps.get("chain_seed", 99)))
         full = (rng.random((batch, m.V)) < 0.5).astype(np.float32)
         m.set_chains(full[ctx.rank * rows:(ctx.rank + 1) * rows] if ctx.world > 1 else full)
-        self._chains_set = batch
+        self._chains_set = rows
 
     def _fit_reference(self, V, batch, epochs, verbose):
         """The reference schedule, run for run (rbm.py:214-234): three single-parameter updates with

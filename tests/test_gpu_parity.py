@@ -570,3 +570,64 @@ def test_mean_normalisation_with_a_remainder_minibatch(ctx):
         assert np.abs(W - orc.W).mean() < 2e-5 and np.abs(W - orc.W).max() < 5e-3, compute
         assert np.abs(b - orc.b).max() < 5e-3 and np.abs(c - orc.c).max() < 5e-3
         ds.close()
+
+
+def test_float32_grade_chain_kernels_equal_per_projection_launches(monkeypatch):
+    """Float32-grade mode (the reference's own precision, rbm.py:39) through the chain kernels (chain.cuh, CH > 0: three
+    term planes of W as K-segments, accumulation cut every 4 k-blocks, pieces added in registers): same draws, same
+    piece boundaries, same order of additions as the launch-per-projection path - states, h_neg and dW bit for bit.
+    Small-tile variant (784 -> 500, batch 128; CD-3 at ragged sizes) and the 256 x 256 CTA-pair variant (forced at a
+    small size, CD-3, 700 rows), PCD with graph replay and a remainder minibatch; then against the oracle at 1e-5."""
+    from keras_unsupervised_b200 import _lib as L
+    from keras_unsupervised_b200.engine import Context, Dataset, Machine
+
+    rng = np.random.default_rng(131)
+    for force, shapes in ((None, ((784, 500, 128, 1), (333, 270, 300, 3))), ("2", ((600, 520, 700, 3),))):
+        if force is None:
+            monkeypatch.delenv("KUCD_CHAIN", raising=False)
+        else:
+            monkeypatch.setenv("KUCD_CHAIN", force)
+        c_chain = Context(device=0, seed=1)
+        monkeypatch.setenv("KUCD_CHAIN", "0")
+        c_plain = Context(device=0, seed=1)
+        for V, H, rows, k in shapes:
+            ms, orc = [], None
+            for c in (c_chain, c_plain):
+                m, orc = _machine(c, V, H, "f32", seed=37)
+                ms.append(m)
+            v = _data(rng, rows, V, 0.2)
+            hp = Machine.hparams(lr=1e-3, k=k, update_mask=0)
+            got = []
+            for m in ms:
+                m.cd_step(v, hp)
+                got.append(m.last_stats(rows))
+            for key in ("h_pos", "v_neg", "h_neg", "dW", "db"):
+                assert np.array_equal(got[0][key], got[1][key]), (V, key)
+            np.testing.assert_allclose(got[0]["dc"], got[1]["dc"], rtol=0, atol=1e-3)
+            # against the oracle's regeneration of the same Philox stream, float32 grade
+            u_h = [O.philox_uniform(37, O.draw_id("train", 0, 0 if t == 0 else 2 * t + 1), 0, rows, H) for t in range(k)]
+            u_v = [None] + [O.philox_uniform(37, O.draw_id("train", 0, 2 * t), 0, rows, V) for t in range(1, k + 1)]
+            st = orc.cd_stats(v, u_h, u_v, k=k)
+            same = ~((got[0]["h_pos"] != st["h_pos"]).any(axis=1) | (got[0]["v_neg"] != st["v_neg"]).any(axis=1))
+            assert not (~same & (st["row_margin"] > 2e-6)).any() and same.mean() > 0.9
+            np.testing.assert_allclose(got[0]["h_neg"][same], st["h_neg"][same], rtol=RTOL_F32, atol=1e-7)
+            # persistent chains + graph replay with a remainder minibatch
+            b = min(rows, 256)
+            chains = _data(rng, b, V, 0.5)
+            data = _data(rng, 2 * b + 88, V, 0.2)
+            hp = Machine.hparams(lr=1e-3, k=2, persistent=True)
+            params = []
+            for c, m in zip((c_chain, c_plain), ms):
+                m.set_chains(chains)
+                ds = Dataset.from_array(c, data, L.COMPUTE_F32X3)
+                for _ in range(2):
+                    m.fit_epoch(ds, b, hp)
+                c.sync()
+                params.append(m.get_params() + (m.get_chains(b),))
+                ds.close()
+            assert np.array_equal(params[0][3], params[1][3])
+            for i in range(3):
+                np.testing.assert_allclose(params[0][i], params[1][i], rtol=0, atol=1e-6)
+        assert c_chain.timings()["chain_launches"] > 0 and c_plain.timings()["chain_launches"] == 0
+        c_chain.close()
+        c_plain.close()

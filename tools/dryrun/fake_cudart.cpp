@@ -659,6 +659,10 @@ cudaError_t cudaFreeAsync(void* p, cudaStream_t) {
   }
   return e;
 }
+cudaError_t cudaDeviceGetAttribute(int* value, cudaDeviceAttr, int) {
+  *value = 0;  // (no cooperative launches in the dry run: the engine then issues plain ones)
+  return cudaSuccess;
+}
 cudaError_t cudaDeviceGetDefaultMemPool(cudaMemPool_t* pool, int) {
   *pool = reinterpret_cast<cudaMemPool_t>(static_cast<uintptr_t>(0x9000));
   return cudaSuccess;
@@ -806,6 +810,11 @@ cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t st) {
 cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
 cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) {
   *ms = 0.f;
+  return cudaSuccess;
+}
+cudaError_t cudaStreamIsCapturing(cudaStream_t st, cudaStreamCaptureStatus* status) {
+  LOCK;
+  *status = captured(st) ? cudaStreamCaptureStatusActive : cudaStreamCaptureStatusNone;
   return cudaSuccess;
 }
 cudaError_t cudaStreamBeginCapture(cudaStream_t st, cudaStreamCaptureMode) {
