@@ -402,8 +402,14 @@ def _main(out):
                     help="weak: the workload's minibatch PER GPU (default, what the metric is quoted on); strong: that "
                          "minibatch is the GLOBAL one, split by rows over the GPUs (SURVEY.md 8d: report both - the weak "
                          "line carries the strong figure as `strong_scaling` when N > 1)")
+    ap.add_argument("--batch", type=int, default=0,
+                    help="rows per GPU instead of the workload's (e.g. 512: the per-GPU share of C3 under strong scaling over "
+                         "8 GPUs, measured on fewer); the line says so in config.workload")
     args = ap.parse_args()
-    cfg = WORKLOADS[args.workload]
+    cfg = dict(WORKLOADS[args.workload])
+    if args.batch > 0:
+        cfg["B"] = args.batch
+        cfg["desc"] += " [--batch %d rows per GPU instead of the workload's]" % args.batch
     V, H, B, k = cfg["V"], cfg["H"], cfg["B"], cfg["k"]
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -591,6 +591,45 @@ __global__ void recon_kernel(const __nv_bfloat16* __restrict__ a_hi, const __nv_
   if ((threadIdx.x & 31) == 0 && s != 0.f) atomicAdd(acc, s);
 }
 
+// Latency-bound minibatches: the whole reconstruction statistic in ONE launch of one block - the squared differences,
+// the mean into stats[1] and, for a streamed fit under graph replay, the write into the caller-visible page-locked log
+// (log_stat_kernel's job) - instead of memset + recon + finish + log.  Single 0/1 planes only.
+__global__ void __launch_bounds__(1024) recon_small_kernel(const __nv_bfloat16* __restrict__ a, int64_t a_ld,
+                                                           const __nv_bfloat16* __restrict__ b, int64_t b_ld, int32_t rows,
+                                                           int32_t cols, const StepDyn* a_dyn, float* __restrict__ stats,
+                                                           const StepDyn* log_dyn, int32_t log_batch, float* host_log) {
+  __shared__ float part[32];
+  int64_t a_row_off = 0;
+  if (a_dyn != nullptr) {
+    a_row_off = a_dyn->row_off;
+    rows = a_dyn->rows_valid < rows ? a_dyn->rows_valid : rows;
+  }
+  const int pairs = (cols + 1) / 2;  // columns are read in bf16 pairs (ld is a multiple of 64: in bounds; pads are zero)
+  const int64_t total = static_cast<int64_t>(rows) * pairs;
+  float s = 0.f;
+  for (int64_t i = threadIdx.x; i < total; i += blockDim.x) {
+    const int64_t r = i / pairs, c = 2 * (i - r * pairs);
+    const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(a + (a_row_off + r) * a_ld + c));
+    const float2 y = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(b + r * b_ld + c));
+    s += (x.x - y.x) * (x.x - y.x);
+    if (c + 1 < cols) s += (x.y - y.y) * (x.y - y.y);
+  }
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    s = threadIdx.x < (blockDim.x >> 5) ? part[threadIdx.x] : 0.f;
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (threadIdx.x == 0) {
+      const float v = rows > 0 ? s / (static_cast<float>(rows) * cols) : 0.f;
+      stats[1] = v;
+      if (host_log != nullptr) host_log[log_dyn->pad + log_dyn->row_off / log_batch] = v;
+    }
+  }
+}
+
 // stats[1] = acc / (rows * cols)
 __global__ void recon_finish_kernel(const float* acc, int32_t rows, int32_t cols, const StepDyn* dyn, float* stats) {
   if (dyn != nullptr) rows = dyn->rows_valid < rows ? dyn->rows_valid : rows;

@@ -1251,8 +1251,11 @@ static int launch_chain_kernel(kucd_ctx* ctx, const ChainParams& p, int total, b
 // The 2k+1 (+1 with persistent chains) projections of one minibatch as one persistent kernel (chain.cuh).
 // `small`: 128 x 64 tiles on single CTAs (latency-bound sizes) instead of 256 x 256 tiles on CTA pairs.
 static int launch_chain(kucd_rbm* r, const Planes& v0, int64_t batch, const kucd_hparams* hp, int64_t global_row0,
-                        uint64_t draw0, uint64_t stride, const StepDyn* dyn, bool v0_dyn, bool with_dw, bool small) {
-  const int bn = small ? 64 : kChainBN, cg = small ? 1 : 2;
+                        uint64_t draw0, uint64_t stride, const StepDyn* dyn, bool v0_dyn, bool with_dw, int variant) {
+  // variant 0: CTA pairs on 256 x 256 tiles; 1: single CTAs on 128 x 64 tiles (latency-bound sizes); 2: single CTAs on
+  // 128 x 256 tiles (minibatches too short to give every CTA pair a 256-row tile, e.g. a 512-row shard of 4096 -> 4096)
+  const bool small = variant == 1;
+  const int bn = small ? 64 : kChainBN, cg = variant == 0 ? 2 : 1;
   const int tile_m = kBlockM * cg;
   kucd_ctx* ctx = r->ctx;
   const int k = hp->k;
@@ -1397,7 +1400,9 @@ static int launch_chain(kucd_rbm* r, const Planes& v0, int64_t batch, const kucd
   const bool prof = ctx->profile && dyn == nullptr;
   size_t pe0 = 0;
   int rc;
-  if (f32)
+  if (variant == 2)
+    rc = launch_chain_kernel<kChainBN, 1, false>(ctx, p, total, prof, &pe0);
+  else if (f32)
     rc = small ? launch_chain_kernel<64, 1, false, kPreciseCH>(ctx, p, total, prof, &pe0)
                : launch_chain_kernel<kChainBN, 2, false, kPreciseCH>(ctx, p, total, prof, &pe0);
   else if (small)
@@ -1666,14 +1671,26 @@ static int enqueue_cd(kucd_rbm* r, const Planes& v0, int64_t batch, const kucd_h
     const char* e = getenv("KUCD_SMALL_CHAIN");
     return !(e != nullptr && e[0] == '0');
   }();
-  const bool small_chain = !whole_chain && small_chain_env && chain_able && batch <= 512 &&
+  // In between - a minibatch (or a data-parallel shard of one) too short for 74 pair tiles per stage but long enough
+  // for >= 32 tiles of 128 x 256: the same flattened chain on single CTAs.  A 512-row shard of 4096 -> 4096 (C3 strong
+  // scaling over 8 GPUs) is 64 such tiles per stage; launched one projection at a time each of its 21 projections cost
+  // 58 us for 17 GFLOP (profiles/r02_scaling.md).  The dW contraction stays a launch of its own (it may push rows to peers).
+  const int64_t mid_tiles = ((batch + kBlockM - 1) / kBlockM) * ((std::min(r->V, r->H) + 255) / 256);
+  static const bool mid_chain_env = [] {
+    const char* e = getenv("KUCD_MID_CHAIN");
+    return !(e != nullptr && e[0] == '0');
+  }();
+  const bool mid_chain = !whole_chain && mid_chain_env && chain_able && !f32 && !gaussian && batch > 256 && mid_tiles >= 32;
+  const bool small_chain = !whole_chain && !mid_chain && small_chain_env && chain_able && batch <= 512 &&
                            !r->fused_now && !nccl16(r) && !slabbed;
   // the small-tile variant carries the dW contraction as its last stage, except at float32 grade (four term products)
   const bool small_dw = small_chain && !f32;
   if (whole_chain) {
-    KU_TRY(launch_chain(r, v0, batch, hp, global_row0, draw0, stride, dyn, v0_dyn, chain_dw, false));
+    KU_TRY(launch_chain(r, v0, batch, hp, global_row0, draw0, stride, dyn, v0_dyn, chain_dw, 0));
+  } else if (mid_chain) {
+    KU_TRY(launch_chain(r, v0, batch, hp, global_row0, draw0, stride, dyn, v0_dyn, false, 2));
   } else if (small_chain) {
-    KU_TRY(launch_chain(r, v0, batch, hp, global_row0, draw0, stride, dyn, v0_dyn, small_dw, true));
+    KU_TRY(launch_chain(r, v0, batch, hp, global_row0, draw0, stride, dyn, v0_dyn, small_dw, 1));
   } else if (!two) {
     KU_TRY(chain(0, batch, ctx->stream, true));
   } else {
@@ -1844,22 +1861,37 @@ static int ensure_chains(kucd_rbm* r, int64_t rows) {
 
 
 // v0_dyn != nullptr: v0 is a resident block of rows and the minibatch starts at v0_dyn->row_off (graph replay)
-static int enqueue_recon(kucd_rbm* r, const Planes& v0, int64_t rows, const StepDyn* v0_dyn = nullptr) {
+// host_log != nullptr (streamed fit under graph replay): the statistic also goes into the caller-visible page-locked log,
+// slot = index of the minibatch (log_dyn, log_batch: see log_stat_kernel).
+static int enqueue_recon(kucd_rbm* r, const Planes& v0, int64_t rows, const StepDyn* v0_dyn = nullptr,
+                         float* host_log = nullptr, const StepDyn* log_dyn = nullptr, int32_t log_batch = 0) {
   kucd_ctx* ctx = r->ctx;
-  float* acc = r->stats.as<float>() + 8;
-  CU_TRY(cudaMemsetAsync(acc, 0, 4, ctx->stream));
   Planes vk = r->vk.view(rows, r->V, r->last_vk_parts);
   if (r->units_now) {  // the last step's v_neg of the GLOBAL minibatch: this rank's rows sit at rank * rows
     vk = (r->chains_g_rows == r->last_rows && r->chains_g.buf[0].p != nullptr && r->units_pcd ? r->chains_g : r->vk)
              .view(rows, r->V, 1);
     vk.p[0] += static_cast<int64_t>(ctx->rank) * (r->last_rows / ctx->world) * vk.ld;
   }
+  if (rows * r->V <= (1 << 18) && v0.n == 1 && vk.n == 1) {  // latency-bound: one launch of one block
+    recon_small_kernel<<<1, 1024, 0, ctx->stream>>>(v0.p[0], v0.ld, vk.p[0], vk.ld, static_cast<int32_t>(rows),
+                                                    static_cast<int32_t>(r->V), v0_dyn, r->stats.as<float>(), log_dyn,
+                                                    log_batch, host_log);
+    ctx->tm.aux_launches++;
+    CU_TRY(cudaGetLastError());
+    return KUCD_OK;
+  }
+  float* acc = r->stats.as<float>() + 8;
+  CU_TRY(cudaMemsetAsync(acc, 0, 4, ctx->stream));
   recon_kernel<<<grid_for(ctx, rows * r->V, 256), 256, 0, ctx->stream>>>(
       v0.p[0], v0.mid(), v0.lo(), v0.ld, 0, vk.p[0], vk.mid(), vk.lo(), vk.ld, static_cast<int32_t>(rows),
       static_cast<int32_t>(r->V), v0_dyn, acc);
   recon_finish_kernel<<<1, 1, 0, ctx->stream>>>(acc, static_cast<int32_t>(rows), static_cast<int32_t>(r->V), v0_dyn,
                                                 r->stats.as<float>());
   ctx->tm.aux_launches += 2;
+  if (host_log != nullptr) {
+    log_stat_kernel<<<1, 1, 0, ctx->stream>>>(r->stats.as<float>() + 1, log_dyn, log_batch, host_log);
+    ctx->tm.aux_launches++;
+  }
   CU_TRY(cudaGetLastError());
   return KUCD_OK;
 }
@@ -2977,9 +3009,7 @@ static int fit_host_chunked(kucd_rbm* r, const kucd_tensor* V_all, int64_t batch
     CU_TRY(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed));
     int crc = enqueue_cd(r, block, batch, hp, nullptr, global_row0, 0, dyn, true);
     if (crc == KUCD_OK && host_stats != nullptr) {
-      crc = enqueue_recon(r, block, batch, dyn);
-      log_stat_kernel<<<1, 1, 0, ctx->stream>>>(r->stats.as<float>() + 1, dyn, static_cast<int32_t>(batch), host_stats);
-      ctx->tm.aux_launches++;
+      crc = enqueue_recon(r, block, batch, dyn, host_stats, dyn, static_cast<int32_t>(batch));
     }
     bool advanced = false;
     if (crc == KUCD_OK) crc = apply_update(r, hp, batch * ctx->world, dyn, static_cast<int32_t>(batch), no_end, &advanced);
@@ -3237,9 +3267,7 @@ int kucd_rbm_fit_host(kucd_rbm* r, const kucd_tensor* V_all, int64_t batch, cons
       v0.n = live;
       int crc = enqueue_cd(r, v0, batch, hp, nullptr, global_row0, 0, dyn, false);
       if (crc == KUCD_OK && host_stats != nullptr) {
-        crc = enqueue_recon(r, v0, batch);
-        log_stat_kernel<<<1, 1, 0, ctx->stream>>>(r->stats.as<float>() + 1, dyn, static_cast<int32_t>(batch), host_stats);
-        ctx->tm.aux_launches++;
+        crc = enqueue_recon(r, v0, batch, nullptr, host_stats, dyn, static_cast<int32_t>(batch));
       }
       bool advanced = false;
       if (crc == KUCD_OK) crc = apply_update(r, hp, batch * ctx->world, dyn, static_cast<int32_t>(batch), no_end, &advanced);

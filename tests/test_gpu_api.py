@@ -69,8 +69,9 @@ def test_rbm_reference_schedule_mode(ctx, capsys):
     out = capsys.readouterr().out
     assert out.count("score:") == 3 and "3/3, score:" in out
     t = ctx.timings()
-    # per step: 3 runs x (3 projections + dW) + score (2 projections + 2 free energies) = 16 contractions
-    assert t["gemm_launches"] == 3 * 16
+    # per step: 3 runs x (the chain kernel with the 3 projections + the float32-grade dW contraction) + score (2 projections
+    # + 2 free energies) = 10 contraction launches
+    assert t["gemm_launches"] == 3 * 10 and t["chain_launches"] == 3 * 3
 
 
 def test_dbn_greedy_pretraining(ctx, capsys):

@@ -631,3 +631,43 @@ def test_float32_grade_chain_kernels_equal_per_projection_launches(monkeypatch):
         assert c_chain.timings()["chain_launches"] > 0 and c_plain.timings()["chain_launches"] == 0
         c_chain.close()
         c_plain.close()
+
+
+def test_mid_chain_variant_equals_per_projection_launches(monkeypatch):
+    """Minibatches too short for 74 pair tiles per stage but with >= 32 tiles of 128 x 256 (a 512-row shard of a
+    4096-wide layer): chain_kernel<256, 1> - the flattened chain on single CTAs.  Bit-identical states and dW to the
+    launch-per-projection path; CD-2 at a ragged row count, then graph replay with a remainder minibatch."""
+    from keras_unsupervised_b200 import _lib as L
+    from keras_unsupervised_b200.engine import Context, Dataset, Machine
+
+    monkeypatch.delenv("KUCD_CHAIN", raising=False)
+    c_mid = Context(device=0, seed=1)
+    monkeypatch.setenv("KUCD_CHAIN", "0")
+    c_plain = Context(device=0, seed=1)
+    rng = np.random.default_rng(137)
+    V, H, rows = 2048, 2304, 600
+    ms = [_machine(c, V, H, "bf16", seed=41)[0] for c in (c_mid, c_plain)]
+    v = _data(rng, rows, V, 0.3)
+    hp = Machine.hparams(lr=1e-3, k=2, update_mask=0)
+    got = []
+    for m in ms:
+        m.cd_step(v, hp)
+        got.append(m.last_stats(rows))
+    assert c_mid.timings()["chain_launches"] == 1 and c_mid.timings()["chain_dw_launches"] == 0
+    for key in ("h_pos", "v_neg", "h_neg", "dW", "db"):
+        assert np.array_equal(got[0][key], got[1][key]), key
+    np.testing.assert_allclose(got[0]["dc"], got[1]["dc"], rtol=0, atol=2e-3)
+    data = _data(rng, 2 * 512 + 200, V, 0.3)
+    hp = Machine.hparams(lr=1e-3, k=1)
+    params = []
+    for c, m in zip((c_mid, c_plain), ms):
+        ds = Dataset.from_array(c, data, L.COMPUTE_BF16)
+        m.fit_epoch(ds, 512, hp)
+        c.sync()
+        params.append(m.get_params())
+        ds.close()
+    for i in range(3):
+        np.testing.assert_allclose(params[0][i], params[1][i], rtol=0, atol=1e-6)
+    assert c_plain.timings()["chain_launches"] == 0
+    c_mid.close()
+    c_plain.close()
