@@ -5,7 +5,8 @@ served by tests/golden/kshim.py):
 
     python tests/golden/make_reference_fixtures.py
 
-Writes tests/golden/ref_rbm_bernoulli.npz, ref_rbm_gaussian.npz and ref_dbn.json.  The tests that consume
+Writes tests/golden/ref_rbm_{bernoulli,gaussian}.npz (64 -> 64, batch 16, 4 minibatches), ref_rbm_{bernoulli,gaussian}_128.npz
+(128 -> 128, batch 32, 8 minibatches, other seeds and learning rate) and ref_dbn.json.  The tests that consume
 them (tests/test_oracle_vs_reference.py) run anywhere: they never read /root/reference.
 
 What can be executed of the reference, and how:
@@ -38,8 +39,14 @@ sys.path.insert(0, HERE)
 import kshim  # noqa: E402
 
 
-def run_rbm(mode_name, out_dir=HERE):
-    kshim.REC = kshim.Recorder(seed=7, param_seed=0)
+# the second size widens the pin: a larger layer, a larger minibatch, twice as many minibatches, other seeds and rate
+SIZES = {"": dict(V=64, B=16, N=80, lr=0.01, seed=7, param_seed=0, data_seed=1234),
+         "_128": dict(V=128, B=32, N=288, lr=0.003, seed=11, param_seed=5, data_seed=4321)}
+
+
+def run_rbm(mode_name, out_dir=HERE, size=""):
+    sz = SIZES[size]
+    kshim.REC = kshim.Recorder(seed=sz["seed"], param_seed=sz["param_seed"])
     kshim.Function._count = 0
     kshim.install("/root/reference")
     for name in [n for n in sys.modules if n.startswith("ku.ebm.")]:
@@ -49,14 +56,14 @@ def run_rbm(mode_name, out_dir=HERE):
     rbm_mod = importlib.import_module("ku.ebm.rbm")
     assert rbm_mod.__file__ == "/root/reference/ku/ebm/rbm.py", rbm_mod.__file__
     mode = rbm_mod.MODE_VISIBLE_BERNOULLI if mode_name == "bernoulli" else rbm_mod.MODE_VISIBLE_GAUSSIAN
-    V = H = 64
-    B, N = 16, 80
-    hps = {"batch_size": B, "epochs": 2, "lr": 0.01}
+    V = H = sz["V"]
+    B, N = sz["B"], sz["N"]
+    hps = {"batch_size": B, "epochs": 2, "lr": sz["lr"]}
     rbm = rbm_mod.RBM(hps, H, name="rbm", mode=mode)
     rbm.build((None, V))
     W0, c0, b0 = rbm.rbm_weight.value.copy(), rbm.hidden_bias.value.copy(), rbm.visible_bias.value.copy()
 
-    data_rng = np.random.default_rng(1234)
+    data_rng = np.random.default_rng(sz["data_seed"])
     if mode_name == "bernoulli":
         X = (data_rng.random((N, V)) < 0.3).astype(np.float32)
     else:
@@ -107,12 +114,12 @@ def run_rbm(mode_name, out_dir=HERE):
     printed = [float(l.split("score:")[1]) for l in out.getvalue().splitlines() if "score:" in l]
     assert len(printed) == steps and np.allclose(printed, scores, atol=1e-6)
     np.savez_compressed(
-        os.path.join(out_dir, "ref_rbm_%s.npz" % mode_name), X=X, W0=W0, b0=b0, c0=c0, lr=np.float32(hps["lr"]),
+        os.path.join(out_dir, "ref_rbm_%s%s.npz" % (mode_name, size)), X=X, W0=W0, b0=b0, c0=c0, lr=np.float32(hps["lr"]),
         batch=np.int64(B), steps=np.int64(steps), scores=np.array(scores, np.float64),
         W_final=rbm.rbm_weight.value, b_final=rbm.visible_bias.value, c_final=rbm.hidden_bias.value,
         fit_error=np.array(err), config=np.array(json.dumps(rbm.get_config(), default=str)),
         **{"infer_" + k: v for k, v in infer.items()}, **arrays)
-    print(mode_name, "steps executed:", steps, "| reference raised:", err, "| scores:", np.round(scores, 4))
+    print(mode_name + size, "steps executed:", steps, "| reference raised:", err, "| scores:", np.round(scores, 4))
 
 
 def run_dbn(out_dir=HERE):
@@ -167,6 +174,7 @@ def run_dbn(out_dir=HERE):
 
 
 if __name__ == "__main__":
-    run_rbm("bernoulli")
-    run_rbm("gaussian")
+    for size in SIZES:
+        run_rbm("bernoulli", size=size)
+        run_rbm("gaussian", size=size)
     run_dbn()

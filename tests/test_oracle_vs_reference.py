@@ -2,6 +2,7 @@
 /root/reference/ku/ebm/rbm.py (on tests/golden/kshim.py, a numpy stand-in for the keras backend) are
 replayed through oracle/cd_oracle.py with the same recorded random draws.
 
+Two sizes (64 -> 64 with minibatches of 16; 128 -> 128 with minibatches of 32, other seeds and learning rate).
 The fixtures cover what the reference can execute at HEAD (see make_reference_fixtures.py): build,
 transform_func / inv_transform_func / free_energy_func, and the first N/B - 1 minibatches of fit() -
 runs A, B, C, the two free energies, run D and the printed score (rbm.py:214-234) - in both modes.
@@ -21,9 +22,10 @@ def _load(name):
     return np.load(os.path.join(GOLD, name), allow_pickle=False)
 
 
+@pytest.mark.parametrize("size", ["", "_128"])
 @pytest.mark.parametrize("mode_name,mode", [("bernoulli", O.MODE_VISIBLE_BERNOULLI), ("gaussian", O.MODE_VISIBLE_GAUSSIAN)])
-def test_inference_functions(mode_name, mode):
-    g = _load("ref_rbm_%s.npz" % mode_name)
+def test_inference_functions(mode_name, mode, size):
+    g = _load("ref_rbm_%s%s.npz" % (mode_name, size))
     orc = O.OracleRBM(g["W0"], g["b0"], g["c0"], mode=mode, compute="f32")
     h, _ = orc.sample_h(g["infer_x"], g["infer_u_h"])                  # rbm.py:45-48 / :57-60
     assert np.array_equal(h, g["infer_h"])
@@ -35,9 +37,10 @@ def test_inference_functions(mode_name, mode):
     np.testing.assert_allclose(orc.free_energy(g["infer_x"]), g["infer_fe"], rtol=1e-6)   # rbm.py:73-76
 
 
+@pytest.mark.parametrize("size", ["", "_128"])
 @pytest.mark.parametrize("mode_name,mode", [("bernoulli", O.MODE_VISIBLE_BERNOULLI), ("gaussian", O.MODE_VISIBLE_GAUSSIAN)])
-def test_fit_schedule_replayed(mode_name, mode):
-    g = _load("ref_rbm_%s.npz" % mode_name)
+def test_fit_schedule_replayed(mode_name, mode, size):
+    g = _load("ref_rbm_%s%s.npz" % (mode_name, size))
     orc = O.OracleRBM(g["W0"], g["b0"], g["c0"], mode=mode, compute="f32")
     X, B, lr = g["X"], int(g["batch"]), float(g["lr"])
     steps = int(g["steps"])
@@ -113,12 +116,14 @@ def test_committed_fixtures_are_what_the_reference_produces(tmp_path, capsys):
     saved = {k: v for k, v in sys.modules.items() if k == "ku" or k.startswith(("ku.", "tensorflow"))}
     try:
         spec.loader.exec_module(gen)
-        for mode in ("bernoulli", "gaussian"):
-            gen.run_rbm(mode, out_dir=str(tmp_path))
-            new, old = np.load(tmp_path / ("ref_rbm_%s.npz" % mode)), _load("ref_rbm_%s.npz" % mode)
-            assert sorted(new.files) == sorted(old.files)
-            for key in old.files:
-                assert np.array_equal(new[key], old[key]), (mode, key)
+        for size in gen.SIZES:
+            for mode in ("bernoulli", "gaussian"):
+                gen.run_rbm(mode, out_dir=str(tmp_path), size=size)
+                name = "ref_rbm_%s%s.npz" % (mode, size)
+                new, old = np.load(tmp_path / name), _load(name)
+                assert sorted(new.files) == sorted(old.files)
+                for key in old.files:
+                    assert np.array_equal(new[key], old[key]), (name, key)
         gen.run_dbn(out_dir=str(tmp_path))
         assert json.load(open(tmp_path / "ref_dbn.json")) == json.load(open(os.path.join(GOLD, "ref_dbn.json")))
     finally:
