@@ -398,6 +398,7 @@ def _main(out):
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-f32-grade", action="store_true", help="skip the float32-grade figure of the c3 line (profiling runs)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: the workload's minibatch PER GPU (default, what the metric is quoted on); strong: that "
                          "minibatch is the GLOBAL one, split by rows over the GPUs (SURVEY.md 8d: report both - the weak "
@@ -711,7 +712,7 @@ def _main(out):
     # ---- the reference's own precision beside the bf16 headline (rbm.py:39 K.floatx() = float32): the same workload
     # with float32-grade contractions (three bf16 terms per operand), a few steps -----------------------------------
     f32_grade = None
-    if args.workload == "c3" and world == 1:
+    if args.workload == "c3" and world == 1 and not args.no_f32_grade:
         try:
             barrier()
             m32 = Machine(ctx, V, H, L.MODE_VISIBLE_BERNOULLI, L.COMPUTE_F32X3, seed=42)

@@ -68,6 +68,15 @@ typedef struct kucd_tensor {
   int64_t strides[2];
 } kucd_tensor;
 
+/* Describe a DLPack tensor.  `dl_managed_tensor` is the `DLManagedTensor*` a producer hands out inside its "dltensor"
+ * capsule (tf.experimental.dlpack.to_dlpack(x), x.__dlpack__() of torch / jax / cupy / numpy >= 1.22): its dl_tensor maps
+ * onto kucd_tensor field by field (data + byte_offset, device, dtype, shape, strides in elements; NULL strides = compact
+ * row-major).  1-D tensors become (n, 1).  The descriptor BORROWS the producer's memory: the caller keeps the capsule
+ * alive for the duration of the engine call and lets its deleter run afterwards.  Nothing is copied; no device is
+ * touched (works without a GPU).  KUCD_ERR_INVALID_ARG: more than two dimensions, vector lanes, an innermost stride
+ * other than 1; KUCD_ERR_UNSUPPORTED_DTYPE: not float32 / bfloat16 / uint8 / bool. */
+int kucd_tensor_from_dlpack(const void* dl_managed_tensor, kucd_tensor* out);
+
 /* visible-unit mode: constants of rbm.py:14-16 */
 #define KUCD_MODE_VISIBLE_BERNOULLI 0
 #define KUCD_MODE_VISIBLE_GAUSSIAN 1

@@ -115,6 +115,7 @@ SIGNATURES = {
                                       C.POINTER(EpochStats)]),
     "kucd_rbm_fit_host": (C.c_int, [_P, _TP, C.c_int64, C.POINTER(HParams), C.c_int64, C.POINTER(C.c_float),
                                      C.POINTER(EpochStats)]),
+    "kucd_tensor_from_dlpack": (C.c_int, [_P, _TP]),
     "kucd_rbm_transform_dataset": (C.c_int, [_P, _P, C.POINTER(_P)]),
     "kucd_rbm_inv_transform_dataset": (C.c_int, [_P, _P, C.POINTER(_P)]),
 }
@@ -177,6 +178,10 @@ def _is_torch(x) -> bool:
     return type(x).__module__.split(".")[0] == "torch"
 
 
+def _is_capsule(x) -> bool:
+    return type(x).__name__ == "PyCapsule"
+
+
 def tensor_of(x, keep: list) -> Tensor:
     """Describe a numpy array or a torch tensor (CPU, pinned or CUDA) as a kucd_tensor without copying
     when its layout allows it.  Objects that must outlive the call are appended to `keep`."""
@@ -217,10 +222,19 @@ def tensor_of(x, keep: list) -> Tensor:
         s0 = t.stride(0) if t.shape[0] > 1 else max(t.shape[1], 1)
         return Tensor(t.data_ptr(), dev, dev_id, code, bits, (C.c_int64 * 2)(*t.shape), (C.c_int64 * 2)(s0, 1))
 
-    if hasattr(x, "__dlpack__") and not isinstance(x, np.ndarray):  # any other DLPack producer (e.g. TF)
-        import torch
-
-        return tensor_of(torch.from_dlpack(x), keep)
+    if _is_capsule(x) or (hasattr(x, "__dlpack__") and not isinstance(x, np.ndarray)):
+        # any other DLPack producer (TensorFlow: tf.experimental.dlpack.to_dlpack(t), jax, cupy ...) or a raw "dltensor"
+        # capsule: the library reads the DLManagedTensor itself (kucd_tensor_from_dlpack) - no torch in between.  The
+        # capsule stays unconsumed in `keep`; when it is dropped after the call its own destructor runs the deleter.
+        cap = x if _is_capsule(x) else x.__dlpack__()
+        C.pythonapi.PyCapsule_GetPointer.restype = C.c_void_p
+        C.pythonapi.PyCapsule_GetPointer.argtypes = [C.py_object, C.c_char_p]
+        ptr = C.pythonapi.PyCapsule_GetPointer(cap, b"dltensor")
+        t = Tensor()
+        check(load().kucd_tensor_from_dlpack(C.c_void_p(ptr), C.byref(t)))
+        keep.append(cap)
+        keep.append(x)
+        return t
 
     a = np.asarray(x)
     if a.ndim == 1:

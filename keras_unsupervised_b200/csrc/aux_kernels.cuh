@@ -755,10 +755,10 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
 // All-to-all arrival barrier between the ranks' streams: everything this rank wrote into peer memory before this
 // kernel is visible to a peer once the peer has seen this rank's flag.  One thread per peer.
 __global__ void peer_barrier_kernel(uint32_t* epoch, PeerSet ps, int me, int n) {
-  __shared__ uint32_t e_sh;
-  if (threadIdx.x == 0) e_sh = ++(*epoch);
-  __syncthreads();
-  const uint32_t e = e_sh;
+  // one warp, no shared memory (see pack_push_kernel)
+  uint32_t e = 0;
+  if (threadIdx.x == 0) e = ++(*epoch);
+  e = __shfl_sync(0xffffffffu, e, 0);
   const int j = threadIdx.x;
   if (j >= n) return;
   __threadfence_system();
@@ -866,31 +866,36 @@ __global__ void __launch_bounds__(256) pack_push_kernel(const __nv_bfloat16* __r
                                                         const StepDyn* dyn, int64_t rows, int64_t col_lo, int64_t cols,
                                                         PeerSet ps, int n, int slot, int64_t dst_row0,
                                                         int64_t pitch_bytes) {
-  __shared__ __align__(16) uint8_t sh[256];
+  // No shared memory (sixteen lanes assemble a 16-byte piece with shuffles): a block of this kernel then fits next to a
+  // persistent contraction CTA that holds all but the last KB of an SM's shared memory, so an exchange on the second
+  // stream really runs while an independent projection computes.
   const int64_t row_off = dyn != nullptr ? dyn->row_off : 0;
-  const int64_t groups_per_row = cols / 8;  // bytes of one row of the rectangle
+  const int64_t groups_per_row = cols / 8;  // bytes of one row of the rectangle (a multiple of 16)
   const int64_t total = rows * groups_per_row;
+  const uint32_t lane = threadIdx.x & 31u;
   for (int64_t base = static_cast<int64_t>(blockIdx.x) * 256; base < total; base += static_cast<int64_t>(gridDim.x) * 256) {
-    const int64_t g = base + threadIdx.x;
+    const int64_t g = base + threadIdx.x;  // total is a multiple of 16: a 16-lane group is inside or outside as a whole
     uint32_t b = 0;
+    int64_t r = 0, c8 = 0;
     if (g < total) {
-      const int64_t r = g / groups_per_row, c8 = g - r * groups_per_row;
+      r = g / groups_per_row;
+      c8 = g - r * groups_per_row;
       const uint4 q = *reinterpret_cast<const uint4*>(src + (row_off + r) * ld + col_lo + 8 * c8);
       const Bf16x8 v{{q.x, q.y, q.z, q.w}};
       b = bf16x8_to_bits(v, 8);
     }
-    sh[threadIdx.x] = static_cast<uint8_t>(b);
-    __syncthreads();
-    if (threadIdx.x < 16) {
-      const int64_t g16 = base + 16 * threadIdx.x;  // first byte of this 16-byte piece
-      if (g16 < total) {
-        const int64_t r = g16 / groups_per_row, c8 = g16 - r * groups_per_row;
-        const uint4 piece = reinterpret_cast<const uint4*>(sh)[threadIdx.x];
-        const int64_t off = static_cast<int64_t>(slot) * kBitSlotBytes + (dst_row0 + r) * pitch_bytes + (col_lo >> 3) + c8;
-        for (int j = 0; j < n; ++j) *reinterpret_cast<uint4*>(ps.bits[j] + off) = piece;
-      }
+    // lane l (l % 4 == 0) collects bytes l .. l+3; lane l (l % 16 == 0) collects the four words of its 16 bytes
+    uint32_t w = b | (__shfl_down_sync(0xffffffffu, b, 1) << 8) | (__shfl_down_sync(0xffffffffu, b, 2) << 16) |
+                 (__shfl_down_sync(0xffffffffu, b, 3) << 24);
+    uint4 piece;
+    piece.x = w;
+    piece.y = __shfl_down_sync(0xffffffffu, w, 4);
+    piece.z = __shfl_down_sync(0xffffffffu, w, 8);
+    piece.w = __shfl_down_sync(0xffffffffu, w, 12);
+    if ((lane & 15u) == 0 && g < total) {
+      const int64_t off = static_cast<int64_t>(slot) * kBitSlotBytes + (dst_row0 + r) * pitch_bytes + (col_lo >> 3) + c8;
+      for (int j = 0; j < n; ++j) *reinterpret_cast<uint4*>(ps.bits[j] + off) = piece;
     }
-    __syncthreads();
   }
 }
 

@@ -181,6 +181,7 @@ struct kucd_ctx {
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;  // second Gibbs chain of a split minibatch
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_units[4] = {};  // unit-sharded step: exchanges on stream2 next to independent projections
   cudaStream_t copy_stream = nullptr;  // host -> device staging of the next minibatch (fit_host)
   // slab-pipelined all-reduce (KUCD_AR_SLABS): dW leaves in row slabs on comm_stream while the next slab is contracted
   static constexpr int kMaxSlabs = 16;
@@ -389,13 +390,13 @@ static bool capturing(const kucd_ctx* ctx) {
   return st != cudaStreamCaptureStatusNone;
 }
 
-static size_t prof_event(kucd_ctx* ctx) {
+static size_t prof_event(kucd_ctx* ctx, cudaStream_t st = nullptr) {
   if (ctx->ev_used == ctx->ev_pool.size()) {
     cudaEvent_t e;
     cudaEventCreate(&e);
     ctx->ev_pool.push_back(e);
   }
-  cudaEventRecord(ctx->ev_pool[ctx->ev_used], ctx->stream);
+  cudaEventRecord(ctx->ev_pool[ctx->ev_used], st != nullptr ? st : ctx->stream);
   return ctx->ev_used++;
 }
 
@@ -1254,8 +1255,9 @@ static int launch_chain(kucd_rbm* r, const Planes& v0, int64_t batch, const kucd
                         uint64_t draw0, uint64_t stride, const StepDyn* dyn, bool v0_dyn, bool with_dw, int variant) {
   // variant 0: CTA pairs on 256 x 256 tiles; 1: single CTAs on 128 x 64 tiles (latency-bound sizes); 2: single CTAs on
   // 128 x 256 tiles (minibatches too short to give every CTA pair a 256-row tile, e.g. a 512-row shard of 4096 -> 4096)
+  // variant 3: single CTAs on 128 x 128 tiles (twice the tiles of variant 2 for the same stage)
   const bool small = variant == 1;
-  const int bn = small ? 64 : kChainBN, cg = variant == 0 ? 2 : 1;
+  const int bn = small ? 64 : (variant == 3 ? 128 : kChainBN), cg = variant == 0 ? 2 : 1;
   const int tile_m = kBlockM * cg;
   kucd_ctx* ctx = r->ctx;
   const int k = hp->k;
@@ -1402,6 +1404,8 @@ static int launch_chain(kucd_rbm* r, const Planes& v0, int64_t batch, const kucd
   int rc;
   if (variant == 2)
     rc = launch_chain_kernel<kChainBN, 1, false>(ctx, p, total, prof, &pe0);
+  else if (variant == 3)
+    rc = launch_chain_kernel<128, 1, false>(ctx, p, total, prof, &pe0);
   else if (f32)
     rc = small ? launch_chain_kernel<64, 1, false, kPreciseCH>(ctx, p, total, prof, &pe0)
                : launch_chain_kernel<kChainBN, 2, false, kPreciseCH>(ctx, p, total, prof, &pe0);
@@ -1424,22 +1428,23 @@ static int launch_chain(kucd_rbm* r, const Planes& v0, int64_t batch, const kucd
 // in_place: the rectangle was computed into G itself (a slice of the units, all rows) - it is not expanded again.
 static int units_exchange(kucd_rbm* r, int& ex, const __nv_bfloat16* src, int64_t src_ld, const StepDyn* src_dyn,
                           int64_t rows, int64_t dst_row0, int64_t col_lo, int64_t cols, const Planes& G,
-                          bool in_place = false) {
+                          bool in_place = false, cudaStream_t st = nullptr) {
   kucd_ctx* ctx = r->ctx;
+  if (st == nullptr) st = ctx->stream;
   const int slot = ex++ & 1;
   const int64_t pitch = G.cols / 8;
   const int64_t total = rows * cols / 8;
   const bool prof = ctx->profile && !capturing(ctx);
-  const size_t pe0 = prof ? prof_event(ctx) : 0;
-  pack_push_kernel<<<grid_for(ctx, total, 256), 256, 0, ctx->stream>>>(src, src_ld, src_dyn, rows, col_lo, cols, r->ps,
-                                                                      ctx->world, slot, dst_row0, pitch);
-  peer_barrier_kernel<<<1, 32, 0, ctx->stream>>>(r->epoch, r->ps, ctx->rank, ctx->world);
-  ingest_bits_kernel<<<grid_for(ctx, G.rows * (G.ld / 8), 256), 256, 0, ctx->stream>>>(
+  const size_t pe0 = prof ? prof_event(ctx, st) : 0;
+  pack_push_kernel<<<grid_for(ctx, total, 256), 256, 0, st>>>(src, src_ld, src_dyn, rows, col_lo, cols, r->ps, ctx->world,
+                                                             slot, dst_row0, pitch);
+  peer_barrier_kernel<<<1, 32, 0, st>>>(r->epoch, r->ps, ctx->rank, ctx->world);
+  ingest_bits_kernel<<<grid_for(ctx, G.rows * (G.ld / 8), 256), 256, 0, st>>>(
       r->ps.bits[ctx->rank] + static_cast<int64_t>(slot) * kBitSlotBytes, pitch, G.rows, G.cols, G.p[0], nullptr, nullptr,
       G.ld, 1, in_place ? col_lo : 0, in_place ? col_lo + cols : 0);
   ctx->tm.aux_launches += 3;
   ctx->tm.unit_exchanges++;
-  if (prof) ctx->marks.push_back({2, pe0, prof_event(ctx), 1});
+  if (prof) ctx->marks.push_back({2, pe0, prof_event(ctx, st), 1});
   CU_TRY(cudaGetLastError());
   return KUCD_OK;
 }
@@ -1461,16 +1466,6 @@ static int enqueue_cd_units(kucd_rbm* r, const Planes& v0_local, int64_t b, cons
   // the last back-projection overwrites them - no copy
   const Planes Gvk = pcd ? r->chains_g.view(Bg, r->V, 1) : r->vk.view(Bg, r->V, 1);
   int ex = 0;
-  // the global minibatch on every rank
-  KU_TRY(units_exchange(r, ex, v0_local.p[0], v0_local.ld, v0_dyn ? dyn : nullptr, b, me * b, 0, r->V, Gv0));
-  CU_TRY(cudaMemsetAsync(r->db(), 0, (r->ldVb() + r->ldHb()) * 4, ctx->stream));
-  {  // db[own visibles] += sum_rows v0   (rbm.py:134)
-    dim3 grid(static_cast<unsigned>((Vs / 2 + 1 + 127) / 128), static_cast<unsigned>((Bg + 63) / 64));
-    colsum_kernel<<<grid, 128, 0, ctx->stream>>>(Gv0.p[0] + v_lo, nullptr, nullptr, Gv0.ld, 0, static_cast<int32_t>(Bg),
-                                                 static_cast<int32_t>(Vs), nullptr, 1.f, r->db() + v_lo);
-    ctx->tm.aux_launches++;
-    CU_TRY(cudaGetLastError());
-  }
   auto stage = [&](bool forward, const Planes& a, const Planes& out, int epi, int phase, float* colsum, float sign) -> int {
     EpiArgs e;
     e.epi = epi;
@@ -1486,24 +1481,59 @@ static int enqueue_cd_units(kucd_rbm* r, const Planes& v0_local, int64_t b, cons
     e.n_cnt = forward ? Hs : Vs;
     return project(r, forward, a, Bg, e);
   };
-  auto share_h = [&](const Planes& G) { return units_exchange(r, ex, G.p[0], G.ld, nullptr, Bg, 0, h_lo, Hs, G, true); };
+  auto share_h = [&](const Planes& G, cudaStream_t st) {
+    return units_exchange(r, ex, G.p[0], G.ld, nullptr, Bg, 0, h_lo, Hs, G, true, st);
+  };
   auto share_v = [&](const Planes& G) { return units_exchange(r, ex, G.p[0], G.ld, nullptr, Bg, 0, v_lo, Vs, G, true); };
-
-  KU_TRY(stage(true, Gv0, Gh0, kEpiSample, 0, r->dc(), 1.f));  // h_pos   rbm.py:120
-  // (with persistent chains nobody back-projects h_pos: only this rank's slice of it is ever read, by dW and dc)
-  if (!pcd) KU_TRY(share_h(Gh0));
+  // Exchanges whose result the NEXT projection does not need run on the second stream, next to that projection (their
+  // kernels use no shared memory and few registers, so their blocks fit beside the persistent contraction CTAs): the
+  // gather of the minibatch next to the chain's first projection, the exchange of that projection's states next to the
+  // positive-phase projection.  KUCD_UNITS_OVERLAP=0: everything in order on one stream.
+  static const bool overlap_env = [] {
+    const char* e = getenv("KUCD_UNITS_OVERLAP");
+    return !(e != nullptr && e[0] == '0');
+  }();
+  const bool overlap = overlap_env && pcd;
+  cudaStream_t s2 = overlap ? ctx->stream2 : ctx->stream;
+  CU_TRY(cudaMemsetAsync(r->db(), 0, (r->ldVb() + r->ldHb()) * 4, ctx->stream));
+  if (overlap) {
+    CU_TRY(cudaEventRecord(ctx->ev_units[0], ctx->stream));
+    CU_TRY(cudaStreamWaitEvent(s2, ctx->ev_units[0], 0));
+  }
+  // the global minibatch on every rank
+  KU_TRY(units_exchange(r, ex, v0_local.p[0], v0_local.ld, v0_dyn ? dyn : nullptr, b, me * b, 0, r->V, Gv0, false, s2));
+  {  // db[own visibles] += sum_rows v0   (rbm.py:134)
+    dim3 grid(static_cast<unsigned>((Vs / 2 + 1 + 127) / 128), static_cast<unsigned>((Bg + 63) / 64));
+    colsum_kernel<<<grid, 128, 0, s2>>>(Gv0.p[0] + v_lo, nullptr, nullptr, Gv0.ld, 0, static_cast<int32_t>(Bg),
+                                        static_cast<int32_t>(Vs), nullptr, 1.f, r->db() + v_lo);
+    ctx->tm.aux_launches++;
+    CU_TRY(cudaGetLastError());
+  }
+  if (overlap) CU_TRY(cudaEventRecord(ctx->ev_units[1], s2));
   Planes hcur = Gh0;
   if (pcd) {  // the negative chain starts at the stored fantasy particles
     KU_TRY(stage(true, Gvk, Ghk, kEpiSample, 1, nullptr, 0.f));
-    KU_TRY(share_h(Ghk));
+    if (overlap) {
+      CU_TRY(cudaEventRecord(ctx->ev_units[2], ctx->stream));
+      CU_TRY(cudaStreamWaitEvent(s2, ctx->ev_units[2], 0));
+    }
+    KU_TRY(share_h(Ghk, s2));
+    if (overlap) {
+      CU_TRY(cudaEventRecord(ctx->ev_units[3], s2));
+      CU_TRY(cudaStreamWaitEvent(ctx->stream, ctx->ev_units[1], 0));  // the gathered minibatch
+    }
     hcur = Ghk;
   }
+  KU_TRY(stage(true, Gv0, Gh0, kEpiSample, 0, r->dc(), 1.f));  // h_pos   rbm.py:120
+  // (with persistent chains nobody back-projects h_pos: only this rank's slice of it is ever read, by dW and dc)
+  if (!pcd) KU_TRY(share_h(Gh0, ctx->stream));
+  if (overlap) CU_TRY(cudaStreamWaitEvent(ctx->stream, ctx->ev_units[3], 0));  // the chain's first hidden states
   for (int t = 1; t <= k; ++t) {
     const bool last = t == k;
     KU_TRY(stage(false, hcur, Gvk, kEpiSample, 2 * t, last ? r->db() : nullptr, -1.f));  // rbm.py:121-123
     KU_TRY(share_v(Gvk));
     KU_TRY(stage(true, Gvk, Ghk, last ? kEpiProb : kEpiSample, 2 * t + 1, last ? r->dc() : nullptr, -1.f));  // :124
-    if (!last) KU_TRY(share_h(Ghk));
+    if (!last) KU_TRY(share_h(Ghk, ctx->stream));
     hcur = Ghk;
   }
   // dW[:, own hidden units] = v0^T h0 - vk^T hk over the whole global minibatch   (rbm.py:125-126)
@@ -1688,7 +1718,13 @@ static int enqueue_cd(kucd_rbm* r, const Planes& v0, int64_t batch, const kucd_h
   if (whole_chain) {
     KU_TRY(launch_chain(r, v0, batch, hp, global_row0, draw0, stride, dyn, v0_dyn, chain_dw, 0));
   } else if (mid_chain) {
-    KU_TRY(launch_chain(r, v0, batch, hp, global_row0, draw0, stride, dyn, v0_dyn, false, 2));
+    // 128 x 256 tiles, or 128 x 128 when that still leaves SMs idle (KUCD_MID_BN=128|256 forces one)
+    static const int mid_bn_env = [] {
+      const char* e = getenv("KUCD_MID_BN");
+      return e != nullptr ? atoi(e) : 0;
+    }();
+    const bool narrow = mid_bn_env == 128 || (mid_bn_env != 256 && mid_tiles < ctx->num_sms * 3 / 4);
+    KU_TRY(launch_chain(r, v0, batch, hp, global_row0, draw0, stride, dyn, v0_dyn, false, narrow ? 3 : 2));
   } else if (small_chain) {
     KU_TRY(launch_chain(r, v0, batch, hp, global_row0, draw0, stride, dyn, v0_dyn, small_dw, 1));
   } else if (!two) {
@@ -1954,6 +1990,61 @@ extern "C" {
 int kucd_abi_version(void) { return KUCD_ABI_VERSION; }
 const char* kucd_last_error(void) { return g_err.c_str(); }
 
+// dlpack.h (v0.8 / v1.0 share this prefix): the part of DLManagedTensor this library reads
+namespace {
+struct DlDevice {
+  int32_t device_type, device_id;
+};
+struct DlDataType {
+  uint8_t code, bits;
+  uint16_t lanes;
+};
+struct DlTensor {
+  void* data;
+  DlDevice device;
+  int32_t ndim;
+  DlDataType dtype;
+  int64_t* shape;
+  int64_t* strides;
+  uint64_t byte_offset;
+};
+}  // namespace
+
+int kucd_tensor_from_dlpack(const void* dl_managed_tensor, kucd_tensor* out) {
+  if (dl_managed_tensor == nullptr || out == nullptr) return fail(KUCD_ERR_INVALID_ARG, "NULL argument");
+  const DlTensor& t = *static_cast<const DlTensor*>(dl_managed_tensor);  // dl_tensor is the first member
+  if (t.ndim < 1 || t.ndim > 2) return fail(KUCD_ERR_INVALID_ARG, "DLPack tensor has %d dimensions, expected 1 or 2", t.ndim);
+  if (t.dtype.lanes != 1) return fail(KUCD_ERR_INVALID_ARG, "DLPack tensor has %d vector lanes", (int)t.dtype.lanes);
+  int code = t.dtype.code, bits = t.dtype.bits;
+  if (code == 6 /* kDLBool */ && bits == 8) code = KUCD_DT_UINT;
+  const bool ok = (code == KUCD_DT_FLOAT && bits == 32) || (code == KUCD_DT_BFLOAT && bits == 16) ||
+                  (code == KUCD_DT_UINT && bits == 8);
+  if (!ok)
+    return fail(KUCD_ERR_UNSUPPORTED_DTYPE, "DLPack dtype code %d / %d bits is not float32, bfloat16, uint8 or bool",
+                (int)t.dtype.code, bits);
+  if (t.device.device_type != KUCD_DEV_CPU && t.device.device_type != KUCD_DEV_CUDA &&
+      t.device.device_type != KUCD_DEV_CUDA_HOST)
+    return fail(KUCD_ERR_INVALID_ARG, "DLPack device type %d is not CPU, CUDA or CUDA-pinned host", t.device.device_type);
+  const int64_t rows = t.shape[0], cols = t.ndim == 2 ? t.shape[1] : 1;
+  int64_t s0 = t.ndim == 2 ? cols : 1, s1 = 1;
+  if (t.strides != nullptr) {
+    s0 = t.strides[0];
+    s1 = t.ndim == 2 ? t.strides[1] : 1;
+  }
+  if (cols > 1 && s1 != 1) return fail(KUCD_ERR_INVALID_ARG, "DLPack tensor: innermost stride %lld, expected 1", (long long)s1);
+  if (rows <= 1) s0 = std::max<int64_t>(cols, 1);
+  out->data = static_cast<char*>(t.data) + t.byte_offset;
+  out->device_type = t.device.device_type;
+  out->device_id = t.device.device_id;
+  out->dtype_code = code;
+  out->bits = bits;
+  out->shape[0] = rows;
+  out->shape[1] = cols;
+  out->strides[0] = s0;
+  out->strides[1] = 1;
+  return KUCD_OK;
+}
+
 int kucd_ctx_create(kucd_ctx** out, int device_id, uint64_t seed) {
   if (out == nullptr) return fail(KUCD_ERR_INVALID_ARG, "out is NULL");
   *out = nullptr;
@@ -1990,6 +2081,7 @@ int kucd_ctx_create(kucd_ctx** out, int device_id, uint64_t seed) {
       CU_TRY(cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
       CU_TRY(cudaEventCreateWithFlags(&c->ev_consumed[i], cudaEventDisableTiming));
     }
+    for (auto& e : c->ev_units) CU_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     CU_TRY(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     CU_TRY(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     CU_TRY(cudaEventCreate(&c->ev0));
@@ -2043,6 +2135,7 @@ int kucd_ctx_destroy(kucd_ctx* ctx) {
   }
   drop_event(ctx->ev_fork);
   drop_event(ctx->ev_join);
+  for (cudaEvent_t e : ctx->ev_units) drop_event(e);
   for (int i = 0; i < kucd_ctx::kMaxSlabs; ++i) {
     drop_event(ctx->ev_slab[i]);
     drop_event(ctx->ev_red[i]);

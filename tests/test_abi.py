@@ -80,3 +80,36 @@ def test_product_never_imports_the_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text, f
                 assert "oracle/" not in text, f
+
+
+def test_dlpack_capsules_are_described_without_torch_or_a_gpu():
+    """kucd_tensor_from_dlpack: the library reads a producer's DLManagedTensor itself (TF's
+    tf.experimental.dlpack.to_dlpack hands out the same capsule), so the TF -> DLPack -> ctypes path needs no torch.
+    numpy is the producer here: data pointer, shape, element strides, dtype and device map field by field; unsupported
+    layouts and dtypes are refused with the library's own message."""
+    import numpy as np
+
+    from keras_unsupervised_b200 import _lib as L
+
+    a = np.arange(6 * 10, dtype=np.float32).reshape(6, 10)
+    keep = []
+    t = L.tensor_of(a.__dlpack__(), keep)                      # a raw "dltensor" capsule
+    assert t.data == a.ctypes.data and (t.shape[0], t.shape[1]) == (6, 10) and (t.strides[0], t.strides[1]) == (10, 1)
+    assert (t.device_type, t.dtype_code, t.bits) == (L.DEV_CPU, L.DT_FLOAT, 32)
+    view = a[1:5, 2:9]                                         # row pitch 10, offset data pointer
+
+    class Producer:                                            # anything with __dlpack__ that is neither numpy nor torch
+        def __dlpack__(self):
+            return view.__dlpack__()
+
+    t = L.tensor_of(Producer(), keep)
+    assert t.data == view.ctypes.data and (t.shape[0], t.shape[1]) == (4, 7) and t.strides[0] == 10
+    v = np.arange(5, dtype=np.uint8)
+    t = L.tensor_of(v.__dlpack__(), keep)                      # 1-D -> (n, 1)
+    assert (t.shape[0], t.shape[1], t.dtype_code, t.bits) == (5, 1, L.DT_UINT, 8)
+    with pytest.raises(ValueError, match="innermost stride"):
+        L.tensor_of(a.T.__dlpack__(), keep)
+    with pytest.raises(ValueError, match="not float32"):
+        L.tensor_of(a.astype(np.float64).__dlpack__(), keep)
+    with pytest.raises(ValueError, match="dimensions"):
+        L.tensor_of(np.zeros((2, 2, 2), np.float32).__dlpack__(), keep)
