@@ -180,6 +180,7 @@ struct kucd_ctx {
   uint64_t seed = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;  // second Gibbs chain of a split minibatch
+  cudaStream_t stream3 = nullptr;  // unit-sharded step: the positive-phase projection, beside the negative chain
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaEvent_t ev_units[4] = {};  // unit-sharded step: exchanges on stream2 next to independent projections
   cudaStream_t copy_stream = nullptr;  // host -> device staging of the next minibatch (fit_host)
@@ -732,11 +733,11 @@ static int project(kucd_rbm* r, bool forward, const Planes& a, int64_t rows, con
   p.a_dyn_mask = dyn_mask;
   std::string err;
   const bool prof = ctx->profile && e.dyn == nullptr && !e.no_prof;
-  const size_t pe0 = prof ? prof_event(ctx) : 0;
+  const size_t pe0 = prof ? prof_event(ctx, e.stream) : 0;
   if (!launch_gemm(p, ops, e.epi, ctx->num_sms, e.stream != nullptr ? e.stream : ctx->stream, &err, 0,
                    r->compute == KUCD_COMPUTE_F32X3))
     return fail(KUCD_ERR_CUDA, "%s", err.c_str());
-  if (prof) ctx->marks.push_back({0, pe0, prof_event(ctx), 1});
+  if (prof) ctx->marks.push_back({0, pe0, prof_event(ctx, e.stream), 1});
   ctx->tm.gemm_launches++;
   return KUCD_OK;
 }
@@ -952,30 +953,8 @@ static int apply_update(kucd_rbm* r, const kucd_hparams* hp, int64_t rows_global
       // slabs are still on the wire; the bias statistics travelled with slab 0, the tail rides on the last slab
       const int S = r->slabs_inflight;
       r->slabs_inflight = 0;
-      const bool solo = ctx->comm == nullptr;
       if (n4 == 0) {  // W is not updated by this call: just join the collective stream
-        if (!solo) CU_TRY(cudaStreamWaitEvent(ctx->stream, ctx->ev_red[S - 1], 0));
-      } else if (solo) {
-        // single rank: the update of slab i goes to the second stream behind that slab's contraction, so it streams
-        // through HBM while the tensor cores contract the later slabs.  The last one carries the bias update and the
-        // step-state advance, so it also waits for everything enqueued so far (statistics that read the step state).
-        CU_TRY(cudaEventRecord(ctx->ev_fork, ctx->stream));
-        for (int i = 0; i < S; ++i) {
-          CU_TRY(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_slab[i], 0));
-          if (i == S - 1) CU_TRY(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_fork, 0));
-          const int64_t w0 = i * r->slab_rows, wn = std::min<int64_t>(r->slab_rows, r->V - w0);
-          const int64_t off = w0 * r->ldH, m4 = wn * r->ldH / 4;
-          kern<<<grid_for(ctx, m4, 256), 256, 0, ctx->comm_stream>>>(
-              r->W32.as<float>() + off, r->dW() + off, use_mom ? r->mW.as<float>() + off : nullptr,
-              r->Wp.buf[0].as<__nv_bfloat16>() + off, nullptr, nullptr, m4, hp->lr, scale, hp->momentum, hp->weight_decay,
-              i == S - 1 ? tail : UpdateTail{}, sdyn, world);
-          ctx->tm.aux_launches++;
-        }
-        CU_TRY(cudaEventRecord(ctx->ev_red[0], ctx->comm_stream));
-        CU_TRY(cudaStreamWaitEvent(ctx->stream, ctx->ev_red[0], 0));
-        if (adv_done != nullptr) *adv_done = adv != nullptr;
-        CU_TRY(cudaGetLastError());
-        return KUCD_OK;
+        CU_TRY(cudaStreamWaitEvent(ctx->stream, ctx->ev_red[S - 1], 0));
       } else {
         for (int i = 0; i < S; ++i) {
           CU_TRY(cudaStreamWaitEvent(ctx->stream, ctx->ev_red[i], 0));
@@ -1087,13 +1066,15 @@ static int prepare_exchange(kucd_rbm* r, int64_t rows_per_rank, const kucd_hpara
     return e != nullptr ? atoi(e) : 1;
   }();
   r->slabs_now = 1;
-  // (single rank: no all-reduce, but the HBM-bound update of slab i still overlaps the tensor-bound contraction of slab
-  // i+1 - at C4's share the update is 0.29 ms of a 1.71 ms step; pointless below a few MiB of weights)
+  // (On a single rank the same slabs were tried as a way to hide the HBM-bound update behind the contraction of the next
+  // slab: measured -1.3 % at C3 with two slabs, +3 ... +7 % at C4's share with 2 ... 8 - profiles/r02_switches.md - and
+  // removed.)
   static const int64_t slab_min_elems = [] {  // tests lower it to exercise the path at small sizes
     const char* e = getenv("KUCD_AR_SLABS_MIN_ELEMS");
     return e != nullptr ? static_cast<int64_t>(atoll(e)) : (int64_t{1} << 22);
   }();
-  if (slabs_env > 1 && !r->fused_now && !r->units_now && r->compute == KUCD_COMPUTE_BF16 && r->V * r->ldH >= slab_min_elems) {
+  if (slabs_env > 1 && ctx->comm != nullptr && !r->fused_now && !r->units_now && r->compute == KUCD_COMPUTE_BF16 &&
+      r->V * r->ldH >= slab_min_elems) {
     const int want = std::min(slabs_env, kucd_ctx::kMaxSlabs);
     const int64_t rows = round_up((r->V + want - 1) / want, 256);
     const int n = static_cast<int>((r->V + rows - 1) / rows);
@@ -1245,7 +1226,17 @@ static int launch_chain_kernel(kucd_ctx* ctx, const ChainParams& p, int total, b
   cfg.gridDim = dim3(units * CG);
   cfg.stream = ctx->stream;
   *pe0 = prof ? prof_event(ctx) : 0;
-  CU_TRY(cudaLaunchKernelEx(&cfg, kern, p));
+  cudaError_t le = cudaLaunchKernelEx(&cfg, kern, p);
+  if (le != cudaSuccess && state[dev] == 2 && !capturing(ctx)) {
+    // the cooperative form was refused for this launch (seen under ncu, which cannot replay it): plain launches from here
+    // on - all CTAs still fit at once on an otherwise idle device, which is all the kernel needs
+    cudaGetLastError();
+    state[dev] = 1;
+    cfg.numAttrs = na - 1;
+    le = cudaLaunchKernelEx(&cfg, kern, p);
+  }
+  if (le != cudaSuccess)
+    return fail(KUCD_ERR_CUDA, "chain kernel launch failed: %s (%s:%d)", cudaGetErrorString(le), __FILE__, __LINE__);
   return KUCD_OK;
 }
 
@@ -1466,7 +1457,8 @@ static int enqueue_cd_units(kucd_rbm* r, const Planes& v0_local, int64_t b, cons
   // the last back-projection overwrites them - no copy
   const Planes Gvk = pcd ? r->chains_g.view(Bg, r->V, 1) : r->vk.view(Bg, r->V, 1);
   int ex = 0;
-  auto stage = [&](bool forward, const Planes& a, const Planes& out, int epi, int phase, float* colsum, float sign) -> int {
+  auto stage = [&](bool forward, const Planes& a, const Planes& out, int epi, int phase, float* colsum, float sign,
+                   cudaStream_t st = nullptr) -> int {
     EpiArgs e;
     e.epi = epi;
     e.out = out;
@@ -1479,22 +1471,22 @@ static int enqueue_cd_units(kucd_rbm* r, const Planes& v0_local, int64_t b, cons
     e.static_rows = true;
     e.n_lo = forward ? h_lo : v_lo;
     e.n_cnt = forward ? Hs : Vs;
+    e.stream = st;
     return project(r, forward, a, Bg, e);
   };
-  auto share_h = [&](const Planes& G, cudaStream_t st) {
-    return units_exchange(r, ex, G.p[0], G.ld, nullptr, Bg, 0, h_lo, Hs, G, true, st);
-  };
+  auto share_h = [&](const Planes& G) { return units_exchange(r, ex, G.p[0], G.ld, nullptr, Bg, 0, h_lo, Hs, G, true); };
   auto share_v = [&](const Planes& G) { return units_exchange(r, ex, G.p[0], G.ld, nullptr, Bg, 0, v_lo, Vs, G, true); };
-  // Exchanges whose result the NEXT projection does not need run on the second stream, next to that projection (their
-  // kernels use no shared memory and few registers, so their blocks fit beside the persistent contraction CTAs): the
-  // gather of the minibatch next to the chain's first projection, the exchange of that projection's states next to the
-  // positive-phase projection.  KUCD_UNITS_OVERLAP=0: everything in order on one stream.
+  // With persistent chains the positive phase (gather the minibatch, project it) and the negative chain (project the
+  // stored chains, exchange, project back, exchange, project) only meet in dW.  The negative chain runs on the main
+  // stream; the gather of the minibatch goes to the second stream and the positive-phase projection to the third: its
+  // CTAs take the SMs the chain's contractions leave idle - their last, partial wave (128 tiles on 74 CTA pairs) and the
+  // gaps in which the chain waits for an exchange.  KUCD_UNITS_OVERLAP=0: everything in order on one stream.
   static const bool overlap_env = [] {
     const char* e = getenv("KUCD_UNITS_OVERLAP");
     return !(e != nullptr && e[0] == '0');
   }();
   const bool overlap = overlap_env && pcd;
-  cudaStream_t s2 = overlap ? ctx->stream2 : ctx->stream;
+  cudaStream_t s2 = overlap ? ctx->stream2 : ctx->stream, s3 = overlap ? ctx->stream3 : ctx->stream;
   CU_TRY(cudaMemsetAsync(r->db(), 0, (r->ldVb() + r->ldHb()) * 4, ctx->stream));
   if (overlap) {
     CU_TRY(cudaEventRecord(ctx->ev_units[0], ctx->stream));
@@ -1509,33 +1501,32 @@ static int enqueue_cd_units(kucd_rbm* r, const Planes& v0_local, int64_t b, cons
     ctx->tm.aux_launches++;
     CU_TRY(cudaGetLastError());
   }
-  if (overlap) CU_TRY(cudaEventRecord(ctx->ev_units[1], s2));
+  if (overlap) {
+    CU_TRY(cudaEventRecord(ctx->ev_units[1], s2));
+    CU_TRY(cudaStreamWaitEvent(s3, ctx->ev_units[1], 0));  // (also forks the third stream off the capture)
+  }
+  // h_pos   rbm.py:120   (with persistent chains nobody back-projects it: only this rank's slice is ever read, by dW and dc)
+  KU_TRY(stage(true, Gv0, Gh0, kEpiSample, 0, r->dc(), 1.f, s3));
+  if (overlap) CU_TRY(cudaEventRecord(ctx->ev_units[2], s3));
+  if (!pcd) KU_TRY(share_h(Gh0));
   Planes hcur = Gh0;
   if (pcd) {  // the negative chain starts at the stored fantasy particles
     KU_TRY(stage(true, Gvk, Ghk, kEpiSample, 1, nullptr, 0.f));
-    if (overlap) {
-      CU_TRY(cudaEventRecord(ctx->ev_units[2], ctx->stream));
-      CU_TRY(cudaStreamWaitEvent(s2, ctx->ev_units[2], 0));
-    }
-    KU_TRY(share_h(Ghk, s2));
-    if (overlap) {
-      CU_TRY(cudaEventRecord(ctx->ev_units[3], s2));
-      CU_TRY(cudaStreamWaitEvent(ctx->stream, ctx->ev_units[1], 0));  // the gathered minibatch
-    }
+    // every rank must run its flag barriers in the same order (they share one epoch counter): the gather's barrier on
+    // the second stream comes before this exchange's - it finished long ago, the projection above is several times longer
+    if (overlap) CU_TRY(cudaStreamWaitEvent(ctx->stream, ctx->ev_units[1], 0));
+    KU_TRY(share_h(Ghk));
     hcur = Ghk;
   }
-  KU_TRY(stage(true, Gv0, Gh0, kEpiSample, 0, r->dc(), 1.f));  // h_pos   rbm.py:120
-  // (with persistent chains nobody back-projects h_pos: only this rank's slice of it is ever read, by dW and dc)
-  if (!pcd) KU_TRY(share_h(Gh0, ctx->stream));
-  if (overlap) CU_TRY(cudaStreamWaitEvent(ctx->stream, ctx->ev_units[3], 0));  // the chain's first hidden states
   for (int t = 1; t <= k; ++t) {
     const bool last = t == k;
     KU_TRY(stage(false, hcur, Gvk, kEpiSample, 2 * t, last ? r->db() : nullptr, -1.f));  // rbm.py:121-123
     KU_TRY(share_v(Gvk));
     KU_TRY(stage(true, Gvk, Ghk, last ? kEpiProb : kEpiSample, 2 * t + 1, last ? r->dc() : nullptr, -1.f));  // :124
-    if (!last) KU_TRY(share_h(Ghk, ctx->stream));
+    if (!last) KU_TRY(share_h(Ghk));
     hcur = Ghk;
   }
+  if (overlap) CU_TRY(cudaStreamWaitEvent(ctx->stream, ctx->ev_units[2], 0));  // the positive phase joins
   // dW[:, own hidden units] = v0^T h0 - vk^T hk over the whole global minibatch   (rbm.py:125-126)
   KU_TRY(delta_w(r, Gv0, Gh0, Gvk, Ghk, Bg, nullptr, false, 0, -1, 0, h_lo, Hs));
   r->last_rows = Bg;
@@ -1751,12 +1742,10 @@ static int enqueue_cd(kucd_rbm* r, const Planes& v0, int64_t batch, const kucd_h
     }();
     const bool d16 = nccl16(r);
     const int S = r->slabs_now;
-    const bool solo = ctx->comm == nullptr;  // nothing to exchange: apply_update runs the slab updates on the second stream
     for (int i = 0; i < S; ++i) {
       const int64_t w0 = i * r->slab_rows, wn = std::min<int64_t>(r->slab_rows, r->V - w0);
-      KU_TRY(delta_w(r, v0, h0, vk, hk, batch, dyn, v0_dyn, w0, wn, solo ? 0 : reserve));
+      KU_TRY(delta_w(r, v0, h0, vk, hk, batch, dyn, v0_dyn, w0, wn, reserve));
       CU_TRY(cudaEventRecord(ctx->ev_slab[i], ctx->stream));
-      if (solo) continue;
       CU_TRY(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_slab[i], 0));
       const size_t off = static_cast<size_t>(w0) * r->ldH, cnt = static_cast<size_t>(wn) * r->ldH;
       int rc = i == 0 ? g_nccl.GroupStart() : 0;
@@ -1780,7 +1769,7 @@ static int enqueue_cd(kucd_rbm* r, const Planes& v0, int64_t batch, const kucd_h
       CU_TRY(cudaEventRecord(ctx->ev_red[i], ctx->comm_stream));
     }
     r->slabs_inflight = S;
-    if (!solo) ctx->tm.allreduce_calls++;
+    ctx->tm.allreduce_calls++;
   } else if (!((whole_chain && chain_dw) || small_dw)) {
     KU_TRY(delta_w(r, v0, h0, vk, hk, batch, dyn, v0_dyn));
   }
@@ -2076,6 +2065,7 @@ int kucd_ctx_create(kucd_ctx** out, int device_id, uint64_t seed) {
   auto init = [&]() -> int {
     CU_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CU_TRY(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+    CU_TRY(cudaStreamCreateWithFlags(&c->stream3, cudaStreamNonBlocking));
     CU_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     for (int i = 0; i < 2; ++i) {
       CU_TRY(cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
@@ -2142,6 +2132,7 @@ int kucd_ctx_destroy(kucd_ctx* ctx) {
   }
   drop_stream(ctx->comm_stream);
   drop_stream(ctx->copy_stream);
+  drop_stream(ctx->stream3);
   drop_stream(ctx->stream2);
   drop_stream(ctx->stream);
   delete ctx;
