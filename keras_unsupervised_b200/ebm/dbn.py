@@ -215,15 +215,22 @@ class DBN(object):
             configs.append(cfg)
             if layer.built:
                 layer.save(os.path.join(directory, "layer%d.npz" % i))
+        # the untied generative parameters fine_tune trains (one engine model per layer below the top one): without them
+        # a reloaded stack would generate through the recognition weights again
+        gen = getattr(self, "_gen", None) or []
+        for i, g in enumerate(gen):
+            W, b, c = g.get_params()
+            np.savez(os.path.join(directory, "gen%d.npz" % i), rbm_weight=W, rbm_visible_bias=b, rbm_hidden_bias=c)
         with open(os.path.join(directory, "dbn.json"), "w") as f:
-            json.dump({"layers": configs}, f, indent=1)
+            json.dump({"layers": configs, "untied": len(gen)}, f, indent=1)
 
     @classmethod
     def load(cls, directory, layer_class=None, **kwargs):
         if layer_class is None:
             from .rbm import RBM as layer_class
         with open(os.path.join(directory, "dbn.json")) as f:
-            configs = json.load(f)["layers"]
+            meta = json.load(f)
+        configs = meta["layers"]
         dbn = cls()
         for i, cfg in enumerate(configs):
             input_dim = cfg.pop("input_dim", None)
@@ -234,4 +241,9 @@ class DBN(object):
                 if input_dim is not None and not layer.built:
                     layer.build((None, input_dim))
                 layer.load(path)
+        if meta.get("untied", 0):
+            gen = dbn.untie()
+            for i, g in enumerate(gen):
+                z = np.load(os.path.join(directory, "gen%d.npz" % i))
+                g.set_params(z["rbm_weight"], z["rbm_visible_bias"], z["rbm_hidden_bias"])
         return dbn

@@ -8,14 +8,16 @@ that keep the reference from running are resolved the wa
 code intends: draws take the row count of their input, the hidden draw is (rows, H), the remainder
 minibatch is the remaining rows, `transform`/`inv_transform` stay methods, `get_config` carries `mode`.
 
-`hps` keeps the reference's keys `batch_size`, `epochs`, `lr` (rbm.py:46,110,113,128).  Optional keys,
-whose defaults reproduce the reference: `k` (1), `persistent` (False), `momentum` (0), `weight_decay`
-(0), `normalize` ('sum' | 'mean'), `shuffle` (False; True: a fresh keyed row permutation per epoch, `shuffle_seed`),
-`dtype` ('float32' = fp32-grade three-term contractions | 'bf16'),
-`compat` ('fused': one chain updates W, b, c | 'reference': the three sequential single-parameter
-runs + per-step score of rbm.py:214-234), `seed` (42), `stream` (True: a one-epoch fit of a host array is streamed, minibatch copies overlapped with
-the chains; False: the array is uploaded first and trained by CUDA-graph replay - measured at the C1 shape, 60000 x 784
-rows in minibatches of 128: 36.7 ms streamed, 5.7 + 20.2 ms uploaded from pinned and 18.0 + 20.2 ms from pageable memory).
+`hps` keeps the reference's keys `batch_size`, `epochs`, `lr` (rbm.py:46,110,113,128).  Optional keys whose
+defaults are the reference's arithmetic: `k` (1), `persistent` (False), `momentum` (0), `weight_decay` (0),
+`normalize` ('sum' | 'mean'), `shuffle` (False; True: a fresh keyed row permutation per epoch, `shuffle_seed`),
+`dtype` ('float32' = fp32-grade three-term contractions | 'bf16'), `seed` (42).
+One default is NOT the reference's: `compat` = 'fused' (one chain per minibatch updates W, b and c from the same
+statistics; the score is printed once per epoch), where rbm.py:214-216 runs three sequential single-parameter graphs
+with fresh draws and rbm.py:233-234 prints the score after every minibatch - `compat='reference'` reproduces that
+schedule run for run (single rank).
+`stream` (True: a one-epoch fit of a host array is streamed, minibatch copies overlapped with the chains; False: the
+array is uploaded first and trained by CUDA-graph replay).
 
 Every array method calls libkucd.so; nothing is computed in Python and there is no fallback.
 """

@@ -289,6 +289,16 @@ def test_dbn_save_load_round_trip(ctx, tmp_path):
         a._machine.set_seed(a.seed, 0)
         b._machine.set_seed(b.seed, 0)
     assert np.array_equal(dbn.transform(X), twin.transform(X))
+    # after fine-tuning the lower layers have untied generative weights: a checkpoint must carry them, or the reloaded
+    # stack would generate through the recognition weights
+    dbn.fine_tune(X, epochs=1, lr=1e-2)
+    dbn.save(tmp_path / "ck2")
+    twin2 = DBN.load(tmp_path / "ck2", context=ctx)
+    assert len(twin2._gen) == 1
+    for g, h in zip(dbn._gen, twin2._gen):
+        for x, y in zip(g.get_params(), h.get_params()):
+            assert np.array_equal(x, y)
+    assert not np.array_equal(dbn._gen[0].get_params()[0], dbn._rbm_layers[0].rbm_weight)   # they did move apart
 
 
 def test_refitting_with_fresh_arrays_never_replays_a_stale_graph(ctx):
