@@ -119,7 +119,10 @@ inline int pick_bn(int64_t M, int64_t N, int num_sms) {
 }
 
 constexpr int kPreciseBN = 128;  // precise mode keeps BN/2 = 64 partial sums per epilogue thread in registers
-constexpr int kPreciseCH = 4;    // k-blocks (of 64) per tensor-memory accumulation piece
+#ifndef KUCD_PRECISE_CH
+#define KUCD_PRECISE_CH 4
+#endif
+constexpr int kPreciseCH = KUCD_PRECISE_CH;  // k-blocks (of 64) per tensor-memory accumulation piece
 
 template <int BN, bool A_MN, bool B_MN, int EPI, int CH = 0, int CG = 1>
 inline cudaError_t launch_one(const GemmParams& p, int num_sms, cudaStream_t stream) {

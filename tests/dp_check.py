@@ -89,11 +89,16 @@ def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    V, H, B, N, seed, k = 320, 256, 128, 128 * 5 + 64, 21, 2
-    data = (np.random.default_rng(3).random((N, V)) < 0.25).astype(np.float32)
+    V, H, seed, k = 320, 256, 21, 2
     W, b, c = O.OracleRBM.init_params(V, H, seed=4)
     ok = True
-    for compute, name in ((L.COMPUTE_F32X3, "f32"), (L.COMPUTE_BF16, "bf16")):
+    # global minibatch 128 (64 rows per rank at 2 ranks, 16 at 8) and 16 rows per rank whatever the world size: shards far
+    # below one 128-row tile, with a half-size remainder step
+    cases = [(compute, name, B) for B in sorted({128, 16 * world}, reverse=True)
+             for compute, name in ((L.COMPUTE_F32X3, "f32"), (L.COMPUTE_BF16, "bf16"))]
+    for compute, name, B in cases:
+        N = B * 5 + B // 2
+        data = (np.random.default_rng(3).random((N, V)) < 0.25).astype(np.float32)
         ctx = Context(device=local, seed=seed)
         ctx.join_group(rank, world)
         m = Machine(ctx, V, H, 0, compute, seed=seed)
@@ -124,9 +129,9 @@ def main():
                          wire_sum_bf16=wire16 and not m.fused_reduce)
             d_solo = float(np.abs(Wd - Ws).max())
             d_orc = float(np.abs(Wd - orc.W).mean())
-            print("[dp_check] %s world=%d fused_reduce=%s wire_bf16=%s (steps enqueued: fused %d, nccl all-reduce %d)  "
+            print("[dp_check] %s world=%d B=%d fused_reduce=%s wire_bf16=%s (steps enqueued: fused %d, nccl all-reduce %d)  "
                   "max|W_dp - W_1gpu| = %.3e  mean|W_dp - W_oracle| = %.3e"
-                  % (name, world, m.fused_reduce, wire16, t["fused_reduce_steps"], t["allreduce_calls"], d_solo, d_orc), flush=True)
+                  % (name, world, B, m.fused_reduce, wire16, t["fused_reduce_steps"], t["allreduce_calls"], d_solo, d_orc), flush=True)
             # identical samples => only the fp32 reduction order differs
             if wire16:
                 # the rounded parts move W by up to a bf16 ulp of a partial sum (~0.25) times lr per step, after which
@@ -139,7 +144,9 @@ def main():
             ok &= t["graph_launches"] == 12
             if name == "bf16" and world <= 8 and os.environ.get("KUCD_FUSED_REDUCE", "1") != "0":
                 ok &= m.fused_reduce and t["fused_reduce_steps"] > 0 and t["allreduce_calls"] == 0
+            solo_ctx.close()
         dist.barrier()
+        ctx.close()
     ok &= units_check(rank, world, local)
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, src=0)

@@ -254,6 +254,31 @@ def test_fit_epoch_graph_replay_matches_oracle(ctx):
     ds.close()
 
 
+@pytest.mark.parametrize("mode", ["f32", "bf16"])
+@pytest.mark.parametrize("B,N", [(16, 88), (32, 176), (8, 44)])
+def test_fit_epoch_tiny_minibatches_match_oracle(ctx, mode, B, N):
+    """Minibatches far below one 128-row tile, with a half-size remainder (what a rank of tests/dp_check.py sees at 8 ranks:
+    16 rows per step, 8 in the last one), CD-2, both compute modes: the replayed steps must follow the oracle."""
+    from keras_unsupervised_b200 import _lib as L
+    from keras_unsupervised_b200.engine import Dataset, Machine
+
+    rng = np.random.default_rng(B)
+    V, H, seed = 320, 256, 21
+    m, orc = _machine(ctx, V, H, mode, seed=seed)
+    data = _data(rng, N, V, 0.25)
+    ds = Dataset.from_array(ctx, data, L.COMPUTE_F32X3 if mode == "f32" else L.COMPUTE_BF16)
+    hp = Machine.hparams(lr=1e-3, k=2)
+    for _ in range(2):
+        m.fit_epoch(ds, B, hp, want_stats=False)
+    ctx.sync()
+    O.philox_fit(orc, data, B, 2, 1e-3, seed, k=2)
+    W, b, c = m.get_params()
+    assert np.abs(W - orc.W).mean() < 2e-6
+    assert np.abs(W - orc.W).max() < 5e-3
+    assert np.abs(b - orc.b).max() < 5e-3 and np.abs(c - orc.c).max() < 5e-3
+    ds.close()
+
+
 def test_dataset_transform_equals_array_transform(ctx):
     from keras_unsupervised_b200 import _lib as L
     from keras_unsupervised_b200.engine import Dataset
