@@ -410,6 +410,7 @@ __global__ void update_bias_kernel(float* __restrict__ x, const float* __restric
 __global__ void colsum_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ mid,
                               const __nv_bfloat16* __restrict__ lo, int64_t ld, int64_t row_off, int32_t rows,
                               int32_t cols, const StepDyn* dyn, float sign, float* __restrict__ out) {
+  const int grid_rows = rows;  // the minibatch size every launch adding into `out` knows: one grid for all of them
   if (dyn != nullptr) {
     row_off += dyn->row_off;
     rows = dyn->rows_valid < rows ? dyn->rows_valid : rows;
@@ -432,8 +433,10 @@ __global__ void colsum_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_b
     s1 += v.y;
   }
   if (r1 > r0) {
-    atomicAdd(out + c, sign * s0);
-    if (c + 1 < cols) atomicAdd(out + c + 1, sign * s1);
+    // real-valued data: slab sums on the grid of stat_grid_round (rng_math.cuh), so that the atomics commute; 0/1 data
+    // sums to integers and is unchanged
+    atomicAdd(out + c, sign * stat_grid_round(s0, grid_rows));
+    if (c + 1 < cols) atomicAdd(out + c + 1, sign * stat_grid_round(s1, grid_rows));
   }
 }
 
@@ -446,6 +449,7 @@ __global__ void colsum_store_kernel(const __nv_bfloat16* __restrict__ hi, const 
                                     float* __restrict__ zero, int32_t zero_len) {
   __shared__ float2 part[16][32];
   int64_t row_off = 0;
+  const int grid_rows = rows;  // as in colsum_kernel: the epilogues' atomics add to these sums and must find them on their grid
   if (dyn != nullptr) {
     row_off = dyn->row_off;
     rows = dyn->rows_valid < rows ? dyn->rows_valid : rows;
@@ -492,8 +496,8 @@ __global__ void colsum_store_kernel(const __nv_bfloat16* __restrict__ hi, const 
       t.x += part[k][threadIdx.x].x;
       t.y += part[k][threadIdx.x].y;
     }
-    out[c] = t.x;
-    out[c + 1] = (c + 1 < cols) ? t.y : 0.f;
+    out[c] = stat_grid_round(t.x, grid_rows);
+    out[c + 1] = (c + 1 < cols) ? stat_grid_round(t.y, grid_rows) : 0.f;
   }
 }
 

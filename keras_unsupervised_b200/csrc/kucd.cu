@@ -666,6 +666,7 @@ struct EpiArgs {
   int64_t ld_u = 0;
   float* colsum = nullptr;
   float colsum_sign = 1.f;
+  int64_t colsum_rows = 0;  // rows adding into `colsum` over all launches that share it (0: the rows of this launch)
   float* rowsum = nullptr;
   uint64_t draw = 0;
   uint64_t draw_stride = 0;
@@ -720,6 +721,7 @@ static int project(kucd_rbm* r, bool forward, const Planes& a, int64_t rows, con
   p.ld_u = e.ld_u;
   p.colsum = e.colsum != nullptr ? e.colsum + n_lo : nullptr;
   p.colsum_sign = e.colsum_sign;
+  p.colsum_rows = static_cast<int32_t>(e.colsum_rows > 0 ? e.colsum_rows : rows);
   p.rowsum = e.rowsum;
   p.seed = r->seed;
   p.draw = e.draw;
@@ -1292,6 +1294,7 @@ static int launch_chain(kucd_rbm* r, const Planes& v0, int64_t batch, const kucd
     q.ld_bf16 = fwd ? r->ldH : r->ldV;
     q.colsum = colsum;
     q.colsum_sign = sign;
+    q.colsum_rows = static_cast<int32_t>(batch);
     q.epi = epi;
     q.M = static_cast<int32_t>(batch);
     q.N = static_cast<int32_t>(fwd ? r->H : r->V);
@@ -1606,6 +1609,7 @@ static int enqueue_cd(kucd_rbm* r, const Planes& v0, int64_t batch, const kucd_h
       e.row_base = base;
       e.stream = st;
       e.no_prof = !timed;
+      e.colsum_rows = batch;  // both chains of a split minibatch add into the same statistics: one grid
     };
     {
       EpiArgs e;

@@ -119,10 +119,15 @@ inline int pick_bn(int64_t M, int64_t N, int num_sms) {
 }
 
 constexpr int kPreciseBN = 128;  // precise mode keeps BN/2 = 64 partial sums per epilogue thread in registers
+// k-blocks (of 64) per tensor-memory accumulation piece of the float32-grade mode.  Measured on one B200, same call
+// (profiles/r02_ch_experiment.log; tools/diag/ch_experiment.py): max relative error of sigmoid(v.W + c) against float64,
+// real-valued v, K = 4096 / 16384, and the C3 float32-grade step -
+//   CH = 4: 1.2e-6 / 3.2e-6, 8.39 ms      CH = 8: 2.1e-6 / 4.6e-6, 7.74 ms      CH = 16: 3.7e-6 / 8.2e-6, 7.22 ms
+// (binary inputs: 0.8e-6 / 1.6e-6 whatever CH).  8 keeps a factor two under the 1e-5 bar at C4's K = 16384.
 #ifndef KUCD_PRECISE_CH
-#define KUCD_PRECISE_CH 4
+#define KUCD_PRECISE_CH 8
 #endif
-constexpr int kPreciseCH = KUCD_PRECISE_CH;  // k-blocks (of 64) per tensor-memory accumulation piece
+constexpr int kPreciseCH = KUCD_PRECISE_CH;
 
 template <int BN, bool A_MN, bool B_MN, int EPI, int CH = 0, int CG = 1>
 inline cudaError_t launch_one(const GemmParams& p, int num_sms, cudaStream_t stream) {

@@ -37,7 +37,7 @@ struct alignas(64) GemmParams {
   uint32_t neg_mask;  // bit s: segment s enters with a minus sign
   int32_t M, N;
   int32_t kblocks;  // ceil(K / 64) per segment
-  int32_t pad0;
+  int32_t colsum_rows;  // rows that add into `colsum` over ALL launches sharing it (0: M) - sets the grid of stat_grid_round
   // ---- epilogue ----
   const float* bias;       // readable up to ceil(N/BN)*BN entries
   __nv_bfloat16* out_bf16;  // (M, ld_bf16), ld multiple of 8, >= round_up(N, 8)
@@ -115,7 +115,7 @@ struct ChainKind {
   int32_t nseg;
   int32_t map_a2, map_b2;
   int32_t map_b3;      // float32-grade chain kernel: third term plane of W (map_b, map_b2, map_b3 = smallest term first)
-  int32_t pad3;
+  int32_t colsum_rows;  // as GemmParams::colsum_rows
   int32_t dep2;        // stage that must be complete in ALL its row blocks before segment 1 is loaded
   int32_t col_off;     // as GemmParams::col_off (always 0: chain launches cover whole layers)
 };

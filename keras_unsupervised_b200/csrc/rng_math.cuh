@@ -51,6 +51,19 @@ __device__ __forceinline__ float sigmoid_f32(float x) { return __fdividef(1.0f, 
 // log(1 + e^x), overflow-free; equals the reference's naive K.log(1 + K.exp(x))
 // (ku/ebm/rbm.py:74) wherever that does not overflow.
 __device__ __forceinline__ float softplus_f32(float x) { return fmaxf(x, 0.0f) + log1pf(__expf(-fabsf(x))); }
+
+// Column statistics (db, dc of rbm.py:129-134) are summed with one fp32 atomicAdd per (32- or 64-row group, column), in
+// whatever order the warps arrive - and fp32 addition does not commute with rounding, so two runs of the same step used to
+// differ in the last bits (1e-8 on a bias), which a later discrete decision (the bf16 rounding of a stored probability, a
+// Bernoulli threshold) now and then amplified to lr * 2^-10.  Rounded to the power-of-two grid 2^(ceil(log2 bound) - 24),
+// every partial sum is a multiple of a grid on which all sums up to `bound` are exact in fp32: the adds commute and the
+// statistic is the same in every run, on every schedule and tiling.  The grid is the fp32 spacing at magnitude `bound`,
+// i.e. what the running sum of an atomic accumulation of that size rounds to anyway.  0/1 counts are integers: unchanged.
+__device__ __forceinline__ float stat_grid_round(float s, int bound) {
+  const int e = 32 - __clz((bound > 2 ? bound : 2) - 1);  // ceil(log2(bound))
+  const float g = __int_as_float((127 + e - 24) << 23), inv = __int_as_float((127 - e + 24) << 23);
+  return rintf(s * inv) * g;
+}
 #endif
 
 }  // namespace kucd

@@ -93,8 +93,8 @@ def test_default_paths_launch_what_design_md_says(dry_build):
     d = run("cd_step")
     assert clean(d["bf16"])["kernels"] == ["ingest_kernel", "colsum_kernel", CHAIN_SMALL, "update_w_kernel<0>"]
     f32 = clean(d["f32"])["kernels"]                     # float32-grade: the chain kernel with piecewise accumulation
-    assert f32 == ["ingest_kernel", "colsum_kernel", "chain_kernel<64,1,0,4>", "gemm_bf16_kernel<128,1,1,0,4,1>",
-                   "update_w_kernel<0>"]                 # (CH = 4), then the four-term dW contraction on its own
+    assert f32 == ["ingest_kernel", "colsum_kernel", "chain_kernel<64,1,0,8>", "gemm_bf16_kernel<128,1,1,0,8,1>",
+                   "update_w_kernel<0>"]                 # (CH = 8), then the four-term dW contraction on its own
     e = clean(run("fit_epoch"))
     assert e["graph"] == ["colsum_store_kernel", "memset", CHAIN_SMALL, "update_w_kernel<0>"]   # 3 kernels per replay
     assert e["kernels"] == ["set_dyn_kernel"] + ["graph_launch"] * 8 and e["steps"] == 8
@@ -139,7 +139,7 @@ def test_data_set_planes_come_from_the_stream_ordered_pool(dry_build):
 def test_delta_rule_is_projection_colsum_dw_update(dry_build):
     d = run("delta_rule")
     for key, proj in (("bf16_fwd", "gemm_bf16_kernel<64,0,1,2,0,1>"), ("bf16_bwd", "gemm_bf16_kernel<64,0,0,2,0,1>"),
-                      ("f32_fwd", "gemm_bf16_kernel<128,0,1,2,4,1>"), ("f32_bwd", "gemm_bf16_kernel<128,0,0,2,4,1>")):
+                      ("f32_fwd", "gemm_bf16_kernel<128,0,1,2,8,1>"), ("f32_bwd", "gemm_bf16_kernel<128,0,0,2,8,1>")):
         k = clean(d[key])["kernels"]
         assert k[:2] == ["ingest_kernel", "ingest_kernel"] and k[2] == proj and k[3] == "colsum_kernel"
         assert k[4].startswith("gemm_bf16_kernel<") and ",1,1,0," in k[4] and k[5] == "update_w_kernel<0>" and len(k) == 6
@@ -324,7 +324,7 @@ def test_reference_facing_classes_end_to_end(dry_build):
     assert ft["gemm_bf16_kernel<64,0,1,2,0,1>"] == 4 and ft["gemm_bf16_kernel<64,0,0,2,0,1>"] == 4   # their predictions
     assert ft["update_w_kernel<0>"] == 10
     f32 = Counter(d["one_epoch_f32"]["kernels"])            # 1000 rows, batch 128: 8 streamed float32-grade steps
-    assert f32["update_w_kernel<0>"] == 8 and f32["gemm_bf16_kernel<128,1,1,0,4,1>"] == 8
+    assert f32["update_w_kernel<0>"] == 8 and f32["gemm_bf16_kernel<128,1,1,0,8,1>"] == 8
 
 
 def test_data_formats_gaussian_pcd_injection_score(dry_build):
@@ -339,7 +339,7 @@ def test_data_formats_gaussian_pcd_injection_score(dry_build):
     assert p[CHAIN_SMALL] == 8 and p["update_w_kernel<0>"] == 8
     g = Counter(clean(d["gaussian"])["kernels"])
     assert g["chain_kernel<64,1,1,0>"] == 1                   # the Gaussian instantiation of the small chain kernel
-    assert g["gemm_bf16_kernel<128,0,1,4,4,1>"] == 1 and g["gemm_bf16_kernel<128,0,0,5,4,1>"] == 1   # relu / normal epilogues
+    assert g["gemm_bf16_kernel<128,0,1,4,8,1>"] == 1 and g["gemm_bf16_kernel<128,0,0,5,8,1>"] == 1   # relu / normal epilogues
     s = Counter(clean(d["pcd_inject_score"])["kernels"])
     assert s["copy_rows_kernel"] == 1 and s["score_kernel"] == 2 and s["free_energy_finish_kernel"] == 4
 
@@ -471,11 +471,11 @@ def test_rbm_fit_under_the_optional_hps_keys(dry_build):
     assert sh["permute_rows_kernel"] == 3 and sh["graph_launch"] == 3 * 5 and d["shuffle"]["history"] == 3
     ref = Counter(clean(d["reference"])["kernels"])          # 600 rows / 128 = 5 minibatches
     assert ref["update_w_kernel<0>"] == 15                   # runs A, B, C: one parameter each (rbm.py:214-216)
-    assert ref["gemm_bf16_kernel<128,1,1,0,4,1>"] == 15      # each with its own chain and statistics
+    assert ref["gemm_bf16_kernel<128,1,1,0,8,1>"] == 15      # each with its own chain and statistics
     assert ref["score_kernel"] == 5 and ref["free_energy_finish_kernel"] == 10     # run D: F(v), F(v_neg) (rbm.py:227-233)
     pcd = Counter(clean(d["pcd"])["kernels"])
     assert pcd["graph_launch"] == 10 and pcd["ingest_kernel"] == 2                 # the data set and the chains' start
     g = Counter(clean(d["gaussian_default"])["kernels"])
-    assert g["gemm_bf16_kernel<128,0,1,4,4,1>"] == 5 and g["gemm_bf16_kernel<128,0,0,5,4,1>"] == 5
+    assert g["gemm_bf16_kernel<128,0,1,4,8,1>"] == 5 and g["gemm_bf16_kernel<128,0,0,5,8,1>"] == 5
     one = Counter(clean(d["resident_one_epoch"])["kernels"])
     assert one["graph_launch"] == 5 and one["ingest_kernel"] == 1

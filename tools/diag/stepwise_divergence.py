@@ -70,8 +70,7 @@ def stepwise():
     for s in range(steps):
         m.fit_range(ds, B, hp, s, s + 1)
         ctx.sync()
-        rows = min(B, N - s * B)
-        st = m.last_stats(rows)
+        st = m.last_stats(B)
         st["W"], st["b"], st["c"] = m.get_params()
         rec.append(st)
     m.close()

@@ -35,3 +35,12 @@ for trial in range(int(sys.argv[1]) if len(sys.argv) > 1 else 12):
             msg += "   c[%d]: %.9g vs %.9g; W[:, %d] max diff %.3e; #W>5e-7: %d; #b>5e-7: %d" % (
                 j, got[1][j], ref[1][j], j, d[0][:, j].max(), int((d[0] > 5e-7).sum()), int((d[2] > 5e-7).sum()))
         print(msg, flush=True)
+        if d[0].max() > 5e-7 or d[1].max() > 5e-7:
+            sd = [a.astype(np.float64) - b.astype(np.float64) for a, b in zip(got, ref)]
+            print("      c diffs beyond 5e-8:", {int(q): float("%.4g" % sd[1][q]) for q in np.argwhere(np.abs(sd[1]) > 5e-8)[:, 0]})
+            cols = np.argwhere((np.abs(sd[0]) > 5e-8).any(0))[:, 0]
+            for q in cols[:4]:
+                rows_ = np.argwhere(np.abs(sd[0][:, q]) > 5e-8)[:, 0]
+                print("      W[:, %d]: %d entries beyond 5e-8; signed diffs (first 12): %s" % (
+                    q, len(rows_), [float("%.4g" % sd[0][i, q]) for i in rows_[:12]]))
+            print("      W columns touched:", [int(q) for q in cols])
