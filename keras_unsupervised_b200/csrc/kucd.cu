@@ -1035,6 +1035,14 @@ static void choose_exchange(kucd_rbm* r, int64_t rows_per_rank, const kucd_hpara
   }();
   const int64_t min_rows = min_rows_env >= 0 ? min_rows_env : (r->wire16 ? 1024 : 2048);
   r->fused_now = r->peer_on && rows_per_rank >= min_rows;
+  // Shorter shards of a SMALL weight matrix (one minibatch strong-scaled over the ranks): the pushes are few bytes even
+  // though the contraction is short, and an all-reduce of the same matrix is all latency and exposure.  Measured at C3
+  // (64 MiB of fp32 dW) with 512 rows per rank on 8 GPUs, same pod: 0.833 ms per step fused (dW with its pushes 0.109 ms)
+  // against 1.002 ms with ncclAllReduce (profiles/r02_call12_n8_c3_strong_fused.json, r02_call11_n8_c3_strong.json).
+  // Minibatches of <= 256 rows keep NCCL: their whole step is one small-tile chain launch with dW as its last stage.
+  if (!r->fused_now && r->peer_on && min_rows_env < 0 && rows_per_rank > 256 &&
+      static_cast<int64_t>(r->V) * r->ldH * 4 <= (int64_t{128} << 20))
+    r->fused_now = true;
   r->units_now = false;
   const int n = r->ctx->world;
   const int64_t Bg = rows_per_rank * n;
@@ -1069,7 +1077,7 @@ static int prepare_exchange(kucd_rbm* r, int64_t rows_per_rank, const kucd_hpara
   }();
   r->slabs_now = 1;
   // (On a single rank the same slabs were tried as a way to hide the HBM-bound update behind the contraction of the next
-  // slab: measured -1.3 % at C3 with two slabs, +3 ... +7 % at C4's share with 2 ... 8 - profiles/r02_switches.md - and
+  // slab: measured -1.3 % at C3 with two slabs, +3 ... +7 % at C4's share with 2 ... 8 - profiles/r02_call1_switches.log - and
   // removed.)
   static const int64_t slab_min_elems = [] {  // tests lower it to exercise the path at small sizes
     const char* e = getenv("KUCD_AR_SLABS_MIN_ELEMS");
@@ -1699,7 +1707,7 @@ static int enqueue_cd(kucd_rbm* r, const Planes& v0, int64_t batch, const kucd_h
   // In between - a minibatch (or a data-parallel shard of one) too short for 74 pair tiles per stage but long enough
   // for >= 32 tiles of 128 x 256: the same flattened chain on single CTAs.  A 512-row shard of 4096 -> 4096 (C3 strong
   // scaling over 8 GPUs) is 64 such tiles per stage; launched one projection at a time each of its 21 projections cost
-  // 58 us for 17 GFLOP (profiles/r02_scaling.md).  The dW contraction stays a launch of its own (it may push rows to peers).
+  // 58 us for 17 GFLOP (profiles/README.md, round 2).  The dW contraction stays a launch of its own (it may push rows to peers).
   const int64_t mid_tiles = ((batch + kBlockM - 1) / kBlockM) * ((std::min(r->V, r->H) + 255) / 256);
   static const bool mid_chain_env = [] {
     const char* e = getenv("KUCD_MID_CHAIN");
@@ -3257,7 +3265,7 @@ int kucd_rbm_fit_host(kucd_rbm* r, const kucd_tensor* V_all, int64_t batch, cons
   }
   // Latency-bound minibatches travel and are ingested C at a time (fit_host_chunked): one copy -> ingest -> step
   // hand-over per C steps instead of per step.  Measured at the C1 shape (60000 x 784 float32 rows, minibatches of 128,
-  // profiles/r02_switches.md): 75.7 us per step unchunked, 61.5 / 61.1 / 61.6 / 61.4 us at C = 4 / 8 / 16 / 32.
+  // profiles/r02_call1_switches.log): 75.7 us per step unchunked, 61.5 / 61.1 / 61.6 / 61.4 us at C = 4 / 8 / 16 / 32.
   // KUCD_STREAM_CHUNK overrides C (0 or 1: per-minibatch stream).
   static const int64_t chunk_env = [] {
     const char* e = getenv("KUCD_STREAM_CHUNK");

@@ -434,11 +434,12 @@ def scenario(name):
             for m in ms:
                 L.check(m.ctx.lib.kucd_rbm_peer_attach(m.handle, b"".join(handles)))
                 m.fused_reduce = True
-        dss = [Dataset.from_array(c, data(256, V, seed=5 + r), L.COMPUTE_BF16) for r, c in enumerate(ctxs)]
+        b = int(os.environ.get("DRY_ROWS", "64"))  # rows of a global minibatch per rank
+        dss = [Dataset.from_array(c, data(4 * b, V, seed=5 + r), L.COMPUTE_BF16) for r, c in enumerate(ctxs)]
         fake.fake_reset()
         hp = Machine.hparams(lr=1e-3, k=1)
         for r, m in enumerate(ms):
-            m.fit_epoch(dss[r], 64, hp, global_row0=64 * r, want_stats=False)
+            m.fit_epoch(dss[r], b, hp, global_row0=b * r, want_stats=False)
         out = snapshot()
         out["timings"] = [c.timings() for c in ctxs]
     elif name == "units":  # KUCD_EXCHANGE=units: the unit-sharded step over DRY_RANKS in-process ranks

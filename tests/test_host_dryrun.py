@@ -178,6 +178,16 @@ def test_two_rank_exchange_variants(dry_build, env, dw, exchange, update):
         assert d["timings"][0]["fused_reduce_steps"] == 4 and d["timings"][0]["allreduce_calls"] == 0
 
 
+def test_which_exchange_the_default_rule_picks(dry_build):
+    """choose_exchange without overrides, a small weight matrix (784 x 500): shards of <= 256 rows keep the all-reduce (their
+    step is one small-tile chain launch with dW inside), shards of 257 ... 2047 rows take the fused exchange (measured at C3
+    strong-scaled over 8 GPUs: 0.833 vs 1.002 ms per step)."""
+    for rows, fused in ((64, False), (256, False), (512, True), (1024, True)):
+        t = clean(run("two_ranks", DRY_ROWS=rows))["timings"][0]
+        assert t["graph_launches"] == 4
+        assert (t["fused_reduce_steps"], t["allreduce_calls"]) == ((4, 0) if fused else (0, 4)), (rows, t)
+
+
 @pytest.mark.parametrize("ranks", [2, 4, 8])
 def test_unit_sharded_step_over_in_process_ranks(dry_build, ranks):
     """KUCD_EXCHANGE=units (kucd.cu: enqueue_cd_units): per projection one launch over the rank's slice of the units and all
