@@ -189,6 +189,16 @@ int kucd_rbm_get_params(kucd_rbm* rbm, kucd_tensor* W, kucd_tensor* b, kucd_tens
 int kucd_rbm_set_seed(kucd_rbm* rbm, uint64_t seed, uint64_t step_count);
 /* what a checkpoint needs besides the parameters: the stream position and the number of stored chains */
 int kucd_rbm_get_counters(kucd_rbm* rbm, uint64_t* seed, uint64_t* step_count, int64_t* n_chains);
+/* ... and, for a resumed fit to continue exactly where an uninterrupted one would be: the positions of the inference
+ * (2^63 + n) and score (2^62 + 2n) streams, which kucd_rbm_set_seed resets to 0 ... */
+int kucd_rbm_get_draw_counters(kucd_rbm* rbm, uint64_t* infer_draws, uint64_t* score_draws);
+int kucd_rbm_set_draw_counters(kucd_rbm* rbm, uint64_t infer_draws, uint64_t score_draws);
+/* ... and the momentum buffers (kucd_hparams.momentum != 0; the reference has none): mW (V,H), mb (V), mc (H), float32.
+ * get: zeros while no momentum step has run; *present (optional) tells which.  set: allocates them.  On several ranks
+ * these are the LOCAL buffers (the fused and the unit-sharded exchange keep only the slices a rank owns up to date):
+ * a checkpoint stores them per rank and restores them into the same group layout. */
+int kucd_rbm_get_momentum(kucd_rbm* rbm, kucd_tensor* mW, kucd_tensor* mb, kucd_tensor* mc, int* present);
+int kucd_rbm_set_momentum(kucd_rbm* rbm, const kucd_tensor* mW, const kucd_tensor* mb, const kucd_tensor* mc);
 
 /* Fused reduction (optional, bf16 compute, 2..8 ranks on one NVLink domain).  After kucd_ctx_comm_init every rank
  * calls kucd_rbm_peer_export on its model (128 bytes of CUDA IPC handles out), the ranks exchange them, and every

@@ -95,6 +95,10 @@ SIGNATURES = {
     "kucd_rbm_peer_detach": (C.c_int, [_P]),
     "kucd_rbm_set_seed": (C.c_int, [_P, C.c_uint64, C.c_uint64]),
     "kucd_rbm_get_counters": (C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_int64)]),
+    "kucd_rbm_get_draw_counters": (C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "kucd_rbm_set_draw_counters": (C.c_int, [_P, C.c_uint64, C.c_uint64]),
+    "kucd_rbm_get_momentum": (C.c_int, [_P, _TP, _TP, _TP, C.POINTER(C.c_int)]),
+    "kucd_rbm_set_momentum": (C.c_int, [_P, _TP, _TP, _TP]),
     "kucd_rbm_transform": (C.c_int, [_P, _TP, _TP, _TP, _TP]),
     "kucd_rbm_inv_transform": (C.c_int, [_P, _TP, _TP, _TP, _TP]),
     "kucd_rbm_free_energy": (C.c_int, [_P, _TP, _TP]),

@@ -2411,6 +2411,79 @@ int kucd_rbm_get_counters(kucd_rbm* r, uint64_t* seed, uint64_t* step_count, int
   return KUCD_OK;
 }
 
+int kucd_rbm_get_draw_counters(kucd_rbm* r, uint64_t* infer_draws, uint64_t* score_draws) {
+  if (r == nullptr) return fail(KUCD_ERR_INVALID_ARG, "rbm is NULL");
+  if (infer_draws != nullptr) *infer_draws = r->infer_draws;
+  if (score_draws != nullptr) *score_draws = r->score_draws;
+  return KUCD_OK;
+}
+
+int kucd_rbm_set_draw_counters(kucd_rbm* r, uint64_t infer_draws, uint64_t score_draws) {
+  if (r == nullptr) return fail(KUCD_ERR_INVALID_ARG, "rbm is NULL");
+  r->infer_draws = infer_draws;
+  r->score_draws = score_draws;
+  return KUCD_OK;
+}
+
+// momentum buffers in and out (checkpoints): same layouts as the parameters (mW padded to ldH like W32)
+int kucd_rbm_get_momentum(kucd_rbm* r, kucd_tensor* mW, kucd_tensor* mb, kucd_tensor* mc, int* present) {
+  if (r == nullptr) return fail(KUCD_ERR_INVALID_ARG, "rbm is NULL");
+  kucd_ctx* ctx = r->ctx;
+  CU_TRY(cudaSetDevice(ctx->device));
+  const bool have = r->mW.p != nullptr && r->mb.p != nullptr && r->mc.p != nullptr;
+  if (present != nullptr) *present = have ? 1 : 0;
+  if (!have && (mW != nullptr || mb != nullptr || mc != nullptr)) {
+    // asked for buffers that no momentum step has created yet: create them (zeroed), so that there is something to copy
+    KU_TRY(r->mW.ensure(static_cast<size_t>(r->V) * r->ldH * 4, true));
+    KU_TRY(r->mb.ensure(r->ldVb() * 4, true));
+    KU_TRY(r->mc.ensure(r->ldHb() * 4, true));
+  }
+  if (mW != nullptr) {
+    KU_TRY(check_tensor(ctx, mW, r->V, r->H, "momentum of rbm_weight", true));
+    CU_TRY(cudaMemcpy2DAsync(mW->data, mW->strides[0] * 4, r->mW.p, r->ldH * 4, r->H * 4, r->V, cudaMemcpyDefault,
+                             ctx->stream));
+  }
+  if (mb != nullptr) {
+    const kucd_tensor m = as_matrix(mb);
+    KU_TRY(check_tensor(ctx, &m, 1, r->V, "momentum of rbm_visible_bias", true));
+    CU_TRY(cudaMemcpyAsync(m.data, r->mb.p, r->V * 4, cudaMemcpyDefault, ctx->stream));
+  }
+  if (mc != nullptr) {
+    const kucd_tensor m = as_matrix(mc);
+    KU_TRY(check_tensor(ctx, &m, 1, r->H, "momentum of rbm_hidden_bias", true));
+    CU_TRY(cudaMemcpyAsync(m.data, r->mc.p, r->H * 4, cudaMemcpyDefault, ctx->stream));
+  }
+  CU_TRY(cudaStreamSynchronize(ctx->stream));
+  return KUCD_OK;
+}
+
+int kucd_rbm_set_momentum(kucd_rbm* r, const kucd_tensor* mW, const kucd_tensor* mb, const kucd_tensor* mc) {
+  if (r == nullptr) return fail(KUCD_ERR_INVALID_ARG, "rbm is NULL");
+  kucd_ctx* ctx = r->ctx;
+  CU_TRY(cudaSetDevice(ctx->device));
+  // all three exist together (apply_update allocates them together, zeroed)
+  KU_TRY(r->mW.ensure(static_cast<size_t>(r->V) * r->ldH * 4, true));
+  KU_TRY(r->mb.ensure(r->ldVb() * 4, true));
+  KU_TRY(r->mc.ensure(r->ldHb() * 4, true));
+  if (mW != nullptr) {
+    KU_TRY(check_tensor(ctx, mW, r->V, r->H, "momentum of rbm_weight", true));
+    CU_TRY(cudaMemcpy2DAsync(r->mW.p, r->ldH * 4, mW->data, mW->strides[0] * 4, r->H * 4, r->V, cudaMemcpyDefault,
+                             ctx->stream));
+  }
+  if (mb != nullptr) {
+    const kucd_tensor m = as_matrix(mb);
+    KU_TRY(check_tensor(ctx, &m, 1, r->V, "momentum of rbm_visible_bias", true));
+    CU_TRY(cudaMemcpyAsync(r->mb.p, m.data, r->V * 4, cudaMemcpyDefault, ctx->stream));
+  }
+  if (mc != nullptr) {
+    const kucd_tensor m = as_matrix(mc);
+    KU_TRY(check_tensor(ctx, &m, 1, r->H, "momentum of rbm_hidden_bias", true));
+    CU_TRY(cudaMemcpyAsync(r->mc.p, m.data, r->H * 4, cudaMemcpyDefault, ctx->stream));
+  }
+  CU_TRY(cudaStreamSynchronize(ctx->stream));
+  return KUCD_OK;
+}
+
 int kucd_rbm_get_params(kucd_rbm* r, kucd_tensor* W, kucd_tensor* b, kucd_tensor* c) {
   if (r == nullptr) return fail(KUCD_ERR_INVALID_ARG, "rbm is NULL");
   kucd_ctx* ctx = r->ctx;

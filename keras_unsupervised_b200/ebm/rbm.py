@@ -248,15 +248,21 @@ class RBM(_Base):
         return "%s.rank%d.npz" % (stem, rank)
 
     def save(self, path):
-        """Parameters under the reference's variable names (rbm.py:30,34,40) plus what resuming a fit needs:
-        the Philox stream position and the persistent chains.  Under data parallelism every rank calls this; the chains
-        stored are the rank's own shard."""
+        """Parameters under the reference's variable names (rbm.py:30,34,40) plus what resuming a fit needs for the
+        resumed run to equal an uninterrupted one: the positions of the Philox streams (training, inference, score), the
+        persistent chains and the momentum buffers.  Under data parallelism every rank calls this; chains and momentum
+        are the rank's own (a checkpoint with either is restored into a group of the same size)."""
         W, b, c = self._machine.get_params()
         st = self._machine.counters()
+        st.update(self._machine.draw_counters())
         ctx = self._machine.ctx
         extra = {}
         if st["n_chains"] > 0:
             extra["chains"] = self._machine.get_chains(st["n_chains"])
+        mom = self._machine.get_momentum()
+        if mom is not None:
+            extra.update(momentum_weight=mom[0], momentum_visible_bias=mom[1], momentum_hidden_bias=mom[2])
+        extra.update(infer_draws=np.uint64(st["infer_draws"]), score_draws=np.uint64(st["score_draws"]))
         np.savez(self._rank_path(path, ctx.rank, ctx.world), rbm_weight=W, rbm_hidden_bias=c, rbm_visible_bias=b,
                  seed=np.uint64(st["seed"]), step_count=np.uint64(st["step_count"]), mode=np.int64(self.mode),
                  output_dim=np.int64(self.output_dim), epochs_done=np.int64(self._epochs_done),
@@ -266,8 +272,8 @@ class RBM(_Base):
         ctx = getattr(getattr(self, "_machine", None), "ctx", None) or self._context or Context.default()
         path = self._rank_path(path, ctx.rank, ctx.world)
         z = np.load(path if str(path).endswith(".npz") else str(path) + ".npz")
-        if "world" in z.files and int(z["world"]) != ctx.world and "chains" in z.files:
-            raise ValueError("checkpoint with persistent chains was written by %d ranks, this group has %d"
+        if "world" in z.files and int(z["world"]) != ctx.world and ("chains" in z.files or "momentum_weight" in z.files):
+            raise ValueError("checkpoint with persistent chains or momentum was written by %d ranks, this group has %d"
                              % (int(z["world"]), ctx.world))
         if not self.built:
             self.build((None, int(z["rbm_weight"].shape[0])))
@@ -277,6 +283,10 @@ class RBM(_Base):
         self._machine.set_params(z["rbm_weight"], z["rbm_visible_bias"], z["rbm_hidden_bias"])
         self._to_keras()
         self._machine.set_seed(int(z["seed"]), int(z["step_count"]))
+        if "infer_draws" in z.files:
+            self._machine.set_draw_counters(int(z["infer_draws"]), int(z["score_draws"]))
+        if "momentum_weight" in z.files:
+            self._machine.set_momentum(z["momentum_weight"], z["momentum_visible_bias"], z["momentum_hidden_bias"])
         if "epochs_done" in z.files:
             self._epochs_done = int(z["epochs_done"])
         if "chains" in z.files:

@@ -218,6 +218,34 @@ class Machine:
         L.check(self.ctx.lib.kucd_rbm_get_counters(self.handle, C.byref(seed), C.byref(step), C.byref(nch)))
         return {"seed": seed.value, "step_count": step.value, "n_chains": nch.value}
 
+    def draw_counters(self) -> dict:
+        """Positions of the inference and score Philox streams (set_seed resets both to 0)."""
+        a, b = C.c_uint64(), C.c_uint64()
+        L.check(self.ctx.lib.kucd_rbm_get_draw_counters(self.handle, C.byref(a), C.byref(b)))
+        return {"infer_draws": a.value, "score_draws": b.value}
+
+    def set_draw_counters(self, infer_draws: int = 0, score_draws: int = 0) -> None:
+        L.check(self.ctx.lib.kucd_rbm_set_draw_counters(self.handle, C.c_uint64(infer_draws), C.c_uint64(score_draws)))
+
+    def get_momentum(self):
+        """(mW, mb, mc) of this rank, or None while no momentum step has run (include/kucd.h: kucd_rbm_get_momentum)."""
+        present = C.c_int(0)
+        L.check(self.ctx.lib.kucd_rbm_get_momentum(self.handle, None, None, None, C.byref(present)))
+        if not present.value:
+            return None
+        mW = np.empty((self.V, self.H), np.float32)
+        mb = np.empty((self.V,), np.float32)
+        mc = np.empty((self.H,), np.float32)
+        keep: list = []
+        ts = [L.tensor_of(x, keep) for x in (mW, mb, mc)]
+        L.check(self.ctx.lib.kucd_rbm_get_momentum(self.handle, *[C.byref(t) for t in ts], None))
+        return mW, mb, mc
+
+    def set_momentum(self, mW, mb, mc) -> None:
+        keep: list = []
+        ts = [L.tensor_of(np.ascontiguousarray(x, dtype=np.float32), keep) for x in (mW, mb, mc)]
+        L.check(self.ctx.lib.kucd_rbm_set_momentum(self.handle, *[C.byref(t) for t in ts]))
+
     # ---- parameters ----
     def set_params(self, W=None, b=None, c=None) -> None:
         keep: list = []

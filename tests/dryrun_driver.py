@@ -392,6 +392,30 @@ def scenario(name):
         fake.fake_reset()
         m.cd_step(data(100, 784), Machine.hparams(lr=1e-3, k=1, update_mask=L.UPDATE_C | L.UPDATE_B))
         out["no_w"] = snapshot()
+    elif name == "momentum":  # checkpoint state in and out of the ABI: momentum buffers (padded rows), draw counters
+        ctx = Context(device=0, seed=1)
+        m = machine(ctx, 333, 130)                              # ldH = 192: the copies are pitched
+        out["absent"] = m.get_momentum() is None
+        rng = np.random.default_rng(4)
+        mW, mb, mc = (rng.normal(0, 1, sh).astype(np.float32) for sh in ((333, 130), (333,), (130,)))
+        m.set_momentum(mW, mb, mc)
+        got = m.get_momentum()
+        out["round_trip"] = bool(got is not None and all(np.array_equal(a, b) for a, b in zip(got, (mW, mb, mc))))
+        m.cd_step(data(200, 333), Machine.hparams(lr=1e-3, k=1, momentum=0.5))   # the buffers it finds are used, not replaced
+        out["used"] = m.get_momentum() is not None
+        m2 = machine(ctx, 333, 130)
+        m2.cd_step(data(200, 333), Machine.hparams(lr=1e-3, k=1, momentum=0.5))
+        out["created_by_step"] = m2.get_momentum() is not None
+        m.set_draw_counters(7, 9)
+        out["draws"] = m.draw_counters()
+        m.set_seed(3, 5)
+        out["draws_after_set_seed"] = m.draw_counters()
+        try:
+            m.set_momentum(mW[:, :100], mb, mc)
+            out["bad_shape"] = "accepted"
+        except ValueError as e:
+            out["bad_shape"] = str(e)
+        out["snapshot"] = snapshot()
     elif name == "delta_rule":
         ctx = Context(device=0, seed=1)
         for compute in (L.COMPUTE_BF16, L.COMPUTE_F32X3):

@@ -228,6 +228,37 @@ def test_checkpoint_resume_is_exact(ctx, tmp_path):
     assert np.array_equal(a._machine.get_chains(128), b._machine.get_chains(128))
 
 
+def test_checkpoint_resume_with_momentum_and_score_streams_is_exact(ctx, tmp_path):
+    """A checkpoint also carries the momentum buffers and the positions of the inference / score streams (round-1 ADVICE):
+    a fit with momentum resumed from a checkpoint equals the uninterrupted one bit for bit, the epoch score it prints
+    (its own Philox stream) included, and so does the next transform."""
+    from keras_unsupervised_b200.ebm import RBM, MODE_VISIBLE_BERNOULLI
+
+    rng = np.random.default_rng(8)
+    V = _structured(rng, 900, 160)
+    for dtype in ("bf16", "float32"):
+        hps = {"batch_size": 128, "epochs": 2, "lr": 1e-3, "dtype": dtype, "momentum": 0.7, "weight_decay": 1e-4,
+               "seed": 6, "stream": False}
+        a = RBM(dict(hps), 64, name="a", mode=MODE_VISIBLE_BERNOULLI, context=ctx)
+        assert a.built is False or a._machine.get_momentum() is None
+        a.fit(V, verbose=1)                       # verbose: the epoch score advances the score stream
+        a.transform(V[:64])                       # ... and this the inference stream
+        a.save(tmp_path / ("m_%s.npz" % dtype))
+        z = np.load(tmp_path / ("m_%s.npz" % dtype))
+        assert {"momentum_weight", "momentum_visible_bias", "momentum_hidden_bias", "infer_draws", "score_draws"} <= set(z.files)
+        assert int(z["infer_draws"]) == 1 and int(z["score_draws"]) == 2 and np.abs(z["momentum_weight"]).max() > 0
+        a.fit(V, verbose=1)
+        ha = a.transform(V[:64])[0]
+        b = RBM(dict(hps), 64, name="b", mode=MODE_VISIBLE_BERNOULLI, context=ctx).load(tmp_path / ("m_%s.npz" % dtype))
+        b.fit(V, verbose=1)
+        hb = b.transform(V[:64])[0]
+        assert np.array_equal(a.rbm_weight, b.rbm_weight) and np.array_equal(a.hidden_bias, b.hidden_bias)
+        assert np.array_equal(a.visible_bias, b.visible_bias) and np.array_equal(ha, hb)
+        assert [h["last_score"] for h in a.history[2:]] == [h["last_score"] for h in b.history]
+        for x, y in zip(a._machine.get_momentum(), b._machine.get_momentum()):
+            assert np.array_equal(x, y)
+
+
 def test_gaussian_visible_rbm_runs_the_default_mode(ctx):
     """MODE_VISIBLE_GAUSSIAN is the constructor default (rbm.py:22) and what examples/rbm uses: relu-threshold
     hiddens, unit-variance Gaussian reconstructions drawn from the engine's Philox stream (Box-Muller)."""

@@ -178,6 +178,17 @@ def test_two_rank_exchange_variants(dry_build, env, dw, exchange, update):
         assert d["timings"][0]["fused_reduce_steps"] == 4 and d["timings"][0]["allreduce_calls"] == 0
 
 
+def test_checkpoint_state_through_the_abi(dry_build):
+    """kucd_rbm_get/set_momentum (pitched copies of the padded fp32 buffers; None until a momentum step or a set has created
+    them), kucd_rbm_get/set_draw_counters (reset by set_seed), shape errors as ValueError - the fake runtime really copies."""
+    d = run("momentum")
+    assert d["absent"] is True and d["round_trip"] is True and d["used"] is True and d["created_by_step"] is True
+    assert d["draws"] == {"infer_draws": 7, "score_draws": 9}
+    assert d["draws_after_set_seed"] == {"infer_draws": 0, "score_draws": 0}
+    assert "momentum of rbm_weight has shape (333, 100), expected (333, 130)" in d["bad_shape"]
+    clean(d["snapshot"])
+
+
 def test_which_exchange_the_default_rule_picks(dry_build):
     """choose_exchange without overrides, a small weight matrix (784 x 500): shards of <= 256 rows keep the all-reduce (their
     step is one small-tile chain launch with dW inside), shards of 257 ... 2047 rows take the fused exchange (measured at C3
