@@ -373,4 +373,24 @@ __global__ void __launch_bounds__(kNumThreads, 1) chain_kernel(const __grid_cons
   }
 }
 
+// The host side launches a chain kernel through its address (cudaLaunchKernelExC), so that the instantiations can live
+// in a translation unit of their own (csrc/inst_chain.cu, KUCD_SPLIT_BUILD).
+template <int BN, int CG, bool GAUSS, int CH>
+const void* chain_kernel_ptr() {
+  return reinterpret_cast<const void*>(&chain_kernel<BN, CG, GAUSS, CH>);
+}
+
+#ifndef KUCD_PRECISE_CH
+#define KUCD_PRECISE_CH 8  // launch.cuh: k-blocks per accumulation piece of the float32-grade mode
+#endif
+// every variant launch_chain (kucd.cu) uses
+#define KUCD_CHAIN_VARIANTS(X)                                                                               \
+  X(256, 2, false, 0) X(256, 2, true, 0) X(64, 1, false, 0) X(64, 1, true, 0) X(256, 1, false, 0) X(128, 1, false, 0) \
+  X(256, 2, false, KUCD_PRECISE_CH) X(64, 1, false, KUCD_PRECISE_CH)
+#ifdef KUCD_SPLIT_BUILD
+#define KUCD_EXTERN_CHAIN(BN, CG, G, CH) extern template const void* chain_kernel_ptr<BN, CG, G, CH>();
+KUCD_CHAIN_VARIANTS(KUCD_EXTERN_CHAIN)
+#undef KUCD_EXTERN_CHAIN
+#endif
+
 }  // namespace kucd

@@ -1173,7 +1173,8 @@ static int gather_master(kucd_rbm* r) {
 template <int BN, int CG, bool GAUSS, int CH = 0>
 static int launch_chain_kernel(kucd_ctx* ctx, const ChainParams& p, int total, bool prof, size_t* pe0) {
   using Cfg = GemmCfg<BN / CG>;
-  auto kern = chain_kernel<BN, CG, GAUSS, CH>;
+  const void* kern = chain_kernel_ptr<BN, CG, GAUSS, CH>();
+  void* args[] = {const_cast<ChainParams*>(&p)};  // one __grid_constant__ parameter block
   const int dev = current_device_slot();
   // per device: 0 = not prepared, 1 = plain launches, 2 = cooperative launches
   static int state[kMaxDevices] = {};
@@ -1220,7 +1221,8 @@ static int launch_chain_kernel(kucd_ctx* ctx, const ChainParams& p, int total, b
       cfg.numAttrs = na + 1;
       cfg.gridDim = dim3(CG);
       cfg.stream = ctx->copy_stream;
-      if (cudaLaunchKernelEx(&cfg, kern, empty) == cudaSuccess && cudaStreamSynchronize(ctx->copy_stream) == cudaSuccess)
+      void* empty_args[] = {&empty};
+      if (cudaLaunchKernelExC(&cfg, kern, empty_args) == cudaSuccess && cudaStreamSynchronize(ctx->copy_stream) == cudaSuccess)
         state[dev] = 2;
       cudaGetLastError();
     }
@@ -1236,14 +1238,14 @@ static int launch_chain_kernel(kucd_ctx* ctx, const ChainParams& p, int total, b
   cfg.gridDim = dim3(units * CG);
   cfg.stream = ctx->stream;
   *pe0 = prof ? prof_event(ctx) : 0;
-  cudaError_t le = cudaLaunchKernelEx(&cfg, kern, p);
+  cudaError_t le = cudaLaunchKernelExC(&cfg, kern, args);
   if (le != cudaSuccess && state[dev] == 2 && !capturing(ctx)) {
     // the cooperative form was refused for this launch (seen under ncu, which cannot replay it): plain launches from here
     // on - all CTAs still fit at once on an otherwise idle device, which is all the kernel needs
     cudaGetLastError();
     state[dev] = 1;
     cfg.numAttrs = na - 1;
-    le = cudaLaunchKernelEx(&cfg, kern, p);
+    le = cudaLaunchKernelExC(&cfg, kern, args);
   }
   if (le != cudaSuccess)
     return fail(KUCD_ERR_CUDA, "chain kernel launch failed: %s (%s:%d)", cudaGetErrorString(le), __FILE__, __LINE__);

@@ -193,9 +193,11 @@ inline cudaError_t launch_major(const GemmParams& p, bool a_mn, bool b_mn, int n
   return launch_if_built<BN, true, false, EPI, CH, CG>(p, num_sms, s);
 }
 
+// (not `inline`: the product library is built from several translation units in parallel, KUCD_SPLIT_BUILD below, and an
+// explicit instantiation declaration does not hold back an inline function)
 template <int EPI>
-inline cudaError_t launch_bn(const GemmParams& p, int bn, bool precise, int cg, bool a_mn, bool b_mn, int num_sms,
-                             cudaStream_t s) {
+cudaError_t launch_bn(const GemmParams& p, int bn, bool precise, int cg, bool a_mn, bool b_mn, int num_sms,
+                      cudaStream_t s) {
   if (precise && cg == 2) return launch_major<256, EPI, kPreciseCH, 2>(p, a_mn, b_mn, num_sms, s);
   if (precise) return launch_major<kPreciseBN, EPI, kPreciseCH>(p, a_mn, b_mn, num_sms, s);
   if (cg == 2) return launch_major<256, EPI, 0, 2>(p, a_mn, b_mn, num_sms, s);
@@ -205,6 +207,21 @@ inline cudaError_t launch_bn(const GemmParams& p, int bn, bool precise, int cg, 
     default: return launch_major<64, EPI, 0>(p, a_mn, b_mn, num_sms, s);
   }
 }
+
+#ifdef KUCD_SPLIT_BUILD
+// libkucd.so is compiled as several translation units side by side (_lib.py: build): csrc/inst_*.cu hold the explicit
+// instantiations of the contraction kernels per epilogue, kucd.cu only refers to them.  Same kernels, same SASS as the
+// single-unit build (the dry-run build and the probe still compile everything in one unit).
+#define KUCD_EXTERN_BN(E) \
+  extern template cudaError_t launch_bn<E>(const GemmParams&, int, bool, int, bool, bool, int, cudaStream_t);
+KUCD_EXTERN_BN(kEpiRaw)
+KUCD_EXTERN_BN(kEpiSample)
+KUCD_EXTERN_BN(kEpiProb)
+KUCD_EXTERN_BN(kEpiFreeEnergy)
+KUCD_EXTERN_BN(kEpiReluSample)
+KUCD_EXTERN_BN(kEpiGaussian)
+#undef KUCD_EXTERN_BN
+#endif
 
 // Fill the tensor maps / shape fields of `p` from `ops` (epilogue fields are the caller's) and launch.
 // cta_group::2 (256 x 256 tiles on CTA pairs) once the problem fills the chip with such tiles
@@ -218,6 +235,7 @@ inline int pick_cg(int64_t M, int64_t N, int num_sms) {
   return tiles >= num_sms / 2 ? 2 : 1;
 }
 
+#ifndef KUCD_INST_UNIT  // (an instantiation unit has no use for the dispatcher - and must not instantiate the bf16-push kernels it names)
 inline bool launch_gemm(GemmParams& p, const GemmOperands& ops, int epi, int num_sms, cudaStream_t stream,
                         std::string* err, int force_bn = 0, bool precise = false, int force_cg = 0) {
   if (ops.num_seg < 1 || ops.num_seg > kMaxSeg) {
@@ -265,5 +283,7 @@ inline bool launch_gemm(GemmParams& p, const GemmOperands& ops, int epi, int num
   }
   return true;
 }
+
+#endif  // KUCD_INST_UNIT
 
 }  // namespace kucd

@@ -4,6 +4,7 @@
 // every wrapper is the exact form one of the kernels in gemm.cuh needs.
 #pragma once
 #include <cstdint>
+#include <cstdio>
 #include <cuda.h>
 
 namespace kucd {
