@@ -595,41 +595,56 @@ __global__ void recon_kernel(const __nv_bfloat16* __restrict__ a_hi, const __nv_
   if ((threadIdx.x & 31) == 0 && s != 0.f) atomicAdd(acc, s);
 }
 
-// Latency-bound minibatches: the whole reconstruction statistic in ONE launch of one block - the squared differences,
-// the mean into stats[1] and, for a streamed fit under graph replay, the write into the caller-visible page-locked log
-// (log_stat_kernel's job) - instead of memset + recon + finish + log.  Single 0/1 planes only.
-__global__ void __launch_bounds__(1024) recon_small_kernel(const __nv_bfloat16* __restrict__ a, int64_t a_ld,
-                                                           const __nv_bfloat16* __restrict__ b, int64_t b_ld, int32_t rows,
-                                                           int32_t cols, const StepDyn* a_dyn, float* __restrict__ stats,
-                                                           const StepDyn* log_dyn, int32_t log_batch, float* host_log) {
-  __shared__ float part[32];
+// Latency-bound minibatches: the whole reconstruction statistic in ONE launch - the squared differences, the mean into
+// stats[1] and, for a streamed fit under graph replay, the write into the caller-visible page-locked log (log_stat_kernel's
+// job) - instead of memset + recon + finish + log.  Single planes only.  Up to kReconBlocks blocks take the rows round-robin
+// (16-byte loads: eight units each; columns beyond `cols` are zero in both planes up to the next multiple of eight), leave
+// their partial sums in `part` and draw a ticket; the block that draws the last one adds the partials IN INDEX ORDER (the
+// statistic is the same in every run), writes the results and puts the ticket back to zero for the next launch.  As one
+// block of 1024 threads walking bf16 pairs with a 64-bit division each, this took about as long as a fifth of a C1 step.
+constexpr int kReconBlocks = 64;
+__global__ void __launch_bounds__(128) recon_small_kernel(const __nv_bfloat16* __restrict__ a, int64_t a_ld,
+                                                          const __nv_bfloat16* __restrict__ b, int64_t b_ld, int32_t rows,
+                                                          int32_t cols, const StepDyn* a_dyn, float* __restrict__ stats,
+                                                          const StepDyn* log_dyn, int32_t log_batch, float* host_log,
+                                                          float* __restrict__ part, unsigned int* __restrict__ ticket) {
+  __shared__ float warp_sum[4];
   int64_t a_row_off = 0;
   if (a_dyn != nullptr) {
     a_row_off = a_dyn->row_off;
     rows = a_dyn->rows_valid < rows ? a_dyn->rows_valid : rows;
   }
-  const int pairs = (cols + 1) / 2;  // columns are read in bf16 pairs (ld is a multiple of 64: in bounds; pads are zero)
-  const int64_t total = static_cast<int64_t>(rows) * pairs;
+  const int nvec = (cols + 7) / 8;
   float s = 0.f;
-  for (int64_t i = threadIdx.x; i < total; i += blockDim.x) {
-    const int64_t r = i / pairs, c = 2 * (i - r * pairs);
-    const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(a + (a_row_off + r) * a_ld + c));
-    const float2 y = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(b + r * b_ld + c));
-    s += (x.x - y.x) * (x.x - y.x);
-    if (c + 1 < cols) s += (x.y - y.y) * (x.y - y.y);
+  for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+    const uint4* pa = reinterpret_cast<const uint4*>(a + (a_row_off + r) * a_ld);
+    const uint4* pb = reinterpret_cast<const uint4*>(b + static_cast<int64_t>(r) * b_ld);
+    for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
+      const uint4 x = pa[v], y = pb[v];
+      const uint32_t xs[4] = {x.x, x.y, x.z, x.w}, ys[4] = {y.x, y.y, y.z, y.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {  // a bf16 is the upper half of the float with the same value
+        const float d0 = __uint_as_float(xs[q] << 16) - __uint_as_float(ys[q] << 16);
+        const float d1 = __uint_as_float(xs[q] & 0xFFFF0000u) - __uint_as_float(ys[q] & 0xFFFF0000u);
+        s += d0 * d0 + d1 * d1;
+      }
+    }
   }
 #pragma unroll
   for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+  if ((threadIdx.x & 31) == 0) warp_sum[threadIdx.x >> 5] = s;
   __syncthreads();
-  if (threadIdx.x < 32) {
-    s = threadIdx.x < (blockDim.x >> 5) ? part[threadIdx.x] : 0.f;
-#pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (threadIdx.x == 0) {
-      const float v = rows > 0 ? s / (static_cast<float>(rows) * cols) : 0.f;
+  if (threadIdx.x == 0) {
+    part[blockIdx.x] = (warp_sum[0] + warp_sum[1]) + (warp_sum[2] + warp_sum[3]);
+    __threadfence();
+    if (atomicAdd(ticket, 1u) == gridDim.x - 1) {
+      __threadfence();
+      float t = 0.f;
+      for (unsigned int i = 0; i < gridDim.x; ++i) t += __ldcg(part + i);
+      const float v = rows > 0 ? t / (static_cast<float>(rows) * cols) : 0.f;
       stats[1] = v;
       if (host_log != nullptr) host_log[log_dyn->pad + log_dyn->row_off / log_batch] = v;
+      *ticket = 0u;
     }
   }
 }

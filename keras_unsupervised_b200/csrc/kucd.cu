@@ -1911,10 +1911,12 @@ static int enqueue_recon(kucd_rbm* r, const Planes& v0, int64_t rows, const Step
              .view(rows, r->V, 1);
     vk.p[0] += static_cast<int64_t>(ctx->rank) * (r->last_rows / ctx->world) * vk.ld;
   }
-  if (rows * r->V <= (1 << 18) && v0.n == 1 && vk.n == 1) {  // latency-bound: one launch of one block
-    recon_small_kernel<<<1, 1024, 0, ctx->stream>>>(v0.p[0], v0.ld, vk.p[0], vk.ld, static_cast<int32_t>(rows),
-                                                    static_cast<int32_t>(r->V), v0_dyn, r->stats.as<float>(), log_dyn,
-                                                    log_batch, host_log);
+  if (rows * r->V <= (1 << 18) && v0.n == 1 && vk.n == 1) {  // latency-bound: one launch, a few small blocks
+    const int blocks = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(rows, kReconBlocks)));
+    recon_small_kernel<<<blocks, 128, 0, ctx->stream>>>(v0.p[0], v0.ld, vk.p[0], vk.ld, static_cast<int32_t>(rows),
+                                                        static_cast<int32_t>(r->V), v0_dyn, r->stats.as<float>(), log_dyn,
+                                                        log_batch, host_log, r->stats.as<float>() + 16,
+                                                        r->stats.as<unsigned int>() + 15);
     ctx->tm.aux_launches++;
     CU_TRY(cudaGetLastError());
     return KUCD_OK;
@@ -2248,7 +2250,7 @@ int kucd_rbm_create(kucd_ctx* ctx, int64_t V, int64_t H, int mode, int compute, 
   T(r->b32.ensure(r->ldVb() * 4, true));
   T(r->c32.ensure(r->ldHb() * 4, true));
   T(r->grad.ensure(r->grad_elems() * 4, true));
-  T(r->stats.ensure(64, true));
+  T(r->stats.ensure(64 + 4 * kReconBlocks, true));  // [0..8] statistics and accumulators, [15] recon ticket, [16..] recon partials
   T(r->flag.ensure(16, true));
   T(r->dyn.ensure(sizeof(StepDyn), true));
   if (rc != KUCD_OK) {
