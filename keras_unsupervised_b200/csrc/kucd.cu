@@ -1039,8 +1039,11 @@ static void choose_exchange(kucd_rbm* r, int64_t rows_per_rank, const kucd_hpara
   // though the contraction is short, and an all-reduce of the same matrix is all latency and exposure.  Measured at C3
   // (64 MiB of fp32 dW) with 512 rows per rank on 8 GPUs, same pod: 0.833 ms per step fused (dW with its pushes 0.109 ms)
   // against 1.002 ms with ncclAllReduce (profiles/r02_call12_n8_c3_strong_fused.json, r02_call11_n8_c3_strong.json).
-  // Minibatches of <= 256 rows keep NCCL: their whole step is one small-tile chain launch with dW as its last stage.
-  if (!r->fused_now && r->peer_on && min_rows_env < 0 && rows_per_rank > 256 &&
+  // Only where the shard's projections run as a mid chain (enqueue_cd: > 256 rows, >= 32 tiles of 128 x 256 per stage):
+  // smaller problems keep NCCL, because their whole step is one small-tile chain launch with dW as its last stage, which
+  // cannot push rows to peers.
+  const int64_t mid_tiles = ((rows_per_rank + kBlockM - 1) / kBlockM) * ((std::min(r->V, r->H) + 255) / 256);
+  if (!r->fused_now && r->peer_on && min_rows_env < 0 && rows_per_rank > 256 && mid_tiles >= 32 &&
       static_cast<int64_t>(r->V) * r->ldH * 4 <= (int64_t{128} << 20))
     r->fused_now = true;
   r->units_now = false;

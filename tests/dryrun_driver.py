@@ -436,7 +436,7 @@ def scenario(name):
         for r, c in enumerate(ctxs):
             L.check(c.lib.kucd_ctx_comm_init(c.handle, bytes(uid), r, 2))
             c.rank, c.world = r, 2
-        V, H = 784, 500
+        V, H = int(os.environ.get("DRY_V", "784")), int(os.environ.get("DRY_H", "500"))
         ms = []
         for c in ctxs:
             m = Machine.__new__(Machine)

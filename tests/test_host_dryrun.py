@@ -190,13 +190,18 @@ def test_checkpoint_state_through_the_abi(dry_build):
 
 
 def test_which_exchange_the_default_rule_picks(dry_build):
-    """choose_exchange without overrides, a small weight matrix (784 x 500): shards of <= 256 rows keep the all-reduce (their
-    step is one small-tile chain launch with dW inside), shards of 257 ... 2047 rows take the fused exchange (measured at C3
-    strong-scaled over 8 GPUs: 0.833 vs 1.002 ms per step)."""
-    for rows, fused in ((64, False), (256, False), (512, True), (1024, True)):
-        t = clean(run("two_ranks", DRY_ROWS=rows))["timings"][0]
-        assert t["graph_launches"] == 4
-        assert (t["fused_reduce_steps"], t["allreduce_calls"]) == ((4, 0) if fused else (0, 4)), (rows, t)
+    """choose_exchange without size overrides.  Between the two data-parallel exchanges (KUCD_EXCHANGE=dp), C3's weight matrix
+    (4096 x 4096): shards of <= 256 rows keep the all-reduce, shards of 257 ... 2047 rows take the fused exchange (their
+    projections run as a mid chain; measured at C3 strong-scaled over 8 GPUs: 0.833 vs 1.002 ms per step), as do shards of
+    >= 2048 rows.  A small model (784 x 500) keeps the all-reduce below 2048 rows: its step is one small-tile chain launch with
+    dW inside.  With nothing forced, a CD-1 step on the large matrix goes unit-sharded (4 bit exchanges against 64 MiB of dW)."""
+    for V, H, rows, fused in ((4096, 4096, 256, False), (4096, 4096, 512, True), (4096, 4096, 1024, True),
+                              (784, 500, 64, False), (784, 500, 512, False), (784, 500, 1024, False), (784, 500, 2048, True)):
+        t = clean(run("two_ranks", DRY_ROWS=rows, DRY_V=V, DRY_H=H, KUCD_EXCHANGE="dp"))["timings"][0]
+        assert t["graph_launches"] == 4 and t["unit_steps"] == 0
+        assert (t["fused_reduce_steps"], t["allreduce_calls"]) == ((4, 0) if fused else (0, 4)), (V, H, rows, t)
+    t = clean(run("two_ranks", DRY_ROWS=512, DRY_V=4096, DRY_H=4096))["timings"][0]
+    assert (t["unit_steps"], t["fused_reduce_steps"], t["allreduce_calls"]) == (4, 0, 0)
 
 
 @pytest.mark.parametrize("ranks", [2, 4, 8])
