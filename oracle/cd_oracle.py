@@ -61,6 +61,16 @@ def split3(x):
     return hi, mid, lo
 
 
+def stat_grid_round(s, bound: int) -> np.ndarray:
+    """The engine's rounding of a partial column sum before its fp32 atomicAdd (csrc/rng_math.cuh: stat_grid_round): to the
+    grid 2^(ceil(log2 bound) - 24), the fp32 spacing just below `bound`.  Every sum of grid values whose magnitude stays
+    within `bound` is exact in fp32, so such additions commute (tests/test_oracle.py).  The oracle's own statistics are exact
+    sums; this restatement exists to check that claim and the size of the rounding."""
+    e = int(np.ceil(np.log2(max(int(bound), 2))))
+    g = np.float32(2.0 ** (e - 24))
+    return (np.rint(np.asarray(s, np.float32) / g) * g).astype(np.float32)
+
+
 def lattice_uniform(rng: np.random.Generator, shape) -> np.ndarray:
     """float32 uniforms on the 2^-23 lattice in [0,1): the values tf.random.uniform can produce."""
     return (rng.integers(0, 1 << 23, size=shape, dtype=np.uint32).astype(np.float32) * F32(2.0 ** -23)).astype(F32)

@@ -194,3 +194,33 @@ def test_wire_shards_model_of_bf16_partial_sums():
     assert np.abs(red["dW"] - plain["dW"]).max() <= 2 * n * rb * 2.0 ** -8
     with pytest.raises(ValueError):
         O.OracleRBM(W, b, c).cd_stats(x[:30], [u_h[:30]], [None, u_v[:30]], wire_shards=4)
+
+
+def test_grid_rounded_partial_sums_add_exactly_in_any_order():
+    """What makes the engine's column statistics order-independent (csrc/rng_math.cuh: stat_grid_round, restated in the
+    oracle): partial sums of probabilities (32 rows each) rounded to the grid of the minibatch size, plus integer counts, add
+    up to the same fp32 value in every order - while the unrounded partials do not - and the rounding costs less than the
+    fp32 spacing at the size of the sums."""
+    rng = np.random.default_rng(0)
+    for rows in (16, 104, 128, 300, 4096, 32768):
+        groups = (rows + 31) // 32
+        p = rng.random((groups, 32)).astype(np.float32)
+        p.reshape(-1)[rows:] = 0                                  # rows beyond the minibatch contribute nothing
+        partial = p.sum(axis=1, dtype=np.float32)                 # one warp's sum
+        valid = np.minimum(32, rows - 32 * np.arange(groups))     # rows of each 32-row group that exist
+        counts = rng.integers(0, valid + 1).astype(np.float32)    # the positive phase: 0/1 states, integer sums
+        grid = O.stat_grid_round(-partial, rows)
+        assert np.abs(grid + partial).max() <= 2.0 ** (int(np.ceil(np.log2(max(rows, 2)))) - 25) + 1e-12
+        seen_grid, seen_raw = set(), set()
+        for _ in range(50):
+            order = rng.permutation(2 * groups)
+            for terms, seen in ((np.concatenate([counts, grid]), seen_grid), (np.concatenate([counts, -partial]), seen_raw)):
+                acc = np.float32(0)
+                for i in order:
+                    acc = np.float32(acc + terms[i])
+                seen.add(float(acc))
+        assert len(seen_grid) == 1, (rows, seen_grid)
+        exact = float(np.sum(counts.astype(np.float64)) + np.sum(grid.astype(np.float64)))
+        assert seen_grid == {exact}                               # ... and that value is the exact sum of the rounded terms
+        if rows >= 300:
+            assert len(seen_raw) > 1                              # the unrounded partials do depend on the order
